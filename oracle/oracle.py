@@ -1,0 +1,125 @@
+"""ctypes front-end of the CPU restatement (``oracle/vcfx_oracle.c``) and helpers to run the
+compiled reference tools (``oracle/_ref/VCFX_*``).
+
+TEST INFRASTRUCTURE ONLY.  Importable from ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` — never from ``vcfx_b200``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+REF_DIR = HERE / "_ref"
+LIB_PATH = REF_DIR / "liboracle.so"
+
+FILE, STDIN = 0, 1
+AC_MT_TEXT, AC_STREAM, AC_UNIFIED = 0, 1, 2
+AC_TEXT, AC_AGGREGATE, AC_BINARY = 0, 1, 2
+
+
+class _Result(C.Structure):
+    _fields_ = [("out", C.c_void_p), ("out_len", C.c_size_t), ("rc", C.c_int),
+                ("data_lines", C.c_longlong), ("rows", C.c_longlong), ("flagged", C.c_longlong),
+                ("warnings", C.c_longlong), ("first_bad_line", C.c_longlong)]
+
+
+class Result:
+    def __init__(self, r: _Result):
+        self.out = C.string_at(r.out, r.out_len) if r.out else b""
+        self.rc = r.rc
+        self.data_lines = r.data_lines
+        self.rows = r.rows
+        self.flagged = r.flagged
+        self.warnings = r.warnings
+        self.first_bad_line = r.first_bad_line
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            subprocess.run(["make", "-C", str(HERE), "all"], check=True, capture_output=True)
+        l = C.CDLL(str(LIB_PATH))
+        P = C.POINTER(_Result)
+        for name in ("oracle_allele_freq", "oracle_hwe", "oracle_missing"):
+            getattr(l, name).argtypes = [C.c_char_p, C.c_size_t, C.c_int, P]
+        l.oracle_variant_count.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, P]
+        l.oracle_allele_counter.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_char_p, P]
+        l.oracle_free.argtypes = [P]
+        for name in ("oracle_fmt_af_file", "oracle_fmt_af_stdin", "oracle_fmt_p_file", "oracle_fmt_p_stdin"):
+            getattr(l, name).argtypes = [C.c_double, C.c_char_p]
+            getattr(l, name).restype = C.c_int
+        l.oracle_hwe_pvalue.argtypes = [C.c_int, C.c_int, C.c_int]
+        l.oracle_hwe_pvalue.restype = C.c_double
+        l.oracle_hwe_class.argtypes = [C.c_char_p, C.c_size_t]
+        l.oracle_gt_index.argtypes = [C.c_char_p, C.c_size_t]
+        l.oracle_af_counts.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        l.oracle_ac_counts.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        _lib = l
+    return _lib
+
+
+def _call(fn, *args) -> Result:
+    r = _Result()
+    fn(*args, C.byref(r))
+    res = Result(r)
+    lib().oracle_free(C.byref(r))
+    return res
+
+
+def allele_freq(data: bytes, mode: int = FILE) -> Result:
+    return _call(lib().oracle_allele_freq, data, len(data), mode)
+
+
+def hwe(data: bytes, mode: int = FILE) -> Result:
+    return _call(lib().oracle_hwe, data, len(data), mode)
+
+
+def missing(data: bytes, mode: int = FILE) -> Result:
+    return _call(lib().oracle_missing, data, len(data), mode)
+
+
+def variant_count(data: bytes, mode: int = FILE, strict: bool = False) -> Result:
+    return _call(lib().oracle_variant_count, data, len(data), mode, int(strict))
+
+
+def allele_counter(data: bytes, path: int = AC_MT_TEXT, fmt: int = AC_TEXT, limit: int = 0,
+                   samples: str | None = None) -> Result:
+    s = samples.encode() if samples else None
+    return _call(lib().oracle_allele_counter, data, len(data), path, fmt, limit, s)
+
+
+def fmt(kind: str, v: float) -> bytes:
+    buf = C.create_string_buffer(512)
+    n = getattr(lib(), f"oracle_fmt_{kind}")(v, buf)
+    return buf.raw[:n]
+
+
+def hwe_pvalue(hr: int, het: int, ha: int) -> float:
+    return lib().oracle_hwe_pvalue(hr, het, ha)
+
+
+# ---------------------------------------------------------------- compiled reference tools
+def ref_tool(name: str) -> Path | None:
+    p = REF_DIR / f"VCFX_{name}"
+    return p if p.exists() else None
+
+
+def have_reference() -> bool:
+    return all(ref_tool(t) for t in ("allele_freq_calc", "allele_counter", "missing_detector",
+                                     "variant_counter", "hwe_tester"))
+
+
+def run_ref(name: str, args: list[str], stdin: bytes | None = None, timeout: float = 20):
+    """Run oracle/_ref/VCFX_<name>; returns (rc, stdout, stderr)."""
+    exe = ref_tool(name)
+    if exe is None:
+        raise FileNotFoundError(f"oracle/_ref/VCFX_{name} not built (make -C oracle ref)")
+    r = subprocess.run([str(exe), *args], input=stdin if stdin is not None else b"",
+                       capture_output=True, timeout=timeout)
+    return r.returncode, r.stdout, r.stderr

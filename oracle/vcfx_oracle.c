@@ -1,0 +1,823 @@
+/*
+ * vcfx_oracle.c — CPU restatement of the VCFX hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Not shipped, not linked into libvcfx_cuda, never used as a fallback: it exists so the
+ * parity tests can compare the CUDA path against the reference's semantics on any input,
+ * including on the GPU box where /root/reference is absent.  It is pinned against the
+ * compiled reference tools (oracle/_ref/VCFX_*) by tests/test_oracle_vs_reference.py and
+ * against tests/golden/.
+ *
+ * Written from the behaviour of the reference (file:line cited per rule), organised
+ * differently: one generic line walker + a per-line tab table, then one routine per tool
+ * and input mode.  Build with -ffp-contract=off: the reference's x86 build has no FMA.
+ */
+#define _GNU_SOURCE
+#include "vcfx_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ output buffer */
+typedef struct { char *p; size_t n, cap; } obuf;
+
+static void ob_need(obuf *o, size_t extra) {
+    if (o->n + extra <= o->cap) return;
+    size_t c = o->cap ? o->cap : 4096;
+    while (c < o->n + extra) c *= 2;
+    o->p = (char *)realloc(o->p, c);
+    o->cap = c;
+}
+static void ob_put(obuf *o, const char *s, size_t n) {
+    ob_need(o, n); memcpy(o->p + o->n, s, n); o->n += n;
+}
+static void ob_str(obuf *o, const char *s) { ob_put(o, s, strlen(s)); }
+static void ob_ch(obuf *o, char c) { ob_need(o, 1); o->p[o->n++] = c; }
+
+static void res_init(oracle_result *r) { memset(r, 0, sizeof *r); }
+static void res_take(oracle_result *r, obuf *o) {
+    r->out = o->p ? o->p : (char *)calloc(1, 1); r->out_len = o->n;
+}
+void oracle_free(oracle_result *r) { if (r && r->out) { free(r->out); r->out = NULL; } }
+
+/* ------------------------------------------------------------------ line walking
+ * Both reader styles of the reference see the same line set: "while (p < end)" over an
+ * mmap and std::getline both yield one line per '\n' plus a final unterminated remainder
+ * when it is non-empty. */
+typedef struct { const char *s, *e; int terminated; } line_t;
+
+static int next_line(const char *buf, size_t n, size_t *pos, line_t *ln) {
+    if (*pos >= n) return 0;
+    const char *s = buf + *pos;
+    const char *nl = (const char *)memchr(s, '\n', n - *pos);
+    ln->s = s;
+    if (nl) { ln->e = nl; ln->terminated = 1; *pos = (size_t)(nl - buf) + 1; }
+    else    { ln->e = buf + n; ln->terminated = 0; *pos = n; }
+    return 1;
+}
+
+/* k-th tab-separated field of [s,e) in the mmap tools' sense: it exists only when its first
+ * byte lies before the line end (allele_freq_calc.cpp:247-256, hwe_tester.cpp:321-336),
+ * so a field that would start exactly at the line end is "absent". Returns 1 if present. */
+static int field_at(const char *s, const char *e, int k, const char **fs, const char **fe) {
+    const char *p = s;
+    for (int i = 0; i < k; ++i) {
+        const char *t = (const char *)memchr(p, '\t', (size_t)(e - p));
+        if (!t) { *fs = *fe = e; return 0; }
+        p = t + 1;
+    }
+    if (p >= e) { *fs = *fe = e; return 0; }
+    const char *t = (const char *)memchr(p, '\t', (size_t)(e - p));
+    *fs = p; *fe = t ? t : e;
+    return 1;
+}
+
+/* ------------------------------------------------------------------ allele_freq_calc */
+
+/* allele_freq_calc.cpp:298-316 — index of the ':'-separated FORMAT key equal to "GT". */
+int oracle_gt_index(const char *f, size_t n) {
+    int idx = 0; size_t i = 0;
+    while (i < n) {
+        size_t j = i;
+        while (j < n && f[j] != ':') ++j;
+        if (j - i == 2 && f[i] == 'G' && f[i + 1] == 'T') return idx;
+        ++idx;
+        i = (j < n) ? j + 1 : j;
+    }
+    return -1;
+}
+
+/* allele_freq_calc.cpp:262-293 — every '/'- or '|'-separated token that is non-empty, does
+ * not begin with '.', and is all digits counts once; it is ALT when any digit is not '0'. */
+void oracle_af_counts(const char *g, size_t n, int *alt, int *total) {
+    size_t i = 0;
+    while (i < n) {
+        while (i < n && (g[i] == '/' || g[i] == '|')) ++i;
+        if (i >= n) break;
+        size_t j = i;
+        while (j < n && g[j] != '/' && g[j] != '|') ++j;
+        if (g[i] != '.') {
+            int numeric = 1, zero = 1;
+            for (size_t k = i; k < j; ++k) {
+                if (g[k] < '0' || g[k] > '9') { numeric = 0; break; }
+                if (g[k] != '0') zero = 0;
+            }
+            if (numeric) { ++*total; if (!zero) ++*alt; }
+        }
+        i = j;
+    }
+}
+
+/* allele_freq_calc.cpp:321-337 + :438-441 — gt_index-th ':' piece of one sample column. */
+static void af_sample(const char *s, const char *e, int gt_index, int *alt, int *total) {
+    const char *p = s;
+    for (int i = 0; i < gt_index && p < e; ++i) {
+        while (p < e && *p != ':') ++p;
+        if (p < e) ++p;
+    }
+    if (p >= e) return;
+    const char *q = p;
+    while (q < e && *q != ':') ++q;
+    oracle_af_counts(p, (size_t)(q - p), alt, total);
+}
+
+/* allele_freq_calc.cpp:119-143 — FILE-mode text: trunc(v*10000+0.5), two roundings. */
+int oracle_fmt_af_file(double v, char *dst) {
+    char *d = dst;
+    if (v < 0) { *d++ = '-'; v = -v; }
+    double scaled_d = v * 10000.0;
+    scaled_d = scaled_d + 0.5;
+    unsigned long long sc = (unsigned long long)scaled_d;
+    d += sprintf(d, "%llu", sc / 10000ULL);
+    unsigned fr = (unsigned)(sc % 10000ULL);
+    *d++ = '.';
+    *d++ = (char)('0' + (fr / 1000) % 10);
+    *d++ = (char)('0' + (fr / 100) % 10);
+    *d++ = (char)('0' + (fr / 10) % 10);
+    *d++ = (char)('0' + fr % 10);
+    return (int)(d - dst);
+}
+/* allele_freq_calc.cpp:553-555 — STDIN-mode text: iostream fixed/setprecision(4). */
+int oracle_fmt_af_stdin(double v, char *dst) { return sprintf(dst, "%.4f", v); }
+
+static const char AF_HEADER[] = "CHROM\tPOS\tID\tREF\tALT\tAllele_Frequency\n";
+
+static int af_file(const char *in, size_t n, oracle_result *r) {
+    obuf o = {0}; size_t pos = 0; line_t ln; int seen_chrom = 0;
+    ob_str(&o, AF_HEADER);                                   /* :353 */
+    while (next_line(in, n, &pos, &ln)) {
+        const char *s = ln.s, *e = ln.e;
+        if (e > s && e[-1] == '\r') --e;                     /* :363-364 */
+        if (s == e) continue;                                /* :366 */
+        if (*s == '#') {                                     /* :372-380 */
+            if (e - s >= 6 && memcmp(s, "#CHROM", 6) == 0) seen_chrom = 1;
+            continue;
+        }
+        if (!seen_chrom) { r->warnings++; continue; }        /* :382-386 */
+        r->data_lines++;
+        const char *fs[9], *fe[9];
+        for (int k = 0; k < 5; ++k) field_at(s, e, k, &fs[k], &fe[k]);
+        field_at(s, e, 8, &fs[8], &fe[8]);
+        if (fs[8] == fe[8]) continue;                        /* :398 */
+        int gi = oracle_gt_index(fs[8], (size_t)(fe[8] - fs[8]));
+        if (gi < 0) continue;                                /* :413 */
+        int alt = 0, total = 0;
+        /* samples: everything after the 9th tab (:423-445) */
+        const char *p = s; int tabs = 0;
+        while (tabs < 9) {
+            const char *t = (const char *)memchr(p, '\t', (size_t)(e - p));
+            if (!t) { p = e; break; }
+            p = t + 1; ++tabs;
+        }
+        while (p < e) {
+            const char *t = (const char *)memchr(p, '\t', (size_t)(e - p));
+            const char *se = t ? t : e;
+            af_sample(p, se, gi, &alt, &total);
+            if (!t) break;
+            p = t + 1;
+        }
+        double f = total > 0 ? (double)alt / (double)total : 0.0;   /* :448-449 */
+        for (int k = 0; k < 5; ++k) { ob_put(&o, fs[k], (size_t)(fe[k] - fs[k])); ob_ch(&o, '\t'); }
+        char nb[40]; int l = oracle_fmt_af_file(f, nb);
+        ob_put(&o, nb, (size_t)l); ob_ch(&o, '\n');
+        r->rows++;
+    }
+    res_take(r, &o);
+    return 0;
+}
+
+static int af_stdin(const char *in, size_t n, oracle_result *r) {
+    obuf o = {0}; size_t pos = 0; line_t ln; int seen_chrom = 0;
+    if (n == 0) {                      /* :638-641 empty stdin prints help, rc 1 (help text not restated) */
+        r->rc = 1; res_take(r, &o); return 0;
+    }
+    ob_str(&o, AF_HEADER);                                   /* :487 */
+    while (next_line(in, n, &pos, &ln)) {
+        const char *s = ln.s, *e = ln.e;                     /* no '\r' handling in this mode */
+        if (s == e) continue;                                /* :490 */
+        if (*s == '#') {                                     /* :492-497 */
+            if (e - s >= 6 && memcmp(s, "#CHROM", 6) == 0) seen_chrom = 1;
+            continue;
+        }
+        if (!seen_chrom) { r->warnings++; continue; }        /* :499-502 */
+        /* split on tabs; nothing is pushed for an empty tail after a final tab (:509-518) */
+        const char *fs[16], *fe[16]; int nf = 0; size_t nfields = 0;
+        const char *p = s; const char *samples = e;
+        while (p < e) {
+            const char *t = (const char *)memchr(p, '\t', (size_t)(e - p));
+            const char *q = t ? t : e;
+            if (nf < 9) { fs[nf] = p; fe[nf] = q; ++nf; }
+            ++nfields;
+            if (nfields == 9) samples = t ? t + 1 : e;
+            if (!t) break;
+            p = t + 1;
+        }
+        if (nfields < 9) { r->warnings++; continue; }        /* :520-523 */
+        r->data_lines++;
+        int gi = oracle_gt_index(fs[8], (size_t)(fe[8] - fs[8]));
+        if (gi < 0) continue;                                /* :537 */
+        int alt = 0, total = 0;
+        p = samples;
+        while (p < e) {
+            const char *t = (const char *)memchr(p, '\t', (size_t)(e - p));
+            const char *se = t ? t : e;
+            af_sample(p, se, gi, &alt, &total);
+            if (!t) break;
+            p = t + 1;
+        }
+        double f = total > 0 ? (double)alt / (double)total : 0.0;
+        for (int k = 0; k < 5; ++k) { ob_put(&o, fs[k], (size_t)(fe[k] - fs[k])); ob_ch(&o, '\t'); }
+        char nb[64]; int l = oracle_fmt_af_stdin(f, nb);
+        ob_put(&o, nb, (size_t)l); ob_ch(&o, '\n');
+        r->rows++;
+    }
+    res_take(r, &o);
+    return 0;
+}
+
+int oracle_allele_freq(const char *in, size_t n, int mode, oracle_result *r) {
+    res_init(r);
+    return mode == ORACLE_FILE ? af_file(in, n, r) : af_stdin(in, n, r);
+}
+
+/* ------------------------------------------------------------------ hwe_tester */
+
+/* hwe_tester.cpp:339-378 — class of one sample column: 0 homRef, 1 het, 2 homAlt, -1 skip.
+ * Only the first ':' piece is read; anything after the second allele is ignored. */
+int oracle_hwe_class(const char *p, size_t n) {
+    const char *e = p + n;
+    if (p >= e) return -1;
+    const char *c = (const char *)memchr(p, ':', (size_t)(e - p));
+    if (c) e = c;
+    while (p < e && (*p == ' ' || *p == '\r')) ++p;
+    if (p >= e) return -1;
+    if (*p < '0' || *p > '9') return -1;                 /* covers '.' */
+    int a1 = 0;
+    while (p < e && *p >= '0' && *p <= '9') { a1 = a1 * 10 + (*p - '0'); ++p; }
+    if (p >= e || (*p != '/' && *p != '|')) return -1;
+    ++p;
+    if (p >= e || *p < '0' || *p > '9') return -1;
+    int a2 = 0;
+    while (p < e && *p >= '0' && *p <= '9') { a2 = a2 * 10 + (*p - '0'); ++p; }
+    if (a1 > 1 || a2 > 1) return -1;                     /* int overflow on absurd digit runs is UB upstream */
+    if (a1 == 0 && a2 == 0) return 0;
+    if (a1 == 1 && a2 == 1) return 2;
+    return 1;
+}
+
+/* hwe_tester.cpp:290-315 and :278-287 — Yates-corrected chi-square, 1-df p-value by the
+ * Abramowitz-Stegun 7.1.26 erfc polynomial.  Operation order is kept term by term. */
+double oracle_hwe_pvalue(int hr, int het, int ha) {
+    int N = hr + het + ha;
+    if (N < 1) return 1.0;
+    double p = (2.0 * hr + het) / (2.0 * N);
+    double q = 1.0 - p;
+    if (p <= 0.0 || p >= 1.0) return 1.0;
+    double ex[3]; double ob[3] = { (double)hr, (double)het, (double)ha };
+    ex[0] = N * p * p;
+    ex[1] = N * 2.0 * p * q;
+    ex[2] = N * q * q;
+    double chi2 = 0.0;
+    for (int i = 0; i < 3; ++i) {
+        double t = 0.0;
+        if (ex[i] > 0.0) {
+            double d = fabs(ob[i] - ex[i]) - 0.5;
+            if (d < 0.0) d = 0.0;
+            t = (d * d) / ex[i];
+        }
+        chi2 = (i == 0) ? t : chi2 + t;
+    }
+    if (chi2 <= 0.0) return 1.0;
+    if (chi2 > 700.0) return 0.0;
+    double x = sqrt(chi2 * 0.5);
+    double t = 1.0 / (1.0 + 0.3275911 * x);
+    double y = t * (0.254829592 + t * (-0.284496736 + t * (1.421413741 +
+               t * (-1.453152027 + t * 1.061405429))));
+    return y * exp(-x * x);
+}
+
+/* hwe_tester.cpp:236-268 — FILE-mode text: six truncated decimal digits. */
+int oracle_fmt_p_file(double v, char *dst) {
+    char *d = dst;
+    if (v < 0) { *d++ = '-'; v = -v; }
+    long long ip = (long long)v;
+    double fr = v - (double)ip;
+    d += sprintf(d, "%lld", ip);
+    *d++ = '.';
+    for (int i = 0; i < 6; ++i) {
+        fr = fr * 10.0;
+        int dg = (int)fr;
+        *d++ = (char)('0' + dg);
+        fr = fr - (double)dg;
+    }
+    return (int)(d - dst);
+}
+/* hwe_tester.cpp:605-606 — STDIN-mode text. */
+int oracle_fmt_p_stdin(double v, char *dst) { return sprintf(dst, "%.6f", v); }
+
+static const char HWE_HEADER[] = "CHROM\tPOS\tID\tREF\tALT\tHWE_pvalue\n";
+
+static int has_comma(const char *s, const char *e) { return memchr(s, ',', (size_t)(e - s)) != NULL; }
+
+static int hwe_file(const char *in, size_t n, oracle_result *r) {
+    obuf o = {0}; size_t pos = 0; line_t ln;
+    if (n == 0) { res_take(r, &o); return 0; }               /* :456 */
+    ob_str(&o, HWE_HEADER);                                  /* :463 */
+    while (next_line(in, n, &pos, &ln)) {
+        const char *s = ln.s, *e = ln.e;
+        if (e > s && e[-1] == '\r') --e;                     /* :480 */
+        if (s == e || *s == '#') continue;                   /* :482, :466-472 */
+        r->data_lines++;
+        const char *fs[9], *fe[9];
+        for (int k = 0; k < 5; ++k) field_at(s, e, k, &fs[k], &fe[k]);
+        if (fs[0] == fe[0] || fs[1] == fe[1] || fs[4] == fe[4]) continue;   /* :497 */
+        if (has_comma(fs[4], fe[4])) continue;               /* :503 */
+        field_at(s, e, 8, &fs[8], &fe[8]);
+        if (fe[8] - fs[8] < 2 || fs[8][0] != 'G' || fs[8][1] != 'T') continue;  /* :510 */
+        const char *sp, *dummy;
+        if (!field_at(s, e, 9, &sp, &dummy)) continue;       /* :516-520 */
+        int c[3] = {0, 0, 0};
+        while (sp < e) {                                     /* :526-536 */
+            const char *t = (const char *)memchr(sp, '\t', (size_t)(e - sp));
+            const char *se = t ? t : e;
+            int k = oracle_hwe_class(sp, (size_t)(se - sp));
+            if (k >= 0) c[k]++;
+            sp = se + 1;
+        }
+        double pv = oracle_hwe_pvalue(c[0], c[1], c[2]);
+        for (int k = 0; k < 5; ++k) { ob_put(&o, fs[k], (size_t)(fe[k] - fs[k])); ob_ch(&o, '\t'); }
+        char nb[64]; int l = oracle_fmt_p_file(pv, nb);
+        ob_put(&o, nb, (size_t)l); ob_ch(&o, '\n');
+        r->rows++;
+    }
+    res_take(r, &o);
+    return 0;
+}
+
+static int hwe_stdin(const char *in, size_t n, oracle_result *r) {
+    obuf o = {0}; size_t pos = 0; line_t ln;
+    ob_str(&o, HWE_HEADER);                                  /* :566, even for empty input */
+    while (next_line(in, n, &pos, &ln)) {
+        const char *s = ln.s, *e = ln.e;
+        if (s == e) continue;                                /* :573 */
+        if (e[-1] == '\r') --e;                              /* :574 */
+        if (s == e || *s == '#') continue;                   /* :575 */
+        r->data_lines++;
+        /* vcfx::split_tabs keeps empty fields, including a trailing one (vcfx_io.h:59-76) */
+        const char *fs[10], *fe[10]; size_t nfields = 0; const char *p = s;
+        for (;;) {
+            const char *t = (const char *)memchr(p, '\t', (size_t)(e - p));
+            const char *q = t ? t : e;
+            if (nfields < 10) { fs[nfields] = p; fe[nfields] = q; }
+            ++nfields;
+            if (!t) break;
+            p = t + 1;
+        }
+        if (nfields < 10) continue;                          /* :578 */
+        if (has_comma(fs[4], fe[4])) continue;               /* :586 */
+        if (fe[8] - fs[8] < 2 || fs[8][0] != 'G' || fs[8][1] != 'T') continue;  /* :590 */
+        int c[3] = {0, 0, 0};
+        const char *sp = fs[9];
+        for (;;) {                                           /* :595-601 every field incl. empty ones */
+            const char *t = (const char *)memchr(sp, '\t', (size_t)(e - sp));
+            const char *se = t ? t : e;
+            int k = oracle_hwe_class(sp, (size_t)(se - sp));
+            if (k >= 0) c[k]++;
+            if (!t) break;
+            sp = t + 1;
+        }
+        double pv = oracle_hwe_pvalue(c[0], c[1], c[2]);
+        for (int k = 0; k < 5; ++k) { ob_put(&o, fs[k], (size_t)(fe[k] - fs[k])); ob_ch(&o, '\t'); }
+        char nb[64]; int l = oracle_fmt_p_stdin(pv, nb);
+        ob_put(&o, nb, (size_t)l); ob_ch(&o, '\n');
+        r->rows++;
+    }
+    res_take(r, &o);
+    return 0;
+}
+
+int oracle_hwe(const char *in, size_t n, int mode, oracle_result *r) {
+    res_init(r);
+    return mode == ORACLE_FILE ? hwe_file(in, n, r) : hwe_stdin(in, n, r);
+}
+
+/* ------------------------------------------------------------------ missing_detector */
+
+/* pointer to the start of field k, or e when the line has fewer tabs
+ * (missing_detector.cpp:277-283 skipToField) */
+static const char *md_skip(const char *s, const char *e, int k) {
+    const char *p = s;
+    for (int i = 0; i < k && p < e; ++i) {
+        const char *t = (const char *)memchr(p, '\t', (size_t)(e - p));
+        p = t ? t + 1 : e;
+    }
+    return p;
+}
+
+/* missing_detector.cpp:290-336 — a sample is "missing" when the first ':' piece holds a '.'
+ * that touches a piece boundary or a '/' '|' separator on either side. FORMAT is ignored. */
+static int md_region_missing(const char *p, const char *e) {
+    while (p < e) {
+        const char *t = (const char *)memchr(p, '\t', (size_t)(e - p));
+        const char *se = t ? t : e;
+        const char *ge = (const char *)memchr(p, ':', (size_t)(se - p));
+        if (!ge) ge = se;
+        for (const char *g = p; g < ge; ++g) {
+            if (*g != '.') continue;
+            int prev_sep = (g == p) || g[-1] == '/' || g[-1] == '|';
+            int next_sep = (g + 1 >= ge) || g[1] == '/' || g[1] == '|';
+            if (prev_sep || next_sep) return 1;
+        }
+        if (!t) break;
+        p = t + 1;
+    }
+    return 0;
+}
+
+static void md_emit_flagged(obuf *o, const char *s, const char *e) {
+    /* INFO = field 7 (missing_detector.cpp:546-568, :893-906) */
+    const char *is = md_skip(s, e, 7);
+    const char *ie = (const char *)memchr(is, '\t', (size_t)(e - is));
+    if (!ie) ie = e;
+    ob_put(o, s, (size_t)(is - s));
+    size_t il = (size_t)(ie - is);
+    if (il == 0 || (il == 1 && is[0] == '.')) {
+        ob_str(o, "MISSING_GENOTYPES=1");
+    } else {
+        ob_put(o, is, il);
+        if (ie[-1] != ';') ob_ch(o, ';');
+        ob_str(o, "MISSING_GENOTYPES=1");
+    }
+    ob_put(o, ie, (size_t)(e - ie));
+    ob_ch(o, '\n');
+}
+
+static int md_file(const char *in, size_t n, oracle_result *r) {
+    obuf o = {0}; size_t pos = 0; line_t ln;
+    /* Pre-scan (missing_detector.cpp:371-392, 347-369, single-thread form = "-t 1"):
+     * skip the leading '#' block, then look for ANY '.' after the 9th tab of every
+     * newline-TERMINATED line; an unterminated last line is not looked at (:354). */
+    int any_dot = 0;
+    {
+        size_t p2 = 0; line_t l2; int in_header = 1;
+        while (next_line(in, n, &p2, &l2)) {
+            if (in_header && *l2.s == '#') continue;   /* an empty line ends the '#' block */
+            in_header = 0;
+            if (!l2.terminated) break;
+            r->data_lines++;          /* the fast path reports this count on stderr */
+            const char *ss = md_skip(l2.s, l2.e, 9);
+            if (ss < l2.e && memchr(ss, '.', (size_t)(l2.e - ss))) { any_dot = 1; break; }
+        }
+    }
+    if (!any_dot) {                                          /* :456-477 verbatim copy */
+        ob_put(&o, in, n);
+        res_take(r, &o);
+        return 0;
+    }
+    r->data_lines = 0;
+    while (next_line(in, n, &pos, &ln)) {                    /* :499-579 */
+        const char *s = ln.s, *e = ln.e;
+        size_t raw = (size_t)(ln.e - ln.s) + (ln.terminated ? 1 : 0);
+        if (e > s && e[-1] == '\r') --e;                     /* :505-506 */
+        if (s == e || *s == '#') { ob_put(&o, s, raw); continue; }      /* :511 */
+        r->data_lines++;
+        const char *ss = md_skip(s, e, 9);
+        if (ss >= e || !md_region_missing(ss, e)) { ob_put(&o, s, raw); continue; }
+        r->flagged++;
+        md_emit_flagged(&o, s, e);          /* '\r' dropped, '\n' always added (:571-574) */
+    }
+    res_take(r, &o);
+    return 0;
+}
+
+static int md_stdin(const char *in, size_t n, oracle_result *r) {
+    obuf o = {0}; size_t pos = 0; line_t ln;
+    while (next_line(in, n, &pos, &ln)) {                    /* :864-910; no '\r' handling */
+        const char *s = ln.s, *e = ln.e;
+        if (s == e) { ob_ch(&o, '\n'); continue; }
+        if (*s == '#') { ob_put(&o, s, (size_t)(e - s)); ob_ch(&o, '\n'); continue; }
+        r->data_lines++;
+        const char *ss = md_skip(s, e, 9);
+        if (ss >= e || !md_region_missing(ss, e)) {
+            ob_put(&o, s, (size_t)(e - s)); ob_ch(&o, '\n'); continue;
+        }
+        r->flagged++;
+        md_emit_flagged(&o, s, e);
+    }
+    res_take(r, &o);
+    return 0;
+}
+
+int oracle_missing(const char *in, size_t n, int mode, oracle_result *r) {
+    res_init(r);
+    return mode == ORACLE_FILE ? md_file(in, n, r) : md_stdin(in, n, r);
+}
+
+/* ------------------------------------------------------------------ variant_counter */
+
+/* variant_counter.cpp:31-44 — at least 7 tabs. */
+static int vc_eight_cols(const char *s, const char *e) {
+    const char *p = s;
+    if (s == e) return 0;
+    for (int i = 0; i < 7; ++i) {
+        p = (const char *)memchr(p, '\t', (size_t)(e - p));
+        if (!p) return 0;
+        ++p;
+    }
+    return 1;
+}
+
+int oracle_variant_count(const char *in, size_t n, int mode, int strict, oracle_result *r) {
+    res_init(r);
+    obuf o = {0}; size_t pos = 0; line_t ln; long long line_no = 0; int count = 0;
+    while (next_line(in, n, &pos, &ln)) {
+        const char *s = ln.s, *e = ln.e;
+        ++line_no;                                           /* :360 / :216 */
+        if (s == e || *s == '#') continue;                   /* :364 / :183-186 */
+        if (mode == ORACLE_FILE && e[-1] == '\r') --e;       /* :366-368 (mmap only) */
+        if (vc_eight_cols(s, e)) { ++count; continue; }
+        if (strict) {                                        /* :373-377 / :195-197 */
+            r->first_bad_line = line_no; r->rc = 1;
+            res_take(r, &o);
+            return 0;                                        /* nothing on stdout (:175-177) */
+        }
+        r->warnings++;
+    }
+    char nb[64]; int l = sprintf(nb, "Total Variants: %d\n", count);   /* :178 */
+    ob_put(&o, nb, (size_t)l);
+    r->rows = count;
+    res_take(r, &o);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ allele_counter */
+
+/* allele_counter.cpp:267-294 — on the first ':' piece: skip separators, '.' consumes one
+ * byte, a digit run is one allele (0 = ref, else alt).  The reference never advances on
+ * any other byte (infinite loop); outside [0-9./|] this restatement skips the byte, which
+ * is outside the parity domain. */
+void oracle_ac_counts(const char *g, size_t n, int *ref, int *alt) {
+    size_t i = 0; *ref = 0; *alt = 0;
+    while (i < n) {
+        while (i < n && (g[i] == '/' || g[i] == '|')) ++i;
+        if (i >= n) break;
+        if (g[i] == '.') { ++i; continue; }
+        unsigned a = 0; int has = 0;                /* unsigned: digit-run overflow is UB upstream */
+        while (i < n && g[i] >= '0' && g[i] <= '9') { a = a * 10u + (unsigned)(g[i] - '0'); has = 1; ++i; }
+        if (has) { if ((int)a == 0) ++*ref; else ++*alt; }
+        else ++i;
+    }
+}
+
+typedef struct { const char *s; size_t n; } sv;
+
+static void put_int(obuf *o, long long v) { char nb[32]; int l = sprintf(nb, "%lld", v); ob_put(o, nb, (size_t)l); }
+
+/* sample names = fields 9.. of a "#CHROM" line (allele_counter.cpp:810-821, 1139-1151) */
+static void ac_header_names(const char *s, const char *e, sv **names, size_t *nn, size_t *cap) {
+    const char *p = md_skip(s, e, 9);
+    while (p < e) {
+        const char *t = (const char *)memchr(p, '\t', (size_t)(e - p));
+        const char *q = t ? t : e;
+        if (*nn == *cap) { *cap = *cap ? *cap * 2 : 64; *names = (sv *)realloc(*names, *cap * sizeof(sv)); }
+        (*names)[*nn].s = p; (*names)[*nn].n = (size_t)(q - p); ++*nn;
+        p = t ? t + 1 : e;
+    }
+}
+
+/* the -s argument: split on ' ', drop empties, trim (allele_counter.cpp:355-373) */
+static size_t ac_parse_samples(const char *arg, sv **req) {
+    size_t n = 0, cap = 0; *req = NULL;
+    if (!arg) return 0;
+    const char *p = arg, *end = arg + strlen(arg);
+    while (p < end) {
+        const char *q = (const char *)memchr(p, ' ', (size_t)(end - p));
+        const char *te = q ? q : end;
+        if (te > p) {
+            const char *a = p, *b = te;
+            while (a < b && strchr(" \t\n\r", *a)) ++a;
+            while (b > a && strchr(" \t\n\r", b[-1])) --b;
+            if (n == cap) { cap = cap ? cap * 2 : 8; *req = (sv *)realloc(*req, cap * sizeof(sv)); }
+            if (a < b) { (*req)[n].s = a; (*req)[n].n = (size_t)(b - a); }
+            else       { (*req)[n].s = p; (*req)[n].n = (size_t)(te - p); }   /* all-blank token kept as is */
+            ++n;
+        }
+        if (!q) break;
+        p = q + 1;
+    }
+    return n;
+}
+
+/* name -> column index; with duplicates the LAST column wins (map overwrite, :845-847) */
+static long ac_lookup(const sv *names, size_t nn, sv key) {
+    long hit = -1;
+    for (size_t i = 0; i < nn; ++i)
+        if (names[i].n == key.n && memcmp(names[i].s, key.s, key.n) == 0) hit = (long)i;
+    return hit;
+}
+
+static void ac_prefix(obuf *pre, const char **pp, const char *e) {
+    /* CHROM..ALT each followed by '\t', absent fields empty (:578-601) */
+    const char *p = *pp;
+    pre->n = 0;
+    for (int k = 0; k < 5; ++k) {
+        const char *t = (const char *)memchr(p, '\t', (size_t)(e - p));
+        const char *q = t ? t : e;
+        ob_put(pre, p, (size_t)(q - p)); ob_ch(pre, '\t');
+        p = q; if (p < e) ++p;
+    }
+    *pp = p;
+}
+
+int oracle_allele_counter(const char *in, size_t n, int path, int format, int limit,
+                          const char *samples, oracle_result *r) {
+    res_init(r);
+    obuf o = {0}, pre = {0};
+    sv *names = NULL; size_t nn = 0, ncap = 0;
+    sv *req = NULL; size_t nreq = ac_parse_samples(samples, &req);
+    size_t *sel = NULL; size_t nsel = 0;
+    size_t pos = 0; line_t ln;
+    int have_header = 0, failed_early = 0;
+    static const char TEXT_HDR[] = "CHROM\tPOS\tID\tREF\tALT\tSample\tRef_Count\tAlt_Count\n";
+    static const char AGG_HDR[]  = "CHROM\tPOS\tID\tREF\tALT\tTotal_Ref\tTotal_Alt\tSample_Count\n";
+
+#define AC_FAIL() do { r->rc = 1; failed_early = 1; goto done; } while (0)
+
+    if (path != ORACLE_AC_STREAM) {
+        if (n == 0) AC_FAIL();                               /* :793-796 / :1273-1276 "Empty file" */
+        /* header block: every leading '#' line; names accumulate over #CHROM lines */
+        size_t data_pos = n; int found_data = 0;
+        for (;;) {
+            size_t save = pos;
+            if (!next_line(in, n, &pos, &ln)) break;
+            if (*ln.s == '#') {   /* next_line never yields past the buffer, so *ln.s is readable */
+                if (ln.e - ln.s >= 6 && memcmp(ln.s, "#CHROM", 6) == 0) {
+                    ac_header_names(ln.s, ln.e, &names, &nn, &ncap); have_header = 1;
+                }
+                continue;
+            }
+            data_pos = save; found_data = 1; break;          /* first non-'#' line (even an empty one) */
+        }
+        if (nn == 0) AC_FAIL();                              /* "No samples found in VCF" */
+        if (path == ORACLE_AC_MT_TEXT && !found_data) AC_FAIL();   /* :836-839 "No data lines found" */
+        (void)have_header;
+        /* selection */
+        if (nreq) {
+            sel = (size_t *)malloc(nreq * sizeof(size_t));
+            for (size_t i = 0; i < nreq; ++i) {
+                long k = ac_lookup(names, nn, req[i]);
+                if (k < 0) AC_FAIL();                        /* "Sample 'x' not found" */
+                sel[nsel++] = (size_t)k;
+            }
+        } else {
+            sel = (size_t *)malloc((nn ? nn : 1) * sizeof(size_t));
+            for (size_t i = 0; i < nn; ++i) sel[nsel++] = i;
+        }
+        if (path == ORACLE_AC_UNIFIED && limit > 0 && nsel > (size_t)limit) nsel = (size_t)limit;  /* :1336 */
+
+        if (path == ORACLE_AC_MT_TEXT || format == ORACLE_AC_TEXT) ob_str(&o, TEXT_HDR);
+        else if (format == ORACLE_AC_AGGREGATE) ob_str(&o, AGG_HDR);
+        else {                                               /* BinaryHeader, packed (:326-333, 1361-1366) */
+            unsigned char h[20] = { 'V', 'C', 'A', 'C', 1, 0, 0, 0 };
+            uint32_t ns = (uint32_t)nsel; memcpy(h + 8, &ns, 4); memset(h + 12, 0, 8);
+            ob_put(&o, (const char *)h, 20);
+        }
+
+        pos = data_pos;
+        const char **starts = NULL; size_t scap = 0;
+        while (next_line(in, n, &pos, &ln)) {
+            const char *s = ln.s, *e = ln.e;                 /* no '\r' handling */
+            if (s >= e || *s == '#') continue;               /* :571 / :1373 */
+            r->data_lines++;
+            const char *p = s;
+            ac_prefix(&pre, &p, e);
+            p = md_skip(p, e, 4);                            /* QUAL FILTER INFO FORMAT (:604) */
+            if (path == ORACLE_AC_MT_TEXT) {
+                /* every sample column start, always at least one entry (:528-544) */
+                size_t ns = 0;
+                const char *q = p;
+                for (;;) {
+                    if (ns == scap) { scap = scap ? scap * 2 : 4096; starts = (const char **)realloc(starts, scap * sizeof(*starts)); }
+                    starts[ns++] = q;
+                    if (q >= e) break;
+                    const char *t = (const char *)memchr(q, '\t', (size_t)(e - q));
+                    if (!t) break;
+                    q = t + 1;
+                }
+                for (size_t i = 0; i < nsel; ++i) {
+                    int rc_ = 0, ac_ = 0;
+                    size_t idx = sel[i];
+                    if (idx < ns) {
+                        const char *gs = starts[idx];
+                        const char *ge = (idx + 1 < ns) ? starts[idx + 1] - 1 : e;
+                        const char *c = (gs < ge) ? (const char *)memchr(gs, ':', (size_t)(ge - gs)) : NULL;
+                        if (c) ge = c;
+                        if (gs < ge) oracle_ac_counts(gs, (size_t)(ge - gs), &rc_, &ac_);
+                    }
+                    ob_put(&o, pre.p, pre.n);
+                    ob_put(&o, names[sel[i]].s, names[sel[i]].n); ob_ch(&o, '\t');
+                    put_int(&o, (int8_t)rc_); ob_ch(&o, '\t');      /* int8_t storage (:621-622) */
+                    put_int(&o, (int8_t)ac_); ob_ch(&o, '\n');
+                    r->rows++;
+                }
+            } else {
+                /* forward-only walk; stops at the first absent column (:1416-1451) */
+                long long tr = 0, ta = 0; int sc = 0;
+                size_t col = 0; const char *sp = p;
+                for (size_t i = 0; i < nsel; ++i) {
+                    while (col < sel[i] && sp < e) {
+                        const char *t = (const char *)memchr(sp, '\t', (size_t)(e - sp));
+                        sp = t ? t + 1 : e; ++col;
+                    }
+                    if (sp >= e) break;
+                    const char *t = (const char *)memchr(sp, '\t', (size_t)(e - sp));
+                    const char *ge = t ? t : e;
+                    const char *c = (const char *)memchr(sp, ':', (size_t)(ge - sp));
+                    if (c) ge = c;
+                    int rc_ = 0, ac_ = 0;
+                    oracle_ac_counts(sp, (size_t)(ge - sp), &rc_, &ac_);
+                    if (format == ORACLE_AC_TEXT) {
+                        ob_put(&o, pre.p, pre.n);
+                        ob_put(&o, names[sel[i]].s, names[sel[i]].n); ob_ch(&o, '\t');
+                        put_int(&o, rc_); ob_ch(&o, '\t'); put_int(&o, ac_); ob_ch(&o, '\n');
+                        r->rows++;
+                    } else if (format == ORACLE_AC_AGGREGATE) {
+                        tr += rc_; ta += ac_; ++sc;
+                    } else {
+                        char b[2] = { (char)(int8_t)rc_, (char)(int8_t)ac_ };
+                        ob_put(&o, b, 2);
+                    }
+                }
+                if (format == ORACLE_AC_AGGREGATE) {
+                    ob_put(&o, pre.p, pre.n);
+                    put_int(&o, tr); ob_ch(&o, '\t'); put_int(&o, ta); ob_ch(&o, '\t');
+                    put_int(&o, sc); ob_ch(&o, '\n');
+                    r->rows++;
+                }
+            }
+        }
+        free(starts);
+    } else {
+        /* stdin: header row first, names/selection rebuilt at every #CHROM line
+         * (allele_counter.cpp:1131, 1138-1181); -a/-b/-l are ignored on this path */
+        ob_str(&o, TEXT_HDR);
+        size_t selcap = 0;
+        while (next_line(in, n, &pos, &ln)) {
+            const char *s = ln.s, *e = ln.e;
+            if (s == e) continue;
+            if (*s == '#') {
+                if (e - s >= 6 && memcmp(s, "#CHROM", 6) == 0) {
+                    ac_header_names(s, e, &names, &nn, &ncap);
+                    size_t add = nreq ? nreq : nn;
+                    if (nsel + add > selcap) { selcap = (nsel + add) * 2 + 8; sel = (size_t *)realloc(sel, selcap * sizeof(size_t)); }
+                    if (nreq) {
+                        for (size_t i = 0; i < nreq; ++i) {
+                            long k = ac_lookup(names, nn, req[i]);
+                            if (k < 0) AC_FAIL();
+                            sel[nsel++] = (size_t)k;
+                        }
+                    } else {
+                        for (size_t i = 0; i < nn; ++i) sel[nsel++] = i;
+                    }
+                    have_header = 1;
+                }
+                continue;
+            }
+            if (!have_header) AC_FAIL();                     /* :1183-1186; nothing was flushed yet */
+            r->data_lines++;
+            const char *p = s;
+            ac_prefix(&pre, &p, e);
+            p = md_skip(p, e, 4);
+            size_t col = 0; const char *sp = p;
+            for (size_t i = 0; i < nsel; ++i) {
+                while (col < sel[i] && sp < e) {
+                    const char *t = (const char *)memchr(sp, '\t', (size_t)(e - sp));
+                    sp = t ? t + 1 : e; ++col;
+                }
+                if (sp >= e) break;
+                const char *t = (const char *)memchr(sp, '\t', (size_t)(e - sp));
+                const char *ge = t ? t : e;
+                const char *c = (const char *)memchr(sp, ':', (size_t)(ge - sp));
+                if (c) ge = c;
+                int rc_ = 0, ac_ = 0;
+                oracle_ac_counts(sp, (size_t)(ge - sp), &rc_, &ac_);
+                ob_put(&o, pre.p, pre.n);
+                ob_put(&o, names[sel[i]].s, names[sel[i]].n); ob_ch(&o, '\t');
+                put_int(&o, rc_); ob_ch(&o, '\t'); put_int(&o, ac_); ob_ch(&o, '\n');
+                r->rows++;
+            }
+        }
+        if (!have_header) r->rc = 1;                         /* :1259 */
+    }
+done:
+    /* Every early failure happens before the first write(2): the file paths validate the
+     * header first, and the stream path keeps its header row in a buffer that is dropped on
+     * error (allele_counter.cpp:1162, :1185).  A header-less stream that reaches EOF does
+     * write that row and then returns rc 1 (:1255-1259). */
+    if (failed_early) o.n = 0;
+    free(pre.p); free(names); free(req); free(sel);
+    res_take(r, &o);
+    return 0;
+#undef AC_FAIL
+}
