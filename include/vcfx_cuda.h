@@ -1,0 +1,162 @@
+/*
+ * vcfx_cuda.h — C ABI of libvcfx_cuda, the B200 (sm_100a) implementation of VCFX's shared
+ * hot path:  VCF bytes -> line/field scan -> FORMAT/GT parse -> per-variant reduce -> text.
+ *
+ * The reference (jorgeMFS/VCFX v1.1.4) has no library boundary for this path: each tool
+ * carries a private copy of the same loop.  Every entry point below therefore names the
+ * reference code it stands in for; INTEGRATION.md shows the change a maintainer makes in
+ * each tool's main() to call it.
+ *
+ *   reference loop being replaced                               op
+ *   ----------------------------------------------------------  ------------------------
+ *   VCFX_variant_counter.cpp:317-389 countVariantsMmap,         VCFX_OP_VARIANT_COUNT
+ *     :204-221 countVariants, :223-290 countVariantsGzip
+ *   VCFX_allele_freq_calc.cpp:342-472 processMmap,              VCFX_OP_ALLELE_FREQ
+ *     :477-557 processStdin
+ *   VCFX_hwe_tester.cpp:455-559 performHWE_Mmap,                VCFX_OP_HWE
+ *     :565-608 performHWE_Stdin
+ *   VCFX_missing_detector.cpp:450-589 processMmapZeroCopy,      VCFX_OP_MISSING_DETECT
+ *     :860-911 detectMissingGenotypes
+ *   VCFX_allele_counter.cpp:550-642 processChunk (+786-950),    VCFX_OP_ALLELE_COUNT
+ *     :1122-1260 countAllelesStream, :1266-1468 countAllelesUnified
+ *
+ * The "mode" selects which of the two behaviours of a tool is reproduced: the reference
+ * formats numbers and skips lines differently when it mmaps a file (-i FILE) and when it
+ * reads stdin (SURVEY.md finding 1).  Output is byte-identical to the reference tool run in
+ * that mode; the fixed header row of each tool is written by the caller, not by the library.
+ *
+ * Conventions: plain pointers and sizes, no C++ types, no exceptions; every function returns
+ * 0 or a negative vcfx_err; the library never prints and never falls back to the CPU
+ * (no device => VCFX_E_NO_DEVICE).  One context drives one GPU; a context is used by one
+ * thread at a time; contexts are independent, so one process can hold one per GPU.
+ */
+#ifndef VCFX_CUDA_H
+#define VCFX_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VCFX_CUDA_ABI_VERSION 1
+
+typedef struct vcfx_ctx vcfx_ctx;
+
+typedef enum {
+    VCFX_OP_VARIANT_COUNT  = 0,
+    VCFX_OP_ALLELE_FREQ    = 1,
+    VCFX_OP_HWE            = 2,
+    VCFX_OP_MISSING_DETECT = 3,
+    VCFX_OP_ALLELE_COUNT   = 4
+} vcfx_op;
+
+typedef enum {
+    VCFX_MODE_FILE  = 0,   /* semantics of `tool -i FILE` (mmap path of the reference)  */
+    VCFX_MODE_STDIN = 1    /* semantics of `tool < FILE`  (getline path of the reference) */
+} vcfx_mode;
+
+typedef enum {
+    VCFX_OK               =  0,
+    VCFX_E_INVALID        = -1,   /* bad argument / call order                         */
+    VCFX_E_NO_DEVICE      = -2,   /* no usable CUDA device: there is no CPU fallback   */
+    VCFX_E_CUDA           = -3,   /* a CUDA call failed (see vcfx_cuda_last_error)     */
+    VCFX_E_NOMEM          = -4,
+    VCFX_E_BUSY           = -5,   /* every pipeline slot is in flight: drain an output */
+    VCFX_E_EMPTY          = -6,   /* nothing in flight                                 */
+    VCFX_E_OUTPUT_TOO_BIG = -7,   /* one chunk's output exceeds the output capacity    */
+    VCFX_E_UNSUPPORTED    = -8
+} vcfx_err;
+
+/* allele_counter variants (cfg.flags) */
+#define VCFX_F_AC_AGGREGATE   0x01u  /* -a: one row per variant (countAllelesUnified :1440-1461)          */
+#define VCFX_F_AC_BINARY      0x02u  /* -b: int8 {ref,alt} per selected sample (:1444-1449)               */
+#define VCFX_F_AC_FORWARD     0x04u  /* stdin / unified column walk: forward only, stop at the first absent
+                                        column (:1222-1229, :1416-1423); without it: processChunk's random
+                                        access with 0/0 padding and int8 storage (:610-627)               */
+
+typedef struct {
+    int32_t  device;          /* CUDA device ordinal                                            */
+    int32_t  op;              /* vcfx_op                                                        */
+    int32_t  mode;            /* vcfx_mode                                                      */
+    uint32_t flags;
+    size_t   chunk_bytes;     /* capacity of one pinned input slot (0 = 64 MiB)                 */
+    size_t   out_bytes;       /* capacity of one output slot (0 = sized from op and chunk)      */
+    int32_t  n_slots;         /* chunks in flight, 1..8 (0 = 3)                                 */
+    int32_t  tile_bytes;      /* bytes of input owned by one warp (0 = 64 KiB; multiple of 512) */
+    void    *stream;          /* optional cudaStream_t for the device-resident entry point      */
+    /* VCFX_OP_ALLELE_COUNT: the selected sample columns, in output order */
+    uint32_t        n_sel;          /* number of selected samples                               */
+    const uint32_t *sel_col;        /* [n_sel] 0-based sample column (field 9 + col)            */
+    const char     *sel_names;      /* concatenated names, each followed by '\t'                */
+    const uint32_t *sel_name_off;   /* [n_sel + 1] offsets into sel_names                       */
+} vcfx_cfg;
+
+/* what the caller knows about the chunk it submits */
+typedef struct {
+    uint64_t data_valid_from;  /* ALLELE_FREQ: data lines starting below this chunk offset precede
+                                  the first "#CHROM" line and are skipped with a warning
+                                  (allele_freq_calc.cpp:382-386); 0 = header already seen       */
+    int32_t  is_final;         /* last chunk: the final line may lack its '\n'                   */
+    int32_t  reserved;
+} vcfx_chunk_info;
+
+typedef struct {
+    uint64_t bytes_in;
+    uint64_t bytes_out;
+    uint64_t lines;            /* lines in the chunk (a final unterminated line counts)          */
+    uint64_t data_lines;       /* lines the tool treats as records                               */
+    uint64_t rows;             /* rows written / variants counted                                */
+    uint64_t flagged;          /* MISSING_DETECT: lines rewritten                                */
+    uint64_t pre_header;       /* ALLELE_FREQ: data lines before #CHROM (one warning each)       */
+    uint64_t short_lines;      /* VARIANT_COUNT: <8 columns; ALLELE_FREQ stdin: <9 fields        */
+    uint64_t first_short_line; /* 1-based line number inside the chunk of the first one, 0=none  */
+    uint64_t n_events;         /* short-line events recorded (see vcfx_cuda_short_lines)         */
+    uint64_t dots_terminated;  /* MISSING_DETECT: '\n'-terminated lines with a '.' after the 9th
+                                  tab (the reference's pre-scan, missing_detector.cpp:347-369)   */
+    uint64_t last_unterminated_flagged; /* MISSING_DETECT: length of the rewritten final line when
+                                  that line had no '\n' and was flagged, else 0                   */
+    float    kernel_ms;        /* device time of this chunk's kernels (CUDA events)              */
+    float    reserved;
+} vcfx_chunk_stats;
+
+int  vcfx_cuda_abi_version(void);
+int  vcfx_cuda_device_count(int *n);
+const char *vcfx_cuda_strerror(int err);
+const char *vcfx_cuda_last_error(const vcfx_ctx *ctx);   /* text of the last CUDA failure */
+
+int  vcfx_cuda_create(const vcfx_cfg *cfg, vcfx_ctx **out);
+void vcfx_cuda_destroy(vcfx_ctx *ctx);
+
+/* ---- streaming path: host buffers in, host text out (replaces the per-line loops) --------
+ * acquire_input  : a pinned buffer of cfg.chunk_bytes to fill (read(2)/memcpy straight in).
+ * submit         : nbytes of it become a chunk.  A chunk must start at a line start and,
+ *                  unless info->is_final, end with '\n'.  Asynchronous: H2D copy, kernels and
+ *                  the D2H copy of the text run on the context's streams.
+ * next_output    : blocks for the OLDEST chunk in flight and returns its text (order
+ *                  preserving).  The pointer stays valid until the next acquire/submit.     */
+int vcfx_cuda_acquire_input(vcfx_ctx *ctx, char **buf, size_t *cap);
+int vcfx_cuda_submit(vcfx_ctx *ctx, size_t nbytes, const vcfx_chunk_info *info);
+int vcfx_cuda_next_output(vcfx_ctx *ctx, const char **text, size_t *n, vcfx_chunk_stats *stats);
+int vcfx_cuda_in_flight(const vcfx_ctx *ctx);
+
+/* 1-based line numbers (inside the chunk last returned by next_output) of lines with too few
+ * columns, ascending; at most `cap` are copied, the total is stats.n_events
+ * (variant_counter.cpp:373-380 prints one message per such line). */
+int vcfx_cuda_short_lines(vcfx_ctx *ctx, uint64_t *line_no, size_t cap, size_t *n);
+
+/* ---- device-resident path: for callers that already hold the bytes in HBM -----------------
+ * d_in must be 16-byte aligned and readable for nbytes + VCFX_DEVICE_PAD bytes (the library
+ * writes '\n' into the first 64 bytes of that pad).  d_out receives the text (out_cap bytes).
+ * Runs on cfg.stream (or the context's own stream), asynchronously; vcfx_cuda_sync waits and
+ * fills stats.  Used by bench.py for the kernel-only figure. */
+#define VCFX_DEVICE_PAD 4096
+int vcfx_cuda_run_device(vcfx_ctx *ctx, void *d_in, size_t nbytes, const vcfx_chunk_info *info,
+                         void *d_out, size_t out_cap);
+int vcfx_cuda_sync(vcfx_ctx *ctx, vcfx_chunk_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCFX_CUDA_H */

@@ -1,0 +1,303 @@
+"""ctypes mirror of ``include/vcfx_cuda.h`` plus the host-side logic the five tools share.
+
+This is the Python twin of the C++ host code in ``vcfx_b200/tools``: header pre-parse,
+newline-aligned chunking, the fixed header rows, and totals — everything per-record happens
+in ``libvcfx_cuda.so`` on the GPU.  There is no CPU fallback: if the library is missing, or
+no CUDA device is usable, the calls raise :class:`VcfxCudaError`.
+
+Function names follow the reference tools (``allele_freq_calc``, ``hwe_tester``,
+``missing_detector``, ``variant_counter``, ``allele_counter``) and take the same two input
+modes the reference has: ``FILE`` (``tool -i file``, mmap semantics) and ``STDIN``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from pathlib import Path
+
+from . import build as _build
+
+OP_VARIANT_COUNT, OP_ALLELE_FREQ, OP_HWE, OP_MISSING_DETECT, OP_ALLELE_COUNT = range(5)
+FILE, STDIN = 0, 1
+F_AC_AGGREGATE, F_AC_BINARY, F_AC_FORWARD = 1, 2, 4
+DEVICE_PAD = 4096
+
+E_BUSY, E_EMPTY = -5, -6
+
+AF_HEADER = b"CHROM\tPOS\tID\tREF\tALT\tAllele_Frequency\n"      # allele_freq_calc.cpp:353
+HWE_HEADER = b"CHROM\tPOS\tID\tREF\tALT\tHWE_pvalue\n"            # hwe_tester.cpp:463
+AC_TEXT_HEADER = b"CHROM\tPOS\tID\tREF\tALT\tSample\tRef_Count\tAlt_Count\n"            # allele_counter.cpp:908
+AC_AGG_HEADER = b"CHROM\tPOS\tID\tREF\tALT\tTotal_Ref\tTotal_Alt\tSample_Count\n"        # :1359
+
+
+class VcfxCudaError(RuntimeError):
+    def __init__(self, code: int, what: str):
+        super().__init__(f"libvcfx_cuda: {what} (code {code})")
+        self.code = code
+
+
+class Cfg(C.Structure):
+    _fields_ = [("device", C.c_int32), ("op", C.c_int32), ("mode", C.c_int32), ("flags", C.c_uint32),
+                ("chunk_bytes", C.c_size_t), ("out_bytes", C.c_size_t), ("n_slots", C.c_int32),
+                ("tile_bytes", C.c_int32), ("stream", C.c_void_p),
+                ("n_sel", C.c_uint32), ("sel_col", C.POINTER(C.c_uint32)), ("sel_names", C.c_char_p),
+                ("sel_name_off", C.POINTER(C.c_uint32))]
+
+
+class ChunkInfo(C.Structure):
+    _fields_ = [("data_valid_from", C.c_uint64), ("is_final", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ChunkStats(C.Structure):
+    _fields_ = [("bytes_in", C.c_uint64), ("bytes_out", C.c_uint64), ("lines", C.c_uint64),
+                ("data_lines", C.c_uint64), ("rows", C.c_uint64), ("flagged", C.c_uint64),
+                ("pre_header", C.c_uint64), ("short_lines", C.c_uint64), ("first_short_line", C.c_uint64),
+                ("n_events", C.c_uint64), ("dots_terminated", C.c_uint64),
+                ("last_unterminated_flagged", C.c_uint64), ("kernel_ms", C.c_float), ("reserved", C.c_float)]
+
+
+EXPORTS = ["vcfx_cuda_abi_version", "vcfx_cuda_device_count", "vcfx_cuda_strerror", "vcfx_cuda_last_error",
+           "vcfx_cuda_create", "vcfx_cuda_destroy", "vcfx_cuda_acquire_input", "vcfx_cuda_submit",
+           "vcfx_cuda_next_output", "vcfx_cuda_in_flight", "vcfx_cuda_short_lines",
+           "vcfx_cuda_run_device", "vcfx_cuda_sync"]
+
+_lib = None
+
+
+def lib_path() -> Path:
+    return _build.CUDA_LIB
+
+
+def load():
+    """Load libvcfx_cuda.so (building it is the job of __graft_entry__.build / build.build_cuda)."""
+    global _lib
+    if _lib is None:
+        p = lib_path()
+        if not p.exists():
+            raise VcfxCudaError(-2, f"{p} is not built; run `python -c 'import __graft_entry__ as g; g.build()'`"
+                                    " — there is no CPU fallback")
+        l = C.CDLL(str(p))
+        l.vcfx_cuda_strerror.restype = C.c_char_p
+        l.vcfx_cuda_last_error.restype = C.c_char_p
+        l.vcfx_cuda_last_error.argtypes = [C.c_void_p]
+        l.vcfx_cuda_create.argtypes = [C.POINTER(Cfg), C.POINTER(C.c_void_p)]
+        l.vcfx_cuda_destroy.argtypes = [C.c_void_p]
+        l.vcfx_cuda_acquire_input.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        l.vcfx_cuda_submit.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(ChunkInfo)]
+        l.vcfx_cuda_next_output.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(ChunkStats)]
+        l.vcfx_cuda_in_flight.argtypes = [C.c_void_p]
+        l.vcfx_cuda_short_lines.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_size_t, C.POINTER(C.c_size_t)]
+        l.vcfx_cuda_run_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(ChunkInfo), C.c_void_p, C.c_size_t]
+        l.vcfx_cuda_sync.argtypes = [C.c_void_p, C.POINTER(ChunkStats)]
+        _lib = l
+    return _lib
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    load().vcfx_cuda_device_count(C.byref(n))
+    return n.value
+
+
+@dataclass
+class Totals:
+    bytes_in: int = 0
+    bytes_out: int = 0
+    lines: int = 0
+    data_lines: int = 0
+    rows: int = 0
+    flagged: int = 0
+    pre_header: int = 0
+    short_lines: int = 0
+    first_short_line: int = 0          # 1-based, over the whole input
+    short_line_numbers: list = field(default_factory=list)
+    dots_terminated: int = 0
+    last_unterminated_flagged: int = 0
+    kernel_ms: float = 0.0
+    chunks: int = 0
+
+    def add(self, s: ChunkStats, line_base: int, events):
+        self.bytes_in += s.bytes_in; self.bytes_out += s.bytes_out
+        self.data_lines += s.data_lines; self.rows += s.rows; self.flagged += s.flagged
+        self.pre_header += s.pre_header; self.short_lines += s.short_lines
+        if s.first_short_line and not self.first_short_line:
+            self.first_short_line = line_base + s.first_short_line
+        self.short_line_numbers += [line_base + e for e in events]
+        self.lines += s.lines
+        self.dots_terminated += s.dots_terminated
+        self.last_unterminated_flagged = s.last_unterminated_flagged
+        self.kernel_ms += s.kernel_ms; self.chunks += 1
+
+
+class Context:
+    """One GPU context (``vcfx_ctx``)."""
+
+    def __init__(self, op: int, mode: int = FILE, device: int = 0, flags: int = 0, chunk_bytes: int = 0,
+                 out_bytes: int = 0, n_slots: int = 0, tile_bytes: int = 0, stream: int | None = None,
+                 sel_cols=None, sel_names=None):
+        self._l = load()
+        self._h = C.c_void_p()
+        cfg = Cfg(device=device, op=op, mode=mode, flags=flags, chunk_bytes=chunk_bytes, out_bytes=out_bytes,
+                  n_slots=n_slots, tile_bytes=tile_bytes, stream=stream)
+        self._keep = []
+        if sel_cols is not None:
+            n = len(sel_cols)
+            cols = (C.c_uint32 * max(n, 1))(*sel_cols)
+            blob = b"".join(nm + b"\t" for nm in sel_names)
+            offs = [0]
+            for nm in sel_names:
+                offs.append(offs[-1] + len(nm) + 1)
+            off_arr = (C.c_uint32 * (n + 1))(*offs)
+            cfg.n_sel = n; cfg.sel_col = cols; cfg.sel_names = blob; cfg.sel_name_off = off_arr
+            self._keep = [cols, blob, off_arr]
+        self._check(self._l.vcfx_cuda_create(C.byref(cfg), C.byref(self._h)))
+        self.op, self.mode = op, mode
+
+    def _check(self, rc: int):
+        if rc != 0:
+            msg = self._l.vcfx_cuda_strerror(rc).decode()
+            if self._h:
+                extra = self._l.vcfx_cuda_last_error(self._h).decode()
+                if extra:
+                    msg += ": " + extra
+            raise VcfxCudaError(rc, msg)
+
+    def close(self):
+        if self._h:
+            self._l.vcfx_cuda_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- streaming path ------------------------------------------------------------------
+    def acquire(self):
+        buf = C.c_void_p(); cap = C.c_size_t()
+        rc = self._l.vcfx_cuda_acquire_input(self._h, C.byref(buf), C.byref(cap))
+        if rc == E_BUSY:
+            return None, 0
+        self._check(rc)
+        return buf.value, cap.value
+
+    def submit(self, nbytes: int, valid_from: int = 0, is_final: bool = True):
+        info = ChunkInfo(valid_from, int(is_final), 0)
+        self._check(self._l.vcfx_cuda_submit(self._h, nbytes, C.byref(info)))
+
+    def in_flight(self) -> int:
+        return self._l.vcfx_cuda_in_flight(self._h)
+
+    def next_output(self):
+        text = C.c_void_p(); n = C.c_size_t(); st = ChunkStats()
+        self._check(self._l.vcfx_cuda_next_output(self._h, C.byref(text), C.byref(n), C.byref(st)))
+        out = C.string_at(text.value, n.value) if n.value else b""
+        events = []
+        if st.n_events:
+            cap = min(int(st.n_events), 1 << 20)
+            arr = (C.c_uint64 * cap)(); got = C.c_size_t()
+            self._check(self._l.vcfx_cuda_short_lines(self._h, arr, cap, C.byref(got)))
+            events = list(arr[: got.value])
+        return out, st, events
+
+    # -- device-resident path ------------------------------------------------------------
+    def run_device(self, d_in: int, nbytes: int, d_out: int, out_cap: int, valid_from: int = 0, is_final: bool = True):
+        info = ChunkInfo(valid_from, int(is_final), 0)
+        self._check(self._l.vcfx_cuda_run_device(self._h, d_in, nbytes, C.byref(info), d_out, out_cap))
+
+    def sync(self) -> ChunkStats:
+        st = ChunkStats()
+        self._check(self._l.vcfx_cuda_sync(self._h, C.byref(st)))
+        return st
+
+
+# ----------------------------------------------------------------------------- host logic
+def find_chrom_header(data) -> int:
+    """Offset of the first line that starts with ``#CHROM`` (len(data) if none): data lines
+    before it are skipped by allele_freq_calc (allele_freq_calc.cpp:372-386, 492-502)."""
+    if bytes(data[:6]) == b"#CHROM":
+        return 0
+    i = data.find(b"\n#CHROM")
+    return len(data) if i < 0 else i + 1
+
+
+def chunk_bounds(data, chunk_bytes: int):
+    """Newline-aligned [start, end) pieces of at most chunk_bytes (the last may be unterminated)."""
+    n = len(data)
+    pos = 0
+    while pos < n:
+        end = min(n, pos + chunk_bytes)
+        if end < n:
+            cut = data.rfind(b"\n", pos, end)
+            if cut < 0:
+                raise VcfxCudaError(-1, f"a line longer than chunk_bytes={chunk_bytes} starts at byte {pos}")
+            end = cut + 1
+        yield pos, end
+        pos = end
+
+
+def stream_bytes(ctx: Context, data, chunk_bytes: int, valid_abs: int = 0):
+    """Push ``data`` through ctx's streaming pipeline; returns (list of output pieces, Totals)."""
+    tot = Totals()
+    outs = []
+    line_base = 0
+
+    def drain():
+        nonlocal line_base
+        out, st, ev = ctx.next_output()
+        outs.append(out)
+        tot.add(st, line_base, ev)
+        line_base += st.lines
+
+    mv = memoryview(data)
+    n = len(data)
+    for s, e in chunk_bounds(data, chunk_bytes):
+        buf, cap = ctx.acquire()
+        while buf is None:
+            drain()
+            buf, cap = ctx.acquire()
+        assert e - s <= cap
+        C.memmove(buf, (C.c_char * (e - s)).from_buffer_copy(mv[s:e]), e - s)
+        vf = min(max(valid_abs - s, 0), e - s)
+        ctx.submit(e - s, valid_from=vf, is_final=(e == n))
+        # line numbers: chunks are drained in order, so the base is exact when drained
+    while ctx.in_flight():
+        drain()
+    return outs, tot
+
+
+def _run(op: int, data: bytes, mode: int, chunk_bytes: int, flags: int = 0, device: int = 0, **kw):
+    chunk_bytes = chunk_bytes or (64 << 20)
+    with Context(op, mode, device=device, flags=flags, chunk_bytes=chunk_bytes, **kw) as ctx:
+        valid_abs = find_chrom_header(data) if op == OP_ALLELE_FREQ else 0
+        outs, tot = stream_bytes(ctx, data, chunk_bytes, valid_abs)
+    return b"".join(outs), tot
+
+
+@dataclass
+class ToolResult:
+    out: bytes
+    rc: int
+    totals: Totals
+
+
+def allele_freq_calc(data: bytes, mode: int = FILE, chunk_bytes: int = 0, **kw) -> ToolResult:
+    if mode == STDIN and len(data) == 0:          # allele_freq_calc.cpp:638-641 prints help, rc 1
+        return ToolResult(b"", 1, Totals())
+    body, tot = _run(OP_ALLELE_FREQ, data, mode, chunk_bytes, **kw)
+    return ToolResult(AF_HEADER + body, 0, tot)
+
+
+def hwe_tester(data: bytes, mode: int = FILE, chunk_bytes: int = 0, **kw) -> ToolResult:
+    if mode == FILE and len(data) == 0:           # hwe_tester.cpp:456 no header for an empty file
+        return ToolResult(b"", 0, Totals())
+    body, tot = _run(OP_HWE, data, mode, chunk_bytes, **kw)
+    return ToolResult(HWE_HEADER + body, 0, tot)
+
+
+def variant_counter(data: bytes, mode: int = FILE, strict: bool = False, chunk_bytes: int = 0, **kw) -> ToolResult:
+    _, tot = _run(OP_VARIANT_COUNT, data, mode, chunk_bytes, **kw)
+    if strict and tot.short_lines:                # variant_counter.cpp:373-377, 175-177
+        return ToolResult(b"", 1, tot)
+    return ToolResult(b"Total Variants: %d\n" % tot.rows, 0, tot)

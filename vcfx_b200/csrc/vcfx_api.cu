@@ -1,0 +1,406 @@
+// vcfx_api.cu — the C ABI of libvcfx_cuda (include/vcfx_cuda.h): context, pinned
+// multi-slot streaming pipeline (H2D || kernels || D2H), and the device-resident entry point.
+// No CPU fallback lives here: without a CUDA device every call fails with VCFX_E_NO_DEVICE.
+#include "vcfx_cuda.h"
+#include "vcfx_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace vcfx;
+
+namespace {
+
+constexpr size_t DEFAULT_CHUNK = 64u << 20;
+constexpr uint32_t DEFAULT_TILE = 64u << 10;
+constexpr uint32_t EVENT_CAP = 1u << 20;
+constexpr int MAX_SLOTS = 8;
+
+struct Work {                      // device-side bookkeeping for one launch
+    unsigned long long *desc = nullptr;
+    uint32_t *tile_lines = nullptr;
+    unsigned long long *tile_base = nullptr;
+    unsigned int *ticket = nullptr;
+    Rec *scratch = nullptr;
+    DevStats *d_stats = nullptr;
+    unsigned long long *events = nullptr;
+    DevStats *h_stats = nullptr;   // pinned
+    uint32_t tiles_cap = 0;
+    size_t scratch_recs = 0;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+};
+
+struct Slot {
+    char *h_in = nullptr;          // pinned
+    uint8_t *d_in = nullptr;
+    uint8_t *d_out = nullptr;
+    char *h_out = nullptr;         // pinned
+    cudaStream_t stream = nullptr;
+    Work w;
+    size_t nbytes = 0;
+    bool in_flight = false;
+    bool acquired = false;
+};
+
+}  // namespace
+
+struct vcfx_ctx {
+    vcfx_cfg cfg;
+    int device = 0;
+    int sm_count = 0;
+    int blocks_per_sm = 1;
+    size_t chunk_bytes = 0, out_bytes = 0;
+    uint32_t tile_bytes = 0;
+    int n_slots = 0;
+    Slot slots[MAX_SLOTS];
+    int head = 0;                  // next slot to acquire
+    int tail = 0;                  // oldest slot in flight
+    int n_in_flight = 0;
+    int acquired_slot = -1;
+    // device-resident path
+    Work dev_work;
+    cudaStream_t dev_stream = nullptr;
+    bool dev_stream_owned = false;
+    bool dev_pending = false;
+    size_t dev_nbytes = 0;
+    // last drained chunk's short-line list
+    std::vector<uint64_t> last_events;
+    uint64_t last_n_events = 0;
+    std::string last_error;
+};
+
+namespace {
+
+#define CU(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t _e = (call);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            ctx->last_error = std::string(#call) + ": " + cudaGetErrorString(_e);       \
+            return (_e == cudaErrorMemoryAllocation) ? VCFX_E_NOMEM : VCFX_E_CUDA;       \
+        }                                                                                \
+    } while (0)
+
+typedef void (*kernel_fn)(const KParams);
+
+kernel_fn kernel_for(int op) {
+    switch (op) {
+    case VCFX_OP_VARIANT_COUNT: return vcfx_scan_kernel<OP_VC>;
+    case VCFX_OP_ALLELE_FREQ:   return vcfx_scan_kernel<OP_AF>;
+    case VCFX_OP_HWE:           return vcfx_scan_kernel<OP_HWE>;
+    default: return nullptr;
+    }
+}
+
+uint32_t tiles_for(const vcfx_ctx *ctx, size_t nbytes) {
+    return (uint32_t)std::max<size_t>(1, (nbytes + ctx->tile_bytes - 1) / ctx->tile_bytes);
+}
+
+int grid_for(const vcfx_ctx *ctx, uint32_t n_tiles) {
+    int resident = ctx->sm_count * ctx->blocks_per_sm;
+    int need = (int)((n_tiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+    return std::max(1, std::min(resident, need));
+}
+
+uint32_t qcap_for(const vcfx_ctx *ctx) { return ctx->tile_bytes / 11 + 2; }
+
+void free_work(Work &w) {
+    cudaFree(w.desc); cudaFree(w.tile_lines); cudaFree(w.tile_base); cudaFree(w.ticket);
+    cudaFree(w.scratch); cudaFree(w.d_stats); cudaFree(w.events);
+    if (w.h_stats) cudaFreeHost(w.h_stats);
+    if (w.ev_k0) cudaEventDestroy(w.ev_k0);
+    if (w.ev_k1) cudaEventDestroy(w.ev_k1);
+    w = Work();
+}
+
+int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes) {
+    uint32_t tiles = tiles_for(ctx, max_bytes);
+    if (!w.d_stats) {
+        CU(cudaMalloc(&w.d_stats, sizeof(DevStats)));
+        CU(cudaMalloc(&w.ticket, sizeof(unsigned int)));
+        CU(cudaMalloc(&w.events, sizeof(unsigned long long) * EVENT_CAP));
+        CU(cudaMallocHost(&w.h_stats, sizeof(DevStats)));
+        CU(cudaEventCreate(&w.ev_k0));
+        CU(cudaEventCreate(&w.ev_k1));
+    }
+    if (tiles > w.tiles_cap) {
+        cudaFree(w.desc); cudaFree(w.tile_lines); cudaFree(w.tile_base);
+        w.desc = nullptr; w.tile_lines = nullptr; w.tile_base = nullptr;
+        CU(cudaMalloc(&w.desc, sizeof(unsigned long long) * tiles));
+        CU(cudaMalloc(&w.tile_lines, sizeof(uint32_t) * tiles));
+        CU(cudaMalloc(&w.tile_base, sizeof(unsigned long long) * tiles));
+        w.tiles_cap = tiles;
+    }
+    size_t recs = (size_t)grid_for(ctx, tiles) * WARPS_PER_CTA * qcap_for(ctx);
+    if (recs > w.scratch_recs) {
+        cudaFree(w.scratch); w.scratch = nullptr;
+        CU(cudaMalloc(&w.scratch, recs * sizeof(Rec)));
+        w.scratch_recs = recs;
+    }
+    return VCFX_OK;
+}
+
+// enqueue the kernels of one chunk on `st`; results land in w.h_stats after the stream drains
+int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t nbytes,
+                 const vcfx_chunk_info *info, uint8_t *d_out, size_t out_cap) {
+    kernel_fn fn = kernel_for(ctx->cfg.op);
+    if (!fn) return VCFX_E_UNSUPPORTED;
+    uint32_t tiles = tiles_for(ctx, nbytes);
+    CU(cudaMemsetAsync(d_in + nbytes, '\n', 64, st));
+    CU(cudaMemsetAsync(w.desc, 0, sizeof(unsigned long long) * tiles, st));
+    CU(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), st));
+    DevStats init; memset(&init, 0, sizeof init); init.first_short_key = ~0ULL;
+    *w.h_stats = init;
+    CU(cudaMemcpyAsync(w.d_stats, w.h_stats, sizeof(DevStats), cudaMemcpyHostToDevice, st));
+
+    KParams P;
+    P.in = d_in; P.n = nbytes; P.lo = 0; P.hi = nbytes;
+    P.tile_bytes = ctx->tile_bytes; P.n_tiles = tiles;
+    P.mode = ctx->cfg.mode; P.flags = ctx->cfg.flags;
+    P.valid_from = info ? info->data_valid_from : 0;
+    P.is_final = info ? info->is_final : 1;
+    P.out = d_out; P.out_cap = out_cap;
+    P.desc = w.desc; P.tile_lines = w.tile_lines; P.ticket = w.ticket;
+    P.scratch = w.scratch; P.qcap = qcap_for(ctx);
+    P.stats = w.d_stats; P.events = w.events; P.ev_cap = EVENT_CAP;
+
+    CU(cudaEventRecord(w.ev_k0, st));
+    if (nbytes > 0) {
+        int grid = grid_for(ctx, tiles);
+        fn<<<grid, WARPS_PER_CTA * 32, 0, st>>>(P);
+        CU(cudaGetLastError());
+        if (ctx->cfg.op == VCFX_OP_VARIANT_COUNT) {
+            resolve_events_kernel<<<1, 1024, 0, st>>>(w.tile_lines, tiles, w.tile_base, w.events, EVENT_CAP, w.d_stats);
+            CU(cudaGetLastError());
+        }
+    }
+    CU(cudaEventRecord(w.ev_k1, st));
+    CU(cudaMemcpyAsync(w.h_stats, w.d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, st));
+    return VCFX_OK;
+}
+
+void fill_stats(const Work &w, size_t nbytes, vcfx_chunk_stats *s) {
+    if (!s) return;
+    memset(s, 0, sizeof *s);
+    const DevStats &d = *w.h_stats;
+    s->bytes_in = nbytes; s->bytes_out = d.bytes_out;
+    s->lines = d.lines; s->data_lines = d.data_lines; s->rows = d.rows; s->flagged = d.flagged;
+    s->pre_header = d.pre_header; s->short_lines = d.short_lines;
+    s->first_short_line = d.first_short_line; s->n_events = d.n_events;
+    s->dots_terminated = d.dots_terminated; s->last_unterminated_flagged = d.last_unterminated_flagged;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, w.ev_k0, w.ev_k1) == cudaSuccess) s->kernel_ms = ms;
+}
+
+int fetch_events(vcfx_ctx *ctx, const Work &w, cudaStream_t st) {
+    uint64_t nev = std::min<uint64_t>(w.h_stats->n_events, EVENT_CAP);
+    ctx->last_n_events = w.h_stats->n_events;
+    ctx->last_events.resize(nev);
+    if (nev) {
+        CU(cudaMemcpyAsync(ctx->last_events.data(), w.events, nev * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        std::sort(ctx->last_events.begin(), ctx->last_events.end());
+    }
+    return VCFX_OK;
+}
+
+size_t default_out_bytes(int op, size_t chunk) {
+    switch (op) {
+    case VCFX_OP_VARIANT_COUNT: return 4096;
+    case VCFX_OP_MISSING_DETECT: return chunk + chunk / 4 + 4096;
+    case VCFX_OP_ALLELE_COUNT: return 4 * chunk + 4096;
+    default: return chunk / 4 + (1u << 20);      // AF / HWE rows are ~0.3 % of the input
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int vcfx_cuda_abi_version(void) { return VCFX_CUDA_ABI_VERSION; }
+
+int vcfx_cuda_device_count(int *n) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (n) *n = (e == cudaSuccess) ? c : 0;
+    return (e == cudaSuccess && c > 0) ? VCFX_OK : VCFX_E_NO_DEVICE;
+}
+
+const char *vcfx_cuda_strerror(int err) {
+    switch (err) {
+    case VCFX_OK: return "ok";
+    case VCFX_E_INVALID: return "invalid argument or call order";
+    case VCFX_E_NO_DEVICE: return "no usable CUDA device (libvcfx_cuda has no CPU fallback)";
+    case VCFX_E_CUDA: return "CUDA call failed";
+    case VCFX_E_NOMEM: return "out of memory";
+    case VCFX_E_BUSY: return "all pipeline slots in flight";
+    case VCFX_E_EMPTY: return "nothing in flight";
+    case VCFX_E_OUTPUT_TOO_BIG: return "chunk output exceeds the output slot";
+    case VCFX_E_UNSUPPORTED: return "operation not supported";
+    default: return "unknown error";
+    }
+}
+
+const char *vcfx_cuda_last_error(const vcfx_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+int vcfx_cuda_create(const vcfx_cfg *cfg, vcfx_ctx **out) {
+    if (!cfg || !out) return VCFX_E_INVALID;
+    *out = nullptr;
+    if (cfg->op < VCFX_OP_VARIANT_COUNT || cfg->op > VCFX_OP_ALLELE_COUNT) return VCFX_E_INVALID;
+    if (cfg->mode != VCFX_MODE_FILE && cfg->mode != VCFX_MODE_STDIN) return VCFX_E_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return VCFX_E_NO_DEVICE;
+    if (cfg->device < 0 || cfg->device >= ndev) return VCFX_E_INVALID;
+    if (!kernel_for(cfg->op)) return VCFX_E_UNSUPPORTED;
+    vcfx_ctx *ctx = new (std::nothrow) vcfx_ctx();
+    if (!ctx) return VCFX_E_NOMEM;
+    ctx->cfg = *cfg;
+    ctx->device = cfg->device;
+    ctx->chunk_bytes = cfg->chunk_bytes ? cfg->chunk_bytes : DEFAULT_CHUNK;
+    ctx->tile_bytes = cfg->tile_bytes > 0 ? (uint32_t)cfg->tile_bytes : DEFAULT_TILE;
+    ctx->tile_bytes = std::max<uint32_t>(512, (ctx->tile_bytes + 511) & ~511u);
+    ctx->out_bytes = cfg->out_bytes ? cfg->out_bytes : default_out_bytes(cfg->op, ctx->chunk_bytes);
+    ctx->n_slots = cfg->n_slots > 0 ? std::min(cfg->n_slots, MAX_SLOTS) : 3;
+    auto fail = [&](int rc) { std::string e = ctx->last_error; vcfx_cuda_destroy(ctx); (void)e; return rc; };
+#define CUC(call)                                                                        \
+    do {                                                                                 \
+        cudaError_t _e = (call);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            ctx->last_error = std::string(#call) + ": " + cudaGetErrorString(_e);       \
+            return fail(_e == cudaErrorMemoryAllocation ? VCFX_E_NOMEM : VCFX_E_CUDA);   \
+        }                                                                                \
+    } while (0)
+    CUC(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CUC(cudaGetDeviceProperties(&prop, ctx->device));
+    ctx->sm_count = prop.multiProcessorCount;
+    int bps = 1;
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel_for(cfg->op), WARPS_PER_CTA * 32, 0));
+    ctx->blocks_per_sm = std::max(1, bps);
+    if (cfg->stream) { ctx->dev_stream = (cudaStream_t)cfg->stream; ctx->dev_stream_owned = false; }
+    else { CUC(cudaStreamCreateWithFlags(&ctx->dev_stream, cudaStreamNonBlocking)); ctx->dev_stream_owned = true; }
+#undef CUC
+    *out = ctx;
+    return VCFX_OK;
+}
+
+void vcfx_cuda_destroy(vcfx_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < MAX_SLOTS; ++i) {
+        Slot &s = ctx->slots[i];
+        if (s.stream) { cudaStreamSynchronize(s.stream); }
+        if (s.h_in) cudaFreeHost(s.h_in);
+        if (s.h_out) cudaFreeHost(s.h_out);
+        cudaFree(s.d_in); cudaFree(s.d_out);
+        free_work(s.w);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    if (ctx->dev_stream) cudaStreamSynchronize(ctx->dev_stream);
+    free_work(ctx->dev_work);
+    if (ctx->dev_stream_owned && ctx->dev_stream) cudaStreamDestroy(ctx->dev_stream);
+    delete ctx;
+}
+
+static int ensure_slot(vcfx_ctx *ctx, Slot &s) {
+    if (s.h_in) return VCFX_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CU(cudaMallocHost(&s.h_in, ctx->chunk_bytes));
+    CU(cudaMalloc(&s.d_in, ctx->chunk_bytes + VCFX_DEVICE_PAD));
+    CU(cudaMalloc(&s.d_out, ctx->out_bytes));
+    CU(cudaMallocHost(&s.h_out, ctx->out_bytes));
+    return ensure_work(ctx, s.w, ctx->chunk_bytes);
+}
+
+int vcfx_cuda_acquire_input(vcfx_ctx *ctx, char **buf, size_t *cap) {
+    if (!ctx || !buf || !cap) return VCFX_E_INVALID;
+    if (ctx->acquired_slot >= 0) {           // re-acquire returns the same buffer
+        *buf = ctx->slots[ctx->acquired_slot].h_in; *cap = ctx->chunk_bytes; return VCFX_OK;
+    }
+    if (ctx->n_in_flight >= ctx->n_slots) return VCFX_E_BUSY;
+    Slot &s = ctx->slots[ctx->head];
+    int rc = ensure_slot(ctx, s);
+    if (rc != VCFX_OK) return rc;
+    ctx->acquired_slot = ctx->head;
+    *buf = s.h_in; *cap = ctx->chunk_bytes;
+    return VCFX_OK;
+}
+
+int vcfx_cuda_submit(vcfx_ctx *ctx, size_t nbytes, const vcfx_chunk_info *info) {
+    if (!ctx || ctx->acquired_slot < 0 || nbytes > ctx->chunk_bytes) return VCFX_E_INVALID;
+    Slot &s = ctx->slots[ctx->acquired_slot];
+    CU(cudaSetDevice(ctx->device));
+    if (nbytes) CU(cudaMemcpyAsync(s.d_in, s.h_in, nbytes, cudaMemcpyHostToDevice, s.stream));
+    int rc = launch_chunk(ctx, s.w, s.stream, s.d_in, nbytes, info, s.d_out, ctx->out_bytes);
+    if (rc != VCFX_OK) return rc;
+    s.nbytes = nbytes; s.in_flight = true;
+    ctx->acquired_slot = -1;
+    ctx->head = (ctx->head + 1) % ctx->n_slots;
+    ctx->n_in_flight++;
+    return VCFX_OK;
+}
+
+int vcfx_cuda_next_output(vcfx_ctx *ctx, const char **text, size_t *n, vcfx_chunk_stats *stats) {
+    if (!ctx || !text || !n) return VCFX_E_INVALID;
+    if (ctx->n_in_flight == 0) return VCFX_E_EMPTY;
+    Slot &s = ctx->slots[ctx->tail];
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(s.stream));
+    s.in_flight = false;
+    ctx->tail = (ctx->tail + 1) % ctx->n_slots;
+    ctx->n_in_flight--;
+    if (s.w.h_stats->overflow) return VCFX_E_OUTPUT_TOO_BIG;
+    size_t nout = (size_t)s.w.h_stats->bytes_out;
+    if (nout > ctx->out_bytes) return VCFX_E_OUTPUT_TOO_BIG;
+    if (nout) {
+        CU(cudaMemcpyAsync(s.h_out, s.d_out, nout, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaStreamSynchronize(s.stream));
+    }
+    int rc = fetch_events(ctx, s.w, s.stream);
+    if (rc != VCFX_OK) return rc;
+    fill_stats(s.w, s.nbytes, stats);
+    *text = s.h_out; *n = nout;
+    return VCFX_OK;
+}
+
+int vcfx_cuda_in_flight(const vcfx_ctx *ctx) { return ctx ? ctx->n_in_flight : 0; }
+
+int vcfx_cuda_short_lines(vcfx_ctx *ctx, uint64_t *line_no, size_t cap, size_t *n) {
+    if (!ctx || !n) return VCFX_E_INVALID;
+    size_t k = std::min(cap, ctx->last_events.size());
+    if (line_no && k) memcpy(line_no, ctx->last_events.data(), k * sizeof(uint64_t));
+    *n = k;
+    return VCFX_OK;
+}
+
+int vcfx_cuda_run_device(vcfx_ctx *ctx, void *d_in, size_t nbytes, const vcfx_chunk_info *info,
+                         void *d_out, size_t out_cap) {
+    if (!ctx || !d_in || ((uintptr_t)d_in & 15)) return VCFX_E_INVALID;
+    if (ctx->dev_pending) return VCFX_E_BUSY;
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_work(ctx, ctx->dev_work, nbytes);
+    if (rc != VCFX_OK) return rc;
+    rc = launch_chunk(ctx, ctx->dev_work, ctx->dev_stream, (uint8_t *)d_in, nbytes, info, (uint8_t *)d_out, out_cap);
+    if (rc != VCFX_OK) return rc;
+    ctx->dev_pending = true; ctx->dev_nbytes = nbytes;
+    return VCFX_OK;
+}
+
+int vcfx_cuda_sync(vcfx_ctx *ctx, vcfx_chunk_stats *stats) {
+    if (!ctx) return VCFX_E_INVALID;
+    if (!ctx->dev_pending) return VCFX_E_EMPTY;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->dev_stream));
+    ctx->dev_pending = false;
+    int rc = fetch_events(ctx, ctx->dev_work, ctx->dev_stream);
+    if (rc != VCFX_OK) return rc;
+    fill_stats(ctx->dev_work, ctx->dev_nbytes, stats);
+    if (ctx->dev_work.h_stats->overflow) return VCFX_E_OUTPUT_TOO_BIG;
+    return VCFX_OK;
+}
+
+}  // extern "C"
