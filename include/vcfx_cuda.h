@@ -139,6 +139,10 @@ void vcfx_cuda_destroy(vcfx_ctx *ctx);
 int vcfx_cuda_acquire_input(vcfx_ctx *ctx, char **buf, size_t *cap);
 int vcfx_cuda_submit(vcfx_ctx *ctx, size_t nbytes, const vcfx_chunk_info *info);
 int vcfx_cuda_next_output(vcfx_ctx *ctx, const char **text, size_t *n, vcfx_chunk_stats *stats);
+/* submit_host    : like acquire + memcpy + submit, but the chunk is copied to the device straight
+ *                  from the caller's buffer (an mmap'ed/pinned region gives the full PCIe rate).
+ *                  The buffer must stay unchanged until next_output has returned this chunk.   */
+int vcfx_cuda_submit_host(vcfx_ctx *ctx, const void *host, size_t nbytes, const vcfx_chunk_info *info);
 int vcfx_cuda_in_flight(const vcfx_ctx *ctx);
 
 /* 1-based line numbers (inside the chunk last returned by next_output) of lines with too few
@@ -149,8 +153,9 @@ int vcfx_cuda_short_lines(vcfx_ctx *ctx, uint64_t *line_no, size_t cap, size_t *
 /* ---- device-resident path: for callers that already hold the bytes in HBM -----------------
  * d_in must be 16-byte aligned and readable for nbytes + VCFX_DEVICE_PAD bytes (the library
  * writes '\n' into the first 64 bytes of that pad).  d_out receives the text (out_cap bytes).
- * Runs on cfg.stream (or the context's own stream), asynchronously; vcfx_cuda_sync waits and
- * fills stats.  Used by bench.py for the kernel-only figure. */
+ * Runs on cfg.stream (or the context's own stream), asynchronously; calls may be queued back to
+ * back; vcfx_cuda_sync waits and fills stats of the LAST one.  Used by bench.py for the
+ * kernel-only figure. */
 #define VCFX_DEVICE_PAD 4096
 int vcfx_cuda_run_device(vcfx_ctx *ctx, void *d_in, size_t nbytes, const vcfx_chunk_info *info,
                          void *d_out, size_t out_cap);

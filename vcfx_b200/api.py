@@ -58,7 +58,7 @@ class ChunkStats(C.Structure):
 
 EXPORTS = ["vcfx_cuda_abi_version", "vcfx_cuda_device_count", "vcfx_cuda_strerror", "vcfx_cuda_last_error",
            "vcfx_cuda_create", "vcfx_cuda_destroy", "vcfx_cuda_acquire_input", "vcfx_cuda_submit",
-           "vcfx_cuda_next_output", "vcfx_cuda_in_flight", "vcfx_cuda_short_lines",
+           "vcfx_cuda_submit_host", "vcfx_cuda_next_output", "vcfx_cuda_in_flight", "vcfx_cuda_short_lines",
            "vcfx_cuda_run_device", "vcfx_cuda_sync"]
 
 _lib = None
@@ -84,6 +84,7 @@ def load():
         l.vcfx_cuda_destroy.argtypes = [C.c_void_p]
         l.vcfx_cuda_acquire_input.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         l.vcfx_cuda_submit.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(ChunkInfo)]
+        l.vcfx_cuda_submit_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(ChunkInfo)]
         l.vcfx_cuda_next_output.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(ChunkStats)]
         l.vcfx_cuda_in_flight.argtypes = [C.c_void_p]
         l.vcfx_cuda_short_lines.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_size_t, C.POINTER(C.c_size_t)]
@@ -185,6 +186,15 @@ class Context:
     def submit(self, nbytes: int, valid_from: int = 0, is_final: bool = True):
         info = ChunkInfo(valid_from, int(is_final), 0)
         self._check(self._l.vcfx_cuda_submit(self._h, nbytes, C.byref(info)))
+
+    def submit_host(self, host_ptr: int, nbytes: int, valid_from: int = 0, is_final: bool = True) -> bool:
+        """Submit a chunk straight from caller memory; False when every slot is in flight."""
+        info = ChunkInfo(valid_from, int(is_final), 0)
+        rc = self._l.vcfx_cuda_submit_host(self._h, host_ptr, nbytes, C.byref(info))
+        if rc == E_BUSY:
+            return False
+        self._check(rc)
+        return True
 
     def in_flight(self) -> int:
         return self._l.vcfx_cuda_in_flight(self._h)

@@ -21,16 +21,18 @@ constexpr uint32_t EVENT_CAP = 1u << 20;
 constexpr int MAX_SLOTS = 8;
 
 struct Work {                      // device-side bookkeeping for one launch
-    unsigned long long *desc = nullptr;
     uint32_t *tile_lines = nullptr;
+    uint32_t *tile_out = nullptr;
     unsigned long long *tile_base = nullptr;
+    unsigned long long *line_base = nullptr;
     unsigned int *ticket = nullptr;
-    Rec *scratch = nullptr;
+    Rec *recs = nullptr;
+    uint64_t rec_cap = 0;
     DevStats *d_stats = nullptr;
     unsigned long long *events = nullptr;
-    DevStats *h_stats = nullptr;   // pinned
+    DevStats *h_stats = nullptr;   // pinned: results of the last launch
+    DevStats *h_init = nullptr;    // pinned: constant initial value uploaded before every launch
     uint32_t tiles_cap = 0;
-    size_t scratch_recs = 0;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
 };
 
@@ -42,8 +44,9 @@ struct Slot {
     cudaStream_t stream = nullptr;
     Work w;
     size_t nbytes = 0;
+    size_t out_cap = 0;
+    vcfx_chunk_info info = {0, 1, 0};
     bool in_flight = false;
-    bool acquired = false;
 };
 
 }  // namespace
@@ -67,6 +70,9 @@ struct vcfx_ctx {
     bool dev_stream_owned = false;
     bool dev_pending = false;
     size_t dev_nbytes = 0;
+    uint8_t *dev_in = nullptr, *dev_out = nullptr;
+    size_t dev_out_cap = 0;
+    vcfx_chunk_info dev_info = {0, 1, 0};
     // last drained chunk's short-line list
     std::vector<uint64_t> last_events;
     uint64_t last_n_events = 0;
@@ -94,6 +100,13 @@ kernel_fn kernel_for(int op) {
     default: return nullptr;
     }
 }
+kernel_fn format_kernel_for(int op) {
+    switch (op) {
+    case VCFX_OP_ALLELE_FREQ: return format_rows_kernel<OP_AF>;
+    case VCFX_OP_HWE:         return format_rows_kernel<OP_HWE>;
+    default: return nullptr;
+    }
+}
 
 uint32_t tiles_for(const vcfx_ctx *ctx, size_t nbytes) {
     return (uint32_t)std::max<size_t>(1, (nbytes + ctx->tile_bytes - 1) / ctx->tile_bytes);
@@ -105,40 +118,49 @@ int grid_for(const vcfx_ctx *ctx, uint32_t n_tiles) {
     return std::max(1, std::min(resident, need));
 }
 
-uint32_t qcap_for(const vcfx_ctx *ctx) { return ctx->tile_bytes / 11 + 2; }
+// Row records are sized for ordinary VCFs (a row-producing line is at least 11 bytes, real ones
+// are far longer); if a chunk ever has more rows the launch reports overflow and is repeated
+// with the exact count (see relaunch_if_overflow).
+uint64_t default_rec_cap(size_t nbytes) { return nbytes / 48 + 65536; }
 
 void free_work(Work &w) {
-    cudaFree(w.desc); cudaFree(w.tile_lines); cudaFree(w.tile_base); cudaFree(w.ticket);
-    cudaFree(w.scratch); cudaFree(w.d_stats); cudaFree(w.events);
+    cudaFree(w.tile_lines); cudaFree(w.tile_out); cudaFree(w.tile_base); cudaFree(w.line_base);
+    cudaFree(w.ticket); cudaFree(w.recs); cudaFree(w.d_stats); cudaFree(w.events);
     if (w.h_stats) cudaFreeHost(w.h_stats);
+    if (w.h_init) cudaFreeHost(w.h_init);
     if (w.ev_k0) cudaEventDestroy(w.ev_k0);
     if (w.ev_k1) cudaEventDestroy(w.ev_k1);
     w = Work();
 }
 
-int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes) {
+int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes, uint64_t min_recs = 0) {
     uint32_t tiles = tiles_for(ctx, max_bytes);
     if (!w.d_stats) {
         CU(cudaMalloc(&w.d_stats, sizeof(DevStats)));
         CU(cudaMalloc(&w.ticket, sizeof(unsigned int)));
         CU(cudaMalloc(&w.events, sizeof(unsigned long long) * EVENT_CAP));
         CU(cudaMallocHost(&w.h_stats, sizeof(DevStats)));
+        CU(cudaMallocHost(&w.h_init, sizeof(DevStats)));
+        memset(w.h_init, 0, sizeof(DevStats)); w.h_init->first_short_key = ~0ULL;
+        memset(w.h_stats, 0, sizeof(DevStats));
         CU(cudaEventCreate(&w.ev_k0));
         CU(cudaEventCreate(&w.ev_k1));
     }
     if (tiles > w.tiles_cap) {
-        cudaFree(w.desc); cudaFree(w.tile_lines); cudaFree(w.tile_base);
-        w.desc = nullptr; w.tile_lines = nullptr; w.tile_base = nullptr;
-        CU(cudaMalloc(&w.desc, sizeof(unsigned long long) * tiles));
+        cudaFree(w.tile_lines); cudaFree(w.tile_out); cudaFree(w.tile_base); cudaFree(w.line_base);
+        w.tile_lines = w.tile_out = nullptr; w.tile_base = w.line_base = nullptr;
         CU(cudaMalloc(&w.tile_lines, sizeof(uint32_t) * tiles));
+        CU(cudaMalloc(&w.tile_out, sizeof(uint32_t) * tiles));
         CU(cudaMalloc(&w.tile_base, sizeof(unsigned long long) * tiles));
+        CU(cudaMalloc(&w.line_base, sizeof(unsigned long long) * tiles));
         w.tiles_cap = tiles;
     }
-    size_t recs = (size_t)grid_for(ctx, tiles) * WARPS_PER_CTA * qcap_for(ctx);
-    if (recs > w.scratch_recs) {
-        cudaFree(w.scratch); w.scratch = nullptr;
-        CU(cudaMalloc(&w.scratch, recs * sizeof(Rec)));
-        w.scratch_recs = recs;
+    uint64_t recs = 0;
+    if (format_kernel_for(ctx->cfg.op)) recs = std::max<uint64_t>(default_rec_cap(max_bytes), min_recs);
+    if (recs > w.rec_cap) {
+        cudaFree(w.recs); w.recs = nullptr; w.rec_cap = 0;
+        CU(cudaMalloc(&w.recs, recs * sizeof(Rec)));
+        w.rec_cap = recs;
     }
     return VCFX_OK;
 }
@@ -150,21 +172,18 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
     if (!fn) return VCFX_E_UNSUPPORTED;
     uint32_t tiles = tiles_for(ctx, nbytes);
     CU(cudaMemsetAsync(d_in + nbytes, '\n', 64, st));
-    CU(cudaMemsetAsync(w.desc, 0, sizeof(unsigned long long) * tiles, st));
     CU(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), st));
-    DevStats init; memset(&init, 0, sizeof init); init.first_short_key = ~0ULL;
-    *w.h_stats = init;
-    CU(cudaMemcpyAsync(w.d_stats, w.h_stats, sizeof(DevStats), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(w.d_stats, w.h_init, sizeof(DevStats), cudaMemcpyHostToDevice, st));
 
     KParams P;
-    P.in = d_in; P.n = nbytes; P.lo = 0; P.hi = nbytes;
+    P.in = d_in; P.n = nbytes;
     P.tile_bytes = ctx->tile_bytes; P.n_tiles = tiles;
     P.mode = ctx->cfg.mode; P.flags = ctx->cfg.flags;
     P.valid_from = info ? info->data_valid_from : 0;
     P.is_final = info ? info->is_final : 1;
     P.out = d_out; P.out_cap = out_cap;
-    P.desc = w.desc; P.tile_lines = w.tile_lines; P.ticket = w.ticket;
-    P.scratch = w.scratch; P.qcap = qcap_for(ctx);
+    P.tile_lines = w.tile_lines; P.tile_out = w.tile_out; P.tile_base = w.tile_base; P.line_base = w.line_base;
+    P.ticket = w.ticket; P.recs = w.recs; P.rec_cap = w.rec_cap;
     P.stats = w.d_stats; P.events = w.events; P.ev_cap = EVENT_CAP;
 
     CU(cudaEventRecord(w.ev_k0, st));
@@ -172,8 +191,10 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
         int grid = grid_for(ctx, tiles);
         fn<<<grid, WARPS_PER_CTA * 32, 0, st>>>(P);
         CU(cudaGetLastError());
-        if (ctx->cfg.op == VCFX_OP_VARIANT_COUNT) {
-            resolve_events_kernel<<<1, 1024, 0, st>>>(w.tile_lines, tiles, w.tile_base, w.events, EVENT_CAP, w.d_stats);
+        tile_scan_kernel<<<1, 1024, 0, st>>>(P);
+        CU(cudaGetLastError());
+        if (kernel_fn ff = format_kernel_for(ctx->cfg.op)) {
+            ff<<<ctx->sm_count * 4, 256, 0, st>>>(P);
             CU(cudaGetLastError());
         }
     }
@@ -313,6 +334,7 @@ static int ensure_slot(vcfx_ctx *ctx, Slot &s) {
     CU(cudaMalloc(&s.d_in, ctx->chunk_bytes + VCFX_DEVICE_PAD));
     CU(cudaMalloc(&s.d_out, ctx->out_bytes));
     CU(cudaMallocHost(&s.h_out, ctx->out_bytes));
+    s.out_cap = ctx->out_bytes;
     return ensure_work(ctx, s.w, ctx->chunk_bytes);
 }
 
@@ -335,10 +357,28 @@ int vcfx_cuda_submit(vcfx_ctx *ctx, size_t nbytes, const vcfx_chunk_info *info) 
     Slot &s = ctx->slots[ctx->acquired_slot];
     CU(cudaSetDevice(ctx->device));
     if (nbytes) CU(cudaMemcpyAsync(s.d_in, s.h_in, nbytes, cudaMemcpyHostToDevice, s.stream));
-    int rc = launch_chunk(ctx, s.w, s.stream, s.d_in, nbytes, info, s.d_out, ctx->out_bytes);
+    if (info) s.info = *info; else s.info = vcfx_chunk_info{0, 1, 0};
+    int rc = launch_chunk(ctx, s.w, s.stream, s.d_in, nbytes, &s.info, s.d_out, s.out_cap);
     if (rc != VCFX_OK) return rc;
     s.nbytes = nbytes; s.in_flight = true;
     ctx->acquired_slot = -1;
+    ctx->head = (ctx->head + 1) % ctx->n_slots;
+    ctx->n_in_flight++;
+    return VCFX_OK;
+}
+
+int vcfx_cuda_submit_host(vcfx_ctx *ctx, const void *host, size_t nbytes, const vcfx_chunk_info *info) {
+    if (!ctx || (!host && nbytes) || nbytes > ctx->chunk_bytes || ctx->acquired_slot >= 0) return VCFX_E_INVALID;
+    if (ctx->n_in_flight >= ctx->n_slots) return VCFX_E_BUSY;
+    Slot &s = ctx->slots[ctx->head];
+    int rc = ensure_slot(ctx, s);
+    if (rc != VCFX_OK) return rc;
+    CU(cudaSetDevice(ctx->device));
+    if (nbytes) CU(cudaMemcpyAsync(s.d_in, host, nbytes, cudaMemcpyHostToDevice, s.stream));
+    if (info) s.info = *info; else s.info = vcfx_chunk_info{0, 1, 0};
+    rc = launch_chunk(ctx, s.w, s.stream, s.d_in, nbytes, &s.info, s.d_out, s.out_cap);
+    if (rc != VCFX_OK) return rc;
+    s.nbytes = nbytes; s.in_flight = true;
     ctx->head = (ctx->head + 1) % ctx->n_slots;
     ctx->n_in_flight++;
     return VCFX_OK;
@@ -353,9 +393,27 @@ int vcfx_cuda_next_output(vcfx_ctx *ctx, const char **text, size_t *n, vcfx_chun
     s.in_flight = false;
     ctx->tail = (ctx->tail + 1) % ctx->n_slots;
     ctx->n_in_flight--;
+    // A chunk with more rows / more text than the slot was sized for is simply run again with
+    // exact sizes (the input is still on the device).
+    for (int attempt = 0; s.w.h_stats->overflow && attempt < 3; ++attempt) {
+        const unsigned long long ov = s.w.h_stats->overflow;
+        if (ov & 1) {
+            int rc = ensure_work(ctx, s.w, ctx->chunk_bytes, s.w.h_stats->n_recs + 1024);
+            if (rc != VCFX_OK) return rc;
+        }
+        if (ov & 2) {
+            size_t want = (size_t)s.w.h_stats->bytes_out + 4096;
+            cudaFree(s.d_out); cudaFreeHost(s.h_out); s.d_out = nullptr; s.h_out = nullptr; s.out_cap = 0;
+            CU(cudaMalloc(&s.d_out, want));
+            CU(cudaMallocHost(&s.h_out, want));
+            s.out_cap = want;
+        }
+        int rc = launch_chunk(ctx, s.w, s.stream, s.d_in, s.nbytes, &s.info, s.d_out, s.out_cap);
+        if (rc != VCFX_OK) return rc;
+        CU(cudaStreamSynchronize(s.stream));
+    }
     if (s.w.h_stats->overflow) return VCFX_E_OUTPUT_TOO_BIG;
     size_t nout = (size_t)s.w.h_stats->bytes_out;
-    if (nout > ctx->out_bytes) return VCFX_E_OUTPUT_TOO_BIG;
     if (nout) {
         CU(cudaMemcpyAsync(s.h_out, s.d_out, nout, cudaMemcpyDeviceToHost, s.stream));
         CU(cudaStreamSynchronize(s.stream));
@@ -380,11 +438,12 @@ int vcfx_cuda_short_lines(vcfx_ctx *ctx, uint64_t *line_no, size_t cap, size_t *
 int vcfx_cuda_run_device(vcfx_ctx *ctx, void *d_in, size_t nbytes, const vcfx_chunk_info *info,
                          void *d_out, size_t out_cap) {
     if (!ctx || !d_in || ((uintptr_t)d_in & 15)) return VCFX_E_INVALID;
-    if (ctx->dev_pending) return VCFX_E_BUSY;
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_work(ctx, ctx->dev_work, nbytes);
     if (rc != VCFX_OK) return rc;
-    rc = launch_chunk(ctx, ctx->dev_work, ctx->dev_stream, (uint8_t *)d_in, nbytes, info, (uint8_t *)d_out, out_cap);
+    ctx->dev_info = info ? *info : vcfx_chunk_info{0, 1, 0};
+    ctx->dev_in = (uint8_t *)d_in; ctx->dev_out = (uint8_t *)d_out; ctx->dev_out_cap = out_cap;
+    rc = launch_chunk(ctx, ctx->dev_work, ctx->dev_stream, ctx->dev_in, nbytes, &ctx->dev_info, ctx->dev_out, out_cap);
     if (rc != VCFX_OK) return rc;
     ctx->dev_pending = true; ctx->dev_nbytes = nbytes;
     return VCFX_OK;
@@ -396,6 +455,14 @@ int vcfx_cuda_sync(vcfx_ctx *ctx, vcfx_chunk_stats *stats) {
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->dev_stream));
     ctx->dev_pending = false;
+    if (ctx->dev_work.h_stats->overflow & 1) {      // more rows than sized for: run again with the exact count
+        int rc2 = ensure_work(ctx, ctx->dev_work, ctx->dev_nbytes, ctx->dev_work.h_stats->n_recs + 1024);
+        if (rc2 != VCFX_OK) return rc2;
+        rc2 = launch_chunk(ctx, ctx->dev_work, ctx->dev_stream, ctx->dev_in, ctx->dev_nbytes, &ctx->dev_info,
+                           ctx->dev_out, ctx->dev_out_cap);
+        if (rc2 != VCFX_OK) return rc2;
+        CU(cudaStreamSynchronize(ctx->dev_stream));
+    }
     int rc = fetch_events(ctx, ctx->dev_work, ctx->dev_stream);
     if (rc != VCFX_OK) return rc;
     fill_stats(ctx->dev_work, ctx->dev_nbytes, stats);

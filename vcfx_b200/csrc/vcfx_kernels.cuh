@@ -1,20 +1,24 @@
-// vcfx_kernels.cuh — sm_100a kernels of the VCFX hot path (one fused pass over the bytes).
+// vcfx_kernels.cuh — sm_100a kernels of the VCFX hot path.
+//
+// K1  vcfx_scan_kernel<OP>   one fused pass over the bytes: line scan, field location,
+//                            genotype parse, per-variant reduction, row records
+// K2a tile_scan_kernel       exclusive scan of the per-tile output sizes / line counts
+// K2b format_rows_kernel<OP> one thread per row: verbatim CHROM..ALT prefix + number text,
+//                            written at its final, file-ordered offset
 //
 // Decomposition: the chunk is cut into byte tiles of `tile_bytes`; one WARP
 // owns every line that STARTS inside its tile — the reference's own thread-chunking rule
 // (allele_counter.cpp:890-903, missing_detector.cpp:404-422) applied at warp granularity, so
-// a line is always parsed from its first byte by one owner and no cross-tile stitching of
-// parser state exists.  A warp streams its lines in 512-byte windows (16 B per lane, fully
-// coalesced 128-bit loads, next window in flight + L2 prefetch further ahead) and does in
-// that single pass what the reference does in its per-line loops:
-//   stage 1  '\n' / '\t' / '\r' detection by SWAR byte compares + __ballot_sync/__popc
-//   stage 2  tabs 1..9 of the record located with a warp prefix sum; FORMAT -> GT index
-//   stage 3  every sample column parsed by the lane that holds its leading tab, straight
-//            from registers (own 16 B + 4 B look-ahead from the neighbour lane); a lane
-//            whose tabs form the period-4 "d|d\t" lattice takes a branch-free SWAR path
-//   stage 4  warp REDUX of the per-lane tallies; rows are queued per tile, the tile's output
-//            size goes through a decoupled look-back (single-pass chained scan), and the
-//            warp then formats its rows at their final, file-ordered offsets.
+// a line is always parsed from its first byte by one owner and no parser state is stitched
+// across tiles.  A warp streams its lines in 512-byte windows (16 B per lane, coalesced
+// 128-bit loads, the next window already in flight, L2 prefetch further ahead):
+//   stage 1  '\n' and '\t' found with exact SWAR byte compares + __ballot_sync / __popc
+//   stage 2  tabs 1..9 of the record ranked by a warp prefix sum; FORMAT -> GT index
+//   stage 3  samples parsed from registers by the lane holding their leading tab (own 16 B
+//            + 4 B look-ahead from the neighbour lane).  A lane whose bytes are the period-4
+//            "d|d\t" lattice of diploid single-digit calls is verified and tallied with a
+//            dozen integer ops per word and never computes a full delimiter mask.
+//   stage 4  warp REDUX of the tallies -> one 32-byte row record; K2 turns records into text.
 // Tensor cores are not involved: this is byte scanning and integer reduction, HBM-bound.
 #pragma once
 #include <cuda_runtime.h>
@@ -25,16 +29,17 @@ namespace vcfx {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int WARPS_PER_CTA = 8;
-constexpr int WINDOW = 512;
+constexpr uint32_t WINDOW = 512;
 
 enum : int { OP_VC = 0, OP_AF = 1, OP_HWE = 2, OP_MD = 3, OP_AC = 4 };
 enum : int { MODE_FILE = 0, MODE_STDIN = 1 };
 
-struct Rec {                 // one queued output row (32 B)
+struct Rec {                 // one output row (32 B)
+    uint32_t tile;           // owning tile
     uint32_t ls_rel;         // line start - tile start
     uint32_t prefix_len;     // bytes of "CHROM\tPOS\tID\tREF\tALT\t" taken verbatim from the line
-    uint32_t a, b, c, d;     // op-specific integers
-    uint32_t e, f;
+    uint32_t off_in_tile;    // output offset of this row inside its tile's output
+    uint32_t a, b, c, d;     // op-specific integers (AF: alt,total; HWE: homRef,het,homAlt)
 };
 
 struct DevStats {
@@ -44,14 +49,14 @@ struct DevStats {
     unsigned long long dots_terminated;
     unsigned long long last_unterminated_flagged;
     unsigned long long bytes_out;
-    unsigned long long overflow;
-    unsigned long long first_short_line;  // filled by resolve_events_kernel
+    unsigned long long overflow;          // bit 0: row records, bit 1: output bytes
+    unsigned long long first_short_line;  // filled by tile_scan_kernel
+    unsigned long long n_recs;            // rows appended (may exceed rec_cap: then overflow)
 };
 
 struct KParams {
     const uint8_t *in;       // chunk bytes; readable and '\n'-filled for >= 64 B past n
     uint64_t n;              // valid bytes
-    uint64_t lo, hi;         // this launch owns lines starting in [lo, hi)
     uint32_t tile_bytes;
     uint32_t n_tiles;
     int32_t mode;
@@ -60,13 +65,15 @@ struct KParams {
     int32_t is_final;
     uint8_t *out;
     uint64_t out_cap;
-    unsigned long long *desc;    // [n_tiles] look-back descriptors (zeroed before launch)
-    uint32_t *tile_lines;        // [n_tiles] lines started in each tile
-    unsigned int *ticket;        // dynamic tile counter (zeroed before launch)
-    Rec *scratch;                // [resident warps][qcap]
-    uint32_t qcap;
+    uint32_t *tile_lines;            // [n_tiles] lines started in each tile
+    uint32_t *tile_out;              // [n_tiles] output bytes produced by each tile
+    unsigned long long *tile_base;   // [n_tiles] exclusive scan of tile_out (K2a)
+    unsigned long long *line_base;   // [n_tiles] exclusive scan of tile_lines (K2a)
+    unsigned int *ticket;            // dynamic tile counter (zeroed before launch)
+    Rec *recs;
+    uint64_t rec_cap;
     DevStats *stats;
-    unsigned long long *events;  // short-line events (tile << 32 | index in tile)
+    unsigned long long *events;      // short-line events (tile << 32 | index in tile)
     uint32_t ev_cap;
 };
 
@@ -77,56 +84,50 @@ __device__ __forceinline__ uint32_t zero_bytes(uint32_t x) {
     return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
 }
 __device__ __forceinline__ uint32_t eq_bytes(uint32_t w, uint32_t c4) { return zero_bytes(w ^ c4); }
-// bytes below 0x10: '\t' '\n' '\r' live there and nothing else in a well-formed VCF
-__device__ __forceinline__ uint32_t ctrl_bytes(uint32_t w) { return zero_bytes(w & 0xF0F0F0F0u); }
 
-constexpr uint32_t C_TAB = 0x09090909u, C_NL = 0x0A0A0A0Au, C_CR = 0x0D0D0D0Du, C_DOT = 0x2E2E2E2Eu;
+constexpr uint32_t C_TAB = 0x09090909u, C_NL = 0x0A0A0A0Au, C_DOT = 0x2E2E2E2Eu;
 
-// keep only bytes whose absolute position p satisfies lo <= p < hi (word starts at `base`)
-__device__ __forceinline__ uint32_t range_mask(uint64_t base, uint64_t lo, uint64_t hi) {
+// 0x80 in the bytes of a word starting at position `base` that satisfy lo <= pos < hi
+__device__ __forceinline__ uint32_t range_mask(uint32_t base, uint32_t lo, uint32_t hi) {
     uint32_t m = 0x80808080u;
-    if (lo > base) { uint64_t s = lo - base; m = (s >= 4) ? 0u : (m << (8 * (uint32_t)s)); }
-    if (hi < base + 4) { if (hi <= base) m = 0u; else m &= (0x80808080u >> (8 * (uint32_t)(base + 4 - hi))); }
+    if (lo > base) { uint32_t s = lo - base; m = (s >= 4) ? 0u : (m << (8 * s)); }
+    if (hi < base + 4) { m = (hi <= base) ? 0u : (m & (0x80808080u >> (8 * (base + 4 - hi)))); }
     return m;
 }
 
-__device__ __forceinline__ uint4 ld16(const uint8_t *p) {
-    return __ldg(reinterpret_cast<const uint4 *>(p));
-}
-__device__ __forceinline__ uint32_t ldb(const uint8_t *in, uint64_t p) { return (uint32_t)__ldg(in + p); }
-__device__ __forceinline__ void prefetch_l2(const void *p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
+__device__ __forceinline__ uint4 ld16(const uint8_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+__device__ __forceinline__ uint32_t ldb(const uint8_t *p) { return (uint32_t)__ldg(p); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ bool is_dig(uint32_t b) { return (b - 48u) <= 9u; }
 __device__ __forceinline__ bool is_sep(uint32_t b) { return b == '/' || b == '|'; }
 
 // ---------------------------------------------------------------------------------------
-// exact scalar parsers (slow path; byte loads hit L1/L2 because the warp just streamed the line)
+// exact scalar parsers (rare path; the bytes were just streamed by this warp, so L1/L2 hits)
 // ---------------------------------------------------------------------------------------
 
 // allele_freq_calc.cpp:321-337 + 262-293 for the sample column starting at p.  The column ends
 // at the next tab or at the line end; with strip_cr a '\r' directly before the '\n' is not
 // content (:363-364).  The chunk is '\n'-padded past its last byte, so the scan always stops.
-__device__ __noinline__ void af_sample_slow(const uint8_t *in, uint64_t p, bool strip_cr, int gt_index,
+__device__ __noinline__ void af_sample_slow(const uint8_t *p, bool strip_cr, int gt_index,
                                             uint32_t &alt, uint32_t &total) {
-    uint64_t se = p;
-    uint32_t c = ldb(in, se);
-    while (c != '\t' && c != '\n') { ++se; c = ldb(in, se); }
-    if (strip_cr && c == '\n' && se > p && ldb(in, se - 1) == '\r') --se;
+    const uint8_t *se = p;
+    uint32_t c = ldb(se);
+    while (c != '\t' && c != '\n') { ++se; c = ldb(se); }
+    if (strip_cr && c == '\n' && se > p && ldb(se - 1) == '\r') --se;
     for (int i = 0; i < gt_index && p < se; ++i) {
-        while (p < se && ldb(in, p) != ':') ++p;
+        while (p < se && ldb(p) != ':') ++p;
         if (p < se) ++p;
     }
     if (p >= se) return;
-    uint64_t ge = p;
-    while (ge < se && ldb(in, ge) != ':') ++ge;
+    const uint8_t *ge = p;
+    while (ge < se && ldb(ge) != ':') ++ge;
     while (p < ge) {
-        while (p < ge && is_sep(ldb(in, p))) ++p;
+        while (p < ge && is_sep(ldb(p))) ++p;
         if (p >= ge) break;
-        uint64_t q = p; bool numeric = true, zero = true; const uint32_t first = ldb(in, p);
+        const uint8_t *q = p; bool numeric = true, zero = true; const uint32_t first = ldb(p);
         while (q < ge) {
-            uint32_t d = ldb(in, q);
+            uint32_t d = ldb(q);
             if (is_sep(d)) break;
             if (numeric) { if (!is_dig(d)) numeric = false; else if (d != '0') zero = false; }
             ++q;
@@ -137,20 +138,20 @@ __device__ __noinline__ void af_sample_slow(const uint8_t *in, uint64_t p, bool 
 }
 
 // hwe_tester.cpp:339-378 for the sample column starting at p: first ':' piece only.  A '\r'
-// before the '\n' never changes the class (it is neither digit nor separator), so the piece
-// simply ends at ':' / tab / '\n'.
-__device__ __noinline__ int hwe_sample_slow(const uint8_t *in, uint64_t p) {
-    uint64_t e = p;
-    for (;;) { uint32_t c = ldb(in, e); if (c == '\t' || c == ':' || c == '\n') break; ++e; }
-    while (p < e) { uint32_t c = ldb(in, p); if (c == ' ' || c == '\r') ++p; else break; }
+// before the '\n' never changes the class (neither digit nor separator), so the piece simply
+// ends at ':' / tab / '\n'.
+__device__ __noinline__ int hwe_sample_slow(const uint8_t *p) {
+    const uint8_t *e = p;
+    for (;;) { uint32_t c = ldb(e); if (c == '\t' || c == ':' || c == '\n') break; ++e; }
+    while (p < e) { uint32_t c = ldb(p); if (c == ' ' || c == '\r') ++p; else break; }
     if (p >= e) return -1;
-    if (!is_dig(ldb(in, p))) return -1;
+    if (!is_dig(ldb(p))) return -1;
     int a1 = 0, a2 = 0;
-    while (p < e && is_dig(ldb(in, p))) { a1 = (a1 > 1) ? 2 : a1 * 10 + (int)(ldb(in, p) - 48u); ++p; }
-    if (p >= e || !is_sep(ldb(in, p))) return -1;
+    while (p < e && is_dig(ldb(p))) { a1 = (a1 > 1) ? 2 : a1 * 10 + (int)(ldb(p) - 48u); ++p; }
+    if (p >= e || !is_sep(ldb(p))) return -1;
     ++p;
-    if (p >= e || !is_dig(ldb(in, p))) return -1;
-    while (p < e && is_dig(ldb(in, p))) { a2 = (a2 > 1) ? 2 : a2 * 10 + (int)(ldb(in, p) - 48u); ++p; }
+    if (p >= e || !is_dig(ldb(p))) return -1;
+    while (p < e && is_dig(ldb(p))) { a2 = (a2 > 1) ? 2 : a2 * 10 + (int)(ldb(p) - 48u); ++p; }
     if (a1 > 1 || a2 > 1) return -1;       // saturating at 2 keeps ">1" without int overflow
     if (a1 == 0 && a2 == 0) return 0;
     if (a1 == 1 && a2 == 1) return 2;
@@ -158,40 +159,24 @@ __device__ __noinline__ int hwe_sample_slow(const uint8_t *in, uint64_t p) {
 }
 
 // allele_freq_calc.cpp:298-316 on the FORMAT field [p, e)
-__device__ __forceinline__ int gt_index_of(const uint8_t *in, uint64_t p, uint64_t e) {
+__device__ __noinline__ int gt_index_of(const uint8_t *p, const uint8_t *e) {
     int idx = 0;
     while (p < e) {
-        uint64_t q = p;
-        while (q < e && ldb(in, q) != ':') ++q;
-        if (q - p == 2 && ldb(in, p) == 'G' && ldb(in, p + 1) == 'T') return idx;
+        const uint8_t *q = p;
+        while (q < e && ldb(q) != ':') ++q;
+        if (q - p == 2 && ldb(p) == 'G' && ldb(p + 1) == 'T') return idx;
         ++idx;
         p = (q < e) ? q + 1 : q;
     }
     return -1;
 }
 
-// byte index (0..15) of the r-th (0-based) set 0x80-bit over the lane's four mask words
-__device__ __forceinline__ int nth_byte(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3, int r) {
-    uint32_t m[4] = {m0, m1, m2, m3};
-    int pos = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        int c = __popc(m[j]);
-        if (r >= 0 && r < c) {
-            uint32_t x = m[j];
-            for (int i = 0; i < r; ++i) x &= x - 1;
-            pos = 4 * j + ((__ffs(x) - 1) >> 3);
-            r = -1;
-        } else if (r >= 0) r -= c;
-    }
-    return pos;
-}
-// clear the first d set bits over the four words
-__device__ __forceinline__ void drop_first(uint32_t &m0, uint32_t &m1, uint32_t &m2, uint32_t &m3, int d) {
-    while (d > 0 && m0) { m0 &= m0 - 1; --d; }
-    while (d > 0 && m1) { m1 &= m1 - 1; --d; }
-    while (d > 0 && m2) { m2 &= m2 - 1; --d; }
-    while (d > 0 && m3) { m3 &= m3 - 1; --d; }
+// byte index (0..15) of the first set 0x80-bit over the lane's four mask words
+__device__ __forceinline__ int first_byte(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+    if (m0) return (__ffs(m0) - 1) >> 3;
+    if (m1) return 4 + ((__ffs(m1) - 1) >> 3);
+    if (m2) return 8 + ((__ffs(m2) - 1) >> 3);
+    return 12 + ((__ffs(m3) - 1) >> 3);
 }
 
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
@@ -206,20 +191,16 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 struct Tally { uint32_t a, b, c; };   // AF: alt,total   HWE: homRef,het,homAlt
 
 // AF, one sample whose first four bytes are q (b0 = first byte after the leading tab)
-__device__ __forceinline__ void af_sample_reg(uint32_t q, const uint8_t *in, uint64_t pos, bool strip_cr,
-                                              int gt_index, Tally &t) {
+__device__ __forceinline__ void af_sample_reg(uint32_t q, const uint8_t *p, bool strip_cr, int gt_index, Tally &t) {
     uint32_t b0 = q & 0xFF, b1 = (q >> 8) & 0xFF, b2 = (q >> 16) & 0xFF, b3 = q >> 24;
     if (gt_index == 0) {
-        bool term0 = (b0 == '\t' || b0 == ':' || b0 == '\n');
-        if (term0) return;                                   // empty sample / empty GT
-        bool d0 = is_dig(b0), dot0 = (b0 == '.');
-        if (d0 || dot0) {
-            bool term1 = (b1 == '\t' || b1 == ':' || b1 == '\n');
-            if (term1) { if (d0) { t.b++; t.a += (b0 != '0'); } return; }
+        if (b0 == '\t' || b0 == ':' || b0 == '\n') return;   // empty sample / empty GT
+        bool d0 = is_dig(b0);
+        if (d0 || b0 == '.') {
+            if (b1 == '\t' || b1 == ':' || b1 == '\n') { if (d0) { t.b++; t.a += (b0 != '0'); } return; }
             if (is_sep(b1)) {
-                bool d2 = is_dig(b2), dot2 = (b2 == '.');
-                bool term3 = (b3 == '\t' || b3 == ':' || b3 == '\n');
-                if ((d2 || dot2) && term3) {
+                bool d2 = is_dig(b2);
+                if ((d2 || b2 == '.') && (b3 == '\t' || b3 == ':' || b3 == '\n')) {
                     if (d0) { t.b++; t.a += (b0 != '0'); }
                     if (d2) { t.b++; t.a += (b2 != '0'); }
                     return;
@@ -227,131 +208,94 @@ __device__ __forceinline__ void af_sample_reg(uint32_t q, const uint8_t *in, uin
             }
         }
     }
-    af_sample_slow(in, pos, strip_cr, gt_index, t.a, t.b);
+    af_sample_slow(p, strip_cr, gt_index, t.a, t.b);
 }
 
-__device__ __forceinline__ void hwe_sample_reg(uint32_t q, const uint8_t *in, uint64_t pos, Tally &t) {
+__device__ __forceinline__ void hwe_sample_reg(uint32_t q, const uint8_t *p, Tally &t) {
     uint32_t b0 = q & 0xFF, b1 = (q >> 8) & 0xFF, b2 = (q >> 16) & 0xFF, b3 = q >> 24;
     int cls;
     if (!is_dig(b0)) {
-        if (b0 == ' ' || b0 == '\r') cls = hwe_sample_slow(in, pos); else return;
+        if (b0 == ' ' || b0 == '\r') cls = hwe_sample_slow(p); else return;
     } else if (is_sep(b1)) {
         if (!is_dig(b2)) return;
-        if (is_dig(b3)) cls = hwe_sample_slow(in, pos);
+        if (is_dig(b3)) cls = hwe_sample_slow(p);
         else { if (b0 > '1' || b2 > '1') return; cls = (int)(b0 - '0') + (int)(b2 - '0'); }
-    } else if (is_dig(b1)) cls = hwe_sample_slow(in, pos);
+    } else if (is_dig(b1)) cls = hwe_sample_slow(p);
     else return;
     if (cls == 0) t.a++; else if (cls == 1) t.b++; else if (cls == 2) t.c++;
 }
 
-// The lane's sample tabs (sm*) with its 16 bytes (w*) and 4 look-ahead bytes (la).
+// generic: one sample per owned tab (tab masks m0..m3 over the lane's words w0..w3, la = next 4 B)
 template <int OP>
-__device__ __forceinline__ void lane_samples(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t la,
-                                             uint32_t sm0, uint32_t sm1, uint32_t sm2, uint32_t sm3,
-                                             const uint8_t *in, uint64_t pb, bool strip_cr, int gt_index, Tally &t) {
-    if ((sm0 | sm1 | sm2 | sm3) == 0) return;
-    // ---- period-4 lattice: tabs at the same byte of all four words, every sample "d s d"
-    if (sm0 == sm1 && sm1 == sm2 && sm2 == sm3 && (sm0 & (sm0 - 1)) == 0 && gt_index == 0) {
-        uint32_t sh = (uint32_t)(__ffs(sm0));               // 8,16,24,32 = 8*(tab byte + 1)
-        uint32_t x0 = __funnelshift_rc(w0, w1, sh), x1 = __funnelshift_rc(w1, w2, sh);
-        uint32_t x2 = __funnelshift_rc(w2, w3, sh), x3 = __funnelshift_rc(w3, la, sh);
-        // x = [d0, sep, d1, tab]: check tab + separator, then both digits
-        uint32_t bad = 0;
-        uint32_t xs[4] = {x0, x1, x2, x3};
-        uint32_t nz = 0, het = 0, ha = 0, hwe_ok = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint32_t x = xs[j];
-            uint32_t f = x & 0xFF00FF00u;
-            bad |= (uint32_t)((f != 0x09007C00u) & (f != 0x09002F00u));
-            uint32_t v = x & 0x00FF00FFu;                    // the two allele bytes, one per 16-bit lane
-            // digit <=> v >= '0' and not v >= ':'  (bit 8 of v+0xD0 set, bit 8 of v+0xC6 clear; no carry leaves a lane)
-            bad |= ((v + 0x00D000D0u) & ~(v + 0x00C600C6u) & 0x01000100u) ^ 0x01000100u;
-            uint32_t u = v - 0x00300030u;                    // 0..9 per lane when both are digits
-            if (OP == OP_AF) {
-                nz += __popc((u + 0x000F000Fu) & 0x00100010u);
-            } else {
-                uint32_t a = u & 0xFFFFu, b = u >> 16;
-                uint32_t ok = (uint32_t)((a | b) <= 1u);
-                hwe_ok += ok; het += ok & (a ^ b); ha += ok & (a & b);
-            }
-        }
-        if (bad == 0) {
-            if (OP == OP_AF) { t.a += nz; t.b += 8; }
-            else { t.a += hwe_ok - het - ha; t.b += het; t.c += ha; }
-            return;
-        }
-    }
-    // ---- generic: one sample per owned tab
+__device__ __forceinline__ void lane_samples_generic(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t la,
+                                                     uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3,
+                                                     const uint8_t *lane_ptr, bool strip_cr, int gt_index, Tally &t) {
     uint32_t ws[5] = {w0, w1, w2, w3, la};
-    uint32_t sm[4] = {sm0, sm1, sm2, sm3};
+    uint32_t ms[4] = {m0, m1, m2, m3};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        uint32_t m = sm[j];
+        uint32_t m = ms[j];
         while (m) {
             int k = (__ffs(m) - 1) >> 3;
             m &= m - 1;
             uint32_t q = __funnelshift_rc(ws[j], ws[j + 1], 8u * (uint32_t)(k + 1));
-            uint64_t pos = pb + 4 * j + k + 1;
-            if (OP == OP_AF) af_sample_reg(q, in, pos, strip_cr, gt_index, t);
-            else hwe_sample_reg(q, in, pos, t);
+            const uint8_t *p = lane_ptr + 4 * j + k + 1;
+            if (OP == OP_AF) af_sample_reg(q, p, strip_cr, gt_index, t);
+            else hwe_sample_reg(q, p, t);
         }
     }
 }
 
-// ---------------------------------------------------------------------------------------
-// decoupled look-back over per-tile output sizes (status in bits 62..63)
-// ---------------------------------------------------------------------------------------
-constexpr unsigned long long ST_AGG = 1ULL << 62, ST_PFX = 2ULL << 62, ST_MASK = 3ULL << 62;
-
-__device__ __forceinline__ unsigned long long ld_desc(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_desc(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-// returns the exclusive prefix of tile `t` and publishes its inclusive prefix
-__device__ __forceinline__ unsigned long long lookback(unsigned long long *desc, uint32_t t,
-                                                       unsigned long long own, int lane) {
-    if (t == 0) { if (lane == 0) st_desc(desc, ST_PFX | own); return 0; }
-    if (lane == 0) st_desc(desc + t, ST_AGG | own);
-    unsigned long long excl = 0;
-    long long idx = (long long)t - 1;
-    for (;;) {
-        long long my = idx - lane;
-        unsigned long long v;
-        do {
-            v = (my >= 0) ? ld_desc(desc + my) : ST_PFX;
-        } while (__any_sync(FULL, (v & ST_MASK) == 0));
-        unsigned pf = __ballot_sync(FULL, (v & ST_MASK) == ST_PFX);
-        int stop = pf ? (__ffs(pf) - 1) : 32;          // nearest predecessor with a full prefix
-        unsigned long long val = (lane <= stop && lane < 32) ? (v & ~ST_MASK) : 0ULL;
-        if (lane > stop) val = 0;
+// Lattice check of one lane: exactly one tab in word 0 (byte tau) and the 16 bytes after it are
+// four times [digit, '/' or '|', digit, '\t'].  Then the lane's tabs are exactly tau+4j and it
+// owns exactly those four samples; bytes tau+1..15 hold no line end (bytes 0..tau-1 are checked
+// by the caller through the word-0 newline mask).  Tallies are returned packed:
+// AF : count of non-'0' digits (the allele total is 8)
+// HWE: n01 | het << 8 | homAlt << 16   (n01 = samples whose two digits are both 0/1)
+template <int OP>
+__device__ __forceinline__ bool lane_lattice(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t la,
+                                             uint32_t &packed) {
+    uint32_t t0 = eq_bytes(w0, C_TAB);
+    if (t0 == 0 || (t0 & (t0 - 1)) != 0) return false;
+    uint32_t sh = (uint32_t)__ffs(t0);                      // 8,16,24,32 = 8 * (tau + 1)
+    uint32_t xs[4] = {__funnelshift_rc(w0, w1, sh), __funnelshift_rc(w1, w2, sh),
+                      __funnelshift_rc(w2, w3, sh), __funnelshift_rc(w3, la, sh)};
+    uint32_t bad = 0, acc = 0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(FULL, val, o);
-        excl += val;
-        if (pf) break;
-        idx -= 32;
+    for (int j = 0; j < 4; ++j) {
+        uint32_t x = xs[j];                                  // [d0, sep, d1, tab]
+        uint32_t f = x & 0xFF00FF00u;
+        bad |= (uint32_t)((f != 0x09007C00u) & (f != 0x09002F00u));
+        uint32_t v = x & 0x00FF00FFu;                        // the two allele bytes, one per 16-bit half
+        // digit <=> v >= '0' and not v >= ':'  (bit 8 of v+0xD0 set, bit 8 of v+0xC6 clear)
+        bad |= ((v + 0x00D000D0u) & ~(v + 0x00C600C6u) & 0x01000100u) ^ 0x01000100u;
+        if (OP == OP_AF) {
+            acc += (v - 0x00210021u) & 0x00100010u;          // bit 4 / bit 20 set for digits 1..9
+        } else {
+            uint32_t u = v - 0x00300030u;                    // digit values
+            uint32_t a = u & 0xFFFFu, b = u >> 16;
+            uint32_t ok = (uint32_t)((a | b) <= 1u);
+            acc += ok + ((ok & (a ^ b)) << 8) + ((ok & a & b) << 16);
+        }
     }
-    if (lane == 0) st_desc(desc + t, ST_PFX | (excl + own));
-    return excl;
+    if (bad) return false;
+    packed = (OP == OP_AF) ? (((acc >> 4) & 0xFFu) + (acc >> 20)) : acc;
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------
-// the fused scan / parse / reduce / format kernel
+// K1: the fused scan / parse / reduce kernel
 // ---------------------------------------------------------------------------------------
 template <int OP>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 vcfx_scan_kernel(const KParams P) {
+    __shared__ uint32_t s_tp[WARPS_PER_CTA][12];
     const int lane = threadIdx.x & 31;
-    const uint32_t gwarp = blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5);
-    const uint8_t *__restrict__ in = P.in;
+    const int wid = threadIdx.x >> 5;
+    volatile uint32_t *tp = s_tp[wid];
     const uint64_t n = P.n;
     const bool strip_cr = (OP == OP_HWE) || (P.mode == MODE_FILE && (OP == OP_AF || OP == OP_VC || OP == OP_MD));
-    Rec *queue = P.scratch ? P.scratch + (size_t)gwarp * P.qcap : nullptr;
+    constexpr int NEED_TABS = (OP == OP_VC) ? 7 : 9;        // the header phase ends once this many tabs are ranked
 
     unsigned long long s_lines = 0, s_data = 0, s_rows = 0, s_pre = 0, s_short = 0;
 
@@ -361,26 +305,30 @@ vcfx_scan_kernel(const KParams P) {
         tile = __shfl_sync(FULL, tile, 0);
         if (tile >= P.n_tiles) break;
 
-        const uint64_t a = P.lo + (uint64_t)tile * P.tile_bytes;
-        const uint64_t b = min(a + (uint64_t)P.tile_bytes, P.hi);
+        const uint64_t a = (uint64_t)tile * P.tile_bytes;
+        const uint64_t b = min(a + (uint64_t)P.tile_bytes, n);
+        // every position inside the tile's work is a 32-bit offset from a0 (16-aligned, <= a-1)
+        const uint64_t a0 = (a >= 16) ? ((a - 16) & ~(uint64_t)15) : 0;
+        const uint8_t *__restrict__ tin = P.in + a0;
+        const uint32_t ra = (uint32_t)(a - a0), rb = (uint32_t)(b - a0);
 
         // ---- first line start in [a, b): byte 0 of the chunk, or one past a '\n' at >= a-1
-        uint64_t ls;
+        uint32_t ls = rb;                                   // "none"
         if (a == 0) ls = 0;
         else {
-            ls = b;                                       // "none"
-            uint64_t from = a - 1, wb = from & ~(uint64_t)15;
-            while (wb < b - 1 + 0) {
-                uint64_t pb = wb + 16 * lane;
-                uint4 v = ld16(in + pb);
-                uint32_t m0 = eq_bytes(v.x, C_NL) & range_mask(pb, from, b - 1);
-                uint32_t m1 = eq_bytes(v.y, C_NL) & range_mask(pb + 4, from, b - 1);
-                uint32_t m2 = eq_bytes(v.z, C_NL) & range_mask(pb + 8, from, b - 1);
-                uint32_t m3 = eq_bytes(v.w, C_NL) & range_mask(pb + 12, from, b - 1);
+            const uint32_t from = ra - 1, to = rb - 1;      // '\n' positions that give a start < b
+            uint32_t wb = from & ~15u;
+            while (wb < to) {
+                const uint32_t pb = wb + 16 * lane;
+                uint4 v = ld16(tin + pb);
+                uint32_t m0 = eq_bytes(v.x, C_NL) & range_mask(pb, from, to);
+                uint32_t m1 = eq_bytes(v.y, C_NL) & range_mask(pb + 4, from, to);
+                uint32_t m2 = eq_bytes(v.z, C_NL) & range_mask(pb + 8, from, to);
+                uint32_t m3 = eq_bytes(v.w, C_NL) & range_mask(pb + 12, from, to);
                 unsigned bal = __ballot_sync(FULL, (m0 | m1 | m2 | m3) != 0);
                 if (bal) {
                     int src = __ffs(bal) - 1;
-                    int k = nth_byte(m0, m1, m2, m3, 0);
+                    int k = first_byte(m0, m1, m2, m3);
                     k = __shfl_sync(FULL, k, src);
                     ls = wb + 16 * src + k + 1;
                     break;
@@ -389,135 +337,177 @@ vcfx_scan_kernel(const KParams P) {
             }
         }
 
-        uint32_t nrows = 0, nlines = 0;
-        unsigned long long out_bytes = 0;
+        uint32_t nlines = 0, out_bytes = 0;
 
         // ---- every line that starts in the tile
-        while (ls < b && ls < n) {
-            uint64_t wb = ls & ~(uint64_t)15;
-            uint4 cur = ld16(in + wb + 16 * lane);
-            uint4 nxt = ld16(in + wb + WINDOW + 16 * lane);
-            int tabs = 0;                    // tabs seen so far in this line (uniform)
-            uint64_t tp[9];                  // positions of tabs 0..8 (uniform)
-#pragma unroll
-            for (int k = 0; k < 9; ++k) tp[k] = 0;
-            bool hdr_done = false, do_samples = false;
-            int gt_index = -1;
-            Tally tl = {0, 0, 0};
-            uint64_t ee = 0, e = 0;          // content end (CR stripped) and '\n' position
-            const uint32_t first = ldb(in, ls);
-            // lines that need no field work: '#' lines (all ops) — still walked to find '\n'
+        while (ls < rb) {
+            uint32_t wb = ls & ~15u;
+            uint4 cur = ld16(tin + wb + 16 * lane);
+            uint4 nxt = ld16(tin + wb + WINDOW + 16 * lane);
+            const uint32_t first = ldb(tin + ls);
             const bool hash = (first == '#');
+            int tabs = 0;                      // tabs ranked so far (uniform)
+            bool found = false;                // '\n' seen
+            uint32_t e = 0;                    // position of the '\n'
+            Tally tl = {0, 0, 0};
+            int gt_index = -1;
+            bool do_samples = false;
             uint32_t wcount = 0;
 
+            // ================= header phase: rank tabs until NEED_TABS are known or the line ends
+            uint32_t t0, t1, t2, t3;           // tab masks of the current window (this lane)
+            int rank0 = 0;                     // rank inside the line of this lane's first tab
             for (;;) {
-                const uint64_t pb = wb + 16 * lane;
-                if ((wcount & 7) == 0) { uint64_t pf = wb + 8 * WINDOW + 128 * lane; if (pf < n) prefetch_l2(in + pf); }
-                ++wcount;
-                // look-ahead: the 4 bytes after my 16
-                uint32_t la = __shfl_down_sync(FULL, cur.x, 1);
-                uint32_t nx0 = __shfl_sync(FULL, nxt.x, 0);
-                if (lane == 31) la = nx0;
-
-                // ---- stage 1: control bytes
-                uint32_t c0 = ctrl_bytes(cur.x), c1 = ctrl_bytes(cur.y), c2 = ctrl_bytes(cur.z), c3 = ctrl_bytes(cur.w);
-                uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, eol0 = 0, eol1 = 0, eol2 = 0, eol3 = 0;
-                bool eol_is_cr = false;
-                if (c0 | c1 | c2 | c3) {
-                    t0 = eq_bytes(cur.x, C_TAB); t1 = eq_bytes(cur.y, C_TAB);
-                    t2 = eq_bytes(cur.z, C_TAB); t3 = eq_bytes(cur.w, C_TAB);
-                    if ((c0 ^ t0) | (c1 ^ t1) | (c2 ^ t2) | (c3 ^ t3)) {
-                        uint32_t n0 = eq_bytes(cur.x, C_NL), n1 = eq_bytes(cur.y, C_NL);
-                        uint32_t n2 = eq_bytes(cur.z, C_NL), n3 = eq_bytes(cur.w, C_NL);
-                        eol0 = n0; eol1 = n1; eol2 = n2; eol3 = n3;
-                        if (strip_cr) {
-                            // a '\r' directly before '\n' ends the content one byte early
-                            uint32_t r0 = eq_bytes(cur.x, C_CR), r1 = eq_bytes(cur.y, C_CR);
-                            uint32_t r2 = eq_bytes(cur.z, C_CR), r3 = eq_bytes(cur.w, C_CR);
-                            uint32_t nla = eq_bytes(la, C_NL);
-                            r0 &= __funnelshift_r(n0, n1, 8); r1 &= __funnelshift_r(n1, n2, 8);
-                            r2 &= __funnelshift_r(n2, n3, 8); r3 &= __funnelshift_r(n3, nla, 8);
-                            eol0 |= r0; eol1 |= r1; eol2 |= r2; eol3 |= r3;
-                        }
-                    }
+                const uint32_t pb = wb + 16 * lane;
+                t0 = eq_bytes(cur.x, C_TAB); t1 = eq_bytes(cur.y, C_TAB);
+                t2 = eq_bytes(cur.z, C_TAB); t3 = eq_bytes(cur.w, C_TAB);
+                uint32_t n0 = eq_bytes(cur.x, C_NL), n1 = eq_bytes(cur.y, C_NL);
+                uint32_t n2 = eq_bytes(cur.z, C_NL), n3 = eq_bytes(cur.w, C_NL);
+                if (wb < ls) {                 // bytes before the line start (first window only)
+                    uint32_t k0 = range_mask(pb, ls, ~0u), k1 = range_mask(pb + 4, ls, ~0u);
+                    uint32_t k2 = range_mask(pb + 8, ls, ~0u), k3 = range_mask(pb + 12, ls, ~0u);
+                    t0 &= k0; t1 &= k1; t2 &= k2; t3 &= k3; n0 &= k0; n1 &= k1; n2 &= k2; n3 &= k3;
                 }
-                // nothing before the line start counts (first window only)
-                if (wb < ls) {
-                    uint32_t k0 = range_mask(pb, ls, ~0ULL), k1 = range_mask(pb + 4, ls, ~0ULL);
-                    uint32_t k2 = range_mask(pb + 8, ls, ~0ULL), k3 = range_mask(pb + 12, ls, ~0ULL);
-                    t0 &= k0; t1 &= k1; t2 &= k2; t3 &= k3; eol0 &= k0; eol1 &= k1; eol2 &= k2; eol3 &= k3;
-                }
-                unsigned ebal = __ballot_sync(FULL, (eol0 | eol1 | eol2 | eol3) != 0);
-                bool found = ebal != 0;
-                uint64_t hi_clip = wb + WINDOW;
-                if (found) {
+                unsigned ebal = __ballot_sync(FULL, (n0 | n1 | n2 | n3) != 0);
+                if (ebal) {
                     int src = __ffs(ebal) - 1;
-                    int k = nth_byte(eol0, eol1, eol2, eol3, 0);
+                    int k = first_byte(n0, n1, n2, n3);
                     k = __shfl_sync(FULL, k, src);
-                    ee = wb + 16 * src + k;
-                    eol_is_cr = (ldb(in, ee) == '\r');
-                    e = eol_is_cr ? ee + 1 : ee;
-                    hi_clip = ee;
-                    uint32_t k0 = range_mask(pb, 0, ee), k1 = range_mask(pb + 4, 0, ee);
-                    uint32_t k2 = range_mask(pb + 8, 0, ee), k3 = range_mask(pb + 12, 0, ee);
-                    t0 &= k0; t1 &= k1; t2 &= k2; t3 &= k3;
+                    e = wb + 16 * src + k; found = true;
+                    t0 &= range_mask(pb, 0, e); t1 &= range_mask(pb + 4, 0, e);
+                    t2 &= range_mask(pb + 8, 0, e); t3 &= range_mask(pb + 12, 0, e);
                 }
-
+                int total = 0;
                 if (!hash) {
-                    uint32_t s0 = t0, s1 = t1, s2 = t2, s3 = t3;        // sample tabs of this lane
-                    if (!hdr_done) {
-                        // ---- stage 2: rank the tabs of this window, pick out tabs 0..8
-                        int cnt = __popc(t0) + __popc(t1) + __popc(t2) + __popc(t3);
-                        int incl = 0, excl = 0, total;
-                        if (OP == OP_VC) total = (int)__reduce_add_sync(FULL, (unsigned)cnt);
-                        else { incl = warp_incl_scan(cnt, lane); excl = incl - cnt; total = __shfl_sync(FULL, incl, 31); }
-                        if (OP != OP_VC && total > 0) {
+                    int cnt = __popc(t0) + __popc(t1) + __popc(t2) + __popc(t3);
+                    if (OP == OP_VC) total = (int)__reduce_add_sync(FULL, (unsigned)cnt);
+                    else {
+                        int incl = warp_incl_scan(cnt, lane);
+                        total = __shfl_sync(FULL, incl, 31);
+                        rank0 = tabs + incl - cnt;
+                        // publish the positions of tabs 0..8
+                        int rank = rank0;
+                        if (cnt && rank < 9) {
+                            uint32_t ms[4] = {t0, t1, t2, t3};
 #pragma unroll
-                            for (int k = 0; k < 9; ++k) {
-                                int r = k - tabs;
-                                if (r >= 0 && r < total) {
-                                    bool mine = (r >= excl) && (r < incl);
-                                    unsigned bal = __ballot_sync(FULL, mine);
-                                    int owner = __ffs(bal) - 1;
-                                    int byte = mine ? nth_byte(t0, t1, t2, t3, r - excl) : 0;
-                                    byte = __shfl_sync(FULL, byte, owner);
-                                    tp[k] = wb + 16 * owner + byte;
+                            for (int j = 0; j < 4; ++j) {
+                                uint32_t m = ms[j];
+                                while (m && rank < 9) {
+                                    tp[rank++] = pb + 4 * j + ((__ffs(m) - 1) >> 3);
+                                    m &= m - 1;
                                 }
                             }
-                            int drop = 8 - (tabs + excl);
-                            if (drop > 0) drop_first(s0, s1, s2, s3, drop);
                         }
-                        tabs += total;
-                        if (tabs >= 9 && OP != OP_VC) {
-                            hdr_done = true;
-                            // FORMAT = [tp[7]+1, tp[8]); decide whether samples are parsed
-                            if (OP == OP_AF) {
-                                gt_index = gt_index_of(in, tp[7] + 1, tp[8]);
-                                do_samples = gt_index >= 0 && (ls >= P.valid_from);
-                            } else if (OP == OP_HWE) {
-                                bool fmt_ok = (tp[8] - tp[7] - 1 >= 2) && ldb(in, tp[7] + 1) == 'G' && ldb(in, tp[7] + 2) == 'T';
-                                do_samples = fmt_ok;
-                                gt_index = 0;
-                            }
-                        }
-                    }
-                    // ---- stage 3: samples owned by this lane
-                    if (do_samples && (OP == OP_AF || OP == OP_HWE)) {
-                        lane_samples<OP>(cur.x, cur.y, cur.z, cur.w, la, s0, s1, s2, s3, in, pb,
-                                         strip_cr, gt_index, tl);
                     }
                 }
-                (void)hi_clip;
-                if (found) break;
-                wb += WINDOW;
-                cur = nxt;
-                nxt = ld16(in + wb + WINDOW + 16 * lane);
+                tabs += total;
+                if (found || tabs >= NEED_TABS) break;
+                wb += WINDOW; cur = nxt; nxt = ld16(tin + wb + WINDOW + 16 * lane);
+                ++wcount;
             }
-            // ---- end of line: ls .. ee (content) .. e ('\n')
+            __syncwarp();
+
+            // ================= decisions that need only the header
+            if ((OP == OP_AF || OP == OP_HWE) && !hash && tabs >= 9) {
+                const uint32_t fs = tp[7] + 1, fe = tp[8];
+                if (OP == OP_AF) {
+                    if (fe - fs == 2 && ldb(tin + fs) == 'G' && ldb(tin + fs + 1) == 'T') gt_index = 0;
+                    else gt_index = gt_index_of(tin + fs, tin + fe);
+                    do_samples = gt_index >= 0 && (a0 + ls >= P.valid_from);
+                } else {
+                    do_samples = (fe - fs >= 2) && ldb(tin + fs) == 'G' && ldb(tin + fs + 1) == 'T';
+                    gt_index = 0;
+                }
+            }
+
+            // ================= sample phase
+            if ((OP == OP_AF || OP == OP_HWE) && do_samples) {
+                {   // the window in which tab 9 was ranked: generic path on its sample tabs (rank >= 8)
+                    int d = 8 - rank0;                       // tabs of this lane that are still header tabs
+                    while (d > 0 && t0) { t0 &= t0 - 1; --d; }
+                    while (d > 0 && t1) { t1 &= t1 - 1; --d; }
+                    while (d > 0 && t2) { t2 &= t2 - 1; --d; }
+                    while (d > 0 && t3) { t3 &= t3 - 1; --d; }
+                    uint32_t la = __shfl_down_sync(FULL, cur.x, 1);
+                    uint32_t nx0 = __shfl_sync(FULL, nxt.x, 0);
+                    if (lane == 31) la = nx0;
+                    if (t0 | t1 | t2 | t3)
+                        lane_samples_generic<OP>(cur.x, cur.y, cur.z, cur.w, la, t0, t1, t2, t3,
+                                                 tin + wb + 16 * lane, strip_cr, gt_index, tl);
+                }
+                // steady state
+                while (!found) {
+                    wb += WINDOW; cur = nxt; nxt = ld16(tin + wb + WINDOW + 16 * lane);
+                    if ((++wcount & 7) == 0) {
+                        uint64_t pf = a0 + wb + 8 * WINDOW + 128 * lane;
+                        if (pf < n) prefetch_l2(P.in + pf);
+                    }
+                    const uint32_t pb = wb + 16 * lane;
+                    uint32_t la = __shfl_down_sync(FULL, cur.x, 1);
+                    uint32_t nx0 = __shfl_sync(FULL, nxt.x, 0);
+                    if (lane == 31) la = nx0;
+                    uint32_t packed = 0;
+                    uint32_t n0 = eq_bytes(cur.x, C_NL), n1 = 0, n2 = 0, n3 = 0;
+                    const bool good = (gt_index == 0) && (n0 == 0) &&
+                                      lane_lattice<OP>(cur.x, cur.y, cur.z, cur.w, la, packed);
+                    uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+                    if (!good) {
+                        m0 = eq_bytes(cur.x, C_TAB); m1 = eq_bytes(cur.y, C_TAB);
+                        m2 = eq_bytes(cur.z, C_TAB); m3 = eq_bytes(cur.w, C_TAB);
+                        n1 = eq_bytes(cur.y, C_NL); n2 = eq_bytes(cur.z, C_NL); n3 = eq_bytes(cur.w, C_NL);
+                    }
+                    unsigned ebal = __ballot_sync(FULL, (n0 | n1 | n2 | n3) != 0);
+                    bool mine = true;                        // this lane's bytes belong to this line
+                    if (ebal) {
+                        int src = __ffs(ebal) - 1;
+                        int k = first_byte(n0, n1, n2, n3);
+                        k = __shfl_sync(FULL, k, src);
+                        e = wb + 16 * src + k; found = true;
+                        mine = pb < e;                       // a lattice lane holds no '\n': wholly before or after
+                        if (!good) {
+                            m0 &= range_mask(pb, 0, e); m1 &= range_mask(pb + 4, 0, e);
+                            m2 &= range_mask(pb + 8, 0, e); m3 &= range_mask(pb + 12, 0, e);
+                        }
+                    }
+                    if (good) {
+                        if (mine) {
+                            if (OP == OP_AF) { tl.a += packed; tl.b += 8; }
+                            else {
+                                uint32_t n01 = packed & 0xFF, het = (packed >> 8) & 0xFF, ha = packed >> 16;
+                                tl.a += n01 - het - ha; tl.b += het; tl.c += ha;
+                            }
+                        }
+                    } else if (m0 | m1 | m2 | m3) {
+                        lane_samples_generic<OP>(cur.x, cur.y, cur.z, cur.w, la, m0, m1, m2, m3,
+                                                 tin + pb, strip_cr, gt_index, tl);
+                    }
+                }
+            }
+            // ================= no (more) per-sample work: just find the '\n'
+            while (!found) {
+                wb += WINDOW; cur = nxt; nxt = ld16(tin + wb + WINDOW + 16 * lane);
+                if ((++wcount & 7) == 0) {
+                    uint64_t pf = a0 + wb + 8 * WINDOW + 128 * lane;
+                    if (pf < n) prefetch_l2(P.in + pf);
+                }
+                uint32_t n0 = eq_bytes(cur.x, C_NL), n1 = eq_bytes(cur.y, C_NL);
+                uint32_t n2 = eq_bytes(cur.z, C_NL), n3 = eq_bytes(cur.w, C_NL);
+                unsigned ebal = __ballot_sync(FULL, (n0 | n1 | n2 | n3) != 0);
+                if (ebal) {
+                    int src = __ffs(ebal) - 1;
+                    int k = first_byte(n0, n1, n2, n3);
+                    k = __shfl_sync(FULL, k, src);
+                    e = wb + 16 * src + k; found = true;
+                }
+            }
+
+            // ================= end of line: [ls, ee) content, '\n' at e
             ++nlines;
-            const bool empty = (OP == OP_VC) ? (e == ls) : (ee == ls);   // variant_counter tests the raw length (:364)
+            uint32_t ee = e;
+            if (strip_cr && e > ls && ldb(tin + e - 1) == '\r') ee = e - 1;
             if (OP == OP_VC) {
-                if (!empty && !hash) {
+                // variant_counter.cpp:364-380: raw-empty and '#' lines are skipped, >= 7 tabs counts
+                if (e != ls && !hash) {
                     if (tabs >= 7) ++s_rows;
                     else {
                         ++s_short;
@@ -529,99 +519,59 @@ vcfx_scan_kernel(const KParams P) {
                         }
                     }
                 }
-            } else if ((OP == OP_AF || OP == OP_HWE) && !empty && !hash) {
-                uint32_t ra = __reduce_add_sync(FULL, tl.a), rb = __reduce_add_sync(FULL, tl.b);
-                uint32_t rc = (OP == OP_HWE) ? __reduce_add_sync(FULL, tl.c) : 0u;
+            } else if ((OP == OP_AF || OP == OP_HWE) && ee != ls && !hash) {
+                uint32_t ra_ = 0, rb_ = 0, rc_ = 0;
+                if (do_samples) {
+                    ra_ = __reduce_add_sync(FULL, tl.a); rb_ = __reduce_add_sync(FULL, tl.b);
+                    if (OP == OP_HWE) rc_ = __reduce_add_sync(FULL, tl.c);
+                }
                 bool row = false;
-                uint32_t prefix_len = 0;
                 if (OP == OP_AF) {
-                    if (ls < P.valid_from) ++s_pre;
+                    if (a0 + ls < P.valid_from) ++s_pre;                 // allele_freq_calc.cpp:382-386 / 499-502
                     else if (P.mode == MODE_FILE) {
                         ++s_data;
-                        // FORMAT must exist and be non-empty (:396-401), GT must be one of its keys (:413)
-                        if (tabs >= 8) {
-                            uint64_t fs = tp[7] + 1, fe = (tabs >= 9) ? tp[8] : ee;
-                            if (fs < fe) {
-                                if (tabs < 9) gt_index = gt_index_of(in, fs, fe);
-                                row = gt_index >= 0;
-                            }
-                        }
+                        // FORMAT must exist and be non-empty (:396-401) and hold a GT key (:413)
+                        if (tabs >= 9) row = gt_index >= 0;
+                        else if (tabs == 8 && tp[7] + 1 < ee) row = gt_index_of(tin + tp[7] + 1, tin + ee) >= 0;
                     } else {
-                        // stdin: fields = tabs + 1, minus a dropped empty tail (:509-518)
-                        int nf = tabs + ((ldb(in, ee - 1) == '\t') ? 0 : 1);
+                        // stdin: fields = tabs + 1, minus a dropped empty tail (:509-518); < 9 warns (:520-523)
+                        int nf = tabs + ((ldb(tin + ee - 1) == '\t') ? 0 : 1);
                         if (nf < 9) ++s_short;
                         else {
                             ++s_data;
-                            if (tabs < 9) gt_index = gt_index_of(in, tp[7] + 1, ee);
-                            row = gt_index >= 0;
+                            if (tabs >= 9) row = gt_index >= 0;
+                            else row = gt_index_of(tin + tp[7] + 1, tin + ee) >= 0;
                         }
                     }
                 } else {
                     ++s_data;
-                    if (tabs >= 9) {
-                        bool fmt_ok = do_samples;
-                        bool alt_has_comma = false;
-                        for (uint64_t q = tp[3] + 1; q < tp[4]; ++q) alt_has_comma |= (ldb(in, q) == ',');
-                        row = fmt_ok && !alt_has_comma;
-                        if (P.mode == MODE_FILE) {
-                            // CHROM, POS, ALT non-empty (:497) and a non-empty remainder after tab 9 (:516-520)
+                    if (tabs >= 9 && do_samples) {
+                        bool comma = false;                              // hwe_tester.cpp:503 / :586
+                        for (uint32_t q = tp[3] + 1; q < tp[4]; ++q) comma |= (ldb(tin + q) == ',');
+                        row = !comma;
+                        if (P.mode == MODE_FILE)                         // :497 and :516-520
                             row = row && (tp[0] > ls) && (tp[1] > tp[0] + 1) && (tp[4] > tp[3] + 1) && (tp[8] + 1 < ee);
-                        }
                     }
                 }
                 if (row) {
-                    prefix_len = (uint32_t)(tp[4] + 1 - ls);
+                    const uint32_t prefix_len = tp[4] + 1 - ls;
+                    const uint32_t row_len = prefix_len + ((OP == OP_AF) ? 7u : 9u);
                     if (lane == 0) {
-                        if (nrows < P.qcap) {
-                            Rec r; r.ls_rel = (uint32_t)(ls - a); r.prefix_len = prefix_len;
-                            r.a = ra; r.b = rb; r.c = rc; r.d = 0; r.e = 0; r.f = 0;
-                            queue[nrows] = r;
+                        unsigned long long slot = atomicAdd(&P.stats->n_recs, 1ULL);
+                        if (slot < P.rec_cap) {
+                            Rec r; r.tile = tile; r.ls_rel = (uint32_t)(a0 + ls - a); r.prefix_len = prefix_len;
+                            r.off_in_tile = out_bytes; r.a = ra_; r.b = rb_; r.c = rc_; r.d = 0;
+                            P.recs[slot] = r;
                         }
                     }
-                    ++nrows; ++s_rows;
-                    out_bytes += prefix_len + ((OP == OP_AF) ? 7 : 9);
+                    out_bytes += row_len; ++s_rows;
                 }
             }
+            __syncwarp();
             ls = e + 1;
         }
         s_lines += nlines;
-        if (lane == 0) P.tile_lines[tile] = nlines;
-
-        // ---- stage 4: place and write this tile's rows
-        if (OP == OP_AF || OP == OP_HWE) {
-            unsigned long long base = lookback(P.desc, tile, out_bytes, lane);
-            if (tile == P.n_tiles - 1 && lane == 0) P.stats->bytes_out = base + out_bytes;
-            if (nrows > P.qcap || base + out_bytes > P.out_cap) {
-                if (lane == 0) atomicAdd(&P.stats->overflow, 1ULL);
-            } else {
-                __syncwarp();
-                for (uint32_t r0 = 0; r0 < nrows; r0 += 32) {
-                    uint32_t r = r0 + lane;
-                    Rec rec; rec.prefix_len = 0; rec.ls_rel = 0; rec.a = rec.b = rec.c = 0;
-                    uint32_t len = 0;
-                    if (r < nrows) { rec = queue[r]; len = rec.prefix_len + ((OP == OP_AF) ? 7 : 9); }
-                    int incl = warp_incl_scan((int)len, lane);
-                    unsigned long long off = base + (unsigned long long)(incl - (int)len);
-                    if (r < nrows) {
-                        uint8_t *o = P.out + off;
-                        const uint8_t *src = in + a + rec.ls_rel;
-                        for (uint32_t i = 0; i < rec.prefix_len; ++i) o[i] = __ldg(src + i);
-                        o += rec.prefix_len;
-                        char num[24]; int nl;
-                        if (OP == OP_AF) {
-                            double v = af_value(rec.a, rec.b);
-                            nl = (P.mode == MODE_FILE) ? fmt_af_file(v, num) : fmt_af_stdin(v, num);
-                        } else {
-                            double pv = hwe_pvalue((int)rec.a, (int)rec.b, (int)rec.c);
-                            nl = (P.mode == MODE_FILE) ? fmt_p_file(pv, num) : fmt_p_stdin(pv, num);
-                        }
-                        for (int i = 0; i < nl; ++i) o[i] = (uint8_t)num[i];
-                        o[nl] = '\n';
-                    }
-                    base += (unsigned long long)__shfl_sync(FULL, incl, 31);
-                }
-            }
-        }
+        if (lane == 0) { P.tile_lines[tile] = nlines; P.tile_out[tile] = out_bytes; }
     }
     if (lane == 0) {
         if (s_lines) atomicAdd(&P.stats->lines, s_lines);
@@ -632,33 +582,84 @@ vcfx_scan_kernel(const KParams P) {
     }
 }
 
-// Turn (tile, index-in-tile) keys into 1-based line numbers: exclusive scan of the per-tile
-// line counts, one CTA (n_tiles is at most a few hundred thousand).
+// ---------------------------------------------------------------------------------------
+// K2a: exclusive scans over the tiles (output offsets, line numbers), one CTA.
+// Also turns short-line keys (tile, index in tile) into 1-based line numbers.
+// ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
-resolve_events_kernel(const uint32_t *tile_lines, uint32_t n_tiles, unsigned long long *tile_base,
-                      unsigned long long *events, uint32_t ev_cap, DevStats *stats) {
-    __shared__ unsigned long long part[1024];
-    const uint32_t tid = threadIdx.x;
+tile_scan_kernel(const KParams P) {
+    __shared__ unsigned long long part_o[1024], part_l[1024];
+    const uint32_t tid = threadIdx.x, n_tiles = P.n_tiles;
     const uint32_t per = (n_tiles + 1023) / 1024;
-    const uint32_t s = tid * per, e = min(s + per, n_tiles);
-    unsigned long long sum = 0;
-    for (uint32_t i = s; i < e; ++i) sum += tile_lines[i];
-    part[tid] = sum;
+    const uint32_t s = min(tid * per, n_tiles), e = min(s + per, n_tiles);
+    unsigned long long so = 0, sl = 0;
+    for (uint32_t i = s; i < e; ++i) { so += P.tile_out[i]; sl += P.tile_lines[i]; }
+    part_o[tid] = so; part_l[tid] = sl;
     __syncthreads();
-    if (tid == 0) { unsigned long long run = 0; for (int i = 0; i < 1024; ++i) { unsigned long long v = part[i]; part[i] = run; run += v; } }
+    if (tid < 32) {            // warp 0 scans the 1024 partials, 32 per lane
+        unsigned long long lo = 0, ll = 0;
+        for (int i = 0; i < 32; ++i) { lo += part_o[tid * 32 + i]; ll += part_l[tid * 32 + i]; }
+        unsigned long long io = lo, il = ll;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long to = __shfl_up_sync(FULL, io, o), tl2 = __shfl_up_sync(FULL, il, o);
+            if ((int)tid >= o) { io += to; il += tl2; }
+        }
+        unsigned long long ro = io - lo, rl = il - ll;
+        for (int i = 0; i < 32; ++i) {
+            unsigned long long vo = part_o[tid * 32 + i], vl = part_l[tid * 32 + i];
+            part_o[tid * 32 + i] = ro; part_l[tid * 32 + i] = rl; ro += vo; rl += vl;
+        }
+        if (tid == 31) P.stats->bytes_out = io;
+    }
     __syncthreads();
-    unsigned long long run = part[tid];
-    for (uint32_t i = s; i < e; ++i) { tile_base[i] = run; run += tile_lines[i]; }
+    unsigned long long ro = part_o[tid], rl = part_l[tid];
+    for (uint32_t i = s; i < e; ++i) {
+        P.tile_base[i] = ro; P.line_base[i] = rl;
+        ro += P.tile_out[i]; rl += P.tile_lines[i];
+    }
     __syncthreads();
-    unsigned long long nev = stats->n_events;
-    if (nev > ev_cap) nev = ev_cap;
+    unsigned long long nev = P.stats->n_events;
+    if (nev > P.ev_cap) nev = P.ev_cap;
     for (unsigned long long i = tid; i < nev; i += 1024) {
-        unsigned long long k = events[i];
-        events[i] = tile_base[k >> 32] + (k & 0xFFFFFFFFULL) + 1ULL;
+        unsigned long long k = P.events[i];
+        P.events[i] = P.line_base[k >> 32] + (k & 0xFFFFFFFFULL) + 1ULL;
     }
     if (tid == 0) {
-        unsigned long long k = stats->first_short_key;
-        stats->first_short_line = (k == ~0ULL) ? 0ULL : tile_base[k >> 32] + (k & 0xFFFFFFFFULL) + 1ULL;
+        unsigned long long k = P.stats->first_short_key;
+        P.stats->first_short_line = (k == ~0ULL) ? 0ULL : P.line_base[k >> 32] + (k & 0xFFFFFFFFULL) + 1ULL;
+        unsigned long long ov = 0;
+        if (P.stats->n_recs > P.rec_cap) ov |= 1;
+        if (P.stats->bytes_out > P.out_cap) ov |= 2;
+        P.stats->overflow = ov;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K2b: rows -> text.  One thread per row record.
+// ---------------------------------------------------------------------------------------
+template <int OP>
+__global__ void __launch_bounds__(256)
+format_rows_kernel(const KParams P) {
+    if (P.stats->overflow) return;
+    const unsigned long long nrec = P.stats->n_recs;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nrec;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const Rec r = P.recs[i];
+        uint8_t *o = P.out + P.tile_base[r.tile] + r.off_in_tile;
+        const uint8_t *src = P.in + (uint64_t)r.tile * P.tile_bytes + r.ls_rel;
+        for (uint32_t k = 0; k < r.prefix_len; ++k) o[k] = __ldg(src + k);
+        o += r.prefix_len;
+        char num[24]; int nl;
+        if (OP == OP_AF) {
+            double v = af_value(r.a, r.b);
+            nl = (P.mode == MODE_FILE) ? fmt_af_file(v, num) : fmt_af_stdin(v, num);
+        } else {
+            double pv = hwe_pvalue((int)r.a, (int)r.b, (int)r.c);
+            nl = (P.mode == MODE_FILE) ? fmt_p_file(pv, num) : fmt_p_stdin(pv, num);
+        }
+        for (int k = 0; k < nl; ++k) o[k] = (uint8_t)num[k];
+        o[nl] = '\n';
     }
 }
 
