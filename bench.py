@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="vcfx_b200", choices=["vcfx_b200", "reference"])
     ap.add_argument("--variants", type=int, default=C2_VARIANTS, help="variants per GPU (default: full C2)")
+    ap.add_argument("--tile", type=int, default=0, help="tile_bytes for the resident path (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -235,8 +236,8 @@ def main():
     stream = tstream.cuda_stream
     assert stream != 0
 
-    ctx_af = api.Context(api.OP_ALLELE_FREQ, api.FILE, device=local_rank, stream=stream, chunk_bytes=CHUNK)
-    ctx_vc = api.Context(api.OP_VARIANT_COUNT, api.FILE, device=local_rank, stream=stream, chunk_bytes=CHUNK)
+    ctx_af = api.Context(api.OP_ALLELE_FREQ, api.FILE, device=local_rank, stream=stream, chunk_bytes=CHUNK, tile_bytes=args.tile)
+    ctx_vc = api.Context(api.OP_VARIANT_COUNT, api.FILE, device=local_rank, stream=stream, chunk_bytes=CHUNK, tile_bytes=args.tile)
     valid_from = 0 if rank else api.find_chrom_header(hdr)
     totals = torch.zeros(2, dtype=torch.int64, device=dev)
 

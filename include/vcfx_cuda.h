@@ -84,7 +84,8 @@ typedef struct {
     size_t   chunk_bytes;     /* capacity of one pinned input slot (0 = 64 MiB)                 */
     size_t   out_bytes;       /* capacity of one output slot (0 = sized from op and chunk)      */
     int32_t  n_slots;         /* chunks in flight, 1..8 (0 = 3)                                 */
-    int32_t  tile_bytes;      /* bytes of input owned by one warp (0 = 64 KiB; multiple of 512) */
+    int32_t  tile_bytes;      /* bytes of input owned by one warp, multiple of 512 (0 = chosen per
+                                 launch from the chunk size, 32..256 KiB)                       */
     void    *stream;          /* optional cudaStream_t for the device-resident entry point      */
     /* VCFX_OP_ALLELE_COUNT: the selected sample columns, in output order */
     uint32_t        n_sel;          /* number of selected samples                               */

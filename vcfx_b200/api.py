@@ -278,7 +278,8 @@ def stream_bytes(ctx: Context, data, chunk_bytes: int, valid_abs: int = 0):
 
 
 def _run(op: int, data: bytes, mode: int, chunk_bytes: int, flags: int = 0, device: int = 0, **kw):
-    chunk_bytes = chunk_bytes or (64 << 20)
+    # default slot size: the input rounded up to 1 MiB, at most 64 MiB (pinned allocations are not free)
+    chunk_bytes = chunk_bytes or min(64 << 20, max(1 << 20, (len(data) + (1 << 20) - 1) & ~((1 << 20) - 1)))
     with Context(op, mode, device=device, flags=flags, chunk_bytes=chunk_bytes, **kw) as ctx:
         valid_abs = find_chrom_header(data) if op == OP_ALLELE_FREQ else 0
         outs, tot = stream_bytes(ctx, data, chunk_bytes, valid_abs)

@@ -16,7 +16,6 @@ using namespace vcfx;
 namespace {
 
 constexpr size_t DEFAULT_CHUNK = 64u << 20;
-constexpr uint32_t DEFAULT_TILE = 64u << 10;
 constexpr uint32_t EVENT_CAP = 1u << 20;
 constexpr int MAX_SLOTS = 8;
 
@@ -108,8 +107,23 @@ kernel_fn format_kernel_for(int op) {
     }
 }
 
-uint32_t tiles_for(const vcfx_ctx *ctx, size_t nbytes) {
-    return (uint32_t)std::max<size_t>(1, (nbytes + ctx->tile_bytes - 1) / ctx->tile_bytes);
+// Bytes of input owned by one warp.  Larger tiles waste less on the overlap at tile borders (the
+// owner of a tile reads on to the end of its last line, and the next owner scans the same bytes for
+// its first line start); smaller tiles keep every resident warp busy on small chunks.  Aim for about
+// four tiles per resident warp, within [32 KiB, 256 KiB]; cfg.tile_bytes pins it.
+constexpr uint32_t MIN_TILE = 32u << 10, MAX_TILE = 256u << 10;
+
+uint32_t tile_for(const vcfx_ctx *ctx, size_t nbytes) {
+    if (ctx->tile_bytes) return ctx->tile_bytes;
+    size_t warps = (size_t)ctx->sm_count * ctx->blocks_per_sm * WARPS_PER_CTA;
+    size_t t = nbytes / (warps * 4 + 1);
+    t = (t + 511) & ~(size_t)511;
+    return (uint32_t)std::min<size_t>(MAX_TILE, std::max<size_t>(MIN_TILE, t));
+}
+
+uint32_t tiles_for(const vcfx_ctx *ctx, size_t nbytes, uint32_t tile) {
+    (void)ctx;
+    return (uint32_t)std::max<size_t>(1, (nbytes + tile - 1) / tile);
 }
 
 int grid_for(const vcfx_ctx *ctx, uint32_t n_tiles) {
@@ -134,7 +148,8 @@ void free_work(Work &w) {
 }
 
 int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes, uint64_t min_recs = 0) {
-    uint32_t tiles = tiles_for(ctx, max_bytes);
+    // sized for the smallest tile any launch of up to max_bytes can pick
+    uint32_t tiles = tiles_for(ctx, max_bytes, ctx->tile_bytes ? ctx->tile_bytes : MIN_TILE);
     if (!w.d_stats) {
         CU(cudaMalloc(&w.d_stats, sizeof(DevStats)));
         CU(cudaMalloc(&w.ticket, sizeof(unsigned int)));
@@ -170,14 +185,15 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
                  const vcfx_chunk_info *info, uint8_t *d_out, size_t out_cap) {
     kernel_fn fn = kernel_for(ctx->cfg.op);
     if (!fn) return VCFX_E_UNSUPPORTED;
-    uint32_t tiles = tiles_for(ctx, nbytes);
+    const uint32_t tile = tile_for(ctx, nbytes);
+    uint32_t tiles = tiles_for(ctx, nbytes, tile);
     CU(cudaMemsetAsync(d_in + nbytes, '\n', 64, st));
     CU(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), st));
     CU(cudaMemcpyAsync(w.d_stats, w.h_init, sizeof(DevStats), cudaMemcpyHostToDevice, st));
 
     KParams P;
     P.in = d_in; P.n = nbytes;
-    P.tile_bytes = ctx->tile_bytes; P.n_tiles = tiles;
+    P.tile_bytes = tile; P.n_tiles = tiles;
     P.mode = ctx->cfg.mode; P.flags = ctx->cfg.flags;
     P.valid_from = info ? info->data_valid_from : 0;
     P.is_final = info ? info->is_final : 1;
@@ -281,8 +297,7 @@ int vcfx_cuda_create(const vcfx_cfg *cfg, vcfx_ctx **out) {
     ctx->cfg = *cfg;
     ctx->device = cfg->device;
     ctx->chunk_bytes = cfg->chunk_bytes ? cfg->chunk_bytes : DEFAULT_CHUNK;
-    ctx->tile_bytes = cfg->tile_bytes > 0 ? (uint32_t)cfg->tile_bytes : DEFAULT_TILE;
-    ctx->tile_bytes = std::max<uint32_t>(512, (ctx->tile_bytes + 511) & ~511u);
+    ctx->tile_bytes = cfg->tile_bytes > 0 ? std::max<uint32_t>(512, ((uint32_t)cfg->tile_bytes + 511) & ~511u) : 0;   // 0 = per launch
     ctx->out_bytes = cfg->out_bytes ? cfg->out_bytes : default_out_bytes(cfg->op, ctx->chunk_bytes);
     ctx->n_slots = cfg->n_slots > 0 ? std::min(cfg->n_slots, MAX_SLOTS) : 3;
     auto fail = [&](int rc) { std::string e = ctx->last_error; vcfx_cuda_destroy(ctx); (void)e; return rc; };

@@ -109,8 +109,8 @@ __device__ __forceinline__ bool is_sep(uint32_t b) { return b == '/' || b == '|'
 // allele_freq_calc.cpp:321-337 + 262-293 for the sample column starting at p.  The column ends
 // at the next tab or at the line end; with strip_cr a '\r' directly before the '\n' is not
 // content (:363-364).  The chunk is '\n'-padded past its last byte, so the scan always stops.
-__device__ __noinline__ void af_sample_slow(const uint8_t *p, bool strip_cr, int gt_index,
-                                            uint32_t &alt, uint32_t &total) {
+__device__ __noinline__ uint2 af_sample_slow(const uint8_t *p, bool strip_cr, int gt_index) {
+    uint32_t alt = 0, total = 0;
     const uint8_t *se = p;
     uint32_t c = ldb(se);
     while (c != '\t' && c != '\n') { ++se; c = ldb(se); }
@@ -119,7 +119,7 @@ __device__ __noinline__ void af_sample_slow(const uint8_t *p, bool strip_cr, int
         while (p < se && ldb(p) != ':') ++p;
         if (p < se) ++p;
     }
-    if (p >= se) return;
+    if (p >= se) return make_uint2(0u, 0u);
     const uint8_t *ge = p;
     while (ge < se && ldb(ge) != ':') ++ge;
     while (p < ge) {
@@ -135,6 +135,7 @@ __device__ __noinline__ void af_sample_slow(const uint8_t *p, bool strip_cr, int
         if (first != '.' && numeric) { ++total; if (!zero) ++alt; }
         p = q;
     }
+    return make_uint2(alt, total);
 }
 
 // hwe_tester.cpp:339-378 for the sample column starting at p: first ':' piece only.  A '\r'
@@ -191,47 +192,50 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 struct Tally { uint32_t a, b, c; };   // AF: alt,total   HWE: homRef,het,homAlt
 
 // AF, one sample whose first four bytes are q (b0 = first byte after the leading tab)
-__device__ __forceinline__ void af_sample_reg(uint32_t q, const uint8_t *p, bool strip_cr, int gt_index, Tally &t) {
+__device__ __forceinline__ void af_sample_reg(uint32_t q, const uint8_t *p, bool strip_cr, int gt_index,
+                                              uint32_t &alt, uint32_t &total) {
     uint32_t b0 = q & 0xFF, b1 = (q >> 8) & 0xFF, b2 = (q >> 16) & 0xFF, b3 = q >> 24;
     if (gt_index == 0) {
         if (b0 == '\t' || b0 == ':' || b0 == '\n') return;   // empty sample / empty GT
         bool d0 = is_dig(b0);
         if (d0 || b0 == '.') {
-            if (b1 == '\t' || b1 == ':' || b1 == '\n') { if (d0) { t.b++; t.a += (b0 != '0'); } return; }
+            if (b1 == '\t' || b1 == ':' || b1 == '\n') { if (d0) { total++; alt += (b0 != '0'); } return; }
             if (is_sep(b1)) {
                 bool d2 = is_dig(b2);
                 if ((d2 || b2 == '.') && (b3 == '\t' || b3 == ':' || b3 == '\n')) {
-                    if (d0) { t.b++; t.a += (b0 != '0'); }
-                    if (d2) { t.b++; t.a += (b2 != '0'); }
+                    if (d0) { total++; alt += (b0 != '0'); }
+                    if (d2) { total++; alt += (b2 != '0'); }
                     return;
                 }
             }
         }
     }
-    af_sample_slow(p, strip_cr, gt_index, t.a, t.b);
+    uint2 r = af_sample_slow(p, strip_cr, gt_index);
+    alt += r.x; total += r.y;
 }
 
-__device__ __forceinline__ void hwe_sample_reg(uint32_t q, const uint8_t *p, Tally &t) {
+// HWE, same; returns the class (0 homRef, 1 het, 2 homAlt, -1 none)
+__device__ __forceinline__ int hwe_sample_reg(uint32_t q, const uint8_t *p) {
     uint32_t b0 = q & 0xFF, b1 = (q >> 8) & 0xFF, b2 = (q >> 16) & 0xFF, b3 = q >> 24;
-    int cls;
-    if (!is_dig(b0)) {
-        if (b0 == ' ' || b0 == '\r') cls = hwe_sample_slow(p); else return;
-    } else if (is_sep(b1)) {
-        if (!is_dig(b2)) return;
-        if (is_dig(b3)) cls = hwe_sample_slow(p);
-        else { if (b0 > '1' || b2 > '1') return; cls = (int)(b0 - '0') + (int)(b2 - '0'); }
-    } else if (is_dig(b1)) cls = hwe_sample_slow(p);
-    else return;
-    if (cls == 0) t.a++; else if (cls == 1) t.b++; else if (cls == 2) t.c++;
+    if (!is_dig(b0)) return (b0 == ' ' || b0 == '\r') ? hwe_sample_slow(p) : -1;
+    if (is_sep(b1)) {
+        if (!is_dig(b2)) return -1;
+        if (is_dig(b3)) return hwe_sample_slow(p);
+        if (b0 > '1' || b2 > '1') return -1;
+        return (int)(b0 - '0') + (int)(b2 - '0');
+    }
+    return is_dig(b1) ? hwe_sample_slow(p) : -1;
 }
 
-// generic: one sample per owned tab (tab masks m0..m3 over the lane's words w0..w3, la = next 4 B)
+// generic: one sample per owned tab (tab masks m0..m3 over the lane's words w0..w3, la = next 4 B).
+// Kept out of line: it is the rare path and must not cost the lattice path registers.
 template <int OP>
-__device__ __forceinline__ void lane_samples_generic(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t la,
-                                                     uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3,
-                                                     const uint8_t *lane_ptr, bool strip_cr, int gt_index, Tally &t) {
+__device__ __noinline__ uint3 lane_samples_generic(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t la,
+                                                   uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3,
+                                                   const uint8_t *lane_ptr, bool strip_cr, int gt_index) {
     uint32_t ws[5] = {w0, w1, w2, w3, la};
     uint32_t ms[4] = {m0, m1, m2, m3};
+    uint32_t ta = 0, tb = 0, tc = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         uint32_t m = ms[j];
@@ -240,46 +244,66 @@ __device__ __forceinline__ void lane_samples_generic(uint32_t w0, uint32_t w1, u
             m &= m - 1;
             uint32_t q = __funnelshift_rc(ws[j], ws[j + 1], 8u * (uint32_t)(k + 1));
             const uint8_t *p = lane_ptr + 4 * j + k + 1;
-            if (OP == OP_AF) af_sample_reg(q, p, strip_cr, gt_index, t);
-            else hwe_sample_reg(q, p, t);
+            if (OP == OP_AF) af_sample_reg(q, p, strip_cr, gt_index, ta, tb);
+            else { int c = hwe_sample_reg(q, p); ta += (c == 0); tb += (c == 1); tc += (c == 2); }
         }
     }
+    return make_uint3(ta, tb, tc);
 }
 
-// Lattice check of one lane: exactly one tab in word 0 (byte tau) and the 16 bytes after it are
-// four times [digit, '/' or '|', digit, '\t'].  Then the lane's tabs are exactly tau+4j and it
-// owns exactly those four samples; bytes tau+1..15 hold no line end (bytes 0..tau-1 are checked
-// by the caller through the word-0 newline mask).  Tallies are returned packed:
+// Lattice check of one lane, branch-free.  tau = byte of the first tab in word 0; the 16 bytes
+// after it must be four times [digit, '/' or '|', digit, '\t'].  When that holds the lane's tabs
+// are exactly tau+4j, it owns exactly those four diploid single-digit samples, and bytes
+// tau+1..tau+16 hold no line end (bytes 0..tau-1 are vouched for by the previous lane's check or
+// by the caller's word-0 newline mask).  A word-0 without tab, or with a second tab, cannot
+// satisfy the pattern, so no separate test is needed.  Tallies come back packed:
 // AF : count of non-'0' digits (the allele total is 8)
 // HWE: n01 | het << 8 | homAlt << 16   (n01 = samples whose two digits are both 0/1)
 template <int OP>
 __device__ __forceinline__ bool lane_lattice(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t la,
                                              uint32_t &packed) {
-    uint32_t t0 = eq_bytes(w0, C_TAB);
-    if (t0 == 0 || (t0 & (t0 - 1)) != 0) return false;
-    uint32_t sh = (uint32_t)__ffs(t0);                      // 8,16,24,32 = 8 * (tau + 1)
-    uint32_t xs[4] = {__funnelshift_rc(w0, w1, sh), __funnelshift_rc(w1, w2, sh),
-                      __funnelshift_rc(w2, w3, sh), __funnelshift_rc(w3, la, sh)};
+    const uint32_t t0 = eq_bytes(w0, C_TAB);
+    const uint32_t sh = (uint32_t)__ffs(t0);                // 8,16,24,32 = 8 * (tau + 1); 0 when no tab
+    const uint32_t xs[4] = {__funnelshift_rc(w0, w1, sh), __funnelshift_rc(w1, w2, sh),
+                            __funnelshift_rc(w2, w3, sh), __funnelshift_rc(w3, la, sh)};
     uint32_t bad = 0, acc = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        uint32_t x = xs[j];                                  // [d0, sep, d1, tab]
-        uint32_t f = x & 0xFF00FF00u;
-        bad |= (uint32_t)((f != 0x09007C00u) & (f != 0x09002F00u));
-        uint32_t v = x & 0x00FF00FFu;                        // the two allele bytes, one per 16-bit half
-        // digit <=> v >= '0' and not v >= ':'  (bit 8 of v+0xD0 set, bit 8 of v+0xC6 clear)
-        bad |= ((v + 0x00D000D0u) & ~(v + 0x00C600C6u) & 0x01000100u) ^ 0x01000100u;
+        const uint32_t y = xs[j] ^ 0x09300030u;              // [d0-'0', sep, d1-'0', 0] when well formed
+        // tab byte zero, both digit bytes <= 9 (adding 6 must not reach bit 4)
+        bad |= ((y + 0x00060006u) | y) & 0xFFF000F0u;
+        const uint32_t sp = y & 0x0000FF00u;
+        bad |= (uint32_t)((sp != 0x00007C00u) & (sp != 0x00002F00u));
         if (OP == OP_AF) {
-            acc += (v - 0x00210021u) & 0x00100010u;          // bit 4 / bit 20 set for digits 1..9
+            acc += (y + 0x000F000Fu) & 0x00100010u;          // bit 4 / bit 20 set for digits 1..9
         } else {
-            uint32_t u = v - 0x00300030u;                    // digit values
-            uint32_t a = u & 0xFFFFu, b = u >> 16;
-            uint32_t ok = (uint32_t)((a | b) <= 1u);
+            const uint32_t a = y & 0xFFu, b = (y >> 16) & 0xFFu;
+            const uint32_t ok = (uint32_t)((a | b) <= 1u);
             acc += ok + ((ok & (a ^ b)) << 8) + ((ok & a & b) << 16);
         }
     }
-    if (bad) return false;
     packed = (OP == OP_AF) ? (((acc >> 4) & 0xFFu) + (acc >> 20)) : acc;
+    return bad == 0;
+}
+
+// Tier-1 check of one window (warp-uniform phase and separator): every lane's four rotated words
+// must be [0|1, sep, 0|1, tab].  y = x ^ pat is then [a, 0, b, 0] with a, b the allele values.
+// Returns false (and changes nothing) when any lane disagrees.
+template <int OP>
+__device__ __forceinline__ bool t1_eval(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t la,
+                                        uint32_t sh_u, uint32_t pat, uint32_t &accp, uint32_t &hetp, uint32_t &hap) {
+    const uint32_t y0 = __funnelshift_rc(w0, w1, sh_u) ^ pat;
+    const uint32_t y1 = __funnelshift_rc(w1, w2, sh_u) ^ pat;
+    const uint32_t y2 = __funnelshift_rc(w2, w3, sh_u) ^ pat;
+    const uint32_t y3 = __funnelshift_rc(w3, la, sh_u) ^ pat;
+    const uint32_t bad = (y0 | y1 | y2 | y3) & 0xFFFEFFFEu;
+    if (__any_sync(FULL, bad != 0)) return false;
+    if (OP == OP_AF) accp += y0 + y1 + y2 + y3;
+    else {
+        const uint32_t pk = y0 + 2u * y1 + 4u * y2 + 8u * y3;   // a-bits in 0..3, b-bits in 16..19
+        const uint32_t ab = pk & 0xFu, bb = (pk >> 16) & 0xFu;
+        hetp += __popc(ab ^ bb); hap += __popc(ab & bb);
+    }
     return true;
 }
 
@@ -287,7 +311,7 @@ __device__ __forceinline__ bool lane_lattice(uint32_t w0, uint32_t w1, uint32_t 
 // K1: the fused scan / parse / reduce kernel
 // ---------------------------------------------------------------------------------------
 template <int OP>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 vcfx_scan_kernel(const KParams P) {
     __shared__ uint32_t s_tp[WARPS_PER_CTA][12];
     const int lane = threadIdx.x & 31;
@@ -344,12 +368,14 @@ vcfx_scan_kernel(const KParams P) {
             uint32_t wb = ls & ~15u;
             uint4 cur = ld16(tin + wb + 16 * lane);
             uint4 nxt = ld16(tin + wb + WINDOW + 16 * lane);
+            uint4 nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);   // two windows ahead: the look-ahead word of
+                                                                    // lane 31 comes from nxt, which must have landed
             const uint32_t first = ldb(tin + ls);
             const bool hash = (first == '#');
             int tabs = 0;                      // tabs ranked so far (uniform)
             bool found = false;                // '\n' seen
             uint32_t e = 0;                    // position of the '\n'
-            Tally tl = {0, 0, 0};
+            uint32_t ta = 0, tb = 0, tc = 0;   // per-lane tallies (AF: alt,total; HWE: homRef,het,homAlt)
             int gt_index = -1;
             bool do_samples = false;
             uint32_t wcount = 0;
@@ -402,7 +428,7 @@ vcfx_scan_kernel(const KParams P) {
                 }
                 tabs += total;
                 if (found || tabs >= NEED_TABS) break;
-                wb += WINDOW; cur = nxt; nxt = ld16(tin + wb + WINDOW + 16 * lane);
+                wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
                 ++wcount;
             }
             __syncwarp();
@@ -422,70 +448,167 @@ vcfx_scan_kernel(const KParams P) {
 
             // ================= sample phase
             if ((OP == OP_AF || OP == OP_HWE) && do_samples) {
-                {   // the window in which tab 9 was ranked: generic path on its sample tabs (rank >= 8)
-                    int d = 8 - rank0;                       // tabs of this lane that are still header tabs
-                    while (d > 0 && t0) { t0 &= t0 - 1; --d; }
-                    while (d > 0 && t1) { t1 &= t1 - 1; --d; }
-                    while (d > 0 && t2) { t2 &= t2 - 1; --d; }
-                    while (d > 0 && t3) { t3 &= t3 - 1; --d; }
-                    uint32_t la = __shfl_down_sync(FULL, cur.x, 1);
-                    uint32_t nx0 = __shfl_sync(FULL, nxt.x, 0);
-                    if (lane == 31) la = nx0;
-                    if (t0 | t1 | t2 | t3)
-                        lane_samples_generic<OP>(cur.x, cur.y, cur.z, cur.w, la, t0, t1, t2, t3,
-                                                 tin + wb + 16 * lane, strip_cr, gt_index, tl);
-                }
-                // steady state
-                while (!found) {
-                    wb += WINDOW; cur = nxt; nxt = ld16(tin + wb + WINDOW + 16 * lane);
-                    if ((++wcount & 7) == 0) {
-                        uint64_t pf = a0 + wb + 8 * WINDOW + 128 * lane;
-                        if (pf < n) prefetch_l2(P.in + pf);
-                    }
-                    const uint32_t pb = wb + 16 * lane;
-                    uint32_t la = __shfl_down_sync(FULL, cur.x, 1);
-                    uint32_t nx0 = __shfl_sync(FULL, nxt.x, 0);
-                    if (lane == 31) la = nx0;
-                    uint32_t packed = 0;
-                    uint32_t n0 = eq_bytes(cur.x, C_NL), n1 = 0, n2 = 0, n3 = 0;
-                    const bool good = (gt_index == 0) && (n0 == 0) &&
-                                      lane_lattice<OP>(cur.x, cur.y, cur.z, cur.w, la, packed);
-                    uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-                    if (!good) {
-                        m0 = eq_bytes(cur.x, C_TAB); m1 = eq_bytes(cur.y, C_TAB);
-                        m2 = eq_bytes(cur.z, C_TAB); m3 = eq_bytes(cur.w, C_TAB);
-                        n1 = eq_bytes(cur.y, C_NL); n2 = eq_bytes(cur.z, C_NL); n3 = eq_bytes(cur.w, C_NL);
-                    }
-                    unsigned ebal = __ballot_sync(FULL, (n0 | n1 | n2 | n3) != 0);
-                    bool mine = true;                        // this lane's bytes belong to this line
-                    if (ebal) {
-                        int src = __ffs(ebal) - 1;
-                        int k = first_byte(n0, n1, n2, n3);
-                        k = __shfl_sync(FULL, k, src);
-                        e = wb + 16 * src + k; found = true;
-                        mine = pb < e;                       // a lattice lane holds no '\n': wholly before or after
-                        if (!good) {
-                            m0 &= range_mask(pb, 0, e); m1 &= range_mask(pb + 4, 0, e);
-                            m2 &= range_mask(pb + 8, 0, e); m3 &= range_mask(pb + 12, 0, e);
+                bool first_win = true;             // `cur` is the window in which tab 9 was ranked
+                bool prev_ok = false;              // the previous window ended on a verified lattice lane
+                // Tier 1 speculation for the whole line: every sample is "a<sep>b" with a, b in {0,1} and the
+                // separator of the first sample, hence a tab every 4 bytes at a phase (tau) that is the same
+                // in every lane and window.  A window that breaks the pattern anywhere is handed to the exact
+                // path below, so the speculation costs nothing in correctness.
+                const uint32_t tab8 = tp[8];
+                const uint32_t sep0 = ldb(tin + tab8 + 2);
+                const bool t1_on = (gt_index == 0) && (sep0 == '|' || sep0 == '/');
+                const uint32_t tau = tab8 & 3u;
+                const uint32_t sh_u = 8u * (tau + 1u);
+                const uint32_t pat = 0x09300030u | (sep0 << 8);
+                // filler: the bytes "\t0<sep>0" rotated so the tab sits on byte tau of every word — a
+                // well-formed 0/0 sample that adds nothing to the alt / het / homAlt sums
+                const uint32_t fill0 = 0x30003009u | (sep0 << 16);
+                const uint32_t fill = __funnelshift_l(fill0, fill0, 8u * tau);
+                uint32_t accp = 0;                 // packed sums: bits 0..15 first alleles, 16..31 second alleles
+                uint32_t hetp = 0, hap = 0;        // HWE tier-1 tallies
+                uint32_t n_real = 0;               // samples tallied by tier 1 (uniform)
+                const uint8_t *const in_end = P.in + n;
+                for (;;) {
+                    // ---- steady state: raw tier-1 windows, three register sets rotating so that nothing is
+                    // moved: the set just consumed receives the load for three windows ahead
+                    if (t1_on && prev_ok) {
+                        const uint8_t *lp = tin + wb + 16 * lane;
+#define VCFX_T1_STEP(A, B, EXIT)                                                                   \
+                        {                                                                          \
+                            uint32_t la_ = __shfl_down_sync(FULL, A.x, 1);                         \
+                            const uint32_t nx_ = __shfl_sync(FULL, B.x, 0);                        \
+                            if (lane == 31) la_ = nx_;                                             \
+                            if (!t1_eval<OP>(A.x, A.y, A.z, A.w, la_, sh_u, pat, accp, hetp, hap)) goto EXIT; \
+                            n_real += 128; wb += WINDOW;                                           \
+                            A = ld16(lp + 3 * WINDOW); lp += WINDOW;                               \
                         }
-                    }
-                    if (good) {
-                        if (mine) {
-                            if (OP == OP_AF) { tl.a += packed; tl.b += 8; }
-                            else {
-                                uint32_t n01 = packed & 0xFF, het = (packed >> 8) & 0xFF, ha = packed >> 16;
-                                tl.a += n01 - het - ha; tl.b += het; tl.c += ha;
+                        for (;;) {
+                            VCFX_T1_STEP(cur, nxt, t1_exit0)
+                            VCFX_T1_STEP(nxt, nx2, t1_exit1)
+                            VCFX_T1_STEP(nx2, cur, t1_exit2)
+                            wcount += 3;
+                            if (lane < 12) {                     // pull the next 1.5 KB into L2, 6 KB ahead
+                                const uint8_t *pf = lp - 16 * lane + 12 * WINDOW + 128 * lane;
+                                if (pf < in_end) prefetch_l2(pf);
+                            }
+                            if (OP == OP_AF && wcount >= 12000) {   // keep the 16-bit packed sums from overflowing
+                                ta += (accp & 0xFFFFu) + (accp >> 16); accp = 0; wcount = 0;
                             }
                         }
-                    } else if (m0 | m1 | m2 | m3) {
-                        lane_samples_generic<OP>(cur.x, cur.y, cur.z, cur.w, la, m0, m1, m2, m3,
-                                                 tin + pb, strip_cr, gt_index, tl);
+#undef VCFX_T1_STEP
+                    t1_exit1: { const uint4 t_ = cur; cur = nxt; nxt = nx2; nx2 = t_; } goto t1_exit0;
+                    t1_exit2: { const uint4 t_ = nx2; nx2 = nxt; nxt = cur; cur = t_; }
+                    t1_exit0: ;
                     }
+                    // ---- this window needs a closer look
+                    const uint32_t pb = wb + 16 * lane;
+                    uint32_t la = __shfl_down_sync(FULL, cur.x, 1);
+                    const uint32_t nx0 = __shfl_sync(FULL, nxt.x, 0);
+                    if (lane == 31) la = nx0;
+                    bool done = false, nl_done = false;
+                    if (!done && t1_on && (first_win || prev_ok)) {
+                        // Perhaps only the two ends of the sample region are in the way: the header up to tab 9
+                        // (first window) and everything from the '\n' on (last window).  Overwrite those bytes
+                        // with filler and try again; the filler samples are not counted.  (Past the first window
+                        // this needs prev_ok: lane 0's bytes before its first tab are vouched for by the window before.)
+                        if (!first_win) {
+                            const uint32_t n0 = eq_bytes(cur.x, C_NL), n1 = eq_bytes(cur.y, C_NL);
+                            const uint32_t n2 = eq_bytes(cur.z, C_NL), n3 = eq_bytes(cur.w, C_NL);
+                            const unsigned ebal = __ballot_sync(FULL, (n0 | n1 | n2 | n3) != 0);
+                            nl_done = true;
+                            if (ebal) {
+                                const int src = __ffs(ebal) - 1;
+                                int k = first_byte(n0, n1, n2, n3);
+                                k = __shfl_sync(FULL, k, src);
+                                e = wb + 16 * src + k; found = true;
+                            }
+                        }
+                        // the '\n' must sit where the lattice expects a tab, or the filler would complete a
+                        // truncated last sample ("1\n" would read "1|0")
+                        if ((first_win || found) && (!found || ((e - tau) & 3u) == 0)) {
+                            const uint32_t lo = first_win ? tab8 : 0u, hi = found ? e : ~0u;
+                            const uint32_t k0 = (range_mask(pb, lo, hi) >> 7) * 0xFFu, k1 = (range_mask(pb + 4, lo, hi) >> 7) * 0xFFu;
+                            const uint32_t k2 = (range_mask(pb + 8, lo, hi) >> 7) * 0xFFu, k3 = (range_mask(pb + 12, lo, hi) >> 7) * 0xFFu;
+                            const uint32_t k4 = (range_mask(pb + 16, lo, hi) >> 7) * 0xFFu;
+                            done = t1_eval<OP>((cur.x & k0) | (fill & ~k0), (cur.y & k1) | (fill & ~k1),
+                                               (cur.z & k2) | (fill & ~k2), (cur.w & k3) | (fill & ~k3),
+                                               (la & k4) | (fill & ~k4), sh_u, pat, accp, hetp, hap);
+                            if (done) {
+                                // real samples of this window: leading tabs at positions = tau (mod 4) in [A, B)
+                                const int A = (int)max(lo, wb), B = (int)min(hi, wb + WINDOW);
+                                const int t = (int)tau;
+                                n_real += (uint32_t)(max(0, (B + 3 - t) >> 2) - max(0, (A + 3 - t) >> 2));
+                            }
+                        }
+                    }
+                    unsigned gbal = FULL;                       // lanes that passed a lattice check
+                    if (!done) {
+                        // exact path for this window
+                        uint32_t packed = 0;
+                        const bool lat = lane_lattice<OP>(cur.x, cur.y, cur.z, cur.w, la, packed) && (gt_index == 0);
+                        gbal = __ballot_sync(FULL, lat);
+                        uint32_t m0, m1, m2, m3;
+                        const uint32_t n0 = eq_bytes(cur.x, C_NL);
+                        if (first_win) { m0 = t0; m1 = t1; m2 = t2; m3 = t3; }   // already clipped to [ls, e)
+                        else {
+                            m0 = eq_bytes(cur.x, C_TAB); m1 = eq_bytes(cur.y, C_TAB);
+                            m2 = eq_bytes(cur.z, C_TAB); m3 = eq_bytes(cur.w, C_TAB);
+                            if (!nl_done) {
+                                const uint32_t n1 = eq_bytes(cur.y, C_NL), n2 = eq_bytes(cur.z, C_NL), n3 = eq_bytes(cur.w, C_NL);
+                                const unsigned ebal = __ballot_sync(FULL, (n0 | n1 | n2 | n3) != 0);
+                                if (ebal) {
+                                    const int src = __ffs(ebal) - 1;
+                                    int k = first_byte(n0, n1, n2, n3);
+                                    k = __shfl_sync(FULL, k, src);
+                                    e = wb + 16 * src + k; found = true;
+                                }
+                            }
+                            if (found) {
+                                m0 &= range_mask(pb, 0, e); m1 &= range_mask(pb + 4, 0, e);
+                                m2 &= range_mask(pb + 8, 0, e); m3 &= range_mask(pb + 12, 0, e);
+                            }
+                        }
+                        // a lattice lane may be used when its bytes before the first tab are vouched for
+                        // (previous lane lattice, or no '\n' in word 0) and all its tabs are sample tabs
+                        bool pg = __shfl_up_sync(FULL, (int)lat, 1) != 0;
+                        if (lane == 0) pg = prev_ok;
+                        const bool use_lat = lat && (pg || n0 == 0) && !(first_win && rank0 < 8);
+                        if (use_lat) {
+                            if (!found || pb < e) {          // a vouched lattice lane holds no '\n'
+                                if (OP == OP_AF) { ta += packed; tb += 8; }
+                                else {
+                                    const uint32_t het = (packed >> 8) & 0xFF, ha = packed >> 16;
+                                    ta += (packed & 0xFF) - het - ha; tb += het; tc += ha;
+                                }
+                            }
+                        } else {
+                            if (first_win) {                 // drop the tabs that still belong to the header
+                                int d = 8 - rank0;
+                                while (d > 0 && m0) { m0 &= m0 - 1; --d; }
+                                while (d > 0 && m1) { m1 &= m1 - 1; --d; }
+                                while (d > 0 && m2) { m2 &= m2 - 1; --d; }
+                                while (d > 0 && m3) { m3 &= m3 - 1; --d; }
+                            }
+                            if (m0 | m1 | m2 | m3) {
+                                const uint3 r = lane_samples_generic<OP>(cur.x, cur.y, cur.z, cur.w, la, m0, m1, m2, m3,
+                                                                         tin + pb, strip_cr, gt_index);
+                                ta += r.x; tb += r.y; tc += r.z;
+                            }
+                        }
+                    }
+                    if (found) break;
+                    prev_ok = (gbal >> 31) != 0;
+                    first_win = false;
+                    wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
+                    if (OP == OP_AF && ++wcount >= 12000) { ta += (accp & 0xFFFFu) + (accp >> 16); accp = 0; wcount = 0; }
                 }
+                // fold the tier-1 tallies in (n_real is uniform: lane 0 carries it)
+                if (OP == OP_AF) { ta += (accp & 0xFFFFu) + (accp >> 16); if (lane == 0) tb += 2u * n_real; }
+                else { ta -= hetp + hap; if (lane == 0) ta += n_real; tb += hetp; tc += hap; }
             }
             // ================= no (more) per-sample work: just find the '\n'
             while (!found) {
-                wb += WINDOW; cur = nxt; nxt = ld16(tin + wb + WINDOW + 16 * lane);
+                wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
                 if ((++wcount & 7) == 0) {
                     uint64_t pf = a0 + wb + 8 * WINDOW + 128 * lane;
                     if (pf < n) prefetch_l2(P.in + pf);
@@ -522,8 +645,8 @@ vcfx_scan_kernel(const KParams P) {
             } else if ((OP == OP_AF || OP == OP_HWE) && ee != ls && !hash) {
                 uint32_t ra_ = 0, rb_ = 0, rc_ = 0;
                 if (do_samples) {
-                    ra_ = __reduce_add_sync(FULL, tl.a); rb_ = __reduce_add_sync(FULL, tl.b);
-                    if (OP == OP_HWE) rc_ = __reduce_add_sync(FULL, tl.c);
+                    ra_ = __reduce_add_sync(FULL, ta); rb_ = __reduce_add_sync(FULL, tb);
+                    if (OP == OP_HWE) rc_ = __reduce_add_sync(FULL, tc);
                 }
                 bool row = false;
                 if (OP == OP_AF) {
