@@ -20,7 +20,7 @@ def _cmp(name, got, exp):
                              f"  got {got[max(0, i - 60): i + 60]!r}\n  exp {exp[max(0, i - 60): i + 60]!r}")
 
 
-def run_all(api, O, data, tag, chunk_bytes=0, tile_bytes=0, tools=("af", "hwe", "vc")):
+def run_all(api, O, data, tag, chunk_bytes=0, tile_bytes=0, tools=("af", "hwe", "vc", "md")):
     kw = dict(chunk_bytes=chunk_bytes, tile_bytes=tile_bytes)
     for mode in MODES:
         if "af" in tools:
@@ -33,6 +33,11 @@ def run_all(api, O, data, tag, chunk_bytes=0, tile_bytes=0, tools=("af", "hwe", 
         if "hwe" in tools:
             r = api.hwe_tester(data, mode, **kw); o = O.hwe(data, mode)
             _cmp(f"{tag} hwe mode{mode}", r.out, o.out)
+        if "md" in tools and not (mode == 0 and max((len(l) for l in data.split(b"\n")), default=0) > 60000):
+            # (FILE mode of the reference overflows its 64 KB line buffer on longer lines: no oracle there)
+            r = api.missing_detector(data, mode, **kw); o = O.missing(data, mode)
+            _cmp(f"{tag} md mode{mode}", r.out, o.out)
+            assert r.totals.flagged == o.flagged or (mode == 0 and r.totals.dots_terminated == 0)
         if "vc" in tools:
             for strict in (False, True):
                 r = api.variant_counter(data, mode, strict, **kw); o = O.variant_count(data, mode, strict)
@@ -84,3 +89,23 @@ def test_empty_and_degenerate(cuda_api, oracle):
                  b"#CHROM\n\t\t\t\t\t\t\t\tGT", b"#CHROM\n1\t1\t.\tA\tG\t.\t.\t.\tGT\t0/1\r\n",
                  b"#CHROM\n1\t1\t.\tA\tG\t.\t.\t.\tGT\t\n", b"#CHROM\n1\t1\t.\tA\tG\t.\t.\t.\tGT\t0/1\t"):
         run_all(cuda_api, oracle, data, repr(data[:20]))
+
+
+def test_missing_detector_cases(cuda_api, oracle):
+    H = b"##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS1\tS2\n"
+    L = lambda info, s1, s2: b"1\t100\t.\tA\tG\t.\tPASS\t" + info + b"\tGT:DP\t" + s1 + b"\t" + s2
+    cases = [
+        H + L(b"DP=25", b"0/1:3", b"./.:0") + b"\n",
+        H + L(b"DP=25;", b"0/1:3", b".") + b"\n",
+        H + L(b".", b".|.", b"0/0") + b"\n" + L(b"", b"0/.", b"1/1") + b"\n",
+        H + L(b"AF=0.5", b"0/1:0.5", b"1/1:.") + b"\n",                # dots outside the first piece only
+        H + L(b"DP=1", b"0/1", b"0/.") ,                                  # unterminated + flagged, only dot (pre-scan quirk)
+        H + L(b"DP=1", b"./.", b"0/0") + b"\n" + L(b"DP=2", b"0/1", b"0/.") ,   # ... with another dotted line before it
+        H + L(b"DP=1", b"0/1", b"0/0") + b"\r\n" + L(b"DP=2", b"0.", b"./1") + b"\r\n",
+        H + L(b"DP=1", b"0.5", b"1.5") + b"\n" + L(b"DP=1", b"0/1:.", b".:1") + b"\n",
+        H + b"1\t100\t.\tA\tG\t.\tPASS\tDP=3\tGT\n" + b"1\t100\t.\tA\tG\t.\tPASS\tDP=3\tGT\t\n" + b"\n#x\t.\n",
+        H + L(b"DP=1", b"0/1", b"0/1").replace(b"0/1\t0/1", b"0/1\t\t.\t") + b"\n",
+    ]
+    for i, data in enumerate(cases):
+        run_all(cuda_api, oracle, data, f"mdcase{i}", tools=("md",))
+        run_all(cuda_api, oracle, data, f"mdcase{i}-tile512", tile_bytes=512, tools=("md",))

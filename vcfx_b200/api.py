@@ -307,6 +307,34 @@ def hwe_tester(data: bytes, mode: int = FILE, chunk_bytes: int = 0, **kw) -> Too
     return ToolResult(HWE_HEADER + body, 0, tot)
 
 
+def first_data_offset(data) -> int:
+    """Offset of the first line that does not start with '#': the end of the leading header block
+    (missing_detector.cpp:378-383 starts its pre-scan there)."""
+    pos = 0
+    n = len(data)
+    while pos < n and data[pos:pos + 1] == b"#":
+        nl = data.find(b"\n", pos)
+        if nl < 0:
+            return n
+        pos = nl + 1
+    return pos
+
+
+def missing_detector(data: bytes, mode: int = FILE, chunk_bytes: int = 0, **kw) -> ToolResult:
+    chunk_bytes = chunk_bytes or min(64 << 20, max(1 << 20, (len(data) + (1 << 20) - 1) & ~((1 << 20) - 1)))
+    with Context(OP_MISSING_DETECT, mode, chunk_bytes=chunk_bytes, **kw) as ctx:
+        outs, tot = stream_bytes(ctx, data, chunk_bytes, first_data_offset(data))
+    if mode == FILE and tot.last_unterminated_flagged and tot.dots_terminated == 0:
+        # The reference's pre-scan ignores an unterminated last line (missing_detector.cpp:354): when
+        # no other line has a '.' in its sample columns it copies the file verbatim, so that last
+        # line stays as it was.
+        body = b"".join(outs)
+        cut = len(body) - tot.last_unterminated_flagged
+        last = data[data.rfind(b"\n") + 1:]
+        return ToolResult(body[:cut] + last, 0, tot)
+    return ToolResult(b"".join(outs), 0, tot)
+
+
 def variant_counter(data: bytes, mode: int = FILE, strict: bool = False, chunk_bytes: int = 0, **kw) -> ToolResult:
     _, tot = _run(OP_VARIANT_COUNT, data, mode, chunk_bytes, **kw)
     if strict and tot.short_lines:                # variant_counter.cpp:373-377, 175-177

@@ -24,6 +24,7 @@ struct Work {                      // device-side bookkeeping for one launch
     uint32_t *tile_out = nullptr;
     unsigned long long *tile_base = nullptr;
     unsigned long long *line_base = nullptr;
+    uint32_t *tail_start = nullptr, *tail_len = nullptr, *tail_off = nullptr;   // MISSING_DETECT
     unsigned int *ticket = nullptr;
     Rec *recs = nullptr;
     uint64_t rec_cap = 0;
@@ -96,6 +97,7 @@ kernel_fn kernel_for(int op) {
     case VCFX_OP_VARIANT_COUNT: return vcfx_scan_kernel<OP_VC>;
     case VCFX_OP_ALLELE_FREQ:   return vcfx_scan_kernel<OP_AF>;
     case VCFX_OP_HWE:           return vcfx_scan_kernel<OP_HWE>;
+    case VCFX_OP_MISSING_DETECT: return vcfx_scan_kernel<OP_MD>;
     default: return nullptr;
     }
 }
@@ -103,6 +105,7 @@ kernel_fn format_kernel_for(int op) {
     switch (op) {
     case VCFX_OP_ALLELE_FREQ: return format_rows_kernel<OP_AF>;
     case VCFX_OP_HWE:         return format_rows_kernel<OP_HWE>;
+    case VCFX_OP_MISSING_DETECT: return md_copy_kernel;
     default: return nullptr;
     }
 }
@@ -140,6 +143,7 @@ uint64_t default_rec_cap(size_t nbytes) { return nbytes / 48 + 65536; }
 void free_work(Work &w) {
     cudaFree(w.tile_lines); cudaFree(w.tile_out); cudaFree(w.tile_base); cudaFree(w.line_base);
     cudaFree(w.ticket); cudaFree(w.recs); cudaFree(w.d_stats); cudaFree(w.events);
+    cudaFree(w.tail_start); cudaFree(w.tail_len); cudaFree(w.tail_off);
     if (w.h_stats) cudaFreeHost(w.h_stats);
     if (w.h_init) cudaFreeHost(w.h_init);
     if (w.ev_k0) cudaEventDestroy(w.ev_k0);
@@ -168,6 +172,13 @@ int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes, uint64_t min_recs = 0)
         CU(cudaMalloc(&w.tile_out, sizeof(uint32_t) * tiles));
         CU(cudaMalloc(&w.tile_base, sizeof(unsigned long long) * tiles));
         CU(cudaMalloc(&w.line_base, sizeof(unsigned long long) * tiles));
+        if (ctx->cfg.op == VCFX_OP_MISSING_DETECT) {
+            cudaFree(w.tail_start); cudaFree(w.tail_len); cudaFree(w.tail_off);
+            w.tail_start = w.tail_len = w.tail_off = nullptr;
+            CU(cudaMalloc(&w.tail_start, sizeof(uint32_t) * tiles));
+            CU(cudaMalloc(&w.tail_len, sizeof(uint32_t) * tiles));
+            CU(cudaMalloc(&w.tail_off, sizeof(uint32_t) * tiles));
+        }
         w.tiles_cap = tiles;
     }
     uint64_t recs = 0;
@@ -199,6 +210,7 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
     P.is_final = info ? info->is_final : 1;
     P.out = d_out; P.out_cap = out_cap;
     P.tile_lines = w.tile_lines; P.tile_out = w.tile_out; P.tile_base = w.tile_base; P.line_base = w.line_base;
+    P.tail_start = w.tail_start; P.tail_len = w.tail_len; P.tail_off = w.tail_off;
     P.ticket = w.ticket; P.recs = w.recs; P.rec_cap = w.rec_cap;
     P.stats = w.d_stats; P.events = w.events; P.ev_cap = EVENT_CAP;
 
@@ -210,7 +222,7 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
         tile_scan_kernel<<<1, 1024, 0, st>>>(P);
         CU(cudaGetLastError());
         if (kernel_fn ff = format_kernel_for(ctx->cfg.op)) {
-            ff<<<ctx->sm_count * 4, 256, 0, st>>>(P);
+            ff<<<ctx->sm_count * (ctx->cfg.op == VCFX_OP_MISSING_DETECT ? 8 : 4), 256, 0, st>>>(P);
             CU(cudaGetLastError());
         }
     }

@@ -69,6 +69,9 @@ struct KParams {
     uint32_t *tile_out;              // [n_tiles] output bytes produced by each tile
     unsigned long long *tile_base;   // [n_tiles] exclusive scan of tile_out (K2a)
     unsigned long long *line_base;   // [n_tiles] exclusive scan of tile_lines (K2a)
+    uint32_t *tail_start;            // MISSING_DETECT [n_tiles]: verbatim tail of the tile (offset from tile start)
+    uint32_t *tail_len;              //   its length; bit 31 = append a '\n' (stdin mode, unterminated last line)
+    uint32_t *tail_off;              //   its offset inside the tile's output
     unsigned int *ticket;            // dynamic tile counter (zeroed before launch)
     Rec *recs;
     uint64_t rec_cap;
@@ -286,6 +289,31 @@ __device__ __forceinline__ bool lane_lattice(uint32_t w0, uint32_t w1, uint32_t 
     return bad == 0;
 }
 
+// missing_detector.cpp:290-336 for the '.' bytes of one lane (masks d0..d3 over its 16 bytes at p).
+// A '.' marks a missing genotype when it lies in the first ':' piece of its sample and touches the
+// piece boundary or a '/' '|' separator on either side.  Neighbour bytes are read back from L1.
+__device__ __noinline__ bool md_lane_dots(const uint8_t *p, uint32_t d0, uint32_t d1, uint32_t d2, uint32_t d3, bool strip_cr) {
+    uint32_t ds[4] = {d0, d1, d2, d3};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t m = ds[j];
+        while (m) {
+            const int k = (__ffs(m) - 1) >> 3;
+            m &= m - 1;
+            const uint8_t *q = p + 4 * j + k;
+            const uint32_t prev = ldb(q - 1), next = ldb(q + 1);
+            const bool a = (prev == '\t') || is_sep(prev);
+            const bool b = is_sep(next) || next == ':' || next == '\t' || next == '\n' ||
+                           (strip_cr && next == '\r' && ldb(q + 2) == '\n');
+            if (!(a || b)) continue;
+            if (prev == '\t') return true;
+            const uint8_t *r = q - 1;                      // in the first piece <=> a tab comes before any ':'
+            for (;;) { const uint32_t c = ldb(r); if (c == '\t') return true; if (c == ':') break; --r; }
+        }
+    }
+    return false;
+}
+
 // Tier-1 check of one window (warp-uniform phase and separator): every lane's four rotated words
 // must be [0|1, sep, 0|1, tab].  y = x ^ pat is then [a, 0, b, 0] with a, b the allele values.
 // Returns false (and changes nothing) when any lane disagrees.
@@ -321,7 +349,7 @@ vcfx_scan_kernel(const KParams P) {
     const bool strip_cr = (OP == OP_HWE) || (P.mode == MODE_FILE && (OP == OP_AF || OP == OP_VC || OP == OP_MD));
     constexpr int NEED_TABS = (OP == OP_VC) ? 7 : 9;        // the header phase ends once this many tabs are ranked
 
-    unsigned long long s_lines = 0, s_data = 0, s_rows = 0, s_pre = 0, s_short = 0;
+    unsigned long long s_lines = 0, s_data = 0, s_rows = 0, s_pre = 0, s_short = 0, s_flag = 0, s_dots = 0;
 
     for (;;) {
         uint32_t tile = 0;
@@ -362,6 +390,8 @@ vcfx_scan_kernel(const KParams P) {
         }
 
         uint32_t nlines = 0, out_bytes = 0;
+        uint32_t md_prev_end = ls, md_last_end = ls;   // MISSING_DETECT: end of the last rewritten line / of the last line
+        bool md_add_nl = false;
 
         // ---- every line that starts in the tile
         while (ls < rb) {
@@ -606,6 +636,48 @@ vcfx_scan_kernel(const KParams P) {
                 if (OP == OP_AF) { ta += (accp & 0xFFFFu) + (accp >> 16); if (lane == 0) tb += 2u * n_real; }
                 else { ta -= hetp + hap; if (lane == 0) ta += n_real; tb += hetp; tc += hap; }
             }
+            // ================= MISSING_DETECT: look for a missing genotype in the sample columns
+            bool md_flag = false, md_any = false;
+            if (OP == OP_MD && !hash && tabs >= 9) {
+                const uint32_t lo = tp[8] + 1;
+                bool firstw = true;
+                for (;;) {
+                    const uint32_t pb = wb + 16 * lane;
+                    if (!firstw) {
+                        const uint32_t n0 = eq_bytes(cur.x, C_NL), n1 = eq_bytes(cur.y, C_NL);
+                        const uint32_t n2 = eq_bytes(cur.z, C_NL), n3 = eq_bytes(cur.w, C_NL);
+                        const unsigned ebal = __ballot_sync(FULL, (n0 | n1 | n2 | n3) != 0);
+                        if (ebal) {
+                            const int src = __ffs(ebal) - 1;
+                            int k = first_byte(n0, n1, n2, n3);
+                            k = __shfl_sync(FULL, k, src);
+                            e = wb + 16 * src + k; found = true;
+                        }
+                    }
+                    if (!md_flag) {                          // the reference stops at the first hit too (:323-325)
+                        uint32_t d0 = eq_bytes(cur.x, C_DOT), d1 = eq_bytes(cur.y, C_DOT);
+                        uint32_t d2 = eq_bytes(cur.z, C_DOT), d3 = eq_bytes(cur.w, C_DOT);
+                        if (firstw || found) {
+                            const uint32_t l = firstw ? lo : 0u, h = found ? e : ~0u;
+                            d0 &= range_mask(pb, l, h); d1 &= range_mask(pb + 4, l, h);
+                            d2 &= range_mask(pb + 8, l, h); d3 &= range_mask(pb + 12, l, h);
+                        }
+                        const bool any = (d0 | d1 | d2 | d3) != 0;
+                        if (__any_sync(FULL, any)) {
+                            md_any = true;
+                            const bool hit = any && md_lane_dots(tin + pb, d0, d1, d2, d3, strip_cr);
+                            md_flag = __any_sync(FULL, hit);
+                        }
+                    }
+                    if (found) break;
+                    firstw = false;
+                    wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
+                    if ((++wcount & 7) == 0) {
+                        const uint64_t pf = a0 + wb + 8 * WINDOW + 128 * lane;
+                        if (pf < n) prefetch_l2(P.in + pf);
+                    }
+                }
+            }
             // ================= no (more) per-sample work: just find the '\n'
             while (!found) {
                 wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
@@ -690,10 +762,49 @@ vcfx_scan_kernel(const KParams P) {
                     out_bytes += row_len; ++s_rows;
                 }
             }
+            else if (OP == OP_MD) {
+                const bool term = (a0 + e) < n;                          // a real '\n', not the pad behind the chunk
+                const uint32_t raw_end = term ? e + 1 : e;
+                const bool data = (ee != ls) && !hash;                   // missing_detector.cpp:511 / :865-873
+                if (data) ++s_data;
+                const bool has_samples = data && tabs >= 9;
+                // the reference's pre-scan looks at every terminated line after the leading '#' block (:347-369)
+                if (term && has_samples && md_any && tp[8] + 1 < e && (a0 + ls >= P.valid_from)) ++s_dots;
+                md_add_nl = false;
+                if (has_samples && md_flag && tp[8] + 1 < ee) {          // :520-527, :530
+                    const uint32_t info_off = tp[6] + 1 - ls, info_len = tp[7] - tp[6] - 1, content_len = ee - ls;
+                    uint32_t mod_len;                                    // :559-574 / :900-909
+                    if (info_len == 0 || (info_len == 1 && ldb(tin + tp[6] + 1) == '.')) mod_len = content_len - info_len + 19;
+                    else mod_len = content_len + 19 + ((ldb(tin + tp[7] - 1) != ';') ? 1u : 0u);
+                    mod_len += 1;                                        // the rewritten line always ends with '\n'
+                    if (lane == 0) {
+                        unsigned long long slot = atomicAdd(&P.stats->n_recs, 1ULL);
+                        if (slot < P.rec_cap) {
+                            Rec r; r.tile = tile; r.ls_rel = (uint32_t)(a0 + ls - a); r.prefix_len = (uint32_t)(a0 + md_prev_end - a);
+                            r.off_in_tile = out_bytes; r.a = info_off; r.b = info_len; r.c = content_len; r.d = mod_len;
+                            P.recs[slot] = r;
+                        }
+                        if (!term) P.stats->last_unterminated_flagged = mod_len;
+                    }
+                    out_bytes += (ls - md_prev_end) + mod_len;
+                    md_prev_end = raw_end;
+                    ++s_flag;
+                } else if (!term && P.mode == MODE_STDIN) md_add_nl = true;   // getline + "\n" (:866-889)
+                md_last_end = raw_end;
+            }
             __syncwarp();
             ls = e + 1;
         }
         s_lines += nlines;
+        if (OP == OP_MD) {
+            const uint32_t tail = md_last_end - md_prev_end;
+            if (lane == 0) {
+                P.tail_start[tile] = (uint32_t)(a0 + md_prev_end - a);
+                P.tail_len[tile] = tail | (md_add_nl ? 0x80000000u : 0u);
+                P.tail_off[tile] = out_bytes;
+            }
+            out_bytes += tail + (md_add_nl ? 1u : 0u);
+        }
         if (lane == 0) { P.tile_lines[tile] = nlines; P.tile_out[tile] = out_bytes; }
     }
     if (lane == 0) {
@@ -702,6 +813,8 @@ vcfx_scan_kernel(const KParams P) {
         if (s_rows) atomicAdd(&P.stats->rows, s_rows);
         if (s_pre) atomicAdd(&P.stats->pre_header, s_pre);
         if (s_short) atomicAdd(&P.stats->short_lines, s_short);
+        if (s_flag) atomicAdd(&P.stats->flagged, s_flag);
+        if (s_dots) atomicAdd(&P.stats->dots_terminated, s_dots);
     }
 }
 
@@ -783,6 +896,69 @@ format_rows_kernel(const KParams P) {
         }
         for (int k = 0; k < nl; ++k) o[k] = (uint8_t)num[k];
         o[nl] = '\n';
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K2c (MISSING_DETECT): assemble the output.  One warp per work item; an item is either a
+// rewritten line together with the verbatim bytes between it and the previous rewritten line
+// of its tile, or the verbatim tail of a tile.
+// ---------------------------------------------------------------------------------------
+// warp-cooperative copy of n bytes, any alignment: 32-bit stores on the aligned middle of dst, each
+// built from the two aligned source words that straddle it
+__device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint32_t n, int lane) {
+    if (n == 0) return;
+    const uint32_t head = min(n, (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3));
+    if (lane < (int)head) dst[lane] = __ldg(src + lane);
+    dst += head; src += head; n -= head;
+    const uint32_t nw = n >> 2;
+    const uint32_t sh = 8u * (uint32_t)((uintptr_t)src & 3);
+    const uint32_t *s4 = reinterpret_cast<const uint32_t *>(src - (sh >> 3));
+    uint32_t *d4 = reinterpret_cast<uint32_t *>(dst);
+    if (sh == 0) { for (uint32_t i = lane; i < nw; i += 32) d4[i] = __ldg(s4 + i); }
+    else { for (uint32_t i = lane; i < nw; i += 32) d4[i] = __funnelshift_r(__ldg(s4 + i), __ldg(s4 + i + 1), sh); }
+    const uint32_t done = nw << 2, rem = n - done;
+    if (lane < (int)rem) dst[done + lane] = __ldg(src + done + lane);
+}
+
+__global__ void __launch_bounds__(256)
+md_copy_kernel(const KParams P) {
+    if (P.stats->overflow) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long nrec = P.stats->n_recs, items = nrec + P.n_tiles;
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    for (unsigned long long it = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < items; it += nwarps) {
+        if (it < nrec) {
+            const Rec r = P.recs[it];
+            const uint8_t *base = P.in + (uint64_t)r.tile * P.tile_bytes;
+            uint8_t *o = P.out + P.tile_base[r.tile] + r.off_in_tile;
+            const uint32_t gap = r.ls_rel - r.prefix_len;                // verbatim bytes before the line
+            warp_copy(o, base + r.prefix_len, gap, lane);
+            o += gap;
+            const uint8_t *ln = base + r.ls_rel;
+            warp_copy(o, ln, r.a, lane);                                 // up to INFO
+            o += r.a;
+            const uint8_t *info = ln + r.a;
+            const bool replace = (r.b == 0) || (r.b == 1 && __ldg(info) == '.');
+            uint32_t w = 0;
+            if (!replace) {
+                warp_copy(o, info, r.b, lane);
+                w = r.b;
+                if (__ldg(info + r.b - 1) != ';') { if (lane == 0) o[w] = ';'; ++w; }
+            }
+            if (lane < 19) o[w + lane] = (uint8_t)"MISSING_GENOTYPES=1"[lane];
+            w += 19;
+            o += w;
+            const uint32_t rest = r.c - r.a - r.b;                       // from the tab after INFO to the content end
+            warp_copy(o, info + r.b, rest, lane);
+            if (lane == 0) o[rest] = '\n';
+        } else {
+            const uint32_t t = (uint32_t)(it - nrec);
+            const uint32_t len = P.tail_len[t] & 0x7FFFFFFFu;
+            uint8_t *o = P.out + P.tile_base[t] + P.tail_off[t];
+            warp_copy(o, P.in + (uint64_t)t * P.tile_bytes + P.tail_start[t], len, lane);
+            if ((P.tail_len[t] >> 31) && lane == 0) o[len] = '\n';
+        }
     }
 }
 
