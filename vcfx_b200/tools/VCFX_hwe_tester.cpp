@@ -1,0 +1,80 @@
+// VCFX_hwe_tester — drop-in replacement for the reference tool of the same name
+// (src/VCFX_hwe_tester/VCFX_hwe_tester.cpp): same flags, messages, exit codes and output bytes in
+// both input modes; performHWE_Mmap / performHWE_Stdin run on the GPU via libvcfx_cuda.
+#include <cstdio>
+#include <cstring>
+#include <fcntl.h>
+#include <getopt.h>
+#include <string>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "vcfx_host.h"
+
+static void display_help() {
+    fputs("VCFX_hwe_tester: Perform Hardy-Weinberg Equilibrium (HWE) tests on a biallelic VCF.\n\n"
+          "Usage:\n"
+          "  VCFX_hwe_tester [options] [input.vcf]\n"
+          "  VCFX_hwe_tester [options] < input.vcf\n\n"
+          "Options:\n"
+          "  -i, --input FILE   Input VCF file (uses memory-mapping for best performance)\n"
+          "  -q, --quiet        Suppress informational messages\n"
+          "  -h, --help         Show this help.\n\n"
+          "Description:\n"
+          "  Reads each variant line, ignoring multi-allelic calls. For biallelic lines,\n"
+          "  collects genotypes as 0/0, 0/1, 1/1, then uses chi-square test with Yates'\n"
+          "  continuity correction to produce a p-value for HWE.\n\n"
+          "Performance:\n"
+          "  Uses memory-mapped I/O and SIMD for ~20x speedup over stdin mode.\n\n"
+          "Example:\n"
+          "  VCFX_hwe_tester -i input.vcf > results.txt\n"
+          "  VCFX_hwe_tester < input.vcf > results.txt\n", stdout);
+}
+
+static const char HEADER[] = "CHROM\tPOS\tID\tREF\tALT\tHWE_pvalue\n";
+
+int main(int argc, char *argv[]) {
+    for (int i = 1; i < argc; ++i)
+        if (!strcmp(argv[i], "--help") || !strcmp(argv[i], "-h")) { display_help(); return 0; }
+    for (int i = 1; i < argc; ++i)
+        if (!strcmp(argv[i], "--version") || !strcmp(argv[i], "-v")) { puts("VCFX_hwe_tester version 1.1.4"); return 0; }
+
+    const char *input = nullptr;
+    bool quiet = false, show_help = false;
+    static struct option long_opts[] = {{"help", no_argument, 0, 'h'}, {"input", required_argument, 0, 'i'},
+                                        {"quiet", no_argument, 0, 'q'}, {0, 0, 0, 0}};
+    optind = 1;
+    for (;;) {
+        int c = getopt_long(argc, argv, "hi:q", long_opts, nullptr);
+        if (c == -1) break;
+        if (c == 'i') input = optarg; else if (c == 'q') quiet = true; else show_help = true;
+    }
+    if (!input && optind < argc) input = argv[optind];
+    if (show_help) { display_help(); return 0; }
+
+    vcfxh::RunOptions opt;
+    opt.op = VCFX_OP_HWE;
+    vcfxh::Totals tot;
+    std::string err;
+    int rc = VCFX_OK;
+    if (input) {
+        int fd = open(input, O_RDONLY);
+        struct stat st;
+        if (fd < 0 || fstat(fd, &st) < 0) { fprintf(stderr, "Error: Cannot open file: %s\n", input); return 1; }
+        if (!quiet) fprintf(stderr, "Processing %s (%llu bytes)...\n", input, (unsigned long long)st.st_size);
+        if (st.st_size > 0) {                       // an empty file prints nothing at all (:456)
+            opt.mode = VCFX_MODE_FILE;
+            vcfxh::write_all(1, HEADER, sizeof HEADER - 1);
+            vcfxh::Source src(fd);
+            rc = vcfxh::run_stream(src, opt, tot, err);
+        }
+        close(fd);
+    } else {
+        opt.mode = VCFX_MODE_STDIN;
+        vcfxh::write_all(1, HEADER, sizeof HEADER - 1);
+        vcfxh::Source src(0);
+        rc = vcfxh::run_stream(src, opt, tot, err);
+    }
+    if (rc != VCFX_OK) { fprintf(stderr, "Error: %s\n", err.c_str()); return 1; }
+    return 0;
+}

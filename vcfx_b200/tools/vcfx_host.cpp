@@ -1,0 +1,230 @@
+// vcfx_host.cpp — streaming chunk reader + output writer over the libvcfx_cuda C ABI.
+#include "vcfx_host.h"
+
+#include <algorithm>
+#include <cerrno>
+#include <cstdlib>
+#include <cstring>
+#include <unistd.h>
+#include <zlib.h>
+
+namespace vcfxh {
+
+// ---------------------------------------------------------------------------------- Source
+Source::~Source() {
+    if (zs_) { inflateEnd(static_cast<z_stream *>(zs_)); delete static_cast<z_stream *>(zs_); }
+}
+
+long Source::raw_read(char *dst, size_t cap) {
+    if (peek_pos_ < peek_.size()) {
+        size_t k = std::min(cap, peek_.size() - peek_pos_);
+        memcpy(dst, peek_.data() + peek_pos_, k);
+        peek_pos_ += k;
+        return (long)k;
+    }
+    for (;;) {
+        ssize_t r = ::read(fd_, dst, cap);
+        if (r < 0 && errno == EINTR) continue;
+        if (r < 0) failed_ = true;
+        return (long)r;
+    }
+}
+
+bool Source::at_eof_initially() {
+    if (!peek_.empty()) return false;
+    char c;
+    long r = raw_read(&c, 1);
+    if (r <= 0) return true;
+    peek_.assign(1, c); peek_pos_ = 0;
+    return false;
+}
+
+bool Source::sniff_gzip() {
+    while (peek_.size() < 2) {
+        char c;
+        ssize_t r = ::read(fd_, &c, 1);
+        if (r < 0 && errno == EINTR) continue;
+        if (r <= 0) break;
+        peek_.push_back(c);
+    }
+    peek_pos_ = 0;
+    return peek_.size() >= 2 && (unsigned char)peek_[0] == 0x1f && (unsigned char)peek_[1] == 0x8b;
+}
+
+void Source::enable_gzip() {
+    z_stream *z = new z_stream();
+    memset(z, 0, sizeof *z);
+    if (inflateInit2(z, 15 + 32) != Z_OK) { delete z; failed_ = true; return; }
+    zs_ = z; gz_ = true; zin_.resize(1 << 16);
+}
+
+long Source::read(char *dst, size_t cap) {
+    if (!gz_) return raw_read(dst, cap);
+    if (gz_done_ || cap == 0) return 0;
+    z_stream *z = static_cast<z_stream *>(zs_);
+    z->next_out = reinterpret_cast<Bytef *>(dst);
+    z->avail_out = (uInt)std::min<size_t>(cap, 1u << 30);
+    while (z->avail_out == (uInt)std::min<size_t>(cap, 1u << 30)) {
+        if (zin_pos_ == zin_len_) {
+            long r = raw_read(zin_.data(), zin_.size());
+            if (r < 0) return -1;
+            if (r == 0) { gz_done_ = true; break; }
+            zin_len_ = (size_t)r; zin_pos_ = 0;
+        }
+        z->next_in = reinterpret_cast<Bytef *>(zin_.data() + zin_pos_);
+        z->avail_in = (uInt)(zin_len_ - zin_pos_);
+        int ret = inflate(z, Z_NO_FLUSH);
+        zin_pos_ = zin_len_ - z->avail_in;
+        if (ret == Z_STREAM_END) {
+            // like the reference loop (variant_counter.cpp:239-275) the first member ends the stream
+            gz_done_ = true; break;
+        }
+        if (ret != Z_OK && ret != Z_BUF_ERROR) { failed_ = true; return -1; }
+    }
+    return (long)(std::min<size_t>(cap, 1u << 30) - z->avail_out);
+}
+
+// ---------------------------------------------------------------------------------- helpers
+bool write_all(int fd, const char *p, size_t n) {
+    while (n) {
+        ssize_t w = ::write(fd, p, n);
+        if (w < 0 && errno == EINTR) continue;
+        if (w <= 0) return false;
+        p += w; n -= (size_t)w;
+    }
+    return true;
+}
+
+int env_device() {
+    const char *e = getenv("VCFX_CUDA_DEVICE");
+    return e ? atoi(e) : 0;
+}
+
+namespace {
+
+struct Drain {
+    vcfx_ctx *ctx; const RunOptions &opt; Totals &tot; uint64_t line_base = 0; bool write_failed = false;
+    long drained = 0, final_index = -1;
+    int one(std::string &err) {
+        const char *text = nullptr; size_t n = 0; vcfx_chunk_stats st;
+        int rc = vcfx_cuda_next_output(ctx, &text, &n, &st);
+        if (rc != VCFX_OK) { err = std::string(vcfx_cuda_strerror(rc)) + ": " + vcfx_cuda_last_error(ctx); return rc; }
+        if (n) {
+            if (opt.capture) opt.capture->append(text, n);
+            else if (opt.capture_final && drained == final_index) opt.capture_final->append(text, n);
+            else if (!write_failed && !write_all(opt.out_fd, text, n)) write_failed = true;   // like the reference, a closed pipe is not an error
+        }
+        tot.bytes_in += st.bytes_in; tot.bytes_out += st.bytes_out; tot.data_lines += st.data_lines;
+        tot.rows += st.rows; tot.flagged += st.flagged; tot.pre_header += st.pre_header;
+        tot.short_lines += st.short_lines; tot.dots_terminated += st.dots_terminated;
+        tot.last_unterminated_flagged = st.last_unterminated_flagged;
+        tot.kernel_ms += st.kernel_ms;
+        if (st.first_short_line && !tot.first_short_line) tot.first_short_line = line_base + st.first_short_line;
+        if (opt.want_short_lines && st.n_events) {
+            std::vector<uint64_t> ev((size_t)std::min<uint64_t>(st.n_events, 1u << 20));
+            size_t got = 0;
+            vcfx_cuda_short_lines(ctx, ev.data(), ev.size(), &got);
+            for (size_t i = 0; i < got; ++i) tot.short_line_numbers.push_back(line_base + ev[i]);
+        }
+        tot.lines += st.lines;
+        line_base += st.lines;
+        ++drained;
+        return VCFX_OK;
+    }
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------- run_stream
+int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err) {
+    vcfx_cfg cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.device = env_device(); cfg.op = opt.op; cfg.mode = opt.mode; cfg.flags = opt.flags;
+    size_t chunk = opt.chunk_bytes;
+    if (!chunk) { const char *e = getenv("VCFX_CHUNK_BYTES"); chunk = e ? (size_t)strtoull(e, nullptr, 10) : (size_t)64 << 20; }
+    cfg.chunk_bytes = chunk; cfg.n_slots = 3;
+    std::string names_blob; std::vector<uint32_t> name_off;
+    if (!opt.sel_col.empty()) {
+        name_off.push_back(0);
+        for (const auto &s : opt.sel_names) { names_blob += s; names_blob.push_back('\t'); name_off.push_back((uint32_t)names_blob.size()); }
+        cfg.n_sel = (uint32_t)opt.sel_col.size(); cfg.sel_col = opt.sel_col.data();
+        cfg.sel_names = names_blob.data(); cfg.sel_name_off = name_off.data();
+    }
+    vcfx_ctx *ctx = nullptr;
+    int rc = vcfx_cuda_create(&cfg, &ctx);
+    if (rc != VCFX_OK) { err = vcfx_cuda_strerror(rc); return rc; }
+
+    Drain drain{ctx, opt, tot};
+    std::string carry = opt.preface;
+    bool eof = false, chrom_seen = false, in_hash_block = true;
+    long submitted = 0;
+    while (!eof) {
+        char *buf = nullptr; size_t cap = 0;
+        rc = vcfx_cuda_acquire_input(ctx, &buf, &cap);
+        while (rc == VCFX_E_BUSY) {
+            if ((rc = drain.one(err)) != VCFX_OK) { vcfx_cuda_destroy(ctx); return rc; }
+            rc = vcfx_cuda_acquire_input(ctx, &buf, &cap);
+        }
+        if (rc != VCFX_OK) { err = std::string(vcfx_cuda_strerror(rc)) + ": " + vcfx_cuda_last_error(ctx); vcfx_cuda_destroy(ctx); return rc; }
+        if (carry.size() > cap) { err = "a line is longer than the chunk size (set VCFX_CHUNK_BYTES)"; vcfx_cuda_destroy(ctx); return VCFX_E_INVALID; }
+        size_t have = carry.size();
+        memcpy(buf, carry.data(), have);
+        carry.clear();
+        while (have < cap) {
+            long r = src.read(buf + have, cap - have);
+            if (r < 0) { err = "read error"; vcfx_cuda_destroy(ctx); return VCFX_E_INVALID; }
+            if (r == 0) { eof = true; break; }
+            have += (size_t)r;
+        }
+        size_t nbytes = have;
+        if (!eof) {
+            const char *nl = static_cast<const char *>(memrchr(buf, '\n', have));
+            if (!nl) { err = "a line is longer than the chunk size (set VCFX_CHUNK_BYTES)"; vcfx_cuda_destroy(ctx); return VCFX_E_INVALID; }
+            nbytes = (size_t)(nl - buf) + 1;
+            carry.assign(buf + nbytes, have - nbytes);
+        } else if (opt.last_unterminated_line && nbytes && buf[nbytes - 1] != '\n') {
+            const char *nl = static_cast<const char *>(memrchr(buf, '\n', nbytes));
+            const char *s = nl ? nl + 1 : buf;
+            opt.last_unterminated_line->assign(s, (size_t)(buf + nbytes - s));
+        }
+        if (nbytes == 0) break;
+        vcfx_chunk_info info; memset(&info, 0, sizeof info);
+        info.is_final = eof ? 1 : 0;
+        if (opt.rule == HeaderRule::ChromHeader) {
+            // data lines before the first line that starts with "#CHROM" are skipped with a warning
+            // (allele_freq_calc.cpp:372-386): a prefix fact, found once, here
+            if (chrom_seen) info.data_valid_from = 0;
+            else {
+                size_t off = nbytes;
+                if (nbytes >= 6 && memcmp(buf, "#CHROM", 6) == 0) off = 0;
+                else if (const void *m = memmem(buf, nbytes, "\n#CHROM", 7)) off = (size_t)(static_cast<const char *>(m) - buf) + 1;
+                if (off < nbytes) chrom_seen = true;
+                info.data_valid_from = off;
+            }
+        } else if (opt.rule == HeaderRule::LeadingHashBlock) {
+            // end of the leading block of '#' lines (missing_detector.cpp:378-383)
+            size_t pos = 0;
+            while (in_hash_block && pos < nbytes) {
+                if (buf[pos] != '#') { in_hash_block = false; break; }
+                const char *nl = static_cast<const char *>(memchr(buf + pos, '\n', nbytes - pos));
+                pos = nl ? (size_t)(nl - buf) + 1 : nbytes;
+            }
+            info.data_valid_from = pos;
+        }
+        if (eof) drain.final_index = submitted;
+        rc = vcfx_cuda_submit(ctx, nbytes, &info);
+        ++submitted;
+        if (rc != VCFX_OK) { err = std::string(vcfx_cuda_strerror(rc)) + ": " + vcfx_cuda_last_error(ctx); vcfx_cuda_destroy(ctx); return rc; }
+        if (opt.stop_at_first_short && vcfx_cuda_in_flight(ctx) >= 2) {
+            // --strict only needs the first short line: check as chunks complete, stop early
+            if ((rc = drain.one(err)) != VCFX_OK) { vcfx_cuda_destroy(ctx); return rc; }
+            if (tot.short_lines) break;
+        }
+    }
+    while (vcfx_cuda_in_flight(ctx) > 0)
+        if ((rc = drain.one(err)) != VCFX_OK) { vcfx_cuda_destroy(ctx); return rc; }
+    vcfx_cuda_destroy(ctx);
+    return VCFX_OK;
+}
+
+}  // namespace vcfxh

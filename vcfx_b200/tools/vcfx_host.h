@@ -1,0 +1,79 @@
+// vcfx_host.h — host side shared by the five drop-in tools: the streaming chunk reader that
+// replaces the per-line loops of the reference (include/vcfx_io.h:14-24 getline + split_tabs,
+// and each tool's private MappedFile / findNewlineSIMD loop), feeding libvcfx_cuda through its
+// C ABI.  Nothing here parses records: it moves bytes, keeps chunks newline-aligned, tracks the
+// two header facts that are prefix state (first "#CHROM" line, end of the leading '#' block),
+// and writes the returned text to stdout in order.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "vcfx_cuda.h"
+
+namespace vcfxh {
+
+// A byte source: a plain fd, or a gzip stream on an fd (variant_counter's stdin, the only place
+// the reference inflates on this path: VCFX_variant_counter.cpp:223-290).
+class Source {
+  public:
+    explicit Source(int fd) : fd_(fd) {}
+    ~Source();
+    // true when the first two bytes are the gzip magic (consumes nothing)
+    bool sniff_gzip();
+    bool at_eof_initially();              // like std::cin.peek() == EOF
+    void enable_gzip();
+    // read up to cap bytes; 0 = end of input; < 0 = error
+    long read(char *dst, size_t cap);
+    bool failed() const { return failed_; }
+
+  private:
+    long raw_read(char *dst, size_t cap);
+    int fd_;
+    std::string peek_;                    // bytes read ahead by sniff/peek
+    size_t peek_pos_ = 0;
+    bool gz_ = false, gz_done_ = false, failed_ = false;
+    void *zs_ = nullptr;                  // z_stream*
+    std::vector<char> zin_;
+    size_t zin_len_ = 0, zin_pos_ = 0;
+};
+
+struct Totals {
+    uint64_t bytes_in = 0, bytes_out = 0, lines = 0, data_lines = 0, rows = 0, flagged = 0;
+    uint64_t pre_header = 0, short_lines = 0, first_short_line = 0, dots_terminated = 0;
+    uint64_t last_unterminated_flagged = 0;
+    std::vector<uint64_t> short_line_numbers;   // 1-based, whole input
+    double kernel_ms = 0;
+};
+
+enum class HeaderRule { None, ChromHeader, LeadingHashBlock };
+
+struct RunOptions {
+    int op = 0, mode = 0;
+    unsigned flags = 0;
+    HeaderRule rule = HeaderRule::None;
+    bool want_short_lines = false;        // collect line numbers of short lines (variant_counter)
+    bool stop_at_first_short = false;     // --strict: stop reading once a short line was seen
+    int out_fd = 1;
+    size_t chunk_bytes = 0;               // 0 = VCFX_CHUNK_BYTES env or 64 MiB
+    // allele_counter selection
+    std::vector<uint32_t> sel_col;
+    std::vector<std::string> sel_names;
+    // when set, the text is appended here instead of being written to out_fd
+    std::string *capture = nullptr;
+    // when set, only the text of the FINAL chunk is held back here (everything before is written)
+    std::string *capture_final = nullptr;
+    // keeps a copy of the last line of the input when it has no '\n' (missing_detector's quirk)
+    std::string *last_unterminated_line = nullptr;
+    // bytes that were already consumed from the source and belong in front of it
+    std::string preface;
+};
+
+// Streams `src` through libvcfx_cuda. Returns 0, or a negative vcfx_err; err_text gets a message.
+int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err_text);
+
+int env_device();
+bool write_all(int fd, const char *p, size_t n);
+
+}  // namespace vcfxh
