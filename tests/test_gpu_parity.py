@@ -109,3 +109,37 @@ def test_missing_detector_cases(cuda_api, oracle):
     for i, data in enumerate(cases):
         run_all(cuda_api, oracle, data, f"mdcase{i}", tools=("md",))
         run_all(cuda_api, oracle, data, f"mdcase{i}-tile512", tile_bytes=512, tools=("md",))
+
+
+def _ac_all(api, O, data, tag, **kw):
+    cases = [(O.AC_MT_TEXT, O.AC_TEXT, 0, None), (O.AC_STREAM, O.AC_TEXT, 0, None), (O.AC_UNIFIED, O.AC_AGGREGATE, 0, None),
+             (O.AC_UNIFIED, O.AC_BINARY, 0, None), (O.AC_UNIFIED, O.AC_TEXT, 2, None),
+             (O.AC_MT_TEXT, O.AC_TEXT, 0, "S1 S0"), (O.AC_STREAM, O.AC_TEXT, 0, "S1 S0"), (O.AC_UNIFIED, O.AC_AGGREGATE, 0, "S2 S0 S1"),
+             (O.AC_MT_TEXT, O.AC_TEXT, 0, "S0 nope")]
+    for path, fmt, limit, samples in cases:
+        o = O.allele_counter(data, path, fmt, limit, samples)
+        r = api.allele_counter(data, path, fmt, limit, samples, **kw)
+        assert r.rc == o.rc, (tag, path, fmt, limit, samples, r.rc, o.rc)
+        _cmp(f"{tag} ac path{path} fmt{fmt} l{limit} s{samples}", r.out, o.out)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_allele_counter_adversarial(cuda_api, oracle, seed):
+    hdr = ["normal", "normal", "late", "none", "double"][seed % 5]
+    data = vcfgen.make_vcf(2000 + seed, n_lines=50, n_samples=1 + seed % 8, domain="ac", final_newline=(seed % 4 != 1), header=hdr)
+    _ac_all(cuda_api, oracle, data, f"acfuzz{seed}")
+    if seed % 4 == 0:
+        _ac_all(cuda_api, oracle, data, f"acfuzz{seed}-tile512", tile_bytes=512)
+
+
+@pytest.mark.parametrize("shape,V,S", [(1, 300, 100), (2, 60, 2504), (3, 60, 2504), (4, 100, 33), (3, 500, 9)])
+def test_allele_counter_shapes(cuda_api, oracle, shape, V, S):
+    data = synth.make_vcf(shape, V, S, seed=300 + shape)
+    for path, fmt in ((oracle.AC_MT_TEXT, oracle.AC_TEXT), (oracle.AC_UNIFIED, oracle.AC_AGGREGATE), (oracle.AC_UNIFIED, oracle.AC_BINARY)):
+        o = oracle.allele_counter(data, path, fmt)
+        r = cuda_api.allele_counter(data, path, fmt)
+        assert r.rc == o.rc
+        _cmp(f"ac shape{shape} path{path} fmt{fmt}", r.out, o.out)
+    # several chunks; the first one overflows the default output slot and is re-run with exact sizes
+    r = cuda_api.allele_counter(data, oracle.AC_MT_TEXT, chunk_bytes=256 << 10)
+    _cmp(f"ac shape{shape} chunks", r.out, oracle.allele_counter(data).out)

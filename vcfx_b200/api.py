@@ -340,3 +340,111 @@ def variant_counter(data: bytes, mode: int = FILE, strict: bool = False, chunk_b
     if strict and tot.short_lines:                # variant_counter.cpp:373-377, 175-177
         return ToolResult(b"", 1, tot)
     return ToolResult(b"Total Variants: %d\n" % tot.rows, 0, tot)
+
+
+# ----------------------------------------------------------------------------- allele_counter
+AC_MT_TEXT, AC_STREAM, AC_UNIFIED = 0, 1, 2          # code paths of the reference (allele_counter.cpp:1522-1533)
+AC_TEXT, AC_AGGREGATE, AC_BINARY = 0, 1, 2
+
+
+def _ac_header_names(data: bytes):
+    """Sample names of the leading '#' block (fields 10.. of every "#CHROM" line, accumulated) and
+    the offset of the first non-'#' line (allele_counter.cpp:806-829, 1285-1307)."""
+    names, pos, n = [], 0, len(data)
+    while pos < n and data[pos:pos + 1] == b"#":
+        nl = data.find(b"\n", pos)
+        end = n if nl < 0 else nl
+        line = data[pos:end]
+        if line.startswith(b"#CHROM"):
+            f = line.split(b"\t")
+            if len(f) > 9:
+                cols = f[9:]
+                if cols and cols[-1] == b"":      # nothing is pushed for an empty tail after a final tab
+                    cols = cols[:-1]
+                names += cols
+        pos = n if nl < 0 else nl + 1
+    return names, pos
+
+
+def _ac_parse_samples(arg: str | None):
+    """The -s argument: split on ' ', drop empties, trim (allele_counter.cpp:355-373)."""
+    if not arg:
+        return []
+    out = []
+    for tok in arg.encode().split(b" "):
+        if tok:
+            t = tok.strip(b" \t\n\r")
+            out.append(t if t else tok)
+    return out
+
+
+def allele_counter(data: bytes, path: int = AC_MT_TEXT, fmt: int = AC_TEXT, limit: int = 0,
+                   samples: str | None = None, chunk_bytes: int = 0, **kw) -> ToolResult:
+    """Host side of VCFX_allele_counter (header parse, sample selection, fixed header rows); the
+    per-line work (processChunk / countAllelesStream / countAllelesUnified) runs in libvcfx_cuda."""
+    req = _ac_parse_samples(samples)
+    if path != AC_STREAM:
+        if len(data) == 0:
+            return ToolResult(b"", 1, Totals())                       # "Error: Empty file"
+        names, data_pos = _ac_header_names(data)
+        if not names:
+            return ToolResult(b"", 1, Totals())                       # "Error: No samples found in VCF"
+        if path == AC_MT_TEXT and data_pos >= len(data):
+            return ToolResult(b"", 1, Totals())                       # "Error: No data lines found"
+    else:
+        # the stream path meets lines one by one: every "#CHROM" line APPENDS its names and then appends
+        # a full selection over all names so far (allele_counter.cpp:1139-1178); blank lines are skipped;
+        # a data line before any "#CHROM" line is an error with nothing written; no header at all ends
+        # with the header row and rc 1
+        names, cols, pos, n = [], [], 0, len(data)
+        while pos < n and data[pos:pos + 1] in (b"#", b"\n"):
+            nl = data.find(b"\n", pos)
+            line = data[pos:(n if nl < 0 else nl)]
+            if line.startswith(b"#CHROM"):
+                f = line.split(b"\t")
+                add = f[9:] if len(f) > 9 else []
+                if add and add[-1] == b"":
+                    add = add[:-1]
+                names += add
+                if req:
+                    last = {nm: i for i, nm in enumerate(names)}
+                    if any(r not in last for r in req):
+                        return ToolResult(b"", 1, Totals())
+                    cols += [last[r] for r in req]
+                else:
+                    cols += list(range(len(names)))
+            pos = n if nl < 0 else nl + 1
+        if not cols and not names:
+            has_data = any(l and not l.startswith(b"#") for l in data[pos:].split(b"\n"))
+            return ToolResult(b"" if has_data else AC_TEXT_HEADER, 1, Totals())
+    if path != AC_STREAM:
+        if req:
+            last = {nm: i for i, nm in enumerate(names)}                  # duplicates: the last column wins (:845-847)
+            if any(r not in last for r in req):
+                return ToolResult(b"", 1, Totals())                       # "Error: Sample 'x' not found"
+            cols = [last[r] for r in req]
+        else:
+            cols = list(range(len(names)))
+        if path == AC_UNIFIED and limit > 0 and len(cols) > limit:
+            cols = cols[:limit]
+    if not cols:
+        # a "#CHROM" line without sample columns: nothing can be selected, every data line yields no row
+        return ToolResult(AC_TEXT_HEADER, 0, Totals())
+    sel_names = [names[c] for c in cols]
+    flags = 0
+    if path == AC_STREAM or (path == AC_UNIFIED and fmt == AC_TEXT):
+        flags = F_AC_FORWARD
+    elif path == AC_UNIFIED and fmt == AC_AGGREGATE:
+        flags = F_AC_AGGREGATE
+    elif path == AC_UNIFIED and fmt == AC_BINARY:
+        flags = F_AC_BINARY
+    body, tot = _run(OP_ALLELE_COUNT, data, FILE if path != AC_STREAM else STDIN, chunk_bytes, flags=flags,
+                     sel_cols=cols, sel_names=sel_names, **kw)
+    if flags == F_AC_AGGREGATE:
+        head = AC_AGG_HEADER
+    elif flags == F_AC_BINARY:
+        import struct
+        head = b"VCAC" + struct.pack("<IIQ", 1, len(cols), 0)        # BinaryHeader, packed (:326-333)
+    else:
+        head = AC_TEXT_HEADER
+    return ToolResult(head + body, 0, tot)

@@ -21,10 +21,11 @@ constexpr int MAX_SLOTS = 8;
 
 struct Work {                      // device-side bookkeeping for one launch
     uint32_t *tile_lines = nullptr;
-    uint32_t *tile_out = nullptr;
+    unsigned long long *tile_out = nullptr;
     unsigned long long *tile_base = nullptr;
     unsigned long long *line_base = nullptr;
     uint32_t *tail_start = nullptr, *tail_len = nullptr, *tail_off = nullptr;   // MISSING_DETECT
+    uint2 *col_scratch = nullptr;   // ALLELE_COUNT
     unsigned int *ticket = nullptr;
     Rec *recs = nullptr;
     uint64_t rec_cap = 0;
@@ -73,6 +74,11 @@ struct vcfx_ctx {
     uint8_t *dev_in = nullptr, *dev_out = nullptr;
     size_t dev_out_cap = 0;
     vcfx_chunk_info dev_info = {0, 1, 0};
+    // allele_counter selection (device copies)
+    uint32_t n_sel = 0, max_col = 0;
+    uint32_t *d_sel_col = nullptr, *d_name_off = nullptr;
+    uint8_t *d_names = nullptr;
+    int ac_fmt = 0;
     // last drained chunk's short-line list
     std::vector<uint64_t> last_events;
     uint64_t last_n_events = 0;
@@ -98,10 +104,12 @@ kernel_fn kernel_for(int op) {
     case VCFX_OP_ALLELE_FREQ:   return vcfx_scan_kernel<OP_AF>;
     case VCFX_OP_HWE:           return vcfx_scan_kernel<OP_HWE>;
     case VCFX_OP_MISSING_DETECT: return vcfx_scan_kernel<OP_MD>;
+    case VCFX_OP_ALLELE_COUNT:  return vcfx_scan_kernel<OP_AC>;
     default: return nullptr;
     }
 }
-kernel_fn format_kernel_for(int op) {
+kernel_fn format_kernel_for(int op, int ac_fmt = 0) {
+    if (op == VCFX_OP_ALLELE_COUNT) return ac_fmt == AC_AGG ? format_rows_kernel<OP_AC> : nullptr;
     switch (op) {
     case VCFX_OP_ALLELE_FREQ: return format_rows_kernel<OP_AF>;
     case VCFX_OP_HWE:         return format_rows_kernel<OP_HWE>;
@@ -143,7 +151,7 @@ uint64_t default_rec_cap(size_t nbytes) { return nbytes / 48 + 65536; }
 void free_work(Work &w) {
     cudaFree(w.tile_lines); cudaFree(w.tile_out); cudaFree(w.tile_base); cudaFree(w.line_base);
     cudaFree(w.ticket); cudaFree(w.recs); cudaFree(w.d_stats); cudaFree(w.events);
-    cudaFree(w.tail_start); cudaFree(w.tail_len); cudaFree(w.tail_off);
+    cudaFree(w.tail_start); cudaFree(w.tail_len); cudaFree(w.tail_off); cudaFree(w.col_scratch);
     if (w.h_stats) cudaFreeHost(w.h_stats);
     if (w.h_init) cudaFreeHost(w.h_init);
     if (w.ev_k0) cudaEventDestroy(w.ev_k0);
@@ -167,9 +175,9 @@ int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes, uint64_t min_recs = 0)
     }
     if (tiles > w.tiles_cap) {
         cudaFree(w.tile_lines); cudaFree(w.tile_out); cudaFree(w.tile_base); cudaFree(w.line_base);
-        w.tile_lines = w.tile_out = nullptr; w.tile_base = w.line_base = nullptr;
+        w.tile_lines = nullptr; w.tile_out = nullptr; w.tile_base = w.line_base = nullptr;
         CU(cudaMalloc(&w.tile_lines, sizeof(uint32_t) * tiles));
-        CU(cudaMalloc(&w.tile_out, sizeof(uint32_t) * tiles));
+        CU(cudaMalloc(&w.tile_out, sizeof(unsigned long long) * tiles));
         CU(cudaMalloc(&w.tile_base, sizeof(unsigned long long) * tiles));
         CU(cudaMalloc(&w.line_base, sizeof(unsigned long long) * tiles));
         if (ctx->cfg.op == VCFX_OP_MISSING_DETECT) {
@@ -182,7 +190,11 @@ int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes, uint64_t min_recs = 0)
         w.tiles_cap = tiles;
     }
     uint64_t recs = 0;
-    if (format_kernel_for(ctx->cfg.op)) recs = std::max<uint64_t>(default_rec_cap(max_bytes), min_recs);
+    if (format_kernel_for(ctx->cfg.op, ctx->ac_fmt)) recs = std::max<uint64_t>(default_rec_cap(max_bytes), min_recs);
+    if (ctx->cfg.op == VCFX_OP_ALLELE_COUNT && !w.col_scratch) {
+        size_t n = (size_t)ctx->sm_count * ctx->blocks_per_sm * WARPS_PER_CTA * std::max<uint32_t>(ctx->max_col, 1);
+        CU(cudaMalloc(&w.col_scratch, n * sizeof(uint2)));
+    }
     if (recs > w.rec_cap) {
         cudaFree(w.recs); w.recs = nullptr; w.rec_cap = 0;
         CU(cudaMalloc(&w.recs, recs * sizeof(Rec)));
@@ -211,6 +223,8 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
     P.out = d_out; P.out_cap = out_cap;
     P.tile_lines = w.tile_lines; P.tile_out = w.tile_out; P.tile_base = w.tile_base; P.line_base = w.line_base;
     P.tail_start = w.tail_start; P.tail_len = w.tail_len; P.tail_off = w.tail_off;
+    P.ac_fmt = ctx->ac_fmt; P.ac_pass = 0; P.n_sel = ctx->n_sel; P.sel_col = ctx->d_sel_col; P.name_off = ctx->d_name_off;
+    P.names = ctx->d_names; P.max_col = ctx->max_col; P.col_scratch = w.col_scratch;
     P.ticket = w.ticket; P.recs = w.recs; P.rec_cap = w.rec_cap;
     P.stats = w.d_stats; P.events = w.events; P.ev_cap = EVENT_CAP;
 
@@ -221,8 +235,14 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
         CU(cudaGetLastError());
         tile_scan_kernel<<<1, 1024, 0, st>>>(P);
         CU(cudaGetLastError());
-        if (kernel_fn ff = format_kernel_for(ctx->cfg.op)) {
+        if (kernel_fn ff = format_kernel_for(ctx->cfg.op, ctx->ac_fmt)) {
             ff<<<ctx->sm_count * (ctx->cfg.op == VCFX_OP_MISSING_DETECT ? 8 : 4), 256, 0, st>>>(P);
+            CU(cudaGetLastError());
+        } else if (ctx->cfg.op == VCFX_OP_ALLELE_COUNT) {
+            // rows are sized in the first pass and written in a second one at their scanned offsets
+            CU(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), st));
+            P.ac_pass = 1;
+            fn<<<grid, WARPS_PER_CTA * 32, 0, st>>>(P);
             CU(cudaGetLastError());
         }
     }
@@ -328,6 +348,23 @@ int vcfx_cuda_create(const vcfx_cfg *cfg, vcfx_ctx **out) {
     int bps = 1;
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel_for(cfg->op), WARPS_PER_CTA * 32, 0));
     ctx->blocks_per_sm = std::max(1, bps);
+    if (cfg->op == VCFX_OP_ALLELE_COUNT) {
+        if (cfg->n_sel == 0 || !cfg->sel_col || !cfg->sel_names || !cfg->sel_name_off) return fail(VCFX_E_INVALID);
+        ctx->ac_fmt = (cfg->flags & VCFX_F_AC_AGGREGATE) ? AC_AGG : (cfg->flags & VCFX_F_AC_BINARY) ? AC_BIN
+                    : (cfg->flags & VCFX_F_AC_FORWARD) ? AC_TEXT_FWD : AC_TEXT_MT;
+        std::vector<uint32_t> cols(cfg->sel_col, cfg->sel_col + cfg->n_sel);
+        if (ctx->ac_fmt != AC_TEXT_MT)                      // forward-only column walk (:1222-1227): running maximum
+            for (size_t i = 1; i < cols.size(); ++i) cols[i] = std::max(cols[i], cols[i - 1]);
+        ctx->n_sel = cfg->n_sel;
+        ctx->max_col = *std::max_element(cols.begin(), cols.end()) + 1;
+        const size_t nb = cfg->sel_name_off[cfg->n_sel];
+        CUC(cudaMalloc(&ctx->d_sel_col, sizeof(uint32_t) * cfg->n_sel));
+        CUC(cudaMalloc(&ctx->d_name_off, sizeof(uint32_t) * (cfg->n_sel + 1)));
+        CUC(cudaMalloc(&ctx->d_names, nb + 16));
+        CUC(cudaMemcpy(ctx->d_sel_col, cols.data(), sizeof(uint32_t) * cfg->n_sel, cudaMemcpyHostToDevice));
+        CUC(cudaMemcpy(ctx->d_name_off, cfg->sel_name_off, sizeof(uint32_t) * (cfg->n_sel + 1), cudaMemcpyHostToDevice));
+        CUC(cudaMemcpy(ctx->d_names, cfg->sel_names, nb, cudaMemcpyHostToDevice));
+    }
     if (cfg->stream) { ctx->dev_stream = (cudaStream_t)cfg->stream; ctx->dev_stream_owned = false; }
     else { CUC(cudaStreamCreateWithFlags(&ctx->dev_stream, cudaStreamNonBlocking)); ctx->dev_stream_owned = true; }
 #undef CUC
@@ -350,6 +387,7 @@ void vcfx_cuda_destroy(vcfx_ctx *ctx) {
     if (ctx->dev_stream) cudaStreamSynchronize(ctx->dev_stream);
     free_work(ctx->dev_work);
     if (ctx->dev_stream_owned && ctx->dev_stream) cudaStreamDestroy(ctx->dev_stream);
+    cudaFree(ctx->d_sel_col); cudaFree(ctx->d_name_off); cudaFree(ctx->d_names);
     delete ctx;
 }
 

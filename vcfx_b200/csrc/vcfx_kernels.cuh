@@ -33,6 +33,8 @@ constexpr uint32_t WINDOW = 512;
 
 enum : int { OP_VC = 0, OP_AF = 1, OP_HWE = 2, OP_MD = 3, OP_AC = 4 };
 enum : int { MODE_FILE = 0, MODE_STDIN = 1 };
+enum : int { AC_TEXT_MT = 0, AC_TEXT_FWD = 1, AC_AGG = 2, AC_BIN = 3 };
+constexpr uint32_t AC_STAGE = 2048;     // per-warp staging bytes for allele_counter rows
 
 struct Rec {                 // one output row (32 B)
     uint32_t tile;           // owning tile
@@ -66,12 +68,21 @@ struct KParams {
     uint8_t *out;
     uint64_t out_cap;
     uint32_t *tile_lines;            // [n_tiles] lines started in each tile
-    uint32_t *tile_out;              // [n_tiles] output bytes produced by each tile
+    unsigned long long *tile_out;    // [n_tiles] output bytes produced by each tile
     unsigned long long *tile_base;   // [n_tiles] exclusive scan of tile_out (K2a)
     unsigned long long *line_base;   // [n_tiles] exclusive scan of tile_lines (K2a)
     uint32_t *tail_start;            // MISSING_DETECT [n_tiles]: verbatim tail of the tile (offset from tile start)
     uint32_t *tail_len;              //   its length; bit 31 = append a '\n' (stdin mode, unterminated last line)
     uint32_t *tail_off;              //   its offset inside the tile's output
+    // ALLELE_COUNT
+    int32_t ac_fmt;                  // AC_TEXT_MT / AC_TEXT_FWD / AC_AGG / AC_BIN
+    int32_t ac_pass;                 // 0 = size the rows, 1 = write them
+    uint32_t n_sel;                  // selected samples, in output order
+    const uint32_t *sel_col;         // [n_sel] sample column (running maximum in the forward modes)
+    const uint32_t *name_off;        // [n_sel + 1] offsets into names
+    const uint8_t *names;            // selected names, each followed by a tab
+    uint32_t max_col;                // 1 + largest selected column
+    uint2 *col_scratch;              // [resident warps][max_col] (ref, alt) of the current line
     unsigned int *ticket;            // dynamic tile counter (zeroed before launch)
     Rec *recs;
     uint64_t rec_cap;
@@ -314,6 +325,67 @@ __device__ __noinline__ bool md_lane_dots(const uint8_t *p, uint32_t d0, uint32_
     return false;
 }
 
+// allele_counter.cpp:267-294 on the first ':' piece of the sample column starting at p: separators
+// are skipped, '.' consumes one byte, a digit run is one allele (all zeros = ref, else alt).  The
+// reference never advances on any other byte (it hangs); here such a byte is skipped — inputs
+// outside [0-9./|] are outside the parity domain.
+__device__ __noinline__ uint2 ac_sample_slow(const uint8_t *p) {
+    uint32_t ref = 0, alt = 0;
+    for (;;) {
+        uint32_t c = ldb(p);
+        if (c == ':' || c == '\t' || c == '\n') break;
+        if (is_dig(c)) {
+            bool nz = false;
+            do { nz |= (c != '0'); ++p; c = ldb(p); } while (is_dig(c));
+            if (nz) ++alt; else ++ref;
+        } else ++p;
+    }
+    return make_uint2(ref, alt);
+}
+__device__ __forceinline__ uint2 ac_sample_reg(uint32_t q, const uint8_t *p) {
+    const uint32_t b0 = q & 0xFF, b1 = (q >> 8) & 0xFF, b2 = (q >> 16) & 0xFF, b3 = q >> 24;
+    if (b0 == '\t' || b0 == ':' || b0 == '\n') return make_uint2(0u, 0u);
+    const bool d0 = is_dig(b0);
+    if (d0 || b0 == '.') {
+        const uint32_t r0 = (uint32_t)(b0 == '0'), a0 = (uint32_t)(d0 && b0 != '0');
+        if (b1 == '\t' || b1 == ':' || b1 == '\n') return make_uint2(r0, a0);
+        if (is_sep(b1)) {
+            const bool d2 = is_dig(b2);
+            if ((d2 || b2 == '.') && (b3 == '\t' || b3 == ':' || b3 == '\n'))
+                return make_uint2(r0 + (uint32_t)(b2 == '0'), a0 + (uint32_t)(d2 && b2 != '0'));
+        }
+    }
+    return ac_sample_slow(p);
+}
+__device__ __forceinline__ uint32_t dec_len(int v) {       // characters of the decimal form, sign included
+    uint32_t n = (v < 0) ? 1u : 0u;
+    uint32_t u = (v < 0) ? (uint32_t)(-v) : (uint32_t)v;
+    do { ++n; u /= 10u; } while (u);
+    return n;
+}
+__device__ __forceinline__ uint8_t *put_dec(uint8_t *d, int v) {
+    if (v < 0) { *d++ = '-'; v = -v; }
+    char t[12]; int n = 0; uint32_t u = (uint32_t)v;
+    do { t[n++] = (char)('0' + u % 10u); u /= 10u; } while (u);
+    while (n) *d++ = (uint8_t)t[--n];
+    return d;
+}
+// flush n staged bytes (shared memory) to dst: 32-bit stores on the aligned middle of dst
+__device__ __forceinline__ void warp_flush_smem(uint8_t *dst, const uint8_t *st, uint32_t n, int lane) {
+    const uint32_t head = min(n, (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3));
+    if (lane < (int)head) dst[lane] = st[lane];
+    const uint32_t nw = (n - head) >> 2;
+    uint32_t *d4 = reinterpret_cast<uint32_t *>(dst + head);
+    const uint32_t *s4 = reinterpret_cast<const uint32_t *>(st);     // st is 4-byte aligned
+    const uint32_t sh = 8u * (head & 3u);
+    for (uint32_t i = lane; i < nw; i += 32) {
+        const uint32_t w0 = s4[(head >> 2) + i], w1 = sh ? s4[(head >> 2) + i + 1] : 0u;
+        d4[i] = sh ? __funnelshift_r(w0, w1, sh) : w0;
+    }
+    const uint32_t done = head + (nw << 2);
+    if (lane < (int)(n - done)) dst[done + lane] = st[done + lane];
+}
+
 // Tier-1 check of one window (warp-uniform phase and separator): every lane's four rotated words
 // must be [0|1, sep, 0|1, tab].  y = x ^ pat is then [a, 0, b, 0] with a, b the allele values.
 // Returns false (and changes nothing) when any lane disagrees.
@@ -342,12 +414,14 @@ template <int OP>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 vcfx_scan_kernel(const KParams P) {
     __shared__ uint32_t s_tp[WARPS_PER_CTA][12];
+    __shared__ __align__(16) uint8_t s_stage[(OP == OP_AC) ? WARPS_PER_CTA * (AC_STAGE + 16) : 16];
     const int lane = threadIdx.x & 31;
     const int wid = threadIdx.x >> 5;
     volatile uint32_t *tp = s_tp[wid];
     const uint64_t n = P.n;
     const bool strip_cr = (OP == OP_HWE) || (P.mode == MODE_FILE && (OP == OP_AF || OP == OP_VC || OP == OP_MD));
     constexpr int NEED_TABS = (OP == OP_VC) ? 7 : 9;        // the header phase ends once this many tabs are ranked
+    if (OP == OP_AC && P.ac_pass && P.stats->overflow) return;
 
     unsigned long long s_lines = 0, s_data = 0, s_rows = 0, s_pre = 0, s_short = 0, s_flag = 0, s_dots = 0;
 
@@ -389,7 +463,8 @@ vcfx_scan_kernel(const KParams P) {
             }
         }
 
-        uint32_t nlines = 0, out_bytes = 0;
+        uint32_t nlines = 0;
+        unsigned long long out_bytes = 0;
         uint32_t md_prev_end = ls, md_last_end = ls;   // MISSING_DETECT: end of the last rewritten line / of the last line
         bool md_add_nl = false;
 
@@ -636,6 +711,61 @@ vcfx_scan_kernel(const KParams P) {
                 if (OP == OP_AF) { ta += (accp & 0xFFFFu) + (accp >> 16); if (lane == 0) tb += 2u * n_real; }
                 else { ta -= hetp + hap; if (lane == 0) ta += n_real; tb += hetp; tc += hap; }
             }
+            // ================= ALLELE_COUNT: (ref, alt) of every sample column into the warp's scratch
+            if (OP == OP_AC && !hash && tabs >= 9) {
+                uint2 *scr = P.col_scratch + (size_t)(blockIdx.x * WARPS_PER_CTA + wid) * P.max_col;
+                bool firstw = true;
+                for (;;) {
+                    const uint32_t pb = wb + 16 * lane;
+                    uint32_t m0, m1, m2, m3;
+                    int r0;                                  // rank in the line of this lane's first tab
+                    if (firstw) { m0 = t0; m1 = t1; m2 = t2; m3 = t3; r0 = rank0; }
+                    else {
+                        m0 = eq_bytes(cur.x, C_TAB); m1 = eq_bytes(cur.y, C_TAB);
+                        m2 = eq_bytes(cur.z, C_TAB); m3 = eq_bytes(cur.w, C_TAB);
+                        const uint32_t n0 = eq_bytes(cur.x, C_NL), n1 = eq_bytes(cur.y, C_NL);
+                        const uint32_t n2 = eq_bytes(cur.z, C_NL), n3 = eq_bytes(cur.w, C_NL);
+                        const unsigned ebal = __ballot_sync(FULL, (n0 | n1 | n2 | n3) != 0);
+                        if (ebal) {
+                            const int src = __ffs(ebal) - 1;
+                            int k = first_byte(n0, n1, n2, n3);
+                            k = __shfl_sync(FULL, k, src);
+                            e = wb + 16 * src + k; found = true;
+                            m0 &= range_mask(pb, 0, e); m1 &= range_mask(pb + 4, 0, e);
+                            m2 &= range_mask(pb + 8, 0, e); m3 &= range_mask(pb + 12, 0, e);
+                        }
+                        const int cnt = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+                        const int incl = warp_incl_scan(cnt, lane);
+                        r0 = tabs + incl - cnt;
+                        tabs += __shfl_sync(FULL, incl, 31);
+                    }
+                    uint32_t la = __shfl_down_sync(FULL, cur.x, 1);
+                    const uint32_t nx0 = __shfl_sync(FULL, nxt.x, 0);
+                    if (lane == 31) la = nx0;
+                    {
+                        const uint32_t ws[5] = {cur.x, cur.y, cur.z, cur.w, la};
+                        const uint32_t ms[4] = {m0, m1, m2, m3};
+                        int r = r0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t m = ms[j];
+                            while (m) {
+                                const int k = (__ffs(m) - 1) >> 3;
+                                m &= m - 1;
+                                if (r >= 8 && (uint32_t)(r - 8) < P.max_col) {
+                                    const uint32_t q = __funnelshift_rc(ws[j], ws[j + 1], 8u * (uint32_t)(k + 1));
+                                    scr[r - 8] = ac_sample_reg(q, tin + pb + 4 * j + k + 1);
+                                }
+                                ++r;
+                            }
+                        }
+                    }
+                    if (found) break;
+                    firstw = false;
+                    wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
+                }
+                __syncwarp();
+            }
             // ================= MISSING_DETECT: look for a missing genotype in the sample columns
             bool md_flag = false, md_any = false;
             if (OP == OP_MD && !hash && tabs >= 9) {
@@ -755,11 +885,89 @@ vcfx_scan_kernel(const KParams P) {
                         unsigned long long slot = atomicAdd(&P.stats->n_recs, 1ULL);
                         if (slot < P.rec_cap) {
                             Rec r; r.tile = tile; r.ls_rel = (uint32_t)(a0 + ls - a); r.prefix_len = prefix_len;
-                            r.off_in_tile = out_bytes; r.a = ra_; r.b = rb_; r.c = rc_; r.d = 0;
+                            r.off_in_tile = (uint32_t)out_bytes; r.a = ra_; r.b = rb_; r.c = rc_; r.d = 0;
                             P.recs[slot] = r;
                         }
                     }
                     out_bytes += row_len; ++s_rows;
+                }
+            }
+            else if (OP == OP_AC) {
+                // allele_counter.cpp:571 / :1373: empty and '#' lines are skipped; no '\r' handling
+                if (e != ls && !hash) {
+                    if (P.ac_pass == 0) ++s_data;
+                    const uint2 *scr = P.col_scratch + (size_t)(blockIdx.x * WARPS_PER_CTA + wid) * P.max_col;
+                    const uint32_t ns_parsed = tabs >= 9 ? (uint32_t)(tabs - 8) : 0u;
+                    uint32_t n_rows = P.n_sel;
+                    if (P.ac_fmt != AC_TEXT_MT) {
+                        // forward walk: a column exists while its first byte lies before the line end
+                        // (:1222-1229, :1416-1423); rows stop at the first selected column that does not
+                        uint32_t ns_f = 0;
+                        if (tabs >= 9 && tp[8] + 1 < e) ns_f = ns_parsed - ((ldb(tin + e - 1) == '\t') ? 1u : 0u);
+                        uint32_t lo_ = 0, hi_ = P.n_sel;           // first i with sel_col[i] >= ns_f (non-decreasing)
+                        while (lo_ < hi_) { const uint32_t mid = (lo_ + hi_) >> 1; if (P.sel_col[mid] < ns_f) lo_ = mid + 1; else hi_ = mid; }
+                        n_rows = lo_;
+                    }
+                    const uint32_t extra_tabs = tabs >= 5 ? 0u : (uint32_t)(5 - tabs);   // absent fields are empty (:578-601)
+                    const uint32_t prefix_src = tabs >= 5 ? tp[4] + 1 - ls : e - ls;
+                    const uint32_t prefix_len = prefix_src + extra_tabs;
+                    if (P.ac_fmt == AC_AGG) {
+                        uint32_t sr = 0, sa = 0;
+                        for (uint32_t i = lane; i < n_rows; i += 32) {
+                            const uint32_t c = P.sel_col[i];
+                            if (c < ns_parsed) { const uint2 v = scr[c]; sr += v.x; sa += v.y; }
+                        }
+                        sr = __reduce_add_sync(FULL, sr); sa = __reduce_add_sync(FULL, sa);
+                        const uint32_t row_len = prefix_len + dec_len((int)sr) + 1 + dec_len((int)sa) + 1 + dec_len((int)n_rows) + 1;
+                        if (lane == 0) {
+                            unsigned long long slot = atomicAdd(&P.stats->n_recs, 1ULL);
+                            if (slot < P.rec_cap) {
+                                Rec r; r.tile = tile; r.ls_rel = (uint32_t)(a0 + ls - a); r.prefix_len = prefix_src;
+                                r.off_in_tile = (uint32_t)out_bytes; r.a = sr; r.b = sa; r.c = n_rows; r.d = extra_tabs;
+                                P.recs[slot] = r;
+                            }
+                        }
+                        out_bytes += row_len; ++s_rows;
+                    } else {
+                        uint8_t *stage = s_stage + wid * (AC_STAGE + 16);
+                        unsigned long long opos = (P.ac_pass ? P.tile_base[tile] : 0ULL) + out_bytes;
+                        const bool text = (P.ac_fmt != AC_BIN);
+                        for (uint32_t i0 = 0; i0 < n_rows; i0 += 32) {
+                            const uint32_t i = i0 + lane;
+                            int vr = 0, va = 0; uint32_t len = 0, noff = 0, nlen = 0;
+                            if (i < n_rows) {
+                                const uint32_t c = P.sel_col[i];
+                                if (c < ns_parsed) { const uint2 v = scr[c]; vr = (int)v.x; va = (int)v.y; }
+                                if (P.ac_fmt != AC_TEXT_FWD) { vr = (int)(int8_t)vr; va = (int)(int8_t)va; }   // int8 storage (:621-622, :1446-1447)
+                                if (text) {
+                                    noff = P.name_off[i]; nlen = P.name_off[i + 1] - noff;     // name + '\t'
+                                    len = prefix_len + nlen + dec_len(vr) + 1 + dec_len(va) + 1;
+                                } else len = 2;
+                            }
+                            const int incl = warp_incl_scan((int)len, lane);
+                            const uint32_t off = (uint32_t)incl - len;
+                            const uint32_t btot = (uint32_t)__shfl_sync(FULL, incl, 31);
+                            if (P.ac_pass) {
+                                const bool staged = btot <= AC_STAGE;
+                                uint8_t *d = staged ? stage + off : P.out + opos + off;
+                                if (i < n_rows) {
+                                    if (text) {
+                                        const uint8_t *src = tin + ls;
+                                        for (uint32_t k = 0; k < prefix_src; ++k) d[k] = (uint8_t)ldb(src + k);
+                                        d += prefix_src;
+                                        for (uint32_t k = 0; k < extra_tabs; ++k) *d++ = '\t';
+                                        const uint8_t *nm = P.names + noff;
+                                        for (uint32_t k = 0; k < nlen; ++k) d[k] = (uint8_t)ldb(nm + k);
+                                        d += nlen;
+                                        d = put_dec(d, vr); *d++ = '\t'; d = put_dec(d, va); *d++ = '\n';
+                                    } else { d[0] = (uint8_t)vr; d[1] = (uint8_t)va; }
+                                }
+                                if (staged) { __syncwarp(); warp_flush_smem(P.out + opos, stage, btot, lane); __syncwarp(); }
+                            }
+                            opos += btot; out_bytes += btot;
+                        }
+                        if (P.ac_pass == 0) s_rows += n_rows;
+                    }
                 }
             }
             else if (OP == OP_MD) {
@@ -781,7 +989,7 @@ vcfx_scan_kernel(const KParams P) {
                         unsigned long long slot = atomicAdd(&P.stats->n_recs, 1ULL);
                         if (slot < P.rec_cap) {
                             Rec r; r.tile = tile; r.ls_rel = (uint32_t)(a0 + ls - a); r.prefix_len = (uint32_t)(a0 + md_prev_end - a);
-                            r.off_in_tile = out_bytes; r.a = info_off; r.b = info_len; r.c = content_len; r.d = mod_len;
+                            r.off_in_tile = (uint32_t)out_bytes; r.a = info_off; r.b = info_len; r.c = content_len; r.d = mod_len;
                             P.recs[slot] = r;
                         }
                         if (!term) P.stats->last_unterminated_flagged = mod_len;
@@ -795,17 +1003,17 @@ vcfx_scan_kernel(const KParams P) {
             __syncwarp();
             ls = e + 1;
         }
-        s_lines += nlines;
+        if (!(OP == OP_AC && P.ac_pass)) s_lines += nlines;
         if (OP == OP_MD) {
             const uint32_t tail = md_last_end - md_prev_end;
             if (lane == 0) {
                 P.tail_start[tile] = (uint32_t)(a0 + md_prev_end - a);
                 P.tail_len[tile] = tail | (md_add_nl ? 0x80000000u : 0u);
-                P.tail_off[tile] = out_bytes;
+                P.tail_off[tile] = (uint32_t)out_bytes;
             }
             out_bytes += tail + (md_add_nl ? 1u : 0u);
         }
-        if (lane == 0) { P.tile_lines[tile] = nlines; P.tile_out[tile] = out_bytes; }
+        if (lane == 0 && !(OP == OP_AC && P.ac_pass)) { P.tile_lines[tile] = nlines; P.tile_out[tile] = out_bytes; }
     }
     if (lane == 0) {
         if (s_lines) atomicAdd(&P.stats->lines, s_lines);
@@ -886,6 +1094,11 @@ format_rows_kernel(const KParams P) {
         const uint8_t *src = P.in + (uint64_t)r.tile * P.tile_bytes + r.ls_rel;
         for (uint32_t k = 0; k < r.prefix_len; ++k) o[k] = __ldg(src + k);
         o += r.prefix_len;
+        if (OP == OP_AC) {                                       // allele_counter.cpp:1454-1461
+            for (uint32_t k = 0; k < r.d; ++k) *o++ = '\t';
+            o = put_dec(o, (int)r.a); *o++ = '\t'; o = put_dec(o, (int)r.b); *o++ = '\t'; o = put_dec(o, (int)r.c); *o = '\n';
+            continue;
+        }
         char num[24]; int nl;
         if (OP == OP_AF) {
             double v = af_value(r.a, r.b);
