@@ -82,10 +82,35 @@ def test_variant_counter(files):
     both("variant_counter", [str(p)], env={"VCFX_CHUNK_BYTES": "4096"})
 
 
-@pytest.mark.parametrize("tool", ["allele_freq_calc", "hwe_tester", "missing_detector", "variant_counter"])
+@pytest.mark.parametrize("tool", ["allele_freq_calc", "hwe_tester", "missing_detector", "variant_counter", "allele_counter"])
 def test_flags(tool, files):
     for args in (["--help"], ["-v"]):
         both(tool, args)
-    a, b = both(tool, ["/nonexistent/file.vcf"] if tool == "variant_counter" else ["-i", "/nonexistent/file.vcf"])
+    a, b = both(tool, ["/nonexistent/file.vcf"] if tool == "variant_counter" else ["-q", "-i", "/nonexistent/file.vcf"])
     assert a[2] == b[2]
     both(tool, [], stdin=b"")          # empty stdin: per-tool behaviour (help+rc1 / header only / nothing / Total 0)
+
+
+def test_allele_counter(tmp_path):
+    a = tmp_path / "a.vcf"; a.write_bytes(vcfgen.make_vcf(901, n_lines=120, n_samples=6, domain="ac"))
+    b = tmp_path / "b.vcf"; b.write_bytes(synth.make_vcf(3, 300, 40, seed=8))
+    c = tmp_path / "c.vcf"; c.write_bytes(vcfgen.make_vcf(902, n_lines=40, n_samples=3, domain="ac", header="double", final_newline=False))
+    for p in (a, b, c):
+        both("allele_counter", ["-q", "-i", str(p)])
+        both("allele_counter", ["-q", str(p)])
+        both("allele_counter", ["-q"], stdin=p.read_bytes())
+        both("allele_counter", ["-q", "-a", "-i", str(p)])
+        both("allele_counter", ["-q", "-b", "-i", str(p)])
+        both("allele_counter", ["-q", "-l", "2", "-i", str(p)])
+    both("allele_counter", ["-q", "-s", "S1 S0", "-i", str(a)])
+    both("allele_counter", ["-q", "-s", "S1 S0"], stdin=a.read_bytes())
+    both("allele_counter", ["-q", "-s", "S1 nope", "-i", str(a)])
+    both("allele_counter", ["-q", "-a", "-s", "S2 S0", "-i", str(a)])
+    both("allele_counter", ["-q", "-i", str(b)], env={"VCFX_CHUNK_BYTES": str(16 << 10)})
+    # -z: the gzip container may differ, the payload may not
+    mine = run(BIN / "VCFX_allele_counter", ["-q", "-z", "-i", str(a)])
+    ref = run(REF / "VCFX_allele_counter", ["-q", "-z", "-i", str(a)])
+    assert mine[0] == ref[0] == 0 and gzip.decompress(mine[1]) == gzip.decompress(ref[1])
+    # header-less inputs
+    both("allele_counter", ["-q"], stdin=b"##only\n")
+    both("allele_counter", ["-q"], stdin=b"1\t1\t.\tA\tG\t.\t.\t.\tGT\t0/1\n")

@@ -166,11 +166,12 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
             rc = vcfx_cuda_acquire_input(ctx, &buf, &cap);
         }
         if (rc != VCFX_OK) { err = std::string(vcfx_cuda_strerror(rc)) + ": " + vcfx_cuda_last_error(ctx); vcfx_cuda_destroy(ctx); return rc; }
-        if (carry.size() > cap) { err = "a line is longer than the chunk size (set VCFX_CHUNK_BYTES)"; vcfx_cuda_destroy(ctx); return VCFX_E_INVALID; }
-        size_t have = carry.size();
+        // bytes already in hand (the tail of the previous chunk, or what the caller consumed while
+        // looking at the header) go first; the source is only read once they fit
+        size_t have = std::min(carry.size(), cap);
         memcpy(buf, carry.data(), have);
-        carry.clear();
-        while (have < cap) {
+        carry.erase(0, have);
+        while (have < cap && carry.empty()) {
             long r = src.read(buf + have, cap - have);
             if (r < 0) { err = "read error"; vcfx_cuda_destroy(ctx); return VCFX_E_INVALID; }
             if (r == 0) { eof = true; break; }
@@ -181,7 +182,7 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
             const char *nl = static_cast<const char *>(memrchr(buf, '\n', have));
             if (!nl) { err = "a line is longer than the chunk size (set VCFX_CHUNK_BYTES)"; vcfx_cuda_destroy(ctx); return VCFX_E_INVALID; }
             nbytes = (size_t)(nl - buf) + 1;
-            carry.assign(buf + nbytes, have - nbytes);
+            carry.insert(0, buf + nbytes, have - nbytes);
         } else if (opt.last_unterminated_line && nbytes && buf[nbytes - 1] != '\n') {
             const char *nl = static_cast<const char *>(memrchr(buf, '\n', nbytes));
             const char *s = nl ? nl + 1 : buf;
