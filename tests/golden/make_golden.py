@@ -1,0 +1,107 @@
+#!/usr/bin/env python
+"""Regenerate tests/golden/*.json from the compiled REFERENCE tools (oracle/_ref/VCFX_*, built by
+`make -C oracle ref` from /root/reference).  Run in the build container only: the GPU box has no
+reference tree, it just reads the committed fixtures.
+
+Each fixture = one small input (base64) + the stdout / exit code of every reference tool on it, in
+FILE mode (`-i file`) and STDIN mode.  Inputs are our own: the synthetic shapes of BASELINE.json at
+toy size, seeded adversarial files, and hand-written cases that restate what the reference's test
+scripts pin (tests/test_allele_freq_calc.sh, test_variant_counter.sh, test_hwe_tester.sh,
+test_missing_detector.sh, test_allele_counter.sh — SURVEY.md §4)."""
+import base64
+import json
+import sys
+import tempfile
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+from oracle import oracle as O          # noqa: E402
+import vcfgen                           # noqa: E402
+from vcfx_b200 import synth            # noqa: E402
+
+H = "##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t"
+
+
+def hand_cases():
+    c = {}
+    # allele frequencies 0.5 / 0.3333 / 0.8333 style cases, multi-allelic, phased, missing
+    c["af_basic"] = (H + "S1\tS2\tS3\n"
+                     "1\t100\trs1\tA\tG\t.\tPASS\t.\tGT\t0/1\t0/0\t1/1\n"
+                     "1\t200\trs2\tA\tG,T\t.\tPASS\t.\tGT\t0/1\t0/2\t0/0\n"
+                     "1\t300\trs3\tA\tG\t.\tPASS\t.\tGT:DP\t0|1:5\t.|.:0\t1|1:9\n"
+                     "1\t400\trs4\tA\tG\t.\tPASS\t.\tGT\t1/1\t1/1\t0/1\n"
+                     "1\t500\trs5\tA\tG\t.\tPASS\t.\tDP\t5\t6\t7\n")
+    c["af_late_header"] = ("##fileformat=VCFv4.2\n1\t50\t.\tA\tG\t.\t.\t.\tGT\t0/1\n" + H.split("\n")[1] + "S1\n"
+                           "1\t100\t.\tA\tG\t.\t.\t.\tGT\t0/1\n1\t200\t.\tA\n")
+    # rounding tie: FILE prints 0.0313, STDIN 0.0312 (SURVEY.md finding 1)
+    c["af_tie"] = H + "\t".join(f"S{i}" for i in range(16)) + "\n1\t1\t.\tA\tG\t.\t.\t.\tGT\t0/1" + "\t0/0" * 15 + "\n"
+    c["vc_mixed"] = (H + "S1\n1\t1\t.\tA\tG\t.\tPASS\t.\tGT\t0/1\n1\t2\t.\tA\n\n#late comment\n1\t3\t.\tA\tG\t.\tPASS\tDP=1\n"
+                     "1\t4\t.\tA\tG\t.\tPASS\n")
+    c["hwe_basic"] = (H + "S1\tS2\tS3\tS4\n"
+                      "1\t100\t.\tA\tG\t.\t.\t.\tGT\t0/0\t0/1\t1/1\t0/1\n"
+                      "1\t200\t.\tA\tG,T\t.\t.\t.\tGT\t0/1\t1/2\t0/0\t0/0\n"
+                      "1\t300\t.\tA\tG\t.\t.\t.\tDP:GT\t3:0/1\t3:0/1\t3:0/1\t3:0/1\n"
+                      "1\t400\t.\tA\tG\t.\t.\t.\tGT\t0/1\t0/1\t0/1\t0/1\n"
+                      "1\t500\t.\tA\tG\t.\t.\t.\tGT\t./.\t0|1\t1\t1/1\n")
+    c["md_basic"] = (H + "S1\tS2\n"
+                     "1\t100\t.\tA\tG\t.\tPASS\tDP=25\tGT\t0/1\t./.\n"
+                     "1\t200\t.\tA\tG\t.\tPASS\t.\tGT\t.\t1\n"
+                     "1\t300\t.\tA\tG\t.\tPASS\tAF=0.5;\tGT:GQ\t0/1:0.5\t.|1:3\n"
+                     "1\t400\t.\tA\tG\t.\tPASS\tDP=1\tGT\t0/1\t1/1\n"
+                     "1\t500\t.\tA\tG\n")
+    c["ac_basic"] = (H + "X\tY\n"
+                     "1\t100\trs1\tA\tG\t.\tPASS\t.\tGT\t0/1\t1/2\n"
+                     "1\t200\trs2\tA\tG\t.\tPASS\t.\tGT\t./.\t0/.\n"
+                     "1\t300\trs3\tA\tG\t.\tPASS\t.\tGT:DP\t0|0:3\t1|1:4\n"
+                     "1\t400\n")
+    return {k: v.encode() for k, v in c.items()}
+
+
+def run_all(data: bytes, ac_ok: bool, md_file_ok: bool = True):
+    out = {}
+    with tempfile.NamedTemporaryFile(suffix=".vcf") as f:
+        f.write(data); f.flush()
+        for tool in ("allele_freq_calc", "hwe_tester", "missing_detector"):
+            extra = ["-t", "1"] if tool == "missing_detector" else []
+            if not (tool == "missing_detector" and not md_file_ok):
+                rc, so, _ = O.run_ref(tool, ["-q", *extra, "-i", f.name])
+                out[f"{tool}.file"] = [rc, base64.b64encode(so).decode()]
+            rc, so, _ = O.run_ref(tool, ["-q"] if tool != "hwe_tester" else [], stdin=data)
+            out[f"{tool}.stdin"] = [rc, base64.b64encode(so).decode()]
+        for strict in (False, True):
+            a = ["--strict"] if strict else []
+            rc, so, se = O.run_ref("variant_counter", [*a, f.name])
+            out[f"variant_counter.file.strict{int(strict)}"] = [rc, base64.b64encode(so).decode(), se.count(b"Warning")]
+            rc, so, se = O.run_ref("variant_counter", a, stdin=data)
+            out[f"variant_counter.stdin.strict{int(strict)}"] = [rc, base64.b64encode(so).decode(), se.count(b"Warning")]
+        if ac_ok:
+            for key, args, stdin in (("mt", ["-q", "-i", f.name], None), ("stream", ["-q"], data), ("agg", ["-q", "-a", "-i", f.name], None),
+                                     ("bin", ["-q", "-b", "-i", f.name], None), ("limit2", ["-q", "-l", "2", "-i", f.name], None)):
+                rc, so, _ = O.run_ref("allele_counter", args, stdin=stdin)
+                out[f"allele_counter.{key}"] = [rc, base64.b64encode(so).decode()]
+    return out
+
+
+def main():
+    assert O.have_reference(), "build the reference tools first: make -C oracle ref"
+    fixtures = {}
+    for name, data in hand_cases().items():
+        fixtures[name] = dict(input=base64.b64encode(data).decode(), expect=run_all(data, ac_ok=True))
+    for shape, V, S in ((1, 40, 12), (2, 12, 300), (3, 30, 60), (4, 12, 9)):
+        data = synth.make_vcf(shape, V, S, seed=70 + shape)
+        fixtures[f"shape{shape}"] = dict(input=base64.b64encode(data).decode(), expect=run_all(data, ac_ok=True))
+    for seed in range(6):
+        data = vcfgen.make_vcf(7000 + seed, n_lines=25, n_samples=2 + seed, crlf=(seed == 2), final_newline=(seed != 3),
+                               header=["normal", "late", "normal", "none", "double", "normal"][seed])
+        fixtures[f"fuzz{seed}"] = dict(input=base64.b64encode(data).decode(), expect=run_all(data, ac_ok=False))
+        data = vcfgen.make_vcf(7100 + seed, n_lines=25, n_samples=2 + seed, domain="ac", final_newline=(seed != 3),
+                               header=["normal", "late", "normal", "none", "double", "normal"][seed])
+        fixtures[f"acfuzz{seed}"] = dict(input=base64.b64encode(data).decode(), expect=run_all(data, ac_ok=True))
+    (HERE / "reference_outputs.json").write_text(json.dumps(fixtures, indent=0, sort_keys=True))
+    print(f"wrote {len(fixtures)} fixtures, {(HERE / 'reference_outputs.json').stat().st_size} bytes")
+
+
+if __name__ == "__main__":
+    main()

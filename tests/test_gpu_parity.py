@@ -143,3 +143,28 @@ def test_allele_counter_shapes(cuda_api, oracle, shape, V, S):
     # several chunks; the first one overflows the default output slot and is re-run with exact sizes
     r = cuda_api.allele_counter(data, oracle.AC_MT_TEXT, chunk_bytes=256 << 10)
     _cmp(f"ac shape{shape} chunks", r.out, oracle.allele_counter(data).out)
+
+
+def test_gpu_matches_reference_golden(cuda_api):
+    """The CUDA path against the committed outputs of the reference tools themselves."""
+    import golden_util
+    api = cuda_api
+    for name, (data, exp) in sorted(golden_util.load().items()):
+        for mode_name, mode in (("file", 0), ("stdin", 1)):
+            for tool, fn in (("allele_freq_calc", api.allele_freq_calc), ("hwe_tester", api.hwe_tester), ("missing_detector", api.missing_detector)):
+                key = f"{tool}.{mode_name}"
+                if key in exp:
+                    r = fn(data, mode)
+                    assert r.rc == exp[key][0], (name, key)
+                    if r.rc == 0:
+                        _cmp(f"golden {name} {key}", r.out, exp[key][1])
+            for strict in (0, 1):
+                key = f"variant_counter.{mode_name}.strict{strict}"
+                r = api.variant_counter(data, mode, bool(strict))
+                assert (r.rc, r.out) == exp[key][:2], (name, key)
+        for key, (path, fmt, limit) in {"mt": (0, 0, 0), "stream": (1, 0, 0), "agg": (2, 1, 0), "bin": (2, 2, 0), "limit2": (2, 0, 2)}.items():
+            k = f"allele_counter.{key}"
+            if k in exp:
+                r = api.allele_counter(data, path, fmt, limit)
+                assert r.rc == exp[k][0], (name, k)
+                _cmp(f"golden {name} {k}", r.out, exp[k][1])
