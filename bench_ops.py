@@ -1,0 +1,95 @@
+#!/usr/bin/env python
+"""bench_ops.py — kernel-only throughput of every op on the BASELINE shapes (1 GPU, data resident
+in HBM).  Complements bench.py (which reports the contractual C2 line): one JSON line per
+(config, tool) with the event-timed kernel time, algorithmic bytes (input + output) per second and
+the fraction of the measured HBM peak.
+
+  C2  427,409 x 2,504 phased GT                      allele_freq_calc, variant_counter, hwe_tester
+  C3  C2 shape + 5 % missing / unphased / haploid    missing_detector, allele_counter (TEXT, -a), allele_freq_calc
+  C4  GT:AD:DP:GQ:PL multi-allelic (scaled to ~4 GB) hwe_tester, allele_freq_calc
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import statistics
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full variant counts")
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--configs", default="C2,C3,C4")
+    args = ap.parse_args()
+
+    import numpy as np
+    import torch
+    from vcfx_b200 import api, synth
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    peak = 6545.3
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        peak = float(json.loads(p.read_text())["hbm_gbs"])
+    S = 2504
+    plans = {
+        "C2": (2, int(427409 * args.scale), [("allele_freq_calc", api.OP_ALLELE_FREQ, 0), ("variant_counter", api.OP_VARIANT_COUNT, 0),
+                                             ("hwe_tester", api.OP_HWE, 0)]),
+        "C3": (3, int(427409 * args.scale), [("missing_detector", api.OP_MISSING_DETECT, 0), ("allele_counter -a", api.OP_ALLELE_COUNT, api.F_AC_AGGREGATE),
+                                             ("allele_counter", api.OP_ALLELE_COUNT, 0), ("allele_freq_calc", api.OP_ALLELE_FREQ, 0)]),
+        "C4": (4, int(60000 * args.scale), [("hwe_tester", api.OP_HWE, 0), ("allele_freq_calc", api.OP_ALLELE_FREQ, 0)]),
+    }
+    for cname in args.configs.split(","):
+        shape, V, tools = plans[cname]
+        hdr = synth.header(shape, S, shape)
+        cap = len(hdr) + synth.line_bound(shape, S) * V
+        host = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+        hnp = host.numpy()
+        hnp[: len(hdr)] = np.frombuffer(hdr, dtype=np.uint8)
+        t0 = time.perf_counter()
+        nbytes = len(hdr) + synth.lines_into(hnp[len(hdr):], shape, S, 0, V, seed=shape)
+        d_in = torch.empty(nbytes + api.DEVICE_PAD, dtype=torch.uint8, device=dev)
+        d_in[:nbytes].copy_(host[:nbytes]); torch.cuda.synchronize()
+        print(f"[{cname}] {nbytes / 1e9:.2f} GB, {V} variants, generated in {time.perf_counter() - t0:.1f}s", file=sys.stderr, flush=True)
+        del host
+        names = [b"HG%05d" % (96 + i) for i in range(S)]
+        for tname, op, flags in tools:
+            out_cap = 64 << 20
+            if op == api.OP_MISSING_DETECT:
+                out_cap = nbytes + nbytes // 50 + (1 << 20)
+            if op == api.OP_ALLELE_COUNT and flags == 0:
+                out_cap = int(nbytes * 9.5) + (1 << 20)
+            d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
+            kw = dict(sel_cols=list(range(S)), sel_names=names) if op == api.OP_ALLELE_COUNT else {}
+            ctx = api.Context(op, api.FILE, flags=flags, **kw)
+            vf = api.find_chrom_header(hdr) if op == api.OP_ALLELE_FREQ else (api.first_data_offset(hdr) if op == api.OP_MISSING_DETECT else 0)
+            ms = []
+            st = None
+            for i in range(args.reps + 2):
+                ctx.run_device(d_in.data_ptr(), nbytes, d_out.data_ptr(), out_cap, valid_from=vf)
+                st = ctx.sync()
+                if i >= 2:
+                    ms.append(st.kernel_ms)
+            k = statistics.median(ms)
+            alg = nbytes + int(st.bytes_out)
+            line = {"config": cname, "tool": tname, "variants": V, "samples": S, "input_GB": nbytes / 1e9, "output_GB": st.bytes_out / 1e9,
+                    "kernel_ms": k, "input_GB_per_s": nbytes / k / 1e6, "algorithmic_GB_per_s": alg / k / 1e6,
+                    "frac_of_measured_hbm_peak": alg / k / 1e6 / peak, "genotypes_per_s": V * S / (k / 1e3),
+                    "rows": int(st.rows), "flagged": int(st.flagged), "data_lines": int(st.data_lines)}
+            print(json.dumps(line), flush=True)
+            ctx.close()
+            del d_out
+            torch.cuda.empty_cache()
+        del d_in
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()

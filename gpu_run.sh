@@ -1,10 +1,6 @@
 cd $GRAFT_REPO_ROOT
-( time timeout 1200 python -m pytest tests -x -q -m gpu ) 2>&1 | tail -6
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r1.json 2> gpurun_out/bench_r1.err; tail -2 gpurun_out/bench_r1.err; cat gpurun_out/bench_r1.json
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r1_ref.json 2>> gpurun_out/bench_r1.err; cat gpurun_out/bench_r1_ref.json
-CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
-$CMD > gpurun_out/ncu_plain.json 2> gpurun_out/ncu_plain.err && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_r1.csv $CMD > gpurun_out/ncu_l.log 2>&1
-$CMD > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:vcfx_scan_kernel -s 8 -c 2 -o gpurun_out/prof_r1_c2 $CMD > gpurun_out/ncu_f.log 2>&1
-tail -2 gpurun_out/ncu_f.log
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -4
+python bench_ops.py > gpurun_out/ops_r1.jsonl 2> gpurun_out/ops_r1.err; tail -3 gpurun_out/ops_r1.err; cat gpurun_out/ops_r1.jsonl | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l); print(d['config'],d['tool'],'in %.2fGB out %.2fGB'%(d['input_GB'],d['output_GB']),'%.3f ms'%d['kernel_ms'],'%.0f GB/s'%d['algorithmic_GB_per_s'],'%.1f%%'%(100*d['frac_of_measured_hbm_peak']),d['rows'],d['flagged'])"

@@ -236,7 +236,7 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
         tile_scan_kernel<<<1, 1024, 0, st>>>(P);
         CU(cudaGetLastError());
         if (kernel_fn ff = format_kernel_for(ctx->cfg.op, ctx->ac_fmt)) {
-            ff<<<ctx->sm_count * (ctx->cfg.op == VCFX_OP_MISSING_DETECT ? 8 : 4), 256, 0, st>>>(P);
+            ff<<<ctx->sm_count * (ctx->cfg.op == VCFX_OP_MISSING_DETECT ? 8 : 16), 256, 0, st>>>(P);
             CU(cudaGetLastError());
         } else if (ctx->cfg.op == VCFX_OP_ALLELE_COUNT) {
             // rows are sized in the first pass and written in a second one at their scanned offsets

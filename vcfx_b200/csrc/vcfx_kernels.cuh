@@ -109,6 +109,21 @@ __device__ __forceinline__ uint32_t range_mask(uint32_t base, uint32_t lo, uint3
     return m;
 }
 
+// The same for the four words of a lane at once (bytes pb .. pb+15): one 16-bit keep mask, then each
+// nibble is spread to the 0x80 bit of its byte.  Cheaper than four range_mask calls.
+__device__ __forceinline__ uint32_t lane_keep16(uint32_t pb, uint32_t lo, uint32_t hi) {
+    const uint32_t a = lo > pb ? min(lo - pb, 16u) : 0u;
+    const uint32_t b = hi > pb ? min(hi - pb, 16u) : 0u;
+    return b > a ? (((1u << b) - 1u) & ~((1u << a) - 1u)) : 0u;
+}
+__device__ __forceinline__ uint32_t nib80(uint32_t keep16, int j) {
+    return ((((keep16 >> (4 * j)) & 0xFu) * 0x00204081u) & 0x01010101u) << 7;
+}
+__device__ __forceinline__ void clip4(uint32_t &m0, uint32_t &m1, uint32_t &m2, uint32_t &m3, uint32_t pb, uint32_t lo, uint32_t hi) {
+    const uint32_t k = lane_keep16(pb, lo, hi);
+    m0 &= nib80(k, 0); m1 &= nib80(k, 1); m2 &= nib80(k, 2); m3 &= nib80(k, 3);
+}
+
 __device__ __forceinline__ uint4 ld16(const uint8_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
 __device__ __forceinline__ uint32_t ldb(const uint8_t *p) { return (uint32_t)__ldg(p); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -447,10 +462,8 @@ vcfx_scan_kernel(const KParams P) {
             while (wb < to) {
                 const uint32_t pb = wb + 16 * lane;
                 uint4 v = ld16(tin + pb);
-                uint32_t m0 = eq_bytes(v.x, C_NL) & range_mask(pb, from, to);
-                uint32_t m1 = eq_bytes(v.y, C_NL) & range_mask(pb + 4, from, to);
-                uint32_t m2 = eq_bytes(v.z, C_NL) & range_mask(pb + 8, from, to);
-                uint32_t m3 = eq_bytes(v.w, C_NL) & range_mask(pb + 12, from, to);
+                uint32_t m0 = eq_bytes(v.x, C_NL), m1 = eq_bytes(v.y, C_NL), m2 = eq_bytes(v.z, C_NL), m3 = eq_bytes(v.w, C_NL);
+                clip4(m0, m1, m2, m3, pb, from, to);
                 unsigned bal = __ballot_sync(FULL, (m0 | m1 | m2 | m3) != 0);
                 if (bal) {
                     int src = __ffs(bal) - 1;
@@ -495,8 +508,8 @@ vcfx_scan_kernel(const KParams P) {
                 uint32_t n0 = eq_bytes(cur.x, C_NL), n1 = eq_bytes(cur.y, C_NL);
                 uint32_t n2 = eq_bytes(cur.z, C_NL), n3 = eq_bytes(cur.w, C_NL);
                 if (wb < ls) {                 // bytes before the line start (first window only)
-                    uint32_t k0 = range_mask(pb, ls, ~0u), k1 = range_mask(pb + 4, ls, ~0u);
-                    uint32_t k2 = range_mask(pb + 8, ls, ~0u), k3 = range_mask(pb + 12, ls, ~0u);
+                    const uint32_t k = lane_keep16(pb, ls, ~0u);
+                    const uint32_t k0 = nib80(k, 0), k1 = nib80(k, 1), k2 = nib80(k, 2), k3 = nib80(k, 3);
                     t0 &= k0; t1 &= k1; t2 &= k2; t3 &= k3; n0 &= k0; n1 &= k1; n2 &= k2; n3 &= k3;
                 }
                 unsigned ebal = __ballot_sync(FULL, (n0 | n1 | n2 | n3) != 0);
@@ -505,8 +518,7 @@ vcfx_scan_kernel(const KParams P) {
                     int k = first_byte(n0, n1, n2, n3);
                     k = __shfl_sync(FULL, k, src);
                     e = wb + 16 * src + k; found = true;
-                    t0 &= range_mask(pb, 0, e); t1 &= range_mask(pb + 4, 0, e);
-                    t2 &= range_mask(pb + 8, 0, e); t3 &= range_mask(pb + 12, 0, e);
+                    clip4(t0, t1, t2, t3, pb, 0, e);
                 }
                 int total = 0;
                 if (!hash) {
@@ -561,7 +573,8 @@ vcfx_scan_kernel(const KParams P) {
                 // path below, so the speculation costs nothing in correctness.
                 const uint32_t tab8 = tp[8];
                 const uint32_t sep0 = ldb(tin + tab8 + 2);
-                const bool t1_on = (gt_index == 0) && (sep0 == '|' || sep0 == '/');
+                const bool lat_possible = (gt_index == 0) && (tp[8] - tp[7] == 3);      // FORMAT is exactly "GT"
+                const bool t1_on = lat_possible && (sep0 == '|' || sep0 == '/');
                 const uint32_t tau = tab8 & 3u;
                 const uint32_t sh_u = 8u * (tau + 1u);
                 const uint32_t pat = 0x09300030u | (sep0 << 8);
@@ -632,8 +645,9 @@ vcfx_scan_kernel(const KParams P) {
                         // truncated last sample ("1\n" would read "1|0")
                         if ((first_win || found) && (!found || ((e - tau) & 3u) == 0)) {
                             const uint32_t lo = first_win ? tab8 : 0u, hi = found ? e : ~0u;
-                            const uint32_t k0 = (range_mask(pb, lo, hi) >> 7) * 0xFFu, k1 = (range_mask(pb + 4, lo, hi) >> 7) * 0xFFu;
-                            const uint32_t k2 = (range_mask(pb + 8, lo, hi) >> 7) * 0xFFu, k3 = (range_mask(pb + 12, lo, hi) >> 7) * 0xFFu;
+                            const uint32_t kk = lane_keep16(pb, lo, hi);
+                            const uint32_t k0 = (nib80(kk, 0) >> 7) * 0xFFu, k1 = (nib80(kk, 1) >> 7) * 0xFFu;
+                            const uint32_t k2 = (nib80(kk, 2) >> 7) * 0xFFu, k3 = (nib80(kk, 3) >> 7) * 0xFFu;
                             const uint32_t k4 = (range_mask(pb + 16, lo, hi) >> 7) * 0xFFu;
                             done = t1_eval<OP>((cur.x & k0) | (fill & ~k0), (cur.y & k1) | (fill & ~k1),
                                                (cur.z & k2) | (fill & ~k2), (cur.w & k3) | (fill & ~k3),
@@ -650,8 +664,9 @@ vcfx_scan_kernel(const KParams P) {
                     if (!done) {
                         // exact path for this window
                         uint32_t packed = 0;
-                        const bool lat = lane_lattice<OP>(cur.x, cur.y, cur.z, cur.w, la, packed) && (gt_index == 0);
-                        gbal = __ballot_sync(FULL, lat);
+                        // samples of a FORMAT with more keys carry ':' pieces: no lattice there, do not look for one
+                        const bool lat = lat_possible && lane_lattice<OP>(cur.x, cur.y, cur.z, cur.w, la, packed);
+                        gbal = lat_possible ? __ballot_sync(FULL, lat) : 0u;
                         uint32_t m0, m1, m2, m3;
                         const uint32_t n0 = eq_bytes(cur.x, C_NL);
                         if (first_win) { m0 = t0; m1 = t1; m2 = t2; m3 = t3; }   // already clipped to [ls, e)
@@ -669,14 +684,13 @@ vcfx_scan_kernel(const KParams P) {
                                 }
                             }
                             if (found) {
-                                m0 &= range_mask(pb, 0, e); m1 &= range_mask(pb + 4, 0, e);
-                                m2 &= range_mask(pb + 8, 0, e); m3 &= range_mask(pb + 12, 0, e);
+                                clip4(m0, m1, m2, m3, pb, 0, e);
                             }
                         }
                         // a lattice lane may be used when its bytes before the first tab are vouched for
                         // (previous lane lattice, or no '\n' in word 0) and all its tabs are sample tabs
-                        bool pg = __shfl_up_sync(FULL, (int)lat, 1) != 0;
-                        if (lane == 0) pg = prev_ok;
+                        bool pg = false;
+                        if (lat_possible) { pg = __shfl_up_sync(FULL, (int)lat, 1) != 0; if (lane == 0) pg = prev_ok; }
                         const bool use_lat = lat && (pg || n0 == 0) && !(first_win && rank0 < 8);
                         if (use_lat) {
                             if (!found || pb < e) {          // a vouched lattice lane holds no '\n'
@@ -695,9 +709,32 @@ vcfx_scan_kernel(const KParams P) {
                                 while (d > 0 && m3) { m3 &= m3 - 1; --d; }
                             }
                             if (m0 | m1 | m2 | m3) {
-                                const uint3 r = lane_samples_generic<OP>(cur.x, cur.y, cur.z, cur.w, la, m0, m1, m2, m3,
-                                                                         tin + pb, strip_cr, gt_index);
-                                ta += r.x; tb += r.y; tc += r.z;
+                                bool handled = false;
+                                if (__popc(m0) + __popc(m1) + __popc(m2) + __popc(m3) == 1 && gt_index == 0) {
+                                    // one sample starts in this lane (the usual case when FORMAT has several
+                                    // keys): classify its first four bytes right here
+                                    const int B = first_byte(m0, m1, m2, m3);
+                                    const uint32_t lo_ = B < 4 ? cur.x : B < 8 ? cur.y : B < 12 ? cur.z : cur.w;
+                                    const uint32_t hi_ = B < 4 ? cur.y : B < 8 ? cur.z : B < 12 ? cur.w : la;
+                                    const uint32_t q = __funnelshift_rc(lo_, hi_, 8u * (uint32_t)((B & 3) + 1));
+                                    const uint32_t b0 = q & 0xFF, b1 = (q >> 8) & 0xFF, b2 = (q >> 16) & 0xFF, b3 = q >> 24;
+                                    if (OP == OP_AF) {
+                                        const bool t3 = (b3 == '\t' || b3 == ':' || b3 == '\n');
+                                        if (is_dig(b0) && is_sep(b1) && is_dig(b2) && t3) {
+                                            tb += 2; ta += (uint32_t)(b0 != '0') + (uint32_t)(b2 != '0'); handled = true;
+                                        } else if (b0 == '.' && is_sep(b1) && b2 == '.' && t3) handled = true;
+                                    } else {
+                                        if (is_dig(b0) && is_sep(b1) && is_dig(b2) && !is_dig(b3)) {
+                                            if (b0 <= '1' && b2 <= '1') { const uint32_t c = (b0 - '0') + (b2 - '0'); ta += (c == 0); tb += (c == 1); tc += (c == 2); }
+                                            handled = true;
+                                        } else if (b0 == '.') handled = true;
+                                    }
+                                }
+                                if (!handled) {
+                                    const uint3 r = lane_samples_generic<OP>(cur.x, cur.y, cur.z, cur.w, la, m0, m1, m2, m3,
+                                                                             tin + pb, strip_cr, gt_index);
+                                    ta += r.x; tb += r.y; tc += r.z;
+                                }
                             }
                         }
                     }
@@ -731,8 +768,7 @@ vcfx_scan_kernel(const KParams P) {
                             int k = first_byte(n0, n1, n2, n3);
                             k = __shfl_sync(FULL, k, src);
                             e = wb + 16 * src + k; found = true;
-                            m0 &= range_mask(pb, 0, e); m1 &= range_mask(pb + 4, 0, e);
-                            m2 &= range_mask(pb + 8, 0, e); m3 &= range_mask(pb + 12, 0, e);
+                            clip4(m0, m1, m2, m3, pb, 0, e);
                         }
                         const int cnt = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
                         const int incl = warp_incl_scan(cnt, lane);
@@ -789,8 +825,7 @@ vcfx_scan_kernel(const KParams P) {
                         uint32_t d2 = eq_bytes(cur.z, C_DOT), d3 = eq_bytes(cur.w, C_DOT);
                         if (firstw || found) {
                             const uint32_t l = firstw ? lo : 0u, h = found ? e : ~0u;
-                            d0 &= range_mask(pb, l, h); d1 &= range_mask(pb + 4, l, h);
-                            d2 &= range_mask(pb + 8, l, h); d3 &= range_mask(pb + 12, l, h);
+                            clip4(d0, d1, d2, d3, pb, l, h);
                         }
                         const bool any = (d0 | d1 | d2 | d3) != 0;
                         if (__any_sync(FULL, any)) {
@@ -1032,36 +1067,42 @@ vcfx_scan_kernel(const KParams P) {
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(const KParams P) {
-    __shared__ unsigned long long part_o[1024], part_l[1024];
-    const uint32_t tid = threadIdx.x, n_tiles = P.n_tiles;
-    const uint32_t per = (n_tiles + 1023) / 1024;
-    const uint32_t s = min(tid * per, n_tiles), e = min(s + per, n_tiles);
-    unsigned long long so = 0, sl = 0;
-    for (uint32_t i = s; i < e; ++i) { so += P.tile_out[i]; sl += P.tile_lines[i]; }
-    part_o[tid] = so; part_l[tid] = sl;
+    __shared__ unsigned long long ws_o[32], ws_l[32];
+    __shared__ unsigned long long carry_o, carry_l;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5, n_tiles = P.n_tiles;
+    if (tid == 0) { carry_o = 0; carry_l = 0; }
     __syncthreads();
-    if (tid < 32) {            // warp 0 scans the 1024 partials, 32 per lane
-        unsigned long long lo = 0, ll = 0;
-        for (int i = 0; i < 32; ++i) { lo += part_o[tid * 32 + i]; ll += part_l[tid * 32 + i]; }
-        unsigned long long io = lo, il = ll;
+    // 1024 tiles per round: coalesced loads, warp scans, one scan over the 32 warp sums
+    for (uint32_t base = 0; base < n_tiles; base += 1024) {
+        const uint32_t i = base + tid;
+        const unsigned long long vo = (i < n_tiles) ? P.tile_out[i] : 0ULL;
+        const unsigned long long vl = (i < n_tiles) ? (unsigned long long)P.tile_lines[i] : 0ULL;
+        unsigned long long io = vo, il = vl;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            unsigned long long to = __shfl_up_sync(FULL, io, o), tl2 = __shfl_up_sync(FULL, il, o);
-            if ((int)tid >= o) { io += to; il += tl2; }
+            const unsigned long long to = __shfl_up_sync(FULL, io, o), tl2 = __shfl_up_sync(FULL, il, o);
+            if ((int)lane >= o) { io += to; il += tl2; }
         }
-        unsigned long long ro = io - lo, rl = il - ll;
-        for (int i = 0; i < 32; ++i) {
-            unsigned long long vo = part_o[tid * 32 + i], vl = part_l[tid * 32 + i];
-            part_o[tid * 32 + i] = ro; part_l[tid * 32 + i] = rl; ro += vo; rl += vl;
+        if (lane == 31) { ws_o[w] = io; ws_l[w] = il; }
+        __syncthreads();
+        if (w == 0) {
+            unsigned long long so = ws_o[lane], sl = ws_l[lane];
+            const unsigned long long so0 = so, sl0 = sl;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long to = __shfl_up_sync(FULL, so, o), tl2 = __shfl_up_sync(FULL, sl, o);
+                if ((int)lane >= o) { so += to; sl += tl2; }
+            }
+            ws_o[lane] = so - so0; ws_l[lane] = sl - sl0;          // exclusive over warps
         }
-        if (tid == 31) P.stats->bytes_out = io;
+        __syncthreads();
+        const unsigned long long eo = carry_o + ws_o[w] + (io - vo), el = carry_l + ws_l[w] + (il - vl);
+        if (i < n_tiles) { P.tile_base[i] = eo; P.line_base[i] = el; }
+        __syncthreads();
+        if (tid == 1023) { carry_o = eo + vo; carry_l = el + vl; }
+        __syncthreads();
     }
-    __syncthreads();
-    unsigned long long ro = part_o[tid], rl = part_l[tid];
-    for (uint32_t i = s; i < e; ++i) {
-        P.tile_base[i] = ro; P.line_base[i] = rl;
-        ro += P.tile_out[i]; rl += P.tile_lines[i];
-    }
+    if (tid == 0) P.stats->bytes_out = carry_o;
     __syncthreads();
     unsigned long long nev = P.stats->n_events;
     if (nev > P.ev_cap) nev = P.ev_cap;
@@ -1117,9 +1158,10 @@ format_rows_kernel(const KParams P) {
 // rewritten line together with the verbatim bytes between it and the previous rewritten line
 // of its tile, or the verbatim tail of a tile.
 // ---------------------------------------------------------------------------------------
-// warp-cooperative copy of n bytes, any alignment: 32-bit stores on the aligned middle of dst, each
-// built from the two aligned source words that straddle it
-__device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint32_t n, int lane) {
+// warp-cooperative copy of n bytes, any alignment.  Large copies run on 128-bit stores to the
+// 16-byte aligned middle of dst, each built from the two aligned 16-byte source blocks that straddle
+// it (funnel shifts by the constant byte misalignment); the rest goes 32 bits / 1 byte at a time.
+__device__ __forceinline__ void warp_copy_words(uint8_t *dst, const uint8_t *src, uint32_t n, int lane) {
     if (n == 0) return;
     const uint32_t head = min(n, (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3));
     if (lane < (int)head) dst[lane] = __ldg(src + lane);
@@ -1132,6 +1174,38 @@ __device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint
     else { for (uint32_t i = lane; i < nw; i += 32) d4[i] = __funnelshift_r(__ldg(s4 + i), __ldg(s4 + i + 1), sh); }
     const uint32_t done = nw << 2, rem = n - done;
     if (lane < (int)rem) dst[done + lane] = __ldg(src + done + lane);
+}
+
+template <int WS>   // WS = whole 32-bit words of misalignment between src and the 16-byte grid of dst
+__device__ __forceinline__ void copy16_loop(uint4 *d16, const uint4 *s16, uint32_t nq, uint32_t bs, int lane) {
+    for (uint32_t i = lane; i < nq; i += 32) {
+        const uint4 A = __ldg(s16 + i), B = __ldg(s16 + i + 1);
+        const uint32_t w[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
+        uint4 o;
+        o.x = __funnelshift_r(w[WS], w[WS + 1], bs); o.y = __funnelshift_r(w[WS + 1], w[WS + 2], bs);
+        o.z = __funnelshift_r(w[WS + 2], w[WS + 3], bs); o.w = __funnelshift_r(w[WS + 3], w[WS + 4], bs);
+        d16[i] = o;
+    }
+}
+
+__device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint32_t n, int lane) {
+    if (n < 256) { warp_copy_words(dst, src, n, lane); return; }
+    const uint32_t head = (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15);
+    warp_copy_words(dst, src, head, lane);
+    dst += head; src += head; n -= head;
+    const uint32_t nq = n >> 4;                                   // 16-byte stores
+    const uint32_t mis = (uint32_t)((uintptr_t)src & 15);
+    const uint4 *s16 = reinterpret_cast<const uint4 *>(src - mis);
+    uint4 *d16 = reinterpret_cast<uint4 *>(dst);
+    const uint32_t bs = 8u * (mis & 3u);
+    if (mis == 0) { for (uint32_t i = lane; i < nq; i += 32) d16[i] = __ldg(s16 + i); }
+    else switch (mis >> 2) {                                      // the last block read ends < 32 B past src + n (pad)
+        case 0: copy16_loop<0>(d16, s16, nq, bs, lane); break;
+        case 1: copy16_loop<1>(d16, s16, nq, bs, lane); break;
+        case 2: copy16_loop<2>(d16, s16, nq, bs, lane); break;
+        default: copy16_loop<3>(d16, s16, nq, bs, lane); break;
+    }
+    warp_copy_words(dst + (nq << 4), src + (nq << 4), n - (nq << 4), lane);
 }
 
 __global__ void __launch_bounds__(256)
