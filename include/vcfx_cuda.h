@@ -139,6 +139,12 @@ void vcfx_cuda_destroy(vcfx_ctx *ctx);
  *                  preserving).  The pointer stays valid until the next acquire/submit.     */
 int vcfx_cuda_acquire_input(vcfx_ctx *ctx, char **buf, size_t *cap);
 int vcfx_cuda_submit(vcfx_ctx *ctx, size_t nbytes, const vcfx_chunk_info *info);
+/* submit_shared  : run THIS context's op on the chunk most recently submitted to `primary` (same
+ *                  device), reading the bytes that are already in the primary's device slot: one
+ *                  upload feeds several tools (e.g. variant_counter next to allele_freq_calc).
+ *                  Drain this context before the primary takes `n_slots` further chunks; a chunk
+ *                  whose output outgrows its slot is re-run and must still find the bytes there.  */
+int vcfx_cuda_submit_shared(vcfx_ctx *ctx, vcfx_ctx *primary, const vcfx_chunk_info *info);
 int vcfx_cuda_next_output(vcfx_ctx *ctx, const char **text, size_t *n, vcfx_chunk_stats *stats);
 /* submit_host    : like acquire + memcpy + submit, but the chunk is copied to the device straight
  *                  from the caller's buffer (an mmap'ed/pinned region gives the full PCIe rate).

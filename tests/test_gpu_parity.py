@@ -168,3 +168,46 @@ def test_gpu_matches_reference_golden(cuda_api):
                 r = api.allele_counter(data, path, fmt, limit)
                 assert r.rc == exp[k][0], (name, k)
                 _cmp(f"golden {name} {k}", r.out, exp[k][1])
+
+
+def test_shared_upload_feeds_two_tools(cuda_api, oracle):
+    """vcfx_cuda_submit_shared: variant_counter runs on the bytes allele_freq_calc uploaded."""
+    import ctypes as C
+    api = cuda_api
+    data = synth.make_vcf(3, 3000, 120, seed=13)
+    chunk = 256 << 10
+    af = api.Context(api.OP_ALLELE_FREQ, api.FILE, chunk_bytes=chunk, n_slots=3)
+    vc = api.Context(api.OP_VARIANT_COUNT, api.FILE, chunk_bytes=chunk, n_slots=3)
+    keep = C.create_string_buffer(data, len(data))
+    base = C.addressof(keep)
+    valid_abs = api.find_chrom_header(data)
+    out_af, rows_vc = [], 0
+
+    def drain():
+        nonlocal rows_vc
+        o, st, _ = vc.next_output(); rows_vc += st.rows
+        o, st, _ = af.next_output(); out_af.append(o)
+
+    n = len(data)
+    for s, e in api.chunk_bounds(data, chunk):
+        vf = min(max(valid_abs - s, 0), e - s)
+        while not af.submit_host(base + s, e - s, valid_from=vf, is_final=(e == n)):
+            drain()
+        assert vc.submit_shared(af, is_final=(e == n))
+    while af.in_flight():
+        drain()
+    af.close(); vc.close()
+    assert api.AF_HEADER + b"".join(out_af) == oracle.allele_freq(data, 0).out
+    assert rows_vc == oracle.variant_count(data, 0).rows
+
+
+def test_line_lengths_sweep(cuda_api, oracle):
+    """Lines of every length class against the 512-byte windows: a line inside one window, ending in
+    the first bytes of the next one, phase shifts (haploid / missing calls) right before a window or
+    line end — the places where the lattice tiers hand over to the exact path."""
+    for shape in (1, 2, 3):
+        for S in list(range(1, 34, 2)) + list(range(100, 134, 3)) + [119, 120, 121, 127, 128, 129, 255, 256, 257, 383, 511, 640]:
+            data = synth.make_vcf(shape, 150 if S < 300 else 40, S, seed=1000 * shape + S)
+            run_all(cuda_api, oracle, data, f"sweep shape{shape} S{S}", tools=("af", "hwe"))
+    data = synth.make_vcf(3, 3000, 120, seed=13)
+    run_all(cuda_api, oracle, data, "sweep regression S120", chunk_bytes=256 << 10)

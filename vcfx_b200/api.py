@@ -58,7 +58,7 @@ class ChunkStats(C.Structure):
 
 EXPORTS = ["vcfx_cuda_abi_version", "vcfx_cuda_device_count", "vcfx_cuda_strerror", "vcfx_cuda_last_error",
            "vcfx_cuda_create", "vcfx_cuda_destroy", "vcfx_cuda_acquire_input", "vcfx_cuda_submit",
-           "vcfx_cuda_submit_host", "vcfx_cuda_next_output", "vcfx_cuda_in_flight", "vcfx_cuda_short_lines",
+           "vcfx_cuda_submit_host", "vcfx_cuda_submit_shared", "vcfx_cuda_next_output", "vcfx_cuda_in_flight", "vcfx_cuda_short_lines",
            "vcfx_cuda_run_device", "vcfx_cuda_sync"]
 
 _lib = None
@@ -85,6 +85,7 @@ def load():
         l.vcfx_cuda_acquire_input.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         l.vcfx_cuda_submit.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(ChunkInfo)]
         l.vcfx_cuda_submit_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(ChunkInfo)]
+        l.vcfx_cuda_submit_shared.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(ChunkInfo)]
         l.vcfx_cuda_next_output.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(ChunkStats)]
         l.vcfx_cuda_in_flight.argtypes = [C.c_void_p]
         l.vcfx_cuda_short_lines.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_size_t, C.POINTER(C.c_size_t)]
@@ -196,6 +197,15 @@ class Context:
         self._check(rc)
         return True
 
+    def submit_shared(self, primary: "Context", valid_from: int = 0, is_final: bool = True) -> bool:
+        """Run this context's op on the chunk last submitted to ``primary`` (no second upload)."""
+        info = ChunkInfo(valid_from, int(is_final), 0)
+        rc = self._l.vcfx_cuda_submit_shared(self._h, primary._h, C.byref(info))
+        if rc == E_BUSY:
+            return False
+        self._check(rc)
+        return True
+
     def in_flight(self) -> int:
         return self._l.vcfx_cuda_in_flight(self._h)
 
@@ -277,12 +287,46 @@ def stream_bytes(ctx: Context, data, chunk_bytes: int, valid_abs: int = 0):
     return outs, tot
 
 
+_ctx_cache: dict = {}
+
+
+def _cached_context(op, mode, device, flags, chunk_bytes, **kw):
+    """Contexts are reusable once drained; creating one costs pinned and device allocations, so the
+    helpers below keep a few around (allele_counter contexts carry a selection and are not cached)."""
+    if "sel_cols" in kw:
+        return Context(op, mode, device=device, flags=flags, chunk_bytes=chunk_bytes, **kw), False
+    key = (op, mode, device, flags, chunk_bytes, tuple(sorted(kw.items())))
+    ctx = _ctx_cache.get(key)
+    if ctx is None:
+        if len(_ctx_cache) >= 24:
+            _ctx_cache.pop(next(iter(_ctx_cache))).close()
+        ctx = _ctx_cache[key] = Context(op, mode, device=device, flags=flags, chunk_bytes=chunk_bytes, **kw)
+    return ctx, True
+
+
+def close_cached_contexts():
+    while _ctx_cache:
+        _ctx_cache.popitem()[1].close()
+
+
+import atexit  # noqa: E402
+atexit.register(close_cached_contexts)
+
+
 def _run(op: int, data: bytes, mode: int, chunk_bytes: int, flags: int = 0, device: int = 0, **kw):
     # default slot size: the input rounded up to 1 MiB, at most 64 MiB (pinned allocations are not free)
     chunk_bytes = chunk_bytes or min(64 << 20, max(1 << 20, (len(data) + (1 << 20) - 1) & ~((1 << 20) - 1)))
-    with Context(op, mode, device=device, flags=flags, chunk_bytes=chunk_bytes, **kw) as ctx:
+    ctx, cached = _cached_context(op, mode, device, flags, chunk_bytes, **kw)
+    try:
         valid_abs = find_chrom_header(data) if op == OP_ALLELE_FREQ else 0
         outs, tot = stream_bytes(ctx, data, chunk_bytes, valid_abs)
+    except Exception:
+        if cached:
+            _ctx_cache.pop(next(k for k, v in _ctx_cache.items() if v is ctx), None)
+        ctx.close()
+        raise
+    if not cached:
+        ctx.close()
     return b"".join(outs), tot
 
 
@@ -322,8 +366,8 @@ def first_data_offset(data) -> int:
 
 def missing_detector(data: bytes, mode: int = FILE, chunk_bytes: int = 0, **kw) -> ToolResult:
     chunk_bytes = chunk_bytes or min(64 << 20, max(1 << 20, (len(data) + (1 << 20) - 1) & ~((1 << 20) - 1)))
-    with Context(OP_MISSING_DETECT, mode, chunk_bytes=chunk_bytes, **kw) as ctx:
-        outs, tot = stream_bytes(ctx, data, chunk_bytes, first_data_offset(data))
+    ctx, _ = _cached_context(OP_MISSING_DETECT, mode, 0, 0, chunk_bytes, **kw)
+    outs, tot = stream_bytes(ctx, data, chunk_bytes, first_data_offset(data))
     if mode == FILE and tot.last_unterminated_flagged and tot.dots_terminated == 0:
         # The reference's pre-scan ignores an unterminated last line (missing_detector.cpp:354): when
         # no other line has a '.' in its sample columns it copies the file verbatim, so that last

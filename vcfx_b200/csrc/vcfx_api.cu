@@ -48,6 +48,10 @@ struct Slot {
     size_t out_cap = 0;
     vcfx_chunk_info info = {0, 1, 0};
     bool in_flight = false;
+    cudaEvent_t ev_h2d = nullptr;          // the chunk is on the device (H2D + pad done)
+    cudaEvent_t ev_shared_done = nullptr;  // a secondary context finished reading this slot's d_in
+    bool shared_pending = false;
+    uint8_t *d_in_used = nullptr;          // the device input of the chunk in flight (own d_in, or a primary's)
 };
 
 }  // namespace
@@ -205,12 +209,12 @@ int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes, uint64_t min_recs = 0)
 
 // enqueue the kernels of one chunk on `st`; results land in w.h_stats after the stream drains
 int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t nbytes,
-                 const vcfx_chunk_info *info, uint8_t *d_out, size_t out_cap) {
+                 const vcfx_chunk_info *info, uint8_t *d_out, size_t out_cap, bool write_pad = true) {
     kernel_fn fn = kernel_for(ctx->cfg.op);
     if (!fn) return VCFX_E_UNSUPPORTED;
     const uint32_t tile = tile_for(ctx, nbytes);
     uint32_t tiles = tiles_for(ctx, nbytes, tile);
-    CU(cudaMemsetAsync(d_in + nbytes, '\n', 64, st));
+    if (write_pad) CU(cudaMemsetAsync(d_in + nbytes, '\n', 64, st));
     CU(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), st));
     CU(cudaMemcpyAsync(w.d_stats, w.h_init, sizeof(DevStats), cudaMemcpyHostToDevice, st));
 
@@ -382,6 +386,8 @@ void vcfx_cuda_destroy(vcfx_ctx *ctx) {
         if (s.h_out) cudaFreeHost(s.h_out);
         cudaFree(s.d_in); cudaFree(s.d_out);
         free_work(s.w);
+        if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+        if (s.ev_shared_done) cudaEventDestroy(s.ev_shared_done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     if (ctx->dev_stream) cudaStreamSynchronize(ctx->dev_stream);
@@ -395,6 +401,8 @@ static int ensure_slot(vcfx_ctx *ctx, Slot &s) {
     if (s.h_in) return VCFX_OK;
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s.ev_shared_done, cudaEventDisableTiming));
     CU(cudaMallocHost(&s.h_in, ctx->chunk_bytes));
     CU(cudaMalloc(&s.d_in, ctx->chunk_bytes + VCFX_DEVICE_PAD));
     CU(cudaMalloc(&s.d_out, ctx->out_bytes));
@@ -421,9 +429,13 @@ int vcfx_cuda_submit(vcfx_ctx *ctx, size_t nbytes, const vcfx_chunk_info *info) 
     if (!ctx || ctx->acquired_slot < 0 || nbytes > ctx->chunk_bytes) return VCFX_E_INVALID;
     Slot &s = ctx->slots[ctx->acquired_slot];
     CU(cudaSetDevice(ctx->device));
+    if (s.shared_pending) { CU(cudaStreamWaitEvent(s.stream, s.ev_shared_done, 0)); s.shared_pending = false; }
     if (nbytes) CU(cudaMemcpyAsync(s.d_in, s.h_in, nbytes, cudaMemcpyHostToDevice, s.stream));
+    CU(cudaMemsetAsync(s.d_in + nbytes, '\n', 64, s.stream));
+    CU(cudaEventRecord(s.ev_h2d, s.stream));
+    s.d_in_used = s.d_in;
     if (info) s.info = *info; else s.info = vcfx_chunk_info{0, 1, 0};
-    int rc = launch_chunk(ctx, s.w, s.stream, s.d_in, nbytes, &s.info, s.d_out, s.out_cap);
+    int rc = launch_chunk(ctx, s.w, s.stream, s.d_in, nbytes, &s.info, s.d_out, s.out_cap, false);
     if (rc != VCFX_OK) return rc;
     s.nbytes = nbytes; s.in_flight = true;
     ctx->acquired_slot = -1;
@@ -439,11 +451,39 @@ int vcfx_cuda_submit_host(vcfx_ctx *ctx, const void *host, size_t nbytes, const 
     int rc = ensure_slot(ctx, s);
     if (rc != VCFX_OK) return rc;
     CU(cudaSetDevice(ctx->device));
+    if (s.shared_pending) { CU(cudaStreamWaitEvent(s.stream, s.ev_shared_done, 0)); s.shared_pending = false; }
     if (nbytes) CU(cudaMemcpyAsync(s.d_in, host, nbytes, cudaMemcpyHostToDevice, s.stream));
+    CU(cudaMemsetAsync(s.d_in + nbytes, '\n', 64, s.stream));
+    CU(cudaEventRecord(s.ev_h2d, s.stream));
+    s.d_in_used = s.d_in;
     if (info) s.info = *info; else s.info = vcfx_chunk_info{0, 1, 0};
-    rc = launch_chunk(ctx, s.w, s.stream, s.d_in, nbytes, &s.info, s.d_out, s.out_cap);
+    rc = launch_chunk(ctx, s.w, s.stream, s.d_in, nbytes, &s.info, s.d_out, s.out_cap, false);
     if (rc != VCFX_OK) return rc;
     s.nbytes = nbytes; s.in_flight = true;
+    ctx->head = (ctx->head + 1) % ctx->n_slots;
+    ctx->n_in_flight++;
+    return VCFX_OK;
+}
+
+int vcfx_cuda_submit_shared(vcfx_ctx *ctx, vcfx_ctx *primary, const vcfx_chunk_info *info) {
+    if (!ctx || !primary || ctx == primary || ctx->device != primary->device || ctx->acquired_slot >= 0) return VCFX_E_INVALID;
+    if (primary->n_in_flight == 0) return VCFX_E_EMPTY;
+    if (ctx->n_in_flight >= ctx->n_slots) return VCFX_E_BUSY;
+    Slot &ps = primary->slots[(primary->head + primary->n_slots - 1) % primary->n_slots];   // its newest chunk
+    if (!ps.in_flight || ps.nbytes > ctx->chunk_bytes) return VCFX_E_INVALID;
+    Slot &s = ctx->slots[ctx->head];
+    int rc = ensure_slot(ctx, s);
+    if (rc != VCFX_OK) return rc;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamWaitEvent(s.stream, ps.ev_h2d, 0));                 // the bytes are there
+    if (info) s.info = *info; else s.info = vcfx_chunk_info{0, 1, 0};
+    s.d_in_used = ps.d_in;
+    rc = launch_chunk(ctx, s.w, s.stream, ps.d_in, ps.nbytes, &s.info, s.d_out, s.out_cap, false);
+    if (rc != VCFX_OK) return rc;
+    // the primary may not overwrite that device buffer before this context has read it
+    CU(cudaEventRecord(ps.ev_shared_done, s.stream));
+    ps.shared_pending = true;
+    s.nbytes = ps.nbytes; s.in_flight = true;
     ctx->head = (ctx->head + 1) % ctx->n_slots;
     ctx->n_in_flight++;
     return VCFX_OK;
@@ -473,7 +513,7 @@ int vcfx_cuda_next_output(vcfx_ctx *ctx, const char **text, size_t *n, vcfx_chun
             CU(cudaMallocHost(&s.h_out, want));
             s.out_cap = want;
         }
-        int rc = launch_chunk(ctx, s.w, s.stream, s.d_in, s.nbytes, &s.info, s.d_out, s.out_cap);
+        int rc = launch_chunk(ctx, s.w, s.stream, s.d_in_used, s.nbytes, &s.info, s.d_out, s.out_cap, false);
         if (rc != VCFX_OK) return rc;
         CU(cudaStreamSynchronize(s.stream));
     }

@@ -220,40 +220,55 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 // ---------------------------------------------------------------------------------------
 struct Tally { uint32_t a, b, c; };   // AF: alt,total   HWE: homRef,het,homAlt
 
-// AF, one sample whose first four bytes are q (b0 = first byte after the leading tab)
+// Quick shapes of a sample column, decided from its first four bytes q (b0 = the byte after the
+// leading tab) WITHOUT branches, so the lanes of a warp do not diverge on mixed data:
+//   A  <end>                 empty column / empty GT
+//   B  t <end>               haploid          t = digit or '.', <end> = tab, ':' or '\n'
+//   C  t sep t <end>         diploid, single-character alleles
+// Everything else (multi-digit alleles, more alleles, '\r', other bytes, GT not first) goes to the
+// exact scalar parsers.
+struct Quad {
+    uint32_t d0, d2, z0, z2;   // allele bytes: is digit / is '0'
+    uint32_t shapeB, shapeC, quick;
+};
+__device__ __forceinline__ Quad classify_quad(uint32_t q) {
+    const uint32_t b0 = q & 0xFF, b1 = (q >> 8) & 0xFF, b2 = (q >> 16) & 0xFF, b3 = q >> 24;
+    Quad r;
+    r.d0 = (uint32_t)((b0 - 48u) <= 9u); r.d2 = (uint32_t)((b2 - 48u) <= 9u);
+    r.z0 = (uint32_t)(b0 == '0'); r.z2 = (uint32_t)(b2 == '0');
+    const uint32_t t0 = (uint32_t)((b0 == '\t') | (b0 == ':') | (b0 == '\n'));
+    const uint32_t t1 = (uint32_t)((b1 == '\t') | (b1 == ':') | (b1 == '\n'));
+    const uint32_t t3 = (uint32_t)((b3 == '\t') | (b3 == ':') | (b3 == '\n'));
+    const uint32_t tok0 = r.d0 | (uint32_t)(b0 == '.'), tok2 = r.d2 | (uint32_t)(b2 == '.');
+    const uint32_t s1 = (uint32_t)((b1 == '/') | (b1 == '|'));
+    r.shapeB = tok0 & t1;
+    r.shapeC = tok0 & s1 & tok2 & t3;
+    r.quick = t0 | r.shapeB | r.shapeC;
+    return r;
+}
+
+// AF (allele_freq_calc.cpp:262-293): every numeric allele counts, non-zero ones are ALT
 __device__ __forceinline__ void af_sample_reg(uint32_t q, const uint8_t *p, bool strip_cr, int gt_index,
                                               uint32_t &alt, uint32_t &total) {
-    uint32_t b0 = q & 0xFF, b1 = (q >> 8) & 0xFF, b2 = (q >> 16) & 0xFF, b3 = q >> 24;
-    if (gt_index == 0) {
-        if (b0 == '\t' || b0 == ':' || b0 == '\n') return;   // empty sample / empty GT
-        bool d0 = is_dig(b0);
-        if (d0 || b0 == '.') {
-            if (b1 == '\t' || b1 == ':' || b1 == '\n') { if (d0) { total++; alt += (b0 != '0'); } return; }
-            if (is_sep(b1)) {
-                bool d2 = is_dig(b2);
-                if ((d2 || b2 == '.') && (b3 == '\t' || b3 == ':' || b3 == '\n')) {
-                    if (d0) { total++; alt += (b0 != '0'); }
-                    if (d2) { total++; alt += (b2 != '0'); }
-                    return;
-                }
-            }
-        }
+    const Quad c = classify_quad(q);
+    if (gt_index == 0 && c.quick) {
+        const uint32_t any = c.shapeB | c.shapeC;
+        total += (any & c.d0) + (c.shapeC & c.d2);
+        alt += (any & c.d0 & (c.z0 ^ 1u)) + (c.shapeC & c.d2 & (c.z2 ^ 1u));
+        return;
     }
-    uint2 r = af_sample_slow(p, strip_cr, gt_index);
+    const uint2 r = af_sample_slow(p, strip_cr, gt_index);
     alt += r.x; total += r.y;
 }
 
-// HWE, same; returns the class (0 homRef, 1 het, 2 homAlt, -1 none)
+// HWE (hwe_tester.cpp:339-378): class 0 homRef, 1 het, 2 homAlt, -1 none; only "a sep b" with a, b in
+// {0,1} counts, whatever follows the second allele
 __device__ __forceinline__ int hwe_sample_reg(uint32_t q, const uint8_t *p) {
-    uint32_t b0 = q & 0xFF, b1 = (q >> 8) & 0xFF, b2 = (q >> 16) & 0xFF, b3 = q >> 24;
-    if (!is_dig(b0)) return (b0 == ' ' || b0 == '\r') ? hwe_sample_slow(p) : -1;
-    if (is_sep(b1)) {
-        if (!is_dig(b2)) return -1;
-        if (is_dig(b3)) return hwe_sample_slow(p);
-        if (b0 > '1' || b2 > '1') return -1;
-        return (int)(b0 - '0') + (int)(b2 - '0');
-    }
-    return is_dig(b1) ? hwe_sample_slow(p) : -1;
+    const uint32_t b0 = q & 0xFF, b1 = (q >> 8) & 0xFF, b2 = (q >> 16) & 0xFF, b3 = q >> 24;
+    const bool d0 = is_dig(b0), d1 = is_dig(b1), d2 = is_dig(b2), d3 = is_dig(b3), s1 = is_sep(b1);
+    if ((!d0 && b0 != ' ' && b0 != '\r') || (d0 && !s1 && !d1) || (d0 && s1 && !d2)) return -1;
+    if (d0 && s1 && d2 && !d3) return (b0 <= '1' && b2 <= '1') ? (int)(b0 - '0') + (int)(b2 - '0') : -1;
+    return hwe_sample_slow(p);
 }
 
 // generic: one sample per owned tab (tab masks m0..m3 over the lane's words w0..w3, la = next 4 B).
@@ -290,9 +305,9 @@ __device__ __noinline__ uint3 lane_samples_generic(uint32_t w0, uint32_t w1, uin
 // HWE: n01 | het << 8 | homAlt << 16   (n01 = samples whose two digits are both 0/1)
 template <int OP>
 __device__ __forceinline__ bool lane_lattice(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t la,
-                                             uint32_t &packed) {
+                                             uint32_t &packed, uint32_t &sh) {
     const uint32_t t0 = eq_bytes(w0, C_TAB);
-    const uint32_t sh = (uint32_t)__ffs(t0);                // 8,16,24,32 = 8 * (tau + 1); 0 when no tab
+    sh = (uint32_t)__ffs(t0);                               // 8,16,24,32 = 8 * (tau + 1); 0 when no tab
     const uint32_t xs[4] = {__funnelshift_rc(w0, w1, sh), __funnelshift_rc(w1, w2, sh),
                             __funnelshift_rc(w2, w3, sh), __funnelshift_rc(w3, la, sh)};
     uint32_t bad = 0, acc = 0;
@@ -358,17 +373,11 @@ __device__ __noinline__ uint2 ac_sample_slow(const uint8_t *p) {
     return make_uint2(ref, alt);
 }
 __device__ __forceinline__ uint2 ac_sample_reg(uint32_t q, const uint8_t *p) {
-    const uint32_t b0 = q & 0xFF, b1 = (q >> 8) & 0xFF, b2 = (q >> 16) & 0xFF, b3 = q >> 24;
-    if (b0 == '\t' || b0 == ':' || b0 == '\n') return make_uint2(0u, 0u);
-    const bool d0 = is_dig(b0);
-    if (d0 || b0 == '.') {
-        const uint32_t r0 = (uint32_t)(b0 == '0'), a0 = (uint32_t)(d0 && b0 != '0');
-        if (b1 == '\t' || b1 == ':' || b1 == '\n') return make_uint2(r0, a0);
-        if (is_sep(b1)) {
-            const bool d2 = is_dig(b2);
-            if ((d2 || b2 == '.') && (b3 == '\t' || b3 == ':' || b3 == '\n'))
-                return make_uint2(r0 + (uint32_t)(b2 == '0'), a0 + (uint32_t)(d2 && b2 != '0'));
-        }
+    const Quad c = classify_quad(q);
+    if (c.quick) {
+        const uint32_t any = c.shapeB | c.shapeC;
+        return make_uint2((any & c.z0) + (c.shapeC & c.z2),
+                          (any & c.d0 & (c.z0 ^ 1u)) + (c.shapeC & c.d2 & (c.z2 ^ 1u)));
     }
     return ac_sample_slow(p);
 }
@@ -665,8 +674,13 @@ vcfx_scan_kernel(const KParams P) {
                         // exact path for this window
                         uint32_t packed = 0;
                         // samples of a FORMAT with more keys carry ':' pieces: no lattice there, do not look for one
-                        const bool lat = lat_possible && lane_lattice<OP>(cur.x, cur.y, cur.z, cur.w, la, packed);
-                        gbal = lat_possible ? __ballot_sync(FULL, lat) : 0u;
+                        uint32_t sh_lane = 0;
+                        const bool lat = lat_possible && lane_lattice<OP>(cur.x, cur.y, cur.z, cur.w, la, packed, sh_lane);
+                        // Tier 1 never looks at a lane's bytes up to its first lattice tab: they must have been
+                        // verified by the lane before it AT THE SAME PHASE.  After a haploid or missing call the
+                        // phase of the samples shifts, so the last lane only vouches for the next window when its
+                        // own phase is the line's tier-1 phase.
+                        gbal = lat_possible ? __ballot_sync(FULL, lat && sh_lane == sh_u) : 0u;
                         uint32_t m0, m1, m2, m3;
                         const uint32_t n0 = eq_bytes(cur.x, C_NL);
                         if (first_win) { m0 = t0; m1 = t1; m2 = t2; m3 = t3; }   // already clipped to [ls, e)
