@@ -609,23 +609,25 @@ vcfx_scan_kernel(const KParams P) {
                             n_real += 128; wb += WINDOW;                                           \
                             A = ld16(lp + 3 * WINDOW); lp += WINDOW;                               \
                         }
-                        for (;;) {
+                        // L2 prefetch 6 KB ahead: lanes 0..11 cover the 1.5 KB one round consumes; rounds whose
+                        // prefetch would pass the end of the chunk are simply not prefetched
+                        const uint8_t *pf = tin + wb + 12 * WINDOW + 128 * lane;
+                        const long long pf_room = (long long)(in_end - pf) - 128 * 12;
+                        int pf_rounds = (lane < 12 && pf_room > 0) ? (int)min((long long)0x7FFFFFFF, pf_room / (3 * WINDOW)) : 0;
+                        // at most 4000 rounds at a time so the 16-bit packed sums cannot overflow (3 * 4 per round)
+                        for (int guard = 0; guard < 4000; ++guard) {
                             VCFX_T1_STEP(cur, nxt, t1_exit0)
                             VCFX_T1_STEP(nxt, nx2, t1_exit1)
                             VCFX_T1_STEP(nx2, cur, t1_exit2)
-                            wcount += 3;
-                            if (lane < 12) {                     // pull the next 1.5 KB into L2, 6 KB ahead
-                                const uint8_t *pf = lp - 16 * lane + 12 * WINDOW + 128 * lane;
-                                if (pf < in_end) prefetch_l2(pf);
-                            }
-                            if (OP == OP_AF && wcount >= 12000) {   // keep the 16-bit packed sums from overflowing
-                                ta += (accp & 0xFFFFu) + (accp >> 16); accp = 0; wcount = 0;
-                            }
+                            if (pf_rounds > 0) { prefetch_l2(pf); --pf_rounds; }
+                            pf += 3 * WINDOW;
                         }
+                        goto t1_exit0;
 #undef VCFX_T1_STEP
                     t1_exit1: { const uint4 t_ = cur; cur = nxt; nxt = nx2; nx2 = t_; } goto t1_exit0;
                     t1_exit2: { const uint4 t_ = nx2; nx2 = nxt; nxt = cur; cur = t_; }
                     t1_exit0: ;
+                        if (OP == OP_AF) { ta += (accp & 0xFFFFu) + (accp >> 16); accp = 0; }
                     }
                     // ---- this window needs a closer look
                     const uint32_t pb = wb + 16 * lane;
@@ -756,7 +758,6 @@ vcfx_scan_kernel(const KParams P) {
                     prev_ok = (gbal >> 31) != 0;
                     first_win = false;
                     wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
-                    if (OP == OP_AF && ++wcount >= 12000) { ta += (accp & 0xFFFFu) + (accp >> 16); accp = 0; wcount = 0; }
                 }
                 // fold the tier-1 tallies in (n_real is uniform: lane 0 carries it)
                 if (OP == OP_AF) { ta += (accp & 0xFFFFu) + (accp >> 16); if (lane == 0) tb += 2u * n_real; }

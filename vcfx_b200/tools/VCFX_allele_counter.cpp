@@ -217,7 +217,7 @@ int main(int argc, char *argv[]) {
     std::string err;
     int rc = vcfxh::run_stream(src, opt, tot, err);
     if (input) close(fd);
-    if (rc != VCFX_OK) { fprintf(stderr, "Error: %s\n", err.c_str()); return 1; }
+    if (rc != VCFX_OK) { fprintf(stderr, "Error: %s\n", err.c_str()); vcfxh::finish(1); }
     if (gzip_out) {                        // gzdopen(dup(1), "wb6") like the reference's GzipWriter
         int dupfd = dup(1);
         gzFile gz = dupfd >= 0 ? gzdopen(dupfd, "wb6") : nullptr;
@@ -227,5 +227,5 @@ int main(int argc, char *argv[]) {
         while (pos < out.size()) { unsigned k = (unsigned)std::min<size_t>(out.size() - pos, 1u << 30); gzwrite(gz, out.data() + pos, k); pos += k; }
         gzclose(gz);
     }
-    return 0;
+    vcfxh::finish(0);
 }

@@ -79,11 +79,11 @@ int main(int argc, char *argv[]) {
         vcfxh::write_all(1, HEADER, sizeof HEADER - 1);
         rc = vcfxh::run_stream(src, opt, tot, err);
     }
-    if (rc != VCFX_OK) { fprintf(stderr, "Error: %s\n", err.c_str()); return 1; }
+    if (rc != VCFX_OK) { fprintf(stderr, "Error: %s\n", err.c_str()); vcfxh::finish(1); }
     if (!quiet) {
         for (uint64_t i = 0; i < tot.pre_header; ++i) fputs("Warning: Data line encountered before #CHROM header. Skipping.\n", stderr);
         if (!input) for (uint64_t i = 0; i < tot.short_lines; ++i) fputs("Warning: Skipping invalid VCF line (fewer than 9 fields).\n", stderr);
         if (input) fprintf(stderr, "Processed %llu variants from %llu data lines\n", (unsigned long long)tot.rows, (unsigned long long)tot.data_lines);
     }
-    return 0;
+    vcfxh::finish(0);
 }

@@ -75,6 +75,6 @@ int main(int argc, char *argv[]) {
         vcfxh::Source src(0);
         rc = vcfxh::run_stream(src, opt, tot, err);
     }
-    if (rc != VCFX_OK) { fprintf(stderr, "Error: %s\n", err.c_str()); return 1; }
-    return 0;
+    if (rc != VCFX_OK) { fprintf(stderr, "Error: %s\n", err.c_str()); vcfxh::finish(1); }
+    vcfxh::finish(0);
 }

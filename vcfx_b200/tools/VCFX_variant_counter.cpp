@@ -73,12 +73,12 @@ int main(int argc, char *argv[]) {
             if (src.failed()) { fputs("Error: inflateInit2 failed.\n", stderr); return 1; }
         }
         rc = vcfxh::run_stream(src, opt, tot, err);
-        if (src.failed()) { fputs("Error: decompression failed.\n", stderr); return 1; }
+        if (src.failed()) { fputs("Error: decompression failed.\n", stderr); vcfxh::finish(1); }
     }
-    if (rc != VCFX_OK) { fprintf(stderr, "Error: %s\n", err.c_str()); return 1; }
+    if (rc != VCFX_OK) { fprintf(stderr, "Error: %s\n", err.c_str()); vcfxh::finish(1); }
     if (strict && tot.short_lines) {
         fprintf(stderr, "Error: line %llu has <8 columns.\n", (unsigned long long)tot.first_short_line);
-        return 1;
+        vcfxh::finish(1);
     }
     for (uint64_t ln : tot.short_line_numbers)
         fprintf(stderr, "Warning: skipping line %llu with <8 columns.\n", (unsigned long long)ln);
@@ -86,5 +86,5 @@ int main(int argc, char *argv[]) {
         fprintf(stderr, "Warning: skipping %llu more lines with <8 columns.\n",
                 (unsigned long long)(tot.short_lines - tot.short_line_numbers.size()));
     printf("Total Variants: %d\n", (int)tot.rows);
-    return 0;
+    vcfxh::finish(0);
 }

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <unistd.h>
 #include <zlib.h>
+#include <chrono>
 
 namespace vcfxh {
 
@@ -95,6 +96,11 @@ bool write_all(int fd, const char *p, size_t n) {
     return true;
 }
 
+void finish(int rc) {
+    fflush(stdout); fflush(stderr);
+    _exit(rc);
+}
+
 int env_device() {
     const char *e = getenv("VCFX_CUDA_DEVICE");
     return e ? atoi(e) : 0;
@@ -150,8 +156,12 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
         cfg.n_sel = (uint32_t)opt.sel_col.size(); cfg.sel_col = opt.sel_col.data();
         cfg.sel_names = names_blob.data(); cfg.sel_name_off = name_off.data();
     }
+    const bool timing = getenv("VCFX_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_start = now(), t_read = 0, t_submit = 0, t_drain = 0, t_acquire = 0;
     vcfx_ctx *ctx = nullptr;
     int rc = vcfx_cuda_create(&cfg, &ctx);
+    double t_create = now() - t_start;
     if (rc != VCFX_OK) { err = vcfx_cuda_strerror(rc); return rc; }
 
     Drain drain{ctx, opt, tot};
@@ -160,11 +170,18 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
     long submitted = 0;
     while (!eof) {
         char *buf = nullptr; size_t cap = 0;
+        double t0 = now();
         rc = vcfx_cuda_acquire_input(ctx, &buf, &cap);
+        t_acquire += now() - t0;
         while (rc == VCFX_E_BUSY) {
+            t0 = now();
             if ((rc = drain.one(err)) != VCFX_OK) { vcfx_cuda_destroy(ctx); return rc; }
+            t_drain += now() - t0;
+            t0 = now();
             rc = vcfx_cuda_acquire_input(ctx, &buf, &cap);
+            t_acquire += now() - t0;
         }
+        t0 = now();
         if (rc != VCFX_OK) { err = std::string(vcfx_cuda_strerror(rc)) + ": " + vcfx_cuda_last_error(ctx); vcfx_cuda_destroy(ctx); return rc; }
         // bytes already in hand (the tail of the previous chunk, or what the caller consumed while
         // looking at the header) go first; the source is only read once they fit
@@ -177,6 +194,7 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
             if (r == 0) { eof = true; break; }
             have += (size_t)r;
         }
+        t_read += now() - t0;
         size_t nbytes = have;
         if (!eof) {
             const char *nl = static_cast<const char *>(memrchr(buf, '\n', have));
@@ -213,7 +231,9 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
             info.data_valid_from = pos;
         }
         if (eof) drain.final_index = submitted;
+        t0 = now();
         rc = vcfx_cuda_submit(ctx, nbytes, &info);
+        t_submit += now() - t0;
         ++submitted;
         if (rc != VCFX_OK) { err = std::string(vcfx_cuda_strerror(rc)) + ": " + vcfx_cuda_last_error(ctx); vcfx_cuda_destroy(ctx); return rc; }
         if (opt.stop_at_first_short && vcfx_cuda_in_flight(ctx) >= 2) {
@@ -222,9 +242,15 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
             if (tot.short_lines) break;
         }
     }
+    double t0 = now();
     while (vcfx_cuda_in_flight(ctx) > 0)
         if ((rc = drain.one(err)) != VCFX_OK) { vcfx_cuda_destroy(ctx); return rc; }
-    vcfx_cuda_destroy(ctx);
+    t_drain += now() - t0;
+    t0 = now();
+    if (!opt.skip_destroy) vcfx_cuda_destroy(ctx);
+    if (timing)
+        fprintf(stderr, "[vcfx timing] create %.3f acquire %.3f read %.3f submit %.3f drain %.3f destroy %.3f total %.3f s, kernels %.3f ms, %ld chunks\n",
+                t_create, t_acquire, t_read, t_submit, t_drain, now() - t0, now() - t_start, tot.kernel_ms, submitted);
     return VCFX_OK;
 }
 

@@ -68,12 +68,16 @@ struct RunOptions {
     std::string *last_unterminated_line = nullptr;
     // bytes that were already consumed from the source and belong in front of it
     std::string preface;
+    // a tool that exits right after the run does not tear the CUDA context down (the OS does, faster)
+    bool skip_destroy = true;
 };
 
 // Streams `src` through libvcfx_cuda. Returns 0, or a negative vcfx_err; err_text gets a message.
 int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err_text);
 
 int env_device();
+// flush stdio and leave without running the CUDA runtime's exit handlers (they cost up to a second)
+[[noreturn]] void finish(int rc);
 bool write_all(int fd, const char *p, size_t n);
 
 }  // namespace vcfxh
