@@ -228,22 +228,25 @@ struct Tally { uint32_t a, b, c; };   // AF: alt,total   HWE: homRef,het,homAlt
 // Everything else (multi-digit alleles, more alleles, '\r', other bytes, GT not first) goes to the
 // exact scalar parsers.
 struct Quad {
-    uint32_t d0, d2, z0, z2;   // allele bytes: is digit / is '0'
+    uint32_t d0, d2, z0, z2;   // allele bytes: is digit / is '0'   (0 or 1)
     uint32_t shapeB, shapeC, quick;
 };
+// SWAR over the four bytes of q at once (0x80 flag per byte), then a handful of bit tests
 __device__ __forceinline__ Quad classify_quad(uint32_t q) {
-    const uint32_t b0 = q & 0xFF, b1 = (q >> 8) & 0xFF, b2 = (q >> 16) & 0xFF, b3 = q >> 24;
+    const uint32_t T = eq_bytes(q, 0x09090909u) | eq_bytes(q, 0x3A3A3A3Au) | eq_bytes(q, 0x0A0A0A0Au);   // tab ':' '\n'
+    const uint32_t S = eq_bytes(q, 0x2F2F2F2Fu) | eq_bytes(q, 0x7C7C7C7Cu);                             // '/' '|'
+    const uint32_t Z = eq_bytes(q, 0x30303030u);
+    const uint32_t P = eq_bytes(q, 0x2E2E2E2Eu);
+    // digits: byte >= '0' and not byte >= ':' (7-bit add; bytes >= 0x80 are excluded explicitly)
+    const uint32_t q7 = q & 0x7F7F7F7Fu;
+    const uint32_t D = (q7 + 0x50505050u) & ~(q7 + 0x46464646u) & ~q & 0x80808080u;
+    const uint32_t tok = D | P;
     Quad r;
-    r.d0 = (uint32_t)((b0 - 48u) <= 9u); r.d2 = (uint32_t)((b2 - 48u) <= 9u);
-    r.z0 = (uint32_t)(b0 == '0'); r.z2 = (uint32_t)(b2 == '0');
-    const uint32_t t0 = (uint32_t)((b0 == '\t') | (b0 == ':') | (b0 == '\n'));
-    const uint32_t t1 = (uint32_t)((b1 == '\t') | (b1 == ':') | (b1 == '\n'));
-    const uint32_t t3 = (uint32_t)((b3 == '\t') | (b3 == ':') | (b3 == '\n'));
-    const uint32_t tok0 = r.d0 | (uint32_t)(b0 == '.'), tok2 = r.d2 | (uint32_t)(b2 == '.');
-    const uint32_t s1 = (uint32_t)((b1 == '/') | (b1 == '|'));
-    r.shapeB = tok0 & t1;
-    r.shapeC = tok0 & s1 & tok2 & t3;
-    r.quick = t0 | r.shapeB | r.shapeC;
+    r.d0 = (D >> 7) & 1u; r.d2 = (D >> 23) & 1u;
+    r.z0 = (Z >> 7) & 1u; r.z2 = (Z >> 23) & 1u;
+    r.shapeB = ((tok & (T >> 8)) >> 7) & 1u;                                   // t <end>
+    r.shapeC = ((tok & (S >> 8) & (tok >> 16) & (T >> 24)) >> 7) & 1u;         // t sep t <end>
+    r.quick = ((T >> 7) & 1u) | r.shapeB | r.shapeC;
     return r;
 }
 
@@ -596,6 +599,49 @@ vcfx_scan_kernel(const KParams P) {
                 uint32_t n_real = 0;               // samples tallied by tier 1 (uniform)
                 const uint8_t *const in_end = P.in + n;
                 for (;;) {
+                    // ---- steady state for a FORMAT with several keys (GT first): samples are tens of bytes long,
+                    // a lane holds at most one sample start.  Tab and newline masks, one vote, and the lanes that
+                    // hold a tab classify the four bytes after it.  The window with the '\n', lanes with two tabs
+                    // and unusual genotypes are left to the exact path below.
+                    if (!first_win && !lat_possible && gt_index == 0) {
+                        for (;;) {
+                            const uint32_t m0 = eq_bytes(cur.x, C_TAB), m1 = eq_bytes(cur.y, C_TAB);
+                            const uint32_t m2 = eq_bytes(cur.z, C_TAB), m3 = eq_bytes(cur.w, C_TAB);
+                            const uint32_t nn = eq_bytes(cur.x, C_NL) | eq_bytes(cur.y, C_NL) | eq_bytes(cur.z, C_NL) | eq_bytes(cur.w, C_NL);
+                            const uint32_t mall = m0 | m1 | m2 | m3;
+                            bool odd = nn != 0;                  // this window is not for the fast loop
+                            uint32_t da = 0, db = 0, dc = 0;
+                            // look-ahead word (needed by lanes whose tab sits in the last bytes)
+                            uint32_t la = __shfl_down_sync(FULL, cur.x, 1);
+                            const uint32_t nx0 = __shfl_sync(FULL, nxt.x, 0);
+                            if (lane == 31) la = nx0;
+                            if (mall) {
+                                if (__popc(m0) + __popc(m1) + __popc(m2) + __popc(m3) == 1) {
+                                    const int B = first_byte(m0, m1, m2, m3);
+                                    const uint32_t lo_ = B < 4 ? cur.x : B < 8 ? cur.y : B < 12 ? cur.z : cur.w;
+                                    const uint32_t hi_ = B < 4 ? cur.y : B < 8 ? cur.z : B < 12 ? cur.w : la;
+                                    const uint32_t q = __funnelshift_rc(lo_, hi_, 8u * (uint32_t)((B & 3) + 1));
+                                    const uint32_t b0 = q & 0xFF, b1 = (q >> 8) & 0xFF, b2 = (q >> 16) & 0xFF, b3 = q >> 24;
+                                    if (OP == OP_AF) {
+                                        const bool t3 = (b3 == '\t' || b3 == ':' || b3 == '\n');
+                                        if (is_dig(b0) && is_sep(b1) && is_dig(b2) && t3) { db = 2; da = (uint32_t)(b0 != '0') + (uint32_t)(b2 != '0'); }
+                                        else if (!(b0 == '.' && is_sep(b1) && b2 == '.' && t3)) odd = true;
+                                    } else {
+                                        if (is_dig(b0) && is_sep(b1) && is_dig(b2) && !is_dig(b3)) {
+                                            if (b0 <= '1' && b2 <= '1') { const uint32_t c = (b0 - '0') + (b2 - '0'); da = (c == 0); db = (c == 1); dc = (c == 2); }
+                                        } else if (b0 != '.') odd = true;
+                                    }
+                                } else odd = true;
+                            }
+                            if (__any_sync(FULL, odd)) break;    // nothing was added for this window
+                            ta += da; tb += db; tc += dc;
+                            wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
+                            if ((++wcount & 7) == 0) {
+                                const uint8_t *pf = tin + wb + 12 * WINDOW + 128 * lane;
+                                if (pf < in_end) prefetch_l2(pf);
+                            }
+                        }
+                    }
                     // ---- steady state: raw tier-1 windows, three register sets rotating so that nothing is
                     // moved: the set just consumed receives the load for three windows ahead
                     if (t1_on && prev_ok) {
