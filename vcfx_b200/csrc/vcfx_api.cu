@@ -28,6 +28,7 @@ struct Work {                      // device-side bookkeeping for one launch
     uint2 *col_scratch = nullptr;   // ALLELE_COUNT
     unsigned int *ticket = nullptr;
     Rec *recs = nullptr;
+    uint8_t *rec_prefix = nullptr;
     uint64_t rec_cap = 0;
     DevStats *d_stats = nullptr;
     unsigned long long *events = nullptr;
@@ -154,7 +155,7 @@ uint64_t default_rec_cap(size_t nbytes) { return nbytes / 48 + 65536; }
 
 void free_work(Work &w) {
     cudaFree(w.tile_lines); cudaFree(w.tile_out); cudaFree(w.tile_base); cudaFree(w.line_base);
-    cudaFree(w.ticket); cudaFree(w.recs); cudaFree(w.d_stats); cudaFree(w.events);
+    cudaFree(w.rec_prefix); cudaFree(w.ticket); cudaFree(w.recs); cudaFree(w.d_stats); cudaFree(w.events);
     cudaFree(w.tail_start); cudaFree(w.tail_len); cudaFree(w.tail_off); cudaFree(w.col_scratch);
     if (w.h_stats) cudaFreeHost(w.h_stats);
     if (w.h_init) cudaFreeHost(w.h_init);
@@ -201,7 +202,9 @@ int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes, uint64_t min_recs = 0)
     }
     if (recs > w.rec_cap) {
         cudaFree(w.recs); w.recs = nullptr; w.rec_cap = 0;
+        cudaFree(w.rec_prefix); w.rec_prefix = nullptr;
         CU(cudaMalloc(&w.recs, recs * sizeof(Rec)));
+        if (ctx->cfg.op == VCFX_OP_ALLELE_FREQ || ctx->cfg.op == VCFX_OP_HWE) CU(cudaMalloc(&w.rec_prefix, recs * 32));
         w.rec_cap = recs;
     }
     return VCFX_OK;
@@ -229,7 +232,7 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
     P.tail_start = w.tail_start; P.tail_len = w.tail_len; P.tail_off = w.tail_off;
     P.ac_fmt = ctx->ac_fmt; P.ac_pass = 0; P.n_sel = ctx->n_sel; P.sel_col = ctx->d_sel_col; P.name_off = ctx->d_name_off;
     P.names = ctx->d_names; P.max_col = ctx->max_col; P.col_scratch = w.col_scratch;
-    P.ticket = w.ticket; P.recs = w.recs; P.rec_cap = w.rec_cap;
+    P.ticket = w.ticket; P.recs = w.recs; P.rec_prefix = w.rec_prefix; P.rec_cap = w.rec_cap;
     P.stats = w.d_stats; P.events = w.events; P.ev_cap = EVENT_CAP;
 
     CU(cudaEventRecord(w.ev_k0, st));
@@ -237,7 +240,7 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
         int grid = grid_for(ctx, tiles);
         fn<<<grid, WARPS_PER_CTA * 32, 0, st>>>(P);
         CU(cudaGetLastError());
-        tile_scan_kernel<<<1, 1024, 0, st>>>(P);
+        tile_scan_kernel<<<1, 1024, SCAN_SMEM_BYTES, st>>>(P);
         CU(cudaGetLastError());
         if (kernel_fn ff = format_kernel_for(ctx->cfg.op, ctx->ac_fmt)) {
             ff<<<ctx->sm_count * (ctx->cfg.op == VCFX_OP_MISSING_DETECT ? 8 : 16), 256, 0, st>>>(P);
@@ -350,6 +353,7 @@ int vcfx_cuda_create(const vcfx_cfg *cfg, vcfx_ctx **out) {
     CUC(cudaGetDeviceProperties(&prop, ctx->device));
     ctx->sm_count = prop.multiProcessorCount;
     int bps = 1;
+    CUC(cudaFuncSetAttribute(tile_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel_for(cfg->op), WARPS_PER_CTA * 32, 0));
     ctx->blocks_per_sm = std::max(1, bps);
     if (cfg->op == VCFX_OP_ALLELE_COUNT) {

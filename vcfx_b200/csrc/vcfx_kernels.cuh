@@ -85,6 +85,7 @@ struct KParams {
     uint2 *col_scratch;              // [resident warps][max_col] (ref, alt) of the current line
     unsigned int *ticket;            // dynamic tile counter (zeroed before launch)
     Rec *recs;
+    uint8_t *rec_prefix;             // [rec_cap][32] copy of the row prefix when it is <= 32 bytes (AF / HWE)
     uint64_t rec_cap;
     DevStats *stats;
     unsigned long long *events;      // short-line events (tile << 32 | index in tile)
@@ -437,8 +438,10 @@ __device__ __forceinline__ bool t1_eval(uint32_t w0, uint32_t w1, uint32_t w2, u
 // ---------------------------------------------------------------------------------------
 // K1: the fused scan / parse / reduce kernel
 // ---------------------------------------------------------------------------------------
+// variant_counter is light enough to run at 48 registers (5 CTAs per SM: +4.5 %); the parsing
+// instantiations need 64 to keep the steady loops free of spills (measured both ways, profiles/README.md)
 template <int OP>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (OP == OP_VC) ? 5 : 4)
 vcfx_scan_kernel(const KParams P) {
     __shared__ uint32_t s_tp[WARPS_PER_CTA][12];
     __shared__ __align__(16) uint8_t s_stage[(OP == OP_AC) ? WARPS_PER_CTA * (AC_STAGE + 16) : 16];
@@ -977,13 +980,18 @@ vcfx_scan_kernel(const KParams P) {
                 if (row) {
                     const uint32_t prefix_len = tp[4] + 1 - ls;
                     const uint32_t row_len = prefix_len + ((OP == OP_AF) ? 7u : 9u);
-                    if (lane == 0) {
-                        unsigned long long slot = atomicAdd(&P.stats->n_recs, 1ULL);
-                        if (slot < P.rec_cap) {
+                    unsigned long long slot = 0;
+                    if (lane == 0) slot = atomicAdd(&P.stats->n_recs, 1ULL);
+                    slot = __shfl_sync(FULL, slot, 0);
+                    if (slot < P.rec_cap) {
+                        if (lane == 0) {
                             Rec r; r.tile = tile; r.ls_rel = (uint32_t)(a0 + ls - a); r.prefix_len = prefix_len;
                             r.off_in_tile = (uint32_t)out_bytes; r.a = ra_; r.b = rb_; r.c = rc_; r.d = 0;
                             P.recs[slot] = r;
                         }
+                        // the line's first bytes are still close (L2): keep a copy of the prefix next to the
+                        // record so that the format kernel does not have to gather it from the input
+                        if (prefix_len <= 32 && (uint32_t)lane < prefix_len) P.rec_prefix[slot * 32 + lane] = (uint8_t)ldb(tin + ls + lane);
                     }
                     out_bytes += row_len; ++s_rows;
                 }
@@ -1126,18 +1134,33 @@ vcfx_scan_kernel(const KParams P) {
 // K2a: exclusive scans over the tiles (output offsets, line numbers), one CTA.
 // Also turns short-line keys (tile, index in tile) into 1-based line numbers.
 // ---------------------------------------------------------------------------------------
+constexpr uint32_t SCAN_BATCH = 8192;                            // tiles per pass: 8 per thread
+constexpr uint32_t SCAN_SMEM_WORDS = SCAN_BATCH + SCAN_BATCH / 8;  // one pad word per 8 keeps thread-strided reads conflict-free
+constexpr size_t SCAN_SMEM_BYTES = 2 * SCAN_SMEM_WORDS * sizeof(unsigned long long);
+__device__ __forceinline__ uint32_t scan_pad(uint32_t i) { return i + (i >> 3); }
+
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(const KParams P) {
+    extern __shared__ unsigned long long scan_smem[];
+    unsigned long long *so = scan_smem, *sl = scan_smem + SCAN_SMEM_WORDS;
     __shared__ unsigned long long ws_o[32], ws_l[32];
     __shared__ unsigned long long carry_o, carry_l;
     const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5, n_tiles = P.n_tiles;
     if (tid == 0) { carry_o = 0; carry_l = 0; }
-    __syncthreads();
-    // 1024 tiles per round: coalesced loads, warp scans, one scan over the 32 warp sums
-    for (uint32_t base = 0; base < n_tiles; base += 1024) {
-        const uint32_t i = base + tid;
-        const unsigned long long vo = (i < n_tiles) ? P.tile_out[i] : 0ULL;
-        const unsigned long long vl = (i < n_tiles) ? (unsigned long long)P.tile_lines[i] : 0ULL;
+    // A pass stages SCAN_BATCH tiles in shared memory with coalesced loads (all of them in flight
+    // together), each thread scans its 8 consecutive tiles there, and the prefixes go back coalesced.
+    for (uint32_t base = 0; base < n_tiles; base += SCAN_BATCH) {
+        const uint32_t cnt = min(SCAN_BATCH, n_tiles - base);
+#pragma unroll
+        for (uint32_t j = 0; j < SCAN_BATCH / 1024; ++j) {
+            const uint32_t i = j * 1024 + tid;
+            so[scan_pad(i)] = i < cnt ? P.tile_out[base + i] : 0ULL;
+            sl[scan_pad(i)] = i < cnt ? (unsigned long long)P.tile_lines[base + i] : 0ULL;
+        }
+        __syncthreads();
+        unsigned long long vo = 0, vl = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j) { vo += so[scan_pad(tid * 8 + j)]; vl += sl[scan_pad(tid * 8 + j)]; }
         unsigned long long io = vo, il = vl;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -1145,24 +1168,37 @@ tile_scan_kernel(const KParams P) {
             if ((int)lane >= o) { io += to; il += tl2; }
         }
         if (lane == 31) { ws_o[w] = io; ws_l[w] = il; }
+        const unsigned long long c_o = carry_o, c_l = carry_l;
         __syncthreads();
         if (w == 0) {
-            unsigned long long so = ws_o[lane], sl = ws_l[lane];
-            const unsigned long long so0 = so, sl0 = sl;
+            unsigned long long s_o = ws_o[lane], s_l = ws_l[lane];
+            const unsigned long long so0 = s_o, sl0 = s_l;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long to = __shfl_up_sync(FULL, so, o), tl2 = __shfl_up_sync(FULL, sl, o);
-                if ((int)lane >= o) { so += to; sl += tl2; }
+                const unsigned long long to = __shfl_up_sync(FULL, s_o, o), tl2 = __shfl_up_sync(FULL, s_l, o);
+                if ((int)lane >= o) { s_o += to; s_l += tl2; }
             }
-            ws_o[lane] = so - so0; ws_l[lane] = sl - sl0;          // exclusive over warps
+            ws_o[lane] = s_o - so0; ws_l[lane] = s_l - sl0;        // exclusive over warps
+            if (lane == 31) { carry_o = c_o + s_o; carry_l = c_l + s_l; }
         }
         __syncthreads();
-        const unsigned long long eo = carry_o + ws_o[w] + (io - vo), el = carry_l + ws_l[w] + (il - vl);
-        if (i < n_tiles) { P.tile_base[i] = eo; P.line_base[i] = el; }
+        unsigned long long ro = c_o + ws_o[w] + (io - vo), rl = c_l + ws_l[w] + (il - vl);
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j) {
+            const uint32_t k = scan_pad(tid * 8 + j);
+            const unsigned long long a = so[k], b = sl[k];
+            so[k] = ro; sl[k] = rl;
+            ro += a; rl += b;
+        }
         __syncthreads();
-        if (tid == 1023) { carry_o = eo + vo; carry_l = el + vl; }
+#pragma unroll
+        for (uint32_t j = 0; j < SCAN_BATCH / 1024; ++j) {
+            const uint32_t i = j * 1024 + tid;
+            if (i < cnt) { P.tile_base[base + i] = so[scan_pad(i)]; P.line_base[base + i] = sl[scan_pad(i)]; }
+        }
         __syncthreads();
     }
+    __syncthreads();
     if (tid == 0) P.stats->bytes_out = carry_o;
     __syncthreads();
     unsigned long long nev = P.stats->n_events;
@@ -1184,33 +1220,80 @@ tile_scan_kernel(const KParams P) {
 // ---------------------------------------------------------------------------------------
 // K2b: rows -> text.  One thread per row record.
 // ---------------------------------------------------------------------------------------
+// AF / HWE: a warp takes 32 records; every lane builds the text of its row in a 64-byte slot of
+// shared memory (prefix copy + number), then the warp writes the rows out one after the other with
+// lane = byte, so a store instruction covers one row's contiguous bytes (1-2 sectors) instead of
+// one byte in each of 32 rows.  Rows whose prefix did not fit the 32-byte side copy gather it from
+// the input.  ALLELE_COUNT -a rows (long prefixes, few rows) keep one thread per row.
 template <int OP>
 __global__ void __launch_bounds__(256)
 format_rows_kernel(const KParams P) {
     if (P.stats->overflow) return;
     const unsigned long long nrec = P.stats->n_recs;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nrec;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const Rec r = P.recs[i];
-        uint8_t *o = P.out + P.tile_base[r.tile] + r.off_in_tile;
-        const uint8_t *src = P.in + (uint64_t)r.tile * P.tile_bytes + r.ls_rel;
-        for (uint32_t k = 0; k < r.prefix_len; ++k) o[k] = __ldg(src + k);
-        o += r.prefix_len;
-        if (OP == OP_AC) {                                       // allele_counter.cpp:1454-1461
+    if (OP == OP_AC) {                                           // allele_counter.cpp:1454-1461
+        for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nrec;
+             i += (unsigned long long)gridDim.x * blockDim.x) {
+            const Rec r = P.recs[i];
+            uint8_t *o = P.out + P.tile_base[r.tile] + r.off_in_tile;
+            const uint8_t *src = P.in + (uint64_t)r.tile * P.tile_bytes + r.ls_rel;
+            for (uint32_t k = 0; k < r.prefix_len; ++k) o[k] = __ldg(src + k);
+            o += r.prefix_len;
             for (uint32_t k = 0; k < r.d; ++k) *o++ = '\t';
             o = put_dec(o, (int)r.a); *o++ = '\t'; o = put_dec(o, (int)r.b); *o++ = '\t'; o = put_dec(o, (int)r.c); *o = '\n';
-            continue;
         }
-        char num[24]; int nl;
-        if (OP == OP_AF) {
-            double v = af_value(r.a, r.b);
-            nl = (P.mode == MODE_FILE) ? fmt_af_file(v, num) : fmt_af_stdin(v, num);
-        } else {
-            double pv = hwe_pvalue((int)r.a, (int)r.b, (int)r.c);
-            nl = (P.mode == MODE_FILE) ? fmt_p_file(pv, num) : fmt_p_stdin(pv, num);
+        return;
+    }
+    __shared__ __align__(16) uint8_t rows_sm[8][32][64];
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const unsigned long long warp0 = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5;
+    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long base = warp0 * 32; base < nrec; base += nwarps * 32) {
+        const unsigned long long i = base + lane;
+        uint8_t *dst = nullptr; const uint8_t *src = nullptr;
+        uint32_t plen = 0, tlen = 0;                             // prefix bytes, bytes of the row staged in shared memory
+        bool gather = false;
+        if (i < nrec) {
+            const Rec r = P.recs[i];
+            dst = P.out + P.tile_base[r.tile] + r.off_in_tile;
+            plen = r.prefix_len;
+            uint8_t *slot = rows_sm[wi][lane];
+            uint32_t at = 0;
+            if (plen <= 32) {
+                *reinterpret_cast<uint4 *>(slot) = *reinterpret_cast<const uint4 *>(P.rec_prefix + i * 32);
+                *reinterpret_cast<uint4 *>(slot + 16) = *reinterpret_cast<const uint4 *>(P.rec_prefix + i * 32 + 16);
+                at = plen;
+            } else {
+                gather = true;
+                src = P.in + (uint64_t)r.tile * P.tile_bytes + r.ls_rel;
+            }
+            char num[24]; int nl;
+            if (OP == OP_AF) {
+                double v = af_value(r.a, r.b);
+                nl = (P.mode == MODE_FILE) ? fmt_af_file(v, num) : fmt_af_stdin(v, num);
+            } else {
+                double pv = hwe_pvalue((int)r.a, (int)r.b, (int)r.c);
+                nl = (P.mode == MODE_FILE) ? fmt_p_file(pv, num) : fmt_p_stdin(pv, num);
+            }
+            for (int k = 0; k < nl; ++k) slot[at + k] = (uint8_t)num[k];
+            slot[at + nl] = '\n';
+            tlen = at + nl + 1;
         }
-        for (int k = 0; k < nl; ++k) o[k] = (uint8_t)num[k];
-        o[nl] = '\n';
+        __syncwarp();
+        const unsigned gm = __ballot_sync(FULL, gather);
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) {
+            uint8_t *d = reinterpret_cast<uint8_t *>(__shfl_sync(FULL, (unsigned long long)dst, j));
+            const uint32_t tl = __shfl_sync(FULL, tlen, j);
+            if ((gm >> j) & 1u) {
+                const uint8_t *sj = reinterpret_cast<const uint8_t *>(__shfl_sync(FULL, (unsigned long long)src, j));
+                const uint32_t pl = __shfl_sync(FULL, plen, j);
+                for (uint32_t k = lane; k < pl; k += 32) d[k] = __ldg(sj + k);
+                d += pl;
+            }
+            if ((uint32_t)lane < tl) d[lane] = rows_sm[wi][j][lane];
+            if ((uint32_t)lane + 32 < tl) d[lane + 32] = rows_sm[wi][j][lane + 32];
+        }
+        __syncwarp();
     }
 }
 
