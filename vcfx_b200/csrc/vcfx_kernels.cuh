@@ -23,6 +23,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stddef.h>
 #include "vcfx_numfmt.cuh"
 
 namespace vcfx {
@@ -55,6 +56,12 @@ struct DevStats {
     unsigned long long first_short_line;  // filled by tile_scan_kernel
     unsigned long long n_recs;            // rows appended (may exceed rec_cap: then overflow)
 };
+
+// shared-memory event counters of K1: slot = index of the 64-bit field in DevStats
+enum : int { C_LINES = 0, C_DATA = 1, C_ROWS = 2, C_FLAG = 3, C_PRE = 4, C_SHORT = 5, C_DOTS = 8, CNT_SLOTS = 9 };
+static_assert(offsetof(DevStats, lines) == 8 * C_LINES && offsetof(DevStats, data_lines) == 8 * C_DATA && offsetof(DevStats, rows) == 8 * C_ROWS &&
+              offsetof(DevStats, flagged) == 8 * C_FLAG && offsetof(DevStats, pre_header) == 8 * C_PRE && offsetof(DevStats, short_lines) == 8 * C_SHORT &&
+              offsetof(DevStats, dots_terminated) == 8 * C_DOTS, "counter slots follow DevStats");
 
 struct KParams {
     const uint8_t *in;       // chunk bytes; readable and '\n'-filled for >= 64 B past n
@@ -127,6 +134,7 @@ __device__ __forceinline__ void clip4(uint32_t &m0, uint32_t &m1, uint32_t &m2, 
 
 __device__ __forceinline__ uint4 ld16(const uint8_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
 __device__ __forceinline__ uint32_t ldb(const uint8_t *p) { return (uint32_t)__ldg(p); }
+__device__ __forceinline__ uint32_t ldw(const uint8_t *p) { return __ldg(reinterpret_cast<const uint32_t *>(p)); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ bool is_dig(uint32_t b) { return (b - 48u) <= 9u; }
@@ -453,7 +461,12 @@ vcfx_scan_kernel(const KParams P) {
     constexpr int NEED_TABS = (OP == OP_VC) ? 7 : 9;        // the header phase ends once this many tabs are ranked
     if (OP == OP_AC && P.ac_pass && P.stats->overflow) return;
 
-    unsigned long long s_lines = 0, s_data = 0, s_rows = 0, s_pre = 0, s_short = 0, s_flag = 0, s_dots = 0;
+    // per-warp event counters live in shared memory (fire-and-forget adds from lane 0) and are folded into
+    // DevStats after every tile; the slot index is the field's index in DevStats
+    __shared__ unsigned int s_cnt[WARPS_PER_CTA][CNT_SLOTS];
+    if (lane < CNT_SLOTS) s_cnt[wid][lane] = 0;
+    __syncwarp();
+#define VCFX_COUNT(slot, v) do { if (lane == 0) atomicAdd(&s_cnt[wid][slot], (unsigned int)(v)); } while (0)
 
     for (;;) {
         uint32_t tile = 0;
@@ -467,6 +480,7 @@ vcfx_scan_kernel(const KParams P) {
         const uint64_t a0 = (a >= 16) ? ((a - 16) & ~(uint64_t)15) : 0;
         const uint8_t *__restrict__ tin = P.in + a0;
         const uint32_t ra = (uint32_t)(a - a0), rb = (uint32_t)(b - a0);
+        const uint32_t nrel = (uint32_t)min(n - a0, (uint64_t)0xFFFFFFFFu);   // chunk end as an offset from a0 (clamped)
 
         // ---- first line start in [a, b): byte 0 of the chunk, or one past a '\n' at >= a-1
         uint32_t ls = rb;                                   // "none"
@@ -645,37 +659,76 @@ vcfx_scan_kernel(const KParams P) {
                             }
                         }
                     }
-                    // ---- steady state: raw tier-1 windows, three register sets rotating so that nothing is
-                    // moved: the set just consumed receives the load for three windows ahead
+                    // ---- steady state: rounds of three raw tier-1 windows, one vote per round.  A lane reads its
+                    // 16 bytes plus the word after them (20 contiguous bytes, so no shuffles and no dependence on
+                    // the neighbour's registers); the loads for the next round are issued as soon as a window's
+                    // words have been rotated, a full round before they are needed.  Nothing is XORed per word:
+                    // every rotated word f is pat + y (y = the two allele bits), so the wrapping sum of the f's is
+                    // N * pat + sum(y) and, for HWE, the wrapping sum of f * f yields sum(a & b) (see the flush).
                     if (t1_on && prev_ok) {
-                        const uint8_t *lp = tin + wb + 16 * lane;
-#define VCFX_T1_STEP(A, B, EXIT)                                                                   \
-                        {                                                                          \
-                            uint32_t la_ = __shfl_down_sync(FULL, A.x, 1);                         \
-                            const uint32_t nx_ = __shfl_sync(FULL, B.x, 0);                        \
-                            if (lane == 31) la_ = nx_;                                             \
-                            if (!t1_eval<OP>(A.x, A.y, A.z, A.w, la_, sh_u, pat, accp, hetp, hap)) goto EXIT; \
-                            n_real += 128; wb += WINDOW;                                           \
-                            A = ld16(lp + 3 * WINDOW); lp += WINDOW;                               \
+                        const uint32_t RMAX = (OP == OP_AF) ? 4000u : 2600u;     // rounds per flush: the packed sums stay exact
+                        for (;;) {
+                            const uint8_t *lp = tin + wb + 16 * lane;
+                            uint32_t la0 = ldw(lp + 16), la1 = ldw(lp + WINDOW + 16), la2 = ldw(lp + 2 * WINDOW + 16);
+                            const uint32_t pf_need = wb + 12 * WINDOW;
+                            const uint32_t pf_rounds = nrel > pf_need ? (nrel - pf_need) / (3 * WINDOW) : 0u;
+                            uint32_t r = 0, accf = 0, acc2 = 0;
+                            bool clean = true;
+                            for (; r < RMAX; ++r) {
+                                // per window: rotate, fold into the round's check / sums, and send the load for the
+                                // same window of the next round into the registers just freed (if this round turns
+                                // out not to be clean, its three windows are simply read again)
+                                uint32_t bad, sum, sq = 0;
+#define VCFX_T1_WIN(X, LA, OFF, FIRST)                                                                       \
+                                {                                                                            \
+                                    const uint32_t f0 = __funnelshift_rc(X.x, X.y, sh_u), f1 = __funnelshift_rc(X.y, X.z, sh_u); \
+                                    const uint32_t f2 = __funnelshift_rc(X.z, X.w, sh_u), f3 = __funnelshift_rc(X.w, LA, sh_u);  \
+                                    X = ld16(lp + (OFF)); LA = ldw(lp + (OFF) + 16);                         \
+                                    if (FIRST) { bad = (f0 ^ pat) | (f1 ^ pat); sum = f0 + f1; }             \
+                                    else { bad |= f0 ^ pat; bad |= f1 ^ pat; sum += f0 + f1; }               \
+                                    bad |= f2 ^ pat; bad |= f3 ^ pat; sum += f2 + f3;                        \
+                                    if (OP == OP_HWE) sq += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3;           \
+                                }
+                                VCFX_T1_WIN(cur, la0, 3 * WINDOW, true)
+                                VCFX_T1_WIN(nxt, la1, 4 * WINDOW, false)
+                                VCFX_T1_WIN(nx2, la2, 5 * WINDOW, false)
+#undef VCFX_T1_WIN
+                                if (__any_sync(FULL, (bad & 0xFFFEFFFEu) != 0)) {
+                                    cur = ld16(lp); nxt = ld16(lp + WINDOW); nx2 = ld16(lp + 2 * WINDOW);
+                                    clean = false; break;
+                                }
+                                accf += sum;
+                                if (OP == OP_HWE) acc2 += sq;
+                                lp += 3 * WINDOW;
+                                if (r < pf_rounds) {          // L2 prefetch 6 KB ahead, 1.5 KB per round
+                                    prefetch_l2(lp + 9 * WINDOW); prefetch_l2(lp + 10 * WINDOW); prefetch_l2(lp + 11 * WINDOW);
+                                }
+                            }
+                            // flush: N rotated words went into the sums
+                            const uint32_t N = 12u * r;
+                            const uint32_t ys = accf - N * pat;                   // sum(a) in bits 0..15, sum(b) in 16..31
+                            const uint32_t sa = ys & 0xFFFFu, sb = ys >> 16;
+                            if (OP == OP_AF) ta += sa + sb;
+                            else {
+                                // f * f = pat^2 + 2 pat y + y^2 and y^2 = a + 2^17 (a & b)   (all mod 2^32)
+                                const uint32_t y2 = acc2 - N * (pat * pat) - 2u * pat * ys;
+                                const uint32_t sab = (y2 - sa) >> 17;
+                                hetp += sa + sb - 2u * sab; hap += sab;
+                            }
+                            n_real += 384u * r; wb += 3 * WINDOW * r;
+                            if (clean) continue;                                 // only the flush limit was reached
+                            break;
                         }
-                        // L2 prefetch 6 KB ahead: lanes 0..11 cover the 1.5 KB one round consumes; rounds whose
-                        // prefetch would pass the end of the chunk are simply not prefetched
-                        const uint8_t *pf = tin + wb + 12 * WINDOW + 128 * lane;
-                        const long long pf_room = (long long)(in_end - pf) - 128 * 12;
-                        int pf_rounds = (lane < 12 && pf_room > 0) ? (int)min((long long)0x7FFFFFFF, pf_room / (3 * WINDOW)) : 0;
-                        // at most 4000 rounds at a time so the 16-bit packed sums cannot overflow (3 * 4 per round)
-                        for (int guard = 0; guard < 4000; ++guard) {
-                            VCFX_T1_STEP(cur, nxt, t1_exit0)
-                            VCFX_T1_STEP(nxt, nx2, t1_exit1)
-                            VCFX_T1_STEP(nx2, cur, t1_exit2)
-                            if (pf_rounds > 0) { prefetch_l2(pf); --pf_rounds; }
-                            pf += 3 * WINDOW;
+                        // the round that failed usually holds the line's '\n': take its clean windows one by one
+#pragma unroll 1
+                        for (int k = 0; k < 3; ++k) {
+                            uint32_t la_ = __shfl_down_sync(FULL, cur.x, 1);
+                            const uint32_t nx_ = __shfl_sync(FULL, nxt.x, 0);
+                            if (lane == 31) la_ = nx_;
+                            if (!t1_eval<OP>(cur.x, cur.y, cur.z, cur.w, la_, sh_u, pat, accp, hetp, hap)) break;
+                            n_real += 128; wb += WINDOW;
+                            cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
                         }
-                        goto t1_exit0;
-#undef VCFX_T1_STEP
-                    t1_exit1: { const uint4 t_ = cur; cur = nxt; nxt = nx2; nx2 = t_; } goto t1_exit0;
-                    t1_exit2: { const uint4 t_ = nx2; nx2 = nxt; nxt = cur; cur = t_; }
-                    t1_exit0: ;
                         if (OP == OP_AF) { ta += (accp & 0xFFFFu) + (accp >> 16); accp = 0; }
                     }
                     // ---- this window needs a closer look
@@ -932,9 +985,9 @@ vcfx_scan_kernel(const KParams P) {
             if (OP == OP_VC) {
                 // variant_counter.cpp:364-380: raw-empty and '#' lines are skipped, >= 7 tabs counts
                 if (e != ls && !hash) {
-                    if (tabs >= 7) ++s_rows;
+                    if (tabs >= 7) VCFX_COUNT(C_ROWS, 1);
                     else {
-                        ++s_short;
+                        VCFX_COUNT(C_SHORT, 1);
                         if (lane == 0) {
                             unsigned long long key = ((unsigned long long)tile << 32) | (nlines - 1);
                             atomicMin(&P.stats->first_short_key, key);
@@ -951,24 +1004,24 @@ vcfx_scan_kernel(const KParams P) {
                 }
                 bool row = false;
                 if (OP == OP_AF) {
-                    if (a0 + ls < P.valid_from) ++s_pre;                 // allele_freq_calc.cpp:382-386 / 499-502
+                    if (a0 + ls < P.valid_from) VCFX_COUNT(C_PRE, 1);                 // allele_freq_calc.cpp:382-386 / 499-502
                     else if (P.mode == MODE_FILE) {
-                        ++s_data;
+                        VCFX_COUNT(C_DATA, 1);
                         // FORMAT must exist and be non-empty (:396-401) and hold a GT key (:413)
                         if (tabs >= 9) row = gt_index >= 0;
                         else if (tabs == 8 && tp[7] + 1 < ee) row = gt_index_of(tin + tp[7] + 1, tin + ee) >= 0;
                     } else {
                         // stdin: fields = tabs + 1, minus a dropped empty tail (:509-518); < 9 warns (:520-523)
                         int nf = tabs + ((ldb(tin + ee - 1) == '\t') ? 0 : 1);
-                        if (nf < 9) ++s_short;
+                        if (nf < 9) VCFX_COUNT(C_SHORT, 1);
                         else {
-                            ++s_data;
+                            VCFX_COUNT(C_DATA, 1);
                             if (tabs >= 9) row = gt_index >= 0;
                             else row = gt_index_of(tin + tp[7] + 1, tin + ee) >= 0;
                         }
                     }
                 } else {
-                    ++s_data;
+                    VCFX_COUNT(C_DATA, 1);
                     if (tabs >= 9 && do_samples) {
                         bool comma = false;                              // hwe_tester.cpp:503 / :586
                         for (uint32_t q = tp[3] + 1; q < tp[4]; ++q) comma |= (ldb(tin + q) == ',');
@@ -993,13 +1046,13 @@ vcfx_scan_kernel(const KParams P) {
                         // record so that the format kernel does not have to gather it from the input
                         if (prefix_len <= 32 && (uint32_t)lane < prefix_len) P.rec_prefix[slot * 32 + lane] = (uint8_t)ldb(tin + ls + lane);
                     }
-                    out_bytes += row_len; ++s_rows;
+                    out_bytes += row_len; VCFX_COUNT(C_ROWS, 1);
                 }
             }
             else if (OP == OP_AC) {
                 // allele_counter.cpp:571 / :1373: empty and '#' lines are skipped; no '\r' handling
                 if (e != ls && !hash) {
-                    if (P.ac_pass == 0) ++s_data;
+                    if (P.ac_pass == 0) VCFX_COUNT(C_DATA, 1);
                     const uint2 *scr = P.col_scratch + (size_t)(blockIdx.x * WARPS_PER_CTA + wid) * P.max_col;
                     const uint32_t ns_parsed = tabs >= 9 ? (uint32_t)(tabs - 8) : 0u;
                     uint32_t n_rows = P.n_sel;
@@ -1031,7 +1084,7 @@ vcfx_scan_kernel(const KParams P) {
                                 P.recs[slot] = r;
                             }
                         }
-                        out_bytes += row_len; ++s_rows;
+                        out_bytes += row_len; VCFX_COUNT(C_ROWS, 1);
                     } else {
                         uint8_t *stage = s_stage + wid * (AC_STAGE + 16);
                         unsigned long long opos = (P.ac_pass ? P.tile_base[tile] : 0ULL) + out_bytes;
@@ -1070,7 +1123,7 @@ vcfx_scan_kernel(const KParams P) {
                             }
                             opos += btot; out_bytes += btot;
                         }
-                        if (P.ac_pass == 0) s_rows += n_rows;
+                        if (P.ac_pass == 0) VCFX_COUNT(C_ROWS, n_rows);
                     }
                 }
             }
@@ -1078,10 +1131,10 @@ vcfx_scan_kernel(const KParams P) {
                 const bool term = (a0 + e) < n;                          // a real '\n', not the pad behind the chunk
                 const uint32_t raw_end = term ? e + 1 : e;
                 const bool data = (ee != ls) && !hash;                   // missing_detector.cpp:511 / :865-873
-                if (data) ++s_data;
+                if (data) VCFX_COUNT(C_DATA, 1);
                 const bool has_samples = data && tabs >= 9;
                 // the reference's pre-scan looks at every terminated line after the leading '#' block (:347-369)
-                if (term && has_samples && md_any && tp[8] + 1 < e && (a0 + ls >= P.valid_from)) ++s_dots;
+                if (term && has_samples && md_any && tp[8] + 1 < e && (a0 + ls >= P.valid_from)) VCFX_COUNT(C_DOTS, 1);
                 md_add_nl = false;
                 if (has_samples && md_flag && tp[8] + 1 < ee) {          // :520-527, :530
                     const uint32_t info_off = tp[6] + 1 - ls, info_len = tp[7] - tp[6] - 1, content_len = ee - ls;
@@ -1100,14 +1153,14 @@ vcfx_scan_kernel(const KParams P) {
                     }
                     out_bytes += (ls - md_prev_end) + mod_len;
                     md_prev_end = raw_end;
-                    ++s_flag;
+                    VCFX_COUNT(C_FLAG, 1);
                 } else if (!term && P.mode == MODE_STDIN) md_add_nl = true;   // getline + "\n" (:866-889)
                 md_last_end = raw_end;
             }
             __syncwarp();
             ls = e + 1;
         }
-        if (!(OP == OP_AC && P.ac_pass)) s_lines += nlines;
+        if (!(OP == OP_AC && P.ac_pass)) VCFX_COUNT(C_LINES, nlines);
         if (OP == OP_MD) {
             const uint32_t tail = md_last_end - md_prev_end;
             if (lane == 0) {
@@ -1118,16 +1171,14 @@ vcfx_scan_kernel(const KParams P) {
             out_bytes += tail + (md_add_nl ? 1u : 0u);
         }
         if (lane == 0 && !(OP == OP_AC && P.ac_pass)) { P.tile_lines[tile] = nlines; P.tile_out[tile] = out_bytes; }
+        __syncwarp();
+        if (lane < CNT_SLOTS) {
+            const unsigned int v = s_cnt[wid][lane];
+            if (v) { s_cnt[wid][lane] = 0; atomicAdd(reinterpret_cast<unsigned long long *>(P.stats) + lane, (unsigned long long)v); }
+        }
+        __syncwarp();
     }
-    if (lane == 0) {
-        if (s_lines) atomicAdd(&P.stats->lines, s_lines);
-        if (s_data) atomicAdd(&P.stats->data_lines, s_data);
-        if (s_rows) atomicAdd(&P.stats->rows, s_rows);
-        if (s_pre) atomicAdd(&P.stats->pre_header, s_pre);
-        if (s_short) atomicAdd(&P.stats->short_lines, s_short);
-        if (s_flag) atomicAdd(&P.stats->flagged, s_flag);
-        if (s_dots) atomicAdd(&P.stats->dots_terminated, s_dots);
-    }
+#undef VCFX_COUNT
 }
 
 // ---------------------------------------------------------------------------------------
