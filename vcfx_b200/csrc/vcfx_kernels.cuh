@@ -659,53 +659,61 @@ vcfx_scan_kernel(const KParams P) {
                             }
                         }
                     }
-                    // ---- steady state: rounds of three raw tier-1 windows, one vote per round.  A lane reads its
-                    // 16 bytes plus the word after them (20 contiguous bytes, so no shuffles and no dependence on
-                    // the neighbour's registers); the loads for the next round are issued as soon as a window's
-                    // words have been rotated, a full round before they are needed.  Nothing is XORed per word:
-                    // every rotated word f is pat + y (y = the two allele bits), so the wrapping sum of the f's is
+                    // ---- steady state: rounds of two raw tier-1 windows, one vote per round, two register sets.
+                    // A lane reads its 16 bytes plus the word after them (20 contiguous bytes: no shuffles, no
+                    // dependence on the neighbour's registers).  Set A is reloaded right after its vote and is not
+                    // touched again until set B's round is over, so every load has a full round to land, and a
+                    // failed vote leaves the failing windows in registers.  Nothing is XORed per word: every
+                    // rotated word f is pat + y (y = the two allele bits), so the wrapping sum of the f's is
                     // N * pat + sum(y) and, for HWE, the wrapping sum of f * f yields sum(a & b) (see the flush).
                     if (t1_on && prev_ok) {
-                        const uint32_t RMAX = (OP == OP_AF) ? 4000u : 2600u;     // rounds per flush: the packed sums stay exact
+                        const uint32_t ITMAX = (OP == OP_AF) ? 4000u : 2000u;    // iterations per flush: the packed sums stay exact
                         for (;;) {
                             const uint8_t *lp = tin + wb + 16 * lane;
-                            uint32_t la0 = ldw(lp + 16), la1 = ldw(lp + WINDOW + 16), la2 = ldw(lp + 2 * WINDOW + 16);
+                            uint4 nx3 = ld16(lp + 3 * WINDOW);
+                            uint32_t la0 = ldw(lp + 16), la1 = ldw(lp + WINDOW + 16);
+                            uint32_t la2 = ldw(lp + 2 * WINDOW + 16), la3 = ldw(lp + 3 * WINDOW + 16);
                             const uint32_t pf_need = wb + 12 * WINDOW;
-                            const uint32_t pf_rounds = nrel > pf_need ? (nrel - pf_need) / (3 * WINDOW) : 0u;
-                            uint32_t r = 0, accf = 0, acc2 = 0;
-                            bool clean = true;
-                            for (; r < RMAX; ++r) {
-                                // per window: rotate, fold into the round's check / sums, and send the load for the
-                                // same window of the next round into the registers just freed (if this round turns
-                                // out not to be clean, its three windows are simply read again)
-                                uint32_t bad, sum, sq = 0;
-#define VCFX_T1_WIN(X, LA, OFF, FIRST)                                                                       \
-                                {                                                                            \
+                            const uint32_t pf_iters = nrel > pf_need ? (nrel - pf_need) / (4 * WINDOW) : 0u;
+                            uint32_t it = 0, accf = 0, acc2 = 0;
+                            int state = 0;                                       // 1: set A's round failed, 2: set B's
+#define VCFX_T1_ROUND(X, LX, Y, LY)                                                                              \
+                                uint32_t bad, sum, sq = 0;                                                       \
+                                {                                                                                \
                                     const uint32_t f0 = __funnelshift_rc(X.x, X.y, sh_u), f1 = __funnelshift_rc(X.y, X.z, sh_u); \
-                                    const uint32_t f2 = __funnelshift_rc(X.z, X.w, sh_u), f3 = __funnelshift_rc(X.w, LA, sh_u);  \
-                                    X = ld16(lp + (OFF)); LA = ldw(lp + (OFF) + 16);                         \
-                                    if (FIRST) { bad = (f0 ^ pat) | (f1 ^ pat); sum = f0 + f1; }             \
-                                    else { bad |= f0 ^ pat; bad |= f1 ^ pat; sum += f0 + f1; }               \
-                                    bad |= f2 ^ pat; bad |= f3 ^ pat; sum += f2 + f3;                        \
-                                    if (OP == OP_HWE) sq += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3;           \
+                                    const uint32_t f2 = __funnelshift_rc(X.z, X.w, sh_u), f3 = __funnelshift_rc(X.w, LX, sh_u);  \
+                                    const uint32_t g0 = __funnelshift_rc(Y.x, Y.y, sh_u), g1 = __funnelshift_rc(Y.y, Y.z, sh_u); \
+                                    const uint32_t g2 = __funnelshift_rc(Y.z, Y.w, sh_u), g3 = __funnelshift_rc(Y.w, LY, sh_u);  \
+                                    bad = (f0 ^ pat) | (f1 ^ pat); bad |= f2 ^ pat; bad |= f3 ^ pat;             \
+                                    bad |= g0 ^ pat; bad |= g1 ^ pat; bad |= g2 ^ pat; bad |= g3 ^ pat;          \
+                                    sum = (f0 + f1 + f2) + (f3 + g0 + g1) + (g2 + g3);                           \
+                                    if (OP == OP_HWE) sq = f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3 + g0 * g0 + g1 * g1 + g2 * g2 + g3 * g3; \
                                 }
-                                VCFX_T1_WIN(cur, la0, 3 * WINDOW, true)
-                                VCFX_T1_WIN(nxt, la1, 4 * WINDOW, false)
-                                VCFX_T1_WIN(nx2, la2, 5 * WINDOW, false)
-#undef VCFX_T1_WIN
-                                if (__any_sync(FULL, (bad & 0xFFFEFFFEu) != 0)) {
-                                    cur = ld16(lp); nxt = ld16(lp + WINDOW); nx2 = ld16(lp + 2 * WINDOW);
-                                    clean = false; break;
+                            for (; it < ITMAX; ++it) {
+                                {
+                                    VCFX_T1_ROUND(cur, la0, nxt, la1)
+                                    if (__any_sync(FULL, (bad & 0xFFFEFFFEu) != 0)) { state = 1; break; }
+                                    accf += sum; if (OP == OP_HWE) acc2 += sq;
+                                    cur = ld16(lp + 4 * WINDOW); la0 = ldw(lp + 4 * WINDOW + 16);
+                                    nxt = ld16(lp + 5 * WINDOW); la1 = ldw(lp + 5 * WINDOW + 16);
                                 }
-                                accf += sum;
-                                if (OP == OP_HWE) acc2 += sq;
-                                lp += 3 * WINDOW;
-                                if (r < pf_rounds) {          // L2 prefetch 6 KB ahead, 1.5 KB per round
-                                    prefetch_l2(lp + 9 * WINDOW); prefetch_l2(lp + 10 * WINDOW); prefetch_l2(lp + 11 * WINDOW);
+                                {
+                                    VCFX_T1_ROUND(nx2, la2, nx3, la3)
+                                    if (__any_sync(FULL, (bad & 0xFFFEFFFEu) != 0)) { state = 2; break; }
+                                    accf += sum; if (OP == OP_HWE) acc2 += sq;
+                                    nx2 = ld16(lp + 6 * WINDOW); la2 = ldw(lp + 6 * WINDOW + 16);
+                                    nx3 = ld16(lp + 7 * WINDOW); la3 = ldw(lp + 7 * WINDOW + 16);
                                 }
+                                if (it < pf_iters) {          // L2 prefetch 6 KB ahead, 2 KB per iteration
+                                    prefetch_l2(lp + 12 * WINDOW); prefetch_l2(lp + 13 * WINDOW);
+                                    prefetch_l2(lp + 14 * WINDOW); prefetch_l2(lp + 15 * WINDOW);
+                                }
+                                lp += 4 * WINDOW;
                             }
+#undef VCFX_T1_ROUND
                             // flush: N rotated words went into the sums
-                            const uint32_t N = 12u * r;
+                            const uint32_t rounds = 2u * it + (state == 2 ? 1u : 0u);
+                            const uint32_t N = 8u * rounds;
                             const uint32_t ys = accf - N * pat;                   // sum(a) in bits 0..15, sum(b) in 16..31
                             const uint32_t sa = ys & 0xFFFFu, sb = ys >> 16;
                             if (OP == OP_AF) ta += sa + sb;
@@ -715,13 +723,13 @@ vcfx_scan_kernel(const KParams P) {
                                 const uint32_t sab = (y2 - sa) >> 17;
                                 hetp += sa + sb - 2u * sab; hap += sab;
                             }
-                            n_real += 384u * r; wb += 3 * WINDOW * r;
-                            if (clean) continue;                                 // only the flush limit was reached
-                            break;
+                            n_real += 256u * rounds; wb += 2 * WINDOW * rounds;
+                            if (state == 2) { const uint4 t_ = cur; cur = nx2; nxt = nx3; nx2 = t_; }   // B failed: A already holds the windows after it
+                            if (state != 0) break;                               // state 0: only the flush limit was reached
                         }
                         // the round that failed usually holds the line's '\n': take its clean windows one by one
 #pragma unroll 1
-                        for (int k = 0; k < 3; ++k) {
+                        for (int k = 0; k < 2; ++k) {
                             uint32_t la_ = __shfl_down_sync(FULL, cur.x, 1);
                             const uint32_t nx_ = __shfl_sync(FULL, nxt.x, 0);
                             if (lane == 31) la_ = nx_;
