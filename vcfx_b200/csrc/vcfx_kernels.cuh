@@ -136,6 +136,7 @@ __device__ __forceinline__ uint4 ld16(const uint8_t *p) { return __ldg(reinterpr
 __device__ __forceinline__ uint32_t ldb(const uint8_t *p) { return (uint32_t)__ldg(p); }
 __device__ __forceinline__ uint32_t ldw(const uint8_t *p) { return __ldg(reinterpret_cast<const uint32_t *>(p)); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ bool is_dig(uint32_t b) { return (b - 48u) <= 9u; }
 __device__ __forceinline__ bool is_sep(uint32_t b) { return b == '/' || b == '|'; }
@@ -443,13 +444,27 @@ __device__ __forceinline__ bool t1_eval(uint32_t w0, uint32_t w1, uint32_t w2, u
     return true;
 }
 
+// Tally four verified (or zeroed) y words: y = [a, 0, b, 0], a and b the allele bits of one sample.
+template <int OP>
+__device__ __forceinline__ void t1_tally(uint32_t y0, uint32_t y1, uint32_t y2, uint32_t y3, uint32_t &accp, uint32_t &hetp, uint32_t &hap) {
+    if (OP == OP_AF) accp += y0 + y1 + y2 + y3;
+    else {
+        const uint32_t pk = y0 + 2u * y1 + 4u * y2 + 8u * y3;   // a-bits in 0..3, b-bits in 16..19
+        const uint32_t ab = pk & 0xFu, bb = (pk >> 16) & 0xFu;
+        hetp += __popc(ab ^ bb); hap += __popc(ab & bb);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // K1: the fused scan / parse / reduce kernel
 // ---------------------------------------------------------------------------------------
 // variant_counter is light enough to run at 48 registers (5 CTAs per SM: +4.5 %); the parsing
 // instantiations need 64 to keep the steady loops free of spills (measured both ways, profiles/README.md)
+#ifndef VCFX_PARSE_CTAS
+#define VCFX_PARSE_CTAS 4
+#endif
 template <int OP>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (OP == OP_VC) ? 5 : 4)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (OP == OP_VC) ? 5 : VCFX_PARSE_CTAS)
 vcfx_scan_kernel(const KParams P) {
     __shared__ uint32_t s_tp[WARPS_PER_CTA][12];
     __shared__ __align__(16) uint8_t s_stage[(OP == OP_AC) ? WARPS_PER_CTA * (AC_STAGE + 16) : 16];
@@ -615,6 +630,28 @@ vcfx_scan_kernel(const KParams P) {
                 uint32_t hetp = 0, hap = 0;        // HWE tier-1 tallies
                 uint32_t n_real = 0;               // samples tallied by tier 1 (uniform)
                 const uint8_t *const in_end = P.in + n;
+                // ---- the window with tab 9, the cheap way.  A rotated word f_k of a lane covers the four bytes
+                // after byte 4k + tau of that lane, i.e. one sample behind its leading tab when the lattice holds.
+                // Tab 9 itself sits on the lattice (tau = its position mod 4), so in its lane the words from its own
+                // on are samples and the earlier ones (and all earlier lanes) are header: whole words are skipped,
+                // no byte masks.  If anything else is in this window the exact path below takes it from scratch.
+                if (t1_on && !found) {
+                    const uint32_t la_ = ldw(tin + wb + 16 * lane + 16);
+                    uint32_t y0 = __funnelshift_rc(cur.x, cur.y, sh_u) ^ pat, y1 = __funnelshift_rc(cur.y, cur.z, sh_u) ^ pat;
+                    uint32_t y2 = __funnelshift_rc(cur.z, cur.w, sh_u) ^ pat, y3 = __funnelshift_rc(cur.w, la_, sh_u) ^ pat;
+                    const uint32_t rel = tab8 - wb, Lb = rel >> 4, kb = (rel >> 2) & 3u;
+                    const uint32_t kmin = (uint32_t)lane > Lb ? 0u : ((uint32_t)lane == Lb ? kb : 4u);
+                    if (kmin > 0) y0 = 0;
+                    if (kmin > 1) y1 = 0;
+                    if (kmin > 2) y2 = 0;
+                    if (kmin > 3) y3 = 0;
+                    if (!__any_sync(FULL, ((y0 | y1 | y2 | y3) & 0xFFFEFFFEu) != 0)) {
+                        t1_tally<OP>(y0, y1, y2, y3, accp, hetp, hap);
+                        n_real += ((wb + WINDOW - 1 - tab8) >> 2) + 1;           // lattice tabs in [tab 9, end of window)
+                        first_win = false; prev_ok = true;
+                        wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
+                    }
+                }
                 for (;;) {
                     // ---- steady state for a FORMAT with several keys (GT first): samples are tens of bytes long,
                     // a lane holds at most one sample start.  Tab and newline masks, one vote, and the lanes that
@@ -668,6 +705,7 @@ vcfx_scan_kernel(const KParams P) {
                     // N * pat + sum(y) and, for HWE, the wrapping sum of f * f yields sum(a & b) (see the flush).
                     if (t1_on && prev_ok) {
                         const uint32_t ITMAX = (OP == OP_AF) ? 4000u : 2000u;    // iterations per flush: the packed sums stay exact
+                        uint32_t la_c = 0, la_n = 0;                             // look-ahead words of cur / nxt once the rounds are over
                         for (;;) {
                             const uint8_t *lp = tin + wb + 16 * lane;
                             uint4 nx3 = ld16(lp + 3 * WINDOW);
@@ -707,6 +745,10 @@ vcfx_scan_kernel(const KParams P) {
                                 if (it < pf_iters) {          // L2 prefetch 6 KB ahead, 2 KB per iteration
                                     prefetch_l2(lp + 12 * WINDOW); prefetch_l2(lp + 13 * WINDOW);
                                     prefetch_l2(lp + 14 * WINDOW); prefetch_l2(lp + 15 * WINDOW);
+#ifdef VCFX_PF1
+                                    prefetch_l1(lp + 8 * WINDOW); prefetch_l1(lp + 9 * WINDOW);
+                                    prefetch_l1(lp + 10 * WINDOW); prefetch_l1(lp + 11 * WINDOW);
+#endif
                                 }
                                 lp += 4 * WINDOW;
                             }
@@ -724,20 +766,45 @@ vcfx_scan_kernel(const KParams P) {
                                 hetp += sa + sb - 2u * sab; hap += sab;
                             }
                             n_real += 256u * rounds; wb += 2 * WINDOW * rounds;
-                            if (state == 2) { const uint4 t_ = cur; cur = nx2; nxt = nx3; nx2 = t_; }   // B failed: A already holds the windows after it
+                            if (state == 2) { const uint4 t_ = cur; cur = nx2; nxt = nx3; nx2 = t_; la_c = la2; la_n = la3; }   // B failed: A already holds the windows after it
+                            else { la_c = la0; la_n = la1; }
                             if (state != 0) break;                               // state 0: only the flush limit was reached
                         }
-                        // the round that failed usually holds the line's '\n': take its clean windows one by one
+                        // ---- the round that failed usually holds the line's '\n'.  Its windows again, one by one, with
+                        // the y words: the first word that is off, in the first lane that has one, must be a sample
+                        // closed by '\n' instead of a tab (y = [a, 0, b, '\n' ^ '\t']); everything before it is tallied
+                        // and the line is finished.  Anything else goes to the exact path below.
+                        bool finished = false;
 #pragma unroll 1
                         for (int k = 0; k < 2; ++k) {
-                            uint32_t la_ = __shfl_down_sync(FULL, cur.x, 1);
-                            const uint32_t nx_ = __shfl_sync(FULL, nxt.x, 0);
-                            if (lane == 31) la_ = nx_;
-                            if (!t1_eval<OP>(cur.x, cur.y, cur.z, cur.w, la_, sh_u, pat, accp, hetp, hap)) break;
-                            n_real += 128; wb += WINDOW;
-                            cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
+                            uint32_t y0 = __funnelshift_rc(cur.x, cur.y, sh_u) ^ pat, y1 = __funnelshift_rc(cur.y, cur.z, sh_u) ^ pat;
+                            uint32_t y2 = __funnelshift_rc(cur.z, cur.w, sh_u) ^ pat, y3 = __funnelshift_rc(cur.w, la_c, sh_u) ^ pat;
+                            const uint32_t b0 = y0 & 0xFFFEFFFEu, b1 = y1 & 0xFFFEFFFEu, b2 = y2 & 0xFFFEFFFEu, b3 = y3 & 0xFFFEFFFEu;
+                            const unsigned fb = __ballot_sync(FULL, (b0 | b1 | b2 | b3) != 0);
+                            if (fb == 0) {
+                                t1_tally<OP>(y0, y1, y2, y3, accp, hetp, hap);
+                                n_real += 128; wb += WINDOW;
+                                cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane); la_c = la_n;
+                                continue;
+                            }
+                            const int Lf = __ffs(fb) - 1;
+                            const uint32_t kf_l = b0 ? 0u : b1 ? 1u : b2 ? 2u : 3u;
+                            const uint32_t yf_l = b0 ? y0 : b1 ? y1 : b2 ? y2 : y3;
+                            const uint32_t kf = __shfl_sync(FULL, kf_l, Lf), yf = __shfl_sync(FULL, yf_l, Lf);
+                            if (((yf ^ 0x03000000u) & 0xFFFEFFFEu) == 0) {
+                                const uint32_t keep = lane < Lf ? 4u : (lane == Lf ? kf + 1u : 0u);   // words of this lane that count
+                                y0 = keep > 0 ? (y0 & 0x00010001u) : 0u;
+                                y1 = keep > 1 ? (y1 & 0x00010001u) : 0u;
+                                y2 = keep > 2 ? (y2 & 0x00010001u) : 0u;
+                                y3 = keep > 3 ? (y3 & 0x00010001u) : 0u;
+                                t1_tally<OP>(y0, y1, y2, y3, accp, hetp, hap);
+                                e = wb + 16u * (uint32_t)Lf + 4u * kf + tau + 4u; found = true; finished = true;
+                                n_real += (e - wb - tau) >> 2;                  // lattice tabs in [wb, e)
+                            }
+                            break;
                         }
                         if (OP == OP_AF) { ta += (accp & 0xFFFFu) + (accp >> 16); accp = 0; }
+                        if (finished) break;
                     }
                     // ---- this window needs a closer look
                     const uint32_t pb = wb + 16 * lane;
