@@ -622,14 +622,9 @@ vcfx_scan_kernel(const KParams P) {
                 const uint32_t tau = tab8 & 3u;
                 const uint32_t sh_u = 8u * (tau + 1u);
                 const uint32_t pat = 0x09300030u | (sep0 << 8);
-                // filler: the bytes "\t0<sep>0" rotated so the tab sits on byte tau of every word — a
-                // well-formed 0/0 sample that adds nothing to the alt / het / homAlt sums
-                const uint32_t fill0 = 0x30003009u | (sep0 << 16);
-                const uint32_t fill = __funnelshift_l(fill0, fill0, 8u * tau);
                 uint32_t accp = 0;                 // packed sums: bits 0..15 first alleles, 16..31 second alleles
                 uint32_t hetp = 0, hap = 0;        // HWE tier-1 tallies
                 uint32_t n_real = 0;               // samples tallied by tier 1 (uniform)
-                const uint8_t *const in_end = P.in + n;
                 // ---- the window with tab 9, the cheap way.  A rotated word f_k of a lane covers the four bytes
                 // after byte 4k + tau of that lane, i.e. one sample behind its leading tab when the lattice holds.
                 // Tab 9 itself sits on the lattice (tau = its position mod 4), so in its lane the words from its own
@@ -691,8 +686,8 @@ vcfx_scan_kernel(const KParams P) {
                             ta += da; tb += db; tc += dc;
                             wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
                             if ((++wcount & 7) == 0) {
-                                const uint8_t *pf = tin + wb + 12 * WINDOW + 128 * lane;
-                                if (pf < in_end) prefetch_l2(pf);
+                                const uint32_t pf = wb + 12 * WINDOW + 128 * lane;
+                                if (pf < nrel) prefetch_l2(tin + pf);
                             }
                         }
                     }
@@ -837,6 +832,10 @@ vcfx_scan_kernel(const KParams P) {
                             const uint32_t k0 = (nib80(kk, 0) >> 7) * 0xFFu, k1 = (nib80(kk, 1) >> 7) * 0xFFu;
                             const uint32_t k2 = (nib80(kk, 2) >> 7) * 0xFFu, k3 = (nib80(kk, 3) >> 7) * 0xFFu;
                             const uint32_t k4 = (range_mask(pb + 16, lo, hi) >> 7) * 0xFFu;
+                            // filler: the bytes "\t0<sep>0" rotated so the tab sits on byte tau of every word — a
+                            // well-formed 0/0 sample that adds nothing to the alt / het / homAlt sums
+                            const uint32_t fill0 = 0x30003009u | (sep0 << 16);
+                            const uint32_t fill = __funnelshift_l(fill0, fill0, 8u * tau);
                             done = t1_eval<OP>((cur.x & k0) | (fill & ~k0), (cur.y & k1) | (fill & ~k1),
                                                (cur.z & k2) | (fill & ~k2), (cur.w & k3) | (fill & ~k3),
                                                (la & k4) | (fill & ~k4), sh_u, pat, accp, hetp, hap);
@@ -862,10 +861,11 @@ vcfx_scan_kernel(const KParams P) {
                         gbal = lat_possible ? __ballot_sync(FULL, lat && sh_lane == sh_u) : 0u;
                         uint32_t m0, m1, m2, m3;
                         const uint32_t n0 = eq_bytes(cur.x, C_NL);
-                        if (first_win) { m0 = t0; m1 = t1; m2 = t2; m3 = t3; }   // already clipped to [ls, e)
+                        m0 = eq_bytes(cur.x, C_TAB); m1 = eq_bytes(cur.y, C_TAB);
+                        m2 = eq_bytes(cur.z, C_TAB); m3 = eq_bytes(cur.w, C_TAB);
+                        // (the header phase's masks are not kept alive for this: registers are short)
+                        if (first_win) clip4(m0, m1, m2, m3, pb, tab8, found ? e : ~0u);   // sample tabs only: tab 9 .. '\n'
                         else {
-                            m0 = eq_bytes(cur.x, C_TAB); m1 = eq_bytes(cur.y, C_TAB);
-                            m2 = eq_bytes(cur.z, C_TAB); m3 = eq_bytes(cur.w, C_TAB);
                             if (!nl_done) {
                                 const uint32_t n1 = eq_bytes(cur.y, C_NL), n2 = eq_bytes(cur.z, C_NL), n3 = eq_bytes(cur.w, C_NL);
                                 const unsigned ebal = __ballot_sync(FULL, (n0 | n1 | n2 | n3) != 0);
@@ -884,7 +884,7 @@ vcfx_scan_kernel(const KParams P) {
                         // (previous lane lattice, or no '\n' in word 0) and all its tabs are sample tabs
                         bool pg = false;
                         if (lat_possible) { pg = __shfl_up_sync(FULL, (int)lat, 1) != 0; if (lane == 0) pg = prev_ok; }
-                        const bool use_lat = lat && (pg || n0 == 0) && !(first_win && rank0 < 8);
+                        const bool use_lat = lat && (pg || n0 == 0) && !(first_win && tp[7] >= pb);   // no header tab in the lane
                         if (use_lat) {
                             if (!found || pb < e) {          // a vouched lattice lane holds no '\n'
                                 if (OP == OP_AF) { ta += packed; tb += 8; }
@@ -894,13 +894,6 @@ vcfx_scan_kernel(const KParams P) {
                                 }
                             }
                         } else {
-                            if (first_win) {                 // drop the tabs that still belong to the header
-                                int d = 8 - rank0;
-                                while (d > 0 && m0) { m0 &= m0 - 1; --d; }
-                                while (d > 0 && m1) { m1 &= m1 - 1; --d; }
-                                while (d > 0 && m2) { m2 &= m2 - 1; --d; }
-                                while (d > 0 && m3) { m3 &= m3 - 1; --d; }
-                            }
                             if (m0 | m1 | m2 | m3) {
                                 bool handled = false;
                                 if (__popc(m0) + __popc(m1) + __popc(m2) + __popc(m3) == 1 && gt_index == 0) {
