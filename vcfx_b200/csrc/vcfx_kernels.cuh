@@ -45,6 +45,9 @@ struct Rec {                 // one output row (32 B)
     uint32_t a, b, c, d;     // op-specific integers (AF: alt,total; HWE: homRef,het,homAlt)
 };
 
+constexpr unsigned int REC_BLOCK = 32;          // row-record slots a warp reserves at a time
+constexpr uint32_t REC_INVALID = 0xFFFFFFFFu;   // Rec::tile of a reserved slot that was never filled
+
 struct DevStats {
     unsigned long long lines, data_lines, rows, flagged, pre_header, short_lines;
     unsigned long long first_short_key;   // (tile << 32 | line index in tile), min
@@ -54,7 +57,7 @@ struct DevStats {
     unsigned long long bytes_out;
     unsigned long long overflow;          // bit 0: row records, bit 1: output bytes
     unsigned long long first_short_line;  // filled by tile_scan_kernel
-    unsigned long long n_recs;            // rows appended (may exceed rec_cap: then overflow)
+    unsigned long long n_recs;            // row-record slots reserved (may exceed rec_cap: then overflow)
 };
 
 // shared-memory event counters of K1: slot = index of the 64-bit field in DevStats
@@ -444,6 +447,9 @@ __device__ __forceinline__ bool t1_eval(uint32_t w0, uint32_t w1, uint32_t w2, u
     return true;
 }
 
+template <int OP> struct OutCount { typedef uint32_t type; };
+template <> struct OutCount<OP_AC> { typedef unsigned long long type; };
+
 // Tally four verified (or zeroed) y words: y = [a, 0, b, 0], a and b the allele bits of one sample.
 template <int OP>
 __device__ __forceinline__ void t1_tally(uint32_t y0, uint32_t y1, uint32_t y2, uint32_t y3, uint32_t &accp, uint32_t &hetp, uint32_t &hap) {
@@ -482,6 +488,19 @@ vcfx_scan_kernel(const KParams P) {
     if (lane < CNT_SLOTS) s_cnt[wid][lane] = 0;
     __syncwarp();
 #define VCFX_COUNT(slot, v) do { if (lane == 0) atomicAdd(&s_cnt[wid][slot], (unsigned int)(v)); } while (0)
+    // Row-record slots are reserved REC_BLOCK at a time: one atomic on the single global counter per 32 rows
+    // (one per row is the kernel's bottleneck: same-address atomics serialise in L2).  The block's state lives in
+    // shared memory, only lane 0 touches it; the slots a warp leaves unused are marked invalid when it exits.
+    __shared__ unsigned long long s_rec_base[WARPS_PER_CTA];
+    __shared__ unsigned int s_rec_used[WARPS_PER_CTA];
+    if (lane == 0) { s_rec_base[wid] = 0; s_rec_used[wid] = REC_BLOCK; }
+    __syncwarp();
+    auto alloc_slot_lane0 = [&]() -> unsigned long long {       // call from lane 0 only
+        unsigned int used = s_rec_used[wid];
+        if (used == REC_BLOCK) { s_rec_base[wid] = atomicAdd(&P.stats->n_recs, (unsigned long long)REC_BLOCK); used = 0; }
+        s_rec_used[wid] = used + 1;
+        return s_rec_base[wid] + used;
+    };
 
     for (;;) {
         uint32_t tile = 0;
@@ -492,7 +511,7 @@ vcfx_scan_kernel(const KParams P) {
         const uint64_t a = (uint64_t)tile * P.tile_bytes;
         const uint64_t b = min(a + (uint64_t)P.tile_bytes, n);
         // every position inside the tile's work is a 32-bit offset from a0 (16-aligned, <= a-1)
-        const uint64_t a0 = (a >= 16) ? ((a - 16) & ~(uint64_t)15) : 0;
+        const uint64_t a0 = a - (tile ? 16u : 0u);             // tile_bytes is a multiple of 512, so a is 16-aligned
         const uint8_t *__restrict__ tin = P.in + a0;
         const uint32_t ra = (uint32_t)(a - a0), rb = (uint32_t)(b - a0);
         const uint32_t nrel = (uint32_t)min(n - a0, (uint64_t)0xFFFFFFFFu);   // chunk end as an offset from a0 (clamped)
@@ -521,7 +540,8 @@ vcfx_scan_kernel(const KParams P) {
         }
 
         uint32_t nlines = 0;
-        unsigned long long out_bytes = 0;
+        // output bytes of the tile: only allele_counter's per-sample rows can exceed 32 bits (input offsets cannot)
+        typename OutCount<OP>::type out_bytes = 0;
         uint32_t md_prev_end = ls, md_last_end = ls;   // MISSING_DETECT: end of the last rewritten line / of the last line
         bool md_add_nl = false;
 
@@ -540,7 +560,6 @@ vcfx_scan_kernel(const KParams P) {
             uint32_t ta = 0, tb = 0, tc = 0;   // per-lane tallies (AF: alt,total; HWE: homRef,het,homAlt)
             int gt_index = -1;
             bool do_samples = false;
-            uint32_t wcount = 0;
 
             // ================= header phase: rank tabs until NEED_TABS are known or the line ends
             uint32_t t0, t1, t2, t3;           // tab masks of the current window (this lane)
@@ -566,31 +585,29 @@ vcfx_scan_kernel(const KParams P) {
                 }
                 int total = 0;
                 if (!hash) {
-                    int cnt = __popc(t0) + __popc(t1) + __popc(t2) + __popc(t3);
-                    if (OP == OP_VC) total = (int)__reduce_add_sync(FULL, (unsigned)cnt);
-                    else {
+                    if (OP == OP_VC) {
+                        const int cnt = __popc(t0) + __popc(t1) + __popc(t2) + __popc(t3);
+                        total = (int)__reduce_add_sync(FULL, (unsigned)cnt);
+                    } else {
+                        // one bit per byte of the lane: the 0x80 markers of a word gathered into its top nibble
+                        // by a multiply (bits 7/15/23/31 times 2^21/2^14/2^7/2^0 land on 28..31, nothing collides)
+                        uint32_t m16 = ((t0 * 0x00204081u) >> 28) | (((t1 * 0x00204081u) >> 24) & 0xF0u) |
+                                       (((t2 * 0x00204081u) >> 20) & 0xF00u) | (((t3 * 0x00204081u) >> 16) & 0xF000u);
+                        const int cnt = __popc(m16);
                         int incl = warp_incl_scan(cnt, lane);
                         total = __shfl_sync(FULL, incl, 31);
                         rank0 = tabs + incl - cnt;
                         // publish the positions of tabs 0..8
                         int rank = rank0;
-                        if (cnt && rank < 9) {
-                            uint32_t ms[4] = {t0, t1, t2, t3};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                uint32_t m = ms[j];
-                                while (m && rank < 9) {
-                                    tp[rank++] = pb + 4 * j + ((__ffs(m) - 1) >> 3);
-                                    m &= m - 1;
-                                }
-                            }
+                        while (m16 && rank < 9) {
+                            tp[rank++] = pb + (uint32_t)(__ffs(m16) - 1);
+                            m16 &= m16 - 1;
                         }
                     }
                 }
                 tabs += total;
                 if (found || tabs >= NEED_TABS) break;
                 wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
-                ++wcount;
             }
             __syncwarp();
 
@@ -685,7 +702,7 @@ vcfx_scan_kernel(const KParams P) {
                             if (__any_sync(FULL, odd)) break;    // nothing was added for this window
                             ta += da; tb += db; tc += dc;
                             wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
-                            if ((++wcount & 7) == 0) {
+                            if (((wb >> 9) & 7u) == 0) {          // every 8th window: L2 prefetch of the 4 KB that follow
                                 const uint32_t pf = wb + 12 * WINDOW + 128 * lane;
                                 if (pf < nrel) prefetch_l2(tin + pf);
                             }
@@ -1022,18 +1039,18 @@ vcfx_scan_kernel(const KParams P) {
                     if (found) break;
                     firstw = false;
                     wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
-                    if ((++wcount & 7) == 0) {
-                        const uint64_t pf = a0 + wb + 8 * WINDOW + 128 * lane;
-                        if (pf < n) prefetch_l2(P.in + pf);
+                    if (((wb >> 9) & 7u) == 0) {          // every 8th window: L2 prefetch of the 4 KB that follow
+                        const uint32_t pf = wb + 8 * WINDOW + 128 * lane;
+                        if (pf < nrel) prefetch_l2(tin + pf);
                     }
                 }
             }
             // ================= no (more) per-sample work: just find the '\n'
             while (!found) {
                 wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
-                if ((++wcount & 7) == 0) {
-                    uint64_t pf = a0 + wb + 8 * WINDOW + 128 * lane;
-                    if (pf < n) prefetch_l2(P.in + pf);
+                if (((wb >> 9) & 7u) == 0) {          // every 8th window: L2 prefetch of the 4 KB that follow
+                    const uint32_t pf = wb + 8 * WINDOW + 128 * lane;
+                    if (pf < nrel) prefetch_l2(tin + pf);
                 }
                 uint32_t n0 = eq_bytes(cur.x, C_NL), n1 = eq_bytes(cur.y, C_NL);
                 uint32_t n2 = eq_bytes(cur.z, C_NL), n3 = eq_bytes(cur.w, C_NL);
@@ -1102,7 +1119,7 @@ vcfx_scan_kernel(const KParams P) {
                     const uint32_t prefix_len = tp[4] + 1 - ls;
                     const uint32_t row_len = prefix_len + ((OP == OP_AF) ? 7u : 9u);
                     unsigned long long slot = 0;
-                    if (lane == 0) slot = atomicAdd(&P.stats->n_recs, 1ULL);
+                    if (lane == 0) slot = alloc_slot_lane0();
                     slot = __shfl_sync(FULL, slot, 0);
                     if (slot < P.rec_cap) {
                         if (lane == 0) {
@@ -1145,7 +1162,7 @@ vcfx_scan_kernel(const KParams P) {
                         sr = __reduce_add_sync(FULL, sr); sa = __reduce_add_sync(FULL, sa);
                         const uint32_t row_len = prefix_len + dec_len((int)sr) + 1 + dec_len((int)sa) + 1 + dec_len((int)n_rows) + 1;
                         if (lane == 0) {
-                            unsigned long long slot = atomicAdd(&P.stats->n_recs, 1ULL);
+                            unsigned long long slot = alloc_slot_lane0();
                             if (slot < P.rec_cap) {
                                 Rec r; r.tile = tile; r.ls_rel = (uint32_t)(a0 + ls - a); r.prefix_len = prefix_src;
                                 r.off_in_tile = (uint32_t)out_bytes; r.a = sr; r.b = sa; r.c = n_rows; r.d = extra_tabs;
@@ -1211,7 +1228,7 @@ vcfx_scan_kernel(const KParams P) {
                     else mod_len = content_len + 19 + ((ldb(tin + tp[7] - 1) != ';') ? 1u : 0u);
                     mod_len += 1;                                        // the rewritten line always ends with '\n'
                     if (lane == 0) {
-                        unsigned long long slot = atomicAdd(&P.stats->n_recs, 1ULL);
+                        unsigned long long slot = alloc_slot_lane0();
                         if (slot < P.rec_cap) {
                             Rec r; r.tile = tile; r.ls_rel = (uint32_t)(a0 + ls - a); r.prefix_len = (uint32_t)(a0 + md_prev_end - a);
                             r.off_in_tile = (uint32_t)out_bytes; r.a = info_off; r.b = info_len; r.c = content_len; r.d = mod_len;
@@ -1247,6 +1264,12 @@ vcfx_scan_kernel(const KParams P) {
         __syncwarp();
     }
 #undef VCFX_COUNT
+    __syncwarp();
+    {
+        const unsigned int used = s_rec_used[wid];
+        const unsigned long long slot = s_rec_base[wid] + lane;
+        if ((unsigned int)lane >= used && (unsigned int)lane < REC_BLOCK && slot < P.rec_cap) P.recs[slot].tile = REC_INVALID;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1353,6 +1376,7 @@ format_rows_kernel(const KParams P) {
         for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nrec;
              i += (unsigned long long)gridDim.x * blockDim.x) {
             const Rec r = P.recs[i];
+            if (r.tile == REC_INVALID) continue;
             uint8_t *o = P.out + P.tile_base[r.tile] + r.off_in_tile;
             const uint8_t *src = P.in + (uint64_t)r.tile * P.tile_bytes + r.ls_rel;
             for (uint32_t k = 0; k < r.prefix_len; ++k) o[k] = __ldg(src + k);
@@ -1371,8 +1395,9 @@ format_rows_kernel(const KParams P) {
         uint8_t *dst = nullptr; const uint8_t *src = nullptr;
         uint32_t plen = 0, tlen = 0;                             // prefix bytes, bytes of the row staged in shared memory
         bool gather = false;
-        if (i < nrec) {
-            const Rec r = P.recs[i];
+        Rec r; r.tile = REC_INVALID;
+        if (i < nrec) r = P.recs[i];
+        if (r.tile != REC_INVALID) {
             dst = P.out + P.tile_base[r.tile] + r.off_in_tile;
             plen = r.prefix_len;
             uint8_t *slot = rows_sm[wi][lane];
@@ -1480,6 +1505,7 @@ md_copy_kernel(const KParams P) {
     for (unsigned long long it = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < items; it += nwarps) {
         if (it < nrec) {
             const Rec r = P.recs[it];
+            if (r.tile == REC_INVALID) continue;
             const uint8_t *base = P.in + (uint64_t)r.tile * P.tile_bytes;
             uint8_t *o = P.out + P.tile_base[r.tile] + r.off_in_tile;
             const uint32_t gap = r.ls_rel - r.prefix_len;                // verbatim bytes before the line
