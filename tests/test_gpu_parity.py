@@ -211,3 +211,36 @@ def test_line_lengths_sweep(cuda_api, oracle):
             run_all(cuda_api, oracle, data, f"sweep shape{shape} S{S}", tools=("af", "hwe"))
     data = synth.make_vcf(3, 3000, 120, seed=13)
     run_all(cuda_api, oracle, data, "sweep regression S120", chunk_bytes=256 << 10)
+
+
+def _mutate_genotypes(data, seed, per_line, forms, crlf_every=0):
+    """Replace `per_line` random sample fields of every data line with one of `forms`."""
+    import random
+    rng = random.Random(seed)
+    out = []
+    for k, line in enumerate(data.split(b"\n")):
+        if line and not line.startswith(b"#"):
+            f = line.split(b"\t")
+            if len(f) > 9:
+                for _ in range(per_line):
+                    f[rng.randrange(9, len(f))] = rng.choice(forms)
+                line = b"\t".join(f)
+                if crlf_every and k % crlf_every == 0:
+                    line += b"\r"
+        out.append(line)
+    return b"\n".join(out)
+
+
+def test_tier1_rounds_long_lines_and_sparse_exceptions(cuda_api, oracle):
+    """The steady tier-1 rounds: lines long enough to hit the periodic flush of the packed sums
+    (64 iterations of 2 KiB), and otherwise regular lines with a few genotypes that are not
+    `a<sep>b` — each one stops the rounds, goes through the exact path and the rounds resume."""
+    for shape in (1, 2):                                   # unphased / phased GT-only
+        data = synth.make_vcf(shape, 6, 40000, seed=77 + shape)
+        run_all(cuda_api, oracle, data, f"long lines shape{shape}", tools=("af", "hwe"))
+    forms = [b".", b"./.", b".|.", b"0", b"1", b"2|1", b"0/1", b"1|0", b"10|1", b"0|1:5", b"", b"./1", b"0|.", b"1/1/1"]
+    base = synth.make_vcf(2, 120, 2504, seed=5)
+    for per_line, seed in ((1, 1), (3, 2), (12, 3)):
+        data = _mutate_genotypes(base, seed, per_line, forms, crlf_every=7 if seed == 2 else 0)
+        run_all(cuda_api, oracle, data, f"sparse exceptions x{per_line}", tools=("af", "hwe", "md", "vc"))
+        run_all(cuda_api, oracle, data, f"sparse exceptions x{per_line} small tiles", tile_bytes=4096, tools=("af", "hwe"))

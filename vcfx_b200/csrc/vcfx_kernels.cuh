@@ -716,7 +716,7 @@ vcfx_scan_kernel(const KParams P) {
                     // rotated word f is pat + y (y = the two allele bits), so the wrapping sum of the f's is
                     // N * pat + sum(y) and, for HWE, the wrapping sum of f * f yields sum(a & b) (see the flush).
                     if (t1_on && prev_ok) {
-                        const uint32_t ITMAX = (OP == OP_AF) ? 4000u : 2000u;    // iterations per flush: the packed sums stay exact
+                        const uint32_t ITMAX = 64u;    // iterations (of 2 KiB) per flush: the packed sums stay exact up to 2000 (HWE) / 4000 (AF)
                         uint32_t la_c = 0, la_n = 0;                             // look-ahead words of cur / nxt once the rounds are over
                         for (;;) {
                             const uint8_t *lp = tin + wb + 16 * lane;
