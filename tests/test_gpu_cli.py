@@ -114,3 +114,31 @@ def test_allele_counter(tmp_path):
     # header-less inputs
     both("allele_counter", ["-q"], stdin=b"##only\n")
     both("allele_counter", ["-q"], stdin=b"1\t1\t.\tA\tG\t.\t.\t.\tGT\t0/1\n")
+
+
+def test_large_file_parallel_io(tmp_path):
+    """Files past the 8 MiB mark take the multi-threaded pread / pwrite paths of the host reader:
+    output to a regular file must be byte-identical to the reference's, with one and with eight I/O
+    threads (VCFX_IO_THREADS), and identical to the pipe path."""
+    if not (REF / "VCFX_missing_detector").exists():
+        pytest.skip("oracle/_ref reference tools not built")
+    src = tmp_path / "big.vcf"
+    src.write_bytes(synth.make_vcf(3, 9000, 600, seed=21))          # ~ 22 MB, dots on most lines
+    assert src.stat().st_size > (20 << 20)
+
+    def to_file(exe, args, out, env=None):
+        e = dict(os.environ); e.update(env or {})
+        with open(out, "wb") as f:
+            r = subprocess.run([str(exe), *args], stdout=f, stderr=subprocess.PIPE, timeout=300, env=e)
+        return r.returncode
+
+    for tool, args in (("missing_detector", ["-q", "-t", "1", "-i", str(src)]), ("allele_freq_calc", ["-q", "-i", str(src)])):
+        ref_out = tmp_path / f"{tool}.ref"
+        assert to_file(REF / f"VCFX_{tool}", args, ref_out) == 0
+        want = ref_out.read_bytes()
+        for threads in ("1", "8"):
+            out = tmp_path / f"{tool}.{threads}"
+            assert to_file(BIN / f"VCFX_{tool}", args, out, {"VCFX_IO_THREADS": threads}) == 0
+            assert out.read_bytes() == want, (tool, threads)
+        rc, piped, _ = run(BIN / f"VCFX_{tool}", args)
+        assert rc == 0 and piped == want

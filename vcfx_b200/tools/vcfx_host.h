@@ -30,7 +30,10 @@ class Source {
 
   private:
     long raw_read(char *dst, size_t cap);
+    long parallel_read(char *dst, size_t cap);   // -2: not applicable (pipe, small read, one thread)
     int fd_;
+    long long file_size_ = -1, file_off_ = 0;    // regular files only (-1: not looked at yet)
+    int io_threads_ = 1;
     std::string peek_;                    // bytes read ahead by sniff/peek
     size_t peek_pos_ = 0;
     bool gz_ = false, gz_done_ = false, failed_ = false;
