@@ -244,3 +244,23 @@ def test_tier1_rounds_long_lines_and_sparse_exceptions(cuda_api, oracle):
         data = _mutate_genotypes(base, seed, per_line, forms, crlf_every=7 if seed == 2 else 0)
         run_all(cuda_api, oracle, data, f"sparse exceptions x{per_line}", tools=("af", "hwe", "md", "vc"))
         run_all(cuda_api, oracle, data, f"sparse exceptions x{per_line} small tiles", tile_bytes=4096, tools=("af", "hwe"))
+
+
+def test_allele_counter_two_digit_counts(cuda_api, oracle):
+    """allele_counter TEXT rows are sized without looking at the genotypes (one digit per count); a
+    sample with ten or more alleles of a kind, or 128+ (int8 wrap to a negative number), breaks that
+    guess: the write pass notices and the chunk is run again with exact sizes."""
+    hdr = b"##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tA\tB\tC\n"
+    deca = b"/".join([b"0"] * 10)
+    wrap = b"|".join([b"1"] * 130)
+    body = b"".join(b"1\t%d\trs%d\tA\tG\t.\tPASS\t.\tGT\t0|1\t%s\t1/1\n" % (100 + i, i, deca if i % 7 == 3 else (wrap if i % 11 == 5 else b"0/0"))
+                    for i in range(60))
+    data = hdr + body
+    for kw in ({}, {"chunk_bytes": 4096}, {"tile_bytes": 512}):
+        o = oracle.allele_counter(data)
+        r = cuda_api.allele_counter(data, **kw)
+        assert r.rc == o.rc
+        _cmp(f"ac two-digit counts {kw}", r.out, o.out)
+    # and the plain case right after it through a fresh context
+    data2 = synth.make_vcf(2, 40, 64, seed=9)
+    _cmp("ac after exact", cuda_api.allele_counter(data2).out, oracle.allele_counter(data2).out)

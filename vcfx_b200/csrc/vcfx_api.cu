@@ -84,6 +84,7 @@ struct vcfx_ctx {
     uint32_t *d_sel_col = nullptr, *d_name_off = nullptr;
     uint8_t *d_names = nullptr;
     int ac_fmt = 0;
+    bool ac_exact = false;               // a chunk had a count of two digits: rows are sized by parsing from now on
     // last drained chunk's short-line list
     std::vector<uint64_t> last_events;
     uint64_t last_n_events = 0;
@@ -230,7 +231,7 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
     P.out = d_out; P.out_cap = out_cap;
     P.tile_lines = w.tile_lines; P.tile_out = w.tile_out; P.tile_base = w.tile_base; P.line_base = w.line_base;
     P.tail_start = w.tail_start; P.tail_len = w.tail_len; P.tail_off = w.tail_off;
-    P.ac_fmt = ctx->ac_fmt; P.ac_pass = 0; P.n_sel = ctx->n_sel; P.sel_col = ctx->d_sel_col; P.name_off = ctx->d_name_off;
+    P.ac_fmt = ctx->ac_fmt; P.ac_pass = 0; P.ac_spec = (ctx->cfg.op == VCFX_OP_ALLELE_COUNT && ctx->ac_fmt == AC_TEXT_MT && !ctx->ac_exact) ? 1 : 0; P.n_sel = ctx->n_sel; P.sel_col = ctx->d_sel_col; P.name_off = ctx->d_name_off;
     P.names = ctx->d_names; P.max_col = ctx->max_col; P.col_scratch = w.col_scratch;
     P.ticket = w.ticket; P.recs = w.recs; P.rec_prefix = w.rec_prefix; P.rec_cap = w.rec_cap;
     P.stats = w.d_stats; P.events = w.events; P.ev_cap = EVENT_CAP;
@@ -506,6 +507,7 @@ int vcfx_cuda_next_output(vcfx_ctx *ctx, const char **text, size_t *n, vcfx_chun
     // exact sizes (the input is still on the device).
     for (int attempt = 0; s.w.h_stats->overflow && attempt < 3; ++attempt) {
         const unsigned long long ov = s.w.h_stats->overflow;
+        if (ov & 4) ctx->ac_exact = true;
         if (ov & 1) {
             int rc = ensure_work(ctx, s.w, ctx->chunk_bytes, s.w.h_stats->n_recs + 1024);
             if (rc != VCFX_OK) return rc;
@@ -564,7 +566,8 @@ int vcfx_cuda_sync(vcfx_ctx *ctx, vcfx_chunk_stats *stats) {
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->dev_stream));
     ctx->dev_pending = false;
-    if (ctx->dev_work.h_stats->overflow & 1) {      // more rows than sized for: run again with the exact count
+    if (ctx->dev_work.h_stats->overflow & 5) {      // more rows than sized for / speculative row sizes off: run again, exact
+        if (ctx->dev_work.h_stats->overflow & 4) ctx->ac_exact = true;
         int rc2 = ensure_work(ctx, ctx->dev_work, ctx->dev_nbytes, ctx->dev_work.h_stats->n_recs + 1024);
         if (rc2 != VCFX_OK) return rc2;
         rc2 = launch_chunk(ctx, ctx->dev_work, ctx->dev_stream, ctx->dev_in, ctx->dev_nbytes, &ctx->dev_info,

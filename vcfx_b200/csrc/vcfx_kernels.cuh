@@ -55,7 +55,7 @@ struct DevStats {
     unsigned long long dots_terminated;
     unsigned long long last_unterminated_flagged;
     unsigned long long bytes_out;
-    unsigned long long overflow;          // bit 0: row records, bit 1: output bytes
+    unsigned long long overflow;          // bit 0: row records, bit 1: output bytes, bit 2: speculative row sizes were wrong
     unsigned long long first_short_line;  // filled by tile_scan_kernel
     unsigned long long n_recs;            // row-record slots reserved (may exceed rec_cap: then overflow)
 };
@@ -87,6 +87,7 @@ struct KParams {
     // ALLELE_COUNT
     int32_t ac_fmt;                  // AC_TEXT_MT / AC_TEXT_FWD / AC_AGG / AC_BIN
     int32_t ac_pass;                 // 0 = size the rows, 1 = write them
+    int32_t ac_spec;                 // TEXT_MT: size the rows without parsing genotypes (every count one digit); pass 1 verifies
     uint32_t n_sel;                  // selected samples, in output order
     const uint32_t *sel_col;         // [n_sel] sample column (running maximum in the forward modes)
     const uint32_t *name_off;        // [n_sel + 1] offsets into names
@@ -398,31 +399,30 @@ __device__ __forceinline__ uint2 ac_sample_reg(uint32_t q, const uint8_t *p) {
     return ac_sample_slow(p);
 }
 __device__ __forceinline__ uint32_t dec_len(int v) {       // characters of the decimal form, sign included
+    if ((uint32_t)v < 10u) return 1u;                      // allele counts of one sample: almost always
     uint32_t n = (v < 0) ? 1u : 0u;
     uint32_t u = (v < 0) ? (uint32_t)(-v) : (uint32_t)v;
     do { ++n; u /= 10u; } while (u);
     return n;
 }
 __device__ __forceinline__ uint8_t *put_dec(uint8_t *d, int v) {
+    if ((uint32_t)v < 10u) { *d = (uint8_t)('0' + v); return d + 1; }
     if (v < 0) { *d++ = '-'; v = -v; }
     char t[12]; int n = 0; uint32_t u = (uint32_t)v;
     do { t[n++] = (char)('0' + u % 10u); u /= 10u; } while (u);
     while (n) *d++ = (uint8_t)t[--n];
     return d;
 }
-// flush n staged bytes (shared memory) to dst: 32-bit stores on the aligned middle of dst
+// flush n staged bytes (shared memory) to dst.  The bytes were staged at the same offset modulo 16 as
+// dst (st - (dst & 15) is 16-byte aligned), so the middle goes out as aligned 128-bit loads / stores.
 __device__ __forceinline__ void warp_flush_smem(uint8_t *dst, const uint8_t *st, uint32_t n, int lane) {
-    const uint32_t head = min(n, (uint32_t)((4 - ((uintptr_t)dst & 3)) & 3));
+    const uint32_t head = min(n, (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15));
     if (lane < (int)head) dst[lane] = st[lane];
-    const uint32_t nw = (n - head) >> 2;
-    uint32_t *d4 = reinterpret_cast<uint32_t *>(dst + head);
-    const uint32_t *s4 = reinterpret_cast<const uint32_t *>(st);     // st is 4-byte aligned
-    const uint32_t sh = 8u * (head & 3u);
-    for (uint32_t i = lane; i < nw; i += 32) {
-        const uint32_t w0 = s4[(head >> 2) + i], w1 = sh ? s4[(head >> 2) + i + 1] : 0u;
-        d4[i] = sh ? __funnelshift_r(w0, w1, sh) : w0;
-    }
-    const uint32_t done = head + (nw << 2);
+    const uint32_t nq = (n - head) >> 4;
+    uint4 *d16 = reinterpret_cast<uint4 *>(dst + head);
+    const uint4 *s16 = reinterpret_cast<const uint4 *>(st + head);
+    for (uint32_t i = lane; i < nq; i += 32) d16[i] = s16[i];
+    const uint32_t done = head + (nq << 4);
     if (lane < (int)(n - done)) dst[done + lane] = st[done + lane];
 }
 
@@ -473,7 +473,7 @@ template <int OP>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (OP == OP_VC) ? 5 : VCFX_PARSE_CTAS)
 vcfx_scan_kernel(const KParams P) {
     __shared__ uint32_t s_tp[WARPS_PER_CTA][12];
-    __shared__ __align__(16) uint8_t s_stage[(OP == OP_AC) ? WARPS_PER_CTA * (AC_STAGE + 16) : 16];
+    __shared__ __align__(16) uint8_t s_stage[(OP == OP_AC) ? WARPS_PER_CTA * (AC_STAGE + 32) : 16];
     const int lane = threadIdx.x & 31;
     const int wid = threadIdx.x >> 5;
     volatile uint32_t *tp = s_tp[wid];
@@ -951,7 +951,8 @@ vcfx_scan_kernel(const KParams P) {
                 else { ta -= hetp + hap; if (lane == 0) ta += n_real; tb += hetp; tc += hap; }
             }
             // ================= ALLELE_COUNT: (ref, alt) of every sample column into the warp's scratch
-            if (OP == OP_AC && !hash && tabs >= 9) {
+            const bool ac_sizing_only = (OP == OP_AC) && P.ac_spec && P.ac_pass == 0;   // no genotype is looked at
+            if (OP == OP_AC && !hash && tabs >= 9 && !ac_sizing_only) {
                 uint2 *scr = P.col_scratch + (size_t)(blockIdx.x * WARPS_PER_CTA + wid) * P.max_col;
                 bool firstw = true;
                 for (;;) {
@@ -1173,9 +1174,15 @@ vcfx_scan_kernel(const KParams P) {
                         }
                         out_bytes += row_len; VCFX_COUNT(C_ROWS, 1);
                     } else {
-                        uint8_t *stage = s_stage + wid * (AC_STAGE + 16);
+                        uint8_t *stage0 = s_stage + wid * (AC_STAGE + 32);
+                        uint32_t n_rows_done = 0;
                         unsigned long long opos = (P.ac_pass ? P.tile_base[tile] : 0ULL) + out_bytes;
                         const bool text = (P.ac_fmt != AC_BIN);
+                        if (ac_sizing_only) {
+                            // every row is prefix + name + '\t' + one digit + '\t' + one digit + '\n'
+                            out_bytes += (unsigned long long)n_rows * (prefix_len + 4u) + (P.name_off[n_rows] - P.name_off[0]);
+                            n_rows_done = n_rows; n_rows = 0;
+                        }
                         for (uint32_t i0 = 0; i0 < n_rows; i0 += 32) {
                             const uint32_t i = i0 + lane;
                             int vr = 0, va = 0; uint32_t len = 0, noff = 0, nlen = 0;
@@ -1193,6 +1200,8 @@ vcfx_scan_kernel(const KParams P) {
                             const uint32_t btot = (uint32_t)__shfl_sync(FULL, incl, 31);
                             if (P.ac_pass) {
                                 const bool staged = btot <= AC_STAGE;
+                                // staged at the destination's offset modulo 16: the flush is aligned 128-bit copies
+                                uint8_t *stage = stage0 + (uint32_t)((uintptr_t)(P.out + opos) & 15);
                                 uint8_t *d = staged ? stage + off : P.out + opos + off;
                                 if (i < n_rows) {
                                     if (text) {
@@ -1210,7 +1219,7 @@ vcfx_scan_kernel(const KParams P) {
                             }
                             opos += btot; out_bytes += btot;
                         }
-                        if (P.ac_pass == 0) VCFX_COUNT(C_ROWS, n_rows);
+                        if (P.ac_pass == 0) VCFX_COUNT(C_ROWS, ac_sizing_only ? n_rows_done : n_rows);
                     }
                 }
             }
@@ -1258,6 +1267,8 @@ vcfx_scan_kernel(const KParams P) {
             out_bytes += tail + (md_add_nl ? 1u : 0u);
         }
         if (lane == 0 && !(OP == OP_AC && P.ac_pass)) { P.tile_lines[tile] = nlines; P.tile_out[tile] = out_bytes; }
+        // the write pass of a speculatively sized launch checks the sizes it was given
+        if (OP == OP_AC && P.ac_pass && P.ac_spec && lane == 0 && (unsigned long long)out_bytes != P.tile_out[tile]) atomicOr(&P.stats->overflow, 4ULL);
         __syncwarp();
         if (lane < CNT_SLOTS) {
             const unsigned int v = s_cnt[wid][lane];
