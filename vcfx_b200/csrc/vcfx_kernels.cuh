@@ -288,26 +288,80 @@ __device__ __forceinline__ int hwe_sample_reg(uint32_t q, const uint8_t *p) {
     return hwe_sample_slow(p);
 }
 
+// Byte classes of one word as 0x80 markers (exact, like classify_quad's)
+struct WClass { uint32_t D, Z, P, S, E, O; };   // digit, '0', '.', '/' or '|', tab / ':' / '\n', '1' (HWE only)
+template <int OP>
+__device__ __forceinline__ WClass classify_word(uint32_t x) {
+    // ge(c): 0x80 in every byte whose low seven bits are >= c (a 7-bit add cannot carry into the next
+    // byte); a class is a difference of two of them, for bytes without the eighth bit
+    const uint32_t x7 = x & 0x7F7F7F7Fu, ok = ~x & 0x80808080u;
+#define VCFX_GE(c) (x7 + (0x80808080u - 0x01010101u * (uint32_t)(c)))
+    const uint32_t g2e = VCFX_GE(0x2E), g2f = VCFX_GE(0x2F), g30 = VCFX_GE(0x30), g31 = VCFX_GE(0x31);
+    const uint32_t g3a = VCFX_GE(0x3A), g3b = VCFX_GE(0x3B), g7c = VCFX_GE(0x7C), g7d = VCFX_GE(0x7D);
+    const uint32_t g09 = VCFX_GE(0x09), g0b = VCFX_GE(0x0B);
+    WClass c;
+    c.P = g2e & ~g2f & ok;                                  // '.'
+    c.Z = g30 & ~g31 & ok;                                  // '0'
+    c.D = g30 & ~g3a & ok;                                  // '0'..'9'
+    c.S = ((g2f & ~g30) | (g7c & ~g7d)) & ok;               // '/' '|'
+    c.E = ((g09 & ~g0b) | (g3a & ~g3b)) & ok;               // '\t' '\n' ':'
+    c.O = (OP == OP_HWE) ? (g31 & ~VCFX_GE(0x32) & ok) : 0u;   // '1'
+#undef VCFX_GE
+    return c;
+}
+// markers of the pair (lo, hi) moved down by k bytes: marker at byte i of the result = marker at byte i + k
+__device__ __forceinline__ uint32_t down(uint32_t lo, uint32_t hi, int k) { return __funnelshift_rc(lo, hi, 8u * (uint32_t)k); }
+
 // generic: one sample per owned tab (tab masks m0..m3 over the lane's words w0..w3, la = next 4 B).
-// Kept out of line: it is the rare path and must not cost the lattice path registers.
+// All the tabs of a word are judged at once: the classes of the bytes behind a tab are the class
+// markers moved down by 1..4 bytes, so the quick shapes of classify_quad (same conditions, same
+// tallies) become a few AND/POPC per word; only tabs whose sample is none of them go to the scalar
+// parsers, one by one.  Kept out of line: it must not cost the lattice path registers.
 template <int OP>
 __device__ __noinline__ uint3 lane_samples_generic(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t la,
                                                    uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3,
                                                    const uint8_t *lane_ptr, bool strip_cr, int gt_index) {
-    uint32_t ws[5] = {w0, w1, w2, w3, la};
-    uint32_t ms[4] = {m0, m1, m2, m3};
+    const uint32_t ws[5] = {w0, w1, w2, w3, la};
+    const uint32_t ms[4] = {m0, m1, m2, m3};
     uint32_t ta = 0, tb = 0, tc = 0;
+    WClass lo = classify_word<OP>(ws[0]);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        uint32_t m = ms[j];
-        while (m) {
-            int k = (__ffs(m) - 1) >> 3;
-            m &= m - 1;
-            uint32_t q = __funnelshift_rc(ws[j], ws[j + 1], 8u * (uint32_t)(k + 1));
-            const uint8_t *p = lane_ptr + 4 * j + k + 1;
-            if (OP == OP_AF) af_sample_reg(q, p, strip_cr, gt_index, ta, tb);
-            else { int c = hwe_sample_reg(q, p); ta += (c == 0); tb += (c == 1); tc += (c == 2); }
+        const WClass hi = classify_word<OP>(ws[j + 1]);
+        const uint32_t m = ms[j];
+        uint32_t rest = m;
+        if (m) {
+            const uint32_t d1 = down(lo.D, hi.D, 1), d3 = down(lo.D, hi.D, 3), s2 = down(lo.S, hi.S, 2);
+            if (OP == OP_AF) {
+                if (gt_index == 0) {
+                    const uint32_t tokl = lo.D | lo.P, tokh = hi.D | hi.P;
+                    const uint32_t t1 = down(tokl, tokh, 1), t3 = down(tokl, tokh, 3);
+                    const uint32_t e1 = down(lo.E, hi.E, 1), e2 = down(lo.E, hi.E, 2), e4 = hi.E;
+                    const uint32_t z1 = down(lo.Z, hi.Z, 1), z3 = down(lo.Z, hi.Z, 3);
+                    const uint32_t A = m & e1, B = m & t1 & e2, C = m & t1 & s2 & t3 & e4, any = B | C;
+                    tb += __popc(any & d1) + __popc(C & d3);                          // total
+                    ta += __popc(any & d1 & ~z1) + __popc(C & d3 & ~z3);              // alt
+                    rest = m & ~(A | any);
+                }
+            } else {
+                const uint32_t d2 = down(lo.D, hi.D, 2), d4 = hi.D, p1 = down(lo.P, hi.P, 1);
+                const uint32_t o1 = down(lo.O, hi.O, 1), o3 = down(lo.O, hi.O, 3);
+                const uint32_t l1 = o1 | down(lo.Z, hi.Z, 1), l3 = o3 | down(lo.Z, hi.Z, 3);   // allele <= 1
+                const uint32_t full = m & d1 & s2 & d3 & ~d4;
+                const uint32_t rej = m & ((~d1 & p1) | (d1 & ~s2 & ~d2) | (d1 & s2 & ~d3));
+                const uint32_t ok = full & l1 & l3;
+                ta += __popc(ok & ~o1 & ~o3); tb += __popc(ok & (o1 ^ o3)); tc += __popc(ok & o1 & o3);
+                rest = m & ~(full | rej);
+            }
         }
+        while (rest) {
+            const int k = (__ffs(rest) - 1) >> 3;
+            rest &= rest - 1;
+            const uint8_t *p = lane_ptr + 4 * j + k + 1;
+            if (OP == OP_AF) { const uint2 r = af_sample_slow(p, strip_cr, gt_index); ta += r.x; tb += r.y; }
+            else { const int c = hwe_sample_slow(p); ta += (c == 0); tb += (c == 1); tc += (c == 2); }
+        }
+        lo = hi;
     }
     return make_uint3(ta, tb, tc);
 }
@@ -985,18 +1039,36 @@ vcfx_scan_kernel(const KParams P) {
                         const uint32_t ws[5] = {cur.x, cur.y, cur.z, cur.w, la};
                         const uint32_t ms[4] = {m0, m1, m2, m3};
                         int r = r0;
+                        // the quick shapes of all the tabs of a word at once (see lane_samples_generic); a tab
+                        // then only picks its bits
+                        WClass lo = classify_word<OP_AC>(ws[0]);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
+                            const WClass hi = classify_word<OP_AC>(ws[j + 1]);
                             uint32_t m = ms[j];
-                            while (m) {
-                                const int k = (__ffs(m) - 1) >> 3;
-                                m &= m - 1;
-                                if (r >= 8 && (uint32_t)(r - 8) < P.max_col) {
-                                    const uint32_t q = __funnelshift_rc(ws[j], ws[j + 1], 8u * (uint32_t)(k + 1));
-                                    scr[r - 8] = ac_sample_reg(q, tin + pb + 4 * j + k + 1);
+                            if (m) {
+                                const uint32_t tokl = lo.D | lo.P, tokh = hi.D | hi.P;
+                                const uint32_t t1 = down(tokl, tokh, 1), t3 = down(tokl, tokh, 3), s2 = down(lo.S, hi.S, 2);
+                                const uint32_t e1 = down(lo.E, hi.E, 1), e2 = down(lo.E, hi.E, 2), e4 = hi.E;
+                                const uint32_t d1 = down(lo.D, hi.D, 1), d3 = down(lo.D, hi.D, 3);
+                                const uint32_t z1 = down(lo.Z, hi.Z, 1), z3 = down(lo.Z, hi.Z, 3);
+                                const uint32_t C = m & t1 & s2 & t3 & e4, any = (m & t1 & e2) | C, quick = (m & e1) | any;
+                                const uint32_t R1 = any & z1, R3 = C & z3, A1 = any & d1 & ~z1, A3 = C & d3 & ~z3;
+                                while (m) {
+                                    const uint32_t bit = m & (0u - m);
+                                    const int k = (__ffs(m) - 1) >> 3;
+                                    m &= m - 1;
+                                    if (r >= 8 && (uint32_t)(r - 8) < P.max_col) {
+                                        uint2 v;
+                                        if (quick & bit) v = make_uint2(((R1 & bit) ? 1u : 0u) + ((R3 & bit) ? 1u : 0u),
+                                                                        ((A1 & bit) ? 1u : 0u) + ((A3 & bit) ? 1u : 0u));
+                                        else v = ac_sample_slow(tin + pb + 4 * j + k + 1);
+                                        scr[r - 8] = v;
+                                    }
+                                    ++r;
                                 }
-                                ++r;
                             }
+                            lo = hi;
                         }
                     }
                     if (found) break;
