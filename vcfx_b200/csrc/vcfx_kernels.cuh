@@ -318,12 +318,12 @@ __device__ __forceinline__ uint32_t down(uint32_t lo, uint32_t hi, int k) { retu
 // tallies) become a few AND/POPC per word; only tabs whose sample is none of them go to the scalar
 // parsers, one by one.  Kept out of line: it must not cost the lattice path registers.
 template <int OP>
-__device__ __noinline__ uint3 lane_samples_generic(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t la,
+__device__ __noinline__ uint4 lane_samples_generic(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t la,
                                                    uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3,
                                                    const uint8_t *lane_ptr, bool strip_cr, int gt_index) {
     const uint32_t ws[5] = {w0, w1, w2, w3, la};
     const uint32_t ms[4] = {m0, m1, m2, m3};
-    uint32_t ta = 0, tb = 0, tc = 0;
+    uint32_t ta = 0, tb = 0, tc = 0, irregular = 0;          // irregular: some sample is not "digit sep digit"
     WClass lo = classify_word<OP>(ws[0]);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -342,7 +342,8 @@ __device__ __noinline__ uint3 lane_samples_generic(uint32_t w0, uint32_t w1, uin
                     tb += __popc(any & d1) + __popc(C & d3);                          // total
                     ta += __popc(any & d1 & ~z1) + __popc(C & d3 & ~z3);              // alt
                     rest = m & ~(A | any);
-                }
+                    irregular |= m & ~(C & d1 & d3);
+                } else irregular = 1;
             } else {
                 const uint32_t d2 = down(lo.D, hi.D, 2), d4 = hi.D, p1 = down(lo.P, hi.P, 1);
                 const uint32_t o1 = down(lo.O, hi.O, 1), o3 = down(lo.O, hi.O, 3);
@@ -352,6 +353,7 @@ __device__ __noinline__ uint3 lane_samples_generic(uint32_t w0, uint32_t w1, uin
                 const uint32_t ok = full & l1 & l3;
                 ta += __popc(ok & ~o1 & ~o3); tb += __popc(ok & (o1 ^ o3)); tc += __popc(ok & o1 & o3);
                 rest = m & ~(full | rej);
+                irregular |= m & ~full;
             }
         }
         while (rest) {
@@ -363,7 +365,7 @@ __device__ __noinline__ uint3 lane_samples_generic(uint32_t w0, uint32_t w1, uin
         }
         lo = hi;
     }
-    return make_uint3(ta, tb, tc);
+    return make_uint4(ta, tb, tc, irregular);
 }
 
 // Lattice check of one lane, branch-free.  tau = byte of the first tab in word 0; the 16 bytes
@@ -547,6 +549,7 @@ vcfx_scan_kernel(const KParams P) {
     // shared memory, only lane 0 touches it; the slots a warp leaves unused are marked invalid when it exits.
     __shared__ unsigned long long s_rec_base[WARPS_PER_CTA];
     __shared__ unsigned int s_rec_used[WARPS_PER_CTA];
+    __shared__ volatile unsigned int s_odd[WARPS_PER_CTA], s_reg[WARPS_PER_CTA];
     if (lane == 0) { s_rec_base[wid] = 0; s_rec_used[wid] = REC_BLOCK; }
     __syncwarp();
     auto alloc_slot_lane0 = [&]() -> unsigned long long {       // call from lane 0 only
@@ -696,6 +699,7 @@ vcfx_scan_kernel(const KParams P) {
                 uint32_t accp = 0;                 // packed sums: bits 0..15 first alleles, 16..31 second alleles
                 uint32_t hetp = 0, hap = 0;        // HWE tier-1 tallies
                 uint32_t n_real = 0;               // samples tallied by tier 1 (uniform)
+                s_odd[wid] = 0; s_reg[wid] = 0;    // windows in a row that went through the exact path / were regular in it (shared: registers are short)
                 // ---- the window with tab 9, the cheap way.  A rotated word f_k of a lane covers the four bytes
                 // after byte 4k + tau of that lane, i.e. one sample behind its leading tab when the lattice holds.
                 // Tab 9 itself sits on the lattice (tau = its position mod 4), so in its lane the words from its own
@@ -924,7 +928,12 @@ vcfx_scan_kernel(const KParams P) {
                         uint32_t packed = 0;
                         // samples of a FORMAT with more keys carry ':' pieces: no lattice there, do not look for one
                         uint32_t sh_lane = 0;
-                        const bool lat = lat_possible && lane_lattice<OP>(cur.x, cur.y, cur.z, cur.w, la, packed, sh_lane);
+                        // A line that keeps leaving the lattice (missing / haploid calls every few samples: two
+                        // windows in a row came here) stops trying: every sample is parsed from its leading tab,
+                        // until eight windows in a row held nothing but "digit sep digit".
+                        const bool qm = lat_possible && !first_win && s_odd[wid] >= 2;
+                        uint32_t irr = 0;
+                        const bool lat = lat_possible && !qm && lane_lattice<OP>(cur.x, cur.y, cur.z, cur.w, la, packed, sh_lane);
                         // Tier 1 never looks at a lane's bytes up to its first lattice tab: they must have been
                         // verified by the lane before it AT THE SAME PHASE.  After a haploid or missing call the
                         // phase of the samples shifts, so the last lane only vouches for the next window when its
@@ -979,23 +988,29 @@ vcfx_scan_kernel(const KParams P) {
                                         const bool t3 = (b3 == '\t' || b3 == ':' || b3 == '\n');
                                         if (is_dig(b0) && is_sep(b1) && is_dig(b2) && t3) {
                                             tb += 2; ta += (uint32_t)(b0 != '0') + (uint32_t)(b2 != '0'); handled = true;
-                                        } else if (b0 == '.' && is_sep(b1) && b2 == '.' && t3) handled = true;
+                                        } else if (b0 == '.' && is_sep(b1) && b2 == '.' && t3) { handled = true; irr = 1; }
                                     } else {
                                         if (is_dig(b0) && is_sep(b1) && is_dig(b2) && !is_dig(b3)) {
                                             if (b0 <= '1' && b2 <= '1') { const uint32_t c = (b0 - '0') + (b2 - '0'); ta += (c == 0); tb += (c == 1); tc += (c == 2); }
                                             handled = true;
-                                        } else if (b0 == '.') handled = true;
+                                        } else if (b0 == '.') { handled = true; irr = 1; }
                                     }
                                 }
                                 if (!handled) {
-                                    const uint3 r = lane_samples_generic<OP>(cur.x, cur.y, cur.z, cur.w, la, m0, m1, m2, m3,
+                                    const uint4 r = lane_samples_generic<OP>(cur.x, cur.y, cur.z, cur.w, la, m0, m1, m2, m3,
                                                                              tin + pb, strip_cr, gt_index);
-                                    ta += r.x; tb += r.y; tc += r.z;
+                                    ta += r.x; tb += r.y; tc += r.z; irr = r.w;
                                 }
                             }
                         }
+                        if (qm) {
+                            const unsigned reg = __any_sync(FULL, irr != 0) ? 0u : s_reg[wid] + 1u;
+                            s_reg[wid] = reg;
+                            if (reg >= 8) { s_reg[wid] = 0; s_odd[wid] = 0; done = true; }   // (done only resets the run below)
+                        }
                     }
                     if (found) break;
+                    s_odd[wid] = done ? 0u : s_odd[wid] + 1u;
                     prev_ok = (gbal >> 31) != 0;
                     first_win = false;
                     wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
