@@ -55,6 +55,8 @@ def main():
         hnp[: len(hdr)] = np.frombuffer(hdr, dtype=np.uint8)
         t0 = time.perf_counter()
         nbytes = len(hdr) + synth.lines_into(hnp[len(hdr):], shape, S, 0, V, seed=shape)
+        first_nl = int(np.argmax(hnp[len(hdr):len(hdr) + (4 << 20)] == 10))
+        line_len = first_nl + 1                       # what a streaming caller's library measures by itself
         d_in = torch.empty(nbytes + api.DEVICE_PAD, dtype=torch.uint8, device=dev)
         d_in[:nbytes].copy_(host[:nbytes]); torch.cuda.synchronize()
         print(f"[{cname}] {nbytes / 1e9:.2f} GB, {V} variants, generated in {time.perf_counter() - t0:.1f}s", file=sys.stderr, flush=True)
@@ -69,6 +71,7 @@ def main():
             d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
             kw = dict(sel_cols=list(range(S)), sel_names=names) if op == api.OP_ALLELE_COUNT else {}
             ctx = api.Context(op, api.FILE, flags=flags, **kw)
+            ctx.set_line_hint(line_len)
             vf = api.find_chrom_header(hdr) if op == api.OP_ALLELE_FREQ else (api.first_data_offset(hdr) if op == api.OP_MISSING_DETECT else 0)
             ms = []
             st = None

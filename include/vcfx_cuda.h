@@ -146,6 +146,12 @@ int vcfx_cuda_submit(vcfx_ctx *ctx, size_t nbytes, const vcfx_chunk_info *info);
  *                  whose output outgrows its slot is re-run and must still find the bytes there.  */
 int vcfx_cuda_submit_shared(vcfx_ctx *ctx, vcfx_ctx *primary, const vcfx_chunk_info *info);
 int vcfx_cuda_next_output(vcfx_ctx *ctx, const char **text, size_t *n, vcfx_chunk_stats *stats);
+/* set_line_hint  : typical bytes per data line (0 = let the library measure it on the host buffers it
+ *                  is given).  A tile's owner re-reads about one line around every tile border, so
+ *                  inputs with very long lines (FORMAT GT:AD:DP:GQ:PL x thousands of samples) get
+ *                  larger tiles.  Only needed by run_device callers, whose bytes the host never sees:
+ *                  the reference tools have no such knob, it changes no result.                   */
+int vcfx_cuda_set_line_hint(vcfx_ctx *ctx, size_t line_bytes);
 /* submit_host    : like acquire + memcpy + submit, but the chunk is copied to the device straight
  *                  from the caller's buffer (an mmap'ed/pinned region gives the full PCIe rate).
  *                  The buffer must stay unchanged until next_output has returned this chunk.   */

@@ -58,7 +58,7 @@ class ChunkStats(C.Structure):
 
 EXPORTS = ["vcfx_cuda_abi_version", "vcfx_cuda_device_count", "vcfx_cuda_strerror", "vcfx_cuda_last_error",
            "vcfx_cuda_create", "vcfx_cuda_destroy", "vcfx_cuda_acquire_input", "vcfx_cuda_submit",
-           "vcfx_cuda_submit_host", "vcfx_cuda_submit_shared", "vcfx_cuda_next_output", "vcfx_cuda_in_flight", "vcfx_cuda_short_lines",
+           "vcfx_cuda_submit_host", "vcfx_cuda_submit_shared", "vcfx_cuda_set_line_hint", "vcfx_cuda_next_output", "vcfx_cuda_in_flight", "vcfx_cuda_short_lines",
            "vcfx_cuda_run_device", "vcfx_cuda_sync"]
 
 _lib = None
@@ -86,6 +86,7 @@ def load():
         l.vcfx_cuda_submit.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(ChunkInfo)]
         l.vcfx_cuda_submit_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(ChunkInfo)]
         l.vcfx_cuda_submit_shared.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(ChunkInfo)]
+        l.vcfx_cuda_set_line_hint.argtypes = [C.c_void_p, C.c_size_t]
         l.vcfx_cuda_next_output.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(ChunkStats)]
         l.vcfx_cuda_in_flight.argtypes = [C.c_void_p]
         l.vcfx_cuda_short_lines.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_size_t, C.POINTER(C.c_size_t)]
@@ -205,6 +206,10 @@ class Context:
             return False
         self._check(rc)
         return True
+
+    def set_line_hint(self, line_bytes: int) -> None:
+        """Typical bytes per data line, for run_device callers (the host never sees their bytes)."""
+        self._check(self._l.vcfx_cuda_set_line_hint(self._h, int(line_bytes)))
 
     def in_flight(self) -> int:
         return self._l.vcfx_cuda_in_flight(self._h)

@@ -215,12 +215,12 @@ __device__ __noinline__ int gt_index_of(const uint8_t *p, const uint8_t *e) {
     return -1;
 }
 
-// byte index (0..15) of the first set 0x80-bit over the lane's four mask words
+// byte index (0..15) of the first set 0x80-bit over the lane's four mask words, with selects instead of
+// branches (the lanes of a warp hold their first tab in different words)
 __device__ __forceinline__ int first_byte(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
-    if (m0) return (__ffs(m0) - 1) >> 3;
-    if (m1) return 4 + ((__ffs(m1) - 1) >> 3);
-    if (m2) return 8 + ((__ffs(m2) - 1) >> 3);
-    return 12 + ((__ffs(m3) - 1) >> 3);
+    const uint32_t m = m0 ? m0 : (m1 ? m1 : (m2 ? m2 : m3));
+    const int base = m0 ? 0 : (m1 ? 4 : (m2 ? 8 : 12));
+    return base + ((__ffs(m) - 1) >> 3);
 }
 
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
