@@ -50,9 +50,11 @@ def log(*a):
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index: int):
+    def __init__(self, indices):
+        """indices: physical GPU indices to watch (rank 0 watches every GPU of the job: one NVML poller
+        per node instead of one per rank, so the polling itself does not perturb the launches)."""
         super().__init__(daemon=True)
-        self.index = index
+        self.indices = list(indices)
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
@@ -62,9 +64,9 @@ class ClockSampler(threading.Thread):
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            self.ok = True
+            self.hs = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in self.indices]
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.hs[0], pynvml.NVML_CLOCK_SM) if self.hs else None
+            self.ok = bool(self.hs)
         except Exception as e:  # pragma: no cover
             log(f"[bench] NVML unavailable: {e}")
 
@@ -79,23 +81,25 @@ class ClockSampler(threading.Thread):
             getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
         }
         while not self._halt.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            for h in self.hs:
                 try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
                 except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(0.004)
+                    pass
+            time.sleep(0.01)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=2)
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_mhz_min": min(self.samples) if self.samples else None, "gpus_watched": len(getattr(self, "hs", [])),
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
@@ -241,14 +245,24 @@ def main():
     valid_from = 0 if rank else api.find_chrom_header(hdr)
     totals = torch.zeros(2, dtype=torch.int64, device=dev)
 
+    pending = []                           # the totals reductions still in flight
+
     def step_resident():
         ctx_af.run_device(d_in.data_ptr(), nbytes, d_out.data_ptr(), out_cap, valid_from=valid_from)
         ctx_vc.run_device(d_in.data_ptr(), nbytes, 0, 0)
         if world > 1:
-            dist.all_reduce(totals)        # the path's only exchange: scalar totals
+            # the path's only exchange: one all-reduce of the scalar totals per job.  It runs on NCCL's own
+            # stream behind this step's kernels and overlaps the next step; the timed region ends only after
+            # every one of them has completed (wait_totals)
+            pending.append(dist.all_reduce(totals, async_op=True))
+
+    def wait_totals():
+        while pending:
+            pending.pop().wait()           # the launch stream waits for the reduction (no host block)
 
     # ---- correctness gate (size-independent properties at full size)
     step_resident()
+    wait_totals()
     torch.cuda.synchronize()
     st_af, st_vc = ctx_af.sync(), ctx_vc.sync()
     assert st_af.rows == V and st_vc.rows == V, (st_af.rows, st_vc.rows, V)
@@ -259,16 +273,20 @@ def main():
 
     for _ in range(warmup):
         step_resident()
+    wait_totals()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(physical_gpu_index(local_rank)); sampler.start()
+    sampler = ClockSampler([physical_gpu_index(r) for r in range(world)] if rank == 0 else []); sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         step_resident()
+    wait_totals()
     e1.record()
+    host_ms_per_step = (time.perf_counter() - t_host0) * 1e3 / args.steps      # enqueue time only (no sync yet)
     torch.cuda.synchronize()
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
@@ -277,6 +295,12 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
+    per_rank_ms = [ms_total / args.steps]
+    if world > 1:                      # every rank's own time, for the record (value uses the slowest)
+        g = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(g, torch.tensor([ms_total / args.steps], dtype=torch.float64, device=dev))
+        per_rank_ms = [round(float(x.item()), 4) for x in g]
+    log(f"[bench r{rank}] timed region: {ms_total / args.steps:.3f} ms/step on the device, {host_ms_per_step:.3f} ms/step of host enqueue")
     value = world * nbytes / (ms_step / 1e3) / 1e9
 
     # per-kernel durations (CUDA events around each tool's kernels on the launch stream)
@@ -385,7 +409,7 @@ def main():
             "genotypes_per_s": world * V * C2_SAMPLES / (ms_step / 1e3),
             "variants_per_s": world * V / (ms_step / 1e3),
             "bytes_per_gpu": nbytes,
-            "e2e": e2e, "gpu_launches": 5 * args.steps, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": 5 * args.steps, "per_rank_ms_per_step": per_rank_ms, "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
