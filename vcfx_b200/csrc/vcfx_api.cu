@@ -174,10 +174,12 @@ int grid_for(const vcfx_ctx *ctx, uint32_t n_tiles) {
     return std::max(1, std::min(resident, need));
 }
 
-// Row records are sized for ordinary VCFs (a row-producing line is at least 11 bytes, real ones
-// are far longer); if a chunk ever has more rows the launch reports overflow and is repeated
-// with the exact count (see relaunch_if_overflow).
-uint64_t default_rec_cap(size_t nbytes) { return nbytes / 48 + 65536; }
+// Row records are sized for ordinary VCFs: one row per 256 input bytes (a line with nine fixed
+// fields and a handful of samples is longer than that; at 2,504 samples a line is 10 KB).  If a
+// chunk ever has more rows the launch reports overflow and is repeated with the exact count (see
+// vcfx_cuda_next_output / vcfx_cuda_sync), and the larger arrays are kept.  64 bytes per record
+// (record + prefix copy): 17 MB per 64 MiB chunk, 1.1 GB for a 4.3 GB resident chunk.
+uint64_t default_rec_cap(size_t nbytes) { return nbytes / 256 + 65536; }
 
 void free_work(Work &w) {
     cudaFree(w.tile_lines); cudaFree(w.tile_out); cudaFree(w.tile_base); cudaFree(w.line_base);

@@ -234,61 +234,14 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 // ---------------------------------------------------------------------------------------
 struct Tally { uint32_t a, b, c; };   // AF: alt,total   HWE: homRef,het,homAlt
 
-// Quick shapes of a sample column, decided from its first four bytes q (b0 = the byte after the
-// leading tab) WITHOUT branches, so the lanes of a warp do not diverge on mixed data:
+// Quick shapes of a sample column, decided from the bytes behind its leading tab WITHOUT branches, so
+// the lanes of a warp do not diverge on mixed data:
 //   A  <end>                 empty column / empty GT
 //   B  t <end>               haploid          t = digit or '.', <end> = tab, ':' or '\n'
 //   C  t sep t <end>         diploid, single-character alleles
 // Everything else (multi-digit alleles, more alleles, '\r', other bytes, GT not first) goes to the
 // exact scalar parsers.
-struct Quad {
-    uint32_t d0, d2, z0, z2;   // allele bytes: is digit / is '0'   (0 or 1)
-    uint32_t shapeB, shapeC, quick;
-};
-// SWAR over the four bytes of q at once (0x80 flag per byte), then a handful of bit tests
-__device__ __forceinline__ Quad classify_quad(uint32_t q) {
-    const uint32_t T = eq_bytes(q, 0x09090909u) | eq_bytes(q, 0x3A3A3A3Au) | eq_bytes(q, 0x0A0A0A0Au);   // tab ':' '\n'
-    const uint32_t S = eq_bytes(q, 0x2F2F2F2Fu) | eq_bytes(q, 0x7C7C7C7Cu);                             // '/' '|'
-    const uint32_t Z = eq_bytes(q, 0x30303030u);
-    const uint32_t P = eq_bytes(q, 0x2E2E2E2Eu);
-    // digits: byte >= '0' and not byte >= ':' (7-bit add; bytes >= 0x80 are excluded explicitly)
-    const uint32_t q7 = q & 0x7F7F7F7Fu;
-    const uint32_t D = (q7 + 0x50505050u) & ~(q7 + 0x46464646u) & ~q & 0x80808080u;
-    const uint32_t tok = D | P;
-    Quad r;
-    r.d0 = (D >> 7) & 1u; r.d2 = (D >> 23) & 1u;
-    r.z0 = (Z >> 7) & 1u; r.z2 = (Z >> 23) & 1u;
-    r.shapeB = ((tok & (T >> 8)) >> 7) & 1u;                                   // t <end>
-    r.shapeC = ((tok & (S >> 8) & (tok >> 16) & (T >> 24)) >> 7) & 1u;         // t sep t <end>
-    r.quick = ((T >> 7) & 1u) | r.shapeB | r.shapeC;
-    return r;
-}
-
-// AF (allele_freq_calc.cpp:262-293): every numeric allele counts, non-zero ones are ALT
-__device__ __forceinline__ void af_sample_reg(uint32_t q, const uint8_t *p, bool strip_cr, int gt_index,
-                                              uint32_t &alt, uint32_t &total) {
-    const Quad c = classify_quad(q);
-    if (gt_index == 0 && c.quick) {
-        const uint32_t any = c.shapeB | c.shapeC;
-        total += (any & c.d0) + (c.shapeC & c.d2);
-        alt += (any & c.d0 & (c.z0 ^ 1u)) + (c.shapeC & c.d2 & (c.z2 ^ 1u));
-        return;
-    }
-    const uint2 r = af_sample_slow(p, strip_cr, gt_index);
-    alt += r.x; total += r.y;
-}
-
-// HWE (hwe_tester.cpp:339-378): class 0 homRef, 1 het, 2 homAlt, -1 none; only "a sep b" with a, b in
-// {0,1} counts, whatever follows the second allele
-__device__ __forceinline__ int hwe_sample_reg(uint32_t q, const uint8_t *p) {
-    const uint32_t b0 = q & 0xFF, b1 = (q >> 8) & 0xFF, b2 = (q >> 16) & 0xFF, b3 = q >> 24;
-    const bool d0 = is_dig(b0), d1 = is_dig(b1), d2 = is_dig(b2), d3 = is_dig(b3), s1 = is_sep(b1);
-    if ((!d0 && b0 != ' ' && b0 != '\r') || (d0 && !s1 && !d1) || (d0 && s1 && !d2)) return -1;
-    if (d0 && s1 && d2 && !d3) return (b0 <= '1' && b2 <= '1') ? (int)(b0 - '0') + (int)(b2 - '0') : -1;
-    return hwe_sample_slow(p);
-}
-
-// Byte classes of one word as 0x80 markers (exact, like classify_quad's)
+// Byte classes of one word as 0x80 markers (exact)
 struct WClass { uint32_t D, Z, P, S, E, O; };   // digit, '0', '.', '/' or '|', tab / ':' / '\n', '1' (HWE only)
 template <int OP>
 __device__ __forceinline__ WClass classify_word(uint32_t x) {
@@ -314,8 +267,7 @@ __device__ __forceinline__ uint32_t down(uint32_t lo, uint32_t hi, int k) { retu
 
 // generic: one sample per owned tab (tab masks m0..m3 over the lane's words w0..w3, la = next 4 B).
 // All the tabs of a word are judged at once: the classes of the bytes behind a tab are the class
-// markers moved down by 1..4 bytes, so the quick shapes of classify_quad (same conditions, same
-// tallies) become a few AND/POPC per word; only tabs whose sample is none of them go to the scalar
+// markers moved down by 1..4 bytes, so the quick shapes A / B / C above become a few AND/POPC per word; only tabs whose sample is none of them go to the scalar
 // parsers, one by one.  Kept out of line: it must not cost the lattice path registers.
 template <int OP>
 __device__ __noinline__ uint4 lane_samples_generic(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t la,
@@ -444,15 +396,6 @@ __device__ __noinline__ uint2 ac_sample_slow(const uint8_t *p) {
         } else ++p;
     }
     return make_uint2(ref, alt);
-}
-__device__ __forceinline__ uint2 ac_sample_reg(uint32_t q, const uint8_t *p) {
-    const Quad c = classify_quad(q);
-    if (c.quick) {
-        const uint32_t any = c.shapeB | c.shapeC;
-        return make_uint2((any & c.z0) + (c.shapeC & c.z2),
-                          (any & c.d0 & (c.z0 ^ 1u)) + (c.shapeC & c.d2 & (c.z2 ^ 1u)));
-    }
-    return ac_sample_slow(p);
 }
 __device__ __forceinline__ uint32_t dec_len(int v) {       // characters of the decimal form, sign included
     if ((uint32_t)v < 10u) return 1u;                      // allele counts of one sample: almost always
