@@ -473,7 +473,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (OP == OP_VC) ? 5 : VCFX_P
 vcfx_scan_kernel(const KParams P) {
     __shared__ uint32_t s_tp[WARPS_PER_CTA][12];
     __shared__ __align__(16) uint8_t s_stage[(OP == OP_AC) ? WARPS_PER_CTA * (AC_STAGE + 32) : 16];
-    const int lane = threadIdx.x & 31;
+    int lane;                                   // %laneid: one S2R when the compiler rematerialises it (it does, a dozen times per line)
+    asm("mov.u32 %0, %%laneid;" : "=r"(lane));
     const int wid = threadIdx.x >> 5;
     volatile uint32_t *tp = s_tp[wid];
     const uint64_t n = P.n;
@@ -492,7 +493,8 @@ vcfx_scan_kernel(const KParams P) {
     // shared memory, only lane 0 touches it; the slots a warp leaves unused are marked invalid when it exits.
     __shared__ unsigned long long s_rec_base[WARPS_PER_CTA];
     __shared__ unsigned int s_rec_used[WARPS_PER_CTA];
-    __shared__ volatile unsigned int s_odd[WARPS_PER_CTA], s_reg[WARPS_PER_CTA];
+    __shared__ volatile unsigned int s_odd[WARPS_PER_CTA], s_reg[WARPS_PER_CTA], s_tag[WARPS_PER_CTA];
+    if (lane == 0) s_tag[wid] = 0;
     if (lane == 0) { s_rec_base[wid] = 0; s_rec_used[wid] = REC_BLOCK; }
     __syncwarp();
     auto alloc_slot_lane0 = [&]() -> unsigned long long {       // call from lane 0 only
@@ -540,6 +542,7 @@ vcfx_scan_kernel(const KParams P) {
         }
 
         uint32_t nlines = 0;
+        s_tag[wid] = 0;                                     // no line of this tile has used the exact-path counters yet
         // output bytes of the tile: only allele_counter's per-sample rows can exceed 32 bits (input offsets cannot)
         typename OutCount<OP>::type out_bytes = 0;
         uint32_t md_prev_end = ls, md_last_end = ls;   // MISSING_DETECT: end of the last rewritten line / of the last line
@@ -642,7 +645,6 @@ vcfx_scan_kernel(const KParams P) {
                 uint32_t accp = 0;                 // packed sums: bits 0..15 first alleles, 16..31 second alleles
                 uint32_t hetp = 0, hap = 0;        // HWE tier-1 tallies
                 uint32_t n_real = 0;               // samples tallied by tier 1 (uniform)
-                s_odd[wid] = 0; s_reg[wid] = 0;    // windows in a row that went through the exact path / were regular in it (shared: registers are short)
                 // ---- the window with tab 9, the cheap way.  A rotated word f_k of a lane covers the four bytes
                 // after byte 4k + tau of that lane, i.e. one sample behind its leading tab when the lattice holds.
                 // Tab 9 itself sits on the lattice (tau = its position mod 4), so in its lane the words from its own
@@ -874,6 +876,9 @@ vcfx_scan_kernel(const KParams P) {
                         // A line that keeps leaving the lattice (missing / haploid calls every few samples: two
                         // windows in a row came here) stops trying: every sample is parsed from its leading tab,
                         // until eight windows in a row held nothing but "digit sep digit".
+                        // (the two counters live in shared memory — registers are short — and belong to the line
+                        // whose start is in s_tag: lines that never come here never touch them)
+                        if (s_tag[wid] != ls + 1u) { s_tag[wid] = ls + 1u; s_odd[wid] = 0; s_reg[wid] = 0; }
                         const bool qm = lat_possible && !first_win && s_odd[wid] >= 2;
                         uint32_t irr = 0;
                         const bool lat = lat_possible && !qm && lane_lattice<OP>(cur.x, cur.y, cur.z, cur.w, la, packed, sh_lane);
