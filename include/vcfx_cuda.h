@@ -165,11 +165,13 @@ int vcfx_cuda_short_lines(vcfx_ctx *ctx, uint64_t *line_no, size_t cap, size_t *
 
 /* ---- device-resident path: for callers that already hold the bytes in HBM -----------------
  * d_in must be 16-byte aligned and readable for nbytes + VCFX_DEVICE_PAD bytes (the library
- * writes '\n' into the first 64 bytes of that pad).  d_out receives the text (out_cap bytes).
+ * writes '\n' into the first 64 bytes of that pad; the kernels keep up to eight 512-byte windows
+ * in flight per warp and so read up to 4,100 bytes past the window that holds the last byte).
+ * d_out receives the text (out_cap bytes).
  * Runs on cfg.stream (or the context's own stream), asynchronously; calls may be queued back to
  * back; vcfx_cuda_sync waits and fills stats of the LAST one.  Used by bench.py for the
  * kernel-only figure. */
-#define VCFX_DEVICE_PAD 4096
+#define VCFX_DEVICE_PAD 8192
 int vcfx_cuda_run_device(vcfx_ctx *ctx, void *d_in, size_t nbytes, const vcfx_chunk_info *info,
                          void *d_out, size_t out_cap);
 int vcfx_cuda_sync(vcfx_ctx *ctx, vcfx_chunk_stats *stats);

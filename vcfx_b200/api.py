@@ -20,7 +20,7 @@ from . import build as _build
 OP_VARIANT_COUNT, OP_ALLELE_FREQ, OP_HWE, OP_MISSING_DETECT, OP_ALLELE_COUNT = range(5)
 FILE, STDIN = 0, 1
 F_AC_AGGREGATE, F_AC_BINARY, F_AC_FORWARD = 1, 2, 4
-DEVICE_PAD = 4096
+DEVICE_PAD = 8192
 
 E_BUSY, E_EMPTY = -5, -6
 
