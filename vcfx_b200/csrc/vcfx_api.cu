@@ -86,6 +86,7 @@ struct vcfx_ctx {
     uint32_t *d_sel_col = nullptr, *d_name_off = nullptr;
     uint8_t *d_names = nullptr;
     int ac_fmt = 0;
+    bool ac_ident = false;               // allele_counter selection = columns 0 .. n_sel-1 in order
     bool ac_exact = false;               // a chunk had a count of two digits: rows are sized by parsing from now on
     // last drained chunk's short-line list
     std::vector<uint64_t> last_events;
@@ -258,7 +259,7 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
     P.out = d_out; P.out_cap = out_cap;
     P.tile_lines = w.tile_lines; P.tile_out = w.tile_out; P.tile_base = w.tile_base; P.line_base = w.line_base;
     P.tail_start = w.tail_start; P.tail_len = w.tail_len; P.tail_off = w.tail_off;
-    P.ac_fmt = ctx->ac_fmt; P.ac_pass = 0; P.ac_spec = (ctx->cfg.op == VCFX_OP_ALLELE_COUNT && ctx->ac_fmt == AC_TEXT_MT && !ctx->ac_exact) ? 1 : 0; P.n_sel = ctx->n_sel; P.sel_col = ctx->d_sel_col; P.name_off = ctx->d_name_off;
+    P.ac_fmt = ctx->ac_fmt; P.ac_ident = ctx->ac_ident ? 1 : 0; P.ac_pass = 0; P.ac_spec = (ctx->cfg.op == VCFX_OP_ALLELE_COUNT && ctx->ac_fmt == AC_TEXT_MT && !ctx->ac_exact) ? 1 : 0; P.n_sel = ctx->n_sel; P.sel_col = ctx->d_sel_col; P.name_off = ctx->d_name_off;
     P.names = ctx->d_names; P.max_col = ctx->max_col; P.col_scratch = w.col_scratch;
     P.ticket = w.ticket; P.recs = w.recs; P.rec_prefix = w.rec_prefix; P.rec_cap = w.rec_cap;
     P.stats = w.d_stats; P.events = w.events; P.ev_cap = EVENT_CAP;
@@ -393,6 +394,8 @@ int vcfx_cuda_create(const vcfx_cfg *cfg, vcfx_ctx **out) {
         if (ctx->ac_fmt != AC_TEXT_MT)                      // forward-only column walk (:1222-1227): running maximum
             for (size_t i = 1; i < cols.size(); ++i) cols[i] = std::max(cols[i], cols[i - 1]);
         ctx->n_sel = cfg->n_sel;
+        ctx->ac_ident = true;
+        for (uint32_t i = 0; i < cfg->n_sel; ++i) if (cfg->sel_col[i] != i) { ctx->ac_ident = false; break; }
         ctx->max_col = *std::max_element(cols.begin(), cols.end()) + 1;
         const size_t nb = cfg->sel_name_off[cfg->n_sel];
         CUC(cudaMalloc(&ctx->d_sel_col, sizeof(uint32_t) * cfg->n_sel));

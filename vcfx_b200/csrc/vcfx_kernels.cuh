@@ -87,6 +87,7 @@ struct KParams {
     // ALLELE_COUNT
     int32_t ac_fmt;                  // AC_TEXT_MT / AC_TEXT_FWD / AC_AGG / AC_BIN
     int32_t ac_pass;                 // 0 = size the rows, 1 = write them
+    int32_t ac_ident;                // the selection is columns 0 .. n_sel-1 in order (-a then needs no per-column scratch)
     int32_t ac_spec;                 // TEXT_MT: size the rows without parsing genotypes (every count one digit); pass 1 verifies
     uint32_t n_sel;                  // selected samples, in output order
     const uint32_t *sel_col;         // [n_sel] sample column (running maximum in the forward modes)
@@ -1010,6 +1011,7 @@ vcfx_scan_kernel(const KParams P) {
                             const WClass hi = classify_word<OP_AC>(ws[j + 1]);
                             uint32_t m = ms[j];
                             if (m) {
+                                const bool agg_fast = (P.ac_fmt == AC_AGG) && P.ac_ident;   // totals only: ta = ref, tb = alt
                                 const uint32_t tokl = lo.D | lo.P, tokh = hi.D | hi.P;
                                 const uint32_t t1 = down(tokl, tokh, 1), t3 = down(tokl, tokh, 3), s2 = down(lo.S, hi.S, 2);
                                 const uint32_t e1 = down(lo.E, hi.E, 1), e2 = down(lo.E, hi.E, 2), e4 = hi.E;
@@ -1017,6 +1019,19 @@ vcfx_scan_kernel(const KParams P) {
                                 const uint32_t z1 = down(lo.Z, hi.Z, 1), z3 = down(lo.Z, hi.Z, 3);
                                 const uint32_t C = m & t1 & s2 & t3 & e4, any = (m & t1 & e2) | C, quick = (m & e1) | any;
                                 const uint32_t R1 = any & z1, R3 = C & z3, A1 = any & d1 & ~z1, A3 = C & d3 & ~z3;
+                                const int nm = __popc(m);
+                                if (agg_fast && r >= 8 && (uint32_t)(r + nm) <= 8u + P.n_sel) {
+                                    // every tab of this word leads a selected column: add the quick ones by count
+                                    ta += __popc(R1) + __popc(R3); tb += __popc(A1) + __popc(A3);
+                                    uint32_t rest = m & ~quick;
+                                    while (rest) {
+                                        const int k = (__ffs(rest) - 1) >> 3;
+                                        rest &= rest - 1;
+                                        const uint2 v = ac_sample_slow(tin + pb + 4 * j + k + 1);
+                                        ta += v.x; tb += v.y;
+                                    }
+                                    r += nm; m = 0;
+                                }
                                 while (m) {
                                     const uint32_t bit = m & (0u - m);
                                     const int k = (__ffs(m) - 1) >> 3;
@@ -1026,7 +1041,8 @@ vcfx_scan_kernel(const KParams P) {
                                         if (quick & bit) v = make_uint2(((R1 & bit) ? 1u : 0u) + ((R3 & bit) ? 1u : 0u),
                                                                         ((A1 & bit) ? 1u : 0u) + ((A3 & bit) ? 1u : 0u));
                                         else v = ac_sample_slow(tin + pb + 4 * j + k + 1);
-                                        scr[r - 8] = v;
+                                        if (agg_fast) { if ((uint32_t)(r - 8) < P.n_sel) { ta += v.x; tb += v.y; } }
+                                        else scr[r - 8] = v;
                                     }
                                     ++r;
                                 }
@@ -1192,10 +1208,13 @@ vcfx_scan_kernel(const KParams P) {
                     const uint32_t prefix_src = tabs >= 5 ? tp[4] + 1 - ls : e - ls;
                     const uint32_t prefix_len = prefix_src + extra_tabs;
                     if (P.ac_fmt == AC_AGG) {
-                        uint32_t sr = 0, sa = 0;
-                        for (uint32_t i = lane; i < n_rows; i += 32) {
-                            const uint32_t c = P.sel_col[i];
-                            if (c < ns_parsed) { const uint2 v = scr[c]; sr += v.x; sa += v.y; }
+                        uint32_t sr = ta, sa = tb;                  // identity selection: the lanes summed while parsing
+                        if (!P.ac_ident) {
+                            sr = 0; sa = 0;
+                            for (uint32_t i = lane; i < n_rows; i += 32) {
+                                const uint32_t c = P.sel_col[i];
+                                if (c < ns_parsed) { const uint2 v = scr[c]; sr += v.x; sa += v.y; }
+                            }
                         }
                         sr = __reduce_add_sync(FULL, sr); sa = __reduce_add_sync(FULL, sa);
                         const uint32_t row_len = prefix_len + dec_len((int)sr) + 1 + dec_len((int)sa) + 1 + dec_len((int)n_rows) + 1;
