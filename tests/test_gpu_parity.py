@@ -264,3 +264,17 @@ def test_allele_counter_two_digit_counts(cuda_api, oracle):
     # and the plain case right after it through a fresh context
     data2 = synth.make_vcf(2, 40, 64, seed=9)
     _cmp("ac after exact", cuda_api.allele_counter(data2).out, oracle.allele_counter(data2).out)
+
+
+def test_more_rows_than_the_default_record_capacity(cuda_api, oracle):
+    """Row records are sized for one row per 256 input bytes (+64 Ki); a chunk of very short lines has
+    more: the launch reports it and is repeated with the exact count (block-wise slot reservation
+    included), through the streaming path and through several chunks."""
+    hdr = b"##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tA\tB\n"
+    gts = [b"0|1", b"1|1", b"0|0", b"./.", b"1|0"]
+    body = b"".join(b"1\t%d\t.\tA\tG\t.\t.\t.\tGT\t%s\t%s\n" % (i + 1, gts[i % 5], gts[(i * 7 + 3) % 5]) for i in range(130000))
+    data = hdr + body
+    chunk = 4 << 20                                       # the slot's capacity is sized from the chunk size
+    assert len(data) <= chunk and chunk // 256 + 65536 < 130000
+    run_all(cuda_api, oracle, data, "many short lines, one 4 MiB chunk", chunk_bytes=chunk, tools=("af", "hwe", "md", "vc"))
+    run_all(cuda_api, oracle, data, "many short lines, 1 MiB chunks", chunk_bytes=1 << 20, tools=("af", "md"))

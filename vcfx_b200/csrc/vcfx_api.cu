@@ -182,6 +182,13 @@ int grid_for(const vcfx_ctx *ctx, uint32_t n_tiles) {
 // (record + prefix copy): 17 MB per 64 MiB chunk, 1.1 GB for a 4.3 GB resident chunk.
 uint64_t default_rec_cap(size_t nbytes) { return nbytes / 256 + 65536; }
 
+// Slots are reserved REC_BLOCK at a time per warp and a warp leaves at most one block partly used, so
+// the count of a re-run can exceed the count of the run before it by that much (the warps draw
+// different tiles the second time).
+uint64_t rec_slack(const vcfx_ctx *ctx) {
+    return (uint64_t)REC_BLOCK * ctx->sm_count * ctx->blocks_per_sm * WARPS_PER_CTA + 1024;
+}
+
 void free_work(Work &w) {
     cudaFree(w.tile_lines); cudaFree(w.tile_out); cudaFree(w.tile_base); cudaFree(w.line_base);
     cudaFree(w.rec_prefix); cudaFree(w.ticket); cudaFree(w.recs); cudaFree(w.d_stats); cudaFree(w.events);
@@ -548,7 +555,7 @@ int vcfx_cuda_next_output(vcfx_ctx *ctx, const char **text, size_t *n, vcfx_chun
         const unsigned long long ov = s.w.h_stats->overflow;
         if (ov & 4) ctx->ac_exact = true;
         if (ov & 1) {
-            int rc = ensure_work(ctx, s.w, ctx->chunk_bytes, s.w.h_stats->n_recs + 1024);
+            int rc = ensure_work(ctx, s.w, ctx->chunk_bytes, s.w.h_stats->n_recs + rec_slack(ctx));
             if (rc != VCFX_OK) return rc;
         }
         if (ov & 2) {
@@ -607,7 +614,7 @@ int vcfx_cuda_sync(vcfx_ctx *ctx, vcfx_chunk_stats *stats) {
     ctx->dev_pending = false;
     if (ctx->dev_work.h_stats->overflow & 5) {      // more rows than sized for / speculative row sizes off: run again, exact
         if (ctx->dev_work.h_stats->overflow & 4) ctx->ac_exact = true;
-        int rc2 = ensure_work(ctx, ctx->dev_work, ctx->dev_nbytes, ctx->dev_work.h_stats->n_recs + 1024);
+        int rc2 = ensure_work(ctx, ctx->dev_work, ctx->dev_nbytes, ctx->dev_work.h_stats->n_recs + rec_slack(ctx));
         if (rc2 != VCFX_OK) return rc2;
         rc2 = launch_chunk(ctx, ctx->dev_work, ctx->dev_stream, ctx->dev_in, ctx->dev_nbytes, &ctx->dev_info,
                            ctx->dev_out, ctx->dev_out_cap);
