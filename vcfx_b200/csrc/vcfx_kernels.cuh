@@ -3,21 +3,25 @@
 // K1  vcfx_scan_kernel<OP>   one fused pass over the bytes: line scan, field location,
 //                            genotype parse, per-variant reduction, row records
 // K2a tile_scan_kernel       exclusive scan of the per-tile output sizes / line counts
-// K2b format_rows_kernel<OP> one thread per row: verbatim CHROM..ALT prefix + number text,
-//                            written at its final, file-ordered offset
+// K2b format_rows_kernel<OP> a warp per 32 rows: verbatim CHROM..ALT prefix + number text built in shared
+//                            memory, written row by row at the final, file-ordered offset
+// K2c md_copy_kernel         missing_detector: the input with insertions (warp per item, 128-bit copies)
 //
 // Decomposition: the chunk is cut into byte tiles of `tile_bytes`; one WARP
 // owns every line that STARTS inside its tile — the reference's own thread-chunking rule
 // (allele_counter.cpp:890-903, missing_detector.cpp:404-422) applied at warp granularity, so
 // a line is always parsed from its first byte by one owner and no parser state is stitched
 // across tiles.  A warp streams its lines in 512-byte windows (16 B per lane, coalesced
-// 128-bit loads, the next window already in flight, L2 prefetch further ahead):
+// 128-bit loads, later windows already in flight, L2 prefetch further ahead):
 //   stage 1  '\n' and '\t' found with exact SWAR byte compares + __ballot_sync / __popc
 //   stage 2  tabs 1..9 of the record ranked by a warp prefix sum; FORMAT -> GT index
-//   stage 3  samples parsed from registers by the lane holding their leading tab (own 16 B
-//            + 4 B look-ahead from the neighbour lane).  A lane whose bytes are the period-4
-//            "d|d\t" lattice of diploid single-digit calls is verified and tallied with a
-//            dozen integer ops per word and never computes a full delimiter mask.
+//   stage 3  genotypes, three tiers, each exact on what it accepts:
+//            tier 1  the whole line is the period-4 lattice "a<sep>b\t", a, b in {0,1}: rounds of two
+//                    windows, four funnel shifts per lane and window, one vote per round, alleles
+//                    summed as packed words (no per-word XOR, HWE via a sum of squares)
+//            tier 2  per-lane lattice (any digit, either separator, per-lane phase)
+//            tier 3  every sample from its leading tab: the quick shapes of all tabs of a word at
+//                    once (byte-class markers shifted by 1..4 bytes), scalar parsers for the rest
 //   stage 4  warp REDUX of the tallies -> one 32-byte row record; K2 turns records into text.
 // Tensor cores are not involved: this is byte scanning and integer reduction, HBM-bound.
 #pragma once
