@@ -85,7 +85,7 @@ long Source::parallel_read(char *dst, size_t cap) {
     const size_t min_slice = (size_t)4 << 20;
     if (n < 2 * min_slice) return -2;
     const int parts = (int)std::min<size_t>((size_t)io_threads_, n / min_slice);
-    const size_t slice = ((n / parts) + 4095) & ~(size_t)4095;
+    const size_t slice = (((n + parts - 1) / parts) + 4095) & ~(size_t)4095;   // parts * slice >= n
     std::vector<size_t> got(parts, 0);
     std::vector<std::thread> th;
     auto work = [&](int i) {
@@ -164,7 +164,7 @@ static bool write_parallel(int fd, const char *p, size_t n) {
     const off_t base = lseek(fd, 0, SEEK_CUR);
     if (base < 0) return false;
     const int parts = (int)std::min<size_t>((size_t)threads, n / min_slice);
-    const size_t slice = ((n / parts) + 4095) & ~(size_t)4095;
+    const size_t slice = (((n + parts - 1) / parts) + 4095) & ~(size_t)4095;   // parts * slice >= n
     std::vector<char> ok(parts, 0);
     std::vector<std::thread> th;
     auto work = [&](int i) {
