@@ -93,7 +93,7 @@ class ClockSampler(threading.Thread):
                             self.reasons.add(name)
                 except Exception:
                     pass
-            time.sleep(0.01)
+            time.sleep(0.003)
 
     def stop(self):
         self._halt.set()
