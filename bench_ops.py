@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full variant counts")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--configs", default="C2,C3,C4")
+    ap.add_argument("--warm", type=int, default=2, help="untimed runs per tool (0 under ncu: one launch per kernel)")
     args = ap.parse_args()
 
     import numpy as np
@@ -75,10 +76,10 @@ def main():
             vf = api.find_chrom_header(hdr) if op == api.OP_ALLELE_FREQ else (api.first_data_offset(hdr) if op == api.OP_MISSING_DETECT else 0)
             ms = []
             st = None
-            for i in range(args.reps + 2):
+            for i in range(args.reps + args.warm):
                 ctx.run_device(d_in.data_ptr(), nbytes, d_out.data_ptr(), out_cap, valid_from=vf)
                 st = ctx.sync()
-                if i >= 2:
+                if i >= args.warm:
                     ms.append(st.kernel_ms)
             k = statistics.median(ms)
             alg = nbytes + int(st.bytes_out)

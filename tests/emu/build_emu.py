@@ -1,0 +1,45 @@
+"""Builds tests/emu/_build/libvcfx_emu.so: the product's kernel + C-ABI sources compiled with g++ against
+the warp emulator in this directory.  TEST INFRASTRUCTURE ONLY — nothing under vcfx_b200/ knows this exists."""
+from __future__ import annotations
+
+import subprocess
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+OUT = HERE / "_build" / "libvcfx_emu.so"
+
+
+def build(force: bool = False) -> Path:
+    srcs = [ROOT / "vcfx_b200" / "csrc" / "vcfx_api.cu", HERE / "cuda_emu.cpp"]
+    deps = srcs + sorted((ROOT / "vcfx_b200" / "csrc").glob("*.cuh")) + sorted((ROOT / "include").glob("*.h")) + [HERE / "cuda_runtime.h"]
+    if not force and OUT.exists() and all(d.stat().st_mtime <= OUT.stat().st_mtime for d in deps):
+        return OUT
+    OUT.parent.mkdir(exist_ok=True)
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas", "-Wno-unused-variable", "-x", "c++", "-DVCFX_EMU",
+           "-I", str(HERE), "-I", str(ROOT / "include"), "-I", str(ROOT / "vcfx_b200" / "csrc"),
+           "-fPIC", "-shared", "-o", str(OUT), *map(str, srcs)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        raise RuntimeError("emulator build failed")
+    return OUT
+
+
+def load_api():
+    """A private copy of vcfx_b200.api bound to the emulator library (the real module stays untouched)."""
+    import importlib.util
+    so = build()
+    spec = importlib.util.spec_from_file_location("vcfx_b200._api_under_emulator", ROOT / "vcfx_b200" / "api.py")
+    mod = importlib.util.module_from_spec(spec)
+    mod.__package__ = "vcfx_b200"
+    sys.modules[spec.name] = mod
+    spec.loader.exec_module(mod)
+    mod.lib_path = lambda: so
+    mod.load()
+    return mod
+
+
+if __name__ == "__main__":
+    print(build(force=True))

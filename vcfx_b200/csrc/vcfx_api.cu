@@ -13,6 +13,11 @@
 
 using namespace vcfx;
 
+// kernel launches go through one macro so that the test-only warp emulator (tests/emu/) can build this file with g++
+#ifndef VCFX_LAUNCH
+#define VCFX_LAUNCH(kern, grid, block, smem, stream, arg) (kern)<<<(grid), (block), (smem), (stream)>>>(arg)
+#endif
+
 namespace {
 
 constexpr size_t DEFAULT_CHUNK = 64u << 20;
@@ -274,18 +279,18 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
     CU(cudaEventRecord(w.ev_k0, st));
     if (nbytes > 0) {
         int grid = grid_for(ctx, tiles);
-        fn<<<grid, WARPS_PER_CTA * 32, 0, st>>>(P);
+        VCFX_LAUNCH(fn, grid, WARPS_PER_CTA * 32, 0, st, P);
         CU(cudaGetLastError());
-        tile_scan_kernel<<<1, 1024, SCAN_SMEM_BYTES, st>>>(P);
+        VCFX_LAUNCH(tile_scan_kernel, 1, 1024, SCAN_SMEM_BYTES, st, P);
         CU(cudaGetLastError());
         if (kernel_fn ff = format_kernel_for(ctx->cfg.op, ctx->ac_fmt)) {
-            ff<<<ctx->sm_count * (ctx->cfg.op == VCFX_OP_MISSING_DETECT ? 8 : 16), 256, 0, st>>>(P);
+            VCFX_LAUNCH(ff, ctx->sm_count * (ctx->cfg.op == VCFX_OP_MISSING_DETECT ? 8 : 16), 256, 0, st, P);
             CU(cudaGetLastError());
         } else if (ctx->cfg.op == VCFX_OP_ALLELE_COUNT) {
             // rows are sized in the first pass and written in a second one at their scanned offsets
             CU(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), st));
             P.ac_pass = 1;
-            fn<<<grid, WARPS_PER_CTA * 32, 0, st>>>(P);
+            VCFX_LAUNCH(fn, grid, WARPS_PER_CTA * 32, 0, st, P);
             CU(cudaGetLastError());
         }
     }

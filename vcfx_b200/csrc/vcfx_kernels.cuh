@@ -144,8 +144,17 @@ __device__ __forceinline__ void clip4(uint32_t &m0, uint32_t &m1, uint32_t &m2, 
 __device__ __forceinline__ uint4 ld16(const uint8_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
 __device__ __forceinline__ uint32_t ldb(const uint8_t *p) { return (uint32_t)__ldg(p); }
 __device__ __forceinline__ uint32_t ldw(const uint8_t *p) { return __ldg(reinterpret_cast<const uint32_t *>(p)); }
+// VCFX_EMU: the test-only warp emulator build of this file (tests/emu/); PTX has no meaning there
+#ifdef VCFX_EMU
+__device__ __forceinline__ void prefetch_l2(const void *) {}
+__device__ __forceinline__ void prefetch_l1(const void *) {}
+__device__ __forceinline__ int lane_id() { return (int)(threadIdx.x & 31u); }
+#else
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// %laneid: one S2R when the compiler rematerialises it (it does, a dozen times per line)
+__device__ __forceinline__ int lane_id() { int l; asm("mov.u32 %0, %%laneid;" : "=r"(l)); return l; }
+#endif
 
 __device__ __forceinline__ bool is_dig(uint32_t b) { return (b - 48u) <= 9u; }
 __device__ __forceinline__ bool is_sep(uint32_t b) { return b == '/' || b == '|'; }
@@ -478,8 +487,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (OP == OP_VC) ? 5 : VCFX_P
 vcfx_scan_kernel(const KParams P) {
     __shared__ uint32_t s_tp[WARPS_PER_CTA][12];
     __shared__ __align__(16) uint8_t s_stage[(OP == OP_AC) ? WARPS_PER_CTA * (AC_STAGE + 32) : 16];
-    int lane;                                   // %laneid: one S2R when the compiler rematerialises it (it does, a dozen times per line)
-    asm("mov.u32 %0, %%laneid;" : "=r"(lane));
+    const int lane = lane_id();
     const int wid = threadIdx.x >> 5;
     volatile uint32_t *tp = s_tp[wid];
     const uint64_t n = P.n;
@@ -1354,7 +1362,11 @@ __device__ __forceinline__ uint32_t scan_pad(uint32_t i) { return i + (i >> 3); 
 
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(const KParams P) {
+#ifdef VCFX_EMU
+    unsigned long long *scan_smem = static_cast<unsigned long long *>(emu::dyn_smem());
+#else
     extern __shared__ unsigned long long scan_smem[];
+#endif
     unsigned long long *so = scan_smem, *sl = scan_smem + SCAN_SMEM_WORDS;
     __shared__ unsigned long long ws_o[32], ws_l[32];
     __shared__ unsigned long long carry_o, carry_l;
