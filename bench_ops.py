@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full variant counts")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--configs", default="C2,C3,C4")
+    ap.add_argument("--tools", default="", help="comma-separated substrings: only tools whose name contains one of them")
     ap.add_argument("--warm", type=int, default=2, help="untimed runs per tool (0 under ncu: one launch per kernel)")
     args = ap.parse_args()
 
@@ -64,6 +65,8 @@ def main():
         del host
         names = [b"HG%05d" % (96 + i) for i in range(S)]
         for tname, op, flags in tools:
+            if args.tools and not any(t == tname for t in args.tools.split(",")):
+                continue
             out_cap = 64 << 20
             if op == api.OP_MISSING_DETECT:
                 out_cap = nbytes + nbytes // 50 + (1 << 20)

@@ -43,6 +43,22 @@ def test_copy_through_source_and_writer(probe, tmp_path, size, threads):
         assert dst.read_bytes() == data, (size, threads, cap)
 
 
+@pytest.mark.parametrize("threads", ["1", "8"])
+def test_reads_with_a_carry_keep_one_file_offset(probe, tmp_path, threads):
+    """A chunk that starts with a carried-over tail asks for less than the pread threshold (read(2)), the next
+    one for a full buffer (pread): both must follow the same file offset (the cached offset
+    went stale and 42 MB came out as 75 MB)."""
+    data = _pattern((41 << 20) + 4321)
+    src = tmp_path / "in.bin"; dst = tmp_path / "out.bin"
+    src.write_bytes(data)
+    env = dict(os.environ, VCFX_IO_THREADS=threads)
+    for cap, carry in ((8 << 20, 1 << 20), (8 << 20, 12345), ((9 << 20) + 7, (1 << 20) + 3)):
+        r = subprocess.run([str(probe), str(src), str(dst), str(cap), str(carry)], capture_output=True, env=env, timeout=120)
+        assert r.returncode == 0, r.stderr
+        assert int(r.stdout) == len(data)
+        assert dst.read_bytes() == data, (threads, cap, carry)
+
+
 def test_pipes_use_plain_read_and_write(probe, tmp_path):
     data = _pattern((10 << 20) + 99)
     src = tmp_path / "in.bin"; src.write_bytes(data)

@@ -475,92 +475,202 @@ __device__ __forceinline__ void t1_tally(uint32_t y0, uint32_t y1, uint32_t y2, 
 }
 
 // ---------------------------------------------------------------------------------------
+// Digit path: the rest of a line whose FORMAT is exactly "GT" once it is off the tier-1 lattice (missing calls,
+// haploid calls, mixed separators — the default shape of multi-sample VCFs).  Nothing is assumed about where a
+// sample starts; every byte is classified by range with SWAR adds (bit 7 of x + (0x80 - c) is set iff the byte
+// is >= c, for bytes < 0x80; the bounds of a word are monotone, so a union of ranges is the XOR of its bounds):
+//   allele_freq_calc   B = tab '\n' '/' '|'.  While no two non-B bytes touch (every token is ONE character)
+//                      and there is no ':' (everything is in the first piece), parseGenotypeAndCount
+//                      (allele_freq_calc.cpp:262-293) counts exactly the digit bytes: total = #[0-9], alt = #[1-9]
+//                      ('.' and any other single byte are tokens that count nothing).
+//   allele_counter -a  parseGenotypeRaw (allele_counter.cpp:267-294) counts digit RUNS of the first piece: while no
+//                      two digits touch and there is no ':', ref = #'0', alt = #[1-9].
+// A digit at byte k is counted by the lane that holds byte k + 1 (the byte that proves the token ends there), so a
+// token is never split between two windows' verdicts.  Anything else (a multi-character token, a ':', a byte
+// >= 0x80, "\r\n" in stdin mode) makes the function return false with nothing kept: the caller then runs its exact
+// per-sample path over the same bytes, as if this function had not been called.
+// Returns true when the line's '\n' was reached: e = its position, a / b / tabs = this lane's partial counts.
+// ---------------------------------------------------------------------------------------
+#ifdef VCFX_EMU
+__device__ __forceinline__ uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c) {
+    return c + (a & 0xFFu) * (b & 0xFFu) + ((a >> 8) & 0xFFu) * ((b >> 8) & 0xFFu) + ((a >> 16) & 0xFFu) * ((b >> 16) & 0xFFu) + (a >> 24) * (b >> 24);
+}
+#else
+__device__ __forceinline__ uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c) { return __dp4a(a, b, c); }
+#endif
+constexpr uint32_t M80 = 0x80808080u;
+#define VCFX_GE(x, c) ((x) + (0x80808080u - 0x01010101u * (uint32_t)(c)))
+// markers moved up by one byte: byte i of the result = byte i - 1 of (prev : w)
+__device__ __forceinline__ uint32_t up1(uint32_t prev, uint32_t w) { return __funnelshift_l(prev, w, 8); }
+
+template <int OP> struct DigitClass { uint32_t adjc, D, NZ, SP, TB; };   // adjc: the class whose neighbours must not touch (AF: B, AC: digit)
+template <int OP>
+__device__ __forceinline__ DigitClass<OP> digit_classes(uint32_t x) {
+    DigitClass<OP> c;
+    const uint32_t g30 = VCFX_GE(x, 0x30), g31 = VCFX_GE(x, 0x31), g3a = VCFX_GE(x, 0x3A), g3b = VCFX_GE(x, 0x3B);
+    const uint32_t g09 = VCFX_GE(x, 0x09), g0a = VCFX_GE(x, 0x0A), g0b = VCFX_GE(x, 0x0B);
+    c.D = (g30 ^ g3a) & M80;
+    c.NZ = (g31 ^ g3a) & M80;
+    c.SP = (g0a ^ g0b ^ g3a ^ g3b) & M80;                       // '\n' ':'
+    if (OP == OP_AF) {
+        const uint32_t g2f = VCFX_GE(x, 0x2F), g7c = VCFX_GE(x, 0x7C), g7d = VCFX_GE(x, 0x7D);
+        c.adjc = (g09 ^ g0b ^ g2f ^ g30 ^ g7c ^ g7d) & M80;     // tab '\n' '/' '|'
+        c.TB = 0;
+    } else {
+        c.adjc = c.D;
+        c.TB = (g09 ^ g0a) & M80;
+    }
+    return c;
+}
+
+template <int OP>
+__device__ __forceinline__ bool line_digits(const uint8_t *__restrict__ tin, uint32_t wb, const uint32_t lo, const uint32_t nrel,
+                                         const bool strip_cr, uint32_t &out_a, uint32_t &out_b, uint32_t &out_tabs, uint32_t &out_e) {
+    const int lane = lane_id();
+    uint32_t accA = 0, accB = 0, accT = 0;               // 128 x count (the markers are 0x80 per byte)
+    uint32_t carry = 0;                                   // lane 0: class bits of the last byte of the window before
+    bool first = true;
+    uint4 cur = ld16(tin + wb + 16 * lane);
+    uint4 nxt = ld16(tin + wb + WINDOW + 16 * lane);
+    uint4 nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
+    for (;;) {
+        // counts of the window first (two registers instead of eight marker words across the vote): bytes pb-1 .. pb+14
+        // are this lane's digits
+        uint32_t tB, tA, tT = 0, odd, pk, adj_prev;
+        {
+            const DigitClass<OP> c3 = digit_classes<OP>(cur.w);
+            // this lane's last byte, for the lane to its right: bit 31 adjacency class, bit 30 digit, bit 29 non-zero digit
+            pk = (c3.adjc & 0x80000000u) | ((c3.D >> 1) & 0x40000000u) | ((c3.NZ >> 2) & 0x20000000u);
+            const DigitClass<OP> c2 = digit_classes<OP>(cur.z);
+            const uint32_t a3 = up1(c2.adjc, c3.adjc);
+            odd = ((OP == OP_AF) ? (~(c3.adjc | a3) & M80) : (c3.adjc & a3)) | c3.SP | c2.SP;
+            tB = dp4a_u(c3.D, 0x00010101u, dp4a_u(c2.D, 0x01010101u, 0u));
+            tA = dp4a_u(c3.NZ, 0x00010101u, dp4a_u(c2.NZ, 0x01010101u, 0u));
+            if (OP == OP_AC) tT = dp4a_u(c3.TB, 0x01010101u, dp4a_u(c2.TB, 0x01010101u, 0u));
+            const DigitClass<OP> c1 = digit_classes<OP>(cur.y);
+            const uint32_t a2 = up1(c1.adjc, c2.adjc);
+            odd |= ((OP == OP_AF) ? (~(c2.adjc | a2) & M80) : (c2.adjc & a2)) | c1.SP;
+            tB = dp4a_u(c1.D, 0x01010101u, tB); tA = dp4a_u(c1.NZ, 0x01010101u, tA);
+            if (OP == OP_AC) tT = dp4a_u(c1.TB, 0x01010101u, tT);
+            const DigitClass<OP> c0 = digit_classes<OP>(cur.x);
+            const uint32_t a1 = up1(c0.adjc, c1.adjc);
+            odd |= ((OP == OP_AF) ? (~(c1.adjc | a1) & M80) : (c1.adjc & a1)) | c0.SP;
+            tB = dp4a_u(c0.D, 0x01010101u, tB); tA = dp4a_u(c0.NZ, 0x01010101u, tA);
+            if (OP == OP_AC) tT = dp4a_u(c0.TB, 0x01010101u, tT);
+            adj_prev = c0.adjc;
+        }
+        uint32_t pv = __shfl_sync(FULL, pk, (lane + 31) & 31);
+        if (lane == 0) { const uint32_t t = pv; pv = carry; carry = t; }
+        {
+            const uint32_t a0 = up1(pv, adj_prev);
+            odd |= ((OP == OP_AF) ? (~(adj_prev | a0) & M80) : (adj_prev & a0)) | ((cur.x | cur.y | cur.z | cur.w) & M80);
+        }
+        if (!__any_sync(FULL, (odd != 0) | first)) {
+            accB += tB + ((pv >> 23) & 0x80u);
+            accA += tA + ((pv >> 22) & 0x80u);
+            if (OP == OP_AC) accT += tT;
+        } else {
+            // the first window (bytes before `lo` are not samples), the window with the '\n', or something odd
+            const uint32_t pb = wb + 16 * lane;
+            const uint32_t L = first ? lo : 0u;
+            const DigitClass<OP> c0 = digit_classes<OP>(cur.x), c1 = digit_classes<OP>(cur.y);
+            const DigitClass<OP> c2 = digit_classes<OP>(cur.z), c3 = digit_classes<OP>(cur.w);
+            const uint32_t a0 = up1(pv, c0.adjc), a1 = up1(c0.adjc, c1.adjc), a2 = up1(c1.adjc, c2.adjc), a3 = up1(c2.adjc, c3.adjc);
+            uint32_t j0, j1, j2, j3;                     // two bytes that must not touch, at the second one
+            if (OP == OP_AF) { j0 = ~(c0.adjc | a0) & M80; j1 = ~(c1.adjc | a1) & M80; j2 = ~(c2.adjc | a2) & M80; j3 = ~(c3.adjc | a3) & M80; }
+            else { j0 = c0.adjc & a0; j1 = c1.adjc & a1; j2 = c2.adjc & a2; j3 = c3.adjc & a3; }
+            uint32_t n0 = eq_bytes(cur.x, C_NL), n1 = eq_bytes(cur.y, C_NL), n2 = eq_bytes(cur.z, C_NL), n3 = eq_bytes(cur.w, C_NL);
+            if (first) clip4(n0, n1, n2, n3, pb, L, ~0u);
+            const unsigned ebal = __ballot_sync(FULL, (n0 | n1 | n2 | n3) != 0);
+            bool found = false;
+            uint32_t e = ~0u, ee = ~0u;                  // '\n'; end of the content (a stripped '\r' is not content)
+            if (ebal) {
+                const int src = __ffs(ebal) - 1;
+                int k = first_byte(n0, n1, n2, n3);
+                k = __shfl_sync(FULL, k, src);
+                e = wb + 16 * src + k; found = true; ee = e;
+                if (OP == OP_AF && strip_cr && e > lo && ldb(tin + e - 1) == '\r') ee = e - 1;
+            }
+            // digits at k in [L, ee) count; a pair (k-1, k) matters for k in [L, ee); a ':' or a high byte for k in [L, ee)
+            const uint32_t keep = lane_keep16(pb, L, ee);
+            const uint32_t k0 = nib80(keep, 0), k1 = nib80(keep, 1), k2 = nib80(keep, 2), k3 = nib80(keep, 3);
+            const uint32_t col = (eq_bytes(cur.x, 0x3A3A3A3Au) & k0) | (eq_bytes(cur.y, 0x3A3A3A3Au) & k1) |
+                                 (eq_bytes(cur.z, 0x3A3A3A3Au) & k2) | (eq_bytes(cur.w, 0x3A3A3A3Au) & k3);
+            const uint32_t bad = (j0 & k0) | (j1 & k1) | (j2 & k2) | (j3 & k3) | col | (cur.x & k0) | (cur.y & k1) | (cur.z & k2) | (cur.w & k3);
+            if (__any_sync(FULL, bad != 0)) return false;
+            // own bytes 0..14 that lie in [L, ee), and the byte before the lane if it does
+            const bool pin = pb != 0 && (pb - 1 >= L) && (pb - 1 < ee) && !(first && lane == 0);   // (lane 0 of the first window has no carry yet)
+            accB = dp4a_u(c0.D & k0, 0x01010101u, dp4a_u(c1.D & k1, 0x01010101u, dp4a_u(c2.D & k2, 0x01010101u, dp4a_u(c3.D & k3, 0x00010101u, accB + (pin ? ((pv >> 23) & 0x80u) : 0u)))));
+            accA = dp4a_u(c0.NZ & k0, 0x01010101u, dp4a_u(c1.NZ & k1, 0x01010101u, dp4a_u(c2.NZ & k2, 0x01010101u, dp4a_u(c3.NZ & k3, 0x00010101u, accA + (pin ? ((pv >> 22) & 0x80u) : 0u)))));
+            // (the last byte of lane 31 goes to the next window through `carry`; in the window with the '\n' it lies past it)
+            if (OP == OP_AC && !first) {
+                const uint32_t kt = lane_keep16(pb, 0u, e);
+                accT = dp4a_u(c0.TB & nib80(kt, 0), 0x01010101u, dp4a_u(c1.TB & nib80(kt, 1), 0x01010101u,
+                       dp4a_u(c2.TB & nib80(kt, 2), 0x01010101u, dp4a_u(c3.TB & nib80(kt, 3), 0x01010101u, accT))));
+            }
+            if (found) { out_a = accA >> 7; out_b = accB >> 7; out_tabs = accT >> 7; out_e = e; return true; }
+            first = false;
+        }
+        wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
+        if (((wb >> 9) & 7u) == 0) {                      // every 8th window: L2 prefetch of the 4 KB that follow
+            const uint32_t pf = wb + 10 * WINDOW + 128 * lane;
+            if (pf < nrel) prefetch_l2(tin + pf);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // K1: the fused scan / parse / reduce kernel
 // ---------------------------------------------------------------------------------------
-// variant_counter is light enough to run at 48 registers (5 CTAs per SM: +4.5 %); the parsing
-// instantiations need 64 to keep the steady loops free of spills (measured both ways, profiles/README.md)
-#ifndef VCFX_PARSE_CTAS
-#define VCFX_PARSE_CTAS 4
-#endif
-template <int OP>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (OP == OP_VC) ? 5 : VCFX_PARSE_CTAS)
-vcfx_scan_kernel(const KParams P) {
-    __shared__ uint32_t s_tp[WARPS_PER_CTA][12];
-    __shared__ __align__(16) uint8_t s_stage[(OP == OP_AC) ? WARPS_PER_CTA * (AC_STAGE + 32) : 16];
-    const int lane = lane_id();
-    const int wid = threadIdx.x >> 5;
-    volatile uint32_t *tp = s_tp[wid];
-    const uint64_t n = P.n;
-    const bool strip_cr = (OP == OP_HWE) || (P.mode == MODE_FILE && (OP == OP_AF || OP == OP_VC || OP == OP_MD));
+// Row-record slots are reserved REC_BLOCK at a time: one atomic on the single global counter per 32 rows
+// (one per row is the kernel's bottleneck: same-address atomics serialise in L2).  The block's state lives in
+// shared memory, only lane 0 touches it; the slots a warp leaves unused are marked invalid when it exits.
+__device__ __forceinline__ unsigned long long alloc_slot(unsigned long long *rec_base, unsigned int *rec_used, DevStats *stats) {   // lane 0 only
+    unsigned int used = *rec_used;
+    if (used == REC_BLOCK) { *rec_base = atomicAdd(&stats->n_recs, (unsigned long long)REC_BLOCK); used = 0; }
+    *rec_used = used + 1;
+    return *rec_base + used;
+}
+
+// what a warp keeps in shared memory (pointers to this warp's entries)
+struct WarpShared {
+    volatile uint32_t *tp;                 // positions of tabs 1..9 of the current line
+    uint8_t *stage0;                       // allele_counter row staging
+    unsigned int *cnt;                     // event counters (CNT_SLOTS)
+    unsigned long long *rec_base; unsigned int *rec_used;
+    volatile unsigned int *odd, *reg, *tag;   // [WARPS_PER_CTA] arrays (indexed by the warp)
+};
+// what a warp carries from line to line inside a tile
+template <int OP> struct TileState {
+    uint32_t ls, nlines;
+    typename OutCount<OP>::type out_bytes;  // only allele_counter's per-sample rows can exceed 32 bits (input offsets cannot)
+    uint32_t md_prev_end, md_last_end;      // MISSING_DETECT: end of the last rewritten line / of the last line
+    bool md_add_nl;
+    uint32_t offlattice_lines;              // VAR 1: lines whose first sample window was not on the tier-1 lattice
+};
+
+// Every line that starts in the tile, from st.ls on.  Two variants of the same text for allele_freq_calc and hwe_tester
+// (both inlined into the kernel, so that neither pays for the other's registers):
+//   VAR 0  the lattice variant: tier 1 + the exact path.  It stops — returning false with st.ls at the line, nothing
+//          of it consumed — at the first line whose first sample window is not tier-1 material
+//   VAR 1  the general variant: the same plus the digit path and the skip-ahead loop for FORMATs with several keys;
+//          it runs to the end of the tile
+// The other operations have one variant (VAR 0, never stops early).
+template <int OP, int VAR>
+__device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws, const int lane, const bool strip_cr,
+                                           const uint32_t tile, const uint64_t a, const uint64_t a0, const uint8_t *__restrict__ tin,
+                                           const uint32_t rb, const uint32_t nrel, const uint64_t n, TileState<OP> &st) {
+    constexpr bool HAS_VAR = (OP == OP_AF || OP == OP_HWE);
     constexpr int NEED_TABS = (OP == OP_VC) ? 7 : 9;        // the header phase ends once this many tabs are ranked
-    if (OP == OP_AC && P.ac_pass && P.stats->overflow) return;
-
-    // per-warp event counters live in shared memory (fire-and-forget adds from lane 0) and are folded into
-    // DevStats after every tile; the slot index is the field's index in DevStats
-    __shared__ unsigned int s_cnt[WARPS_PER_CTA][CNT_SLOTS];
-    if (lane < CNT_SLOTS) s_cnt[wid][lane] = 0;
-    __syncwarp();
-#define VCFX_COUNT(slot, v) do { if (lane == 0) atomicAdd(&s_cnt[wid][slot], (unsigned int)(v)); } while (0)
-    // Row-record slots are reserved REC_BLOCK at a time: one atomic on the single global counter per 32 rows
-    // (one per row is the kernel's bottleneck: same-address atomics serialise in L2).  The block's state lives in
-    // shared memory, only lane 0 touches it; the slots a warp leaves unused are marked invalid when it exits.
-    __shared__ unsigned long long s_rec_base[WARPS_PER_CTA];
-    __shared__ unsigned int s_rec_used[WARPS_PER_CTA];
-    __shared__ volatile unsigned int s_odd[WARPS_PER_CTA], s_reg[WARPS_PER_CTA], s_tag[WARPS_PER_CTA];
-    if (lane == 0) s_tag[wid] = 0;
-    if (lane == 0) { s_rec_base[wid] = 0; s_rec_used[wid] = REC_BLOCK; }
-    __syncwarp();
-    auto alloc_slot_lane0 = [&]() -> unsigned long long {       // call from lane 0 only
-        unsigned int used = s_rec_used[wid];
-        if (used == REC_BLOCK) { s_rec_base[wid] = atomicAdd(&P.stats->n_recs, (unsigned long long)REC_BLOCK); used = 0; }
-        s_rec_used[wid] = used + 1;
-        return s_rec_base[wid] + used;
-    };
-
-    for (;;) {
-        uint32_t tile = 0;
-        if (lane == 0) tile = atomicAdd(P.ticket, 1u);
-        tile = __shfl_sync(FULL, tile, 0);
-        if (tile >= P.n_tiles) break;
-
-        const uint64_t a = (uint64_t)tile * P.tile_bytes;
-        const uint64_t b = min(a + (uint64_t)P.tile_bytes, n);
-        // every position inside the tile's work is a 32-bit offset from a0 (16-aligned, <= a-1)
-        const uint64_t a0 = a - (tile ? 16u : 0u);             // tile_bytes is a multiple of 512, so a is 16-aligned
-        const uint8_t *__restrict__ tin = P.in + a0;
-        const uint32_t ra = (uint32_t)(a - a0), rb = (uint32_t)(b - a0);
-        const uint32_t nrel = (uint32_t)min(n - a0, (uint64_t)0xFFFFFFFFu);   // chunk end as an offset from a0 (clamped)
-
-        // ---- first line start in [a, b): byte 0 of the chunk, or one past a '\n' at >= a-1
-        uint32_t ls = rb;                                   // "none"
-        if (a == 0) ls = 0;
-        else {
-            const uint32_t from = ra - 1, to = rb - 1;      // '\n' positions that give a start < b
-            uint32_t wb = from & ~15u;
-            while (wb < to) {
-                const uint32_t pb = wb + 16 * lane;
-                uint4 v = ld16(tin + pb);
-                uint32_t m0 = eq_bytes(v.x, C_NL), m1 = eq_bytes(v.y, C_NL), m2 = eq_bytes(v.z, C_NL), m3 = eq_bytes(v.w, C_NL);
-                clip4(m0, m1, m2, m3, pb, from, to);
-                unsigned bal = __ballot_sync(FULL, (m0 | m1 | m2 | m3) != 0);
-                if (bal) {
-                    int src = __ffs(bal) - 1;
-                    int k = first_byte(m0, m1, m2, m3);
-                    k = __shfl_sync(FULL, k, src);
-                    ls = wb + 16 * src + k + 1;
-                    break;
-                }
-                wb += WINDOW;
-            }
-        }
-
-        uint32_t nlines = 0;
-        s_tag[wid] = 0;                                     // no line of this tile has used the exact-path counters yet
-        // output bytes of the tile: only allele_counter's per-sample rows can exceed 32 bits (input offsets cannot)
-        typename OutCount<OP>::type out_bytes = 0;
-        uint32_t md_prev_end = ls, md_last_end = ls;   // MISSING_DETECT: end of the last rewritten line / of the last line
-        bool md_add_nl = false;
-
+    volatile uint32_t *tp = ws.tp;
+    const int wid = threadIdx.x >> 5;
+    volatile unsigned int *s_odd = ws.odd, *s_reg = ws.reg, *s_tag = ws.tag;
+    uint32_t ls = st.ls, nlines = st.nlines;
+    typename OutCount<OP>::type out_bytes = st.out_bytes;
+    uint32_t md_prev_end = st.md_prev_end, md_last_end = st.md_last_end;
+    bool md_add_nl = st.md_add_nl;
+#define VCFX_COUNT(slot, v) do { if (lane == 0) atomicAdd(&ws.cnt[slot], (unsigned int)(v)); } while (0)
+#define VCFX_SAVE_STATE() do { st.ls = ls; st.nlines = nlines; st.out_bytes = out_bytes; st.md_prev_end = md_prev_end; st.md_last_end = md_last_end; st.md_add_nl = md_add_nl; } while (0)
         // ---- every line that starts in the tile
         while (ls < rb) {
             uint32_t wb = ls & ~15u;
@@ -643,6 +753,7 @@ vcfx_scan_kernel(const KParams P) {
             // ================= sample phase
             if ((OP == OP_AF || OP == OP_HWE) && do_samples) {
                 bool first_win = true;             // `cur` is the window in which tab 9 was ranked
+                bool digits_tried = false;
                 bool prev_ok = false;              // the previous window ended on a verified lattice lane
                 // Tier 1 speculation for the whole line: every sample is "a<sep>b" with a, b in {0,1} and the
                 // separator of the first sample, hence a tab every 4 bytes at a phase (tau) that is the same
@@ -680,40 +791,67 @@ vcfx_scan_kernel(const KParams P) {
                         wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
                     }
                 }
+                // ---- not tier-1 material from the first sample window on: the lattice variant hands the line (and the
+                // rest of the tile) to the general variant; nothing of the line has been counted yet
+                if (HAS_VAR && !found && first_win) {
+                    if (VAR == 0) { VCFX_SAVE_STATE(); return false; }
+                    ++st.offlattice_lines;
+                }
                 for (;;) {
-                    // ---- steady state for a FORMAT with several keys (GT first): samples are tens of bytes long,
-                    // a lane holds at most one sample start.  Tab and newline masks, one vote, and the lanes that
-                    // hold a tab classify the four bytes after it.  The window with the '\n', lanes with two tabs
-                    // and unusual genotypes are left to the exact path below.
-                    if (!first_win && !lat_possible && gt_index == 0) {
+                    // ---- steady state for a FORMAT with several keys (GT first): samples are tens of bytes long, so a
+                    // lane holds at most one sample start and almost all bytes only have to be searched for tabs.  Per
+                    // word: tab and '\n' markers by range (3 adds, 2 LOP3).  A lane that holds a tab fetches the four
+                    // bytes behind it (two aligned loads from L1: the load pipe is idle here) and decides the sample from
+                    // them.  The window with the '\n', a lane with two tabs, a byte >= 0x80 and every genotype that
+                    // needs more than four bytes leave the loop with nothing added, for the exact path below.
+                    if (VAR == 1 && !first_win && !lat_possible && gt_index == 0) {
                         for (;;) {
-                            const uint32_t m0 = eq_bytes(cur.x, C_TAB), m1 = eq_bytes(cur.y, C_TAB);
-                            const uint32_t m2 = eq_bytes(cur.z, C_TAB), m3 = eq_bytes(cur.w, C_TAB);
-                            const uint32_t nn = eq_bytes(cur.x, C_NL) | eq_bytes(cur.y, C_NL) | eq_bytes(cur.z, C_NL) | eq_bytes(cur.w, C_NL);
-                            const uint32_t mall = m0 | m1 | m2 | m3;
-                            bool odd = nn != 0;                  // this window is not for the fast loop
+                            uint32_t tm0, tm1, tm2, tm3, nl;
+                            {
+                                const uint32_t a0_ = VCFX_GE(cur.x, 0x09), b0_ = VCFX_GE(cur.x, 0x0A), c0_ = VCFX_GE(cur.x, 0x0B);
+                                const uint32_t a1_ = VCFX_GE(cur.y, 0x09), b1_ = VCFX_GE(cur.y, 0x0A), c1_ = VCFX_GE(cur.y, 0x0B);
+                                const uint32_t a2_ = VCFX_GE(cur.z, 0x09), b2_ = VCFX_GE(cur.z, 0x0A), c2_ = VCFX_GE(cur.z, 0x0B);
+                                const uint32_t a3_ = VCFX_GE(cur.w, 0x09), b3_ = VCFX_GE(cur.w, 0x0A), c3_ = VCFX_GE(cur.w, 0x0B);
+                                tm0 = (a0_ ^ b0_) & M80; tm1 = (a1_ ^ b1_) & M80; tm2 = (a2_ ^ b2_) & M80; tm3 = (a3_ ^ b3_) & M80;
+                                nl = ((b0_ ^ c0_) | (b1_ ^ c1_) | (b2_ ^ c2_) | (b3_ ^ c3_) | cur.x | cur.y | cur.z | cur.w) & M80;   // '\n' or a high byte
+                            }
+                            bool odd = nl != 0;                  // this window is not for the fast loop
                             uint32_t da = 0, db = 0, dc = 0;
-                            // look-ahead word (needed by lanes whose tab sits in the last bytes)
-                            uint32_t la = __shfl_down_sync(FULL, cur.x, 1);
-                            const uint32_t nx0 = __shfl_sync(FULL, nxt.x, 0);
-                            if (lane == 31) la = nx0;
-                            if (mall) {
-                                if (__popc(m0) + __popc(m1) + __popc(m2) + __popc(m3) == 1) {
-                                    const int B = first_byte(m0, m1, m2, m3);
-                                    const uint32_t lo_ = B < 4 ? cur.x : B < 8 ? cur.y : B < 12 ? cur.z : cur.w;
-                                    const uint32_t hi_ = B < 4 ? cur.y : B < 8 ? cur.z : B < 12 ? cur.w : la;
-                                    const uint32_t q = __funnelshift_rc(lo_, hi_, 8u * (uint32_t)((B & 3) + 1));
-                                    const uint32_t b0 = q & 0xFF, b1 = (q >> 8) & 0xFF, b2 = (q >> 16) & 0xFF, b3 = q >> 24;
-                                    if (OP == OP_AF) {
-                                        const bool t3 = (b3 == '\t' || b3 == ':' || b3 == '\n');
-                                        if (is_dig(b0) && is_sep(b1) && is_dig(b2) && t3) { db = 2; da = (uint32_t)(b0 != '0') + (uint32_t)(b2 != '0'); }
-                                        else if (!(b0 == '.' && is_sep(b1) && b2 == '.' && t3)) odd = true;
-                                    } else {
-                                        if (is_dig(b0) && is_sep(b1) && is_dig(b2) && !is_dig(b3)) {
-                                            if (b0 <= '1' && b2 <= '1') { const uint32_t c = (b0 - '0') + (b2 - '0'); da = (c == 0); db = (c == 1); dc = (c == 2); }
-                                        } else if (b0 != '.') odd = true;
-                                    }
-                                } else odd = true;
+                            if (tm0 | tm1 | tm2 | tm3) {
+                                // one bit per byte of the lane (see the header phase), then the first tab's byte index
+                                const uint32_t m16 = ((tm0 * 0x00204081u) >> 28) | (((tm1 * 0x00204081u) >> 24) & 0xF0u) |
+                                                     (((tm2 * 0x00204081u) >> 20) & 0xF00u) | (((tm3 * 0x00204081u) >> 16) & 0xF000u);
+                                if (m16 & (m16 - 1u)) odd = true;   // two sample starts in 16 bytes
+                                const uint8_t *p = tin + wb + 16 * lane + __ffs(m16);        // first byte of the sample
+                                const uint32_t *p4 = reinterpret_cast<const uint32_t *>((uintptr_t)p & ~(uintptr_t)3);
+                                const uint32_t q = __funnelshift_r(__ldg(p4), __ldg(p4 + 1), 8u * (uint32_t)((uintptr_t)p & 3));
+                                const uint32_t g30 = VCFX_GE(q, 0x30), g31 = VCFX_GE(q, 0x31), g3a = VCFX_GE(q, 0x3A);
+                                const uint32_t g2f = VCFX_GE(q, 0x2F), g7c = VCFX_GE(q, 0x7C), g7d = VCFX_GE(q, 0x7D);
+                                const uint32_t D = (g30 ^ g3a) & M80, S = (g2f ^ g30 ^ g7c ^ g7d) & M80;
+                                if (q & M80) odd = true;
+                                if (OP == OP_AF) {
+                                    // allele_freq_calc.cpp:262-293 on "t sep t <end>" and "t <end>", t a digit or '.', <end> = tab ':' '\n'
+                                    const uint32_t g09 = VCFX_GE(q, 0x09), g0b = VCFX_GE(q, 0x0B), g3b = VCFX_GE(q, 0x3B), g2e = VCFX_GE(q, 0x2E);
+                                    const uint32_t E = (g09 ^ g0b ^ g3a ^ g3b) & M80, NZ = (g31 ^ g3a) & M80, TK = ((g2e ^ g2f) | D) & M80;
+                                    if (((TK & 0x00800080u) | (S & 0x00008000u) | (E & 0x80000000u)) == M80) {
+                                        db = __popc(D & 0x00800080u); da = __popc(NZ & 0x00800080u);
+                                    } else if (((TK & 0x00000080u) | (E & 0x00008000u)) == 0x00008080u) {
+                                        db = (D >> 7) & 1u; da = (NZ >> 7) & 1u;
+                                    } else odd = true;
+                                } else {
+                                    // hwe_tester.cpp:339-378 on the four bytes: digit sep digit non-digit is a call (alleles <= 1 count);
+                                    // a second digit in either place or a leading blank needs the scalar parser; the rest is no call
+                                    const uint32_t g32 = VCFX_GE(q, 0x32);
+                                    const uint32_t O = (g31 ^ g32) & M80, L1 = (g30 ^ g32) & M80;
+                                    const uint32_t b0 = q & 0xFFu;
+                                    if ((D & 0x00000080u) && (S & 0x00008000u) && (D & 0x00800000u)) {
+                                        if (D & 0x80000000u) odd = true;
+                                        else if ((L1 & 0x00800080u) == 0x00800080u) {
+                                            const uint32_t c = __popc(O & 0x00800080u);
+                                            da = (c == 0); db = (c == 1); dc = (c == 2);
+                                        }
+                                    } else if (((D & 0x00008080u) == 0x00008080u) || b0 == ' ' || b0 == '\r') odd = true;
+                                }
                             }
                             if (__any_sync(FULL, odd)) break;    // nothing was added for this window
                             ta += da; tb += db; tc += dc;
@@ -833,6 +971,20 @@ vcfx_scan_kernel(const KParams P) {
                         }
                         if (OP == OP_AF) { ta += (accp & 0xFFFFu) + (accp >> 16); accp = 0; }
                         if (finished) break;
+                    }
+                    // ---- off the lattice.  FORMAT "GT": the digit path takes the rest of the line (once per line; when it
+                    // declines, nothing of it is kept and the exact path below starts at this very window).  It may only
+                    // start where the bytes before are accounted for: at tab 9, or behind windows verified on the line's
+                    // lattice, whose last sample ends with the tab at wb + tau.
+                    if (VAR == 1 && OP == OP_AF && lat_possible && !digits_tried && !found && (first_win || prev_ok)) {
+                        digits_tried = true;
+                        uint32_t da = 0, db = 0, dt = 0, de = 0;
+                        if (line_digits<OP_AF>(tin, wb, first_win ? tab8 + 1u : wb + tau + 1u, nrel, strip_cr, da, db, dt, de)) {
+                            ta += da; tb += db; e = de; found = true;
+                            break;
+                        }
+                        // (declined: the windows are loaded again rather than kept in registers across the call)
+                        cur = ld16(tin + wb + 16 * lane); nxt = ld16(tin + wb + WINDOW + 16 * lane); nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
                     }
                     // ---- this window needs a closer look
                     const uint32_t pb = wb + 16 * lane;
@@ -985,6 +1137,17 @@ vcfx_scan_kernel(const KParams P) {
             if (OP == OP_AC && !hash && tabs >= 9 && !ac_sizing_only) {
                 uint2 *scr = P.col_scratch + (size_t)(blockIdx.x * WARPS_PER_CTA + wid) * P.max_col;
                 bool firstw = true;
+                // -a over all the samples, FORMAT "GT": the digit path sums the whole line (every sample column must be
+                // a selected one; when it declines, the loop below does the line)
+                bool summed = false;
+                if (P.ac_fmt == AC_AGG && P.ac_ident && !found && tp[8] - tp[7] == 3 && ldb(tin + tp[7] + 1) == 'G' && ldb(tin + tp[7] + 2) == 'T') {
+                    uint32_t da = 0, db = 0, dt = 0, de = 0;
+                    if (line_digits<OP_AC>(tin, wb, tp[8] + 1u, nrel, false, da, db, dt, de) &&
+                        (uint32_t)__reduce_add_sync(FULL, dt) + (uint32_t)tabs <= 8u + P.n_sel) {
+                        ta = db - da; tb = da; tabs += (int)__reduce_add_sync(FULL, dt); e = de; found = true; summed = true;
+                    }
+                }
+                if (!summed)
                 for (;;) {
                     const uint32_t pb = wb + 16 * lane;
                     uint32_t m0, m1, m2, m3;
@@ -1185,7 +1348,7 @@ vcfx_scan_kernel(const KParams P) {
                     const uint32_t prefix_len = tp[4] + 1 - ls;
                     const uint32_t row_len = prefix_len + ((OP == OP_AF) ? 7u : 9u);
                     unsigned long long slot = 0;
-                    if (lane == 0) slot = alloc_slot_lane0();
+                    if (lane == 0) slot = alloc_slot(ws.rec_base, ws.rec_used, P.stats);
                     slot = __shfl_sync(FULL, slot, 0);
                     if (slot < P.rec_cap) {
                         if (lane == 0) {
@@ -1231,7 +1394,7 @@ vcfx_scan_kernel(const KParams P) {
                         sr = __reduce_add_sync(FULL, sr); sa = __reduce_add_sync(FULL, sa);
                         const uint32_t row_len = prefix_len + dec_len((int)sr) + 1 + dec_len((int)sa) + 1 + dec_len((int)n_rows) + 1;
                         if (lane == 0) {
-                            unsigned long long slot = alloc_slot_lane0();
+                            unsigned long long slot = alloc_slot(ws.rec_base, ws.rec_used, P.stats);
                             if (slot < P.rec_cap) {
                                 Rec r; r.tile = tile; r.ls_rel = (uint32_t)(a0 + ls - a); r.prefix_len = prefix_src;
                                 r.off_in_tile = (uint32_t)out_bytes; r.a = sr; r.b = sa; r.c = n_rows; r.d = extra_tabs;
@@ -1240,7 +1403,7 @@ vcfx_scan_kernel(const KParams P) {
                         }
                         out_bytes += row_len; VCFX_COUNT(C_ROWS, 1);
                     } else {
-                        uint8_t *stage0 = s_stage + wid * (AC_STAGE + 32);
+                        uint8_t *stage0 = ws.stage0;
                         uint32_t n_rows_done = 0;
                         unsigned long long opos = (P.ac_pass ? P.tile_base[tile] : 0ULL) + out_bytes;
                         const bool text = (P.ac_fmt != AC_BIN);
@@ -1305,7 +1468,7 @@ vcfx_scan_kernel(const KParams P) {
                     else mod_len = content_len + 19 + ((ldb(tin + tp[7] - 1) != ';') ? 1u : 0u);
                     mod_len += 1;                                        // the rewritten line always ends with '\n'
                     if (lane == 0) {
-                        unsigned long long slot = alloc_slot_lane0();
+                        unsigned long long slot = alloc_slot(ws.rec_base, ws.rec_used, P.stats);
                         if (slot < P.rec_cap) {
                             Rec r; r.tile = tile; r.ls_rel = (uint32_t)(a0 + ls - a); r.prefix_len = (uint32_t)(a0 + md_prev_end - a);
                             r.off_in_tile = (uint32_t)out_bytes; r.a = info_off; r.b = info_len; r.c = content_len; r.d = mod_len;
@@ -1322,6 +1485,97 @@ vcfx_scan_kernel(const KParams P) {
             __syncwarp();
             ls = e + 1;
         }
+    VCFX_SAVE_STATE();
+    return true;
+#undef VCFX_COUNT
+#undef VCFX_SAVE_STATE
+}
+
+// variant_counter is light enough to run at 48 registers (5 CTAs per SM: +4.5 %); the parsing
+// instantiations need 64 to keep the steady loops free of spills (measured both ways, profiles/README.md)
+#ifndef VCFX_PARSE_CTAS
+#define VCFX_PARSE_CTAS 4
+#endif
+template <int OP>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (OP == OP_VC) ? 5 : VCFX_PARSE_CTAS)
+vcfx_scan_kernel(const KParams P) {
+    __shared__ uint32_t s_tp[WARPS_PER_CTA][12];
+    __shared__ __align__(16) uint8_t s_stage[(OP == OP_AC) ? WARPS_PER_CTA * (AC_STAGE + 32) : 16];
+    const int lane = lane_id();
+    const int wid = threadIdx.x >> 5;
+    const uint64_t n = P.n;
+    const bool strip_cr = (OP == OP_HWE) || (P.mode == MODE_FILE && (OP == OP_AF || OP == OP_VC || OP == OP_MD));
+    if (OP == OP_AC && P.ac_pass && P.stats->overflow) return;
+
+    // per-warp event counters live in shared memory (fire-and-forget adds from lane 0) and are folded into
+    // DevStats after every tile; the slot index is the field's index in DevStats
+    __shared__ unsigned int s_cnt[WARPS_PER_CTA][CNT_SLOTS];
+    if (lane < CNT_SLOTS) s_cnt[wid][lane] = 0;
+    __syncwarp();
+#define VCFX_COUNT(slot, v) do { if (lane == 0) atomicAdd(&s_cnt[wid][slot], (unsigned int)(v)); } while (0)
+    __shared__ unsigned long long s_rec_base[WARPS_PER_CTA];
+    __shared__ unsigned int s_rec_used[WARPS_PER_CTA];
+    __shared__ volatile unsigned int s_odd[WARPS_PER_CTA], s_reg[WARPS_PER_CTA], s_tag[WARPS_PER_CTA];
+    if (lane == 0) s_tag[wid] = 0;
+    if (lane == 0) { s_rec_base[wid] = 0; s_rec_used[wid] = REC_BLOCK; }
+    __syncwarp();
+    WarpShared ws;
+    ws.tp = s_tp[wid]; ws.stage0 = s_stage + ((OP == OP_AC) ? wid * (AC_STAGE + 32) : 0); ws.cnt = s_cnt[wid];
+    ws.rec_base = &s_rec_base[wid]; ws.rec_used = &s_rec_used[wid]; ws.odd = s_odd; ws.reg = s_reg; ws.tag = s_tag;
+    int var = 0;                                 // allele_freq_calc / hwe_tester: the variant the next tile starts with
+
+    for (;;) {
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(P.ticket, 1u);
+        tile = __shfl_sync(FULL, tile, 0);
+        if (tile >= P.n_tiles) break;
+
+        const uint64_t a = (uint64_t)tile * P.tile_bytes;
+        const uint64_t b = min(a + (uint64_t)P.tile_bytes, n);
+        // every position inside the tile's work is a 32-bit offset from a0 (16-aligned, <= a-1)
+        const uint64_t a0 = a - (tile ? 16u : 0u);             // tile_bytes is a multiple of 512, so a is 16-aligned
+        const uint8_t *__restrict__ tin = P.in + a0;
+        const uint32_t ra = (uint32_t)(a - a0), rb = (uint32_t)(b - a0);
+        const uint32_t nrel = (uint32_t)min(n - a0, (uint64_t)0xFFFFFFFFu);   // chunk end as an offset from a0 (clamped)
+
+        // ---- first line start in [a, b): byte 0 of the chunk, or one past a '\n' at >= a-1
+        uint32_t ls = rb;                                   // "none"
+        if (a == 0) ls = 0;
+        else {
+            const uint32_t from = ra - 1, to = rb - 1;      // '\n' positions that give a start < b
+            uint32_t wb = from & ~15u;
+            while (wb < to) {
+                const uint32_t pb = wb + 16 * lane;
+                uint4 v = ld16(tin + pb);
+                uint32_t m0 = eq_bytes(v.x, C_NL), m1 = eq_bytes(v.y, C_NL), m2 = eq_bytes(v.z, C_NL), m3 = eq_bytes(v.w, C_NL);
+                clip4(m0, m1, m2, m3, pb, from, to);
+                unsigned bal = __ballot_sync(FULL, (m0 | m1 | m2 | m3) != 0);
+                if (bal) {
+                    int src = __ffs(bal) - 1;
+                    int k = first_byte(m0, m1, m2, m3);
+                    k = __shfl_sync(FULL, k, src);
+                    ls = wb + 16 * src + k + 1;
+                    break;
+                }
+                wb += WINDOW;
+            }
+        }
+
+        s_tag[wid] = 0;                                     // no line of this tile has used the exact-path counters yet
+        TileState<OP> st;
+        st.ls = ls; st.nlines = 0; st.out_bytes = 0; st.md_prev_end = ls; st.md_last_end = ls; st.md_add_nl = false; st.offlattice_lines = 0;
+        if (OP == OP_AF || OP == OP_HWE) {
+            if (var == 0 && !tile_lines<OP, 0>(P, ws, lane, strip_cr, tile, a, a0, tin, rb, nrel, n, st)) var = 1;
+            if (var == 1) {
+                tile_lines<OP, 1>(P, ws, lane, strip_cr, tile, a, a0, tin, rb, nrel, n, st);
+                if (st.offlattice_lines == 0) var = 0;      // nothing but lattice lines: the next tile starts with the lattice variant
+            }
+        } else tile_lines<OP, 0>(P, ws, lane, strip_cr, tile, a, a0, tin, rb, nrel, n, st);
+        const uint32_t nlines = st.nlines;
+        typename OutCount<OP>::type out_bytes = st.out_bytes;
+        const uint32_t md_prev_end = st.md_prev_end, md_last_end = st.md_last_end;
+        const bool md_add_nl = st.md_add_nl;
+
         if (!(OP == OP_AC && P.ac_pass)) VCFX_COUNT(C_LINES, nlines);
         if (OP == OP_MD) {
             const uint32_t tail = md_last_end - md_prev_end;

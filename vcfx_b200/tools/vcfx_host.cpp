@@ -67,18 +67,20 @@ void Source::enable_gzip() {
 // below what the PCIe link takes.  Pipes, gzip streams and small reads keep
 // the single read(2).
 long Source::parallel_read(char *dst, size_t cap) {
-    if (file_size_ < 0) {
+    if (!io_init_) {
+        io_init_ = true;
         struct stat st;
-        file_size_ = -2;                                    // "not a regular file"
-        if (fstat(fd_, &st) == 0 && S_ISREG(st.st_mode)) {
-            const off_t cur = lseek(fd_, 0, SEEK_CUR);
-            if (cur >= 0) { file_size_ = st.st_size; file_off_ = cur; }
-        }
+        file_size_ = -1;                                    // "not a regular file"
+        if (fstat(fd_, &st) == 0 && S_ISREG(st.st_mode) && lseek(fd_, 0, SEEK_CUR) >= 0) file_size_ = st.st_size;
         const char *e = getenv("VCFX_IO_THREADS");
         unsigned hw = std::thread::hardware_concurrency();
         io_threads_ = e ? std::max(1, atoi(e)) : (int)std::min(8u, std::max(1u, hw));
     }
     if (file_size_ < 0 || io_threads_ <= 1) return -2;
+    // the descriptor's own offset is the one source of truth: small reads in between go through read(2) and move it
+    const off_t cur = lseek(fd_, 0, SEEK_CUR);
+    if (cur < 0) return -2;
+    file_off_ = cur;
     const long long left = file_size_ - file_off_;
     if (left <= 0) return 0;
     const size_t n = (size_t)std::min<long long>((long long)cap, left);

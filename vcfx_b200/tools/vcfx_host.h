@@ -32,7 +32,8 @@ class Source {
     long raw_read(char *dst, size_t cap);
     long parallel_read(char *dst, size_t cap);   // -2: not applicable (pipe, small read, one thread)
     int fd_;
-    long long file_size_ = -1, file_off_ = 0;    // regular files only (-1: not looked at yet)
+    long long file_size_ = -1, file_off_ = 0;    // regular files only (-1: not a regular file)
+    bool io_init_ = false;
     int io_threads_ = 1;
     std::string peek_;                    // bytes read ahead by sniff/peek
     size_t peek_pos_ = 0;
