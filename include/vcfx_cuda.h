@@ -176,6 +176,12 @@ int vcfx_cuda_run_device(vcfx_ctx *ctx, void *d_in, size_t nbytes, const vcfx_ch
                          void *d_out, size_t out_cap);
 int vcfx_cuda_sync(vcfx_ctx *ctx, vcfx_chunk_stats *stats);
 
+/* hwe_tester's p-value (VCFX_hwe_tester.cpp:278-315 chi2_pvalue_1df + calculateHWE_chisq) evaluated ON THE DEVICE
+ * for n (hom_ref, het, hom_alt) triples: counts[3*i .. 3*i+2] -> pvalues[i] (host arrays).  It is the same device
+ * code the row formatter runs; exported so that the difference to the reference's libm arithmetic can be measured
+ * and reported (BASELINE.json: any HWE p-value difference must stay within 1e-12 relative and be reported). */
+int vcfx_cuda_hwe_pvalues(int device, const int32_t *counts, size_t n, double *pvalues);
+
 #ifdef __cplusplus
 }
 #endif

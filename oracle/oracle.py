@@ -56,6 +56,8 @@ def lib():
             getattr(l, name).restype = C.c_int
         l.oracle_hwe_pvalue.argtypes = [C.c_int, C.c_int, C.c_int]
         l.oracle_hwe_pvalue.restype = C.c_double
+        l.oracle_hwe_pvalues.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        l.oracle_hwe_pvalues.restype = None
         l.oracle_hwe_class.argtypes = [C.c_char_p, C.c_size_t]
         l.oracle_gt_index.argtypes = [C.c_char_p, C.c_size_t]
         l.oracle_af_counts.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -102,6 +104,27 @@ def fmt(kind: str, v: float) -> bytes:
 
 def hwe_pvalue(hr: int, het: int, ha: int) -> float:
     return lib().oracle_hwe_pvalue(hr, het, ha)
+
+
+def p_text_diffs(a, b):
+    """(#pairs whose FILE-mode text differs, #pairs whose "%.6f" text differs) for two float64 arrays."""
+    import numpy as np
+    a = np.ascontiguousarray(a, dtype=np.float64); b = np.ascontiguousarray(b, dtype=np.float64)
+    fd, sd = C.c_size_t(0), C.c_size_t(0)
+    l = lib()
+    l.oracle_p_text_diffs.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    l.oracle_p_text_diffs.restype = None
+    l.oracle_p_text_diffs(a.ctypes.data, b.ctypes.data, len(a), C.byref(fd), C.byref(sd))
+    return fd.value, sd.value
+
+
+def hwe_pvalues(counts):
+    """counts: int32 array [n, 3] (homRef, het, homAlt) -> float64 array [n], the reference's arithmetic (glibc exp)."""
+    import numpy as np
+    c = np.ascontiguousarray(counts, dtype=np.int32).reshape(-1, 3)
+    out = np.empty(len(c), dtype=np.float64)
+    lib().oracle_hwe_pvalues(c.ctypes.data, len(c), out.ctypes.data)
+    return out
 
 
 # ---------------------------------------------------------------- compiled reference tools

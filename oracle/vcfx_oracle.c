@@ -268,6 +268,23 @@ int oracle_hwe_class(const char *p, size_t n) {
 
 /* hwe_tester.cpp:290-315 and :278-287 — Yates-corrected chi-square, 1-df p-value by the
  * Abramowitz-Stegun 7.1.26 erfc polynomial.  Operation order is kept term by term. */
+/* how many of n value pairs print differently as FILE-mode text (truncated, hwe_tester.cpp:236-268) and as "%.6f" */
+void oracle_p_text_diffs(const double *a, const double *b, size_t n, size_t *file_diffs, size_t *stdin_diffs) {
+    size_t fd = 0, sd = 0;
+    for (size_t i = 0; i < n; ++i) {
+        char x[64], y[64];
+        int lx = oracle_fmt_p_file(a[i], x), ly = oracle_fmt_p_file(b[i], y);
+        if (lx != ly || memcmp(x, y, (size_t)lx) != 0) ++fd;
+        lx = oracle_fmt_p_stdin(a[i], x); ly = oracle_fmt_p_stdin(b[i], y);
+        if (lx != ly || memcmp(x, y, (size_t)lx) != 0) ++sd;
+    }
+    *file_diffs = fd; *stdin_diffs = sd;
+}
+
+void oracle_hwe_pvalues(const int *counts, size_t n, double *out) {
+    for (size_t i = 0; i < n; ++i) out[i] = oracle_hwe_pvalue(counts[3 * i], counts[3 * i + 1], counts[3 * i + 2]);
+}
+
 double oracle_hwe_pvalue(int hr, int het, int ha) {
     int N = hr + het + ha;
     if (N < 1) return 1.0;

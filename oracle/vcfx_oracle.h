@@ -59,6 +59,8 @@ int    oracle_fmt_af_stdin(double v, char *dst);  /* "%.4f" */
 int    oracle_fmt_p_file(double v, char *dst);    /* appendDouble twin (truncating) */
 int    oracle_fmt_p_stdin(double v, char *dst);   /* "%.6f" */
 double oracle_hwe_pvalue(int hom_ref, int het, int hom_alt);
+void   oracle_hwe_pvalues(const int *counts, size_t n, double *out);   /* the same over n triples */
+void   oracle_p_text_diffs(const double *a, const double *b, size_t n, size_t *file_diffs, size_t *stdin_diffs);
 void   oracle_af_counts(const char *gt, size_t n, int *alt, int *total);
 int    oracle_hwe_class(const char *sample, size_t n);
 void   oracle_ac_counts(const char *gt, size_t n, int *ref, int *alt);

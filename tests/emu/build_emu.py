@@ -27,6 +27,30 @@ def build(force: bool = False) -> Path:
     return OUT
 
 
+def build_tools(force: bool = False) -> Path:
+    """The five drop-in executables linked against the emulator library (tests/emu/_build/bin): the host side of the
+    tools — chunking, carry, prefix facts, ordered output, several contexts in one process — runs for real, the
+    kernels under the emulator."""
+    so = build(force)
+    tools_dir = ROOT / "vcfx_b200" / "tools"
+    out_dir = HERE / "_build" / "bin"
+    out_dir.mkdir(parents=True, exist_ok=True)
+    common = sorted(p for p in tools_dir.glob("*.cpp") if not p.name.startswith("VCFX_"))
+    hdrs = sorted(tools_dir.glob("*.h")) + sorted((ROOT / "include").glob("*.h"))
+    for src in sorted(tools_dir.glob("VCFX_*.cpp")):
+        exe = out_dir / src.stem
+        deps = [src, *common, *hdrs, so]
+        if not force and exe.exists() and all(d.stat().st_mtime <= exe.stat().st_mtime for d in deps):
+            continue
+        cmd = ["g++", "-O1", "-g", "-std=c++17", "-I", str(ROOT / "include"), "-I", str(tools_dir), str(src), *map(str, common),
+               "-o", str(exe), f"-L{so.parent}", "-lvcfx_emu", f"-Wl,-rpath,{so.parent}", "-lz", "-lpthread", "-ldl", "-lrt"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+            raise RuntimeError("emulator tool build failed")
+    return out_dir
+
+
 def load_api():
     """A private copy of vcfx_b200.api bound to the emulator library (the real module stays untouched)."""
     import importlib.util

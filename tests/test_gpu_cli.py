@@ -142,3 +142,30 @@ def test_large_file_parallel_io(tmp_path):
             assert out.read_bytes() == want, (tool, threads)
         rc, piped, _ = run(BIN / f"VCFX_{tool}", args)
         assert rc == 0 and piped == want
+
+
+def test_multi_gpu_same_bytes(tmp_path):
+    """VCFX_CUDA_DEVICES: one context per GPU in one process, chunks dealt round-robin, text drained in submission order
+    (the reference's own decomposition, allele_counter.cpp:870-947: newline-aligned ranges, results written in order).
+    The bytes must be those of the one-GPU run and of the reference tool, for all five tools."""
+    import ctypes
+    n = ctypes.c_int(0)
+    lib = ctypes.CDLL(str(ROOT / "vcfx_b200" / "libvcfx_cuda.so"))
+    lib.vcfx_cuda_device_count(ctypes.byref(n))
+    if n.value < 2:
+        pytest.skip("needs at least two GPUs")
+    src = tmp_path / "m.vcf"
+    src.write_bytes(synth.make_vcf(3, 3000, 300, seed=33))           # ~3.6 MB: dozens of 128 KiB chunks over the GPUs
+    late = tmp_path / "late.vcf"
+    late.write_bytes(vcfgen.make_vcf(77, n_lines=3000, n_samples=6, header="late"))
+    env_multi = {"VCFX_CUDA_DEVICES": "all", "VCFX_CHUNK_BYTES": str(128 << 10)}
+    env_one = {"VCFX_CHUNK_BYTES": str(128 << 10)}
+    cases = [("allele_freq_calc", ["-q", "-i"]), ("hwe_tester", ["-q", "-i"]), ("missing_detector", ["-q", "-t", "1", "-i"]),
+             ("variant_counter", []), ("allele_counter", ["-q", "-i"]), ("allele_counter", ["-q", "-a", "-i"])]
+    for f in (src, late):
+        for tool, args in cases:
+            one = run(BIN / f"VCFX_{tool}", [*args, str(f)], env=env_one)
+            many = run(BIN / f"VCFX_{tool}", [*args, str(f)], env=env_multi)
+            assert one[0] == many[0] and one[1] == many[1], (tool, f.name)
+            both(tool, [*args, str(f)], env=env_multi)
+    both("variant_counter", ["--strict", str(late)], env=env_multi)

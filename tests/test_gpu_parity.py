@@ -246,6 +246,53 @@ def test_tier1_rounds_long_lines_and_sparse_exceptions(cuda_api, oracle):
         run_all(cuda_api, oracle, data, f"sparse exceptions x{per_line} small tiles", tile_bytes=4096, tools=("af", "hwe"))
 
 
+def test_multikey_format_exceptions(cuda_api, oracle):
+    """Lines whose FORMAT has several keys (GT:AD:DP:GQ:PL) run through the skip-ahead loop: a lane decides the one
+    sample that starts in it from four bytes.  Everything else — haploid and missing calls, multi-digit alleles, a
+    leading blank, empty columns, samples short enough for two to start in one lane, CRLF — must leave the loop
+    and come out of the exact path unchanged."""
+    forms = [b".", b"./.:.:.:.:.", b"0:1,2:3", b"10/1:5,5:10:50:0,1,2", b"0/10:5,5:10:50:0,1,2", b"0/1", b"1|1:9", b" 0/1:3",
+             b"", b"0/1/1:2,2:4:9:1,2,3", b".|.:1", b"1", b"0|2:3,4:7:20:9,8,7", b"./1:2", b"0/.:2", b"00/1:3", b"0/1:", b"1/1\r"]
+    base = synth.make_vcf(4, 60, 2504, seed=21)
+    for per_line, seed in ((1, 1), (6, 2), (60, 3)):
+        data = _mutate_genotypes(base, seed, per_line, forms, crlf_every=5 if seed == 2 else 0)
+        run_all(cuda_api, oracle, data, f"multikey exceptions x{per_line}", tools=("af", "hwe", "vc"))
+        run_all(cuda_api, oracle, data, f"multikey exceptions x{per_line} small tiles", tile_bytes=8192, tools=("af", "hwe"))
+    # GT first with other keys behind it, every sample one of the short forms: two or more sample starts per lane
+    short = synth.make_vcf(4, 30, 300, seed=22)
+    data = _mutate_genotypes(short, 4, 250, [b".", b"0/1", b"1", b"./.", b"0|0:1"])
+    run_all(cuda_api, oracle, data, "multikey short samples", tools=("af", "hwe"))
+
+
+def test_digit_path_exceptions(cuda_api, oracle):
+    """GT-only lines off the lattice run through the digit path (every byte classified, digits counted); a token of
+    more than one character, a ':' piece, a high byte, CRLF in stdin mode make it decline and the exact path takes the
+    line: multi-digit alleles, junk bytes, pieces, empty tokens — at every distance from the window borders."""
+    forms = [b".", b"./.", b".|.", b"0", b"1", b"0/1", b"1|0", b"./1", b"0|.", b"", b"2|1", b"9/0"]
+    odd_forms = [b"10|1", b"0|1:5", b"1/1/1", b"0x/1", b"1.", b".1", b"0/:/1", b":", b"/", b"||", b"1\xc3\xa9", b"01/0", b" 0/1", b"0/1 "]
+    base = synth.make_vcf(3, 80, 2504, seed=31)
+    for per_line, seed in ((0, 1), (2, 2), (30, 3)):
+        data = _mutate_genotypes(base, seed, 40, forms, crlf_every=6 if seed == 2 else 0)
+        if per_line:
+            data = _mutate_genotypes(data, seed + 10, per_line, odd_forms)
+        run_all(cuda_api, oracle, data, f"digit path x{per_line}", tools=("af", "hwe", "md", "vc"))
+        run_all(cuda_api, oracle, data, f"digit path x{per_line} small tiles", tile_bytes=4096, tools=("af",))
+        for path, fmt in ((oracle.AC_UNIFIED, oracle.AC_AGGREGATE),):
+            if per_line == 0:                      # (allele_counter's reference loops forever on bytes outside [0-9./|:]: no oracle there)
+                o = oracle.allele_counter(data, path, fmt)
+                r = cuda_api.allele_counter(data, path, fmt)
+                _cmp(f"digit path ac -a x{per_line}", r.out, o.out)
+    # one odd genotype at every offset of a 2 KiB stretch: each position relative to the 512-byte windows and the lanes
+    line_hdr = b"##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + b"\t".join(b"S%d" % i for i in range(700)) + b"\n"
+    body = []
+    for k in range(700):
+        gts = [b"0|1", b"1/1", b".", b"0", b"./."] * 140
+        gts[k] = [b"10|1", b"0|1:5", b"1.", b"11"][k % 4]
+        body.append(b"1\t%d\t.\tA\tG\t.\tPASS\t.\tGT\t" % (k + 1) + b"\t".join(gts))
+    data = line_hdr + b"\n".join(body) + b"\n"
+    run_all(cuda_api, oracle, data, "digit path, one odd genotype at every offset", tools=("af",))
+
+
 def test_allele_counter_two_digit_counts(cuda_api, oracle):
     """allele_counter TEXT rows are sized without looking at the genotypes (one digit per count); a
     sample with ten or more alleles of a kind, or 128+ (int8 wrap to a negative number), breaks that

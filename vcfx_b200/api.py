@@ -59,7 +59,7 @@ class ChunkStats(C.Structure):
 EXPORTS = ["vcfx_cuda_abi_version", "vcfx_cuda_device_count", "vcfx_cuda_strerror", "vcfx_cuda_last_error",
            "vcfx_cuda_create", "vcfx_cuda_destroy", "vcfx_cuda_acquire_input", "vcfx_cuda_submit",
            "vcfx_cuda_submit_host", "vcfx_cuda_submit_shared", "vcfx_cuda_set_line_hint", "vcfx_cuda_next_output", "vcfx_cuda_in_flight", "vcfx_cuda_short_lines",
-           "vcfx_cuda_run_device", "vcfx_cuda_sync"]
+           "vcfx_cuda_run_device", "vcfx_cuda_sync", "vcfx_cuda_hwe_pvalues"]
 
 _lib = None
 
@@ -92,8 +92,20 @@ def load():
         l.vcfx_cuda_short_lines.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_size_t, C.POINTER(C.c_size_t)]
         l.vcfx_cuda_run_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(ChunkInfo), C.c_void_p, C.c_size_t]
         l.vcfx_cuda_sync.argtypes = [C.c_void_p, C.POINTER(ChunkStats)]
+        l.vcfx_cuda_hwe_pvalues.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
         _lib = l
     return _lib
+
+
+def hwe_pvalues(counts, device: int = 0):
+    """hwe_tester's p-value computed on the device for an int32 array [n, 3] of (homRef, het, homAlt)."""
+    import numpy as np
+    c = np.ascontiguousarray(counts, dtype=np.int32).reshape(-1, 3)
+    out = np.empty(len(c), dtype=np.float64)
+    rc = load().vcfx_cuda_hwe_pvalues(device, c.ctypes.data, len(c), out.ctypes.data)
+    if rc != 0:
+        raise VcfxCudaError(rc, load().vcfx_cuda_strerror(rc).decode())
+    return out
 
 
 def device_count() -> int:

@@ -31,7 +31,8 @@ struct Work {                      // device-side bookkeeping for one launch
     unsigned long long *line_base = nullptr;
     uint32_t *tail_start = nullptr, *tail_len = nullptr, *tail_off = nullptr;   // MISSING_DETECT
     uint2 *col_scratch = nullptr;   // ALLELE_COUNT
-    unsigned int *ticket = nullptr;
+    unsigned int *ticket = nullptr;      // two counters: [0] lattice / only kernel, [1] general kernel
+    uint32_t *tile_resume = nullptr;
     Rec *recs = nullptr;
     uint8_t *rec_prefix = nullptr;
     uint64_t rec_cap = 0;
@@ -41,6 +42,7 @@ struct Work {                      // device-side bookkeeping for one launch
     DevStats *h_init = nullptr;    // pinned: constant initial value uploaded before every launch
     uint32_t tiles_cap = 0;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+    cudaEvent_t ev_stats = nullptr;     // the launch's DevStats have landed in h_stats
 };
 
 struct Slot {
@@ -58,6 +60,8 @@ struct Slot {
     cudaEvent_t ev_shared_done = nullptr;  // a secondary context finished reading this slot's d_in
     bool shared_pending = false;
     uint8_t *d_in_used = nullptr;          // the device input of the chunk in flight (own d_in, or a primary's)
+    bool d2h_issued = false;               // the text of the chunk in flight is already on its way to h_out
+    size_t d2h_bytes = 0;
 };
 
 }  // namespace
@@ -112,13 +116,29 @@ namespace {
 
 typedef void (*kernel_fn)(const KParams);
 
+#ifdef VCFX_EMU
+struct HweArgs { const int32_t *c; size_t n; double *p; };
+void hwe_pvalue_entry(const HweArgs a) { hwe_pvalue_kernel(a.c, a.n, a.p); }
+void hwe_pvalue_launch(int grid, const int32_t *c, size_t n, double *p) { HweArgs a = {c, n, p}; emu_launch(hwe_pvalue_entry, dim3(grid), dim3(256), 0, nullptr, a); }
+#else
+void hwe_pvalue_launch(int grid, const int32_t *c, size_t n, double *p) { hwe_pvalue_kernel<<<grid, 256>>>(c, n, p); }
+#endif
+
 kernel_fn kernel_for(int op) {
     switch (op) {
-    case VCFX_OP_VARIANT_COUNT: return vcfx_scan_kernel<OP_VC>;
-    case VCFX_OP_ALLELE_FREQ:   return vcfx_scan_kernel<OP_AF>;
-    case VCFX_OP_HWE:           return vcfx_scan_kernel<OP_HWE>;
-    case VCFX_OP_MISSING_DETECT: return vcfx_scan_kernel<OP_MD>;
-    case VCFX_OP_ALLELE_COUNT:  return vcfx_scan_kernel<OP_AC>;
+    case VCFX_OP_VARIANT_COUNT: return vcfx_scan_kernel<OP_VC, 0>;
+    case VCFX_OP_ALLELE_FREQ:   return vcfx_scan_kernel<OP_AF, 0>;
+    case VCFX_OP_HWE:           return vcfx_scan_kernel<OP_HWE, 0>;
+    case VCFX_OP_MISSING_DETECT: return vcfx_scan_kernel<OP_MD, 0>;
+    case VCFX_OP_ALLELE_COUNT:  return vcfx_scan_kernel<OP_AC, 0>;
+    default: return nullptr;
+    }
+}
+// the general kernel that finishes the tiles the lattice kernel left (allele_freq_calc / hwe_tester)
+kernel_fn general_kernel_for(int op) {
+    switch (op) {
+    case VCFX_OP_ALLELE_FREQ: return vcfx_scan_kernel<OP_AF, 1>;
+    case VCFX_OP_HWE:         return vcfx_scan_kernel<OP_HWE, 1>;
     default: return nullptr;
     }
 }
@@ -197,11 +217,12 @@ uint64_t rec_slack(const vcfx_ctx *ctx) {
 void free_work(Work &w) {
     cudaFree(w.tile_lines); cudaFree(w.tile_out); cudaFree(w.tile_base); cudaFree(w.line_base);
     cudaFree(w.rec_prefix); cudaFree(w.ticket); cudaFree(w.recs); cudaFree(w.d_stats); cudaFree(w.events);
-    cudaFree(w.tail_start); cudaFree(w.tail_len); cudaFree(w.tail_off); cudaFree(w.col_scratch);
+    cudaFree(w.tail_start); cudaFree(w.tail_len); cudaFree(w.tail_off); cudaFree(w.col_scratch); cudaFree(w.tile_resume);
     if (w.h_stats) cudaFreeHost(w.h_stats);
     if (w.h_init) cudaFreeHost(w.h_init);
     if (w.ev_k0) cudaEventDestroy(w.ev_k0);
     if (w.ev_k1) cudaEventDestroy(w.ev_k1);
+    if (w.ev_stats) cudaEventDestroy(w.ev_stats);
     w = Work();
 }
 
@@ -210,7 +231,7 @@ int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes, uint64_t min_recs = 0)
     uint32_t tiles = tiles_for(ctx, max_bytes, ctx->tile_bytes ? ctx->tile_bytes : MIN_TILE);
     if (!w.d_stats) {
         CU(cudaMalloc(&w.d_stats, sizeof(DevStats)));
-        CU(cudaMalloc(&w.ticket, sizeof(unsigned int)));
+        CU(cudaMalloc(&w.ticket, 2 * sizeof(unsigned int)));
         CU(cudaMalloc(&w.events, sizeof(unsigned long long) * EVENT_CAP));
         CU(cudaMallocHost(&w.h_stats, sizeof(DevStats)));
         CU(cudaMallocHost(&w.h_init, sizeof(DevStats)));
@@ -218,6 +239,7 @@ int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes, uint64_t min_recs = 0)
         memset(w.h_stats, 0, sizeof(DevStats));
         CU(cudaEventCreate(&w.ev_k0));
         CU(cudaEventCreate(&w.ev_k1));
+        CU(cudaEventCreateWithFlags(&w.ev_stats, cudaEventDisableTiming));
     }
     if (tiles > w.tiles_cap) {
         cudaFree(w.tile_lines); cudaFree(w.tile_out); cudaFree(w.tile_base); cudaFree(w.line_base);
@@ -226,6 +248,10 @@ int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes, uint64_t min_recs = 0)
         CU(cudaMalloc(&w.tile_out, sizeof(unsigned long long) * tiles));
         CU(cudaMalloc(&w.tile_base, sizeof(unsigned long long) * tiles));
         CU(cudaMalloc(&w.line_base, sizeof(unsigned long long) * tiles));
+        if (general_kernel_for(ctx->cfg.op)) {
+            cudaFree(w.tile_resume); w.tile_resume = nullptr;
+            CU(cudaMalloc(&w.tile_resume, sizeof(uint32_t) * tiles));
+        }
         if (ctx->cfg.op == VCFX_OP_MISSING_DETECT) {
             cudaFree(w.tail_start); cudaFree(w.tail_len); cudaFree(w.tail_off);
             w.tail_start = w.tail_len = w.tail_off = nullptr;
@@ -259,7 +285,9 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
     const uint32_t tile = tile_for(ctx, nbytes);
     uint32_t tiles = tiles_for(ctx, nbytes, tile);
     if (write_pad) CU(cudaMemsetAsync(d_in + nbytes, '\n', 64, st));
-    CU(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), st));
+    CU(cudaMemsetAsync(w.ticket, 0, 2 * sizeof(unsigned int), st));
+    kernel_fn gfn = general_kernel_for(ctx->cfg.op);
+    if (gfn) CU(cudaMemsetAsync(w.tile_resume, 0xFF, sizeof(uint32_t) * tiles, st));
     CU(cudaMemcpyAsync(w.d_stats, w.h_init, sizeof(DevStats), cudaMemcpyHostToDevice, st));
 
     KParams P;
@@ -273,7 +301,7 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
     P.tail_start = w.tail_start; P.tail_len = w.tail_len; P.tail_off = w.tail_off;
     P.ac_fmt = ctx->ac_fmt; P.ac_ident = ctx->ac_ident ? 1 : 0; P.ac_pass = 0; P.ac_spec = (ctx->cfg.op == VCFX_OP_ALLELE_COUNT && ctx->ac_fmt == AC_TEXT_MT && !ctx->ac_exact) ? 1 : 0; P.n_sel = ctx->n_sel; P.sel_col = ctx->d_sel_col; P.name_off = ctx->d_name_off;
     P.names = ctx->d_names; P.max_col = ctx->max_col; P.col_scratch = w.col_scratch;
-    P.ticket = w.ticket; P.recs = w.recs; P.rec_prefix = w.rec_prefix; P.rec_cap = w.rec_cap;
+    P.ticket = w.ticket; P.ticket2 = w.ticket + 1; P.tile_resume = w.tile_resume; P.recs = w.recs; P.rec_prefix = w.rec_prefix; P.rec_cap = w.rec_cap;
     P.stats = w.d_stats; P.events = w.events; P.ev_cap = EVENT_CAP;
 
     CU(cudaEventRecord(w.ev_k0, st));
@@ -281,6 +309,10 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
         int grid = grid_for(ctx, tiles);
         VCFX_LAUNCH(fn, grid, WARPS_PER_CTA * 32, 0, st, P);
         CU(cudaGetLastError());
+        if (gfn) {                       // finishes the tiles the lattice kernel left; exits at once when there are none
+            VCFX_LAUNCH(gfn, grid, WARPS_PER_CTA * 32, 0, st, P);
+            CU(cudaGetLastError());
+        }
         VCFX_LAUNCH(tile_scan_kernel, 1, 1024, SCAN_SMEM_BYTES, st, P);
         CU(cudaGetLastError());
         if (kernel_fn ff = format_kernel_for(ctx->cfg.op, ctx->ac_fmt)) {
@@ -288,7 +320,7 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
             CU(cudaGetLastError());
         } else if (ctx->cfg.op == VCFX_OP_ALLELE_COUNT) {
             // rows are sized in the first pass and written in a second one at their scanned offsets
-            CU(cudaMemsetAsync(w.ticket, 0, sizeof(unsigned int), st));
+            CU(cudaMemsetAsync(w.ticket, 0, 2 * sizeof(unsigned int), st));
             P.ac_pass = 1;
             VCFX_LAUNCH(fn, grid, WARPS_PER_CTA * 32, 0, st, P);
             CU(cudaGetLastError());
@@ -296,6 +328,7 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
     }
     CU(cudaEventRecord(w.ev_k1, st));
     CU(cudaMemcpyAsync(w.h_stats, w.d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(w.ev_stats, st));
     return VCFX_OK;
 }
 
@@ -324,12 +357,29 @@ int fetch_events(vcfx_ctx *ctx, const Work &w, cudaStream_t st) {
     return VCFX_OK;
 }
 
-size_t default_out_bytes(int op, size_t chunk) {
+size_t default_out_bytes(int op, unsigned flags, size_t chunk) {
     switch (op) {
     case VCFX_OP_VARIANT_COUNT: return 4096;
     case VCFX_OP_MISSING_DETECT: return chunk + chunk / 4 + 4096;
-    case VCFX_OP_ALLELE_COUNT: return 4 * chunk + 4096;
+    case VCFX_OP_ALLELE_COUNT:
+        if (flags & VCFX_F_AC_AGGREGATE) return chunk / 4 + (1u << 20);
+        if (flags & VCFX_F_AC_BINARY) return chunk + 4096;
+        return 10 * chunk + 4096;                // a text row per genotype: ~9x the input at 2,504 samples
     default: return chunk / 4 + (1u << 20);      // AF / HWE rows are ~0.3 % of the input
+    }
+}
+
+// The text of finished chunks starts its way to the host as soon as their kernels are done, oldest first, whenever the
+// caller is in the library: the device->host copy of chunk k+1 then runs while the caller writes chunk k out.
+void kick_ready(vcfx_ctx *ctx) {
+    for (int i = 0, k = ctx->tail; i < ctx->n_in_flight; ++i, k = (k + 1) % ctx->n_slots) {
+        Slot &s = ctx->slots[k];
+        if (!s.in_flight || s.d2h_issued) continue;
+        if (cudaEventQuery(s.w.ev_stats) != cudaSuccess) break;          // not finished: nor is anything behind it
+        if (s.w.h_stats->overflow) continue;                             // next_output runs it again
+        const size_t nout = (size_t)s.w.h_stats->bytes_out;
+        if (nout && cudaMemcpyAsync(s.h_out, s.d_out, nout, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess) { cudaGetLastError(); break; }
+        s.d2h_issued = true; s.d2h_bytes = nout;
     }
 }
 
@@ -378,7 +428,7 @@ int vcfx_cuda_create(const vcfx_cfg *cfg, vcfx_ctx **out) {
     ctx->device = cfg->device;
     ctx->chunk_bytes = cfg->chunk_bytes ? cfg->chunk_bytes : DEFAULT_CHUNK;
     ctx->tile_bytes = cfg->tile_bytes > 0 ? std::max<uint32_t>(512, ((uint32_t)cfg->tile_bytes + 511) & ~511u) : 0;   // 0 = per launch
-    ctx->out_bytes = cfg->out_bytes ? cfg->out_bytes : default_out_bytes(cfg->op, ctx->chunk_bytes);
+    ctx->out_bytes = cfg->out_bytes ? cfg->out_bytes : default_out_bytes(cfg->op, cfg->flags, ctx->chunk_bytes);
     ctx->n_slots = cfg->n_slots > 0 ? std::min(cfg->n_slots, MAX_SLOTS) : 3;
     auto fail = [&](int rc) { std::string e = ctx->last_error; vcfx_cuda_destroy(ctx); (void)e; return rc; };
 #define CUC(call)                                                                        \
@@ -486,10 +536,11 @@ int vcfx_cuda_submit(vcfx_ctx *ctx, size_t nbytes, const vcfx_chunk_info *info) 
     if (info) s.info = *info; else s.info = vcfx_chunk_info{0, 1, 0};
     int rc = launch_chunk(ctx, s.w, s.stream, s.d_in, nbytes, &s.info, s.d_out, s.out_cap, false);
     if (rc != VCFX_OK) return rc;
-    s.nbytes = nbytes; s.in_flight = true;
+    s.nbytes = nbytes; s.in_flight = true; s.d2h_issued = false;
     ctx->acquired_slot = -1;
     ctx->head = (ctx->head + 1) % ctx->n_slots;
     ctx->n_in_flight++;
+    kick_ready(ctx);
     return VCFX_OK;
 }
 
@@ -509,9 +560,10 @@ int vcfx_cuda_submit_host(vcfx_ctx *ctx, const void *host, size_t nbytes, const 
     if (info) s.info = *info; else s.info = vcfx_chunk_info{0, 1, 0};
     rc = launch_chunk(ctx, s.w, s.stream, s.d_in, nbytes, &s.info, s.d_out, s.out_cap, false);
     if (rc != VCFX_OK) return rc;
-    s.nbytes = nbytes; s.in_flight = true;
+    s.nbytes = nbytes; s.in_flight = true; s.d2h_issued = false;
     ctx->head = (ctx->head + 1) % ctx->n_slots;
     ctx->n_in_flight++;
+    kick_ready(ctx);
     return VCFX_OK;
 }
 
@@ -533,13 +585,25 @@ int vcfx_cuda_submit_shared(vcfx_ctx *ctx, vcfx_ctx *primary, const vcfx_chunk_i
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamWaitEvent(s.stream, ps.ev_h2d, 0));                 // the bytes are there
     if (info) s.info = *info; else s.info = vcfx_chunk_info{0, 1, 0};
-    s.d_in_used = ps.d_in;
-    rc = launch_chunk(ctx, s.w, s.stream, ps.d_in, ps.nbytes, &s.info, s.d_out, s.out_cap, false);
+    // An operation that may have to run a chunk again (more rows or more text than its slot was sized for) takes a
+    // private device copy (a few tens of microseconds): the primary is then free to reuse its buffer at once and a
+    // re-run never reads bytes the primary has overwritten.  variant_counter never re-runs and reads the primary's bytes.
+    const bool own_copy = ctx->cfg.op != VCFX_OP_VARIANT_COUNT;
+    if (own_copy) {
+        if (ps.nbytes) CU(cudaMemcpyAsync(s.d_in, ps.d_in, ps.nbytes, cudaMemcpyDeviceToDevice, s.stream));
+        CU(cudaMemsetAsync(s.d_in + ps.nbytes, '\n', 64, s.stream));
+        CU(cudaEventRecord(ps.ev_shared_done, s.stream));
+        ps.shared_pending = true;
+    }
+    s.d_in_used = own_copy ? s.d_in : ps.d_in;
+    rc = launch_chunk(ctx, s.w, s.stream, s.d_in_used, ps.nbytes, &s.info, s.d_out, s.out_cap, false);
     if (rc != VCFX_OK) return rc;
-    // the primary may not overwrite that device buffer before this context has read it
-    CU(cudaEventRecord(ps.ev_shared_done, s.stream));
-    ps.shared_pending = true;
-    s.nbytes = ps.nbytes; s.in_flight = true;
+    if (!own_copy) {
+        // the primary may not overwrite that device buffer before this context has read it
+        CU(cudaEventRecord(ps.ev_shared_done, s.stream));
+        ps.shared_pending = true;
+    }
+    s.nbytes = ps.nbytes; s.in_flight = true; s.d2h_issued = false;
     ctx->head = (ctx->head + 1) % ctx->n_slots;
     ctx->n_in_flight++;
     return VCFX_OK;
@@ -550,12 +614,13 @@ int vcfx_cuda_next_output(vcfx_ctx *ctx, const char **text, size_t *n, vcfx_chun
     if (ctx->n_in_flight == 0) return VCFX_E_EMPTY;
     Slot &s = ctx->slots[ctx->tail];
     CU(cudaSetDevice(ctx->device));
-    CU(cudaStreamSynchronize(s.stream));
+    kick_ready(ctx);
+    CU(cudaStreamSynchronize(s.stream));            // kernels, stats and (when already issued) the text of this chunk
     s.in_flight = false;
     ctx->tail = (ctx->tail + 1) % ctx->n_slots;
     ctx->n_in_flight--;
     // A chunk with more rows / more text than the slot was sized for is simply run again with
-    // exact sizes (the input is still on the device).
+    // exact sizes (the input is still on the device); the larger buffers are kept, with headroom.
     for (int attempt = 0; s.w.h_stats->overflow && attempt < 3; ++attempt) {
         const unsigned long long ov = s.w.h_stats->overflow;
         if (ov & 4) ctx->ac_exact = true;
@@ -564,7 +629,7 @@ int vcfx_cuda_next_output(vcfx_ctx *ctx, const char **text, size_t *n, vcfx_chun
             if (rc != VCFX_OK) return rc;
         }
         if (ov & 2) {
-            size_t want = (size_t)s.w.h_stats->bytes_out + 4096;
+            const size_t want = std::max((size_t)s.w.h_stats->bytes_out + (1u << 20), s.out_cap + s.out_cap / 4);
             cudaFree(s.d_out); cudaFreeHost(s.h_out); s.d_out = nullptr; s.h_out = nullptr; s.out_cap = 0;
             CU(cudaMalloc(&s.d_out, want));
             CU(cudaMallocHost(&s.h_out, want));
@@ -573,17 +638,20 @@ int vcfx_cuda_next_output(vcfx_ctx *ctx, const char **text, size_t *n, vcfx_chun
         int rc = launch_chunk(ctx, s.w, s.stream, s.d_in_used, s.nbytes, &s.info, s.d_out, s.out_cap, false);
         if (rc != VCFX_OK) return rc;
         CU(cudaStreamSynchronize(s.stream));
+        s.d2h_issued = false;
     }
     if (s.w.h_stats->overflow) return VCFX_E_OUTPUT_TOO_BIG;
     size_t nout = (size_t)s.w.h_stats->bytes_out;
-    if (nout) {
+    if (!s.d2h_issued && nout) {
         CU(cudaMemcpyAsync(s.h_out, s.d_out, nout, cudaMemcpyDeviceToHost, s.stream));
         CU(cudaStreamSynchronize(s.stream));
     }
+    s.d2h_issued = false;
     int rc = fetch_events(ctx, s.w, s.stream);
     if (rc != VCFX_OK) return rc;
     fill_stats(s.w, s.nbytes, stats);
     *text = s.h_out; *n = nout;
+    kick_ready(ctx);                                // whatever finished meanwhile starts its copy before the caller leaves
     return VCFX_OK;
 }
 
@@ -631,6 +699,26 @@ int vcfx_cuda_sync(vcfx_ctx *ctx, vcfx_chunk_stats *stats) {
     fill_stats(ctx->dev_work, ctx->dev_nbytes, stats);
     if (ctx->dev_work.h_stats->overflow) return VCFX_E_OUTPUT_TOO_BIG;
     return VCFX_OK;
+}
+
+int vcfx_cuda_hwe_pvalues(int device, const int32_t *counts, size_t n, double *pvalues) {
+    if ((!counts || !pvalues) && n) return VCFX_E_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return VCFX_E_NO_DEVICE;
+    if (device < 0 || device >= ndev) return VCFX_E_INVALID;
+    if (n == 0) return VCFX_OK;
+    if (cudaSetDevice(device) != cudaSuccess) return VCFX_E_CUDA;
+    int32_t *d_c = nullptr; double *d_p = nullptr;
+    int rc = VCFX_OK;
+    if (cudaMalloc(&d_c, n * 3 * sizeof(int32_t)) != cudaSuccess || cudaMalloc(&d_p, n * sizeof(double)) != cudaSuccess) rc = VCFX_E_NOMEM;
+    if (rc == VCFX_OK && cudaMemcpy(d_c, counts, n * 3 * sizeof(int32_t), cudaMemcpyHostToDevice) != cudaSuccess) rc = VCFX_E_CUDA;
+    if (rc == VCFX_OK) {
+        const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+        hwe_pvalue_launch(grid, d_c, n, d_p);
+        if (cudaGetLastError() != cudaSuccess || cudaMemcpy(pvalues, d_p, n * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) rc = VCFX_E_CUDA;
+    }
+    cudaFree(d_c); cudaFree(d_p);
+    return rc;
 }
 
 }  // extern "C"

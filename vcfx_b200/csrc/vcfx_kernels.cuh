@@ -50,6 +50,7 @@ struct Rec {                 // one output row (32 B)
 };
 
 constexpr unsigned int REC_BLOCK = 32;          // row-record slots a warp reserves at a time
+constexpr uint32_t RESUME_DONE = 0xFFFFFFFFu;
 constexpr uint32_t REC_INVALID = 0xFFFFFFFFu;   // Rec::tile of a reserved slot that was never filled
 
 struct DevStats {
@@ -62,6 +63,7 @@ struct DevStats {
     unsigned long long overflow;          // bit 0: row records, bit 1: output bytes, bit 2: speculative row sizes were wrong
     unsigned long long first_short_line;  // filled by tile_scan_kernel
     unsigned long long n_recs;            // row-record slots reserved (may exceed rec_cap: then overflow)
+    unsigned long long n_unfinished;      // tiles the lattice kernel left to the general kernel
 };
 
 // shared-memory event counters of K1: slot = index of the 64-bit field in DevStats
@@ -100,6 +102,8 @@ struct KParams {
     uint32_t max_col;                // 1 + largest selected column
     uint2 *col_scratch;              // [resident warps][max_col] (ref, alt) of the current line
     unsigned int *ticket;            // dynamic tile counter (zeroed before launch)
+    unsigned int *ticket2;           // the same for the general kernel (allele_freq_calc / hwe_tester)
+    uint32_t *tile_resume;           // [n_tiles] allele_freq_calc / hwe_tester: where the lattice kernel stopped in the tile (RESUME_DONE: it did not)
     Rec *recs;
     uint8_t *rec_prefix;             // [rec_cap][32] copy of the row prefix when it is <= 32 bytes (AF / HWE)
     uint64_t rec_cap;
@@ -146,10 +150,12 @@ __device__ __forceinline__ uint32_t ldb(const uint8_t *p) { return (uint32_t)__l
 __device__ __forceinline__ uint32_t ldw(const uint8_t *p) { return __ldg(reinterpret_cast<const uint32_t *>(p)); }
 // VCFX_EMU: the test-only warp emulator build of this file (tests/emu/); PTX has no meaning there
 #ifdef VCFX_EMU
+#define VCFX_GRID_CONSTANT
 __device__ __forceinline__ void prefetch_l2(const void *) {}
 __device__ __forceinline__ void prefetch_l1(const void *) {}
 __device__ __forceinline__ int lane_id() { return (int)(threadIdx.x & 31u); }
 #else
+#define VCFX_GRID_CONSTANT __grid_constant__      // the parameter block may be passed on by reference without a local copy
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // %laneid: one S2R when the compiler rematerialises it (it does, a dozen times per line)
@@ -523,94 +529,93 @@ __device__ __forceinline__ DigitClass<OP> digit_classes(uint32_t x) {
     return c;
 }
 
+// bytes of the lane (positions pb .. pb+15) outside [lo, hi) replaced by the filler byte
+__device__ __forceinline__ void patch_outside(uint4 &v, uint32_t pb, uint32_t lo, uint32_t hi, uint32_t filler4) {
+    const uint32_t keep = lane_keep16(pb, lo, hi);
+    const uint32_t k0 = (nib80(keep, 0) >> 7) * 0xFFu, k1 = (nib80(keep, 1) >> 7) * 0xFFu;
+    const uint32_t k2 = (nib80(keep, 2) >> 7) * 0xFFu, k3 = (nib80(keep, 3) >> 7) * 0xFFu;
+    v.x = (v.x & k0) | (filler4 & ~k0); v.y = (v.y & k1) | (filler4 & ~k1);
+    v.z = (v.z & k2) | (filler4 & ~k2); v.w = (v.w & k3) | (filler4 & ~k3);
+}
+
+// One window of the digit path: the lane's counts (128 x: the markers are 0x80 per byte) of digits / non-zero digits /
+// tabs among bytes pb-1 .. pb+14 (the byte before the lane comes from its left neighbour, lane 0's from `carry_in`),
+// and `odd` != 0 when the window holds anything the path does not decide (two touching bytes of the class that must
+// stand alone, a '\n', a ':', a byte >= 0x80).  next_carry (valid in lane 0) = the class bits of the window's last byte.
+template <int OP>
+__device__ __forceinline__ void digits_window(const uint4 cur, const uint32_t carry_in, const int lane,
+                                              uint32_t &tB, uint32_t &tA, uint32_t &tT, uint32_t &odd, uint32_t &next_carry) {
+    uint32_t pk, adj_first;
+    tT = 0;
+    {
+        const DigitClass<OP> c3 = digit_classes<OP>(cur.w);
+        // this lane's last byte, for the lane to its right: bit 31 adjacency class, bit 30 digit, bit 29 non-zero digit
+        pk = (c3.adjc & 0x80000000u) | ((c3.D >> 1) & 0x40000000u) | ((c3.NZ >> 2) & 0x20000000u);
+        const DigitClass<OP> c2 = digit_classes<OP>(cur.z);
+        const uint32_t a3 = up1(c2.adjc, c3.adjc);
+        odd = ((OP == OP_AF) ? (~(c3.adjc | a3) & M80) : (c3.adjc & a3)) | c3.SP | c2.SP;
+        tB = dp4a_u(c3.D, 0x00010101u, dp4a_u(c2.D, 0x01010101u, 0u));
+        tA = dp4a_u(c3.NZ, 0x00010101u, dp4a_u(c2.NZ, 0x01010101u, 0u));
+        if (OP == OP_AC) tT = dp4a_u(c3.TB, 0x01010101u, dp4a_u(c2.TB, 0x01010101u, 0u));
+        const DigitClass<OP> c1 = digit_classes<OP>(cur.y);
+        const uint32_t a2 = up1(c1.adjc, c2.adjc);
+        odd |= ((OP == OP_AF) ? (~(c2.adjc | a2) & M80) : (c2.adjc & a2)) | c1.SP;
+        tB = dp4a_u(c1.D, 0x01010101u, tB); tA = dp4a_u(c1.NZ, 0x01010101u, tA);
+        if (OP == OP_AC) tT = dp4a_u(c1.TB, 0x01010101u, tT);
+        const DigitClass<OP> c0 = digit_classes<OP>(cur.x);
+        const uint32_t a1 = up1(c0.adjc, c1.adjc);
+        odd |= ((OP == OP_AF) ? (~(c1.adjc | a1) & M80) : (c1.adjc & a1)) | c0.SP;
+        tB = dp4a_u(c0.D, 0x01010101u, tB); tA = dp4a_u(c0.NZ, 0x01010101u, tA);
+        if (OP == OP_AC) tT = dp4a_u(c0.TB, 0x01010101u, tT);
+        adj_first = c0.adjc;
+    }
+    uint32_t pv = __shfl_sync(FULL, pk, (lane + 31) & 31);
+    next_carry = pv;
+    if (lane == 0) pv = carry_in;
+    const uint32_t a0 = up1(pv, adj_first);
+    odd |= ((OP == OP_AF) ? (~(adj_first | a0) & M80) : (adj_first & a0)) | ((cur.x | cur.y | cur.z | cur.w) & M80);
+    tB += (pv >> 23) & 0x80u;
+    tA += (pv >> 22) & 0x80u;
+}
+
 template <int OP>
 __device__ __forceinline__ bool line_digits(const uint8_t *__restrict__ tin, uint32_t wb, const uint32_t lo, const uint32_t nrel,
-                                         const bool strip_cr, uint32_t &out_a, uint32_t &out_b, uint32_t &out_tabs, uint32_t &out_e) {
+                                           const bool strip_cr, uint32_t &out_a, uint32_t &out_b, uint32_t &out_tabs, uint32_t &out_e) {
     const int lane = lane_id();
-    uint32_t accA = 0, accB = 0, accT = 0;               // 128 x count (the markers are 0x80 per byte)
-    uint32_t carry = 0;                                   // lane 0: class bits of the last byte of the window before
-    bool first = true;
+    // bytes outside the sample region are overwritten with a byte that counts nothing and touches nothing before they
+    // are classified: a tab for allele_freq_calc, a blank for allele_counter (whose tabs are counted)
+    constexpr uint32_t FILL = (OP == OP_AF) ? 0x09090909u : 0x20202020u;
+    uint32_t accA = 0, accB = 0, accT = 0;               // 128 x count
+    uint32_t carry = (OP == OP_AF) ? 0x80000000u : 0u;    // lane 0: class bits of the last byte of the window before
     uint4 cur = ld16(tin + wb + 16 * lane);
     uint4 nxt = ld16(tin + wb + WINDOW + 16 * lane);
     uint4 nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
+    patch_outside(cur, wb + 16 * lane, lo, ~0u, FILL);    // the first window: nothing before `lo` is a sample
+    bool first = true;                                    // (the caller has counted the tabs of this window)
     for (;;) {
-        // counts of the window first (two registers instead of eight marker words across the vote): bytes pb-1 .. pb+14
-        // are this lane's digits
-        uint32_t tB, tA, tT = 0, odd, pk, adj_prev;
-        {
-            const DigitClass<OP> c3 = digit_classes<OP>(cur.w);
-            // this lane's last byte, for the lane to its right: bit 31 adjacency class, bit 30 digit, bit 29 non-zero digit
-            pk = (c3.adjc & 0x80000000u) | ((c3.D >> 1) & 0x40000000u) | ((c3.NZ >> 2) & 0x20000000u);
-            const DigitClass<OP> c2 = digit_classes<OP>(cur.z);
-            const uint32_t a3 = up1(c2.adjc, c3.adjc);
-            odd = ((OP == OP_AF) ? (~(c3.adjc | a3) & M80) : (c3.adjc & a3)) | c3.SP | c2.SP;
-            tB = dp4a_u(c3.D, 0x00010101u, dp4a_u(c2.D, 0x01010101u, 0u));
-            tA = dp4a_u(c3.NZ, 0x00010101u, dp4a_u(c2.NZ, 0x01010101u, 0u));
-            if (OP == OP_AC) tT = dp4a_u(c3.TB, 0x01010101u, dp4a_u(c2.TB, 0x01010101u, 0u));
-            const DigitClass<OP> c1 = digit_classes<OP>(cur.y);
-            const uint32_t a2 = up1(c1.adjc, c2.adjc);
-            odd |= ((OP == OP_AF) ? (~(c2.adjc | a2) & M80) : (c2.adjc & a2)) | c1.SP;
-            tB = dp4a_u(c1.D, 0x01010101u, tB); tA = dp4a_u(c1.NZ, 0x01010101u, tA);
-            if (OP == OP_AC) tT = dp4a_u(c1.TB, 0x01010101u, tT);
-            const DigitClass<OP> c0 = digit_classes<OP>(cur.x);
-            const uint32_t a1 = up1(c0.adjc, c1.adjc);
-            odd |= ((OP == OP_AF) ? (~(c1.adjc | a1) & M80) : (c1.adjc & a1)) | c0.SP;
-            tB = dp4a_u(c0.D, 0x01010101u, tB); tA = dp4a_u(c0.NZ, 0x01010101u, tA);
-            if (OP == OP_AC) tT = dp4a_u(c0.TB, 0x01010101u, tT);
-            adj_prev = c0.adjc;
-        }
-        uint32_t pv = __shfl_sync(FULL, pk, (lane + 31) & 31);
-        if (lane == 0) { const uint32_t t = pv; pv = carry; carry = t; }
-        {
-            const uint32_t a0 = up1(pv, adj_prev);
-            odd |= ((OP == OP_AF) ? (~(adj_prev | a0) & M80) : (adj_prev & a0)) | ((cur.x | cur.y | cur.z | cur.w) & M80);
-        }
-        if (!__any_sync(FULL, (odd != 0) | first)) {
-            accB += tB + ((pv >> 23) & 0x80u);
-            accA += tA + ((pv >> 22) & 0x80u);
-            if (OP == OP_AC) accT += tT;
-        } else {
-            // the first window (bytes before `lo` are not samples), the window with the '\n', or something odd
-            const uint32_t pb = wb + 16 * lane;
-            const uint32_t L = first ? lo : 0u;
-            const DigitClass<OP> c0 = digit_classes<OP>(cur.x), c1 = digit_classes<OP>(cur.y);
-            const DigitClass<OP> c2 = digit_classes<OP>(cur.z), c3 = digit_classes<OP>(cur.w);
-            const uint32_t a0 = up1(pv, c0.adjc), a1 = up1(c0.adjc, c1.adjc), a2 = up1(c1.adjc, c2.adjc), a3 = up1(c2.adjc, c3.adjc);
-            uint32_t j0, j1, j2, j3;                     // two bytes that must not touch, at the second one
-            if (OP == OP_AF) { j0 = ~(c0.adjc | a0) & M80; j1 = ~(c1.adjc | a1) & M80; j2 = ~(c2.adjc | a2) & M80; j3 = ~(c3.adjc | a3) & M80; }
-            else { j0 = c0.adjc & a0; j1 = c1.adjc & a1; j2 = c2.adjc & a2; j3 = c3.adjc & a3; }
-            uint32_t n0 = eq_bytes(cur.x, C_NL), n1 = eq_bytes(cur.y, C_NL), n2 = eq_bytes(cur.z, C_NL), n3 = eq_bytes(cur.w, C_NL);
-            if (first) clip4(n0, n1, n2, n3, pb, L, ~0u);
+        uint32_t tB, tA, tT, odd, nc;
+        digits_window<OP>(cur, carry, lane, tB, tA, tT, odd, nc);
+        if (__any_sync(FULL, odd != 0)) {
+            // the window with the '\n' (or something the path does not decide)
+            const uint32_t n0 = eq_bytes(cur.x, C_NL), n1 = eq_bytes(cur.y, C_NL), n2 = eq_bytes(cur.z, C_NL), n3 = eq_bytes(cur.w, C_NL);
             const unsigned ebal = __ballot_sync(FULL, (n0 | n1 | n2 | n3) != 0);
-            bool found = false;
-            uint32_t e = ~0u, ee = ~0u;                  // '\n'; end of the content (a stripped '\r' is not content)
-            if (ebal) {
-                const int src = __ffs(ebal) - 1;
-                int k = first_byte(n0, n1, n2, n3);
-                k = __shfl_sync(FULL, k, src);
-                e = wb + 16 * src + k; found = true; ee = e;
-                if (OP == OP_AF && strip_cr && e > lo && ldb(tin + e - 1) == '\r') ee = e - 1;
-            }
-            // digits at k in [L, ee) count; a pair (k-1, k) matters for k in [L, ee); a ':' or a high byte for k in [L, ee)
-            const uint32_t keep = lane_keep16(pb, L, ee);
-            const uint32_t k0 = nib80(keep, 0), k1 = nib80(keep, 1), k2 = nib80(keep, 2), k3 = nib80(keep, 3);
-            const uint32_t col = (eq_bytes(cur.x, 0x3A3A3A3Au) & k0) | (eq_bytes(cur.y, 0x3A3A3A3Au) & k1) |
-                                 (eq_bytes(cur.z, 0x3A3A3A3Au) & k2) | (eq_bytes(cur.w, 0x3A3A3A3Au) & k3);
-            const uint32_t bad = (j0 & k0) | (j1 & k1) | (j2 & k2) | (j3 & k3) | col | (cur.x & k0) | (cur.y & k1) | (cur.z & k2) | (cur.w & k3);
-            if (__any_sync(FULL, bad != 0)) return false;
-            // own bytes 0..14 that lie in [L, ee), and the byte before the lane if it does
-            const bool pin = pb != 0 && (pb - 1 >= L) && (pb - 1 < ee) && !(first && lane == 0);   // (lane 0 of the first window has no carry yet)
-            accB = dp4a_u(c0.D & k0, 0x01010101u, dp4a_u(c1.D & k1, 0x01010101u, dp4a_u(c2.D & k2, 0x01010101u, dp4a_u(c3.D & k3, 0x00010101u, accB + (pin ? ((pv >> 23) & 0x80u) : 0u)))));
-            accA = dp4a_u(c0.NZ & k0, 0x01010101u, dp4a_u(c1.NZ & k1, 0x01010101u, dp4a_u(c2.NZ & k2, 0x01010101u, dp4a_u(c3.NZ & k3, 0x00010101u, accA + (pin ? ((pv >> 22) & 0x80u) : 0u)))));
-            // (the last byte of lane 31 goes to the next window through `carry`; in the window with the '\n' it lies past it)
-            if (OP == OP_AC && !first) {
-                const uint32_t kt = lane_keep16(pb, 0u, e);
-                accT = dp4a_u(c0.TB & nib80(kt, 0), 0x01010101u, dp4a_u(c1.TB & nib80(kt, 1), 0x01010101u,
-                       dp4a_u(c2.TB & nib80(kt, 2), 0x01010101u, dp4a_u(c3.TB & nib80(kt, 3), 0x01010101u, accT))));
-            }
-            if (found) { out_a = accA >> 7; out_b = accB >> 7; out_tabs = accT >> 7; out_e = e; return true; }
-            first = false;
+            if (!ebal) return false;
+            const int src = __ffs(ebal) - 1;
+            int k = first_byte(n0, n1, n2, n3);
+            k = __shfl_sync(FULL, k, src);
+            const uint32_t e = wb + 16 * src + k;
+            uint32_t ee = e;                              // end of the content (a stripped '\r' is not content)
+            if (OP == OP_AF && strip_cr && e > lo && ldb(tin + e - 1) == '\r') ee = e - 1;
+            patch_outside(cur, wb + 16 * lane, 0u, ee, FILL);
+            digits_window<OP>(cur, carry, lane, tB, tA, tT, odd, nc);
+            if (__any_sync(FULL, odd != 0)) return false;
+            accB += tB; accA += tA; if (OP == OP_AC && !first) accT += tT;
+            out_a = accA >> 7; out_b = accB >> 7; out_tabs = accT >> 7; out_e = e;
+            return true;
         }
+        accB += tB; accA += tA; if (OP == OP_AC && !first) accT += tT;
+        if (lane == 0) carry = nc;
+        first = false;
         wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
         if (((wb >> 9) & 7u) == 0) {                      // every 8th window: L2 prefetch of the 4 KB that follow
             const uint32_t pf = wb + 10 * WINDOW + 128 * lane;
@@ -619,9 +624,6 @@ __device__ __forceinline__ bool line_digits(const uint8_t *__restrict__ tin, uin
     }
 }
 
-// ---------------------------------------------------------------------------------------
-// K1: the fused scan / parse / reduce kernel
-// ---------------------------------------------------------------------------------------
 // Row-record slots are reserved REC_BLOCK at a time: one atomic on the single global counter per 32 rows
 // (one per row is the kernel's bottleneck: same-address atomics serialise in L2).  The block's state lives in
 // shared memory, only lane 0 touches it; the slots a warp leaves unused are marked invalid when it exits.
@@ -648,6 +650,49 @@ template <int OP> struct TileState {
     bool md_add_nl;
     uint32_t offlattice_lines;              // VAR 1: lines whose first sample window was not on the tier-1 lattice
 };
+
+// One window of a line whose FORMAT has several keys (GT first), for the lane that holds its 16 bytes at p: the sample
+// that starts in the lane — if one does — decided from its first four bytes.  Returns true when the window holds
+// anything this does not decide (then nothing may be added for the window).
+//   allele_freq_calc (allele_freq_calc.cpp:262-293): "d sep d" closed by ':' or a tab is two alleles, ". sep ." is none
+//   hwe_tester (hwe_tester.cpp:339-378): "d sep d" and no third digit is a call (both alleles <= 1 count), ". sep ." is none
+template <int OP>
+__device__ __forceinline__ bool multikey_window(const uint4 v, const uint8_t *__restrict__ p, uint32_t &da, uint32_t &db, uint32_t &dc) {
+    // tab and '\n' markers by range: 3 adds and 2 LOP3 per word
+    const uint32_t a0 = VCFX_GE(v.x, 0x09), b0 = VCFX_GE(v.x, 0x0A), c0 = VCFX_GE(v.x, 0x0B);
+    const uint32_t a1 = VCFX_GE(v.y, 0x09), b1 = VCFX_GE(v.y, 0x0A), c1 = VCFX_GE(v.y, 0x0B);
+    const uint32_t a2 = VCFX_GE(v.z, 0x09), b2 = VCFX_GE(v.z, 0x0A), c2 = VCFX_GE(v.z, 0x0B);
+    const uint32_t a3 = VCFX_GE(v.w, 0x09), b3 = VCFX_GE(v.w, 0x0A), c3 = VCFX_GE(v.w, 0x0B);
+    const uint32_t tm0 = (a0 ^ b0) & M80, tm1 = (a1 ^ b1) & M80, tm2 = (a2 ^ b2) & M80, tm3 = (a3 ^ b3) & M80;
+    bool odd = (((b0 ^ c0) | (b1 ^ c1) | (b2 ^ c2) | (b3 ^ c3) | v.x | v.y | v.z | v.w) & M80) != 0;     // '\n' or a high byte
+    da = 0; db = 0; dc = 0;
+    if (tm0 | tm1 | tm2 | tm3) {
+        // one bit per byte of the lane (see the header phase), then the first tab's byte index
+        const uint32_t m16 = ((tm0 * 0x00204081u) >> 28) | (((tm1 * 0x00204081u) >> 24) & 0xF0u) |
+                             (((tm2 * 0x00204081u) >> 20) & 0xF00u) | (((tm3 * 0x00204081u) >> 16) & 0xF000u);
+        if (m16 & (m16 - 1u)) odd = true;            // two sample starts in 16 bytes
+        // the four bytes behind the tab: two aligned loads (L1: the bytes were streamed by this warp a moment ago)
+        const uint8_t *s = p + __ffs(m16);
+        const uint32_t *s4 = reinterpret_cast<const uint32_t *>((uintptr_t)s & ~(uintptr_t)3);
+        const uint32_t q = __funnelshift_r(__ldg(s4), __ldg(s4 + 1), 8u * (uint32_t)((uintptr_t)s & 3));
+        const uint32_t q1 = (q >> 8) & 0xFFu, q3 = q >> 24;
+        const bool sep = (q1 == '/') | (q1 == '|');
+        const uint32_t dg = q & 0x00FF00FFu;         // bytes 0 and 2
+        const bool two_digits = ((dg & 0x00F000F0u) == 0x00300030u) & ((((dg & 0x000F000Fu) + 0x00060006u) & 0x00100010u) == 0u);
+        if (OP == OP_AF) {
+            const bool end = (q3 == ':') | (q3 == '\t');
+            if (sep & end & two_digits) { db = 2; da = (uint32_t)((dg & 0x0000000Fu) != 0u) + (uint32_t)((dg & 0x000F0000u) != 0u); }
+            else if (!(sep & end & (dg == 0x002E002Eu))) odd = true;
+        } else {
+            const bool more = (q3 - 48u) <= 9u;
+            if (sep & two_digits & !more) {
+                const uint32_t al = dg & 0x000F000Fu;   // the two allele values
+                if ((al & 0x000E000Eu) == 0u) { const uint32_t c = (al & 1u) + (al >> 16); da = (c == 0); db = (c == 1); dc = (c == 2); }
+            } else if (!(sep & (dg == 0x002E002Eu))) odd = true;
+        }
+    }
+    return odd;
+}
 
 // Every line that starts in the tile, from st.ls on.  Two variants of the same text for allele_freq_calc and hwe_tester
 // (both inlined into the kernel, so that neither pays for the other's registers):
@@ -795,72 +840,47 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                 // rest of the tile) to the general variant; nothing of the line has been counted yet
                 if (HAS_VAR && !found && first_win) {
                     if (VAR == 0) { VCFX_SAVE_STATE(); return false; }
-                    ++st.offlattice_lines;
                 }
                 for (;;) {
                     // ---- steady state for a FORMAT with several keys (GT first): samples are tens of bytes long, so a
-                    // lane holds at most one sample start and almost all bytes only have to be searched for tabs.  Per
-                    // word: tab and '\n' markers by range (3 adds, 2 LOP3).  A lane that holds a tab fetches the four
-                    // bytes behind it (two aligned loads from L1: the load pipe is idle here) and decides the sample from
-                    // them.  The window with the '\n', a lane with two tabs, a byte >= 0x80 and every genotype that
-                    // needs more than four bytes leave the loop with nothing added, for the exact path below.
+                    // lane holds at most one sample start and almost all bytes only have to be searched for tabs
+                    // (multikey_window above).  Two windows per vote, two register pairs that alternate: each pair is loaded
+                    // again (four windows ahead) right after its own vote by load instructions of its own, so that a wait
+                    // for one window is not a wait for the newest load.  The window with the '\n', a lane with two tabs, a
+                    // byte >= 0x80 and every genotype that needs more than four bytes leave the loop with nothing added, for
+                    // the exact path below.
                     if (VAR == 1 && !first_win && !lat_possible && gt_index == 0) {
+                        uint4 nx3 = ld16(tin + wb + 3 * WINDOW + 16 * lane);
+                        int state = 0;                           // which pair met something odd: 1 = (cur, nxt), 2 = (nx2, nx3)
+                        const uint8_t *lp = tin + wb + 16 * lane;
+                        uint32_t it = 0;
                         for (;;) {
-                            uint32_t tm0, tm1, tm2, tm3, nl;
                             {
-                                const uint32_t a0_ = VCFX_GE(cur.x, 0x09), b0_ = VCFX_GE(cur.x, 0x0A), c0_ = VCFX_GE(cur.x, 0x0B);
-                                const uint32_t a1_ = VCFX_GE(cur.y, 0x09), b1_ = VCFX_GE(cur.y, 0x0A), c1_ = VCFX_GE(cur.y, 0x0B);
-                                const uint32_t a2_ = VCFX_GE(cur.z, 0x09), b2_ = VCFX_GE(cur.z, 0x0A), c2_ = VCFX_GE(cur.z, 0x0B);
-                                const uint32_t a3_ = VCFX_GE(cur.w, 0x09), b3_ = VCFX_GE(cur.w, 0x0A), c3_ = VCFX_GE(cur.w, 0x0B);
-                                tm0 = (a0_ ^ b0_) & M80; tm1 = (a1_ ^ b1_) & M80; tm2 = (a2_ ^ b2_) & M80; tm3 = (a3_ ^ b3_) & M80;
-                                nl = ((b0_ ^ c0_) | (b1_ ^ c1_) | (b2_ ^ c2_) | (b3_ ^ c3_) | cur.x | cur.y | cur.z | cur.w) & M80;   // '\n' or a high byte
+                                uint32_t da0, db0, dc0, da1, db1, dc1;
+                                const bool o0 = multikey_window<OP>(cur, lp, da0, db0, dc0);
+                                const bool o1 = multikey_window<OP>(nxt, lp + WINDOW, da1, db1, dc1);
+                                if (__any_sync(FULL, o0 | o1)) { state = 1; break; }
+                                ta += da0 + da1; tb += db0 + db1; tc += dc0 + dc1;
+                                cur = ld16(lp + 4 * WINDOW); nxt = ld16(lp + 5 * WINDOW);
                             }
-                            bool odd = nl != 0;                  // this window is not for the fast loop
-                            uint32_t da = 0, db = 0, dc = 0;
-                            if (tm0 | tm1 | tm2 | tm3) {
-                                // one bit per byte of the lane (see the header phase), then the first tab's byte index
-                                const uint32_t m16 = ((tm0 * 0x00204081u) >> 28) | (((tm1 * 0x00204081u) >> 24) & 0xF0u) |
-                                                     (((tm2 * 0x00204081u) >> 20) & 0xF00u) | (((tm3 * 0x00204081u) >> 16) & 0xF000u);
-                                if (m16 & (m16 - 1u)) odd = true;   // two sample starts in 16 bytes
-                                const uint8_t *p = tin + wb + 16 * lane + __ffs(m16);        // first byte of the sample
-                                const uint32_t *p4 = reinterpret_cast<const uint32_t *>((uintptr_t)p & ~(uintptr_t)3);
-                                const uint32_t q = __funnelshift_r(__ldg(p4), __ldg(p4 + 1), 8u * (uint32_t)((uintptr_t)p & 3));
-                                const uint32_t g30 = VCFX_GE(q, 0x30), g31 = VCFX_GE(q, 0x31), g3a = VCFX_GE(q, 0x3A);
-                                const uint32_t g2f = VCFX_GE(q, 0x2F), g7c = VCFX_GE(q, 0x7C), g7d = VCFX_GE(q, 0x7D);
-                                const uint32_t D = (g30 ^ g3a) & M80, S = (g2f ^ g30 ^ g7c ^ g7d) & M80;
-                                if (q & M80) odd = true;
-                                if (OP == OP_AF) {
-                                    // allele_freq_calc.cpp:262-293 on "t sep t <end>" and "t <end>", t a digit or '.', <end> = tab ':' '\n'
-                                    const uint32_t g09 = VCFX_GE(q, 0x09), g0b = VCFX_GE(q, 0x0B), g3b = VCFX_GE(q, 0x3B), g2e = VCFX_GE(q, 0x2E);
-                                    const uint32_t E = (g09 ^ g0b ^ g3a ^ g3b) & M80, NZ = (g31 ^ g3a) & M80, TK = ((g2e ^ g2f) | D) & M80;
-                                    if (((TK & 0x00800080u) | (S & 0x00008000u) | (E & 0x80000000u)) == M80) {
-                                        db = __popc(D & 0x00800080u); da = __popc(NZ & 0x00800080u);
-                                    } else if (((TK & 0x00000080u) | (E & 0x00008000u)) == 0x00008080u) {
-                                        db = (D >> 7) & 1u; da = (NZ >> 7) & 1u;
-                                    } else odd = true;
-                                } else {
-                                    // hwe_tester.cpp:339-378 on the four bytes: digit sep digit non-digit is a call (alleles <= 1 count);
-                                    // a second digit in either place or a leading blank needs the scalar parser; the rest is no call
-                                    const uint32_t g32 = VCFX_GE(q, 0x32);
-                                    const uint32_t O = (g31 ^ g32) & M80, L1 = (g30 ^ g32) & M80;
-                                    const uint32_t b0 = q & 0xFFu;
-                                    if ((D & 0x00000080u) && (S & 0x00008000u) && (D & 0x00800000u)) {
-                                        if (D & 0x80000000u) odd = true;
-                                        else if ((L1 & 0x00800080u) == 0x00800080u) {
-                                            const uint32_t c = __popc(O & 0x00800080u);
-                                            da = (c == 0); db = (c == 1); dc = (c == 2);
-                                        }
-                                    } else if (((D & 0x00008080u) == 0x00008080u) || b0 == ' ' || b0 == '\r') odd = true;
-                                }
+                            {
+                                uint32_t da0, db0, dc0, da1, db1, dc1;
+                                const bool o0 = multikey_window<OP>(nx2, lp + 2 * WINDOW, da0, db0, dc0);
+                                const bool o1 = multikey_window<OP>(nx3, lp + 3 * WINDOW, da1, db1, dc1);
+                                if (__any_sync(FULL, o0 | o1)) { state = 2; break; }
+                                ta += da0 + da1; tb += db0 + db1; tc += dc0 + dc1;
+                                nx2 = ld16(lp + 6 * WINDOW); nx3 = ld16(lp + 7 * WINDOW);
                             }
-                            if (__any_sync(FULL, odd)) break;    // nothing was added for this window
-                            ta += da; tb += db; tc += dc;
-                            wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
-                            if (((wb >> 9) & 7u) == 0) {          // every 8th window: L2 prefetch of the 4 KB that follow
-                                const uint32_t pf = wb + 12 * WINDOW + 128 * lane;
-                                if (pf < nrel) prefetch_l2(tin + pf);
+                            if ((++it & 1u) == 0) {              // every second iteration (4 KiB): L2 prefetch of the 4 KiB that follow the loads
+                                const uint8_t *pf = lp - 16 * lane + 16 * WINDOW + 128 * lane;
+                                if ((uint32_t)(pf - tin) < nrel) prefetch_l2(pf);
                             }
+                            lp += 4 * WINDOW;
                         }
+                        // back to the three windows the rest of the line loop works with: cur = the first window not added
+                        wb = (uint32_t)(lp - tin) - 16u * (uint32_t)lane;
+                        if (state == 2) { const uint4 t_ = cur; wb += 2 * WINDOW; cur = nx2; nxt = nx3; nx2 = t_; }
+                        // (the first window of the pair may be a regular one: the exact path below takes it all the same)
                     }
                     // ---- steady state: rounds of two raw tier-1 windows, one vote per round, two register sets.
                     // A lane reads its 16 bytes plus the word after them (20 contiguous bytes: no shuffles, no
@@ -1427,6 +1447,11 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                             const int incl = warp_incl_scan((int)len, lane);
                             const uint32_t off = (uint32_t)incl - len;
                             const uint32_t btot = (uint32_t)__shfl_sync(FULL, incl, 31);
+                            // the write pass never stores past the bytes the size pass gave this tile (speculative sizes can be
+                            // too small: a count of two digits) nor past the output buffer; the chunk is then run again, exact
+                            if (P.ac_pass && opos + btot > min((unsigned long long)P.out_cap, P.tile_base[tile] + P.tile_out[tile])) {
+                                if (lane == 0) atomicOr(&P.stats->overflow, 4ULL);
+                            } else
                             if (P.ac_pass) {
                                 const bool staged = btot <= AC_STAGE;
                                 // staged at the destination's offset modulo 16: the flush is aligned 128-bit copies
@@ -1496,9 +1521,17 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
 #ifndef VCFX_PARSE_CTAS
 #define VCFX_PARSE_CTAS 4
 #endif
-template <int OP>
+// Two kernels for allele_freq_calc and hwe_tester, launched one after the other over the same tiles, so that each is
+// compiled (registers, schedule) on its own:
+//   VAR 0  the lattice kernel: tier 1 + the exact path.  In a tile it stops at the first line whose first sample
+//          window is not tier-1 material, leaves the tile's state (next line, lines and output bytes so far) behind
+//          and goes on to the next tile
+//   VAR 1  the general kernel: picks up exactly those tiles where they were left and finishes them (digit path,
+//          skip-ahead loop for multi-key FORMATs, tier 1 and the exact path); it exits at once when none was left
+// The other operations have one kernel (VAR 0, never stops early).
+template <int OP, int VAR>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (OP == OP_VC) ? 5 : VCFX_PARSE_CTAS)
-vcfx_scan_kernel(const KParams P) {
+vcfx_scan_kernel(const VCFX_GRID_CONSTANT KParams P) {
     __shared__ uint32_t s_tp[WARPS_PER_CTA][12];
     __shared__ __align__(16) uint8_t s_stage[(OP == OP_AC) ? WARPS_PER_CTA * (AC_STAGE + 32) : 16];
     const int lane = lane_id();
@@ -1506,6 +1539,7 @@ vcfx_scan_kernel(const KParams P) {
     const uint64_t n = P.n;
     const bool strip_cr = (OP == OP_HWE) || (P.mode == MODE_FILE && (OP == OP_AF || OP == OP_VC || OP == OP_MD));
     if (OP == OP_AC && P.ac_pass && P.stats->overflow) return;
+    if (VAR == 1 && P.stats->n_unfinished == 0) return;
 
     // per-warp event counters live in shared memory (fire-and-forget adds from lane 0) and are folded into
     // DevStats after every tile; the slot index is the field's index in DevStats
@@ -1522,13 +1556,14 @@ vcfx_scan_kernel(const KParams P) {
     WarpShared ws;
     ws.tp = s_tp[wid]; ws.stage0 = s_stage + ((OP == OP_AC) ? wid * (AC_STAGE + 32) : 0); ws.cnt = s_cnt[wid];
     ws.rec_base = &s_rec_base[wid]; ws.rec_used = &s_rec_used[wid]; ws.odd = s_odd; ws.reg = s_reg; ws.tag = s_tag;
-    int var = 0;                                 // allele_freq_calc / hwe_tester: the variant the next tile starts with
 
     for (;;) {
         uint32_t tile = 0;
-        if (lane == 0) tile = atomicAdd(P.ticket, 1u);
+        if (lane == 0) tile = atomicAdd(VAR == 1 ? P.ticket2 : P.ticket, 1u);
         tile = __shfl_sync(FULL, tile, 0);
         if (tile >= P.n_tiles) break;
+        uint32_t resume = RESUME_DONE;
+        if (VAR == 1) { resume = P.tile_resume[tile]; if (resume == RESUME_DONE) continue; }
 
         const uint64_t a = (uint64_t)tile * P.tile_bytes;
         const uint64_t b = min(a + (uint64_t)P.tile_bytes, n);
@@ -1540,7 +1575,8 @@ vcfx_scan_kernel(const KParams P) {
 
         // ---- first line start in [a, b): byte 0 of the chunk, or one past a '\n' at >= a-1
         uint32_t ls = rb;                                   // "none"
-        if (a == 0) ls = 0;
+        if (VAR == 1) ls = resume;
+        else if (a == 0) ls = 0;
         else {
             const uint32_t from = ra - 1, to = rb - 1;      // '\n' positions that give a start < b
             uint32_t wb = from & ~15u;
@@ -1564,19 +1600,27 @@ vcfx_scan_kernel(const KParams P) {
         s_tag[wid] = 0;                                     // no line of this tile has used the exact-path counters yet
         TileState<OP> st;
         st.ls = ls; st.nlines = 0; st.out_bytes = 0; st.md_prev_end = ls; st.md_last_end = ls; st.md_add_nl = false; st.offlattice_lines = 0;
-        if (OP == OP_AF || OP == OP_HWE) {
-            if (var == 0 && !tile_lines<OP, 0>(P, ws, lane, strip_cr, tile, a, a0, tin, rb, nrel, n, st)) var = 1;
-            if (var == 1) {
-                tile_lines<OP, 1>(P, ws, lane, strip_cr, tile, a, a0, tin, rb, nrel, n, st);
-                if (st.offlattice_lines == 0) var = 0;      // nothing but lattice lines: the next tile starts with the lattice variant
+        if (VAR == 1) { st.nlines = P.tile_lines[tile]; st.out_bytes = (typename OutCount<OP>::type)P.tile_out[tile]; }
+        const uint32_t lines_before = st.nlines;
+        const bool finished = tile_lines<OP, VAR>(P, ws, lane, strip_cr, tile, a, a0, tin, rb, nrel, n, st);
+        if (!finished) {
+            // (VAR 0 of allele_freq_calc / hwe_tester only) the rest of the tile is the general kernel's
+            if (lane == 0) { P.tile_lines[tile] = st.nlines; P.tile_out[tile] = st.out_bytes; P.tile_resume[tile] = st.ls; atomicAdd(&P.stats->n_unfinished, 1ULL); }
+            VCFX_COUNT(C_LINES, st.nlines);
+            __syncwarp();
+            if (lane < CNT_SLOTS) {
+                const unsigned int v = s_cnt[wid][lane];
+                if (v) { s_cnt[wid][lane] = 0; atomicAdd(reinterpret_cast<unsigned long long *>(P.stats) + lane, (unsigned long long)v); }
             }
-        } else tile_lines<OP, 0>(P, ws, lane, strip_cr, tile, a, a0, tin, rb, nrel, n, st);
+            __syncwarp();
+            continue;
+        }
         const uint32_t nlines = st.nlines;
         typename OutCount<OP>::type out_bytes = st.out_bytes;
         const uint32_t md_prev_end = st.md_prev_end, md_last_end = st.md_last_end;
         const bool md_add_nl = st.md_add_nl;
 
-        if (!(OP == OP_AC && P.ac_pass)) VCFX_COUNT(C_LINES, nlines);
+        if (!(OP == OP_AC && P.ac_pass)) VCFX_COUNT(C_LINES, VAR == 1 ? nlines - lines_before : nlines);
         if (OP == OP_MD) {
             const uint32_t tail = md_last_end - md_prev_end;
             if (lane == 0) {
@@ -1873,6 +1917,14 @@ md_copy_kernel(const KParams P) {
             if ((P.tail_len[t] >> 31) && lane == 0) o[len] = '\n';
         }
     }
+}
+
+// hwe_pvalue() of vcfx_numfmt.cuh over an array of (homRef, het, homAlt) triples: the measuring stick for the one
+// operation of the path that is not bit-identical by construction (exp)
+__global__ void __launch_bounds__(256)
+hwe_pvalue_kernel(const int32_t *__restrict__ counts, size_t n, double *__restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = hwe_pvalue(counts[3 * i], counts[3 * i + 1], counts[3 * i + 2]);
 }
 
 }  // namespace vcfx

@@ -191,7 +191,6 @@ int main(int argc, char *argv[]) {
     }
 
     // ---- fixed header + body
-    std::string out;                       // only used with -z
     vcfxh::RunOptions opt;
     opt.op = VCFX_OP_ALLELE_COUNT;
     opt.mode = input ? VCFX_MODE_FILE : VCFX_MODE_STDIN;
@@ -212,20 +211,31 @@ int main(int argc, char *argv[]) {
     }
     opt.sel_col = cols;
     for (uint32_t c : cols) opt.sel_names.push_back(names[c]);
-    if (gzip_out) opt.capture = &out; else vcfxh::write_all(1, header.data(), header.size());
+    // -z: the text is gzipped piece by piece as the chunks come back (gzdopen(dup(1), "wb6") like the reference's
+    // GzipWriter, allele_counter.cpp:431-514), never held in memory as a whole
+    gzFile gz = nullptr;
+    bool gz_failed = false;
+    if (gzip_out) {
+        int dupfd = dup(1);
+        gz = dupfd >= 0 ? gzdopen(dupfd, "wb6") : nullptr;
+        if (!gz) { if (dupfd >= 0) close(dupfd); fprintf(stderr, "Error: cannot open gzip stream on stdout\n"); vcfxh::finish(1); }
+        auto put = [&gz, &gz_failed](const char *p, size_t n) {
+            while (n) {
+                const unsigned k = (unsigned)std::min<size_t>(n, 1u << 30);
+                const int w = gzwrite(gz, p, k);
+                if (w <= 0) { gz_failed = true; return false; }
+                p += w; n -= (size_t)w;
+            }
+            return true;
+        };
+        if (!put(header.data(), header.size())) { fprintf(stderr, "Error: gzip write failed\n"); vcfxh::finish(1); }
+        opt.sink = put;
+    } else vcfxh::write_all(1, header.data(), header.size());
     vcfxh::Totals tot;
     std::string err;
     int rc = vcfxh::run_stream(src, opt, tot, err);
     if (input) close(fd);
-    if (rc != VCFX_OK) { fprintf(stderr, "Error: %s\n", err.c_str()); vcfxh::finish(1); }
-    if (gzip_out) {                        // gzdopen(dup(1), "wb6") like the reference's GzipWriter
-        int dupfd = dup(1);
-        gzFile gz = dupfd >= 0 ? gzdopen(dupfd, "wb6") : nullptr;
-        if (!gz) { vcfxh::write_all(1, header.data(), header.size()); vcfxh::write_all(1, out.data(), out.size()); return 0; }
-        gzwrite(gz, header.data(), (unsigned)header.size());
-        size_t pos = 0;
-        while (pos < out.size()) { unsigned k = (unsigned)std::min<size_t>(out.size() - pos, 1u << 30); gzwrite(gz, out.data() + pos, k); pos += k; }
-        gzclose(gz);
-    }
+    if (gz) { if (gzclose(gz) != Z_OK) gz_failed = true; }
+    if (rc != VCFX_OK || gz_failed) { fprintf(stderr, "Error: %s\n", gz_failed ? "gzip write failed" : err.c_str()); vcfxh::finish(1); }
     vcfxh::finish(0);
 }

@@ -10,6 +10,9 @@
 #include <unistd.h>
 #include <zlib.h>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <thread>
 
 namespace vcfxh {
@@ -209,20 +212,85 @@ int env_device() {
     return e ? atoi(e) : 0;
 }
 
+// VCFX_CUDA_DEVICES=0,1,2,3 (or "all"): one context per GPU in this one process, chunks dealt round-robin and drained
+// in submission order — the text leaves in file order, exactly as with one GPU (the reference's own decomposition at
+// thread level: allele_counter.cpp:870-947 cuts the data into newline-aligned ranges and writes the results in order).
+std::vector<int> env_devices() {
+    std::vector<int> d;
+    const char *e = getenv("VCFX_CUDA_DEVICES");
+    if (e && *e) {
+        if (strcmp(e, "all") == 0) {
+            int n = 0;
+            vcfx_cuda_device_count(&n);
+            for (int i = 0; i < n; ++i) d.push_back(i);
+        } else {
+            const char *p = e;
+            while (*p) {
+                char *end = nullptr;
+                long v = strtol(p, &end, 10);
+                if (end == p) break;
+                if (v >= 0) d.push_back((int)v);
+                p = (*end == ',') ? end + 1 : end;
+                if (*end && *end != ',') break;
+            }
+        }
+    }
+    if (d.empty()) d.push_back(env_device());
+    return d;
+}
+
 namespace {
 
+// Finished text goes to the output descriptor on a thread of its own, in order: while chunk k is being written
+// (a pipe or a file can be slow) the main thread reads and submits the next chunk and the library copies chunk
+// k+1 back from the device.  A slot's pinned output buffer is handed to a new chunk only after its text was written
+// (wait_done before the slot is acquired again).
+class Writer {
+  public:
+    Writer(int fd) : fd_(fd), th_([this] { loop(); }) {}
+    ~Writer() { { std::lock_guard<std::mutex> g(m_); stop_ = true; } cv_.notify_all(); th_.join(); }
+    void push(const char *p, size_t n) { { std::lock_guard<std::mutex> g(m_); q_.push_back({p, n}); ++pushed_; } cv_.notify_all(); }
+    // block until the first k pieces are written (pieces are pushed one per drained chunk, in order)
+    void wait_done_at_least(long k) { std::unique_lock<std::mutex> g(m_); cv_.wait(g, [&] { return done_ >= std::min(k, pushed_); }); }
+    bool failed() { std::lock_guard<std::mutex> g(m_); return failed_; }
+
+  private:
+    void loop() {
+        for (;;) {
+            std::pair<const char *, size_t> it;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                it = q_.front(); q_.pop_front();
+            }
+            bool ok = true;
+            { std::lock_guard<std::mutex> g(m_); ok = !failed_; }
+            if (ok && !write_all(fd_, it.first, it.second)) { std::lock_guard<std::mutex> g(m_); failed_ = true; }   // like the reference, a closed pipe is not an error
+            { std::lock_guard<std::mutex> g(m_); ++done_; }
+            cv_.notify_all();
+        }
+    }
+    int fd_;
+    std::mutex m_; std::condition_variable cv_;
+    std::deque<std::pair<const char *, size_t>> q_;
+    long pushed_ = 0, done_ = 0;
+    bool stop_ = false, failed_ = false;
+    std::thread th_;
+};
+
 struct Drain {
-    vcfx_ctx *ctx; const RunOptions &opt; Totals &tot; uint64_t line_base = 0; bool write_failed = false;
+    std::vector<vcfx_ctx *> ctxs; const RunOptions &opt; Totals &tot; Writer *writer = nullptr; uint64_t line_base = 0;
     long drained = 0, final_index = -1;
     int one(std::string &err) {
         const char *text = nullptr; size_t n = 0; vcfx_chunk_stats st;
+        vcfx_ctx *ctx = ctxs[(size_t)drained % ctxs.size()];        // chunks were dealt round-robin: the oldest one is this context's
         int rc = vcfx_cuda_next_output(ctx, &text, &n, &st);
         if (rc != VCFX_OK) { err = std::string(vcfx_cuda_strerror(rc)) + ": " + vcfx_cuda_last_error(ctx); return rc; }
-        if (n) {
-            if (opt.capture) opt.capture->append(text, n);
-            else if (opt.capture_final && drained == final_index) opt.capture_final->append(text, n);
-            else if (!write_failed && !write_all(opt.out_fd, text, n)) write_failed = true;   // like the reference, a closed pipe is not an error
-        }
+        if (opt.capture) { if (n) opt.capture->append(text, n); }
+        else if (opt.capture_final && drained == final_index) { if (n) opt.capture_final->append(text, n); }
+        else if (opt.sink) { if (n && !opt.sink(text, n)) { err = "output sink failed"; return VCFX_E_INVALID; } }
+        else if (writer) writer->push(text, n);        // (empty pieces too: the writer's count follows the chunks)
         tot.bytes_in += st.bytes_in; tot.bytes_out += st.bytes_out; tot.data_lines += st.data_lines;
         tot.rows += st.rows; tot.flagged += st.flagged; tot.pre_header += st.pre_header;
         tot.short_lines += st.short_lines; tot.dots_terminated += st.dots_terminated;
@@ -262,30 +330,48 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
     const bool timing = getenv("VCFX_TIMING") != nullptr;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_start = now(), t_read = 0, t_submit = 0, t_drain = 0, t_acquire = 0;
-    vcfx_ctx *ctx = nullptr;
-    int rc = vcfx_cuda_create(&cfg, &ctx);
+    const std::vector<int> devices = env_devices();
+    std::vector<vcfx_ctx *> ctxs;
+    int rc = VCFX_OK;
+    auto destroy_all = [&ctxs] { for (vcfx_ctx *c : ctxs) vcfx_cuda_destroy(c); ctxs.clear(); };
+    for (int dev : devices) {
+        vcfx_ctx *c = nullptr;
+        cfg.device = dev;
+        rc = vcfx_cuda_create(&cfg, &c);
+        if (rc != VCFX_OK) { err = vcfx_cuda_strerror(rc); destroy_all(); return rc; }
+        ctxs.push_back(c);
+    }
+    const size_t G = ctxs.size();
     double t_create = now() - t_start;
-    if (rc != VCFX_OK) { err = vcfx_cuda_strerror(rc); return rc; }
+    auto in_flight_total = [&ctxs] { long k = 0; for (vcfx_ctx *c : ctxs) k += vcfx_cuda_in_flight(c); return k; };
 
-    Drain drain{ctx, opt, tot};
+    const bool direct = !opt.capture && !opt.sink;
+    Writer *writer = direct ? new Writer(opt.out_fd) : nullptr;
+    struct WriterGuard { Writer *w; ~WriterGuard() { delete w; } } writer_guard{writer};     // joins after the last piece is out
+    Drain drain{ctxs, opt, tot, writer};
+    const long n_slots = (long)cfg.n_slots * (long)G;     // pinned output buffers in rotation over all the contexts
     std::string carry = opt.preface;
     bool eof = false, chrom_seen = false, in_hash_block = true;
     long submitted = 0;
     while (!eof) {
         char *buf = nullptr; size_t cap = 0;
+        vcfx_ctx *ctx = ctxs[(size_t)submitted % G];                 // this chunk's GPU
         double t0 = now();
         rc = vcfx_cuda_acquire_input(ctx, &buf, &cap);
         t_acquire += now() - t0;
         while (rc == VCFX_E_BUSY) {
             t0 = now();
-            if ((rc = drain.one(err)) != VCFX_OK) { vcfx_cuda_destroy(ctx); return rc; }
+            if ((rc = drain.one(err)) != VCFX_OK) { destroy_all(); return rc; }
             t_drain += now() - t0;
             t0 = now();
             rc = vcfx_cuda_acquire_input(ctx, &buf, &cap);
             t_acquire += now() - t0;
         }
         t0 = now();
-        if (rc != VCFX_OK) { err = std::string(vcfx_cuda_strerror(rc)) + ": " + vcfx_cuda_last_error(ctx); vcfx_cuda_destroy(ctx); return rc; }
+        if (rc != VCFX_OK) { err = std::string(vcfx_cuda_strerror(rc)) + ": " + vcfx_cuda_last_error(ctx); destroy_all(); return rc; }
+        // the slot just acquired held the chunk n_slots back (drained by now): its text must have left the pinned
+        // output buffer before this chunk's text can land there
+        if (writer) writer->wait_done_at_least(submitted - n_slots + 1);
         // bytes already in hand (the tail of the previous chunk, or what the caller consumed while
         // looking at the header) go first; the source is only read once they fit
         size_t have = std::min(carry.size(), cap);
@@ -293,7 +379,7 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
         carry.erase(0, have);
         while (have < cap && carry.empty()) {
             long r = src.read(buf + have, cap - have);
-            if (r < 0) { err = "read error"; vcfx_cuda_destroy(ctx); return VCFX_E_INVALID; }
+            if (r < 0) { err = "read error"; destroy_all(); return VCFX_E_INVALID; }
             if (r == 0) { eof = true; break; }
             have += (size_t)r;
         }
@@ -301,7 +387,7 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
         size_t nbytes = have;
         if (!eof) {
             const char *nl = static_cast<const char *>(memrchr(buf, '\n', have));
-            if (!nl) { err = "a line is longer than the chunk size (set VCFX_CHUNK_BYTES)"; vcfx_cuda_destroy(ctx); return VCFX_E_INVALID; }
+            if (!nl) { err = "a line is longer than the chunk size (set VCFX_CHUNK_BYTES)"; destroy_all(); return VCFX_E_INVALID; }
             nbytes = (size_t)(nl - buf) + 1;
             carry.insert(0, buf + nbytes, have - nbytes);
         } else if (opt.last_unterminated_line && nbytes && buf[nbytes - 1] != '\n') {
@@ -338,22 +424,23 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
         rc = vcfx_cuda_submit(ctx, nbytes, &info);
         t_submit += now() - t0;
         ++submitted;
-        if (rc != VCFX_OK) { err = std::string(vcfx_cuda_strerror(rc)) + ": " + vcfx_cuda_last_error(ctx); vcfx_cuda_destroy(ctx); return rc; }
-        if (opt.stop_at_first_short && vcfx_cuda_in_flight(ctx) >= 2) {
+        if (rc != VCFX_OK) { err = std::string(vcfx_cuda_strerror(rc)) + ": " + vcfx_cuda_last_error(ctx); destroy_all(); return rc; }
+        if (opt.stop_at_first_short && in_flight_total() >= 2) {
             // --strict only needs the first short line: check as chunks complete, stop early
-            if ((rc = drain.one(err)) != VCFX_OK) { vcfx_cuda_destroy(ctx); return rc; }
+            if ((rc = drain.one(err)) != VCFX_OK) { destroy_all(); return rc; }
             if (tot.short_lines) break;
         }
     }
     double t0 = now();
-    while (vcfx_cuda_in_flight(ctx) > 0)
-        if ((rc = drain.one(err)) != VCFX_OK) { vcfx_cuda_destroy(ctx); return rc; }
+    while (in_flight_total() > 0)
+        if ((rc = drain.one(err)) != VCFX_OK) { destroy_all(); return rc; }
+    if (writer) writer->wait_done_at_least(submitted);
     t_drain += now() - t0;
     t0 = now();
-    if (!opt.skip_destroy) vcfx_cuda_destroy(ctx);
+    if (!opt.skip_destroy) destroy_all();
     if (timing)
-        fprintf(stderr, "[vcfx timing] create %.3f acquire %.3f read %.3f submit %.3f drain %.3f destroy %.3f total %.3f s, kernels %.3f ms, %ld chunks\n",
-                t_create, t_acquire, t_read, t_submit, t_drain, now() - t0, now() - t_start, tot.kernel_ms, submitted);
+        fprintf(stderr, "[vcfx timing] create %.3f acquire %.3f read %.3f submit %.3f drain %.3f destroy %.3f total %.3f s, kernels %.3f ms, %ld chunks, %zu GPU(s)\n",
+                t_create, t_acquire, t_read, t_submit, t_drain, now() - t0, now() - t_start, tot.kernel_ms, submitted, G);
     return VCFX_OK;
 }
 

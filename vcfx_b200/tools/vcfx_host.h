@@ -7,6 +7,7 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -66,6 +67,8 @@ struct RunOptions {
     std::vector<std::string> sel_names;
     // when set, the text is appended here instead of being written to out_fd
     std::string *capture = nullptr;
+    // when set, every piece of text is handed to this function instead (in order; false = stop with an error)
+    std::function<bool(const char *, size_t)> sink;
     // when set, only the text of the FINAL chunk is held back here (everything before is written)
     std::string *capture_final = nullptr;
     // keeps a copy of the last line of the input when it has no '\n' (missing_detector's quirk)
@@ -80,6 +83,7 @@ struct RunOptions {
 int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err_text);
 
 int env_device();
+std::vector<int> env_devices();       // VCFX_CUDA_DEVICES=0,1,.. | all (else the one device of VCFX_CUDA_DEVICE)
 // flush stdio and leave without running the CUDA runtime's exit handlers (they cost up to a second)
 [[noreturn]] void finish(int rc);
 bool write_all(int fd, const char *p, size_t n);
