@@ -369,9 +369,9 @@ def e2e_stream(api, ctx, shard, valid_abs, steps):
         for (s, e) in shard.bounds:
             vf = min(max(valid_abs - s, 0), e - s)
             while not ctx.submit_host(base_ptr + s, e - s, valid_from=vf, is_final=(e == shard.nbytes)):
-                out, st, _ = ctx.next_output(); rows += st.rows; nout += len(out)
+                _, n, st = ctx.next_output_raw(); rows += st.rows; nout += n      # the text is in the library's pinned buffer: on the host
         while ctx.in_flight():
-            out, st, _ = ctx.next_output(); rows += st.rows; nout += len(out)
+            _, n, st = ctx.next_output_raw(); rows += st.rows; nout += n
         return rows, nout
     step()
     t0 = time.perf_counter()

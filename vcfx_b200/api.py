@@ -238,6 +238,13 @@ class Context:
             events = list(arr[: got.value])
         return out, st, events
 
+    def next_output_raw(self):
+        """Like next_output, without copying the text out of the library's pinned buffer: (address, length, stats).
+        The buffer is valid until the next call on this context."""
+        text = C.c_void_p(); n = C.c_size_t(); st = ChunkStats()
+        self._check(self._l.vcfx_cuda_next_output(self._h, C.byref(text), C.byref(n), C.byref(st)))
+        return text.value, n.value, st
+
     # -- device-resident path ------------------------------------------------------------
     def run_device(self, d_in: int, nbytes: int, d_out: int, out_cap: int, valid_from: int = 0, is_final: bool = True):
         info = ChunkInfo(valid_from, int(is_final), 0)

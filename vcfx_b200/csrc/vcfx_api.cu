@@ -5,7 +5,10 @@
 #include "vcfx_kernels.cuh"
 
 #include <algorithm>
+#include <cctype>
 #include <cstdio>
+#include <cstdlib>
+#include <sched.h>
 #include <cstring>
 #include <new>
 #include <string>
@@ -495,9 +498,62 @@ void vcfx_cuda_destroy(vcfx_ctx *ctx) {
     delete ctx;
 }
 
+// Pinned staging memory should live on the NUMA node the GPU hangs off: with several GPUs fed from one node's memory
+// the host fabric, not PCIe, limits the copies (round 1: 22.8 GB/s per GPU at 8 GPUs against 54.7 alone).  Linux
+// places pages on the node of the thread that first touches them, and cudaMallocHost touches them in the calling
+// thread: for the duration of the allocations the thread is bound to the cores sysfs lists as local to the GPU
+// (/sys/bus/pci/devices/<id>/local_cpulist).  VCFX_NUMA=0 switches it off; a box without NUMA information is untouched.
+class NumaBind {
+  public:
+    explicit NumaBind(int device) {
+#ifndef VCFX_EMU
+        const char *e = getenv("VCFX_NUMA");
+        if (e && *e == '0') return;
+        char bus[32] = {0};
+        if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return; }
+        for (char *c = bus; *c; ++c) *c = (char)tolower((unsigned char)*c);
+        std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+        FILE *f = fopen(path.c_str(), "r");
+        if (!f) return;
+        char line[1024] = {0};
+        const bool got = fgets(line, sizeof line, f) != nullptr;
+        fclose(f);
+        if (!got) return;
+        cpu_set_t want; CPU_ZERO(&want);
+        int n_want = 0;
+        for (const char *p = line; *p && *p != '\n';) {
+            char *end = nullptr;
+            long a = strtol(p, &end, 10);
+            if (end == p) break;
+            long b = a;
+            if (*end == '-') { p = end + 1; b = strtol(p, &end, 10); }
+            for (long c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET((int)c, &want); ++n_want; }
+            p = (*end == ',') ? end + 1 : end;
+        }
+        if (sched_getaffinity(0, sizeof old_, &old_) != 0) return;
+        cpu_set_t both; CPU_AND(&both, &want, &old_);
+        if (CPU_COUNT(&both) == 0 || CPU_COUNT(&both) == CPU_COUNT(&old_)) return;      // nothing local we may use, or nothing to narrow
+        if (sched_setaffinity(0, sizeof both, &both) == 0) bound_ = true;
+#else
+        (void)device;
+#endif
+    }
+    ~NumaBind() {
+#ifndef VCFX_EMU
+        if (bound_) sched_setaffinity(0, sizeof old_, &old_);
+#endif
+    }
+    bool bound() const { return bound_; }
+
+  private:
+    cpu_set_t old_;
+    bool bound_ = false;
+};
+
 static int ensure_slot(vcfx_ctx *ctx, Slot &s) {
     if (s.h_in) return VCFX_OK;
     CU(cudaSetDevice(ctx->device));
+    NumaBind numa(ctx->device);
     CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&s.ev_shared_done, cudaEventDisableTiming));

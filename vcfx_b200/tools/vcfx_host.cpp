@@ -330,7 +330,25 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
     const bool timing = getenv("VCFX_TIMING") != nullptr;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_start = now(), t_read = 0, t_submit = 0, t_drain = 0, t_acquire = 0;
-    const std::vector<int> devices = env_devices();
+    std::vector<int> devices = env_devices();
+    // One GPU: hide the others from the CUDA runtime before it initialises (it would set up every visible GPU — on an
+    // 8-GPU box that is most of a tool's wall time).  VCFX_CUDA_DEVICE counts within CUDA_VISIBLE_DEVICES when that is set.
+    if (devices.size() == 1 && !getenv("VCFX_KEEP_VISIBLE")) {
+        const char *vis = getenv("CUDA_VISIBLE_DEVICES");
+        std::string pick;
+        if (!vis || !*vis) pick = std::to_string(devices[0]);
+        else {
+            std::string v(vis);
+            size_t pos = 0; int k = 0;
+            while (pos <= v.size()) {
+                size_t c = v.find(',', pos);
+                if (c == std::string::npos) c = v.size();
+                if (k == devices[0]) { pick = v.substr(pos, c - pos); break; }
+                pos = c + 1; ++k;
+            }
+        }
+        if (!pick.empty()) { setenv("CUDA_VISIBLE_DEVICES", pick.c_str(), 1); devices[0] = 0; }
+    }
     std::vector<vcfx_ctx *> ctxs;
     int rc = VCFX_OK;
     auto destroy_all = [&ctxs] { for (vcfx_ctx *c : ctxs) vcfx_cuda_destroy(c); ctxs.clear(); };
