@@ -79,6 +79,7 @@ inline void *dyn_smem() { return g_dyn_smem; }
 static inline void emu_mask(unsigned m) { if (m != 0xFFFFFFFFu) { fprintf(stderr, "emu: partial warp mask %08x not supported\n", m); abort(); } }
 static inline unsigned __ballot_sync(unsigned m, int p) { emu_mask(m); return (unsigned)emu::collective(emu::OP_BALLOT, p ? 1 : 0, 0); }
 static inline int __any_sync(unsigned m, int p) { emu_mask(m); return (int)emu::collective(emu::OP_ANY, p ? 1 : 0, 0); }
+static inline int __all_sync(unsigned m, int p) { emu_mask(m); return !(int)emu::collective(emu::OP_ANY, p ? 0 : 1, 0); }
 static inline void __syncwarp(unsigned m = 0xFFFFFFFFu) { emu_mask(m); emu::collective(emu::OP_SYNCWARP, 0, 0); }
 static inline void __syncthreads() { emu::collective(emu::OP_SYNCTHREADS, 0, 0); }
 static inline unsigned __reduce_add_sync(unsigned m, unsigned v) { emu_mask(m); return (unsigned)emu::collective(emu::OP_REDUCE_ADD, v, 0); }

@@ -97,6 +97,9 @@ struct vcfx_ctx {
     uint32_t n_sel = 0, max_col = 0;
     uint32_t *d_sel_col = nullptr, *d_name_off = nullptr;
     uint8_t *d_names = nullptr;
+    uint4 *d_names16 = nullptr;          // one zero-padded 16-byte slot per selected name + tab, when they all have the same length
+    uint32_t name_len = 0;
+    bool ac_bulk = false;                // VCFX_AC_BULK=1: staged rows leave shared memory through cp.async.bulk
     int ac_fmt = 0;
     bool ac_ident = false;               // allele_counter selection = columns 0 .. n_sel-1 in order
     bool ac_exact = false;               // a chunk had a count of two digits: rows are sized by parsing from now on
@@ -303,7 +306,7 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
     P.tile_lines = w.tile_lines; P.tile_out = w.tile_out; P.tile_base = w.tile_base; P.line_base = w.line_base;
     P.tail_start = w.tail_start; P.tail_len = w.tail_len; P.tail_off = w.tail_off;
     P.ac_fmt = ctx->ac_fmt; P.ac_ident = ctx->ac_ident ? 1 : 0; P.ac_pass = 0; P.ac_spec = (ctx->cfg.op == VCFX_OP_ALLELE_COUNT && ctx->ac_fmt == AC_TEXT_MT && !ctx->ac_exact) ? 1 : 0; P.n_sel = ctx->n_sel; P.sel_col = ctx->d_sel_col; P.name_off = ctx->d_name_off;
-    P.names = ctx->d_names; P.max_col = ctx->max_col; P.col_scratch = w.col_scratch;
+    P.names = ctx->d_names; P.names16 = ctx->d_names16; P.name_len = ctx->name_len; P.ac_bulk = ctx->ac_bulk ? 1 : 0; P.max_col = ctx->max_col; P.col_scratch = w.col_scratch;
     P.ticket = w.ticket; P.ticket2 = w.ticket + 1; P.tile_resume = w.tile_resume; P.recs = w.recs; P.rec_prefix = w.rec_prefix; P.rec_cap = w.rec_cap;
     P.stats = w.d_stats; P.events = w.events; P.ev_cap = EVENT_CAP;
 
@@ -469,6 +472,18 @@ int vcfx_cuda_create(const vcfx_cfg *cfg, vcfx_ctx **out) {
         CUC(cudaMemcpy(ctx->d_sel_col, cols.data(), sizeof(uint32_t) * cfg->n_sel, cudaMemcpyHostToDevice));
         CUC(cudaMemcpy(ctx->d_name_off, cfg->sel_name_off, sizeof(uint32_t) * (cfg->n_sel + 1), cudaMemcpyHostToDevice));
         CUC(cudaMemcpy(ctx->d_names, cfg->sel_names, nb, cudaMemcpyHostToDevice));
+        // the fast row writer needs every name (with its tab) to have the same length, at most 12 bytes
+        uint32_t nl = cfg->sel_name_off[1] - cfg->sel_name_off[0];
+        for (uint32_t i = 1; i < cfg->n_sel && nl; ++i) if (cfg->sel_name_off[i + 1] - cfg->sel_name_off[i] != nl) nl = 0;
+        if (nl >= 1 && nl <= 12 && !getenv("VCFX_AC_SLOW_ROWS")) {
+            std::vector<unsigned char> n16((size_t)cfg->n_sel * 16, 0);
+            for (uint32_t i = 0; i < cfg->n_sel; ++i) memcpy(&n16[(size_t)i * 16], cfg->sel_names + cfg->sel_name_off[i], nl);
+            CUC(cudaMalloc(&ctx->d_names16, n16.size()));
+            CUC(cudaMemcpy(ctx->d_names16, n16.data(), n16.size(), cudaMemcpyHostToDevice));
+            ctx->name_len = nl;
+            const char *be = getenv("VCFX_AC_BULK");
+            ctx->ac_bulk = be && *be == '1';
+        }
     }
     if (cfg->stream) { ctx->dev_stream = (cudaStream_t)cfg->stream; ctx->dev_stream_owned = false; }
     else { CUC(cudaStreamCreateWithFlags(&ctx->dev_stream, cudaStreamNonBlocking)); ctx->dev_stream_owned = true; }
@@ -494,7 +509,7 @@ void vcfx_cuda_destroy(vcfx_ctx *ctx) {
     if (ctx->dev_stream) cudaStreamSynchronize(ctx->dev_stream);
     free_work(ctx->dev_work);
     if (ctx->dev_stream_owned && ctx->dev_stream) cudaStreamDestroy(ctx->dev_stream);
-    cudaFree(ctx->d_sel_col); cudaFree(ctx->d_name_off); cudaFree(ctx->d_names);
+    cudaFree(ctx->d_sel_col); cudaFree(ctx->d_name_off); cudaFree(ctx->d_names); cudaFree(ctx->d_names16);
     delete ctx;
 }
 

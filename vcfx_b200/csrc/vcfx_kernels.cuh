@@ -99,6 +99,9 @@ struct KParams {
     const uint32_t *sel_col;         // [n_sel] sample column (running maximum in the forward modes)
     const uint32_t *name_off;        // [n_sel + 1] offsets into names
     const uint8_t *names;            // selected names, each followed by a tab
+    const uint4 *names16;            // [n_sel] the same, one 16-byte zero-padded slot per sample, when all are name_len bytes long
+    int32_t ac_bulk;                 // flush the staged rows with cp.async.bulk (shared -> global) instead of 128-bit stores
+    uint32_t name_len;               // bytes of every selected name + its tab (<= 12), 0 when they differ: the fast row writer is off
     uint32_t max_col;                // 1 + largest selected column
     uint2 *col_scratch;              // [resident warps][max_col] (ref, alt) of the current line
     unsigned int *ticket;            // dynamic tile counter (zeroed before launch)
@@ -445,6 +448,29 @@ __device__ __forceinline__ void warp_flush_smem(uint8_t *dst, const uint8_t *st,
     if (lane < (int)(n - done)) dst[done + lane] = st[done + lane];
 }
 
+// The same flush with the 16-byte aligned middle handed to the bulk-copy engine: ONE cp.async.bulk (shared -> global,
+// the 1-D TMA path: UBLKCP in SASS) issued by lane 0 instead of a loop of 128-bit stores by all lanes.  The staged bytes
+// were written through the generic proxy, so a proxy fence comes first; wait_group.read returns when the engine has read
+// the shared memory (the global writes may still be in flight), i.e. when the buffer may be reused.
+__device__ __forceinline__ void warp_flush_smem_bulk(uint8_t *dst, const uint8_t *st, uint32_t n, int lane) {
+#ifdef VCFX_EMU
+    warp_flush_smem(dst, st, n, lane);
+#else
+    const uint32_t head = min(n, (uint32_t)((16 - ((uintptr_t)dst & 15)) & 15));
+    if (lane < (int)head) dst[lane] = st[lane];
+    const uint32_t nq = (n - head) >> 4;
+    if (lane == 0 && nq) {
+        const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(st + head);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst + head), "r"(saddr), "r"(nq << 4) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    const uint32_t done = head + (nq << 4);
+    if (lane < (int)(n - done)) dst[done + lane] = st[done + lane];
+#endif
+}
+
 // Tier-1 check of one window (warp-uniform phase and separator): every lane's four rotated words
 // must be [0|1, sep, 0|1, tab].  y = x ^ pat is then [a, 0, b, 0] with a, b the allele values.
 // Returns false (and changes nothing) when any lane disagrees.
@@ -638,6 +664,7 @@ __device__ __forceinline__ unsigned long long alloc_slot(unsigned long long *rec
 struct WarpShared {
     volatile uint32_t *tp;                 // positions of tabs 1..9 of the current line
     uint8_t *stage0;                       // allele_counter row staging
+    uint32_t *u;                           // allele_counter: the bytes all rows of the current line share (see the fast row writer)
     unsigned int *cnt;                     // event counters (CNT_SLOTS)
     unsigned long long *rec_base; unsigned int *rec_used;
     volatile unsigned int *odd, *reg, *tag;   // [WARPS_PER_CTA] arrays (indexed by the warp)
@@ -1432,6 +1459,32 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                             out_bytes += (unsigned long long)n_rows * (prefix_len + 4u) + (P.name_off[n_rows] - P.name_off[0]);
                             n_rows_done = n_rows; n_rows = 0;
                         }
+                        // ---- the fast row writer (write pass, text rows, every selected name of the same length NL <= 12 with its
+                        // tab, counts of one digit): all rows of a line then have the same length L = prefix + NL + 4 and differ in
+                        // 16 bytes.  Lane i assembles the ALIGNED WORDS its row covers in the staging buffer from registers: the bytes
+                        // every row shares (U, built once per line: the prefix, and around it what the neighbours put there — the
+                        // last 3 bytes of the row before, "\t a \n", and the first 3 of the row after, again the prefix), its own
+                        // name and digits shifted into place, all of it rotated by the row's misalignment.  Neighbouring lanes write
+                        // the words they share with identical contents, so no byte stores and no ordering are needed.
+                        const uint32_t NL = P.name_len;
+                        const bool fast_line = P.ac_pass && text && NL != 0u && extra_tabs == 0u && prefix_src <= 40u && prefix_src >= 1u;
+                        const uint32_t L = prefix_src + NL + 4u;
+                        if (fast_line) {
+                            __syncwarp();
+                            if (lane < 20) {
+                                uint32_t w = 0;
+#pragma unroll
+                                for (uint32_t bb = 0; bb < 4; ++bb) {
+                                    const uint32_t pp = 4u * (uint32_t)lane + bb;                 // position in the lane's view of its row
+                                    uint32_t byte = 0;
+                                    if (pp >= 3u && pp < 3u + prefix_src) byte = ldb(tin + ls + pp - 3u);
+                                    else if (pp >= 3u + L && pp < 6u + L) byte = ldb(tin + ls + pp - 3u - L);
+                                    w |= byte << (8u * bb);
+                                }
+                                ws.u[lane] = w;
+                            }
+                            __syncwarp();
+                        }
                         for (uint32_t i0 = 0; i0 < n_rows; i0 += 32) {
                             const uint32_t i = i0 + lane;
                             int vr = 0, va = 0; uint32_t len = 0, noff = 0, nlen = 0;
@@ -1451,6 +1504,48 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                             // too small: a count of two digits) nor past the output buffer; the chunk is then run again, exact
                             if (P.ac_pass && opos + btot > min((unsigned long long)P.out_cap, P.tile_base[tile] + P.tile_out[tile])) {
                                 if (lane == 0) atomicOr(&P.stats->overflow, 4ULL);
+                            } else
+                            if (fast_line && __all_sync(FULL, i >= n_rows || ((uint32_t)vr <= 9u && (uint32_t)va <= 9u))) {
+                                uint32_t *sw = reinterpret_cast<uint32_t *>(stage0);
+                                const uint32_t o = (uint32_t)((uintptr_t)(P.out + opos) & 15) + (uint32_t)lane * L;   // the row's place in the staging buffer
+                                const uint32_t sh = 8u * (3u - (o & 3u));
+                                const uint32_t a_prev = __shfl_up_sync(FULL, (uint32_t)va, 1);
+                                if (i < n_rows) {
+                                    const uint32_t tl = 0x000A0009u | ((48u + a_prev) << 8);              // "\t a \n" of the row before
+                                    // the row's own 16 bytes: name and tab (zero padded), then r '\t' a '\n' at byte NL
+                                    const uint4 nm = __ldg(P.names16 + i);
+                                    const uint32_t T = (48u + (uint32_t)vr) | (0x09u << 8) | ((48u + (uint32_t)va) << 16) | (0x0Au << 24);
+                                    const uint32_t ti = NL >> 2, ts = 8u * (NL & 3u);
+                                    const uint32_t Tlo = T << ts, Thi = ts ? (T >> (32u - ts)) : 0u;
+                                    const uint32_t v0 = nm.x | (ti == 0 ? Tlo : 0u);
+                                    const uint32_t v1 = nm.y | (ti == 1 ? Tlo : 0u) | (ti == 0 ? Thi : 0u);
+                                    const uint32_t v2 = nm.z | (ti == 2 ? Tlo : 0u) | (ti == 1 ? Thi : 0u);
+                                    const uint32_t v3 = nm.w | (ti == 3 ? Tlo : 0u) | (ti == 2 ? Thi : 0u);
+                                    // ... moved up to byte (3 + prefix) & 3 of word q = (3 + prefix) >> 2 of the lane's view
+                                    const uint32_t q = (3u + prefix_src) >> 2, sv = 8u * ((3u + prefix_src) & 3u);
+                                    const uint32_t s0 = __funnelshift_l(0u, v0, sv), s1 = __funnelshift_l(v0, v1, sv), s2 = __funnelshift_l(v1, v2, sv);
+                                    const uint32_t s3 = __funnelshift_l(v2, v3, sv), s4 = __funnelshift_l(v3, 0u, sv);
+                                    const uint32_t nw = ((o & 3u) + L + 3u) >> 2;                          // aligned words the row touches
+                                    uint32_t *dw = sw + (o >> 2);
+                                    // words that hold shared bytes only
+                                    for (uint32_t k = 0; k + 1u < q; ++k) {
+                                        const uint32_t lo_ = ws.u[k] | (k == 0u ? tl : 0u), hi_ = ws.u[k + 1];
+                                        dw[k] = __funnelshift_r(lo_, hi_, sh);
+                                    }
+                                    // the six words around the row's own bytes
+                                    const uint32_t c_1 = ws.u[q - 1] | (q == 1u ? tl : 0u);
+                                    const uint32_t c0 = ws.u[q] | s0, c1 = ws.u[q + 1] | s1, c2 = ws.u[q + 2] | s2, c3 = ws.u[q + 3] | s3, c4 = ws.u[q + 4] | s4, c5 = ws.u[q + 5];
+                                    if (q - 1u < nw) dw[q - 1] = __funnelshift_r(c_1, c0, sh);
+                                    if (q < nw) dw[q] = __funnelshift_r(c0, c1, sh);
+                                    if (q + 1u < nw) dw[q + 1] = __funnelshift_r(c1, c2, sh);
+                                    if (q + 2u < nw) dw[q + 2] = __funnelshift_r(c2, c3, sh);
+                                    if (q + 3u < nw) dw[q + 3] = __funnelshift_r(c3, c4, sh);
+                                    if (q + 4u < nw) dw[q + 4] = __funnelshift_r(c4, c5, sh);
+                                }
+                                __syncwarp();
+                                if (P.ac_bulk) warp_flush_smem_bulk(P.out + opos, stage0 + (uint32_t)((uintptr_t)(P.out + opos) & 15), btot, lane);
+                                else warp_flush_smem(P.out + opos, stage0 + (uint32_t)((uintptr_t)(P.out + opos) & 15), btot, lane);
+                                __syncwarp();
                             } else
                             if (P.ac_pass) {
                                 const bool staged = btot <= AC_STAGE;
@@ -1534,6 +1629,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (OP == OP_VC) ? 5 : VCFX_P
 vcfx_scan_kernel(const VCFX_GRID_CONSTANT KParams P) {
     __shared__ uint32_t s_tp[WARPS_PER_CTA][12];
     __shared__ __align__(16) uint8_t s_stage[(OP == OP_AC) ? WARPS_PER_CTA * (AC_STAGE + 32) : 16];
+    __shared__ uint32_t s_u[(OP == OP_AC) ? WARPS_PER_CTA : 1][20];
     const int lane = lane_id();
     const int wid = threadIdx.x >> 5;
     const uint64_t n = P.n;
@@ -1554,7 +1650,7 @@ vcfx_scan_kernel(const VCFX_GRID_CONSTANT KParams P) {
     if (lane == 0) { s_rec_base[wid] = 0; s_rec_used[wid] = REC_BLOCK; }
     __syncwarp();
     WarpShared ws;
-    ws.tp = s_tp[wid]; ws.stage0 = s_stage + ((OP == OP_AC) ? wid * (AC_STAGE + 32) : 0); ws.cnt = s_cnt[wid];
+    ws.tp = s_tp[wid]; ws.stage0 = s_stage + ((OP == OP_AC) ? wid * (AC_STAGE + 32) : 0); ws.cnt = s_cnt[wid]; ws.u = s_u[(OP == OP_AC) ? wid : 0];
     ws.rec_base = &s_rec_base[wid]; ws.rec_used = &s_rec_used[wid]; ws.odd = s_odd; ws.reg = s_reg; ws.tag = s_tag;
 
     for (;;) {
@@ -1846,15 +1942,25 @@ __device__ __forceinline__ void warp_copy_words(uint8_t *dst, const uint8_t *src
 }
 
 template <int WS>   // WS = whole 32-bit words of misalignment between src and the 16-byte grid of dst
-__device__ __forceinline__ void copy16_loop(uint4 *d16, const uint4 *s16, uint32_t nq, uint32_t bs, int lane) {
-    for (uint32_t i = lane; i < nq; i += 32) {
-        const uint4 A = __ldg(s16 + i), B = __ldg(s16 + i + 1);
-        const uint32_t w[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
-        uint4 o;
-        o.x = __funnelshift_r(w[WS], w[WS + 1], bs); o.y = __funnelshift_r(w[WS + 1], w[WS + 2], bs);
-        o.z = __funnelshift_r(w[WS + 2], w[WS + 3], bs); o.w = __funnelshift_r(w[WS + 3], w[WS + 4], bs);
-        d16[i] = o;
+__device__ __forceinline__ uint4 realign16(const uint4 A, const uint4 B, uint32_t bs) {
+    const uint32_t w[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
+    uint4 o;
+    o.x = __funnelshift_r(w[WS], w[WS + 1], bs); o.y = __funnelshift_r(w[WS + 1], w[WS + 2], bs);
+    o.z = __funnelshift_r(w[WS + 2], w[WS + 3], bs); o.w = __funnelshift_r(w[WS + 3], w[WS + 4], bs);
+    return o;
+}
+// Four 512-byte rows per iteration: all the loads of an iteration are issued before its first store (the copy is bound by
+// the latency of the loads, not by their number), and a 16-byte source block that two stores need is loaded once.
+template <int WS>
+__device__ __forceinline__ void copy16_loop(uint4 *__restrict__ d16, const uint4 *__restrict__ s16, uint32_t nq, uint32_t bs, int lane) {
+    uint32_t i = lane;
+    for (; i + 96 < nq; i += 128) {
+        const uint4 A0 = __ldg(s16 + i), B0 = __ldg(s16 + i + 1), A1 = __ldg(s16 + i + 32), B1 = __ldg(s16 + i + 33);
+        const uint4 A2 = __ldg(s16 + i + 64), B2 = __ldg(s16 + i + 65), A3 = __ldg(s16 + i + 96), B3 = __ldg(s16 + i + 97);
+        d16[i] = realign16<WS>(A0, B0, bs); d16[i + 32] = realign16<WS>(A1, B1, bs);
+        d16[i + 64] = realign16<WS>(A2, B2, bs); d16[i + 96] = realign16<WS>(A3, B3, bs);
     }
+    for (; i < nq; i += 32) d16[i] = realign16<WS>(__ldg(s16 + i), __ldg(s16 + i + 1), bs);
 }
 
 __device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint32_t n, int lane) {
@@ -1864,10 +1970,17 @@ __device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint
     dst += head; src += head; n -= head;
     const uint32_t nq = n >> 4;                                   // 16-byte stores
     const uint32_t mis = (uint32_t)((uintptr_t)src & 15);
-    const uint4 *s16 = reinterpret_cast<const uint4 *>(src - mis);
-    uint4 *d16 = reinterpret_cast<uint4 *>(dst);
+    const uint4 *__restrict__ s16 = reinterpret_cast<const uint4 *>(src - mis);
+    uint4 *__restrict__ d16 = reinterpret_cast<uint4 *>(dst);
     const uint32_t bs = 8u * (mis & 3u);
-    if (mis == 0) { for (uint32_t i = lane; i < nq; i += 32) d16[i] = __ldg(s16 + i); }
+    if (mis == 0) {
+        uint32_t i = lane;
+        for (; i + 96 < nq; i += 128) {
+            const uint4 a = __ldg(s16 + i), b = __ldg(s16 + i + 32), c = __ldg(s16 + i + 64), d = __ldg(s16 + i + 96);
+            d16[i] = a; d16[i + 32] = b; d16[i + 64] = c; d16[i + 96] = d;
+        }
+        for (; i < nq; i += 32) d16[i] = __ldg(s16 + i);
+    }
     else switch (mis >> 2) {                                      // the last block read ends < 32 B past src + n (pad)
         case 0: copy16_loop<0>(d16, s16, nq, bs, lane); break;
         case 1: copy16_loop<1>(d16, s16, nq, bs, lane); break;
