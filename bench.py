@@ -388,7 +388,7 @@ def config_entries(torch, np, api, synth, O, dev, peak, threads, only=None):
     names = [b"HG%05d" % (96 + i) for i in range(SAMPLES)]
     sel = dict(sel_cols=list(range(SAMPLES)), sel_names=names)
     plans = [
-        ("C2", 2, C2_VARIANTS, [("hwe_tester", api.OP_HWE, 0, {}, 20000)]),
+        ("C2", 2, C2_VARIANTS, [("hwe_tester", api.OP_HWE, 0, {}, 20000), ("nonref_filter", api.OP_NONREF_FILTER, 0, {}, 20000)]),
         ("C3", 3, C2_VARIANTS, [("missing_detector", api.OP_MISSING_DETECT, 0, {}, 20000),
                                 ("allele_counter", api.OP_ALLELE_COUNT, 0, sel, 4000),
                                 ("allele_counter -a", api.OP_ALLELE_COUNT, api.F_AC_AGGREGATE, sel, 400),
@@ -404,14 +404,14 @@ def config_entries(torch, np, api, synth, O, dev, peak, threads, only=None):
         log(f"[bench] {cname}: {sh.nbytes / 1e9:.2f} GB, {V} variants generated in {sh.gen_s:.1f}s")
         for tname, op, flags, kw, ref_variants in tools:
             out_cap = 64 << 20
-            if op == api.OP_MISSING_DETECT:
+            if op in (api.OP_MISSING_DETECT, api.OP_NONREF_FILTER):
                 out_cap = sh.nbytes + sh.nbytes // 50 + (1 << 20)
             if op == api.OP_ALLELE_COUNT and flags == 0:
                 out_cap = int(sh.nbytes * 9.5) + (1 << 20)
             d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
             ctx = api.Context(op, api.FILE, flags=flags, **kw)
             ctx.set_line_hint(sh.line_len)
-            vf = api.find_chrom_header(sh.hdr) if op == api.OP_ALLELE_FREQ else (api.first_data_offset(sh.hdr) if op == api.OP_MISSING_DETECT else 0)
+            vf = api.find_chrom_header(sh.hdr) if op in (api.OP_ALLELE_FREQ, api.OP_NONREF_FILTER) else (api.first_data_offset(sh.hdr) if op == api.OP_MISSING_DETECT else 0)
             ms = []
             for i in range(5):
                 ctx.run_device(sh.d_in.data_ptr(), sh.nbytes, d_out.data_ptr(), out_cap, valid_from=vf)
@@ -469,7 +469,7 @@ def parity_vs_reference(api, O, np, shard, tname, n_variants):
     """GPU tool output (through the C ABI, FILE semantics) against the stdout of the unmodified reference tool
     on the first n_variants lines of the shard."""
     tool = {"hwe_tester": "hwe_tester", "allele_freq_calc": "allele_freq_calc", "missing_detector": "missing_detector",
-            "allele_counter": "allele_counter", "allele_counter -a": "allele_counter", "variant_counter": "variant_counter"}[tname]
+            "allele_counter": "allele_counter", "allele_counter -a": "allele_counter", "variant_counter": "variant_counter", "nonref_filter": "nonref_filter"}[tname]
     exe = ref_tool(tool)
     data = shard.prefix_bytes(np, n_variants)
     if tname == "hwe_tester":
@@ -478,6 +478,8 @@ def parity_vs_reference(api, O, np, shard, tname, n_variants):
         got = api.allele_freq_calc(data, api.FILE).out; args = ["-q", "-i"]
     elif tname == "missing_detector":
         got = api.missing_detector(data, api.FILE).out; args = ["-q", "-t", "1", "-i"]   # default threads abort on dotted files >= 10 MB (SURVEY finding 2)
+    elif tname == "nonref_filter":
+        got = api.nonref_filter(data, api.FILE).out; args = ["-i"]
     elif tname == "allele_counter":
         got = api.allele_counter(data, api.AC_MT_TEXT, api.AC_TEXT).out; args = ["-q", "-i"]
     elif tname == "allele_counter -a":
@@ -488,7 +490,7 @@ def parity_vs_reference(api, O, np, shard, tname, n_variants):
     if exe is None:
         # no reference binary on this box: the CPU restatement (pinned to the reference by tests/) stands in
         fn = {"hwe_tester": lambda: O.hwe(data, 0), "allele_freq_calc": lambda: O.allele_freq(data, 0), "missing_detector": lambda: O.missing(data, 0),
-              "allele_counter": lambda: O.allele_counter(data), "allele_counter -a": lambda: O.allele_counter(data, O.AC_UNIFIED, O.AC_AGGREGATE),
+              "nonref_filter": lambda: O.nonref_filter(data, 0), "allele_counter": lambda: O.allele_counter(data), "allele_counter -a": lambda: O.allele_counter(data, O.AC_UNIFIED, O.AC_AGGREGATE),
               "variant_counter": lambda: O.variant_count(data, 0)}[tname]
         exp = fn().out
         res.update({"against": "oracle port (reference binary not built on this box)", "equal": exp == got})

@@ -49,7 +49,8 @@ typedef enum {
     VCFX_OP_ALLELE_FREQ    = 1,
     VCFX_OP_HWE            = 2,
     VCFX_OP_MISSING_DETECT = 3,
-    VCFX_OP_ALLELE_COUNT   = 4
+    VCFX_OP_ALLELE_COUNT   = 4,
+    VCFX_OP_NONREF_FILTER  = 5    /* VCFX_nonref_filter.cpp:458-548 filterNonRefMmap, :553-631 filterNonRef */
 } vcfx_op;
 
 typedef enum {

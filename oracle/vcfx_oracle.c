@@ -4,7 +4,7 @@
  * Not shipped, not linked into libvcfx_cuda, never used as a fallback: it exists so the
  * parity tests can compare the CUDA path against the reference's semantics on any input,
  * including on the GPU box where /root/reference is absent.  It is pinned against the
- * compiled reference tools (oracle/_ref/VCFX_*) by tests/test_oracle_vs_reference.py and
+ * compiled reference tools (oracle/_ref/VCFX_*) by tests/test_oracle_golden.py and
  * against tests/golden/.
  *
  * Written from the behaviour of the reference (file:line cited per rule), organised
@@ -529,6 +529,137 @@ static int md_stdin(const char *in, size_t n, oracle_result *r) {
 int oracle_missing(const char *in, size_t n, int mode, oracle_result *r) {
     res_init(r);
     return mode == ORACLE_FILE ? md_file(in, n, r) : md_stdin(in, n, r);
+}
+
+/* ------------------------------------------------------------------ nonref_filter (§8 f2: a sibling tool on the same
+ * scan -> GT -> per-line predicate shape).  A data line is dropped when EVERY sample is "definitely" homozygous
+ * reference; everything else passes through, each written line closed by '\n'. */
+
+/* VCFX_nonref_filter.cpp:286-302 (file mode, inlined in allSamplesHomRefDirect): a GT of exactly three bytes must be
+ * 0/0 or 0|0; any other non-empty GT is hom-ref when it holds nothing but '0', '/' and '|'. */
+static int nr_homref_file(const char *g, const char *ge) {
+    size_t n = (size_t)(ge - g);
+    if (n == 3) return g[0] == '0' && (g[1] == '/' || g[1] == '|') && g[2] == '0';
+    if (n == 0) return 0;
+    for (const char *p = g; p < ge; ++p) if (*p != '/' && *p != '|' && *p != '0') return 0;
+    return 1;
+}
+/* :419-449 isDefinitelyHomRef (stdin mode): empty is not; otherwise nothing but '0', '/' and '|' (the special cases in
+ * front of the general scan decide the same way) */
+static int nr_homref_stdin(const char *g, const char *ge) {
+    if (g == ge) return 0;
+    for (const char *p = g; p < ge; ++p) if (*p != '/' && *p != '|' && *p != '0') return 0;
+    return 1;
+}
+/* :179-198 extractNthField: the n-th ':' piece of [s,e), empty when there are fewer */
+static void nr_nth_piece(const char *s, const char *e, int k, const char **gs, const char **ge) {
+    const char *fs = s; int idx = 0;
+    for (const char *p = s; p <= e; ++p) {
+        if (p == e || *p == ':') {
+            if (idx == k) { *gs = fs; *ge = p; return; }
+            ++idx; fs = p + 1;
+        }
+    }
+    *gs = *ge = e;
+}
+/* :224-231 skipToField: start of field k (k tabs passed), NULL when the line has fewer tabs */
+static const char *nr_skip(const char *p, const char *e, int k) {
+    int idx = 0;
+    while (p < e && idx < k) { if (*p == '\t') ++idx; ++p; }
+    return idx == k ? p : NULL;
+}
+
+static int nr_file(const char *in, size_t n, oracle_result *r) {       /* :458-548 filterNonRefMmap */
+    obuf o = {0}; size_t pos = 0; line_t ln; int header = 0;
+    while (next_line(in, n, &pos, &ln)) {
+        const char *s = ln.s, *e = ln.e;
+        if (e > s && e[-1] == '\r') --e;                               /* :484-486 */
+        if (s == e) { ob_ch(&o, '\n'); continue; }                     /* :489-493 */
+        if (*s == '#') {                                               /* :496-504 */
+            ob_put(&o, s, (size_t)(e - s)); ob_ch(&o, '\n');
+            if (e - s >= 6 && memcmp(s + 1, "CHROM", 5) == 0) header = 1;
+            continue;
+        }
+        r->data_lines++;
+        int keep = 1;
+        if (!header) r->warnings++;                                    /* :507-512 passes the line */
+        else {
+            const char *f = nr_skip(s, e, 8);                          /* :515 */
+            if (f) {
+                const char *fe = f; while (fe < e && *fe != '\t') ++fe;
+                int gi = oracle_gt_index(f, (size_t)(fe - f));         /* :317-335 findGTIndex, :526-529 (the cache changes nothing) */
+                if (gi >= 0) {
+                    const char *p = nr_skip(s, e, 9);                  /* :248-309 allSamplesHomRefDirect */
+                    if (p) {
+                        int all = 1;
+                        while (p < e) {
+                            const char *se = p; while (se < e && *se != '\t') ++se;
+                            if (se == p) { all = 0; break; }           /* empty sample: keep */
+                            const char *gs, *ge;
+                            if (gi == 0) { gs = p; ge = memchr(p, ':', (size_t)(se - p)); if (!ge) ge = se; }
+                            else nr_nth_piece(p, se, gi, &gs, &ge);
+                            if (!nr_homref_file(gs, ge)) { all = 0; break; }
+                            p = se; if (p < e && *p == '\t') ++p;
+                        }
+                        if (all) keep = 0;
+                    }
+                }
+            }
+        }
+        if (keep) { ob_put(&o, s, (size_t)(e - s)); ob_ch(&o, '\n'); r->rows++; }
+    }
+    res_take(r, &o);
+    return 0;
+}
+
+static int nr_stdin(const char *in, size_t n, oracle_result *r) {      /* :553-631 filterNonRef */
+    obuf o = {0}; size_t pos = 0; line_t ln; int header = 0;
+    while (next_line(in, n, &pos, &ln)) {
+        const char *s = ln.s, *e = ln.e;                               /* getline: '\r' stays */
+        if (s == e) { ob_ch(&o, '\n'); continue; }
+        if (*s == '#') {
+            ob_put(&o, s, (size_t)(e - s)); ob_ch(&o, '\n');
+            if (e - s >= 6 && memcmp(s, "#CHROM", 6) == 0) header = 1;
+            continue;
+        }
+        r->data_lines++;
+        int keep = 1;
+        if (!header) r->warnings++;
+        else {
+            int tabs = 0; for (const char *p = s; p < e; ++p) tabs += (*p == '\t');
+            if (tabs + 1 >= 10) {                                      /* :578-582 */
+                const char *f = nr_skip(s, e, 8), *fe = f; while (fe < e && *fe != '\t') ++fe;
+                /* FORMAT split on ':' with std::getline (:584-590): a piece equal to "GT"; the pieces std::getline
+                 * drops (nothing after a final ':', nothing at all for an empty string) never equal "GT" */
+                int gi = oracle_gt_index(f, (size_t)(fe - f));
+                if (gi >= 0) {
+                    int all = 1;
+                    const char *p = fe + 1;                            /* field 9 (exists: >= 9 tabs) */
+                    for (;;) {
+                        const char *se = p; while (se < e && *se != '\t') ++se;
+                        /* the sample split on ':' with std::getline (:610-616): pieces = ':' count + 1, minus one when
+                         * the sample is empty or ends with ':' */
+                        int pieces = 0;
+                        if (se > p) { pieces = 1; for (const char *q = p; q < se; ++q) pieces += (*q == ':'); if (se[-1] == ':') --pieces; }
+                        if (gi >= pieces) { all = 0; break; }          /* :618-621 */
+                        const char *gs, *ge; nr_nth_piece(p, se, gi, &gs, &ge);
+                        if (!nr_homref_stdin(gs, ge)) { all = 0; break; }
+                        if (se >= e) break;
+                        p = se + 1;
+                    }
+                    if (all) keep = 0;
+                }
+            }
+        }
+        if (keep) { ob_put(&o, s, (size_t)(e - s)); ob_ch(&o, '\n'); r->rows++; }
+    }
+    res_take(r, &o);
+    return 0;
+}
+
+int oracle_nonref_filter(const char *in, size_t n, int mode, oracle_result *r) {
+    res_init(r);
+    return mode == ORACLE_FILE ? nr_file(in, n, r) : nr_stdin(in, n, r);
 }
 
 /* ------------------------------------------------------------------ variant_counter */

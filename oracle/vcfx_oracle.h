@@ -7,7 +7,7 @@
  *
  * Every function restates, in plain C, what one reference tool does to a whole VCF held in
  * memory; the reference file:line each rule comes from is cited in vcfx_oracle.c.
- * Pinning: tests/test_oracle_vs_reference.py checks it byte-for-byte against the compiled
+ * Pinning: tests/test_oracle_golden.py checks it byte-for-byte against the compiled
  * reference tools (oracle/_ref/VCFX_*, built by oracle/Makefile from /root/reference) on the
  * reference test-suite's cases and on seeded fuzz inputs, and tests/golden/ holds outputs
  * of those reference binaries.
@@ -48,6 +48,7 @@ void oracle_free(oracle_result *r);
 int oracle_allele_freq(const char *in, size_t n, int mode, oracle_result *r);
 int oracle_hwe(const char *in, size_t n, int mode, oracle_result *r);
 int oracle_missing(const char *in, size_t n, int mode, oracle_result *r);
+int oracle_nonref_filter(const char *in, size_t n, int mode, oracle_result *r);   /* VCFX_nonref_filter (§8 f2) */
 int oracle_variant_count(const char *in, size_t n, int mode, int strict, oracle_result *r);
 /* samples: NULL/"" = all; else the -s argument (space separated names) */
 int oracle_allele_counter(const char *in, size_t n, int path, int format, int limit_samples,

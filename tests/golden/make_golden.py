@@ -56,6 +56,14 @@ def hand_cases():
                      "1\t200\trs2\tA\tG\t.\tPASS\t.\tGT\t./.\t0/.\n"
                      "1\t300\trs3\tA\tG\t.\tPASS\t.\tGT:DP\t0|0:3\t1|1:4\n"
                      "1\t400\n")
+    # nonref_filter: what "definitely hom-ref" means in the two modes (000 vs 00, empty columns, GT not first, a final tab,
+    # CRLF, a data line in front of the header, an unterminated last line)
+    L = lambda fmt, *s: "1\t1\t.\tA\tG\t.\t.\t.\t" + fmt + "\t" + "\t".join(s)
+    c["nr_quirks"] = ("1\t1\t.\tA\tG\t.\t.\t.\tGT\t0/0\n" + H + "S1\tS2\n" + "\n".join([
+        L("GT", "0/0", "0|0"), L("GT", "0/0", "0|1"), L("GT", "000", "0/0"), L("GT", "00", "0"), L("GT", "//", "|"), L("GT", "0/0", ""),
+        L("GT", "0/0") + "\t", L("GT"), "1\t1\t.\tA\tG\t.\t.\t.\tGT", L("GT:DP", "0/0:1", "0/0:"), L("DP:GT", "1:0/0", "1"),
+        L("DP:GT", "1:0/0", "1:"), L("DP:GT", "1:0/0", ":0|0"), L("DP", "1", "2"), L("GT:", "0/0", "0/0"), L("", "0/0", "0/0"), "",
+        L("GT", "0/0", "0/0\r"), L("GT", "0/0", "0/0") + "\r", "\r", L("GT", "0/0/0", "0|0|0|0"), L("GT", "./.", "0/0"), L("GT", "0/0", "0/0")]))
     return {k: v.encode() for k, v in c.items()}
 
 
@@ -70,6 +78,10 @@ def run_all(data: bytes, ac_ok: bool, md_file_ok: bool = True):
                 out[f"{tool}.file"] = [rc, base64.b64encode(so).decode()]
             rc, so, _ = O.run_ref(tool, ["-q"] if tool != "hwe_tester" else [], stdin=data)
             out[f"{tool}.stdin"] = [rc, base64.b64encode(so).decode()]
+        rc, so, se = O.run_ref("nonref_filter", ["-i", f.name])
+        out["nonref_filter.file"] = [rc, base64.b64encode(so).decode(), se.count(b"Warning")]
+        rc, so, se = O.run_ref("nonref_filter", [], stdin=data)
+        out["nonref_filter.stdin"] = [rc, base64.b64encode(so).decode(), se.count(b"Warning")]
         for strict in (False, True):
             a = ["--strict"] if strict else []
             rc, so, se = O.run_ref("variant_counter", [*a, f.name])

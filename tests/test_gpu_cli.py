@@ -82,11 +82,28 @@ def test_variant_counter(files):
     both("variant_counter", [str(p)], env={"VCFX_CHUNK_BYTES": "4096"})
 
 
-@pytest.mark.parametrize("tool", ["allele_freq_calc", "hwe_tester", "missing_detector", "variant_counter", "allele_counter"])
+def test_nonref_filter(files, tmp_path):
+    """VCFX_nonref_filter: file (-i and positional), "-" and stdin, several chunks, the quirks fixture."""
+    import golden_util
+    q = tmp_path / "q.vcf"; q.write_bytes(golden_util.load()["nr_quirks"][0])
+    homref = tmp_path / "h.vcf"
+    rows = [b"21\t%d\t.\tA\tG\t.\tPASS\t.\tGT\t" % (i + 1) + b"\t".join([b"0|0"] * 299 + [b"0|1" if i % 3 == 0 else b"0|0"]) for i in range(400)]
+    homref.write_bytes(b"##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + b"\t".join(b"S%d" % i for i in range(300)) + b"\n" + b"\n".join(rows) + b"\n")
+    for p in list(files.values()) + [q, homref]:
+        both("nonref_filter", ["-i", str(p)])
+        both("nonref_filter", [str(p)])
+        both("nonref_filter", [], stdin=p.read_bytes())
+        both("nonref_filter", ["-"], stdin=p.read_bytes())
+    both("nonref_filter", ["-i", str(homref)], env=SMALL_CHUNK)
+    both("nonref_filter", [], stdin=files["nonl"].read_bytes(), env={"VCFX_CHUNK_BYTES": "4096"})
+    both("nonref_filter", ["-i", str(files["c3"])], env=SMALL_CHUNK)
+
+
+@pytest.mark.parametrize("tool", ["allele_freq_calc", "hwe_tester", "missing_detector", "variant_counter", "allele_counter", "nonref_filter"])
 def test_flags(tool, files):
     for args in (["--help"], ["-v"]):
         both(tool, args)
-    a, b = both(tool, ["/nonexistent/file.vcf"] if tool == "variant_counter" else ["-q", "-i", "/nonexistent/file.vcf"])
+    a, b = both(tool, ["/nonexistent/file.vcf"] if tool == "variant_counter" else (["-i", "/nonexistent/file.vcf"] if tool == "nonref_filter" else ["-q", "-i", "/nonexistent/file.vcf"]))
     assert a[2] == b[2]
     both(tool, [], stdin=b"")          # empty stdin: per-tool behaviour (help+rc1 / header only / nothing / Total 0)
 
@@ -161,7 +178,7 @@ def test_multi_gpu_same_bytes(tmp_path):
     env_multi = {"VCFX_CUDA_DEVICES": "all", "VCFX_CHUNK_BYTES": str(128 << 10)}
     env_one = {"VCFX_CHUNK_BYTES": str(128 << 10)}
     cases = [("allele_freq_calc", ["-q", "-i"]), ("hwe_tester", ["-q", "-i"]), ("missing_detector", ["-q", "-t", "1", "-i"]),
-             ("variant_counter", []), ("allele_counter", ["-q", "-i"]), ("allele_counter", ["-q", "-a", "-i"])]
+             ("variant_counter", []), ("allele_counter", ["-q", "-i"]), ("allele_counter", ["-q", "-a", "-i"]), ("nonref_filter", ["-i"])]
     for f in (src, late):
         for tool, args in cases:
             one = run(BIN / f"VCFX_{tool}", [*args, str(f)], env=env_one)

@@ -20,7 +20,7 @@ def _cmp(name, got, exp):
                              f"  got {got[max(0, i - 60): i + 60]!r}\n  exp {exp[max(0, i - 60): i + 60]!r}")
 
 
-def run_all(api, O, data, tag, chunk_bytes=0, tile_bytes=0, tools=("af", "hwe", "vc", "md")):
+def run_all(api, O, data, tag, chunk_bytes=0, tile_bytes=0, tools=("af", "hwe", "vc", "md", "nr")):
     kw = dict(chunk_bytes=chunk_bytes, tile_bytes=tile_bytes)
     for mode in MODES:
         if "af" in tools:
@@ -38,6 +38,10 @@ def run_all(api, O, data, tag, chunk_bytes=0, tile_bytes=0, tools=("af", "hwe", 
             r = api.missing_detector(data, mode, **kw); o = O.missing(data, mode)
             _cmp(f"{tag} md mode{mode}", r.out, o.out)
             assert r.totals.flagged == o.flagged or (mode == 0 and r.totals.dots_terminated == 0)
+        if "nr" in tools:
+            r = api.nonref_filter(data, mode, **kw); o = O.nonref_filter(data, mode)
+            _cmp(f"{tag} nr mode{mode}", r.out, o.out)
+            assert (r.totals.rows, r.totals.pre_header) == (o.rows, o.warnings)
         if "vc" in tools:
             for strict in (False, True):
                 r = api.variant_counter(data, mode, strict, **kw); o = O.variant_count(data, mode, strict)
@@ -158,6 +162,11 @@ def test_gpu_matches_reference_golden(cuda_api):
                     assert r.rc == exp[key][0], (name, key)
                     if r.rc == 0:
                         _cmp(f"golden {name} {key}", r.out, exp[key][1])
+            key = f"nonref_filter.{mode_name}"
+            if key in exp:
+                r = api.nonref_filter(data, mode)
+                assert (r.rc, r.totals.pre_header) == (exp[key][0], exp[key][2]), (name, key)
+                _cmp(f"golden {name} {key}", r.out, exp[key][1])
             for strict in (0, 1):
                 key = f"variant_counter.{mode_name}.strict{strict}"
                 r = api.variant_counter(data, mode, bool(strict))
@@ -291,6 +300,28 @@ def test_digit_path_exceptions(cuda_api, oracle):
         body.append(b"1\t%d\t.\tA\tG\t.\tPASS\t.\tGT\t" % (k + 1) + b"\t".join(gts))
     data = line_hdr + b"\n".join(body) + b"\n"
     run_all(cuda_api, oracle, data, "digit path, one odd genotype at every offset", tools=("af",))
+
+
+def test_nonref_filter_cases(cuda_api, oracle):
+    """VCFX_nonref_filter: the two meanings of "definitely hom-ref" (file mode: three bytes must be 0/0 or 0|0; stdin mode: nothing
+    but 0 / |), empty columns, GT not the first key, a final tab, CRLF, lines in front of the header, all-hom-ref lines of every
+    length against the 512-byte windows."""
+    import golden_util
+    data, _ = golden_util.load()["nr_quirks"]
+    for kw in ({}, {"tile_bytes": 512}, {"chunk_bytes": 4096}):
+        run_all(cuda_api, oracle, data, f"nr quirks {kw}", tools=("nr",), **kw)
+    hdr = b"##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t"
+    for S in (1, 2, 100, 126, 127, 128, 129, 255, 256, 257, 700):
+        names = b"\t".join(b"S%d" % i for i in range(S))
+        lines = []
+        for k in range(60):
+            gts = [b"0|0" if (i + k) % 3 else b"0/0" for i in range(S)]
+            if k % 4 == 1:
+                gts[(k * 37) % S] = [b"0|1", b".", b"0", b"./.", b"0/0/0", b"000", b"1"][k % 7]
+            lines.append(b"1\t%d\t.\tA\tG\t.\tPASS\t.\tGT\t" % (k + 1) + b"\t".join(gts))
+        data = hdr + names + b"\n" + b"\n".join(lines) + (b"\n" if S % 2 else b"")
+        run_all(cuda_api, oracle, data, f"nr S{S}", tools=("nr",))
+        run_all(cuda_api, oracle, data, f"nr S{S} tile512", tile_bytes=512, tools=("nr",))
 
 
 def test_allele_counter_two_digit_counts(cuda_api, oracle):

@@ -20,6 +20,10 @@ def check_case(O, data, exp, name):
             if key in exp:
                 r = fn(data, mode)
                 assert (r.rc, r.out) == exp[key][:2], (name, key)
+        key = f"nonref_filter.{mode_name}"
+        if key in exp:
+            r = O.nonref_filter(data, mode)
+            assert (r.rc, r.out, r.warnings) == tuple(exp[key][:3]), (name, key)
         for strict in (0, 1):
             key = f"variant_counter.{mode_name}.strict{strict}"
             r = O.variant_count(data, mode, bool(strict))
@@ -66,6 +70,10 @@ def test_oracle_matches_reference_binaries_fuzz(oracle, seed):
             assert (r.rc, r.out) == (rc, out), (tool, "file")
             rc, out, _ = O.run_ref(tool, ["-q"] if tool != "hwe_tester" else [], stdin=data); r = fn(data, O.STDIN)
             assert (r.rc, r.out) == (rc, out), (tool, "stdin")
+        rc, out, err = O.run_ref("nonref_filter", ["-i", f.name]); r = O.nonref_filter(data, O.FILE)
+        assert (r.rc, r.out, r.warnings) == (rc, out, err.count(b"Warning")), "nonref_filter file"
+        rc, out, err = O.run_ref("nonref_filter", [], stdin=data); r = O.nonref_filter(data, O.STDIN)
+        assert (r.rc, r.out, r.warnings) == (rc, out, err.count(b"Warning")), "nonref_filter stdin"
         for strict in (False, True):
             a = ["--strict"] if strict else []
             rc, out, err = O.run_ref("variant_counter", [*a, f.name]); r = O.variant_count(data, O.FILE, strict)
@@ -96,6 +104,8 @@ def test_oracle_matches_reference_binaries_shapes(oracle):
                 assert (fn(data, O.FILE).out) == out, (shape, tool)
             rc, out, _ = O.run_ref("variant_counter", [f.name])
             assert O.variant_count(data).out == out
+            rc, out, _ = O.run_ref("nonref_filter", ["-i", f.name], timeout=60)
+            assert O.nonref_filter(data, O.FILE).out == out, (shape, "nonref_filter")
 
 
 def test_hwe_numbers_and_formatters(oracle):

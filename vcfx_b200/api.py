@@ -17,7 +17,7 @@ from pathlib import Path
 
 from . import build as _build
 
-OP_VARIANT_COUNT, OP_ALLELE_FREQ, OP_HWE, OP_MISSING_DETECT, OP_ALLELE_COUNT = range(5)
+OP_VARIANT_COUNT, OP_ALLELE_FREQ, OP_HWE, OP_MISSING_DETECT, OP_ALLELE_COUNT, OP_NONREF_FILTER = range(6)
 FILE, STDIN = 0, 1
 F_AC_AGGREGATE, F_AC_BINARY, F_AC_FORWARD = 1, 2, 4
 DEVICE_PAD = 8192
@@ -342,7 +342,7 @@ def _run(op: int, data: bytes, mode: int, chunk_bytes: int, flags: int = 0, devi
     chunk_bytes = chunk_bytes or min(64 << 20, max(1 << 20, (len(data) + (1 << 20) - 1) & ~((1 << 20) - 1)))
     ctx, cached = _cached_context(op, mode, device, flags, chunk_bytes, **kw)
     try:
-        valid_abs = find_chrom_header(data) if op == OP_ALLELE_FREQ else 0
+        valid_abs = find_chrom_header(data) if op in (OP_ALLELE_FREQ, OP_NONREF_FILTER) else 0
         outs, tot = stream_bytes(ctx, data, chunk_bytes, valid_abs)
     except Exception:
         if cached:
@@ -401,6 +401,14 @@ def missing_detector(data: bytes, mode: int = FILE, chunk_bytes: int = 0, **kw) 
         last = data[data.rfind(b"\n") + 1:]
         return ToolResult(body[:cut] + last, 0, tot)
     return ToolResult(b"".join(outs), 0, tot)
+
+
+def nonref_filter(data: bytes, mode: int = FILE, chunk_bytes: int = 0, **kw) -> ToolResult:
+    """VCFX_nonref_filter: data lines behind the "#CHROM" line whose samples are all homozygous reference are dropped,
+    every other line is written as its content + '\\n' (VCFX_nonref_filter.cpp:458-548 file mode, :553-631 stdin mode).
+    totals.pre_header = data lines in front of the header (each prints a warning), totals.flagged = lines dropped."""
+    body, tot = _run(OP_NONREF_FILTER, data, mode, chunk_bytes, **kw)
+    return ToolResult(body, 0, tot)
 
 
 def variant_counter(data: bytes, mode: int = FILE, strict: bool = False, chunk_bytes: int = 0, **kw) -> ToolResult:

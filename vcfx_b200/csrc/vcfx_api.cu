@@ -136,6 +136,7 @@ kernel_fn kernel_for(int op) {
     case VCFX_OP_ALLELE_FREQ:   return vcfx_scan_kernel<OP_AF, 0>;
     case VCFX_OP_HWE:           return vcfx_scan_kernel<OP_HWE, 0>;
     case VCFX_OP_MISSING_DETECT: return vcfx_scan_kernel<OP_MD, 0>;
+    case VCFX_OP_NONREF_FILTER: return vcfx_scan_kernel<OP_NR, 0>;
     case VCFX_OP_ALLELE_COUNT:  return vcfx_scan_kernel<OP_AC, 0>;
     default: return nullptr;
     }
@@ -154,6 +155,7 @@ kernel_fn format_kernel_for(int op, int ac_fmt = 0) {
     case VCFX_OP_ALLELE_FREQ: return format_rows_kernel<OP_AF>;
     case VCFX_OP_HWE:         return format_rows_kernel<OP_HWE>;
     case VCFX_OP_MISSING_DETECT: return md_copy_kernel;
+    case VCFX_OP_NONREF_FILTER: return md_copy_kernel;
     default: return nullptr;
     }
 }
@@ -258,7 +260,7 @@ int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes, uint64_t min_recs = 0)
             cudaFree(w.tile_resume); w.tile_resume = nullptr;
             CU(cudaMalloc(&w.tile_resume, sizeof(uint32_t) * tiles));
         }
-        if (ctx->cfg.op == VCFX_OP_MISSING_DETECT) {
+        if (ctx->cfg.op == VCFX_OP_MISSING_DETECT || ctx->cfg.op == VCFX_OP_NONREF_FILTER) {
             cudaFree(w.tail_start); cudaFree(w.tail_len); cudaFree(w.tail_off);
             w.tail_start = w.tail_len = w.tail_off = nullptr;
             CU(cudaMalloc(&w.tail_start, sizeof(uint32_t) * tiles));
@@ -322,7 +324,7 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
         VCFX_LAUNCH(tile_scan_kernel, 1, 1024, SCAN_SMEM_BYTES, st, P);
         CU(cudaGetLastError());
         if (kernel_fn ff = format_kernel_for(ctx->cfg.op, ctx->ac_fmt)) {
-            VCFX_LAUNCH(ff, ctx->sm_count * (ctx->cfg.op == VCFX_OP_MISSING_DETECT ? 8 : 16), 256, 0, st, P);
+            VCFX_LAUNCH(ff, ctx->sm_count * ((ctx->cfg.op == VCFX_OP_MISSING_DETECT || ctx->cfg.op == VCFX_OP_NONREF_FILTER) ? 8 : 16), 256, 0, st, P);
             CU(cudaGetLastError());
         } else if (ctx->cfg.op == VCFX_OP_ALLELE_COUNT) {
             // rows are sized in the first pass and written in a second one at their scanned offsets
@@ -367,6 +369,7 @@ size_t default_out_bytes(int op, unsigned flags, size_t chunk) {
     switch (op) {
     case VCFX_OP_VARIANT_COUNT: return 4096;
     case VCFX_OP_MISSING_DETECT: return chunk + chunk / 4 + 4096;
+    case VCFX_OP_NONREF_FILTER: return chunk + 4096;          // never longer than the input plus one '\n'
     case VCFX_OP_ALLELE_COUNT:
         if (flags & VCFX_F_AC_AGGREGATE) return chunk / 4 + (1u << 20);
         if (flags & VCFX_F_AC_BINARY) return chunk + 4096;
@@ -422,7 +425,7 @@ const char *vcfx_cuda_last_error(const vcfx_ctx *ctx) { return ctx ? ctx->last_e
 int vcfx_cuda_create(const vcfx_cfg *cfg, vcfx_ctx **out) {
     if (!cfg || !out) return VCFX_E_INVALID;
     *out = nullptr;
-    if (cfg->op < VCFX_OP_VARIANT_COUNT || cfg->op > VCFX_OP_ALLELE_COUNT) return VCFX_E_INVALID;
+    if (cfg->op < VCFX_OP_VARIANT_COUNT || cfg->op > VCFX_OP_NONREF_FILTER) return VCFX_E_INVALID;
     if (cfg->mode != VCFX_MODE_FILE && cfg->mode != VCFX_MODE_STDIN) return VCFX_E_INVALID;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return VCFX_E_NO_DEVICE;

@@ -36,7 +36,8 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int WARPS_PER_CTA = 8;
 constexpr uint32_t WINDOW = 512;
 
-enum : int { OP_VC = 0, OP_AF = 1, OP_HWE = 2, OP_MD = 3, OP_AC = 4 };
+enum : int { OP_VC = 0, OP_AF = 1, OP_HWE = 2, OP_MD = 3, OP_AC = 4, OP_NR = 5 };
+constexpr uint32_t NR_PLAIN = 0xFFFFFFFFu;     // Rec::b of a nonref_filter record: the line is written as its content + '\n' (or not at all)
 enum : int { MODE_FILE = 0, MODE_STDIN = 1 };
 enum : int { AC_TEXT_MT = 0, AC_TEXT_FWD = 1, AC_AGG = 2, AC_BIN = 3 };
 constexpr uint32_t AC_STAGE = 2048;     // per-warp staging bytes for allele_counter rows
@@ -236,6 +237,41 @@ __device__ __noinline__ int gt_index_of(const uint8_t *p, const uint8_t *e) {
         p = (q < e) ? q + 1 : q;
     }
     return -1;
+}
+
+// VCFX_nonref_filter.cpp for the sample column starting at p: is its GT "definitely" homozygous reference?
+//   file mode  (:248-309 allSamplesHomRefDirect): the column ends at a tab or at the line end ('\r' before '\n' is not
+//              content); at the line end there is no column (the reference's loop is over: true, "nothing against it");
+//              an empty column keeps the line; GT = the piece before the first ':' (gt_index 0) or the gt_index-th piece
+//              (empty when there are fewer: keeps the line); three bytes must be 0/0 or 0|0, any other non-empty GT
+//              may hold nothing but '0' '/' '|'
+//   stdin mode (:553-631 filterNonRef + :419-449 isDefinitelyHomRef): the column ends at a tab or '\n' ('\r' is content);
+//              pieces as std::getline yields them (none for an empty column, no empty piece after a final ':'):
+//              gt_index beyond them keeps the line; the GT may hold nothing but '0' '/' '|' and must not be empty
+__device__ __noinline__ bool nr_sample_homref(const uint8_t *p, bool file_mode, int gt_index) {
+    const uint8_t *se = p;
+    uint32_t c = ldb(se);
+    while (c != '\t' && c != '\n') { ++se; c = ldb(se); }
+    if (file_mode && c == '\n' && ldb(se - 1) == '\r') { if (se - 1 >= p) --se; else return true; }   // ("\t\r\n": the line ended before p)
+    if (se == p) return (c == '\n') ? file_mode : false;
+    const uint8_t *gs = p, *ge = se;
+    if (file_mode && gt_index == 0) { ge = p; while (ge < se && ldb(ge) != ':') ++ge; }
+    else {
+        int idx = 0; const uint8_t *fs = p; bool got = false;
+        for (const uint8_t *q = p; q <= se; ++q) {
+            if (q == se || ldb(q) == ':') {
+                if (idx == gt_index) { gs = fs; ge = q; got = true; break; }
+                ++idx; fs = q + 1;
+            }
+        }
+        if (!got) return false;
+        if (!file_mode && ge == se && gs == se && ldb(se - 1) == ':') return false;     // std::getline yields no empty piece after a final ':'
+    }
+    const uint32_t n = (uint32_t)(ge - gs);
+    if (n == 0) return false;
+    if (file_mode && n == 3) return ldb(gs) == '0' && is_sep(ldb(gs + 1)) && ldb(gs + 2) == '0';
+    for (const uint8_t *q = gs; q < ge; ++q) { const uint32_t b = ldb(q); if (b != '0' && !is_sep(b)) return false; }
+    return true;
 }
 
 // byte index (0..15) of the first set 0x80-bit over the lane's four mask words, with selects instead of
@@ -1319,6 +1355,57 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                     }
                 }
             }
+            // ================= NONREF_FILTER: is every sample homozygous reference?
+            bool nr_all = false;               // the line can be dropped and no sample so far speaks against it
+            if (OP == OP_NR && !hash && tabs >= 9 && (a0 + ls >= P.valid_from)) {
+                const int gi = gt_index_of(tin + tp[7] + 1, tin + tp[8]);        // :317-335 findGTIndex on FORMAT
+                if (gi >= 0) {
+                    nr_all = true;
+                    const uint32_t lo = tp[8];                                    // the tab in front of the first sample
+                    const bool file_mode = P.mode == MODE_FILE;
+                    bool firstw = true;
+                    for (;;) {
+                        const uint32_t pb = wb + 16 * lane;
+                        if (!firstw) {
+                            const uint32_t n0 = eq_bytes(cur.x, C_NL), n1 = eq_bytes(cur.y, C_NL);
+                            const uint32_t n2 = eq_bytes(cur.z, C_NL), n3 = eq_bytes(cur.w, C_NL);
+                            const unsigned ebal = __ballot_sync(FULL, (n0 | n1 | n2 | n3) != 0);
+                            if (ebal) {
+                                const int src = __ffs(ebal) - 1;
+                                int k = first_byte(n0, n1, n2, n3);
+                                k = __shfl_sync(FULL, k, src);
+                                e = wb + 16 * src + k; found = true;
+                            }
+                        }
+                        if (nr_all) {                             // the reference stops at the first sample that is not hom-ref too
+                            uint32_t m0 = eq_bytes(cur.x, C_TAB), m1 = eq_bytes(cur.y, C_TAB);
+                            uint32_t m2 = eq_bytes(cur.z, C_TAB), m3 = eq_bytes(cur.w, C_TAB);
+                            if (firstw || found) clip4(m0, m1, m2, m3, pb, firstw ? lo : 0u, found ? e : ~0u);
+                            uint32_t m16 = ((m0 * 0x00204081u) >> 28) | (((m1 * 0x00204081u) >> 24) & 0xF0u) |
+                                           (((m2 * 0x00204081u) >> 20) & 0xF00u) | (((m3 * 0x00204081u) >> 16) & 0xF000u);
+                            bool bad = false;
+                            while (m16) {
+                                const uint8_t *sp = tin + pb + __ffs(m16);          // first byte of the sample behind this tab
+                                m16 &= m16 - 1u;
+                                // "0/0" or "0|0" closed by a tab (by ':' as well when GT is the first key) needs no second look
+                                const uint32_t *s4 = reinterpret_cast<const uint32_t *>((uintptr_t)sp & ~(uintptr_t)3);
+                                const uint32_t q = __funnelshift_r(__ldg(s4), __ldg(s4 + 1), 8u * (uint32_t)((uintptr_t)sp & 3));
+                                const uint32_t g3 = q & 0x00FFFFFFu, b3 = q >> 24;
+                                const bool quick = (g3 == 0x00302F30u || g3 == 0x00307C30u) && (b3 == '\t' || (gi == 0 && b3 == ':'));
+                                if (!quick && !nr_sample_homref(sp, file_mode, gi)) bad = true;
+                            }
+                            if (__any_sync(FULL, bad)) nr_all = false;
+                        }
+                        if (found) break;
+                        firstw = false;
+                        wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
+                        if (((wb >> 9) & 7u) == 0) {          // every 8th window: L2 prefetch of the 4 KB that follow
+                            const uint32_t pf = wb + 8 * WINDOW + 128 * lane;
+                            if (pf < nrel) prefetch_l2(tin + pf);
+                        }
+                    }
+                }
+            }
             // ================= no (more) per-sample work: just find the '\n'
             uint32_t wcount = 0;               // windows since the search began: prefetching on a line-relative beat
                                                // measured 7 % faster than on absolute 4 KB boundaries (variant_counter)
@@ -1572,6 +1659,36 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                     }
                 }
             }
+            else if (OP == OP_NR) {
+                // VCFX_nonref_filter.cpp:478-544 / 553-631: every line is written as its content + '\n' (file mode: without a
+                // '\r' before the '\n'), except data lines behind the "#CHROM" line whose samples are all hom-ref.  Lines that
+                // come out exactly as they went in stay part of the verbatim spans; the others get a record.
+                const bool term = (a0 + e) < n;                          // a real '\n', not the pad behind the chunk
+                const uint32_t raw_end = term ? e + 1 : e;
+                const bool data = (ee != ls) && !hash;
+                if (data) {
+                    VCFX_COUNT(C_DATA, 1);
+                    if (a0 + ls < P.valid_from) VCFX_COUNT(C_PRE, 1);    // "data line encountered before #CHROM": passed, with a warning
+                }
+                const bool drop = data && nr_all;
+                if (data && !drop) VCFX_COUNT(C_ROWS, 1);
+                if (drop || ee != e || !term) {
+                    const uint32_t content_len = drop ? 0u : ee - ls, mod_len = drop ? 0u : content_len + 1u;
+                    if (lane == 0) {
+                        unsigned long long slot = alloc_slot(ws.rec_base, ws.rec_used, P.stats);
+                        if (slot < P.rec_cap) {
+                            Rec r; r.tile = tile; r.ls_rel = (uint32_t)(a0 + ls - a); r.prefix_len = (uint32_t)(a0 + md_prev_end - a);
+                            r.off_in_tile = (uint32_t)out_bytes; r.a = 0; r.b = NR_PLAIN; r.c = content_len; r.d = mod_len;
+                            P.recs[slot] = r;
+                        }
+                    }
+                    out_bytes += (ls - md_prev_end) + mod_len;
+                    md_prev_end = raw_end;
+                    if (drop) VCFX_COUNT(C_FLAG, 1);
+                }
+                md_add_nl = false;
+                md_last_end = raw_end;
+            }
             else if (OP == OP_MD) {
                 const bool term = (a0 + e) < n;                          // a real '\n', not the pad behind the chunk
                 const uint32_t raw_end = term ? e + 1 : e;
@@ -1633,7 +1750,7 @@ vcfx_scan_kernel(const VCFX_GRID_CONSTANT KParams P) {
     const int lane = lane_id();
     const int wid = threadIdx.x >> 5;
     const uint64_t n = P.n;
-    const bool strip_cr = (OP == OP_HWE) || (P.mode == MODE_FILE && (OP == OP_AF || OP == OP_VC || OP == OP_MD));
+    const bool strip_cr = (OP == OP_HWE) || (P.mode == MODE_FILE && (OP == OP_AF || OP == OP_VC || OP == OP_MD || OP == OP_NR));
     if (OP == OP_AC && P.ac_pass && P.stats->overflow) return;
     if (VAR == 1 && P.stats->n_unfinished == 0) return;
 
@@ -1717,7 +1834,7 @@ vcfx_scan_kernel(const VCFX_GRID_CONSTANT KParams P) {
         const bool md_add_nl = st.md_add_nl;
 
         if (!(OP == OP_AC && P.ac_pass)) VCFX_COUNT(C_LINES, VAR == 1 ? nlines - lines_before : nlines);
-        if (OP == OP_MD) {
+        if (OP == OP_MD || OP == OP_NR) {
             const uint32_t tail = md_last_end - md_prev_end;
             if (lane == 0) {
                 P.tail_start[tile] = (uint32_t)(a0 + md_prev_end - a);
@@ -2006,6 +2123,11 @@ md_copy_kernel(const KParams P) {
             warp_copy(o, base + r.prefix_len, gap, lane);
             o += gap;
             const uint8_t *ln = base + r.ls_rel;
+            if (r.b == NR_PLAIN) {                                       // nonref_filter: the line's content and a '\n', or nothing
+                warp_copy(o, ln, r.c, lane);
+                if (r.d > r.c && lane == 0) o[r.c] = '\n';
+                continue;
+            }
             warp_copy(o, ln, r.a, lane);                                 // up to INFO
             o += r.a;
             const uint8_t *info = ln + r.a;

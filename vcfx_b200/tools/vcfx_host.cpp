@@ -352,12 +352,18 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
     std::vector<vcfx_ctx *> ctxs;
     int rc = VCFX_OK;
     auto destroy_all = [&ctxs] { for (vcfx_ctx *c : ctxs) vcfx_cuda_destroy(c); ctxs.clear(); };
-    for (int dev : devices) {
-        vcfx_ctx *c = nullptr;
-        cfg.device = dev;
-        rc = vcfx_cuda_create(&cfg, &c);
-        if (rc != VCFX_OK) { err = vcfx_cuda_strerror(rc); destroy_all(); return rc; }
-        ctxs.push_back(c);
+    {
+        // one context per GPU, created side by side (a CUDA context costs about a second, most of a tool's wall time)
+        std::vector<vcfx_ctx *> made(devices.size(), nullptr);
+        std::vector<int> rcs(devices.size(), VCFX_OK);
+        std::vector<std::thread> th;
+        auto make = [&](size_t i) { vcfx_cfg c = cfg; c.device = devices[i]; rcs[i] = vcfx_cuda_create(&c, &made[i]); };
+        for (size_t i = 1; i < devices.size(); ++i) th.emplace_back(make, i);
+        make(0);
+        for (auto &t : th) t.join();
+        for (size_t i = 0; i < devices.size(); ++i) if (made[i]) ctxs.push_back(made[i]);
+        for (size_t i = 0; i < devices.size(); ++i)
+            if (rcs[i] != VCFX_OK) { rc = rcs[i]; err = vcfx_cuda_strerror(rc); destroy_all(); return rc; }
     }
     const size_t G = ctxs.size();
     double t_create = now() - t_start;
