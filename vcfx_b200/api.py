@@ -65,7 +65,9 @@ _lib = None
 
 
 def lib_path() -> Path:
-    return _build.CUDA_LIB
+    import os
+    alt = os.environ.get("VCFX_CUDA_LIB")          # an alternative build of the same library (kernel experiments)
+    return Path(alt) if alt else _build.CUDA_LIB
 
 
 def load():

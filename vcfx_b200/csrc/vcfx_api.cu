@@ -318,7 +318,8 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
         VCFX_LAUNCH(fn, grid, WARPS_PER_CTA * 32, 0, st, P);
         CU(cudaGetLastError());
         if (gfn) {                       // finishes the tiles the lattice kernel left; exits at once when there are none
-            VCFX_LAUNCH(gfn, grid, WARPS_PER_CTA * 32, 0, st, P);
+            const int ggrid = std::max(1, std::min(ctx->sm_count * VCFX_GENERAL_CTAS, (int)((tiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA)));
+            VCFX_LAUNCH(gfn, ggrid, WARPS_PER_CTA * 32, 0, st, P);
             CU(cudaGetLastError());
         }
         VCFX_LAUNCH(tile_scan_kernel, 1, 1024, SCAN_SMEM_BYTES, st, P);
@@ -456,7 +457,7 @@ int vcfx_cuda_create(const vcfx_cfg *cfg, vcfx_ctx **out) {
     CUC(cudaFuncSetAttribute(tile_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_SMEM_BYTES));
     CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel_for(cfg->op), WARPS_PER_CTA * 32, 0));
     // the kernels are tuned at their __launch_bounds__ occupancy (variant_counter measured slower at 6 CTAs than at 5)
-    ctx->blocks_per_sm = std::max(1, std::min(bps, cfg->op == VCFX_OP_VARIANT_COUNT ? 5 : VCFX_PARSE_CTAS));
+    ctx->blocks_per_sm = std::max(1, std::min(bps, cfg->op == VCFX_OP_VARIANT_COUNT ? 5 : (cfg->op == VCFX_OP_ALLELE_COUNT ? VCFX_AC_CTAS : VCFX_PARSE_CTAS)));
     if (cfg->op == VCFX_OP_ALLELE_COUNT) {
         if (cfg->n_sel == 0 || !cfg->sel_col || !cfg->sel_names || !cfg->sel_name_off) return fail(VCFX_E_INVALID);
         ctx->ac_fmt = (cfg->flags & VCFX_F_AC_AGGREGATE) ? AC_AGG : (cfg->flags & VCFX_F_AC_BINARY) ? AC_BIN

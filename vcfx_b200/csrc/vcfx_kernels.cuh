@@ -1733,6 +1733,12 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
 #ifndef VCFX_PARSE_CTAS
 #define VCFX_PARSE_CTAS 4
 #endif
+#ifndef VCFX_AC_CTAS
+#define VCFX_AC_CTAS 4               // allele_counter
+#endif
+#ifndef VCFX_GENERAL_CTAS
+#define VCFX_GENERAL_CTAS 3          // resident CTAs per SM of the general kernel: 80 registers, no spills (C3 allele_freq_calc 1.85 ms at 4 CTAs / 64 registers, 1.90 at 5 / 48, 1.72 at 3 / 80)
+#endif
 // Two kernels for allele_freq_calc and hwe_tester, launched one after the other over the same tiles, so that each is
 // compiled (registers, schedule) on its own:
 //   VAR 0  the lattice kernel: tier 1 + the exact path.  In a tile it stops at the first line whose first sample
@@ -1742,7 +1748,7 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
 //          skip-ahead loop for multi-key FORMATs, tier 1 and the exact path); it exits at once when none was left
 // The other operations have one kernel (VAR 0, never stops early).
 template <int OP, int VAR>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (OP == OP_VC) ? 5 : VCFX_PARSE_CTAS)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (OP == OP_VC) ? 5 : (VAR == 1 ? VCFX_GENERAL_CTAS : (OP == OP_AC ? VCFX_AC_CTAS : VCFX_PARSE_CTAS)))
 vcfx_scan_kernel(const VCFX_GRID_CONSTANT KParams P) {
     __shared__ uint32_t s_tp[WARPS_PER_CTA][12];
     __shared__ __align__(16) uint8_t s_stage[(OP == OP_AC) ? WARPS_PER_CTA * (AC_STAGE + 32) : 16];
