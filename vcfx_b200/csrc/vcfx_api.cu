@@ -99,7 +99,7 @@ struct vcfx_ctx {
     uint8_t *d_names = nullptr;
     uint4 *d_names16 = nullptr;          // one zero-padded 16-byte slot per selected name + tab, when they all have the same length
     uint32_t name_len = 0;
-    bool ac_bulk = false;                // VCFX_AC_BULK=1: staged rows leave shared memory through cp.async.bulk
+    bool ac_bulk = true;                 // staged rows leave shared memory through cp.async.bulk (VCFX_AC_BULK=0: 128-bit stores)
     int ac_fmt = 0;
     bool ac_ident = false;               // allele_counter selection = columns 0 .. n_sel-1 in order
     bool ac_exact = false;               // a chunk had a count of two digits: rows are sized by parsing from now on
@@ -485,8 +485,8 @@ int vcfx_cuda_create(const vcfx_cfg *cfg, vcfx_ctx **out) {
             CUC(cudaMalloc(&ctx->d_names16, n16.size()));
             CUC(cudaMemcpy(ctx->d_names16, n16.data(), n16.size(), cudaMemcpyHostToDevice));
             ctx->name_len = nl;
-            const char *be = getenv("VCFX_AC_BULK");
-            ctx->ac_bulk = be && *be == '1';
+            const char *be = getenv("VCFX_AC_BULK");          // staged rows leave shared memory through cp.async.bulk (default; 0 = 128-bit stores)
+            ctx->ac_bulk = !(be && *be == '0');
         }
     }
     if (cfg->stream) { ctx->dev_stream = (cudaStream_t)cfg->stream; ctx->dev_stream_owned = false; }

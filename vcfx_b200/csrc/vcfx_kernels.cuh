@@ -1553,6 +1553,7 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                         // last 3 bytes of the row before, "\t a \n", and the first 3 of the row after, again the prefix), its own
                         // name and digits shifted into place, all of it rotated by the row's misalignment.  Neighbouring lanes write
                         // the words they share with identical contents, so no byte stores and no ordering are needed.
+                        const unsigned long long out_limit = P.ac_pass ? min((unsigned long long)P.out_cap, P.tile_base[tile] + P.tile_out[tile]) : 0ULL;
                         const uint32_t NL = P.name_len;
                         const bool fast_line = P.ac_pass && text && NL != 0u && extra_tabs == 0u && prefix_src <= 40u && prefix_src >= 1u;
                         const uint32_t L = prefix_src + NL + 4u;
@@ -1576,23 +1577,31 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                             const uint32_t i = i0 + lane;
                             int vr = 0, va = 0; uint32_t len = 0, noff = 0, nlen = 0;
                             if (i < n_rows) {
-                                const uint32_t c = P.sel_col[i];
+                                const uint32_t c = P.ac_ident ? i : P.sel_col[i];      // (all samples in order: one dependent load less)
                                 if (c < ns_parsed) { const uint2 v = scr[c]; vr = (int)v.x; va = (int)v.y; }
                                 if (P.ac_fmt != AC_TEXT_FWD) { vr = (int)(int8_t)vr; va = (int)(int8_t)va; }   // int8 storage (:621-622, :1446-1447)
-                                if (text) {
-                                    noff = P.name_off[i]; nlen = P.name_off[i + 1] - noff;     // name + '\t'
-                                    len = prefix_len + nlen + dec_len(vr) + 1 + dec_len(va) + 1;
-                                } else len = 2;
                             }
-                            const int incl = warp_incl_scan((int)len, lane);
-                            const uint32_t off = (uint32_t)incl - len;
-                            const uint32_t btot = (uint32_t)__shfl_sync(FULL, incl, 31);
+                            // rows of one length (the fast row writer's case) need no scan: row i starts at i * L
+                            const bool fast = fast_line && __all_sync(FULL, i >= n_rows || ((uint32_t)vr <= 9u && (uint32_t)va <= 9u));
+                            uint32_t off, btot;
+                            if (fast) { off = (uint32_t)lane * L; btot = min(32u, n_rows - i0) * L; }
+                            else {
+                                if (i < n_rows) {
+                                    if (text) {
+                                        noff = P.name_off[i]; nlen = P.name_off[i + 1] - noff;     // name + '\t'
+                                        len = prefix_len + nlen + dec_len(vr) + 1 + dec_len(va) + 1;
+                                    } else len = 2;
+                                }
+                                const int incl = warp_incl_scan((int)len, lane);
+                                off = (uint32_t)incl - len;
+                                btot = (uint32_t)__shfl_sync(FULL, incl, 31);
+                            }
                             // the write pass never stores past the bytes the size pass gave this tile (speculative sizes can be
                             // too small: a count of two digits) nor past the output buffer; the chunk is then run again, exact
-                            if (P.ac_pass && opos + btot > min((unsigned long long)P.out_cap, P.tile_base[tile] + P.tile_out[tile])) {
+                            if (P.ac_pass && opos + btot > out_limit) {
                                 if (lane == 0) atomicOr(&P.stats->overflow, 4ULL);
                             } else
-                            if (fast_line && __all_sync(FULL, i >= n_rows || ((uint32_t)vr <= 9u && (uint32_t)va <= 9u))) {
+                            if (fast) {
                                 uint32_t *sw = reinterpret_cast<uint32_t *>(stage0);
                                 const uint32_t o = (uint32_t)((uintptr_t)(P.out + opos) & 15) + (uint32_t)lane * L;   // the row's place in the staging buffer
                                 const uint32_t sh = 8u * (3u - (o & 3u));
