@@ -1,7 +1,9 @@
-"""The N>1 host logic on CPU: two ranks over gloo.  Each rank takes its newline-aligned shard from
-vcfx_b200.shard.plan, processes it independently (here with the oracle standing in for the GPU —
-tests may use it), the totals cross ranks in one all-reduce and the texts are concatenated in rank
-order.  The result must equal the single-process result on the whole file."""
+"""The N>1 path on CPU: two ranks over gloo.  Each rank takes its newline-aligned shard from
+vcfx_b200.shard.plan and runs it through the library's streaming entry points — the product's own kernel and
+C-ABI sources under the warp emulator (tests/emu/), with the shard's prefix facts (header seen before the
+shard, end of the leading '#' block, first line number) passed exactly as a GPU rank passes them; the totals
+cross ranks in one all-reduce and the texts are concatenated in rank order.  The result must equal the oracle
+on the whole file."""
 import os
 import socket
 import sys
@@ -24,16 +26,31 @@ def _worker(rank, world, port, data, q):
     from vcfx_b200 import api, shard
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, str(ROOT / "tests" / "emu"))
+    import build_emu
+    dev = build_emu.load_api()                             # libvcfx_emu.so: the kernels, emulated
     sh = shard.plan(data, world)[rank]
     body = data[sh.start:sh.end]
-    # prefix facts: a shard that starts after the "#CHROM" line behaves as if the header had been seen
-    pre = b"#CHROM\n" if sh.chrom_seen_before else b""
-    af = O.allele_freq(pre + body, O.FILE)
-    af_rows = af.out[len(api.AF_HEADER):]
-    vc = O.variant_count(body, O.FILE, True)
-    bad = (sh.first_line - 1 + vc.first_bad_line) if vc.first_bad_line else 1 << 62
-    md = O.missing(body, O.STDIN)
-    tot = torch.tensor([af.rows, O.variant_count(body, O.FILE).rows, md.flagged], dtype=torch.int64)
+    chunk = 64 << 10
+
+    def run(op, mode, valid_abs=0, flags=0):
+        ctx = dev.Context(op, mode, flags=flags, chunk_bytes=chunk)
+        outs, t = dev.stream_bytes(ctx, body, chunk, valid_abs)
+        ctx.close()
+        return b"".join(outs), t
+    # prefix facts: data lines in front of the "#CHROM" line do not count for allele_freq_calc; the leading '#'
+    # block bounds missing_detector's pre-scan; line numbers continue from the shards before
+    af_rows, af_t = run(dev.OP_ALLELE_FREQ, dev.FILE, shard.valid_from(sh, dev.find_chrom_header(data)))
+    _, vc_t = run(dev.OP_VARIANT_COUNT, dev.FILE)
+    bad = (sh.first_line - 1 + vc_t.first_short_line) if vc_t.first_short_line else 1 << 62
+    md_out, md_t = run(dev.OP_MISSING_DETECT, dev.STDIN, min(max(sh.header_block_end - sh.start, 0), len(body)))
+
+    class _R:
+        pass
+    af = _R(); af.rows = af_t.rows
+    md = _R(); md.flagged = md_t.flagged; md.out = md_out
+    vc_rows = vc_t.rows
+    tot = torch.tensor([af.rows, vc_rows, md.flagged], dtype=torch.int64)
     dist.all_reduce(tot)                                   # the path's only exchange: scalar totals
     first_bad = torch.tensor([bad], dtype=torch.int64)
     dist.all_reduce(first_bad, op=dist.ReduceOp.MIN)       # --strict: the smallest failing line wins
