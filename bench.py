@@ -332,16 +332,17 @@ def oracle_parallel(O, fn_name, shard, np, pieces=48, **kw):
     return h.hexdigest(), total
 
 
-def measure_h2d_ceiling(torch, shard, dev, dist, world, seconds=0.6):
+def measure_h2d_ceiling(torch, shard, dev, dist, world, seconds=1.0):
     """Bare pinned host->device copies of the shard's own 64 MiB chunks on three streams (what the streaming
     path does, without any kernel), all ranks at once: the ceiling of `e2e` on this box."""
-    streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
-    bufs = [torch.empty(CHUNK, dtype=torch.uint8, device=dev) for _ in range(3)]
+    K = 6                                          # copies in flight (the streaming path keeps three slots per context busy)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(K)]
+    bufs = [torch.empty(CHUNK, dtype=torch.uint8, device=dev) for _ in range(K)]
 
     def one_pass():
         for i, (s, e) in enumerate(shard.bounds):
-            with torch.cuda.stream(streams[i % 3]):
-                bufs[i % 3][: e - s].copy_(shard.host[s:e], non_blocking=True)
+            with torch.cuda.stream(streams[i % K]):
+                bufs[i % K][: e - s].copy_(shard.host[s:e], non_blocking=True)
     one_pass(); torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
