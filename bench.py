@@ -369,7 +369,7 @@ def e2e_stream(api, ctx, shard, valid_abs, steps):
         rows = nout = 0
         for (s, e) in shard.bounds:
             vf = min(max(valid_abs - s, 0), e - s)
-            while not ctx.submit_host(base_ptr + s, e - s, valid_from=vf, is_final=(e == shard.nbytes)):
+            while not ctx.submit_host(base_ptr + s, e - s, valid_from=vf, is_final=(e == shard.nbytes), file_offset=s):
                 _, n, st = ctx.next_output_raw(); rows += st.rows; nout += n      # the text is in the library's pinned buffer: on the host
         while ctx.in_flight():
             _, n, st = ctx.next_output_raw(); rows += st.rows; nout += n
@@ -389,7 +389,8 @@ def config_entries(torch, np, api, synth, O, dev, peak, threads, only=None):
     names = [b"HG%05d" % (96 + i) for i in range(SAMPLES)]
     sel = dict(sel_cols=list(range(SAMPLES)), sel_names=names)
     plans = [
-        ("C2", 2, C2_VARIANTS, [("hwe_tester", api.OP_HWE, 0, {}, 20000), ("nonref_filter", api.OP_NONREF_FILTER, 0, {}, 20000)]),
+        ("C2", 2, C2_VARIANTS, [("hwe_tester", api.OP_HWE, 0, {}, 20000), ("nonref_filter", api.OP_NONREF_FILTER, 0, {}, 20000),
+                                ("indexer", api.OP_INDEX, 0, {}, 60000)]),
         ("C3", 3, C2_VARIANTS, [("missing_detector", api.OP_MISSING_DETECT, 0, {}, 20000),
                                 ("allele_counter", api.OP_ALLELE_COUNT, 0, sel, 4000),
                                 ("allele_counter -a", api.OP_ALLELE_COUNT, api.F_AC_AGGREGATE, sel, 400),
@@ -412,7 +413,7 @@ def config_entries(torch, np, api, synth, O, dev, peak, threads, only=None):
             d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
             ctx = api.Context(op, api.FILE, flags=flags, **kw)
             ctx.set_line_hint(sh.line_len)
-            vf = api.find_chrom_header(sh.hdr) if op in (api.OP_ALLELE_FREQ, api.OP_NONREF_FILTER) else (api.first_data_offset(sh.hdr) if op == api.OP_MISSING_DETECT else 0)
+            vf = api.find_chrom_header(sh.hdr) if op in (api.OP_ALLELE_FREQ, api.OP_NONREF_FILTER, api.OP_INDEX) else (api.first_data_offset(sh.hdr) if op == api.OP_MISSING_DETECT else 0)
             ms = []
             for i in range(5):
                 ctx.run_device(sh.d_in.data_ptr(), sh.nbytes, d_out.data_ptr(), out_cap, valid_from=vf)
@@ -470,7 +471,7 @@ def parity_vs_reference(api, O, np, shard, tname, n_variants):
     """GPU tool output (through the C ABI, FILE semantics) against the stdout of the unmodified reference tool
     on the first n_variants lines of the shard."""
     tool = {"hwe_tester": "hwe_tester", "allele_freq_calc": "allele_freq_calc", "missing_detector": "missing_detector",
-            "allele_counter": "allele_counter", "allele_counter -a": "allele_counter", "variant_counter": "variant_counter", "nonref_filter": "nonref_filter"}[tname]
+            "allele_counter": "allele_counter", "allele_counter -a": "allele_counter", "variant_counter": "variant_counter", "nonref_filter": "nonref_filter", "indexer": "indexer"}[tname]
     exe = ref_tool(tool)
     data = shard.prefix_bytes(np, n_variants)
     if tname == "hwe_tester":
@@ -481,6 +482,8 @@ def parity_vs_reference(api, O, np, shard, tname, n_variants):
         got = api.missing_detector(data, api.FILE).out; args = ["-q", "-t", "1", "-i"]   # default threads abort on dotted files >= 10 MB (SURVEY finding 2)
     elif tname == "nonref_filter":
         got = api.nonref_filter(data, api.FILE).out; args = ["-i"]
+    elif tname == "indexer":
+        got = api.indexer(data, api.FILE).out; args = []
     elif tname == "allele_counter":
         got = api.allele_counter(data, api.AC_MT_TEXT, api.AC_TEXT).out; args = ["-q", "-i"]
     elif tname == "allele_counter -a":
@@ -491,7 +494,7 @@ def parity_vs_reference(api, O, np, shard, tname, n_variants):
     if exe is None:
         # no reference binary on this box: the CPU restatement (pinned to the reference by tests/) stands in
         fn = {"hwe_tester": lambda: O.hwe(data, 0), "allele_freq_calc": lambda: O.allele_freq(data, 0), "missing_detector": lambda: O.missing(data, 0),
-              "nonref_filter": lambda: O.nonref_filter(data, 0), "allele_counter": lambda: O.allele_counter(data), "allele_counter -a": lambda: O.allele_counter(data, O.AC_UNIFIED, O.AC_AGGREGATE),
+              "nonref_filter": lambda: O.nonref_filter(data, 0), "indexer": lambda: O.indexer(data, 0), "allele_counter": lambda: O.allele_counter(data), "allele_counter -a": lambda: O.allele_counter(data, O.AC_UNIFIED, O.AC_AGGREGATE),
               "variant_counter": lambda: O.variant_count(data, 0)}[tname]
         exp = fn().out
         res.update({"against": "oracle port (reference binary not built on this box)", "equal": exp == got})

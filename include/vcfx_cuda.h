@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define VCFX_CUDA_ABI_VERSION 1
+#define VCFX_CUDA_ABI_VERSION 2
 
 typedef struct vcfx_ctx vcfx_ctx;
 
@@ -50,6 +50,7 @@ typedef enum {
     VCFX_OP_HWE            = 2,
     VCFX_OP_MISSING_DETECT = 3,
     VCFX_OP_ALLELE_COUNT   = 4,
+    VCFX_OP_INDEX          = 6,   /* VCFX_indexer.cpp:205-322 createVCFIndexMmap, :329-443 createVCFIndex */
     VCFX_OP_NONREF_FILTER  = 5    /* VCFX_nonref_filter.cpp:458-548 filterNonRefMmap, :553-631 filterNonRef */
 } vcfx_op;
 
@@ -102,6 +103,7 @@ typedef struct {
                                   (allele_freq_calc.cpp:382-386); 0 = header already seen       */
     int32_t  is_final;         /* last chunk: the final line may lack its '\n'                   */
     int32_t  reserved;
+    uint64_t file_offset;      /* ABI 2: offset of the chunk's first byte in the whole input (VCFX_OP_INDEX prints absolute offsets) */
 } vcfx_chunk_info;
 
 typedef struct {

@@ -46,7 +46,7 @@ def lib():
             subprocess.run(["make", "-C", str(HERE), "all"], check=True, capture_output=True)
         l = C.CDLL(str(LIB_PATH))
         P = C.POINTER(_Result)
-        for name in ("oracle_allele_freq", "oracle_hwe", "oracle_missing", "oracle_nonref_filter"):
+        for name in ("oracle_allele_freq", "oracle_hwe", "oracle_missing", "oracle_nonref_filter", "oracle_indexer"):
             getattr(l, name).argtypes = [C.c_char_p, C.c_size_t, C.c_int, P]
         l.oracle_variant_count.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, P]
         l.oracle_allele_counter.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_char_p, P]
@@ -84,6 +84,10 @@ def hwe(data: bytes, mode: int = FILE) -> Result:
 
 def missing(data: bytes, mode: int = FILE) -> Result:
     return _call(lib().oracle_missing, data, len(data), mode)
+
+
+def indexer(data: bytes, mode: int = FILE) -> Result:
+    return _call(lib().oracle_indexer, data, len(data), mode)
 
 
 def nonref_filter(data: bytes, mode: int = FILE) -> Result:

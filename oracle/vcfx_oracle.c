@@ -35,6 +35,7 @@ static void ob_put(obuf *o, const char *s, size_t n) {
 static void ob_str(obuf *o, const char *s) { ob_put(o, s, strlen(s)); }
 static void ob_ch(obuf *o, char c) { ob_need(o, 1); o->p[o->n++] = c; }
 
+static void put_int(obuf *o, long long v);
 static void res_init(oracle_result *r) { memset(r, 0, sizeof *r); }
 static void res_take(oracle_result *r, obuf *o) {
     r->out = o->p ? o->p : (char *)calloc(1, 1); r->out_len = o->n;
@@ -660,6 +661,95 @@ static int nr_stdin(const char *in, size_t n, oracle_result *r) {      /* :553-6
 int oracle_nonref_filter(const char *in, size_t n, int mode, oracle_result *r) {
     res_init(r);
     return mode == ORACLE_FILE ? nr_file(in, n, r) : nr_stdin(in, n, r);
+}
+
+/* ------------------------------------------------------------------ indexer (§8 f4): CHROM, POS and the byte offset of
+ * every data line behind the "#CHROM" line.  out: rows = data rows written; warnings = 1 when the tool prints
+ * "Error: no #CHROM header found before variant lines." */
+
+static int ix_space(int c) { return c == ' ' || c == '\t' || c == '\n' || c == '\v' || c == '\f' || c == '\r'; }   /* std::isspace, C locale */
+
+static int ix_file(const char *in, size_t n, oracle_result *r) {         /* VCFX_indexer.cpp:205-322 createVCFIndexMmap */
+    obuf o = {0}; size_t pos = 0; line_t ln; int found = 0, warned = 0, saw_header = 0;
+    while (next_line(in, n, &pos, &ln)) {
+        const char *s = ln.s, *e = ln.e;
+        long long off = (long long)(s - in);
+        if (e > s && e[-1] == '\r') --e;                                   /* :263-266 */
+        if (s == e) continue;
+        const char *p = s;
+        while (p < e && (*p == ' ' || *p == '\t')) ++p;                    /* :271-274 */
+        if (p < e && *p == '#') {
+            saw_header = 1;
+            if (!found && e - s >= 6 && e - p >= 6 && memcmp(p, "#CHROM", 6) == 0) {   /* :108-122 isChromHeaderLine */
+                found = 1; ob_str(&o, "CHROM\tPOS\tFILE_OFFSET\n");
+            }
+        } else if (found) {                                                /* :74-105 extractChromPos */
+            if (p >= e) continue;
+            const char *cs = p;
+            while (p < e && *p != '\t') ++p;
+            if (p == cs || p >= e) continue;
+            const char *ce = p; ++p;
+            unsigned long long v = 0;                                      /* int64 arithmetic that wraps, as compiled */
+            while (p < e && *p >= '0' && *p <= '9') { v = v * 10ULL + (unsigned long long)(*p - '0'); ++p; }
+            long long pv = (long long)v;
+            if (pv <= 0) continue;
+            ob_put(&o, cs, (size_t)(ce - cs)); ob_ch(&o, '\t'); put_int(&o, pv); ob_ch(&o, '\t'); put_int(&o, off); ob_ch(&o, '\n');
+            r->rows++;
+        } else if (!saw_header && !warned) { warned = 1; r->warnings = 1; }
+    }
+    res_take(r, &o);
+    return 0;
+}
+
+static int ix_stdin(const char *in, size_t n, oracle_result *r) {        /* :329-443 createVCFIndex */
+    obuf o = {0}; size_t pos = 0; line_t ln; int found = 0, warned = 0, saw_header = 0;
+    while (next_line(in, n, &pos, &ln)) {
+        const char *s = ln.s, *e = ln.e;
+        long long off = (long long)(s - in);
+        if (e > s && e[-1] == '\r') --e;                                   /* :421-423 / :437-439 */
+        if (s == e) continue;
+        const char *t = s;
+        while (t < e && ix_space((unsigned char)*t)) ++t;                  /* ltrim */
+        if (t < e && *t == '#') {
+            saw_header = 1;
+            if (!found) {                                                  /* fields[0] == "#CHROM" and a second field */
+                const char *tab = memchr(t, '\t', (size_t)(e - t));
+                if (tab && tab - t == 6 && memcmp(t, "#CHROM", 6) == 0) { found = 1; ob_str(&o, "CHROM\tPOS\tFILE_OFFSET\n"); }
+            }
+            continue;
+        }
+        if (!found) { if (!saw_header && !warned) { warned = 1; r->warnings = 1; } continue; }
+        const char *tab = memchr(s, '\t', (size_t)(e - s));                /* splitTabs(line): the line as it is */
+        if (!tab) continue;
+        const char *ps = tab + 1, *pe = memchr(ps, '\t', (size_t)(e - ps));
+        if (!pe) pe = e;
+        /* std::stoll: leading isspace, an optional sign, at least one digit, out of range throws (line skipped) */
+        const char *q = ps;
+        while (q < pe && ix_space((unsigned char)*q)) ++q;
+        int neg = 0;
+        if (q < pe && (*q == '+' || *q == '-')) { neg = (*q == '-'); ++q; }
+        if (q >= pe || *q < '0' || *q > '9') continue;
+        unsigned long long v = 0; int over = 0;
+        const unsigned long long lim = neg ? 9223372036854775808ULL : 9223372036854775807ULL;
+        while (q < pe && *q >= '0' && *q <= '9') {
+            unsigned d = (unsigned)(*q - '0');
+            if (v > (lim - d) / 10ULL) over = 1;
+            v = v * 10ULL + d; ++q;
+        }
+        if (over) continue;
+        ob_put(&o, s, (size_t)(tab - s)); ob_ch(&o, '\t');
+        if (neg) { if (v) ob_ch(&o, '-'); }
+        { char nb[32]; int l = sprintf(nb, "%llu", v); ob_put(&o, nb, (size_t)l); }
+        ob_ch(&o, '\t'); put_int(&o, off); ob_ch(&o, '\n');
+        r->rows++;
+    }
+    res_take(r, &o);
+    return 0;
+}
+
+int oracle_indexer(const char *in, size_t n, int mode, oracle_result *r) {
+    res_init(r);
+    return mode == ORACLE_FILE ? ix_file(in, n, r) : ix_stdin(in, n, r);
 }
 
 /* ------------------------------------------------------------------ variant_counter */

@@ -64,6 +64,9 @@ def hand_cases():
         L("GT", "0/0") + "\t", L("GT"), "1\t1\t.\tA\tG\t.\t.\t.\tGT", L("GT:DP", "0/0:1", "0/0:"), L("DP:GT", "1:0/0", "1"),
         L("DP:GT", "1:0/0", "1:"), L("DP:GT", "1:0/0", ":0|0"), L("DP", "1", "2"), L("GT:", "0/0", "0/0"), L("", "0/0", "0/0"), "",
         L("GT", "0/0", "0/0\r"), L("GT", "0/0", "0/0") + "\r", "\r", L("GT", "0/0/0", "0|0|0|0"), L("GT", "./.", "0/0"), L("GT", "0/0", "0/0")]))
+    # indexer: what counts as CHROM and POS in the two modes (blanks in front, signs, wrap-around, CRLF, "#CHROM" look-alikes)
+    c["ix_quirks"] = ("##x\n #CHROMX\tY\n#CHROM\tPOS\tID\n1\t100\t.\n 2\t+7x\t.\n\t3\t5\n4\t0\n5\t-3\n6\t 12\n7\n8\t99999999999999999999\n"
+                      "9\t12\r\n\n#late\t1\nchrX\t007\tid\n10\t9223372036854775807\n11\t9223372036854775808\n12\t-9223372036854775808\n13\t5")
     return {k: v.encode() for k, v in c.items()}
 
 
@@ -78,6 +81,10 @@ def run_all(data: bytes, ac_ok: bool, md_file_ok: bool = True):
                 out[f"{tool}.file"] = [rc, base64.b64encode(so).decode()]
             rc, so, _ = O.run_ref(tool, ["-q"] if tool != "hwe_tester" else [], stdin=data)
             out[f"{tool}.stdin"] = [rc, base64.b64encode(so).decode()]
+        rc, so, se = O.run_ref("indexer", [f.name])
+        out["indexer.file"] = [rc, base64.b64encode(so).decode(), se.count(b"no #CHROM")]
+        rc, so, se = O.run_ref("indexer", [], stdin=data)
+        out["indexer.stdin"] = [rc, base64.b64encode(so).decode(), se.count(b"no #CHROM")]
         rc, so, se = O.run_ref("nonref_filter", ["-i", f.name])
         out["nonref_filter.file"] = [rc, base64.b64encode(so).decode(), se.count(b"Warning")]
         rc, so, se = O.run_ref("nonref_filter", [], stdin=data)

@@ -99,11 +99,25 @@ def test_nonref_filter(files, tmp_path):
     both("nonref_filter", ["-i", str(files["c3"])], env=SMALL_CHUNK)
 
 
-@pytest.mark.parametrize("tool", ["allele_freq_calc", "hwe_tester", "missing_detector", "variant_counter", "allele_counter", "nonref_filter"])
+def test_indexer(files, tmp_path):
+    """VCFX_indexer: file argument and stdin, several chunks (offsets stay absolute), the quirks fixture."""
+    import golden_util
+    q = tmp_path / "q.vcf"; q.write_bytes(golden_util.load()["ix_quirks"][0])
+    for p in list(files.values()) + [q]:
+        a, b = both("indexer", [str(p)])
+        assert a[2] == b[2]
+        a, b = both("indexer", [], stdin=p.read_bytes())
+        assert a[2] == b[2]
+    both("indexer", [str(files["c3"])], env=SMALL_CHUNK)
+    both("indexer", [], stdin=files["c3"].read_bytes(), env=SMALL_CHUNK)
+    both("indexer", [], stdin=files["nonl"].read_bytes(), env={"VCFX_CHUNK_BYTES": "4096"})
+
+
+@pytest.mark.parametrize("tool", ["allele_freq_calc", "hwe_tester", "missing_detector", "variant_counter", "allele_counter", "nonref_filter", "indexer"])
 def test_flags(tool, files):
     for args in (["--help"], ["-v"]):
         both(tool, args)
-    a, b = both(tool, ["/nonexistent/file.vcf"] if tool == "variant_counter" else (["-i", "/nonexistent/file.vcf"] if tool == "nonref_filter" else ["-q", "-i", "/nonexistent/file.vcf"]))
+    a, b = both(tool, ["/nonexistent/file.vcf"] if tool == "variant_counter" else (["-i", "/nonexistent/file.vcf"] if tool == "nonref_filter" else ["/nonexistent/file.vcf"] if tool == "indexer" else ["-q", "-i", "/nonexistent/file.vcf"]))
     assert a[2] == b[2]
     both(tool, [], stdin=b"")          # empty stdin: per-tool behaviour (help+rc1 / header only / nothing / Total 0)
 
@@ -178,7 +192,7 @@ def test_multi_gpu_same_bytes(tmp_path):
     env_multi = {"VCFX_CUDA_DEVICES": "all", "VCFX_CHUNK_BYTES": str(128 << 10)}
     env_one = {"VCFX_CHUNK_BYTES": str(128 << 10)}
     cases = [("allele_freq_calc", ["-q", "-i"]), ("hwe_tester", ["-q", "-i"]), ("missing_detector", ["-q", "-t", "1", "-i"]),
-             ("variant_counter", []), ("allele_counter", ["-q", "-i"]), ("allele_counter", ["-q", "-a", "-i"]), ("nonref_filter", ["-i"])]
+             ("variant_counter", []), ("allele_counter", ["-q", "-i"]), ("allele_counter", ["-q", "-a", "-i"]), ("nonref_filter", ["-i"]), ("indexer", [])]
     for f in (src, late):
         for tool, args in cases:
             one = run(BIN / f"VCFX_{tool}", [*args, str(f)], env=env_one)

@@ -20,7 +20,7 @@ def _cmp(name, got, exp):
                              f"  got {got[max(0, i - 60): i + 60]!r}\n  exp {exp[max(0, i - 60): i + 60]!r}")
 
 
-def run_all(api, O, data, tag, chunk_bytes=0, tile_bytes=0, tools=("af", "hwe", "vc", "md", "nr")):
+def run_all(api, O, data, tag, chunk_bytes=0, tile_bytes=0, tools=("af", "hwe", "vc", "md", "nr", "ix")):
     kw = dict(chunk_bytes=chunk_bytes, tile_bytes=tile_bytes)
     for mode in MODES:
         if "af" in tools:
@@ -38,6 +38,10 @@ def run_all(api, O, data, tag, chunk_bytes=0, tile_bytes=0, tools=("af", "hwe", 
             r = api.missing_detector(data, mode, **kw); o = O.missing(data, mode)
             _cmp(f"{tag} md mode{mode}", r.out, o.out)
             assert r.totals.flagged == o.flagged or (mode == 0 and r.totals.dots_terminated == 0)
+        if "ix" in tools:
+            r = api.indexer(data, mode, **kw); o = O.indexer(data, mode)
+            _cmp(f"{tag} ix mode{mode}", r.out, o.out)
+            assert (r.totals.rows, r.totals.pre_header) == (o.rows, o.warnings)
         if "nr" in tools:
             r = api.nonref_filter(data, mode, **kw); o = O.nonref_filter(data, mode)
             _cmp(f"{tag} nr mode{mode}", r.out, o.out)
@@ -162,6 +166,11 @@ def test_gpu_matches_reference_golden(cuda_api):
                     assert r.rc == exp[key][0], (name, key)
                     if r.rc == 0:
                         _cmp(f"golden {name} {key}", r.out, exp[key][1])
+            key = f"indexer.{mode_name}"
+            if key in exp:
+                r = api.indexer(data, mode)
+                assert (r.rc, r.totals.pre_header) == (exp[key][0], exp[key][2]), (name, key)
+                _cmp(f"golden {name} {key}", r.out, exp[key][1])
             key = f"nonref_filter.{mode_name}"
             if key in exp:
                 r = api.nonref_filter(data, mode)
@@ -300,6 +309,35 @@ def test_digit_path_exceptions(cuda_api, oracle):
         body.append(b"1\t%d\t.\tA\tG\t.\tPASS\t.\tGT\t" % (k + 1) + b"\t".join(gts))
     data = line_hdr + b"\n".join(body) + b"\n"
     run_all(cuda_api, oracle, data, "digit path, one odd genotype at every offset", tools=("af",))
+
+
+def test_indexer_cases(cuda_api, oracle):
+    """VCFX_indexer: CHROM / POS as the two modes read them, and byte offsets that must be absolute — across tiles, across
+    the chunks of the streaming path, and beyond 4 GiB (a chunk submitted with a large file_offset)."""
+    import golden_util
+    data, _ = golden_util.load()["ix_quirks"]
+    for kw in ({}, {"tile_bytes": 512}, {"chunk_bytes": 4096}):
+        run_all(cuda_api, oracle, data, f"ix quirks {kw}", tools=("ix",), **kw)
+    data = synth.make_vcf(2, 3000, 40, seed=77)
+    run_all(cuda_api, oracle, data, "ix chunks", chunk_bytes=64 << 10, tools=("ix",))
+    # one chunk far into a large file: the offsets are the chunk's plus 5 GiB
+    api = cuda_api
+    body = data[api.find_chrom_header(data):]
+    base = 5 << 30
+    ctx = api.Context(api.OP_INDEX, api.FILE, chunk_bytes=1 << 20)
+    buf, cap = ctx.acquire()
+    import ctypes as C
+    C.memmove(buf, body, len(body))
+    ctx.submit(len(body), valid_from=0, is_final=True, file_offset=base)
+    out, st, _ = ctx.next_output()
+    ctx.close()
+    exp = oracle.indexer(data, 0).out.split(b"\n")[1:-1]
+    got = out.split(b"\n")[:-1]
+    shift = base - api.find_chrom_header(data)
+    assert len(got) == len(exp) == 3000
+    for g, e in zip(got, exp):
+        c1, p1, o1 = g.split(b"\t"); c2, p2, o2 = e.split(b"\t")
+        assert (c1, p1) == (c2, p2) and int(o1) == int(o2) + shift
 
 
 def test_nonref_filter_cases(cuda_api, oracle):

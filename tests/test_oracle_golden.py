@@ -20,6 +20,10 @@ def check_case(O, data, exp, name):
             if key in exp:
                 r = fn(data, mode)
                 assert (r.rc, r.out) == exp[key][:2], (name, key)
+        key = f"indexer.{mode_name}"
+        if key in exp:
+            r = O.indexer(data, mode)
+            assert (r.rc, r.out, r.warnings) == tuple(exp[key][:3]), (name, key)
         key = f"nonref_filter.{mode_name}"
         if key in exp:
             r = O.nonref_filter(data, mode)
@@ -70,6 +74,10 @@ def test_oracle_matches_reference_binaries_fuzz(oracle, seed):
             assert (r.rc, r.out) == (rc, out), (tool, "file")
             rc, out, _ = O.run_ref(tool, ["-q"] if tool != "hwe_tester" else [], stdin=data); r = fn(data, O.STDIN)
             assert (r.rc, r.out) == (rc, out), (tool, "stdin")
+        rc, out, err = O.run_ref("indexer", [f.name]); r = O.indexer(data, O.FILE)
+        assert (r.rc, r.out, r.warnings) == (rc, out, err.count(b"no #CHROM")), "indexer file"
+        rc, out, err = O.run_ref("indexer", [], stdin=data); r = O.indexer(data, O.STDIN)
+        assert (r.rc, r.out, r.warnings) == (rc, out, err.count(b"no #CHROM")), "indexer stdin"
         rc, out, err = O.run_ref("nonref_filter", ["-i", f.name]); r = O.nonref_filter(data, O.FILE)
         assert (r.rc, r.out, r.warnings) == (rc, out, err.count(b"Warning")), "nonref_filter file"
         rc, out, err = O.run_ref("nonref_filter", [], stdin=data); r = O.nonref_filter(data, O.STDIN)

@@ -17,7 +17,7 @@ from pathlib import Path
 
 from . import build as _build
 
-OP_VARIANT_COUNT, OP_ALLELE_FREQ, OP_HWE, OP_MISSING_DETECT, OP_ALLELE_COUNT, OP_NONREF_FILTER = range(6)
+OP_VARIANT_COUNT, OP_ALLELE_FREQ, OP_HWE, OP_MISSING_DETECT, OP_ALLELE_COUNT, OP_NONREF_FILTER, OP_INDEX = range(7)
 FILE, STDIN = 0, 1
 F_AC_AGGREGATE, F_AC_BINARY, F_AC_FORWARD = 1, 2, 4
 DEVICE_PAD = 8192
@@ -45,7 +45,7 @@ class Cfg(C.Structure):
 
 
 class ChunkInfo(C.Structure):
-    _fields_ = [("data_valid_from", C.c_uint64), ("is_final", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("data_valid_from", C.c_uint64), ("is_final", C.c_int32), ("reserved", C.c_int32), ("file_offset", C.c_uint64)]
 
 
 class ChunkStats(C.Structure):
@@ -199,22 +199,22 @@ class Context:
         self._check(rc)
         return buf.value, cap.value
 
-    def submit(self, nbytes: int, valid_from: int = 0, is_final: bool = True):
-        info = ChunkInfo(valid_from, int(is_final), 0)
+    def submit(self, nbytes: int, valid_from: int = 0, is_final: bool = True, file_offset: int = 0):
+        info = ChunkInfo(valid_from, int(is_final), 0, file_offset)
         self._check(self._l.vcfx_cuda_submit(self._h, nbytes, C.byref(info)))
 
-    def submit_host(self, host_ptr: int, nbytes: int, valid_from: int = 0, is_final: bool = True) -> bool:
+    def submit_host(self, host_ptr: int, nbytes: int, valid_from: int = 0, is_final: bool = True, file_offset: int = 0) -> bool:
         """Submit a chunk straight from caller memory; False when every slot is in flight."""
-        info = ChunkInfo(valid_from, int(is_final), 0)
+        info = ChunkInfo(valid_from, int(is_final), 0, file_offset)
         rc = self._l.vcfx_cuda_submit_host(self._h, host_ptr, nbytes, C.byref(info))
         if rc == E_BUSY:
             return False
         self._check(rc)
         return True
 
-    def submit_shared(self, primary: "Context", valid_from: int = 0, is_final: bool = True) -> bool:
+    def submit_shared(self, primary: "Context", valid_from: int = 0, is_final: bool = True, file_offset: int = 0) -> bool:
         """Run this context's op on the chunk last submitted to ``primary`` (no second upload)."""
-        info = ChunkInfo(valid_from, int(is_final), 0)
+        info = ChunkInfo(valid_from, int(is_final), 0, file_offset)
         rc = self._l.vcfx_cuda_submit_shared(self._h, primary._h, C.byref(info))
         if rc == E_BUSY:
             return False
@@ -248,8 +248,8 @@ class Context:
         return text.value, n.value, st
 
     # -- device-resident path ------------------------------------------------------------
-    def run_device(self, d_in: int, nbytes: int, d_out: int, out_cap: int, valid_from: int = 0, is_final: bool = True):
-        info = ChunkInfo(valid_from, int(is_final), 0)
+    def run_device(self, d_in: int, nbytes: int, d_out: int, out_cap: int, valid_from: int = 0, is_final: bool = True, file_offset: int = 0):
+        info = ChunkInfo(valid_from, int(is_final), 0, file_offset)
         self._check(self._l.vcfx_cuda_run_device(self._h, d_in, nbytes, C.byref(info), d_out, out_cap))
 
     def sync(self) -> ChunkStats:
@@ -306,7 +306,7 @@ def stream_bytes(ctx: Context, data, chunk_bytes: int, valid_abs: int = 0):
         assert e - s <= cap
         C.memmove(buf, (C.c_char * (e - s)).from_buffer_copy(mv[s:e]), e - s)
         vf = min(max(valid_abs - s, 0), e - s)
-        ctx.submit(e - s, valid_from=vf, is_final=(e == n))
+        ctx.submit(e - s, valid_from=vf, is_final=(e == n), file_offset=s)
         # line numbers: chunks are drained in order, so the base is exact when drained
     while ctx.in_flight():
         drain()
@@ -403,6 +403,44 @@ def missing_detector(data: bytes, mode: int = FILE, chunk_bytes: int = 0, **kw) 
         last = data[data.rfind(b"\n") + 1:]
         return ToolResult(body[:cut] + last, 0, tot)
     return ToolResult(b"".join(outs), 0, tot)
+
+
+INDEX_HEADER = b"CHROM\tPOS\tFILE_OFFSET\n"                     # VCFX_indexer.cpp:283 / :364
+
+
+def _index_header(data: bytes, mode: int):
+    """(offset of the first line VCFX_indexer takes for the "#CHROM" line or len(data), whether a data line came before
+    any '#' line).  File mode: blanks / tabs, then "#CHROM" (VCFX_indexer.cpp:108-122); stdin mode: white space, then a
+    first field that is exactly "#CHROM" with a second field behind it (:349-356)."""
+    pos, n, saw_hash, warned = 0, len(data), False, False
+    ws = b" \t" if mode == FILE else b" \t\n\v\f\r"
+    while pos < n:
+        nl = data.find(b"\n", pos)
+        le = n if nl < 0 else nl
+        line = data[pos:le]
+        if line.endswith(b"\r"):
+            line = line[:-1]
+        if line:
+            t = line.lstrip(ws)
+            if t.startswith(b"#"):
+                saw_hash = True
+                if (mode == FILE and len(line) >= 6 and t.startswith(b"#CHROM")) or (mode == STDIN and t.startswith(b"#CHROM\t")):
+                    return pos, warned
+            elif not saw_hash:
+                warned = True
+        pos = le + 1
+    return n, warned
+
+
+def indexer(data: bytes, mode: int = FILE, chunk_bytes: int = 0, **kw) -> ToolResult:
+    """VCFX_indexer: CHROM, POS and byte offset of every data line behind the "#CHROM" line.  totals.pre_header = 1 when
+    the tool prints "Error: no #CHROM header found before variant lines."."""
+    hdr_off, warned = _index_header(data, mode)
+    chunk_bytes = chunk_bytes or min(64 << 20, max(1 << 20, (len(data) + (1 << 20) - 1) & ~((1 << 20) - 1)))
+    ctx, cached = _cached_context(OP_INDEX, mode, 0, 0, chunk_bytes, **kw)
+    outs, tot = stream_bytes(ctx, data, chunk_bytes, hdr_off)
+    tot.pre_header = int(warned)
+    return ToolResult((INDEX_HEADER if hdr_off < len(data) else b"") + b"".join(outs), 0, tot)
 
 
 def nonref_filter(data: bytes, mode: int = FILE, chunk_bytes: int = 0, **kw) -> ToolResult:

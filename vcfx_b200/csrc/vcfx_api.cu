@@ -57,7 +57,7 @@ struct Slot {
     Work w;
     size_t nbytes = 0;
     size_t out_cap = 0;
-    vcfx_chunk_info info = {0, 1, 0};
+    vcfx_chunk_info info = {0, 1, 0, 0};
     bool in_flight = false;
     cudaEvent_t ev_h2d = nullptr;          // the chunk is on the device (H2D + pad done)
     cudaEvent_t ev_shared_done = nullptr;  // a secondary context finished reading this slot's d_in
@@ -92,7 +92,7 @@ struct vcfx_ctx {
     size_t dev_nbytes = 0;
     uint8_t *dev_in = nullptr, *dev_out = nullptr;
     size_t dev_out_cap = 0;
-    vcfx_chunk_info dev_info = {0, 1, 0};
+    vcfx_chunk_info dev_info = {0, 1, 0, 0};
     // allele_counter selection (device copies)
     uint32_t n_sel = 0, max_col = 0;
     uint32_t *d_sel_col = nullptr, *d_name_off = nullptr;
@@ -137,6 +137,7 @@ kernel_fn kernel_for(int op) {
     case VCFX_OP_HWE:           return vcfx_scan_kernel<OP_HWE, 0>;
     case VCFX_OP_MISSING_DETECT: return vcfx_scan_kernel<OP_MD, 0>;
     case VCFX_OP_NONREF_FILTER: return vcfx_scan_kernel<OP_NR, 0>;
+    case VCFX_OP_INDEX: return vcfx_scan_kernel<OP_IX, 0>;
     case VCFX_OP_ALLELE_COUNT:  return vcfx_scan_kernel<OP_AC, 0>;
     default: return nullptr;
     }
@@ -156,6 +157,7 @@ kernel_fn format_kernel_for(int op, int ac_fmt = 0) {
     case VCFX_OP_HWE:         return format_rows_kernel<OP_HWE>;
     case VCFX_OP_MISSING_DETECT: return md_copy_kernel;
     case VCFX_OP_NONREF_FILTER: return md_copy_kernel;
+    case VCFX_OP_INDEX: return format_rows_kernel<OP_IX>;
     default: return nullptr;
     }
 }
@@ -303,6 +305,7 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
     P.tile_bytes = tile; P.n_tiles = tiles;
     P.mode = ctx->cfg.mode; P.flags = ctx->cfg.flags;
     P.valid_from = info ? info->data_valid_from : 0;
+    P.file_offset = info ? info->file_offset : 0;
     P.is_final = info ? info->is_final : 1;
     P.out = d_out; P.out_cap = out_cap;
     P.tile_lines = w.tile_lines; P.tile_out = w.tile_out; P.tile_base = w.tile_base; P.line_base = w.line_base;
@@ -426,7 +429,7 @@ const char *vcfx_cuda_last_error(const vcfx_ctx *ctx) { return ctx ? ctx->last_e
 int vcfx_cuda_create(const vcfx_cfg *cfg, vcfx_ctx **out) {
     if (!cfg || !out) return VCFX_E_INVALID;
     *out = nullptr;
-    if (cfg->op < VCFX_OP_VARIANT_COUNT || cfg->op > VCFX_OP_NONREF_FILTER) return VCFX_E_INVALID;
+    if (cfg->op < VCFX_OP_VARIANT_COUNT || cfg->op > VCFX_OP_INDEX) return VCFX_E_INVALID;
     if (cfg->mode != VCFX_MODE_FILE && cfg->mode != VCFX_MODE_STDIN) return VCFX_E_INVALID;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return VCFX_E_NO_DEVICE;
@@ -608,7 +611,7 @@ int vcfx_cuda_submit(vcfx_ctx *ctx, size_t nbytes, const vcfx_chunk_info *info) 
     CU(cudaMemsetAsync(s.d_in + nbytes, '\n', 64, s.stream));
     CU(cudaEventRecord(s.ev_h2d, s.stream));
     s.d_in_used = s.d_in;
-    if (info) s.info = *info; else s.info = vcfx_chunk_info{0, 1, 0};
+    if (info) s.info = *info; else s.info = vcfx_chunk_info{0, 1, 0, 0};
     int rc = launch_chunk(ctx, s.w, s.stream, s.d_in, nbytes, &s.info, s.d_out, s.out_cap, false);
     if (rc != VCFX_OK) return rc;
     s.nbytes = nbytes; s.in_flight = true; s.d2h_issued = false;
@@ -632,7 +635,7 @@ int vcfx_cuda_submit_host(vcfx_ctx *ctx, const void *host, size_t nbytes, const 
     CU(cudaMemsetAsync(s.d_in + nbytes, '\n', 64, s.stream));
     CU(cudaEventRecord(s.ev_h2d, s.stream));
     s.d_in_used = s.d_in;
-    if (info) s.info = *info; else s.info = vcfx_chunk_info{0, 1, 0};
+    if (info) s.info = *info; else s.info = vcfx_chunk_info{0, 1, 0, 0};
     rc = launch_chunk(ctx, s.w, s.stream, s.d_in, nbytes, &s.info, s.d_out, s.out_cap, false);
     if (rc != VCFX_OK) return rc;
     s.nbytes = nbytes; s.in_flight = true; s.d2h_issued = false;
@@ -659,7 +662,7 @@ int vcfx_cuda_submit_shared(vcfx_ctx *ctx, vcfx_ctx *primary, const vcfx_chunk_i
     if (rc != VCFX_OK) return rc;
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamWaitEvent(s.stream, ps.ev_h2d, 0));                 // the bytes are there
-    if (info) s.info = *info; else s.info = vcfx_chunk_info{0, 1, 0};
+    if (info) s.info = *info; else s.info = vcfx_chunk_info{0, 1, 0, 0};
     // An operation that may have to run a chunk again (more rows or more text than its slot was sized for) takes a
     // private device copy (a few tens of microseconds): the primary is then free to reuse its buffer at once and a
     // re-run never reads bytes the primary has overwritten.  variant_counter never re-runs and reads the primary's bytes.
@@ -746,7 +749,7 @@ int vcfx_cuda_run_device(vcfx_ctx *ctx, void *d_in, size_t nbytes, const vcfx_ch
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_work(ctx, ctx->dev_work, nbytes);
     if (rc != VCFX_OK) return rc;
-    ctx->dev_info = info ? *info : vcfx_chunk_info{0, 1, 0};
+    ctx->dev_info = info ? *info : vcfx_chunk_info{0, 1, 0, 0};
     ctx->dev_in = (uint8_t *)d_in; ctx->dev_out = (uint8_t *)d_out; ctx->dev_out_cap = out_cap;
     rc = launch_chunk(ctx, ctx->dev_work, ctx->dev_stream, ctx->dev_in, nbytes, &ctx->dev_info, ctx->dev_out, out_cap);
     if (rc != VCFX_OK) return rc;

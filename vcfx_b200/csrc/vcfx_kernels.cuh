@@ -36,7 +36,7 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int WARPS_PER_CTA = 8;
 constexpr uint32_t WINDOW = 512;
 
-enum : int { OP_VC = 0, OP_AF = 1, OP_HWE = 2, OP_MD = 3, OP_AC = 4, OP_NR = 5 };
+enum : int { OP_VC = 0, OP_AF = 1, OP_HWE = 2, OP_MD = 3, OP_AC = 4, OP_NR = 5, OP_IX = 6 };
 constexpr uint32_t NR_PLAIN = 0xFFFFFFFFu;     // Rec::b of a nonref_filter record: the line is written as its content + '\n' (or not at all)
 enum : int { MODE_FILE = 0, MODE_STDIN = 1 };
 enum : int { AC_TEXT_MT = 0, AC_TEXT_FWD = 1, AC_AGG = 2, AC_BIN = 3 };
@@ -81,6 +81,7 @@ struct KParams {
     int32_t mode;
     uint32_t flags;
     uint64_t valid_from;
+    uint64_t file_offset;            // offset of the chunk in the whole input (indexer)
     int32_t is_final;
     uint8_t *out;
     uint64_t out_cap;
@@ -272,6 +273,67 @@ __device__ __noinline__ bool nr_sample_homref(const uint8_t *p, bool file_mode, 
     if (file_mode && n == 3) return ldb(gs) == '0' && is_sep(ldb(gs + 1)) && ldb(gs + 2) == '0';
     for (const uint8_t *q = gs; q < ge; ++q) { const uint32_t b = ldb(q); if (b != '0' && !is_sep(b)) return false; }
     return true;
+}
+
+// VCFX_indexer on one data line [s, e) (a '\r' before the '\n' already cut off): where CHROM is and what POS reads as.
+//   file mode  (VCFX_indexer.cpp:74-105 extractChromPos): blanks and tabs in front are skipped, CHROM runs to the first
+//              tab (not empty, the tab must exist), POS is the digit run behind it in wrapping 64-bit arithmetic and
+//              must come out > 0
+//   stdin mode (:373-397): fields as splitTabs cuts the line (CHROM = everything in front of the first tab, possibly
+//              empty or led by blanks; a second field must exist), POS as std::stoll reads it (white space, a sign,
+//              at least one digit, anything behind ignored, out of range = no row)
+// A line whose first non-blank byte is '#' is a header line: no row.
+__device__ __noinline__ bool ix_parse_line(const uint8_t *s, const uint8_t *e, bool file_mode, uint32_t &c_off, uint32_t &c_len, long long &pos) {
+    auto space = [](uint32_t c) { return c == ' ' || (c >= 9u && c <= 13u); };
+    const uint8_t *p = s;
+    if (file_mode) {
+        while (p < e && (ldb(p) == ' ' || ldb(p) == '\t')) ++p;
+        if (p >= e || ldb(p) == '#') return false;
+        const uint8_t *cs = p;
+        while (p < e && ldb(p) != '\t') ++p;
+        if (p == cs || p >= e) return false;
+        c_off = (uint32_t)(cs - s); c_len = (uint32_t)(p - cs);
+        ++p;
+        unsigned long long v = 0;
+        while (p < e && is_dig(ldb(p))) { v = v * 10ULL + (ldb(p) - 48u); ++p; }
+        pos = (long long)v;
+        return pos > 0;
+    }
+    while (p < e && space(ldb(p))) ++p;
+    if (p < e && ldb(p) == '#') return false;
+    const uint8_t *tab = s;
+    while (tab < e && ldb(tab) != '\t') ++tab;
+    if (tab >= e) return false;
+    c_off = 0; c_len = (uint32_t)(tab - s);
+    const uint8_t *q = tab + 1, *pe = q;
+    while (pe < e && ldb(pe) != '\t') ++pe;
+    while (q < pe && space(ldb(q))) ++q;
+    bool neg = false;
+    if (q < pe && (ldb(q) == '+' || ldb(q) == '-')) { neg = ldb(q) == '-'; ++q; }
+    if (q >= pe || !is_dig(ldb(q))) return false;
+    const unsigned long long lim = neg ? 9223372036854775808ULL : 9223372036854775807ULL;
+    unsigned long long v = 0;
+    while (q < pe && is_dig(ldb(q))) {
+        const unsigned long long d = ldb(q) - 48u;
+        if (v > (lim - d) / 10ULL) return false;
+        v = v * 10ULL + d; ++q;
+    }
+    pos = neg ? (long long)(0ULL - v) : (long long)v;
+    return true;
+}
+__device__ __forceinline__ uint32_t dec_len64(long long v) {
+    unsigned long long u = v < 0 ? 0ULL - (unsigned long long)v : (unsigned long long)v;
+    uint32_t n = v < 0 ? 1u : 0u;
+    do { ++n; u /= 10ULL; } while (u);
+    return n;
+}
+__device__ __forceinline__ uint8_t *put_dec64(uint8_t *d, long long v) {
+    unsigned long long u = v < 0 ? 0ULL - (unsigned long long)v : (unsigned long long)v;
+    if (v < 0) *d++ = '-';
+    char t[24]; int n = 0;
+    do { t[n++] = (char)('0' + (int)(u % 10ULL)); u /= 10ULL; } while (u);
+    while (n) *d++ = (uint8_t)t[--n];
+    return d;
 }
 
 // byte index (0..15) of the first set 0x80-bit over the lane's four mask words, with selects instead of
@@ -769,7 +831,7 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                                            const uint32_t tile, const uint64_t a, const uint64_t a0, const uint8_t *__restrict__ tin,
                                            const uint32_t rb, const uint32_t nrel, const uint64_t n, TileState<OP> &st) {
     constexpr bool HAS_VAR = (OP == OP_AF || OP == OP_HWE);
-    constexpr int NEED_TABS = (OP == OP_VC) ? 7 : 9;        // the header phase ends once this many tabs are ranked
+    constexpr int NEED_TABS = (OP == OP_VC) ? 7 : (OP == OP_IX) ? 1 : 9;        // the header phase ends once this many tabs are ranked
     volatile uint32_t *tp = ws.tp;
     const int wid = threadIdx.x >> 5;
     volatile unsigned int *s_odd = ws.odd, *s_reg = ws.reg, *s_tag = ws.tag;
@@ -1668,6 +1730,29 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                     }
                 }
             }
+            else if (OP == OP_IX) {
+                // VCFX_indexer: a row (CHROM, POS, byte offset of the line) for every data line behind the "#CHROM" line
+                // that parses; both modes cut a '\r' in front of the '\n' and skip empty lines
+                if (ee != ls && (a0 + ls >= P.valid_from)) {
+                    uint32_t c_off = 0, c_len = 0; long long pos = 0; bool ok = false;
+                    if (lane == 0) ok = ix_parse_line(tin + ls, tin + ee, P.mode == MODE_FILE, c_off, c_len, pos);
+                    ok = __shfl_sync(FULL, (int)ok, 0) != 0;
+                    if (ok) {
+                        uint32_t row_len = 0;
+                        if (lane == 0) {
+                            row_len = c_len + 1u + dec_len64(pos) + 1u + dec_len64((long long)(P.file_offset + a0 + ls)) + 1u;
+                            unsigned long long slot = alloc_slot(ws.rec_base, ws.rec_used, P.stats);
+                            if (slot < P.rec_cap) {
+                                Rec r; r.tile = tile; r.ls_rel = (uint32_t)(a0 + ls - a); r.prefix_len = c_len;
+                                r.off_in_tile = (uint32_t)out_bytes; r.a = c_off; r.b = 0;
+                                r.c = (uint32_t)((unsigned long long)pos & 0xFFFFFFFFULL); r.d = (uint32_t)((unsigned long long)pos >> 32);
+                                P.recs[slot] = r;
+                            }
+                        }
+                        out_bytes += __shfl_sync(FULL, row_len, 0); VCFX_COUNT(C_ROWS, 1);
+                    }
+                }
+            }
             else if (OP == OP_NR) {
                 // VCFX_nonref_filter.cpp:478-544 / 553-631: every line is written as its content + '\n' (file mode: without a
                 // '\r' before the '\n'), except data lines behind the "#CHROM" line whose samples are all hom-ref.  Lines that
@@ -1765,7 +1850,7 @@ vcfx_scan_kernel(const VCFX_GRID_CONSTANT KParams P) {
     const int lane = lane_id();
     const int wid = threadIdx.x >> 5;
     const uint64_t n = P.n;
-    const bool strip_cr = (OP == OP_HWE) || (P.mode == MODE_FILE && (OP == OP_AF || OP == OP_VC || OP == OP_MD || OP == OP_NR));
+    const bool strip_cr = (OP == OP_HWE) || (P.mode == MODE_FILE && (OP == OP_AF || OP == OP_VC || OP == OP_MD || OP == OP_NR)) || OP == OP_IX;
     if (OP == OP_AC && P.ac_pass && P.stats->overflow) return;
     if (VAR == 1 && P.stats->n_unfinished == 0) return;
 
@@ -1981,6 +2066,21 @@ __global__ void __launch_bounds__(256)
 format_rows_kernel(const KParams P) {
     if (P.stats->overflow) return;
     const unsigned long long nrec = P.stats->n_recs;
+    if (OP == OP_IX) {                                           // VCFX_indexer.cpp:291-303 / :397: CHROM \t POS \t FILE_OFFSET \n
+        for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nrec;
+             i += (unsigned long long)gridDim.x * blockDim.x) {
+            const Rec r = P.recs[i];
+            if (r.tile == REC_INVALID) continue;
+            uint8_t *o = P.out + P.tile_base[r.tile] + r.off_in_tile;
+            const uint64_t line_off = (uint64_t)r.tile * P.tile_bytes + r.ls_rel;
+            const uint8_t *src = P.in + line_off + r.a;
+            for (uint32_t k = 0; k < r.prefix_len; ++k) o[k] = __ldg(src + k);
+            o += r.prefix_len;
+            *o++ = '\t'; o = put_dec64(o, (long long)(((unsigned long long)r.d << 32) | r.c));
+            *o++ = '\t'; o = put_dec64(o, (long long)(P.file_offset + line_off)); *o = '\n';
+        }
+        return;
+    }
     if (OP == OP_AC) {                                           // allele_counter.cpp:1454-1461
         for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nrec;
              i += (unsigned long long)gridDim.x * blockDim.x) {

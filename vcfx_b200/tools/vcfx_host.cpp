@@ -375,7 +375,8 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
     Drain drain{ctxs, opt, tot, writer};
     const long n_slots = (long)cfg.n_slots * (long)G;     // pinned output buffers in rotation over all the contexts
     std::string carry = opt.preface;
-    bool eof = false, chrom_seen = false, in_hash_block = true;
+    bool eof = false, chrom_seen = false, in_hash_block = true, index_saw_hash = false;
+    uint64_t file_pos = 0;                         // offset of the next chunk in the whole input
     long submitted = 0;
     while (!eof) {
         char *buf = nullptr; size_t cap = 0;
@@ -422,6 +423,8 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
         if (nbytes == 0) break;
         vcfx_chunk_info info; memset(&info, 0, sizeof info);
         info.is_final = eof ? 1 : 0;
+        info.file_offset = file_pos;
+        file_pos += nbytes;
         if (opt.rule == HeaderRule::ChromHeader) {
             // data lines before the first line that starts with "#CHROM" are skipped with a warning
             // (allele_freq_calc.cpp:372-386): a prefix fact, found once, here
@@ -431,6 +434,42 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
                 if (nbytes >= 6 && memcmp(buf, "#CHROM", 6) == 0) off = 0;
                 else if (const void *m = memmem(buf, nbytes, "\n#CHROM", 7)) off = (size_t)(static_cast<const char *>(m) - buf) + 1;
                 if (off < nbytes) chrom_seen = true;
+                info.data_valid_from = off;
+            }
+        } else if (opt.rule == HeaderRule::IndexChrom) {
+            // VCFX_indexer: rows start behind the first "#CHROM" line — file mode: blanks / tabs, then "#CHROM" (:108-122);
+            // stdin mode: white space, then a first field that is exactly "#CHROM" with a second one behind it (:349-356).
+            // A data line in front of every '#' line makes the tool complain once (:313-316 / :362-366).
+            if (chrom_seen) info.data_valid_from = 0;
+            else {
+                size_t pos = 0, off = nbytes;
+                while (pos < nbytes) {
+                    const char *nl = static_cast<const char *>(memchr(buf + pos, '\n', nbytes - pos));
+                    const size_t le = nl ? (size_t)(nl - buf) : nbytes;
+                    size_t e2 = le;
+                    if (e2 > pos && buf[e2 - 1] == '\r') --e2;
+                    if (e2 > pos) {
+                        size_t p = pos;
+                        if (opt.mode == VCFX_MODE_FILE) while (p < e2 && (buf[p] == ' ' || buf[p] == '\t')) ++p;
+                        else while (p < e2 && (buf[p] == ' ' || (buf[p] >= 9 && buf[p] <= 13))) ++p;
+                        if (p < e2 && buf[p] == '#') {
+                            index_saw_hash = true;
+                            bool hit;
+                            if (opt.mode == VCFX_MODE_FILE) hit = e2 - pos >= 6 && e2 - p >= 6 && memcmp(buf + p, "#CHROM", 6) == 0;
+                            else hit = e2 - p >= 7 && memcmp(buf + p, "#CHROM\t", 7) == 0;
+                            if (hit) { off = pos; break; }
+                        } else if (!index_saw_hash) tot.index_warned = true;
+                    }
+                    pos = le + 1;
+                }
+                if (off < nbytes) {
+                    chrom_seen = true; tot.index_header_found = true;
+                    if (!opt.header_row.empty()) {
+                        if (opt.capture) opt.capture->append(opt.header_row);
+                        else if (opt.sink) opt.sink(opt.header_row.data(), opt.header_row.size());
+                        else write_all(opt.out_fd, opt.header_row.data(), opt.header_row.size());
+                    }
+                }
                 info.data_valid_from = off;
             }
         } else if (opt.rule == HeaderRule::LeadingHashBlock) {

@@ -50,9 +50,11 @@ struct Totals {
     uint64_t last_unterminated_flagged = 0;
     std::vector<uint64_t> short_line_numbers;   // 1-based, whole input
     double kernel_ms = 0;
+    bool index_header_found = false;            // IndexChrom: a "#CHROM" line was seen (the header row was written)
+    bool index_warned = false;                  // IndexChrom: a data line came before any '#' line
 };
 
-enum class HeaderRule { None, ChromHeader, LeadingHashBlock };
+enum class HeaderRule { None, ChromHeader, LeadingHashBlock, IndexChrom };
 
 struct RunOptions {
     int op = 0, mode = 0;
@@ -67,6 +69,8 @@ struct RunOptions {
     std::vector<std::string> sel_names;
     // when set, the text is appended here instead of being written to out_fd
     std::string *capture = nullptr;
+    // IndexChrom: written once, in stream order, when the "#CHROM" line is found (VCFX_indexer prints its header row then)
+    std::string header_row;
     // when set, every piece of text is handed to this function instead (in order; false = stop with an error)
     std::function<bool(const char *, size_t)> sink;
     // when set, only the text of the FINAL chunk is held back here (everything before is written)
