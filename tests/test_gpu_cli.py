@@ -89,11 +89,11 @@ def test_nonref_filter(files, tmp_path):
     homref = tmp_path / "h.vcf"
     rows = [b"21\t%d\t.\tA\tG\t.\tPASS\t.\tGT\t" % (i + 1) + b"\t".join([b"0|0"] * 299 + [b"0|1" if i % 3 == 0 else b"0|0"]) for i in range(400)]
     homref.write_bytes(b"##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + b"\t".join(b"S%d" % i for i in range(300)) + b"\n" + b"\n".join(rows) + b"\n")
-    for p in list(files.values()) + [q, homref]:
+    for p in (files["late"], files["crlf"], q, homref):          # (every invocation is a process with its own CUDA context)
         both("nonref_filter", ["-i", str(p)])
-        both("nonref_filter", [str(p)])
         both("nonref_filter", [], stdin=p.read_bytes())
-        both("nonref_filter", ["-"], stdin=p.read_bytes())
+    both("nonref_filter", [str(q)])
+    both("nonref_filter", ["-"], stdin=q.read_bytes())
     both("nonref_filter", ["-i", str(homref)], env=SMALL_CHUNK)
     both("nonref_filter", [], stdin=files["nonl"].read_bytes(), env={"VCFX_CHUNK_BYTES": "4096"})
     both("nonref_filter", ["-i", str(files["c3"])], env=SMALL_CHUNK)
@@ -103,7 +103,7 @@ def test_indexer(files, tmp_path):
     """VCFX_indexer: file argument and stdin, several chunks (offsets stay absolute), the quirks fixture."""
     import golden_util
     q = tmp_path / "q.vcf"; q.write_bytes(golden_util.load()["ix_quirks"][0])
-    for p in list(files.values()) + [q]:
+    for p in (files["late"], files["crlf"], q):
         a, b = both("indexer", [str(p)])
         assert a[2] == b[2]
         a, b = both("indexer", [], stdin=p.read_bytes())
