@@ -390,7 +390,7 @@ def config_entries(torch, np, api, synth, O, dev, peak, threads, only=None):
     sel = dict(sel_cols=list(range(SAMPLES)), sel_names=names)
     plans = [
         ("C2", 2, C2_VARIANTS, [("hwe_tester", api.OP_HWE, 0, {}, 20000), ("nonref_filter", api.OP_NONREF_FILTER, 0, {}, 20000),
-                                ("indexer", api.OP_INDEX, 0, {}, 60000)]),
+                                ("indexer", api.OP_INDEX, 0, {}, 60000), ("phase_checker", api.OP_PHASE_CHECK, 0, {}, 20000)]),
         ("C3", 3, C2_VARIANTS, [("missing_detector", api.OP_MISSING_DETECT, 0, {}, 20000),
                                 ("allele_counter", api.OP_ALLELE_COUNT, 0, sel, 4000),
                                 ("allele_counter -a", api.OP_ALLELE_COUNT, api.F_AC_AGGREGATE, sel, 400),
@@ -406,17 +406,18 @@ def config_entries(torch, np, api, synth, O, dev, peak, threads, only=None):
         log(f"[bench] {cname}: {sh.nbytes / 1e9:.2f} GB, {V} variants generated in {sh.gen_s:.1f}s")
         for tname, op, flags, kw, ref_variants in tools:
             out_cap = 64 << 20
-            if op in (api.OP_MISSING_DETECT, api.OP_NONREF_FILTER):
+            if op in (api.OP_MISSING_DETECT, api.OP_NONREF_FILTER, api.OP_PHASE_CHECK):
                 out_cap = sh.nbytes + sh.nbytes // 50 + (1 << 20)
             if op == api.OP_ALLELE_COUNT and flags == 0:
                 out_cap = int(sh.nbytes * 9.5) + (1 << 20)
             d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
             ctx = api.Context(op, api.FILE, flags=flags, **kw)
             ctx.set_line_hint(sh.line_len)
-            vf = api.find_chrom_header(sh.hdr) if op in (api.OP_ALLELE_FREQ, api.OP_NONREF_FILTER, api.OP_INDEX) else (api.first_data_offset(sh.hdr) if op == api.OP_MISSING_DETECT else 0)
+            vf = api.find_chrom_header(sh.hdr) if op in (api.OP_ALLELE_FREQ, api.OP_NONREF_FILTER, api.OP_INDEX, api.OP_PHASE_CHECK) else (api.first_data_offset(sh.hdr) if op == api.OP_MISSING_DETECT else 0)
+            fc = api.first_format_line(sh.prefix_bytes(np, 4), vf) if op == api.OP_PHASE_CHECK else 0     # (every line of these shapes has a FORMAT)
             ms = []
             for i in range(5):
-                ctx.run_device(sh.d_in.data_ptr(), sh.nbytes, d_out.data_ptr(), out_cap, valid_from=vf)
+                ctx.run_device(sh.d_in.data_ptr(), sh.nbytes, d_out.data_ptr(), out_cap, valid_from=vf, format_cache_from=fc)
                 st = ctx.sync()
                 if i >= 2:
                     ms.append(st.kernel_ms)
@@ -471,7 +472,7 @@ def parity_vs_reference(api, O, np, shard, tname, n_variants):
     """GPU tool output (through the C ABI, FILE semantics) against the stdout of the unmodified reference tool
     on the first n_variants lines of the shard."""
     tool = {"hwe_tester": "hwe_tester", "allele_freq_calc": "allele_freq_calc", "missing_detector": "missing_detector",
-            "allele_counter": "allele_counter", "allele_counter -a": "allele_counter", "variant_counter": "variant_counter", "nonref_filter": "nonref_filter", "indexer": "indexer"}[tname]
+            "allele_counter": "allele_counter", "allele_counter -a": "allele_counter", "variant_counter": "variant_counter", "nonref_filter": "nonref_filter", "indexer": "indexer", "phase_checker": "phase_checker"}[tname]
     exe = ref_tool(tool)
     data = shard.prefix_bytes(np, n_variants)
     if tname == "hwe_tester":
@@ -484,6 +485,8 @@ def parity_vs_reference(api, O, np, shard, tname, n_variants):
         got = api.nonref_filter(data, api.FILE).out; args = ["-i"]
     elif tname == "indexer":
         got = api.indexer(data, api.FILE).out; args = []
+    elif tname == "phase_checker":
+        got = api.phase_checker(data, api.FILE, quiet=True).out; args = ["-q", "-i"]
     elif tname == "allele_counter":
         got = api.allele_counter(data, api.AC_MT_TEXT, api.AC_TEXT).out; args = ["-q", "-i"]
     elif tname == "allele_counter -a":
@@ -494,7 +497,7 @@ def parity_vs_reference(api, O, np, shard, tname, n_variants):
     if exe is None:
         # no reference binary on this box: the CPU restatement (pinned to the reference by tests/) stands in
         fn = {"hwe_tester": lambda: O.hwe(data, 0), "allele_freq_calc": lambda: O.allele_freq(data, 0), "missing_detector": lambda: O.missing(data, 0),
-              "nonref_filter": lambda: O.nonref_filter(data, 0), "indexer": lambda: O.indexer(data, 0), "allele_counter": lambda: O.allele_counter(data), "allele_counter -a": lambda: O.allele_counter(data, O.AC_UNIFIED, O.AC_AGGREGATE),
+              "nonref_filter": lambda: O.nonref_filter(data, 0), "indexer": lambda: O.indexer(data, 0), "phase_checker": lambda: O.phase_checker(data, 0), "allele_counter": lambda: O.allele_counter(data), "allele_counter -a": lambda: O.allele_counter(data, O.AC_UNIFIED, O.AC_AGGREGATE),
               "variant_counter": lambda: O.variant_count(data, 0)}[tname]
         exp = fn().out
         res.update({"against": "oracle port (reference binary not built on this box)", "equal": exp == got})

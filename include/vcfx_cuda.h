@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define VCFX_CUDA_ABI_VERSION 2
+#define VCFX_CUDA_ABI_VERSION 3
 
 typedef struct vcfx_ctx vcfx_ctx;
 
@@ -50,6 +50,9 @@ typedef enum {
     VCFX_OP_HWE            = 2,
     VCFX_OP_MISSING_DETECT = 3,
     VCFX_OP_ALLELE_COUNT   = 4,
+    VCFX_OP_PHASE_CHECK    = 7,   /* VCFX_phase_checker.cpp:470-558 filterPhaseCheckedMmap, :563-650 processVCF; vcfx_cuda_short_lines
+                                     then returns, per dropped line, (offset of the line in the chunk << 2 | reason): 0 unphased, 1 before
+                                     the header, 2 fewer than ten columns, 3 no GT key */
     VCFX_OP_INDEX          = 6,   /* VCFX_indexer.cpp:205-322 createVCFIndexMmap, :329-443 createVCFIndex */
     VCFX_OP_NONREF_FILTER  = 5    /* VCFX_nonref_filter.cpp:458-548 filterNonRefMmap, :553-631 filterNonRef */
 } vcfx_op;
@@ -104,6 +107,10 @@ typedef struct {
     int32_t  is_final;         /* last chunk: the final line may lack its '\n'                   */
     int32_t  reserved;
     uint64_t file_offset;      /* ABI 2: offset of the chunk's first byte in the whole input (VCFX_OP_INDEX prints absolute offsets) */
+    uint64_t format_cache_from;/* ABI 3, VCFX_OP_PHASE_CHECK in file mode: data lines starting below this chunk offset are checked
+                                  while the reference's FORMAT cache is still ("", GT index 0) — no line with a non-empty FORMAT
+                                  column was looked at before them — so an empty FORMAT column means "GT is the first key" there
+                                  (VCFX_phase_checker.cpp:486-488, :313-316); 0 = a non-empty FORMAT was already seen */
 } vcfx_chunk_info;
 
 typedef struct {

@@ -46,7 +46,7 @@ def lib():
             subprocess.run(["make", "-C", str(HERE), "all"], check=True, capture_output=True)
         l = C.CDLL(str(LIB_PATH))
         P = C.POINTER(_Result)
-        for name in ("oracle_allele_freq", "oracle_hwe", "oracle_missing", "oracle_nonref_filter", "oracle_indexer"):
+        for name in ("oracle_allele_freq", "oracle_hwe", "oracle_missing", "oracle_nonref_filter", "oracle_indexer", "oracle_phase_checker"):
             getattr(l, name).argtypes = [C.c_char_p, C.c_size_t, C.c_int, P]
         l.oracle_variant_count.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, P]
         l.oracle_allele_counter.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_char_p, P]
@@ -84,6 +84,21 @@ def hwe(data: bytes, mode: int = FILE) -> Result:
 
 def missing(data: bytes, mode: int = FILE) -> Result:
     return _call(lib().oracle_missing, data, len(data), mode)
+
+
+def phase_checker(data: bytes, mode: int = FILE) -> Result:
+    return _call(lib().oracle_phase_checker, data, len(data), mode)
+
+
+def phase_checker_stderr(data: bytes, mode: int = FILE) -> bytes:
+    """What VCFX_phase_checker prints on stderr without -q."""
+    l = lib()
+    l.oracle_phase_checker_err.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(_Result), C.POINTER(_Result)]
+    r, e = _Result(), _Result()
+    l.oracle_phase_checker_err(data, len(data), mode, C.byref(r), C.byref(e))
+    out = C.string_at(e.out, e.out_len) if e.out_len else b""
+    l.oracle_free(C.byref(r)); l.oracle_free(C.byref(e))
+    return out
 
 
 def indexer(data: bytes, mode: int = FILE) -> Result:

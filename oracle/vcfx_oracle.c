@@ -752,6 +752,131 @@ int oracle_indexer(const char *in, size_t n, int mode, oracle_result *r) {
     return mode == ORACLE_FILE ? ix_file(in, n, r) : ix_stdin(in, n, r);
 }
 
+/* ------------------------------------------------------------------ phase_checker (§8 f2): only lines whose samples are ALL
+ * fully phased pass; every other data line is dropped with a message on stderr (unless -q).  The restatement returns stdout in
+ * `out`; the stderr text it would print without -q is appended to *err_text when that is given (oracle_phase_checker_err). */
+
+/* VCFX_phase_checker.cpp:218-268 isFullyPhasedFast */
+static int pc_phased(const char *g, const char *ge) {
+    size_t len = (size_t)(ge - g);
+    if (len == 0) return 0;
+    if (len == 3) return g[1] == '|' && g[0] != '.' && g[2] != '.';
+    if (len == 1) return 0;
+    if (g[0] == '.' && len >= 3 && (g[1] == '/' || g[1] == '|') && g[2] == '.') return 0;
+    int pipe = 0; const char *as = g;
+    for (const char *p = g; p < ge; ++p) {
+        if (*p == '|') {
+            size_t al = (size_t)(p - as);
+            if (al == 0 || (al == 1 && *as == '.')) return 0;
+            pipe = 1; as = p + 1;
+        } else if (*p == '/') return 0;
+    }
+    size_t al = (size_t)(ge - as);
+    if (al == 0 || (al == 1 && *as == '.')) return 0;
+    return pipe;
+}
+
+static void pc_msg_unphased(obuf *err, const char *s, const char *e) {     /* :541-555 / :645-648 */
+    const char *t1 = memchr(s, '\t', (size_t)(e - s));
+    if (!t1) return;
+    const char *t2 = memchr(t1 + 1, '\t', (size_t)(e - t1 - 1));
+    if (!t2) return;
+    ob_str(err, "Unphased genotype found at CHROM="); ob_put(err, s, (size_t)(t1 - s));
+    ob_str(err, ", POS="); ob_put(err, t1 + 1, (size_t)(t2 - t1 - 1)); ob_str(err, "; line skipped.\n");
+}
+
+static int pc_run(const char *in, size_t n, int file_mode, oracle_result *r, obuf *err) {
+    obuf o = {0}; size_t pos = 0; line_t ln; int header = 0;
+    /* file mode keeps the last FORMAT string and its GT index, and starts with ("", 0): an empty FORMAT column means "GT first"
+     * until the first non-empty one has been looked at (:486-488, :313-316); stdin mode starts with ("", -1) (:572-574) */
+    const char *cf = ""; size_t cfl = 0; int cgi = 0;
+    while (next_line(in, n, &pos, &ln)) {
+        const char *s = ln.s, *e = ln.e;
+        if (file_mode && e > s && e[-1] == '\r') --e;                      /* :499-501 (stdin: getline keeps it) */
+        if (s == e) { ob_ch(&o, '\n'); continue; }
+        if (*s == '#') {
+            ob_put(&o, s, (size_t)(e - s)); ob_ch(&o, '\n');
+            if (e - s >= 6 && memcmp(s + 1, "CHROM", 5) == 0) header = 1;
+            continue;
+        }
+        r->data_lines++;
+        if (!header) { r->warnings++; if (err) ob_str(err, "Warning: Data line encountered before #CHROM header; skipping line.\n"); continue; }
+        int tabs = 0; for (const char *p = s; p < e; ++p) tabs += (*p == '\t');
+        const char *f = nr_skip(s, e, 8);
+        int res;                                                           /* 1 all phased, 0 not, -1 invalid, -2 no GT (stdin) */
+        if (file_mode) {                                                   /* :296-359 checkAllSamplesPhasedDirect */
+            if (!f || f >= e) res = -1;
+            else {
+                const char *fe = f; while (fe < e && *fe != '\t') ++fe;
+                if ((size_t)(fe - f) != cfl || memcmp(f, cf, cfl) != 0) { cgi = oracle_gt_index(f, (size_t)(fe - f)); cf = f; cfl = (size_t)(fe - f); }
+                int gi = cgi;
+                if (gi < 0) res = 0;
+                else if (fe >= e) res = -1;
+                else {
+                    res = 1;
+                    const char *p = fe + 1;
+                    while (p < e) {
+                        const char *se = p; while (se < e && *se != '\t') ++se;
+                        if (se == p) { res = 0; break; }
+                        const char *gs, *ge;
+                        if (gi == 0) { gs = p; ge = memchr(p, ':', (size_t)(se - p)); if (!ge) ge = se; }
+                        else nr_nth_piece(p, se, gi, &gs, &ge);
+                        if (!pc_phased(gs, ge)) { res = 0; break; }
+                        p = se; if (p < e) ++p;
+                    }
+                }
+            }
+        } else {                                                           /* :563-650 processVCF */
+            if (tabs + 1 < 10) res = -1;
+            else {
+                const char *fe = f; while (fe < e && *fe != '\t') ++fe;
+                int gi = oracle_gt_index(f, (size_t)(fe - f));
+                if (gi < 0) res = -2;
+                else {
+                    res = 1;
+                    const char *p = fe + 1;
+                    for (;;) {
+                        const char *se = p; while (se < e && *se != '\t') ++se;
+                        const char *gs, *ge;
+                        if (gi == 0) { gs = p; ge = memchr(p, ':', (size_t)(se - p)); if (!ge) ge = se; }
+                        else nr_nth_piece(p, se, gi, &gs, &ge);
+                        if (!pc_phased(gs, ge)) { res = 0; break; }
+                        if (se >= e) break;
+                        p = se + 1;
+                    }
+                }
+            }
+        }
+        if (res == 1) { ob_put(&o, s, (size_t)(e - s)); ob_ch(&o, '\n'); r->rows++; }
+        else {
+            r->flagged++;
+            if (err) {
+                if (res == -1) ob_str(err, "Warning: Invalid VCF line with fewer than 10 columns; skipping line.\n");
+                else if (res == -2) ob_str(err, "Warning: GT field not found; skipping line.\n");
+                else if (file_mode) pc_msg_unphased(err, s, e);
+                else {                                                     /* fields[0], fields[1]: they exist (>= 10 fields) */
+                    pc_msg_unphased(err, s, e);
+                }
+            }
+        }
+    }
+    res_take(r, &o);
+    return 0;
+}
+
+int oracle_phase_checker(const char *in, size_t n, int mode, oracle_result *r) {
+    res_init(r);
+    return pc_run(in, n, mode == ORACLE_FILE, r, NULL);
+}
+/* the same, and the stderr text of a run without -q in a second result */
+int oracle_phase_checker_err(const char *in, size_t n, int mode, oracle_result *r, oracle_result *err) {
+    res_init(r); res_init(err);
+    obuf eb = {0};
+    int rc = pc_run(in, n, mode == ORACLE_FILE, r, &eb);
+    res_take(err, &eb);
+    return rc;
+}
+
 /* ------------------------------------------------------------------ variant_counter */
 
 /* variant_counter.cpp:31-44 — at least 7 tabs. */

@@ -48,6 +48,8 @@ void oracle_free(oracle_result *r);
 int oracle_allele_freq(const char *in, size_t n, int mode, oracle_result *r);
 int oracle_hwe(const char *in, size_t n, int mode, oracle_result *r);
 int oracle_missing(const char *in, size_t n, int mode, oracle_result *r);
+int oracle_phase_checker(const char *in, size_t n, int mode, oracle_result *r);    /* VCFX_phase_checker (§8 f2) */
+int oracle_phase_checker_err(const char *in, size_t n, int mode, oracle_result *r, oracle_result *err);   /* + stderr text without -q */
 int oracle_indexer(const char *in, size_t n, int mode, oracle_result *r);          /* VCFX_indexer (§8 f4) */
 int oracle_nonref_filter(const char *in, size_t n, int mode, oracle_result *r);   /* VCFX_nonref_filter (§8 f2) */
 int oracle_variant_count(const char *in, size_t n, int mode, int strict, oracle_result *r);

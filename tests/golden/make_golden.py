@@ -64,6 +64,21 @@ def hand_cases():
         L("GT", "0/0") + "\t", L("GT"), "1\t1\t.\tA\tG\t.\t.\t.\tGT", L("GT:DP", "0/0:1", "0/0:"), L("DP:GT", "1:0/0", "1"),
         L("DP:GT", "1:0/0", "1:"), L("DP:GT", "1:0/0", ":0|0"), L("DP", "1", "2"), L("GT:", "0/0", "0/0"), L("", "0/0", "0/0"), "",
         L("GT", "0/0", "0/0\r"), L("GT", "0/0", "0/0") + "\r", "\r", L("GT", "0/0/0", "0|0|0|0"), L("GT", "./.", "0/0"), L("GT", "0/0", "0/0")]))
+    # phase_checker: what "fully phased" means (three bytes x|y with x, y not '.'; otherwise every '|'-separated allele non-empty
+    # and not "."), empty columns (dropped in the middle, ignored at the end of a file-mode line), GT not first, no GT key,
+    # short lines, CRLF (content in stdin mode), a data line in front of the header, an unterminated last line
+    c["pc_quirks"] = ("1\t1\t.\tA\tG\t.\t.\t.\tGT\t0|1\n" + H + "S1\tS2\n" + "\n".join([
+        L("GT", "0|1", "1|0"), L("GT", "0|1", "0/1"), L("GT", "0|1", ".|."), L("GT", "0|1", "."), L("GT", "0|1", "0"), L("GT", "0|", "|1"),
+        L("GT", "0|1|1", "10|2"), L("GT", "0|.|1", "0|1"), L("GT", "0||1", "0|1"), L("GT", "/|/", "||1"), L("GT", "..|1", ".1|0"), L("GT", "0|1", ""),
+        L("GT", "0|1") + "\t", L("GT"), "1\t1\t.\tA\tG\t.\t.\t.\tGT", "1\t1\t.\tA\tG\t.\t.\t.\tDP", "1\t1\t.\tA\tG\t.\t.\t.\t", "1\t5\tx",
+        L("GT:DP", "0|1:1", "1|1:"), L("DP:GT", "1:0|1", "1"), L("DP:GT", "1:0|1", "1:"), L("DP:GT", "1:0|1", ":1|0:7"), L("DP", "1", "2"),
+        L("GT:", "0|1", "0|1"), L("", "0|1", "0|1"), "", L("GT", "0|1", "0|1\r"), L("GT", "0|1", "0|1") + "\r", "\r", "x\ty",
+        L("GT", "1|2|3|4", "12|345"), L("GT", "./.", "0|1"), L("GT", "0|1", "0|1")]))
+    # phase_checker, file mode: the FORMAT cache starts as ("", GT index 0) — an empty FORMAT column means "GT first" until the
+    # first non-empty FORMAT was looked at (a line that ends behind its eighth tab does not get that far)
+    c["pc_format_cache"] = (H + "S1\tS2\n" + "\n".join([
+        L("", "0|1", "1|0"), L("", "0/1", "1|0"), "1\t1\t.\tA\tG\t.\t.\t.\t", "1\t2\tx", L("", "1|1:9", "2|1"), "", L("", "0|1") + "\t",
+        L("DP", "1", "2"), L("", "0|1", "1|0"), L("GT", "0|1", "1|0"), L("", "0|1", "1|0")]) + "\n")
     # indexer: what counts as CHROM and POS in the two modes (blanks in front, signs, wrap-around, CRLF, "#CHROM" look-alikes)
     c["ix_quirks"] = ("##x\n #CHROMX\tY\n#CHROM\tPOS\tID\n1\t100\t.\n 2\t+7x\t.\n\t3\t5\n4\t0\n5\t-3\n6\t 12\n7\n8\t99999999999999999999\n"
                       "9\t12\r\n\n#late\t1\nchrX\t007\tid\n10\t9223372036854775807\n11\t9223372036854775808\n12\t-9223372036854775808\n13\t5")
@@ -89,6 +104,12 @@ def run_all(data: bytes, ac_ok: bool, md_file_ok: bool = True):
         out["nonref_filter.file"] = [rc, base64.b64encode(so).decode(), se.count(b"Warning")]
         rc, so, se = O.run_ref("nonref_filter", [], stdin=data)
         out["nonref_filter.stdin"] = [rc, base64.b64encode(so).decode(), se.count(b"Warning")]
+        # phase_checker: stdout and the whole stderr text ("-" = stdin without the reference's own "is there anything on
+        # stdin yet" probe, which shows the help text when the pipe is not filled in time)
+        rc, so, se = O.run_ref("phase_checker", ["-i", f.name])
+        out["phase_checker.file"] = [rc, base64.b64encode(so).decode(), base64.b64encode(se).decode()]
+        rc, so, se = O.run_ref("phase_checker", ["-"], stdin=data)
+        out["phase_checker.stdin"] = [rc, base64.b64encode(so).decode(), base64.b64encode(se).decode()]
         for strict in (False, True):
             a = ["--strict"] if strict else []
             rc, so, se = O.run_ref("variant_counter", [*a, f.name])

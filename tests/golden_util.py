@@ -13,6 +13,9 @@ def load():
     for name, f in fx.items():
         exp = {}
         for k, v in f["expect"].items():
+            if k.startswith("phase_checker"):          # [rc, stdout, stderr text]
+                exp[k] = (v[0], base64.b64decode(v[1]), base64.b64decode(v[2]))
+                continue
             exp[k] = (v[0], base64.b64decode(v[1])) + tuple(v[2:])
         out[name] = (base64.b64decode(f["input"]), exp)
     return out

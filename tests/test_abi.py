@@ -27,7 +27,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version_and_strerror(lib):
-    assert lib.vcfx_cuda_abi_version() == 2
+    assert lib.vcfx_cuda_abi_version() == 3
     lib.vcfx_cuda_strerror.restype = C.c_char_p
     assert b"no CPU fallback" in lib.vcfx_cuda_strerror(-2)
 
@@ -35,7 +35,7 @@ def test_abi_version_and_strerror(lib):
 def test_struct_layouts_match_the_header():
     """ctypes mirrors vs the C structs (sizes are what the C side was compiled with)."""
     from vcfx_b200 import api
-    assert C.sizeof(api.ChunkInfo) == 24          # ABI 2: + file_offset
+    assert C.sizeof(api.ChunkInfo) == 32          # ABI 2: + file_offset, ABI 3: + format_cache_from
     assert C.sizeof(api.ChunkStats) == 12 * 8 + 8
     assert C.sizeof(api.Cfg) == 4 * 4 + 8 + 8 + 4 + 4 + 8 + 4 + 4 + 8 + 8 + 8
 

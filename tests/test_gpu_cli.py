@@ -99,6 +99,34 @@ def test_nonref_filter(files, tmp_path):
     both("nonref_filter", ["-i", str(files["c3"])], env=SMALL_CHUNK)
 
 
+def test_phase_checker(files, tmp_path):
+    """VCFX_phase_checker: stdout and the messages on stderr, file (-i and positional) and stdin ("-": the
+    reference shows its help text when started without arguments before anything can be read from the pipe), -q,
+    several chunks (messages stay in line order; file mode's FORMAT cache spans the chunk borders)."""
+    import golden_util
+    q = tmp_path / "q.vcf"; q.write_bytes(golden_util.load()["pc_quirks"][0])
+    fc = tmp_path / "fc.vcf"; fc.write_bytes(golden_util.load()["pc_format_cache"][0])
+    phased = tmp_path / "p.vcf"
+    rows = [b"21\t%d\t.\tA\tG\t.\tPASS\t.\tGT\t" % (i + 1) + b"\t".join([b"0|1"] * 299 + [b"0/1" if i % 3 == 0 else b"1|0"]) for i in range(400)]
+    phased.write_bytes(b"##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + b"\t".join(b"S%d" % i for i in range(300)) + b"\n" + b"\n".join(rows) + b"\n")
+    for p in (files["late"], files["crlf"], q, fc, phased):
+        a, b = both("phase_checker", ["-i", str(p)])
+        assert a[2] == b[2]
+        a, b = both("phase_checker", ["-"], stdin=p.read_bytes())
+        assert a[2] == b[2]
+    a, b = both("phase_checker", [str(q)])
+    assert a[2] == b[2]
+    a, b = both("phase_checker", ["-q", "-i", str(q)])
+    assert a[2] == b[2] == b""
+    a, b = both("phase_checker", ["--quiet"], stdin=q.read_bytes())
+    assert a[2] == b[2] == b""
+    for f, env in ((phased, SMALL_CHUNK), (fc, {"VCFX_CHUNK_BYTES": "128"}), (files["c3"], SMALL_CHUNK)):
+        a, b = both("phase_checker", ["-i", str(f)], env=env)
+        assert a[2] == b[2]
+    a, b = both("phase_checker", ["-"], stdin=files["nonl"].read_bytes(), env={"VCFX_CHUNK_BYTES": "4096"})
+    assert a[2] == b[2]
+
+
 def test_indexer(files, tmp_path):
     """VCFX_indexer: file argument and stdin, several chunks (offsets stay absolute), the quirks fixture."""
     import golden_util
@@ -113,13 +141,15 @@ def test_indexer(files, tmp_path):
     both("indexer", [], stdin=files["nonl"].read_bytes(), env={"VCFX_CHUNK_BYTES": "4096"})
 
 
-@pytest.mark.parametrize("tool", ["allele_freq_calc", "hwe_tester", "missing_detector", "variant_counter", "allele_counter", "nonref_filter", "indexer"])
+@pytest.mark.parametrize("tool", ["allele_freq_calc", "hwe_tester", "missing_detector", "variant_counter", "allele_counter", "nonref_filter", "indexer", "phase_checker"])
 def test_flags(tool, files):
     for args in (["--help"], ["-v"]):
         both(tool, args)
-    a, b = both(tool, ["/nonexistent/file.vcf"] if tool == "variant_counter" else (["-i", "/nonexistent/file.vcf"] if tool == "nonref_filter" else ["/nonexistent/file.vcf"] if tool == "indexer" else ["-q", "-i", "/nonexistent/file.vcf"]))
+    a, b = both(tool, ["/nonexistent/file.vcf"] if tool == "variant_counter" else (["-i", "/nonexistent/file.vcf"] if tool in ("nonref_filter", "phase_checker") else ["/nonexistent/file.vcf"] if tool == "indexer" else ["-q", "-i", "/nonexistent/file.vcf"]))
     assert a[2] == b[2]
-    both(tool, [], stdin=b"")          # empty stdin: per-tool behaviour (help+rc1 / header only / nothing / Total 0)
+    # empty stdin: per-tool behaviour (help+rc1 / header only / nothing / Total 0); phase_checker without arguments prints its
+    # help text unless stdin is readable at that very moment (a race with the parent closing the pipe): give it an argument
+    both(tool, ["-q"] if tool == "phase_checker" else [], stdin=b"")
 
 
 def test_allele_counter(tmp_path):
@@ -192,7 +222,7 @@ def test_multi_gpu_same_bytes(tmp_path):
     env_multi = {"VCFX_CUDA_DEVICES": "all", "VCFX_CHUNK_BYTES": str(128 << 10)}
     env_one = {"VCFX_CHUNK_BYTES": str(128 << 10)}
     cases = [("allele_freq_calc", ["-q", "-i"]), ("hwe_tester", ["-q", "-i"]), ("missing_detector", ["-q", "-t", "1", "-i"]),
-             ("variant_counter", []), ("allele_counter", ["-q", "-i"]), ("allele_counter", ["-q", "-a", "-i"]), ("nonref_filter", ["-i"]), ("indexer", [])]
+             ("variant_counter", []), ("allele_counter", ["-q", "-i"]), ("allele_counter", ["-q", "-a", "-i"]), ("nonref_filter", ["-i"]), ("indexer", []), ("phase_checker", ["-i"])]
     for f in (src, late):
         for tool, args in cases:
             one = run(BIN / f"VCFX_{tool}", [*args, str(f)], env=env_one)

@@ -20,7 +20,7 @@ def _cmp(name, got, exp):
                              f"  got {got[max(0, i - 60): i + 60]!r}\n  exp {exp[max(0, i - 60): i + 60]!r}")
 
 
-def run_all(api, O, data, tag, chunk_bytes=0, tile_bytes=0, tools=("af", "hwe", "vc", "md", "nr", "ix")):
+def run_all(api, O, data, tag, chunk_bytes=0, tile_bytes=0, tools=("af", "hwe", "vc", "md", "nr", "ix", "pc")):
     kw = dict(chunk_bytes=chunk_bytes, tile_bytes=tile_bytes)
     for mode in MODES:
         if "af" in tools:
@@ -46,6 +46,11 @@ def run_all(api, O, data, tag, chunk_bytes=0, tile_bytes=0, tools=("af", "hwe", 
             r = api.nonref_filter(data, mode, **kw); o = O.nonref_filter(data, mode)
             _cmp(f"{tag} nr mode{mode}", r.out, o.out)
             assert (r.totals.rows, r.totals.pre_header) == (o.rows, o.warnings)
+        if "pc" in tools:
+            r = api.phase_checker(data, mode, **kw); o = O.phase_checker(data, mode)
+            _cmp(f"{tag} pc mode{mode}", r.out, o.out)
+            _cmp(f"{tag} pc mode{mode} stderr", r.err, O.phase_checker_stderr(data, mode))
+            assert (r.totals.rows, r.totals.pre_header, r.totals.flagged) == (o.rows, o.warnings, o.flagged + o.warnings)
         if "vc" in tools:
             for strict in (False, True):
                 r = api.variant_counter(data, mode, strict, **kw); o = O.variant_count(data, mode, strict)
@@ -360,6 +365,48 @@ def test_nonref_filter_cases(cuda_api, oracle):
         data = hdr + names + b"\n" + b"\n".join(lines) + (b"\n" if S % 2 else b"")
         run_all(cuda_api, oracle, data, f"nr S{S}", tools=("nr",))
         run_all(cuda_api, oracle, data, f"nr S{S} tile512", tile_bytes=512, tools=("nr",))
+
+
+def test_phase_checker_cases(cuda_api, oracle):
+    """VCFX_phase_checker: what "fully phased" means, empty columns, GT not the first key / no GT key, short lines, CRLF, lines in
+    front of the header, file mode's FORMAT cache that starts as ("", GT first); every dropped line with the message the tool
+    prints for it; all-phased lines of every length against the 512-byte windows; -q prints nothing."""
+    import golden_util
+    for name in ("pc_quirks", "pc_format_cache", "nr_quirks"):
+        data, _ = golden_util.load()[name]
+        for kw in ({}, {"tile_bytes": 512}, {"chunk_bytes": 4096}):
+            run_all(cuda_api, oracle, data, f"{name} {kw}", tools=("pc",), **kw)
+    # the FORMAT cache across chunk borders: no non-empty FORMAT for the first chunks
+    hdr = b"##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t"
+    lines = [b"1\t%d\t.\tA\tG\t.\tPASS\t.\t\t%s\t1|0" % (k + 1, [b"0|1", b"0/1", b"1|1:7"][k % 3]) for k in range(200)]
+    lines += [b"1\t900\t.\tA\tG\t.\tPASS\t.\tGT\t0|1\t1|0"] + lines[:50]
+    data = hdr + b"S1\tS2\n" + b"\n".join(lines) + b"\n"
+    for kw in ({}, {"chunk_bytes": 1024}, {"tile_bytes": 512}):
+        run_all(cuda_api, oracle, data, f"pc format cache {kw}", tools=("pc",), **kw)
+    assert cuda_api.phase_checker(data, 0, quiet=True).err == b""
+    for S in (1, 2, 100, 126, 127, 128, 129, 255, 256, 257, 700):
+        names = b"\t".join(b"S%d" % i for i in range(S))
+        lines = []
+        for k in range(60):
+            gts = [b"0|1" if (i + k) % 3 else b"1|0" for i in range(S)]
+            if k % 4 == 1:
+                gts[(k * 37) % S] = [b"0/1", b".", b"0", b".|.", b"0|1|1", b"0|.", b"10|11"][k % 7]
+            lines.append(b"%d\t%d\t.\tA\tG\t.\tPASS\t.\tGT\t" % (k % 22 + 1, k + 1) + b"\t".join(gts))
+        data = hdr + names + b"\n" + b"\n".join(lines) + (b"\n" if S % 2 else b"")
+        run_all(cuda_api, oracle, data, f"pc S{S}", tools=("pc",))
+        run_all(cuda_api, oracle, data, f"pc S{S} tile512", tile_bytes=512, tools=("pc",))
+
+
+def test_phase_checker_more_dropped_lines_than_the_event_list(cuda_api, oracle):
+    """Every dropped line is reported; the list starts with room for 2^20 of them and the chunk is run again with a longer
+    one when that is not enough."""
+    hdr = b"##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tA\n"
+    n = (1 << 20) + 5000
+    data = hdr + b"1\t2\n" * n + b"1\t7\t.\tA\tG\t.\t.\t.\tGT\t0|1\n"
+    r = cuda_api.phase_checker(data, 0)
+    o = oracle.phase_checker(data, 0)
+    assert r.out == o.out and r.totals.flagged == n
+    assert r.err == b"Warning: Invalid VCF line with fewer than 10 columns; skipping line.\n" * n
 
 
 def test_allele_counter_two_digit_counts(cuda_api, oracle):

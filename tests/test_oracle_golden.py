@@ -28,6 +28,10 @@ def check_case(O, data, exp, name):
         if key in exp:
             r = O.nonref_filter(data, mode)
             assert (r.rc, r.out, r.warnings) == tuple(exp[key][:3]), (name, key)
+        key = f"phase_checker.{mode_name}"
+        if key in exp:
+            r = O.phase_checker(data, mode)
+            assert (r.rc, r.out, O.phase_checker_stderr(data, mode)) == tuple(exp[key][:3]), (name, key)
         for strict in (0, 1):
             key = f"variant_counter.{mode_name}.strict{strict}"
             r = O.variant_count(data, mode, bool(strict))
@@ -82,6 +86,12 @@ def test_oracle_matches_reference_binaries_fuzz(oracle, seed):
         assert (r.rc, r.out, r.warnings) == (rc, out, err.count(b"Warning")), "nonref_filter file"
         rc, out, err = O.run_ref("nonref_filter", [], stdin=data); r = O.nonref_filter(data, O.STDIN)
         assert (r.rc, r.out, r.warnings) == (rc, out, err.count(b"Warning")), "nonref_filter stdin"
+        rc, out, err = O.run_ref("phase_checker", ["-i", f.name]); r = O.phase_checker(data, O.FILE)
+        assert (r.rc, r.out, O.phase_checker_stderr(data, O.FILE)) == (rc, out, err), "phase_checker file"
+        rc, out, err = O.run_ref("phase_checker", ["-"], stdin=data); r = O.phase_checker(data, O.STDIN)
+        assert (r.rc, r.out, O.phase_checker_stderr(data, O.STDIN)) == (rc, out, err), "phase_checker stdin"
+        rc, out, err = O.run_ref("phase_checker", ["-q"], stdin=data)
+        assert (rc, out, err) == (r.rc, r.out, b""), "phase_checker -q"
         for strict in (False, True):
             a = ["--strict"] if strict else []
             rc, out, err = O.run_ref("variant_counter", [*a, f.name]); r = O.variant_count(data, O.FILE, strict)
@@ -114,6 +124,8 @@ def test_oracle_matches_reference_binaries_shapes(oracle):
             assert O.variant_count(data).out == out
             rc, out, _ = O.run_ref("nonref_filter", ["-i", f.name], timeout=60)
             assert O.nonref_filter(data, O.FILE).out == out, (shape, "nonref_filter")
+            rc, out, err = O.run_ref("phase_checker", ["-i", f.name], timeout=60)
+            assert (O.phase_checker(data, O.FILE).out, O.phase_checker_stderr(data, O.FILE)) == (out, err), (shape, "phase_checker")
 
 
 def test_hwe_numbers_and_formatters(oracle):

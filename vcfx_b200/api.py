@@ -17,7 +17,7 @@ from pathlib import Path
 
 from . import build as _build
 
-OP_VARIANT_COUNT, OP_ALLELE_FREQ, OP_HWE, OP_MISSING_DETECT, OP_ALLELE_COUNT, OP_NONREF_FILTER, OP_INDEX = range(7)
+OP_VARIANT_COUNT, OP_ALLELE_FREQ, OP_HWE, OP_MISSING_DETECT, OP_ALLELE_COUNT, OP_NONREF_FILTER, OP_INDEX, OP_PHASE_CHECK = range(8)
 FILE, STDIN = 0, 1
 F_AC_AGGREGATE, F_AC_BINARY, F_AC_FORWARD = 1, 2, 4
 DEVICE_PAD = 8192
@@ -45,7 +45,8 @@ class Cfg(C.Structure):
 
 
 class ChunkInfo(C.Structure):
-    _fields_ = [("data_valid_from", C.c_uint64), ("is_final", C.c_int32), ("reserved", C.c_int32), ("file_offset", C.c_uint64)]
+    _fields_ = [("data_valid_from", C.c_uint64), ("is_final", C.c_int32), ("reserved", C.c_int32), ("file_offset", C.c_uint64),
+                ("format_cache_from", C.c_uint64)]
 
 
 class ChunkStats(C.Structure):
@@ -199,22 +200,22 @@ class Context:
         self._check(rc)
         return buf.value, cap.value
 
-    def submit(self, nbytes: int, valid_from: int = 0, is_final: bool = True, file_offset: int = 0):
-        info = ChunkInfo(valid_from, int(is_final), 0, file_offset)
+    def submit(self, nbytes: int, valid_from: int = 0, is_final: bool = True, file_offset: int = 0, format_cache_from: int = 0):
+        info = ChunkInfo(valid_from, int(is_final), 0, file_offset, format_cache_from)
         self._check(self._l.vcfx_cuda_submit(self._h, nbytes, C.byref(info)))
 
-    def submit_host(self, host_ptr: int, nbytes: int, valid_from: int = 0, is_final: bool = True, file_offset: int = 0) -> bool:
+    def submit_host(self, host_ptr: int, nbytes: int, valid_from: int = 0, is_final: bool = True, file_offset: int = 0, format_cache_from: int = 0) -> bool:
         """Submit a chunk straight from caller memory; False when every slot is in flight."""
-        info = ChunkInfo(valid_from, int(is_final), 0, file_offset)
+        info = ChunkInfo(valid_from, int(is_final), 0, file_offset, format_cache_from)
         rc = self._l.vcfx_cuda_submit_host(self._h, host_ptr, nbytes, C.byref(info))
         if rc == E_BUSY:
             return False
         self._check(rc)
         return True
 
-    def submit_shared(self, primary: "Context", valid_from: int = 0, is_final: bool = True, file_offset: int = 0) -> bool:
+    def submit_shared(self, primary: "Context", valid_from: int = 0, is_final: bool = True, file_offset: int = 0, format_cache_from: int = 0) -> bool:
         """Run this context's op on the chunk last submitted to ``primary`` (no second upload)."""
-        info = ChunkInfo(valid_from, int(is_final), 0, file_offset)
+        info = ChunkInfo(valid_from, int(is_final), 0, file_offset, format_cache_from)
         rc = self._l.vcfx_cuda_submit_shared(self._h, primary._h, C.byref(info))
         if rc == E_BUSY:
             return False
@@ -234,7 +235,7 @@ class Context:
         out = C.string_at(text.value, n.value) if n.value else b""
         events = []
         if st.n_events:
-            cap = min(int(st.n_events), 1 << 20)
+            cap = int(st.n_events)
             arr = (C.c_uint64 * cap)(); got = C.c_size_t()
             self._check(self._l.vcfx_cuda_short_lines(self._h, arr, cap, C.byref(got)))
             events = list(arr[: got.value])
@@ -248,8 +249,8 @@ class Context:
         return text.value, n.value, st
 
     # -- device-resident path ------------------------------------------------------------
-    def run_device(self, d_in: int, nbytes: int, d_out: int, out_cap: int, valid_from: int = 0, is_final: bool = True, file_offset: int = 0):
-        info = ChunkInfo(valid_from, int(is_final), 0, file_offset)
+    def run_device(self, d_in: int, nbytes: int, d_out: int, out_cap: int, valid_from: int = 0, is_final: bool = True, file_offset: int = 0, format_cache_from: int = 0):
+        info = ChunkInfo(valid_from, int(is_final), 0, file_offset, format_cache_from)
         self._check(self._l.vcfx_cuda_run_device(self._h, d_in, nbytes, C.byref(info), d_out, out_cap))
 
     def sync(self) -> ChunkStats:
@@ -283,16 +284,24 @@ def chunk_bounds(data, chunk_bytes: int):
         pos = end
 
 
-def stream_bytes(ctx: Context, data, chunk_bytes: int, valid_abs: int = 0):
-    """Push ``data`` through ctx's streaming pipeline; returns (list of output pieces, Totals)."""
+def stream_bytes(ctx: Context, data, chunk_bytes: int, valid_abs: int = 0, on_events=None, fmt0_abs: int = 0):
+    """Push ``data`` through ctx's streaming pipeline; returns (list of output pieces, Totals).  ``on_events(chunk_start,
+    events)`` is called per drained chunk, in order, with its raw event list (phase_checker) instead of adding the
+    events to the totals as line numbers."""
     tot = Totals()
     outs = []
     line_base = 0
+    starts = []
 
     def drain():
         nonlocal line_base
         out, st, ev = ctx.next_output()
         outs.append(out)
+        start = starts.pop(0)
+        if on_events is not None:
+            if ev:
+                on_events(start, ev)
+            ev = []
         tot.add(st, line_base, ev)
         line_base += st.lines
 
@@ -306,7 +315,8 @@ def stream_bytes(ctx: Context, data, chunk_bytes: int, valid_abs: int = 0):
         assert e - s <= cap
         C.memmove(buf, (C.c_char * (e - s)).from_buffer_copy(mv[s:e]), e - s)
         vf = min(max(valid_abs - s, 0), e - s)
-        ctx.submit(e - s, valid_from=vf, is_final=(e == n), file_offset=s)
+        ctx.submit(e - s, valid_from=vf, is_final=(e == n), file_offset=s, format_cache_from=min(max(fmt0_abs - s, 0), e - s))
+        starts.append(s)
         # line numbers: chunks are drained in order, so the base is exact when drained
     while ctx.in_flight():
         drain()
@@ -339,13 +349,14 @@ import atexit  # noqa: E402
 atexit.register(close_cached_contexts)
 
 
-def _run(op: int, data: bytes, mode: int, chunk_bytes: int, flags: int = 0, device: int = 0, **kw):
+def _run(op: int, data: bytes, mode: int, chunk_bytes: int, flags: int = 0, device: int = 0, on_events=None, **kw):
     # default slot size: the input rounded up to 1 MiB, at most 64 MiB (pinned allocations are not free)
     chunk_bytes = chunk_bytes or min(64 << 20, max(1 << 20, (len(data) + (1 << 20) - 1) & ~((1 << 20) - 1)))
     ctx, cached = _cached_context(op, mode, device, flags, chunk_bytes, **kw)
     try:
-        valid_abs = find_chrom_header(data) if op in (OP_ALLELE_FREQ, OP_NONREF_FILTER) else 0
-        outs, tot = stream_bytes(ctx, data, chunk_bytes, valid_abs)
+        valid_abs = find_chrom_header(data) if op in (OP_ALLELE_FREQ, OP_NONREF_FILTER, OP_PHASE_CHECK) else 0
+        fmt0_abs = first_format_line(data, valid_abs) if (op == OP_PHASE_CHECK and mode == FILE) else 0
+        outs, tot = stream_bytes(ctx, data, chunk_bytes, valid_abs, on_events, fmt0_abs)
     except Exception:
         if cached:
             _ctx_cache.pop(next(k for k, v in _ctx_cache.items() if v is ctx), None)
@@ -361,6 +372,7 @@ class ToolResult:
     out: bytes
     rc: int
     totals: Totals
+    err: bytes = b""            # what the tool prints on stderr (phase_checker)
 
 
 def allele_freq_calc(data: bytes, mode: int = FILE, chunk_bytes: int = 0, **kw) -> ToolResult:
@@ -388,6 +400,25 @@ def first_data_offset(data) -> int:
             return n
         pos = nl + 1
     return pos
+
+
+def first_format_line(data, start: int = 0) -> int:
+    """Offset of the first data line at or behind ``start`` that has eight tabs and a non-empty FORMAT column behind them
+    (len(data) when there is none): VCFX_phase_checker's file mode treats an empty FORMAT column as "GT first" for the
+    lines in front of it (its FORMAT cache starts as ("", 0), VCFX_phase_checker.cpp:486-488, :313-316)."""
+    pos, n = start, len(data)
+    while pos < n:
+        nl = data.find(b"\n", pos)
+        le = n if nl < 0 else nl
+        line = bytes(data[pos:le])
+        if line.endswith(b"\r"):
+            line = line[:-1]
+        if line and not line.startswith(b"#"):
+            f = line.split(b"\t", 9)
+            if len(f) >= 9 and f[8] != b"":
+                return pos
+        pos = le + 1
+    return n
 
 
 def missing_detector(data: bytes, mode: int = FILE, chunk_bytes: int = 0, **kw) -> ToolResult:
@@ -449,6 +480,38 @@ def nonref_filter(data: bytes, mode: int = FILE, chunk_bytes: int = 0, **kw) -> 
     totals.pre_header = data lines in front of the header (each prints a warning), totals.flagged = lines dropped."""
     body, tot = _run(OP_NONREF_FILTER, data, mode, chunk_bytes, **kw)
     return ToolResult(body, 0, tot)
+
+
+PC_UNPHASED, PC_PRE_HEADER, PC_SHORT, PC_NO_GT = range(4)      # why VCFX_OP_PHASE_CHECK dropped a line (event & 3)
+
+
+def phase_checker(data: bytes, mode: int = FILE, quiet: bool = False, chunk_bytes: int = 0, **kw) -> ToolResult:
+    """VCFX_phase_checker: '#' lines and empty lines pass, a data line passes when it lies behind the "#CHROM" line, has
+    ten columns and a GT key and every sample is fully phased (VCFX_phase_checker.cpp:470-558 file mode, :563-650 stdin
+    mode).  The device reports every dropped line (offset, reason); ``err`` is the text the tool prints for them on
+    stderr without -q.  totals.flagged = lines dropped."""
+    msgs = []
+
+    def on_events(start, events):
+        for ev in events:
+            off, why = start + (ev >> 2), ev & 3
+            if why == PC_PRE_HEADER:
+                msgs.append(b"Warning: Data line encountered before #CHROM header; skipping line.\n")
+            elif why == PC_SHORT:
+                msgs.append(b"Warning: Invalid VCF line with fewer than 10 columns; skipping line.\n")
+            elif why == PC_NO_GT:
+                msgs.append(b"Warning: GT field not found; skipping line.\n")
+            else:
+                nl = data.find(b"\n", off)
+                line = bytes(data[off:len(data) if nl < 0 else nl])
+                if mode == FILE and line.endswith(b"\r"):
+                    line = line[:-1]
+                f = line.split(b"\t", 2)
+                if len(f) == 3:
+                    msgs.append(b"Unphased genotype found at CHROM=" + f[0] + b", POS=" + f[1] + b"; line skipped.\n")
+
+    body, tot = _run(OP_PHASE_CHECK, data, mode, chunk_bytes, on_events=None if quiet else on_events, **kw)
+    return ToolResult(body, 0, tot, b"".join(msgs))
 
 
 def variant_counter(data: bytes, mode: int = FILE, strict: bool = False, chunk_bytes: int = 0, **kw) -> ToolResult:

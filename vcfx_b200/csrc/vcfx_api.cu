@@ -41,6 +41,7 @@ struct Work {                      // device-side bookkeeping for one launch
     uint64_t rec_cap = 0;
     DevStats *d_stats = nullptr;
     unsigned long long *events = nullptr;
+    uint32_t ev_cap = 0;                 // entries in events (phase_checker grows it when a chunk drops more lines)
     DevStats *h_stats = nullptr;   // pinned: results of the last launch
     DevStats *h_init = nullptr;    // pinned: constant initial value uploaded before every launch
     uint32_t tiles_cap = 0;
@@ -138,6 +139,7 @@ kernel_fn kernel_for(int op) {
     case VCFX_OP_MISSING_DETECT: return vcfx_scan_kernel<OP_MD, 0>;
     case VCFX_OP_NONREF_FILTER: return vcfx_scan_kernel<OP_NR, 0>;
     case VCFX_OP_INDEX: return vcfx_scan_kernel<OP_IX, 0>;
+    case VCFX_OP_PHASE_CHECK: return vcfx_scan_kernel<OP_PC, 0>;
     case VCFX_OP_ALLELE_COUNT:  return vcfx_scan_kernel<OP_AC, 0>;
     default: return nullptr;
     }
@@ -157,6 +159,7 @@ kernel_fn format_kernel_for(int op, int ac_fmt = 0) {
     case VCFX_OP_HWE:         return format_rows_kernel<OP_HWE>;
     case VCFX_OP_MISSING_DETECT: return md_copy_kernel;
     case VCFX_OP_NONREF_FILTER: return md_copy_kernel;
+    case VCFX_OP_PHASE_CHECK: return md_copy_kernel;
     case VCFX_OP_INDEX: return format_rows_kernel<OP_IX>;
     default: return nullptr;
     }
@@ -243,6 +246,7 @@ int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes, uint64_t min_recs = 0)
         CU(cudaMalloc(&w.d_stats, sizeof(DevStats)));
         CU(cudaMalloc(&w.ticket, 2 * sizeof(unsigned int)));
         CU(cudaMalloc(&w.events, sizeof(unsigned long long) * EVENT_CAP));
+        w.ev_cap = EVENT_CAP;
         CU(cudaMallocHost(&w.h_stats, sizeof(DevStats)));
         CU(cudaMallocHost(&w.h_init, sizeof(DevStats)));
         memset(w.h_init, 0, sizeof(DevStats)); w.h_init->first_short_key = ~0ULL;
@@ -262,7 +266,7 @@ int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes, uint64_t min_recs = 0)
             cudaFree(w.tile_resume); w.tile_resume = nullptr;
             CU(cudaMalloc(&w.tile_resume, sizeof(uint32_t) * tiles));
         }
-        if (ctx->cfg.op == VCFX_OP_MISSING_DETECT || ctx->cfg.op == VCFX_OP_NONREF_FILTER) {
+        if (ctx->cfg.op == VCFX_OP_MISSING_DETECT || ctx->cfg.op == VCFX_OP_NONREF_FILTER || ctx->cfg.op == VCFX_OP_PHASE_CHECK) {
             cudaFree(w.tail_start); cudaFree(w.tail_len); cudaFree(w.tail_off);
             w.tail_start = w.tail_len = w.tail_off = nullptr;
             CU(cudaMalloc(&w.tail_start, sizeof(uint32_t) * tiles));
@@ -305,6 +309,7 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
     P.tile_bytes = tile; P.n_tiles = tiles;
     P.mode = ctx->cfg.mode; P.flags = ctx->cfg.flags;
     P.valid_from = info ? info->data_valid_from : 0;
+    P.fmt0_until = info ? info->format_cache_from : 0;
     P.file_offset = info ? info->file_offset : 0;
     P.is_final = info ? info->is_final : 1;
     P.out = d_out; P.out_cap = out_cap;
@@ -313,7 +318,7 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
     P.ac_fmt = ctx->ac_fmt; P.ac_ident = ctx->ac_ident ? 1 : 0; P.ac_pass = 0; P.ac_spec = (ctx->cfg.op == VCFX_OP_ALLELE_COUNT && ctx->ac_fmt == AC_TEXT_MT && !ctx->ac_exact) ? 1 : 0; P.n_sel = ctx->n_sel; P.sel_col = ctx->d_sel_col; P.name_off = ctx->d_name_off;
     P.names = ctx->d_names; P.names16 = ctx->d_names16; P.name_len = ctx->name_len; P.ac_bulk = ctx->ac_bulk ? 1 : 0; P.max_col = ctx->max_col; P.col_scratch = w.col_scratch;
     P.ticket = w.ticket; P.ticket2 = w.ticket + 1; P.tile_resume = w.tile_resume; P.recs = w.recs; P.rec_prefix = w.rec_prefix; P.rec_cap = w.rec_cap;
-    P.stats = w.d_stats; P.events = w.events; P.ev_cap = EVENT_CAP;
+    P.stats = w.d_stats; P.events = w.events; P.ev_cap = w.ev_cap; P.ev_raw = (ctx->cfg.op == VCFX_OP_PHASE_CHECK) ? 1 : 0;
 
     CU(cudaEventRecord(w.ev_k0, st));
     if (nbytes > 0) {
@@ -328,7 +333,7 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
         VCFX_LAUNCH(tile_scan_kernel, 1, 1024, SCAN_SMEM_BYTES, st, P);
         CU(cudaGetLastError());
         if (kernel_fn ff = format_kernel_for(ctx->cfg.op, ctx->ac_fmt)) {
-            VCFX_LAUNCH(ff, ctx->sm_count * ((ctx->cfg.op == VCFX_OP_MISSING_DETECT || ctx->cfg.op == VCFX_OP_NONREF_FILTER) ? 8 : 16), 256, 0, st, P);
+            VCFX_LAUNCH(ff, ctx->sm_count * ((ctx->cfg.op == VCFX_OP_MISSING_DETECT || ctx->cfg.op == VCFX_OP_NONREF_FILTER || ctx->cfg.op == VCFX_OP_PHASE_CHECK) ? 8 : 16), 256, 0, st, P);
             CU(cudaGetLastError());
         } else if (ctx->cfg.op == VCFX_OP_ALLELE_COUNT) {
             // rows are sized in the first pass and written in a second one at their scanned offsets
@@ -358,7 +363,7 @@ void fill_stats(const Work &w, size_t nbytes, vcfx_chunk_stats *s) {
 }
 
 int fetch_events(vcfx_ctx *ctx, const Work &w, cudaStream_t st) {
-    uint64_t nev = std::min<uint64_t>(w.h_stats->n_events, EVENT_CAP);
+    uint64_t nev = std::min<uint64_t>(w.h_stats->n_events, w.ev_cap);
     ctx->last_n_events = w.h_stats->n_events;
     ctx->last_events.resize(nev);
     if (nev) {
@@ -369,11 +374,24 @@ int fetch_events(vcfx_ctx *ctx, const Work &w, cudaStream_t st) {
     return VCFX_OK;
 }
 
+// phase_checker reports every dropped line: a chunk that dropped more lines than the list holds gets a longer list (and
+// is run again by the caller).  Returns 1 when it grew, 0 when nothing was lost, a negative vcfx_err on failure.
+int grow_events(vcfx_ctx *ctx, Work &w) {
+    if (ctx->cfg.op != VCFX_OP_PHASE_CHECK || w.h_stats->n_events <= w.ev_cap) return 0;
+    const uint64_t want = w.h_stats->n_events + (w.h_stats->n_events >> 3) + 1024;
+    if (want > 0xFFFFFFFFull) return VCFX_E_OUTPUT_TOO_BIG;
+    cudaFree(w.events); w.events = nullptr; w.ev_cap = 0;
+    CU(cudaMalloc(&w.events, sizeof(unsigned long long) * want));
+    w.ev_cap = (uint32_t)want;
+    return 1;
+}
+
 size_t default_out_bytes(int op, unsigned flags, size_t chunk) {
     switch (op) {
     case VCFX_OP_VARIANT_COUNT: return 4096;
     case VCFX_OP_MISSING_DETECT: return chunk + chunk / 4 + 4096;
     case VCFX_OP_NONREF_FILTER: return chunk + 4096;          // never longer than the input plus one '\n'
+    case VCFX_OP_PHASE_CHECK: return chunk + 4096;
     case VCFX_OP_ALLELE_COUNT:
         if (flags & VCFX_F_AC_AGGREGATE) return chunk / 4 + (1u << 20);
         if (flags & VCFX_F_AC_BINARY) return chunk + 4096;
@@ -429,7 +447,7 @@ const char *vcfx_cuda_last_error(const vcfx_ctx *ctx) { return ctx ? ctx->last_e
 int vcfx_cuda_create(const vcfx_cfg *cfg, vcfx_ctx **out) {
     if (!cfg || !out) return VCFX_E_INVALID;
     *out = nullptr;
-    if (cfg->op < VCFX_OP_VARIANT_COUNT || cfg->op > VCFX_OP_INDEX) return VCFX_E_INVALID;
+    if (cfg->op < VCFX_OP_VARIANT_COUNT || cfg->op > VCFX_OP_PHASE_CHECK) return VCFX_E_INVALID;
     if (cfg->mode != VCFX_MODE_FILE && cfg->mode != VCFX_MODE_STDIN) return VCFX_E_INVALID;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return VCFX_E_NO_DEVICE;
@@ -611,7 +629,7 @@ int vcfx_cuda_submit(vcfx_ctx *ctx, size_t nbytes, const vcfx_chunk_info *info) 
     CU(cudaMemsetAsync(s.d_in + nbytes, '\n', 64, s.stream));
     CU(cudaEventRecord(s.ev_h2d, s.stream));
     s.d_in_used = s.d_in;
-    if (info) s.info = *info; else s.info = vcfx_chunk_info{0, 1, 0, 0};
+    if (info) s.info = *info; else s.info = vcfx_chunk_info{0, 1, 0, 0, 0};
     int rc = launch_chunk(ctx, s.w, s.stream, s.d_in, nbytes, &s.info, s.d_out, s.out_cap, false);
     if (rc != VCFX_OK) return rc;
     s.nbytes = nbytes; s.in_flight = true; s.d2h_issued = false;
@@ -635,7 +653,7 @@ int vcfx_cuda_submit_host(vcfx_ctx *ctx, const void *host, size_t nbytes, const 
     CU(cudaMemsetAsync(s.d_in + nbytes, '\n', 64, s.stream));
     CU(cudaEventRecord(s.ev_h2d, s.stream));
     s.d_in_used = s.d_in;
-    if (info) s.info = *info; else s.info = vcfx_chunk_info{0, 1, 0, 0};
+    if (info) s.info = *info; else s.info = vcfx_chunk_info{0, 1, 0, 0, 0};
     rc = launch_chunk(ctx, s.w, s.stream, s.d_in, nbytes, &s.info, s.d_out, s.out_cap, false);
     if (rc != VCFX_OK) return rc;
     s.nbytes = nbytes; s.in_flight = true; s.d2h_issued = false;
@@ -662,7 +680,7 @@ int vcfx_cuda_submit_shared(vcfx_ctx *ctx, vcfx_ctx *primary, const vcfx_chunk_i
     if (rc != VCFX_OK) return rc;
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamWaitEvent(s.stream, ps.ev_h2d, 0));                 // the bytes are there
-    if (info) s.info = *info; else s.info = vcfx_chunk_info{0, 1, 0, 0};
+    if (info) s.info = *info; else s.info = vcfx_chunk_info{0, 1, 0, 0, 0};
     // An operation that may have to run a chunk again (more rows or more text than its slot was sized for) takes a
     // private device copy (a few tens of microseconds): the primary is then free to reuse its buffer at once and a
     // re-run never reads bytes the primary has overwritten.  variant_counter never re-runs and reads the primary's bytes.
@@ -699,7 +717,10 @@ int vcfx_cuda_next_output(vcfx_ctx *ctx, const char **text, size_t *n, vcfx_chun
     ctx->n_in_flight--;
     // A chunk with more rows / more text than the slot was sized for is simply run again with
     // exact sizes (the input is still on the device); the larger buffers are kept, with headroom.
-    for (int attempt = 0; s.w.h_stats->overflow && attempt < 3; ++attempt) {
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        const int grew = grow_events(ctx, s.w);
+        if (grew < 0) return grew;
+        if (!s.w.h_stats->overflow && !grew) break;
         const unsigned long long ov = s.w.h_stats->overflow;
         if (ov & 4) ctx->ac_exact = true;
         if (ov & 1) {
@@ -749,7 +770,7 @@ int vcfx_cuda_run_device(vcfx_ctx *ctx, void *d_in, size_t nbytes, const vcfx_ch
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_work(ctx, ctx->dev_work, nbytes);
     if (rc != VCFX_OK) return rc;
-    ctx->dev_info = info ? *info : vcfx_chunk_info{0, 1, 0, 0};
+    ctx->dev_info = info ? *info : vcfx_chunk_info{0, 1, 0, 0, 0};
     ctx->dev_in = (uint8_t *)d_in; ctx->dev_out = (uint8_t *)d_out; ctx->dev_out_cap = out_cap;
     rc = launch_chunk(ctx, ctx->dev_work, ctx->dev_stream, ctx->dev_in, nbytes, &ctx->dev_info, ctx->dev_out, out_cap);
     if (rc != VCFX_OK) return rc;
@@ -763,7 +784,9 @@ int vcfx_cuda_sync(vcfx_ctx *ctx, vcfx_chunk_stats *stats) {
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->dev_stream));
     ctx->dev_pending = false;
-    if (ctx->dev_work.h_stats->overflow & 5) {      // more rows than sized for / speculative row sizes off: run again, exact
+    const int grew = grow_events(ctx, ctx->dev_work);
+    if (grew < 0) return grew;
+    if ((ctx->dev_work.h_stats->overflow & 5) || grew) {      // more rows than sized for / speculative row sizes off / more events: run again
         if (ctx->dev_work.h_stats->overflow & 4) ctx->ac_exact = true;
         int rc2 = ensure_work(ctx, ctx->dev_work, ctx->dev_nbytes, ctx->dev_work.h_stats->n_recs + rec_slack(ctx));
         if (rc2 != VCFX_OK) return rc2;

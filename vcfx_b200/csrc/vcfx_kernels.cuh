@@ -36,7 +36,7 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int WARPS_PER_CTA = 8;
 constexpr uint32_t WINDOW = 512;
 
-enum : int { OP_VC = 0, OP_AF = 1, OP_HWE = 2, OP_MD = 3, OP_AC = 4, OP_NR = 5, OP_IX = 6 };
+enum : int { OP_VC = 0, OP_AF = 1, OP_HWE = 2, OP_MD = 3, OP_AC = 4, OP_NR = 5, OP_IX = 6, OP_PC = 7 };
 constexpr uint32_t NR_PLAIN = 0xFFFFFFFFu;     // Rec::b of a nonref_filter record: the line is written as its content + '\n' (or not at all)
 enum : int { MODE_FILE = 0, MODE_STDIN = 1 };
 enum : int { AC_TEXT_MT = 0, AC_TEXT_FWD = 1, AC_AGG = 2, AC_BIN = 3 };
@@ -115,6 +115,8 @@ struct KParams {
     DevStats *stats;
     unsigned long long *events;      // short-line events (tile << 32 | index in tile)
     uint32_t ev_cap;
+    unsigned long long fmt0_until;   // phase_checker, file mode: an empty FORMAT column of a line starting below this offset means GT index 0
+    int32_t ev_raw;                  // 1: events are final values (phase_checker: line offset << 2 | kind), not (tile, index) keys
 };
 
 // ---------------------------------------------------------------------------------------
@@ -273,6 +275,48 @@ __device__ __noinline__ bool nr_sample_homref(const uint8_t *p, bool file_mode, 
     if (file_mode && n == 3) return ldb(gs) == '0' && is_sep(ldb(gs + 1)) && ldb(gs + 2) == '0';
     for (const uint8_t *q = gs; q < ge; ++q) { const uint32_t b = ldb(q); if (b != '0' && !is_sep(b)) return false; }
     return true;
+}
+
+// VCFX_phase_checker.cpp:218-268 isFullyPhasedFast on the GT of the sample column starting at p.  The column ends at a tab
+// or at the line end (file mode: a '\r' before the '\n' is not content; stdin mode: it is).  At the line end there is no
+// column in file mode (the reference's loop is over: true) and an empty one in stdin mode (false); an empty column in the
+// middle is never phased.  GT = the piece before the first ':' (gt_index 0) or the gt_index-th piece (:194-213, empty when
+// there are fewer).  Three bytes: x|y with x, y not '.'; one byte: no; otherwise every '|'-separated allele must be
+// non-empty and not ".", no '/', at least one '|'.
+__device__ __noinline__ bool pc_sample_phased(const uint8_t *p, bool file_mode, int gt_index) {
+    const uint8_t *se = p;
+    uint32_t c = ldb(se);
+    while (c != '\t' && c != '\n') { ++se; c = ldb(se); }
+    if (file_mode && c == '\n' && ldb(se - 1) == '\r') { if (se - 1 >= p) --se; else return true; }
+    if (se == p) return (c == '\n') ? file_mode : false;
+    const uint8_t *gs = p, *ge = se;
+    if (gt_index == 0) { ge = p; while (ge < se && ldb(ge) != ':') ++ge; }
+    else {
+        int idx = 0; const uint8_t *fs = p; bool got = false;
+        for (const uint8_t *q = p; q <= se; ++q) {
+            if (q == se || ldb(q) == ':') {
+                if (idx == gt_index) { gs = fs; ge = q; got = true; break; }
+                ++idx; fs = q + 1;
+            }
+        }
+        if (!got) return false;
+    }
+    const uint32_t n = (uint32_t)(ge - gs);
+    if (n == 0 || n == 1) return false;
+    if (n == 3) return ldb(gs + 1) == '|' && ldb(gs) != '.' && ldb(gs + 2) != '.';
+    if (ldb(gs) == '.' && is_sep(ldb(gs + 1)) && ldb(gs + 2) == '.') return false;
+    bool pipe = false; const uint8_t *as = gs;
+    for (const uint8_t *q = gs; q < ge; ++q) {
+        const uint32_t b = ldb(q);
+        if (b == '|') {
+            const uint32_t al = (uint32_t)(q - as);
+            if (al == 0 || (al == 1 && ldb(as) == '.')) return false;
+            pipe = true; as = q + 1;
+        } else if (b == '/') return false;
+    }
+    const uint32_t al = (uint32_t)(ge - as);
+    if (al == 0 || (al == 1 && ldb(as) == '.')) return false;
+    return pipe;
 }
 
 // VCFX_indexer on one data line [s, e) (a '\r' before the '\n' already cut off): where CHROM is and what POS reads as.
@@ -1419,8 +1463,10 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
             }
             // ================= NONREF_FILTER: is every sample homozygous reference?
             bool nr_all = false;               // the line can be dropped and no sample so far speaks against it
-            if (OP == OP_NR && !hash && tabs >= 9 && (a0 + ls >= P.valid_from)) {
-                const int gi = gt_index_of(tin + tp[7] + 1, tin + tp[8]);        // :317-335 findGTIndex on FORMAT
+            if ((OP == OP_NR || OP == OP_PC) && !hash && tabs >= 9 && (a0 + ls >= P.valid_from)) {
+                const int gi_ = gt_index_of(tin + tp[7] + 1, tin + tp[8]);        // findGTIndex on FORMAT (nonref_filter :317-335, phase_checker :171-189)
+                // phase_checker's file mode starts with the FORMAT cache ("", 0): an empty FORMAT column is "GT first" until a non-empty one was seen
+                const int gi = (OP == OP_PC && gi_ < 0 && P.mode == MODE_FILE && tp[8] == tp[7] + 1 && (a0 + ls) < P.fmt0_until) ? 0 : gi_;
                 if (gi >= 0) {
                     nr_all = true;
                     const uint32_t lo = tp[8];                                    // the tab in front of the first sample
@@ -1453,8 +1499,17 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                                 const uint32_t *s4 = reinterpret_cast<const uint32_t *>((uintptr_t)sp & ~(uintptr_t)3);
                                 const uint32_t q = __funnelshift_r(__ldg(s4), __ldg(s4 + 1), 8u * (uint32_t)((uintptr_t)sp & 3));
                                 const uint32_t g3 = q & 0x00FFFFFFu, b3 = q >> 24;
-                                const bool quick = (g3 == 0x00302F30u || g3 == 0x00307C30u) && (b3 == '\t' || (gi == 0 && b3 == ':'));
-                                if (!quick && !nr_sample_homref(sp, file_mode, gi)) bad = true;
+                                if (OP == OP_NR) {
+                                    const bool quick = (g3 == 0x00302F30u || g3 == 0x00307C30u) && (b3 == '\t' || (gi == 0 && b3 == ':'));
+                                    if (!quick && !nr_sample_homref(sp, file_mode, gi)) bad = true;
+                                } else {
+                                    // phase_checker: "x|y" of exactly three bytes, x and y anything but '.' (and not an end of the GT)
+                                    const uint32_t b0 = q & 0xFFu, b2 = (q >> 16) & 0xFFu;
+                                    const bool e0 = b0 == '.' || b0 == '\t' || b0 == '\n' || b0 == ':' || b0 == '\r';
+                                    const bool e2 = b2 == '.' || b2 == '\t' || b2 == '\n' || b2 == ':' || b2 == '\r';
+                                    const bool quick = gi == 0 && ((q >> 8) & 0xFFu) == '|' && !e0 && !e2 && (b3 == '\t' || b3 == ':');
+                                    if (!quick && !pc_sample_phased(sp, file_mode, gi)) bad = true;
+                                }
                             }
                             if (__any_sync(FULL, bad)) nr_all = false;
                         }
@@ -1753,6 +1808,54 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                     }
                 }
             }
+            else if (OP == OP_PC) {
+                // VCFX_phase_checker.cpp:493-558 / 576-650: '#' lines and empty lines pass; a data line passes when it lies behind
+                // the "#CHROM" line, has its ten columns and a GT key, and every sample is fully phased; each dropped line leaves
+                // an event (its offset and why) for the message the tool prints on stderr.
+                const bool term = (a0 + e) < n;
+                const uint32_t raw_end = term ? e + 1 : e;
+                const bool file_mode = P.mode == MODE_FILE;
+                const uint32_t cend = file_mode ? ee : e;                // stdin mode: getline keeps a '\r'
+                const bool data = (cend != ls) && !hash;
+                bool drop = false; uint32_t why = 0;                     // 0 unphased (or no GT key, file mode), 1 before the header, 2 fewer than ten columns, 3 no GT key (stdin mode)
+                if (data) {
+                    VCFX_COUNT(C_DATA, 1);
+                    if (a0 + ls < P.valid_from) { drop = true; why = 1; VCFX_COUNT(C_PRE, 1); }
+                    else if (file_mode) {
+                        // :296-359: eight tabs and a byte behind them, a GT key, a tab behind FORMAT, then the samples
+                        if (tabs < 8 || tp[7] + 1 >= cend) { drop = true; why = 2; }
+                        else if (tabs == 8) { drop = true; why = gt_index_of(tin + tp[7] + 1, tin + cend) < 0 ? 0u : 2u; }
+                        else if (!nr_all) drop = true;                   // (no GT key, or a sample that is not phased)
+                    } else {
+                        if (tabs < 9) { drop = true; why = 2; }
+                        else if (gt_index_of(tin + tp[7] + 1, tin + tp[8]) < 0) { drop = true; why = 3; }
+                        else if (!nr_all) drop = true;
+                    }
+                }
+                if (data && !drop) VCFX_COUNT(C_ROWS, 1);
+                if (drop) {
+                    VCFX_COUNT(C_FLAG, 1);
+                    if (lane == 0) {
+                        const unsigned long long slot = atomicAdd(&P.stats->n_events, 1ULL);
+                        if (slot < P.ev_cap) P.events[slot] = ((unsigned long long)(a0 + ls) << 2) | why;
+                    }
+                }
+                if (drop || cend != e || !term) {
+                    const uint32_t content_len = drop ? 0u : cend - ls, mod_len = drop ? 0u : content_len + 1u;
+                    if (lane == 0) {
+                        unsigned long long slot = alloc_slot(ws.rec_base, ws.rec_used, P.stats);
+                        if (slot < P.rec_cap) {
+                            Rec r; r.tile = tile; r.ls_rel = (uint32_t)(a0 + ls - a); r.prefix_len = (uint32_t)(a0 + md_prev_end - a);
+                            r.off_in_tile = (uint32_t)out_bytes; r.a = 0; r.b = NR_PLAIN; r.c = content_len; r.d = mod_len;
+                            P.recs[slot] = r;
+                        }
+                    }
+                    out_bytes += (ls - md_prev_end) + mod_len;
+                    md_prev_end = raw_end;
+                }
+                md_add_nl = false;
+                md_last_end = raw_end;
+            }
             else if (OP == OP_NR) {
                 // VCFX_nonref_filter.cpp:478-544 / 553-631: every line is written as its content + '\n' (file mode: without a
                 // '\r' before the '\n'), except data lines behind the "#CHROM" line whose samples are all hom-ref.  Lines that
@@ -1850,7 +1953,7 @@ vcfx_scan_kernel(const VCFX_GRID_CONSTANT KParams P) {
     const int lane = lane_id();
     const int wid = threadIdx.x >> 5;
     const uint64_t n = P.n;
-    const bool strip_cr = (OP == OP_HWE) || (P.mode == MODE_FILE && (OP == OP_AF || OP == OP_VC || OP == OP_MD || OP == OP_NR)) || OP == OP_IX;
+    const bool strip_cr = (OP == OP_HWE) || (P.mode == MODE_FILE && (OP == OP_AF || OP == OP_VC || OP == OP_MD || OP == OP_NR || OP == OP_PC)) || OP == OP_IX;
     if (OP == OP_AC && P.ac_pass && P.stats->overflow) return;
     if (VAR == 1 && P.stats->n_unfinished == 0) return;
 
@@ -1934,7 +2037,7 @@ vcfx_scan_kernel(const VCFX_GRID_CONSTANT KParams P) {
         const bool md_add_nl = st.md_add_nl;
 
         if (!(OP == OP_AC && P.ac_pass)) VCFX_COUNT(C_LINES, VAR == 1 ? nlines - lines_before : nlines);
-        if (OP == OP_MD || OP == OP_NR) {
+        if (OP == OP_MD || OP == OP_NR || OP == OP_PC) {
             const uint32_t tail = md_last_end - md_prev_end;
             if (lane == 0) {
                 P.tail_start[tile] = (uint32_t)(a0 + md_prev_end - a);
@@ -2039,7 +2142,7 @@ tile_scan_kernel(const KParams P) {
     __syncthreads();
     unsigned long long nev = P.stats->n_events;
     if (nev > P.ev_cap) nev = P.ev_cap;
-    for (unsigned long long i = tid; i < nev; i += 1024) {
+    for (unsigned long long i = tid; i < nev && !P.ev_raw; i += 1024) {
         unsigned long long k = P.events[i];
         P.events[i] = P.line_base[k >> 32] + (k & 0xFFFFFFFFULL) + 1ULL;
     }

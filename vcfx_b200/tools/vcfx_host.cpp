@@ -282,6 +282,7 @@ class Writer {
 struct Drain {
     std::vector<vcfx_ctx *> ctxs; const RunOptions &opt; Totals &tot; Writer *writer = nullptr; uint64_t line_base = 0;
     long drained = 0, final_index = -1;
+    std::deque<std::pair<const char *, size_t>> inputs;      // the pinned input of every chunk in flight (intact until its slot is acquired again)
     int one(std::string &err) {
         const char *text = nullptr; size_t n = 0; vcfx_chunk_stats st;
         vcfx_ctx *ctx = ctxs[(size_t)drained % ctxs.size()];        // chunks were dealt round-robin: the oldest one is this context's
@@ -303,6 +304,13 @@ struct Drain {
             vcfx_cuda_short_lines(ctx, ev.data(), ev.size(), &got);
             for (size_t i = 0; i < got; ++i) tot.short_line_numbers.push_back(line_base + ev[i]);
         }
+        if (opt.on_events && st.n_events && !inputs.empty()) {
+            std::vector<uint64_t> ev((size_t)st.n_events);
+            size_t got = 0;
+            vcfx_cuda_short_lines(ctx, ev.data(), ev.size(), &got);
+            opt.on_events(inputs.front().first, inputs.front().second, ev.data(), got);
+        }
+        if (!inputs.empty()) inputs.pop_front();
         tot.lines += st.lines;
         line_base += st.lines;
         ++drained;
@@ -375,7 +383,7 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
     Drain drain{ctxs, opt, tot, writer};
     const long n_slots = (long)cfg.n_slots * (long)G;     // pinned output buffers in rotation over all the contexts
     std::string carry = opt.preface;
-    bool eof = false, chrom_seen = false, in_hash_block = true, index_saw_hash = false;
+    bool eof = false, chrom_seen = false, in_hash_block = true, index_saw_hash = false, format_seen = false;
     uint64_t file_pos = 0;                         // offset of the next chunk in the whole input
     long submitted = 0;
     while (!eof) {
@@ -436,6 +444,24 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
                 if (off < nbytes) chrom_seen = true;
                 info.data_valid_from = off;
             }
+            if (opt.op == VCFX_OP_PHASE_CHECK && opt.mode == VCFX_MODE_FILE && !format_seen) {
+                // VCFX_phase_checker's file mode keeps the last FORMAT string with its GT index and starts with ("", 0): an empty
+                // FORMAT column means "GT first" for the lines in front of the first one with a non-empty FORMAT (:486-488, :313-316)
+                size_t pos = (size_t)info.data_valid_from, bound = nbytes;
+                while (pos < nbytes) {
+                    const char *nl = static_cast<const char *>(memchr(buf + pos, '\n', nbytes - pos));
+                    const size_t le = nl ? (size_t)(nl - buf) : nbytes;
+                    size_t e2 = le;
+                    if (e2 > pos && buf[e2 - 1] == '\r') --e2;
+                    if (e2 > pos && buf[pos] != '#') {
+                        size_t p = pos; int tabs = 0;
+                        while (p < e2 && tabs < 8) { if (buf[p] == '\t') ++tabs; ++p; }
+                        if (tabs == 8 && p < e2 && buf[p] != '\t') { bound = pos; format_seen = true; break; }
+                    }
+                    pos = le + 1;
+                }
+                info.format_cache_from = bound;
+            }
         } else if (opt.rule == HeaderRule::IndexChrom) {
             // VCFX_indexer: rows start behind the first "#CHROM" line — file mode: blanks / tabs, then "#CHROM" (:108-122);
             // stdin mode: white space, then a first field that is exactly "#CHROM" with a second one behind it (:349-356).
@@ -486,6 +512,7 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
         t0 = now();
         rc = vcfx_cuda_submit(ctx, nbytes, &info);
         t_submit += now() - t0;
+        drain.inputs.push_back({buf, nbytes});
         ++submitted;
         if (rc != VCFX_OK) { err = std::string(vcfx_cuda_strerror(rc)) + ": " + vcfx_cuda_last_error(ctx); destroy_all(); return rc; }
         if (opt.stop_at_first_short && in_flight_total() >= 2) {

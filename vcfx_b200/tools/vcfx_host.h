@@ -73,6 +73,9 @@ struct RunOptions {
     std::string header_row;
     // when set, every piece of text is handed to this function instead (in order; false = stop with an error)
     std::function<bool(const char *, size_t)> sink;
+    // when set, called once per chunk that has events, in stream order, with the chunk's input bytes and its sorted event
+    // list (VCFX_OP_PHASE_CHECK: offset of a dropped line in the chunk << 2 | reason)
+    std::function<void(const char *chunk, size_t nbytes, const uint64_t *events, size_t n)> on_events;
     // when set, only the text of the FINAL chunk is held back here (everything before is written)
     std::string *capture_final = nullptr;
     // keeps a copy of the last line of the input when it has no '\n' (missing_detector's quirk)
