@@ -101,6 +101,16 @@ def phase_checker_stderr(data: bytes, mode: int = FILE) -> bytes:
     return out
 
 
+IB_GLOBAL, IB_SKIP_BOUNDARY, IB_COUNT_BOUNDARY, IB_QUIET = 1, 2, 4, 8
+IB_MESSAGES = {0: b"", 1: b"Error: Empty file.\n", 2: b"Error: No #CHROM line or no samples found.\n", 3: b"No biallelic variants found.\n",
+               4: b"Error: No #CHROM line found.\n", 5: b"Error: No sample columns found.\n"}
+
+
+def inbreeding(data: bytes, mode: int = FILE, flags: int = 0) -> Result:
+    """VCFX_inbreeding_calculator; .warnings = key of IB_MESSAGES (what goes to stderr), .rows = sites used."""
+    return _call(lib().oracle_inbreeding, data, len(data), mode, flags)
+
+
 def indexer(data: bytes, mode: int = FILE) -> Result:
     return _call(lib().oracle_indexer, data, len(data), mode)
 

@@ -877,6 +877,201 @@ int oracle_phase_checker_err(const char *in, size_t n, int mode, oracle_result *
     return rc;
 }
 
+/* ------------------------------------------------------------------ inbreeding_calculator (§8 f3): per-sample F = 1 - observed
+ * heterozygotes / expected heterozygotes over the biallelic sites, the expectation summed in file order in double. */
+
+/* VCFX_inbreeding_calculator.cpp:296-339 parseGenotypeCode: the piece before the first ':', blanks / '\r' in front skipped,
+ * digits, '/' or '|', digits (whatever follows them is not looked at); both alleles 0 or 1 -> 0, 1, 2; anything else -1.
+ * (Allele numbers are accumulated in int; ten or more digits are outside what the restatement promises.) */
+static int ib_code(const char *p, const char *end) {
+    if (p >= end) return -1;
+    const char *c = memchr(p, ':', (size_t)(end - p));
+    if (c) end = c;
+    while (p < end && (*p == ' ' || *p == '\r')) ++p;
+    if (p >= end || *p < '0' || *p > '9') return -1;
+    unsigned a1 = 0, a2 = 0;
+    while (p < end && *p >= '0' && *p <= '9') { a1 = a1 * 10u + (unsigned)(*p - '0'); ++p; }
+    if (p >= end || (*p != '/' && *p != '|')) return -1;
+    ++p;
+    if (p >= end || *p < '0' || *p > '9') return -1;
+    while (p < end && *p >= '0' && *p <= '9') { a2 = a2 * 10u + (unsigned)(*p - '0'); ++p; }
+    if ((int)a1 > 1 || (int)a2 > 1 || (int)a1 < 0 || (int)a2 < 0) return -1;
+    return a1 == a2 ? (a1 == 0 ? 0 : 2) : 1;
+}
+
+typedef struct { double *sum; double *het; int *used; int *code; int n; long long variants; } ib_acc;
+
+/* :603-636 / :760-790: one site's contribution to every sample that has a genotype code */
+static void ib_site(ib_acc *a, int alt_sum, int n_good, int global, int skip_boundary, int count_boundary) {
+    double global_p = (double)alt_sum / (2.0 * n_good);
+    for (int s = 0; s < a->n; ++s) {
+        int code = a->code[s];
+        if (code < 0) continue;
+        double freq;
+        if (global) freq = global_p;
+        else {
+            int alt_ex = alt_sum - code, valid_ex = n_good - 1;
+            if (valid_ex < 1) continue;
+            freq = (double)alt_ex / (2.0 * valid_ex);
+        }
+        if (skip_boundary && (freq <= 0.0 || freq >= 1.0)) { if (count_boundary) a->used[s]++; continue; }
+        a->used[s]++;
+        double e_het = 2.0 * freq * (1.0 - freq);
+        a->sum[s] += e_het;
+        if (code == 1) a->het[s] += 1.0;
+    }
+}
+
+static void ib_report(obuf *o, const ib_acc *a, const char **name, const size_t *name_len, int quiet, oracle_result *r) {   /* :641-667 / :806-826 */
+    if (a->variants == 0) {
+        if (!quiet) r->warnings = 3;                                       /* "No biallelic variants found." */
+        for (int s = 0; s < a->n; ++s) { ob_put(o, name[s], name_len[s]); ob_str(o, "\tNA\n"); }
+        return;
+    }
+    for (int s = 0; s < a->n; ++s) {
+        ob_put(o, name[s], name_len[s]); ob_ch(o, '\t');
+        if (a->used[s] == 0) { ob_str(o, "NA\n"); continue; }
+        double e = a->sum[s];
+        if (e <= 0.0) { ob_str(o, "1.000000\n"); continue; }
+        double f = 1.0 - (a->het[s] / e);
+        char nb[64]; int l = oracle_fmt_p_file(f, nb);                     /* :205-240 appendDouble: the same truncating digits as hwe_tester's */
+        ob_put(o, nb, (size_t)l); ob_ch(o, '\n');
+    }
+}
+
+static int ib_alloc(ib_acc *a, int n) {
+    a->n = n; a->variants = 0;
+    a->sum = calloc((size_t)n + 1, sizeof(double)); a->het = calloc((size_t)n + 1, sizeof(double));
+    a->used = calloc((size_t)n + 1, sizeof(int)); a->code = calloc((size_t)n + 1, sizeof(int));
+    return a->sum && a->het && a->used && a->code;
+}
+static void ib_free(ib_acc *a) { free(a->sum); free(a->het); free(a->used); free(a->code); }
+
+/* flags: 1 = --freq-mode global, 2 = --skip-boundary, 4 = --count-boundary-as-used, 8 = -q.
+ * r->warnings = which message goes to stderr: 1 "Error: Empty file.", 2 "Error: No #CHROM line or no samples found.",
+ * 3 "No biallelic variants found." (not with -q), 4 "Error: No #CHROM line found.", 5 "Error: No sample columns found."
+ * r->rows = sites used (at least two samples with a genotype code). */
+int oracle_inbreeding(const char *in, size_t n, int mode, int flags, oracle_result *r) {
+    res_init(r);
+    obuf o = {0};
+    const int global = flags & 1, skipb = (flags >> 1) & 1, countb = (flags >> 2) & 1, quiet = (flags >> 3) & 1;
+    const char **name = NULL; size_t *name_len = NULL; int ns = 0, cap = 0;
+    ib_acc a; memset(&a, 0, sizeof a);
+    size_t pos = 0; line_t ln;
+#define IB_PUSH(ps, pe) do { if (ns == cap) { cap = cap ? cap * 2 : 64; name = realloc(name, (size_t)cap * sizeof *name); name_len = realloc(name_len, (size_t)cap * sizeof *name_len); } \
+                             name[ns] = (ps); name_len[ns] = (size_t)((pe) - (ps)); ++ns; } while (0)
+    if (mode == ORACLE_FILE) {                                             /* :456-668 calculateInbreedingMmap */
+        if (n == 0) { r->warnings = 1; ob_str(&o, "Sample\tInbreedingCoefficient\n"); res_take(r, &o); return 0; }
+        int found_chrom = 0;
+        size_t data_pos = n;
+        /* the leading block of '#' and empty lines: every "#CHROM" line in it ADDS its columns 10.. to the sample list (:487-508) */
+        for (;;) {
+            size_t at = pos;
+            if (!next_line(in, n, &pos, &ln)) { data_pos = n; break; }
+            const char *s = ln.s, *e = ln.e;
+            if (e > s && e[-1] == '\r') --e;
+            if (s == e) continue;
+            if (*s != '#') { data_pos = at; break; }
+            if (e - s >= 6 && memcmp(s, "#CHROM", 6) == 0) {
+                found_chrom = 1;
+                const char *fs = s; int idx = 0;
+                while (fs < e) {
+                    const char *t = memchr(fs, '\t', (size_t)(e - fs)); if (!t) t = e;
+                    if (idx >= 9) { const char *ne = t; if (ne > fs && ne[-1] == '\r') --ne; IB_PUSH(fs, ne); }
+                    ++idx; fs = t + 1;
+                }
+            }
+        }
+        if (!found_chrom || ns == 0) { r->warnings = 2; ob_str(&o, "Sample\tInbreedingCoefficient\n"); res_take(r, &o); free(name); free(name_len); return 0; }
+        if (!ib_alloc(&a, ns)) return -1;
+        pos = data_pos;
+        while (next_line(in, n, &pos, &ln)) {
+            const char *s = ln.s, *e = ln.e;
+            if (e > s && e[-1] == '\r') --e;
+            if (s == e || *s == '#') continue;
+            const char *fs, *fe;
+            if (!field_at(s, e, 4, &fs, &fe) || fs == fe || memchr(fs, ',', (size_t)(fe - fs))) continue;     /* :549-553 */
+            const char *sp, *spe;
+            if (!field_at(s, e, 9, &sp, &spe)) continue;                   /* :557-561 */
+            r->data_lines++;
+            int alt_sum = 0, n_good = 0;
+            /* a column the line does not have keeps the code of the last line that had it (the buffer is reused, :574-588) */
+            for (int k = 0; k < ns && sp < e; ++k) {
+                const char *t = memchr(sp, '\t', (size_t)(e - sp)); if (!t) t = e;
+                int code = ib_code(sp, t);
+                a.code[k] = code;
+                if (code >= 0) { alt_sum += code; n_good++; }
+                sp = t + 1;
+            }
+            if (n_good < 2) continue;
+            a.variants++;
+            ib_site(&a, alt_sum, n_good, global, skipb, countb);
+        }
+        ob_str(&o, "Sample\tInbreedingCoefficient\n");
+        ib_report(&o, &a, name, name_len, quiet, r);
+    } else {                                                               /* :670-826 calculateInbreedingStdin */
+        int found_chrom = 0;
+        while (next_line(in, n, &pos, &ln)) {
+            const char *s = ln.s, *e = ln.e;
+            if (s == e) continue;
+            if (e[-1] == '\r') --e;
+            if (s == e) continue;
+            if (*s == '#') {
+                if (!found_chrom) {
+                    int hit = 0;
+                    for (const char *q = s; q + 6 <= e; ++q) if (memcmp(q, "#CHROM", 6) == 0) { hit = 1; break; }
+                    if (hit) {
+                        found_chrom = 1;
+                        const char *fs = s; int idx = 0;
+                        for (;;) {                                         /* split_tabs: a final empty field counts */
+                            const char *t = memchr(fs, '\t', (size_t)(e - fs));
+                            const char *fe2 = t ? t : e;
+                            if (idx >= 9) IB_PUSH(fs, fe2);
+                            ++idx;
+                            if (!t) break;
+                            fs = t + 1;
+                        }
+                        if (!ib_alloc(&a, ns)) return -1;
+                    }
+                }
+                continue;
+            }
+            if (!found_chrom) continue;
+            int tabs = 0; for (const char *q = s; q < e; ++q) tabs += (*q == '\t');
+            if (tabs + 1 < 10) continue;
+            const char *fs, *fe;
+            fs = nr_skip(s, e, 4); fe = fs; while (fe < e && *fe != '\t') ++fe;
+            if (memchr(fs, ',', (size_t)(fe - fs))) continue;
+            r->data_lines++;
+            int alt_sum = 0, n_good = 0;
+            const char *sp = nr_skip(s, e, 9);
+            int gone = 0;
+            for (int k = 0; k < ns; ++k) {
+                int code = -1;
+                if (!gone) {
+                    const char *t = sp; while (t < e && *t != '\t') ++t;
+                    code = ib_code(sp, t);
+                    if (t >= e) gone = 1; else sp = t + 1;
+                }
+                a.code[k] = code;
+                if (code >= 0) { alt_sum += code; n_good++; }
+            }
+            if (n_good < 2) continue;
+            a.variants++;
+            ib_site(&a, alt_sum, n_good, global, skipb, countb);
+        }
+        ob_str(&o, "Sample\tInbreedingCoefficient\n");
+        if (!found_chrom) r->warnings = 4;
+        else if (ns == 0) r->warnings = 5;
+        else ib_report(&o, &a, name, name_len, quiet, r);
+    }
+#undef IB_PUSH
+    r->rows = a.variants;
+    ib_free(&a); free(name); free(name_len);
+    res_take(r, &o);
+    return 0;
+}
+
 /* ------------------------------------------------------------------ variant_counter */
 
 /* variant_counter.cpp:31-44 — at least 7 tabs. */
