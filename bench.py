@@ -390,11 +390,13 @@ def config_entries(torch, np, api, synth, O, dev, peak, threads, only=None):
     sel = dict(sel_cols=list(range(SAMPLES)), sel_names=names)
     plans = [
         ("C2", 2, C2_VARIANTS, [("hwe_tester", api.OP_HWE, 0, {}, 20000), ("nonref_filter", api.OP_NONREF_FILTER, 0, {}, 20000),
-                                ("indexer", api.OP_INDEX, 0, {}, 60000), ("phase_checker", api.OP_PHASE_CHECK, 0, {}, 20000)]),
+                                ("indexer", api.OP_INDEX, 0, {}, 60000), ("phase_checker", api.OP_PHASE_CHECK, 0, {}, 20000),
+                                ("inbreeding_calculator", api.OP_INBREEDING, 0, sel, 20000)]),
         ("C3", 3, C2_VARIANTS, [("missing_detector", api.OP_MISSING_DETECT, 0, {}, 20000),
                                 ("allele_counter", api.OP_ALLELE_COUNT, 0, sel, 4000),
                                 ("allele_counter -a", api.OP_ALLELE_COUNT, api.F_AC_AGGREGATE, sel, 400),
-                                ("allele_freq_calc", api.OP_ALLELE_FREQ, 0, {}, 20000)]),
+                                ("allele_freq_calc", api.OP_ALLELE_FREQ, 0, {}, 20000),
+                                ("inbreeding_calculator", api.OP_INBREEDING, 0, sel, 20000)]),
         ("C4", 4, C4_VARIANTS, [("hwe_tester", api.OP_HWE, 0, {}, 3000),
                                 ("allele_freq_calc", api.OP_ALLELE_FREQ, 0, {}, 3000)]),
     ]
@@ -436,6 +438,13 @@ def config_entries(torch, np, api, synth, O, dev, peak, threads, only=None):
                     exp, n_exp = oracle_parallel(O, {"hwe_tester": "hwe", "allele_freq_calc": "allele_freq"}[tname], sh, np)
                 ent["parity_full"] = {"against": "oracle port, all host cores, the whole input", "bytes": int(st.bytes_out),
                                       "equal": got == exp and n_exp == int(st.bytes_out), "sha256": got}
+            if tname == "inbreeding_calculator":
+                # the sums depend on the order of the sites: the restatement walks the whole input on one core
+                got_b = d_out[:int(st.bytes_out)].cpu().numpy().tobytes()
+                t0 = time.perf_counter()
+                exp_b = O.inbreeding(sh.hnp[:sh.nbytes].tobytes(), 0, O.IB_QUIET).out[len(api.IB_HEADER):]
+                ent["parity_full"] = {"against": "oracle port, one core, the whole input in file order", "bytes": len(got_b), "equal": got_b == exp_b,
+                                      "sha256": hashlib.sha256(got_b).hexdigest(), "oracle_seconds": time.perf_counter() - t0}
             del d_out
             torch.cuda.empty_cache()
             # end to end from pinned host memory
@@ -472,7 +481,7 @@ def parity_vs_reference(api, O, np, shard, tname, n_variants):
     """GPU tool output (through the C ABI, FILE semantics) against the stdout of the unmodified reference tool
     on the first n_variants lines of the shard."""
     tool = {"hwe_tester": "hwe_tester", "allele_freq_calc": "allele_freq_calc", "missing_detector": "missing_detector",
-            "allele_counter": "allele_counter", "allele_counter -a": "allele_counter", "variant_counter": "variant_counter", "nonref_filter": "nonref_filter", "indexer": "indexer", "phase_checker": "phase_checker"}[tname]
+            "allele_counter": "allele_counter", "allele_counter -a": "allele_counter", "variant_counter": "variant_counter", "nonref_filter": "nonref_filter", "indexer": "indexer", "phase_checker": "phase_checker", "inbreeding_calculator": "inbreeding_calculator"}[tname]
     exe = ref_tool(tool)
     data = shard.prefix_bytes(np, n_variants)
     if tname == "hwe_tester":
@@ -487,6 +496,8 @@ def parity_vs_reference(api, O, np, shard, tname, n_variants):
         got = api.indexer(data, api.FILE).out; args = []
     elif tname == "phase_checker":
         got = api.phase_checker(data, api.FILE, quiet=True).out; args = ["-q", "-i"]
+    elif tname == "inbreeding_calculator":
+        got = api.inbreeding_calculator(data, api.FILE).out; args = ["-q", "-i"]
     elif tname == "allele_counter":
         got = api.allele_counter(data, api.AC_MT_TEXT, api.AC_TEXT).out; args = ["-q", "-i"]
     elif tname == "allele_counter -a":
@@ -497,7 +508,7 @@ def parity_vs_reference(api, O, np, shard, tname, n_variants):
     if exe is None:
         # no reference binary on this box: the CPU restatement (pinned to the reference by tests/) stands in
         fn = {"hwe_tester": lambda: O.hwe(data, 0), "allele_freq_calc": lambda: O.allele_freq(data, 0), "missing_detector": lambda: O.missing(data, 0),
-              "nonref_filter": lambda: O.nonref_filter(data, 0), "indexer": lambda: O.indexer(data, 0), "phase_checker": lambda: O.phase_checker(data, 0), "allele_counter": lambda: O.allele_counter(data), "allele_counter -a": lambda: O.allele_counter(data, O.AC_UNIFIED, O.AC_AGGREGATE),
+              "nonref_filter": lambda: O.nonref_filter(data, 0), "indexer": lambda: O.indexer(data, 0), "phase_checker": lambda: O.phase_checker(data, 0), "inbreeding_calculator": lambda: O.inbreeding(data, 0, O.IB_QUIET), "allele_counter": lambda: O.allele_counter(data), "allele_counter -a": lambda: O.allele_counter(data, O.AC_UNIFIED, O.AC_AGGREGATE),
               "variant_counter": lambda: O.variant_count(data, 0)}[tname]
         exp = fn().out
         res.update({"against": "oracle port (reference binary not built on this box)", "equal": exp == got})

@@ -53,6 +53,10 @@ typedef enum {
     VCFX_OP_PHASE_CHECK    = 7,   /* VCFX_phase_checker.cpp:470-558 filterPhaseCheckedMmap, :563-650 processVCF; vcfx_cuda_short_lines
                                      then returns, per dropped line, (offset of the line in the chunk << 2 | reason): 0 unphased, 1 before
                                      the header, 2 fewer than ten columns, 3 no GT key */
+    VCFX_OP_INBREEDING     = 8,   /* VCFX_inbreeding_calculator.cpp:456-668 calculateInbreedingMmap, :670-826 calculateInbreedingStdin
+                                     (a sample-axis reduction): cfg.n_sel / sel_names / sel_name_off = the samples of the
+                                     "#CHROM" line in column order (sel_col is not used); the per-sample sums live in the context from
+                                     chunk to chunk and the text ("name \t F \n" per sample) comes with the chunk submitted as final */
     VCFX_OP_INDEX          = 6,   /* VCFX_indexer.cpp:205-322 createVCFIndexMmap, :329-443 createVCFIndex */
     VCFX_OP_NONREF_FILTER  = 5    /* VCFX_nonref_filter.cpp:458-548 filterNonRefMmap, :553-631 filterNonRef */
 } vcfx_op;
@@ -75,6 +79,9 @@ typedef enum {
 } vcfx_err;
 
 /* allele_counter variants (cfg.flags) */
+#define VCFX_F_IB_GLOBAL         0x01u  /* inbreeding_calculator --freq-mode global (:596-604)                 */
+#define VCFX_F_IB_SKIP_BOUNDARY  0x02u  /* --skip-boundary (:614-620)                                          */
+#define VCFX_F_IB_COUNT_BOUNDARY 0x04u  /* --count-boundary-as-used                                            */
 #define VCFX_F_AC_AGGREGATE   0x01u  /* -a: one row per variant (countAllelesUnified :1440-1461)          */
 #define VCFX_F_AC_BINARY      0x02u  /* -b: int8 {ref,alt} per selected sample (:1444-1449)               */
 #define VCFX_F_AC_FORWARD     0x04u  /* stdin / unified column walk: forward only, stop at the first absent

@@ -2,6 +2,7 @@
 the warp emulator in this directory.  TEST INFRASTRUCTURE ONLY — nothing under vcfx_b200/ knows this exists."""
 from __future__ import annotations
 
+import os
 import subprocess
 import sys
 from pathlib import Path
@@ -42,12 +43,14 @@ def build_tools(force: bool = False) -> Path:
         deps = [src, *common, *hdrs, so]
         if not force and exe.exists() and all(d.stat().st_mtime <= exe.stat().st_mtime for d in deps):
             continue
+        tmp = exe.with_name(f".{exe.name}.{os.getpid()}")          # (several test processes may build at once: link aside, rename)
         cmd = ["g++", "-O1", "-g", "-std=c++17", "-I", str(ROOT / "include"), "-I", str(tools_dir), str(src), *map(str, common),
-               "-o", str(exe), f"-L{so.parent}", "-lvcfx_emu", f"-Wl,-rpath,{so.parent}", "-lz", "-lpthread", "-ldl", "-lrt"]
+               "-o", str(tmp), f"-L{so.parent}", "-lvcfx_emu", f"-Wl,-rpath,{so.parent}", "-lz", "-lpthread", "-ldl", "-lrt"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
             raise RuntimeError("emulator tool build failed")
+        os.replace(tmp, exe)
     return out_dir
 
 

@@ -127,6 +127,43 @@ def test_phase_checker(files, tmp_path):
     assert a[2] == b[2]
 
 
+def test_inbreeding_calculator(files, tmp_path):
+    """VCFX_inbreeding_calculator: file (-i and positional) and stdin, every option, several chunks (the
+    per-sample sums are carried from chunk to chunk in file order), the quirks fixture, the fixed messages."""
+    import golden_util
+    q = tmp_path / "q.vcf"; q.write_bytes(golden_util.load()["ib_quirks"][0])
+    wide = tmp_path / "w.vcf"; wide.write_bytes(synth.make_vcf(3, 1500, 300, seed=21))
+    for p in (files["late"], files["crlf"], q, wide):
+        a, b = both("inbreeding_calculator", ["-q", "-i", str(p)])
+        assert a[2] == b[2]
+        a, b = both("inbreeding_calculator", ["-q"], stdin=p.read_bytes())
+        assert a[2] == b[2]
+    a, b = both("inbreeding_calculator", [str(q)])
+    assert a[2] == b[2]                                  # "Processing <file> (<n> bytes)..."
+    for args in (["--freq-mode", "global"], ["--skip-boundary"], ["--skip-boundary", "--count-boundary-as-used"], ["--freq-mode", "bogus"]):
+        a, b = both("inbreeding_calculator", ["-q", *args, "-i", str(q)])
+        assert a[2] == b[2]
+        both("inbreeding_calculator", ["-q", *args], stdin=wide.read_bytes(), env=SMALL_CHUNK)
+    both("inbreeding_calculator", ["-q", "-i", str(wide)], env=SMALL_CHUNK)
+    both("inbreeding_calculator", ["-q", "-i", str(files["c3"])], env={"VCFX_CHUNK_BYTES": str(wide.stat().st_size // 3)})
+    both("inbreeding_calculator", ["-q"], stdin=files["nonl"].read_bytes(), env={"VCFX_CHUNK_BYTES": "4096"})
+    multi = tmp_path / "m.vcf"                           # every site multi-allelic: "No biallelic variants found."
+    multi.write_bytes(b"##f\n#CHROM\tP\tI\tR\tA\tQ\tF\tI\tFORMAT\tA\tB\n1\t1\t.\tA\tG,T\t.\t.\t.\tGT\t0/1\t1/1\n")
+    a, b = both("inbreeding_calculator", [], stdin=multi.read_bytes())
+    assert a[2] == b[2]
+    hdr_only = tmp_path / "h.vcf"; hdr_only.write_bytes(b"##f\n#CHROM\tP\tI\tR\tA\tQ\tF\tI\tFORMAT\tA\tB\n")
+    for p in (hdr_only,):
+        a, b = both("inbreeding_calculator", ["-q", "-i", str(p)])
+        assert a[2] == b[2]
+        a, b = both("inbreeding_calculator", ["-q"], stdin=p.read_bytes())
+        assert a[2] == b[2]
+    nohdr = tmp_path / "n.vcf"; nohdr.write_bytes(b"##f\n1\t1\t.\tA\tG\t.\t.\t.\tGT\t0/1\t1/1\n")
+    a, b = both("inbreeding_calculator", ["-q", "-i", str(nohdr)])
+    assert a[2] == b[2]
+    a, b = both("inbreeding_calculator", ["-q"], stdin=nohdr.read_bytes())
+    assert a[2] == b[2]
+
+
 def test_indexer(files, tmp_path):
     """VCFX_indexer: file argument and stdin, several chunks (offsets stay absolute), the quirks fixture."""
     import golden_util
@@ -141,7 +178,7 @@ def test_indexer(files, tmp_path):
     both("indexer", [], stdin=files["nonl"].read_bytes(), env={"VCFX_CHUNK_BYTES": "4096"})
 
 
-@pytest.mark.parametrize("tool", ["allele_freq_calc", "hwe_tester", "missing_detector", "variant_counter", "allele_counter", "nonref_filter", "indexer", "phase_checker"])
+@pytest.mark.parametrize("tool", ["allele_freq_calc", "hwe_tester", "missing_detector", "variant_counter", "allele_counter", "nonref_filter", "indexer", "phase_checker", "inbreeding_calculator"])
 def test_flags(tool, files):
     for args in (["--help"], ["-v"]):
         both(tool, args)

@@ -20,7 +20,7 @@ def _cmp(name, got, exp):
                              f"  got {got[max(0, i - 60): i + 60]!r}\n  exp {exp[max(0, i - 60): i + 60]!r}")
 
 
-def run_all(api, O, data, tag, chunk_bytes=0, tile_bytes=0, tools=("af", "hwe", "vc", "md", "nr", "ix", "pc")):
+def run_all(api, O, data, tag, chunk_bytes=0, tile_bytes=0, tools=("af", "hwe", "vc", "md", "nr", "ix", "pc", "ib")):
     kw = dict(chunk_bytes=chunk_bytes, tile_bytes=tile_bytes)
     for mode in MODES:
         if "af" in tools:
@@ -51,6 +51,13 @@ def run_all(api, O, data, tag, chunk_bytes=0, tile_bytes=0, tools=("af", "hwe", 
             _cmp(f"{tag} pc mode{mode}", r.out, o.out)
             _cmp(f"{tag} pc mode{mode} stderr", r.err, O.phase_checker_stderr(data, mode))
             assert (r.totals.rows, r.totals.pre_header, r.totals.flagged) == (o.rows, o.warnings, o.flagged + o.warnings)
+        if "ib" in tools:
+            for fl in ((0, 6) if mode == 0 else (0, 1)):
+                r = api.inbreeding_calculator(data, mode, bool(fl & 1), bool(fl & 2), bool(fl & 4), quiet=False, **kw); o = O.inbreeding(data, mode, fl)
+                _cmp(f"{tag} ib mode{mode} flags{fl}", r.out, o.out)
+                assert r.err == O.IB_MESSAGES[o.warnings]
+                if o.warnings in (0, 3):
+                    assert r.totals.rows == o.rows
         if "vc" in tools:
             for strict in (False, True):
                 r = api.variant_counter(data, mode, strict, **kw); o = O.variant_count(data, mode, strict)
@@ -407,6 +414,41 @@ def test_phase_checker_more_dropped_lines_than_the_event_list(cuda_api, oracle):
     o = oracle.phase_checker(data, 0)
     assert r.out == o.out and r.totals.flagged == n
     assert r.err == b"Warning: Invalid VCF line with fewer than 10 columns; skipping line.\n" * n
+
+
+def test_inbreeding_calculator_cases(cuda_api, oracle):
+    """VCFX_inbreeding_calculator: what a genotype code is, lines with fewer columns than samples (the file mode takes the code
+    of the last line that had the column), multi-allelic / empty ALT, two "#CHROM" lines, every option; sums that need the
+    sites in file order (thousands of sites, hundreds of samples, several chunks and tiny tiles); two streams through one
+    context one after the other."""
+    import golden_util
+    data, _ = golden_util.load()["ib_quirks"]
+    for kw in ({}, {"tile_bytes": 512}, {"chunk_bytes": 4096}):
+        for mode in MODES:
+            for fl in range(8):
+                r = cuda_api.inbreeding_calculator(data, mode, bool(fl & 1), bool(fl & 2), bool(fl & 4), quiet=False, **kw)
+                o = oracle.inbreeding(data, mode, fl)
+                _cmp(f"ib quirks {kw} mode{mode} flags{fl}", r.out, o.out)
+                assert r.err == oracle.IB_MESSAGES[o.warnings]
+    for shape, V, S in ((2, 3000, 300), (3, 2000, 257), (4, 300, 64), (2, 40, 2504)):
+        data = synth.make_vcf(shape, V, S, seed=40 + shape)
+        run_all(cuda_api, oracle, data, f"ib shape{shape}", tools=("ib",))
+        run_all(cuda_api, oracle, data, f"ib shape{shape} chunks", chunk_bytes=1 << 20 if S > 1000 else 64 << 10, tools=("ib",))
+    run_all(cuda_api, oracle, synth.make_vcf(3, 400, 100, seed=77), "ib tile512", tile_bytes=512, tools=("ib",))
+    # a context is good for one stream after the other: the sums start again behind a final chunk
+    a = synth.make_vcf(3, 200, 20, seed=5); b = synth.make_vcf(2, 150, 20, seed=6)
+    names = [b"S%d" % i for i in range(20)]
+
+    def body(d):
+        return d[cuda_api._ib_header(d, 0)[1]:]
+    ctx = cuda_api.Context(cuda_api.OP_INBREEDING, cuda_api.FILE, chunk_bytes=1 << 20, sel_cols=list(range(20)), sel_names=names)
+    for d in (a, b, a):
+        outs, _ = cuda_api.stream_bytes(ctx, body(d), 16 << 10)
+        exp = oracle.inbreeding(d, 0, 0).out
+        got = cuda_api.IB_HEADER + b"".join(outs)
+        # (the names of the synthetic header are not S0..S19: compare the numbers)
+        assert [l.split(b"\t")[1] for l in got.splitlines()[1:]] == [l.split(b"\t")[1] for l in exp.splitlines()[1:]]
+    ctx.close()
 
 
 def test_allele_counter_two_digit_counts(cuda_api, oracle):

@@ -38,6 +38,12 @@ def check_case(O, data, exp, name):
             assert (r.rc, r.out) == exp[key][:2], (name, key)
             if not strict:
                 assert r.warnings == exp[key][2], (name, key)
+    for key, mode, flags in (("file", O.FILE, 0), ("stdin", O.STDIN, 0), ("file.global", O.FILE, O.IB_GLOBAL),
+                             ("file.skipcount", O.FILE, O.IB_SKIP_BOUNDARY | O.IB_COUNT_BOUNDARY), ("stdin.skip", O.STDIN, O.IB_SKIP_BOUNDARY)):
+        k = f"inbreeding_calculator.{key}"
+        if k in exp:
+            r = O.inbreeding(data, mode, flags | O.IB_QUIET)
+            assert (r.rc, r.out, O.IB_MESSAGES[r.warnings]) == tuple(exp[k][:3]), (name, k)
     for key, (path, fmt, limit) in {"mt": (O.AC_MT_TEXT, O.AC_TEXT, 0), "stream": (O.AC_STREAM, O.AC_TEXT, 0),
                                     "agg": (O.AC_UNIFIED, O.AC_AGGREGATE, 0), "bin": (O.AC_UNIFIED, O.AC_BINARY, 0),
                                     "limit2": (O.AC_UNIFIED, O.AC_TEXT, 2)}.items():
@@ -92,6 +98,12 @@ def test_oracle_matches_reference_binaries_fuzz(oracle, seed):
         assert (r.rc, r.out, O.phase_checker_stderr(data, O.STDIN)) == (rc, out, err), "phase_checker stdin"
         rc, out, err = O.run_ref("phase_checker", ["-q"], stdin=data)
         assert (rc, out, err) == (r.rc, r.out, b""), "phase_checker -q"
+        for flags, args in ((0, []), (O.IB_GLOBAL, ["--freq-mode", "global"]), (O.IB_SKIP_BOUNDARY, ["--skip-boundary"]),
+                            (O.IB_SKIP_BOUNDARY | O.IB_COUNT_BOUNDARY, ["--skip-boundary", "--count-boundary-as-used"])):
+            rc, out, err = O.run_ref("inbreeding_calculator", ["-q", *args, "-i", f.name]); r = O.inbreeding(data, O.FILE, flags | O.IB_QUIET)
+            assert (r.rc, r.out, O.IB_MESSAGES[r.warnings]) == (rc, out, err), ("inbreeding_calculator file", args)
+            rc, out, err = O.run_ref("inbreeding_calculator", ["-q", *args], stdin=data); r = O.inbreeding(data, O.STDIN, flags | O.IB_QUIET)
+            assert (r.rc, r.out, O.IB_MESSAGES[r.warnings]) == (rc, out, err), ("inbreeding_calculator stdin", args)
         for strict in (False, True):
             a = ["--strict"] if strict else []
             rc, out, err = O.run_ref("variant_counter", [*a, f.name]); r = O.variant_count(data, O.FILE, strict)
@@ -124,6 +136,8 @@ def test_oracle_matches_reference_binaries_shapes(oracle):
             assert O.variant_count(data).out == out
             rc, out, _ = O.run_ref("nonref_filter", ["-i", f.name], timeout=60)
             assert O.nonref_filter(data, O.FILE).out == out, (shape, "nonref_filter")
+            rc, out, err = O.run_ref("inbreeding_calculator", ["-q", "-i", f.name], timeout=60)
+            assert O.inbreeding(data, O.FILE, O.IB_QUIET).out == out, (shape, "inbreeding_calculator")
             rc, out, err = O.run_ref("phase_checker", ["-i", f.name], timeout=60)
             assert (O.phase_checker(data, O.FILE).out, O.phase_checker_stderr(data, O.FILE)) == (out, err), (shape, "phase_checker")
 

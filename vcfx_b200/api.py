@@ -17,7 +17,7 @@ from pathlib import Path
 
 from . import build as _build
 
-OP_VARIANT_COUNT, OP_ALLELE_FREQ, OP_HWE, OP_MISSING_DETECT, OP_ALLELE_COUNT, OP_NONREF_FILTER, OP_INDEX, OP_PHASE_CHECK = range(8)
+OP_VARIANT_COUNT, OP_ALLELE_FREQ, OP_HWE, OP_MISSING_DETECT, OP_ALLELE_COUNT, OP_NONREF_FILTER, OP_INDEX, OP_PHASE_CHECK, OP_INBREEDING = range(9)
 FILE, STDIN = 0, 1
 F_AC_AGGREGATE, F_AC_BINARY, F_AC_FORWARD = 1, 2, 4
 DEVICE_PAD = 8192
@@ -480,6 +480,75 @@ def nonref_filter(data: bytes, mode: int = FILE, chunk_bytes: int = 0, **kw) -> 
     totals.pre_header = data lines in front of the header (each prints a warning), totals.flagged = lines dropped."""
     body, tot = _run(OP_NONREF_FILTER, data, mode, chunk_bytes, **kw)
     return ToolResult(body, 0, tot)
+
+
+F_IB_GLOBAL, F_IB_SKIP_BOUNDARY, F_IB_COUNT_BOUNDARY = 1, 2, 4
+IB_HEADER = b"Sample\tInbreedingCoefficient\n"                    # VCFX_inbreeding_calculator.cpp:639
+IB_MESSAGES = {0: b"", 1: b"Error: Empty file.\n", 2: b"Error: No #CHROM line or no samples found.\n", 3: b"No biallelic variants found.\n",
+               4: b"Error: No #CHROM line found.\n", 5: b"Error: No sample columns found.\n"}
+
+
+def _ib_header(data: bytes, mode: int):
+    """(sample names or None when no "#CHROM" line was found, offset the data lines start at).  File mode: the leading block
+    of '#' and empty lines; EVERY line in it that starts with "#CHROM" adds its columns 10.. (VCFX_inbreeding_calculator.cpp
+    :474-513).  Stdin mode: the first '#' line that contains "#CHROM" anywhere; lines in front of it do not count (:689-706)."""
+    names, found, pos, n = [], False, 0, len(data)
+    while pos < n:
+        nl = data.find(b"\n", pos)
+        le = n if nl < 0 else nl
+        line = data[pos:le]
+        if line.endswith(b"\r"):
+            line = line[:-1]
+        nxt = le + 1
+        if mode == FILE:
+            if line:
+                if not line.startswith(b"#"):
+                    return (names if found else None), pos
+                if line.startswith(b"#CHROM"):
+                    found = True
+                    f = line.split(b"\t")
+                    if f and f[-1] == b"":                 # nothing is read behind a final tab
+                        f = f[:-1]
+                    names += f[9:]
+        elif line.startswith(b"#") and b"#CHROM" in line:
+            return line.split(b"\t")[9:], nxt
+        pos = nxt
+    return (names if found else None), n
+
+
+def inbreeding_calculator(data: bytes, mode: int = FILE, freq_global: bool = False, skip_boundary: bool = False,
+                          count_boundary: bool = False, quiet: bool = True, chunk_bytes: int = 0, **kw) -> ToolResult:
+    """VCFX_inbreeding_calculator: per-sample F = 1 - observed / expected heterozygotes over the biallelic sites, the
+    expectation summed in file order (calculateInbreedingMmap :456-668, calculateInbreedingStdin :670-826).  The scan leaves
+    a genotype code per sample column, a second pass walks the sites in order with one thread per sample; the state lives
+    in the context from chunk to chunk and the text arrives with the final chunk.  ``err`` = what goes to stderr,
+    totals.rows = sites used."""
+    if mode == FILE and len(data) == 0:
+        return ToolResult(IB_HEADER, 0, Totals(), IB_MESSAGES[1])
+    names, start = _ib_header(data, mode)
+    if mode == FILE and not names:
+        return ToolResult(IB_HEADER, 0, Totals(), IB_MESSAGES[2])
+    if mode == STDIN and names is None:
+        return ToolResult(IB_HEADER, 0, Totals(), IB_MESSAGES[4])
+    if mode == STDIN and not names:
+        return ToolResult(IB_HEADER, 0, Totals(), IB_MESSAGES[5])
+    flags = (F_IB_GLOBAL if freq_global else 0) | (F_IB_SKIP_BOUNDARY if skip_boundary else 0) | (F_IB_COUNT_BOUNDARY if count_boundary else 0)
+    body = data[start:]
+    chunk_bytes = chunk_bytes or min(64 << 20, max(1 << 20, (len(body) + (1 << 20) - 1) & ~((1 << 20) - 1)))
+    ctx = Context(OP_INBREEDING, mode, flags=flags, chunk_bytes=chunk_bytes, sel_cols=list(range(len(names))), sel_names=names, **kw)
+    try:
+        if len(body) == 0:                                 # no data line at all: a final chunk of nothing still reports
+            buf, cap = ctx.acquire()
+            ctx.submit(0, is_final=True)
+            out, st, _ = ctx.next_output()
+            tot = Totals(); tot.add(st, 0, [])
+            outs = [out]
+        else:
+            outs, tot = stream_bytes(ctx, body, chunk_bytes, 0)
+    finally:
+        ctx.close()
+    err = IB_MESSAGES[3] if (tot.rows == 0 and not quiet) else b""
+    return ToolResult(IB_HEADER + b"".join(outs), 0, tot, err)
 
 
 PC_UNPHASED, PC_PRE_HEADER, PC_SHORT, PC_NO_GT = range(4)      # why VCFX_OP_PHASE_CHECK dropped a line (event & 3)

@@ -42,6 +42,10 @@ struct Work {                      // device-side bookkeeping for one launch
     DevStats *d_stats = nullptr;
     unsigned long long *events = nullptr;
     uint32_t ev_cap = 0;                 // entries in events (phase_checker grows it when a chunk drops more lines)
+    // inbreeding_calculator: a code per sample column (as many bytes as the chunk), the rows in file order, the chunk's place in the order
+    uint8_t *ib_codes = nullptr; size_t ib_codes_cap = 0;
+    IbRow *ib_rows = nullptr; uint64_t ib_rows_cap = 0;
+    unsigned long long ib_seq = 0; bool ib_first = false;
     DevStats *h_stats = nullptr;   // pinned: results of the last launch
     DevStats *h_init = nullptr;    // pinned: constant initial value uploaded before every launch
     uint32_t tiles_cap = 0;
@@ -104,6 +108,12 @@ struct vcfx_ctx {
     int ac_fmt = 0;
     bool ac_ident = false;               // allele_counter selection = columns 0 .. n_sel-1 in order
     bool ac_exact = false;               // a chunk had a count of two digits: rows are sized by parsing from now on
+    // inbreeding_calculator: the per-sample state that lives from chunk to chunk, and the order the chunks are applied in
+    IbState *d_ib = nullptr; double *d_ib_sum = nullptr; unsigned long long *d_ib_het = nullptr; unsigned int *d_ib_used = nullptr; uint8_t *d_ib_last = nullptr;
+    cudaEvent_t ib_event = nullptr;      // the last chunk launched has been applied
+    bool ib_event_set = false;
+    unsigned long long ib_next_seq = 0;
+    bool ib_open = false;                // a stream is under way (its final chunk has not been submitted yet)
     // last drained chunk's short-line list
     std::vector<uint64_t> last_events;
     uint64_t last_n_events = 0;
@@ -140,6 +150,7 @@ kernel_fn kernel_for(int op) {
     case VCFX_OP_NONREF_FILTER: return vcfx_scan_kernel<OP_NR, 0>;
     case VCFX_OP_INDEX: return vcfx_scan_kernel<OP_IX, 0>;
     case VCFX_OP_PHASE_CHECK: return vcfx_scan_kernel<OP_PC, 0>;
+    case VCFX_OP_INBREEDING: return vcfx_scan_kernel<OP_IB, 0>;
     case VCFX_OP_ALLELE_COUNT:  return vcfx_scan_kernel<OP_AC, 0>;
     default: return nullptr;
     }
@@ -161,6 +172,7 @@ kernel_fn format_kernel_for(int op, int ac_fmt = 0) {
     case VCFX_OP_NONREF_FILTER: return md_copy_kernel;
     case VCFX_OP_PHASE_CHECK: return md_copy_kernel;
     case VCFX_OP_INDEX: return format_rows_kernel<OP_IX>;
+    case VCFX_OP_INBREEDING: return ib_rows_kernel;
     default: return nullptr;
     }
 }
@@ -231,6 +243,7 @@ void free_work(Work &w) {
     cudaFree(w.tile_lines); cudaFree(w.tile_out); cudaFree(w.tile_base); cudaFree(w.line_base);
     cudaFree(w.rec_prefix); cudaFree(w.ticket); cudaFree(w.recs); cudaFree(w.d_stats); cudaFree(w.events);
     cudaFree(w.tail_start); cudaFree(w.tail_len); cudaFree(w.tail_off); cudaFree(w.col_scratch); cudaFree(w.tile_resume);
+    cudaFree(w.ib_codes); cudaFree(w.ib_rows);
     if (w.h_stats) cudaFreeHost(w.h_stats);
     if (w.h_init) cudaFreeHost(w.h_init);
     if (w.ev_k0) cudaEventDestroy(w.ev_k0);
@@ -281,6 +294,19 @@ int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes, uint64_t min_recs = 0)
         size_t n = (size_t)ctx->sm_count * ctx->blocks_per_sm * WARPS_PER_CTA * std::max<uint32_t>(ctx->max_col, 1);
         CU(cudaMalloc(&w.col_scratch, n * sizeof(uint2)));
     }
+    if (ctx->cfg.op == VCFX_OP_INBREEDING) {
+        if (max_bytes + VCFX_DEVICE_PAD > w.ib_codes_cap) {
+            cudaFree(w.ib_codes); w.ib_codes = nullptr; w.ib_codes_cap = 0;
+            CU(cudaMalloc(&w.ib_codes, max_bytes + VCFX_DEVICE_PAD));
+            w.ib_codes_cap = max_bytes + VCFX_DEVICE_PAD;
+        }
+        if (std::max<uint64_t>(recs, w.rec_cap) > w.ib_rows_cap) {
+            const uint64_t want = std::max<uint64_t>(recs, w.rec_cap);
+            cudaFree(w.ib_rows); w.ib_rows = nullptr; w.ib_rows_cap = 0;
+            CU(cudaMalloc(&w.ib_rows, want * sizeof(IbRow)));
+            w.ib_rows_cap = want;
+        }
+    }
     if (recs > w.rec_cap) {
         cudaFree(w.recs); w.recs = nullptr; w.rec_cap = 0;
         cudaFree(w.rec_prefix); w.rec_prefix = nullptr;
@@ -289,6 +315,15 @@ int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes, uint64_t min_recs = 0)
         w.rec_cap = recs;
     }
     return VCFX_OK;
+}
+
+// inbreeding_calculator: a NEW chunk takes the next place in the order its context applies chunks in (a chunk that is run
+// again keeps its place); the first chunk behind a final one starts a new stream
+void ib_begin(vcfx_ctx *ctx, Work &w, const vcfx_chunk_info *info) {
+    if (ctx->cfg.op != VCFX_OP_INBREEDING) return;
+    w.ib_seq = ctx->ib_next_seq++;
+    w.ib_first = !ctx->ib_open;
+    ctx->ib_open = !(info ? info->is_final != 0 : true);
 }
 
 // enqueue the kernels of one chunk on `st`; results land in w.h_stats after the stream drains
@@ -318,6 +353,8 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
     P.ac_fmt = ctx->ac_fmt; P.ac_ident = ctx->ac_ident ? 1 : 0; P.ac_pass = 0; P.ac_spec = (ctx->cfg.op == VCFX_OP_ALLELE_COUNT && ctx->ac_fmt == AC_TEXT_MT && !ctx->ac_exact) ? 1 : 0; P.n_sel = ctx->n_sel; P.sel_col = ctx->d_sel_col; P.name_off = ctx->d_name_off;
     P.names = ctx->d_names; P.names16 = ctx->d_names16; P.name_len = ctx->name_len; P.ac_bulk = ctx->ac_bulk ? 1 : 0; P.max_col = ctx->max_col; P.col_scratch = w.col_scratch;
     P.ticket = w.ticket; P.ticket2 = w.ticket + 1; P.tile_resume = w.tile_resume; P.recs = w.recs; P.rec_prefix = w.rec_prefix; P.rec_cap = w.rec_cap;
+    P.ib_codes = w.ib_codes; P.ib_rows = w.ib_rows; P.ib = ctx->d_ib; P.ib_seq = w.ib_seq; P.ib_first = w.ib_first ? 1 : 0; P.text_cap = out_cap;
+    if (ctx->cfg.op == VCFX_OP_INBREEDING) P.out_cap = ~0ULL;       // the scan counts rows there, not bytes of text
     P.stats = w.d_stats; P.events = w.events; P.ev_cap = w.ev_cap; P.ev_raw = (ctx->cfg.op == VCFX_OP_PHASE_CHECK) ? 1 : 0;
 
     CU(cudaEventRecord(w.ev_k0, st));
@@ -342,6 +379,16 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
             VCFX_LAUNCH(fn, grid, WARPS_PER_CTA * 32, 0, st, P);
             CU(cudaGetLastError());
         }
+    }
+    if (ctx->cfg.op == VCFX_OP_INBREEDING) {
+        // the sample-axis pass: chunks are applied one after the other, whatever stream they were scanned on
+        if (ctx->ib_event_set) CU(cudaStreamWaitEvent(st, ctx->ib_event, 0));
+        VCFX_LAUNCH(ib_accumulate_kernel, (int)((ctx->n_sel + 63) / 64), 64, 0, st, P);   // (an empty chunk still opens or closes a stream)
+        CU(cudaGetLastError());
+        VCFX_LAUNCH(ib_finish_kernel, 1, 1024, 0, st, P);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ib_event, st));
+        ctx->ib_event_set = true;
     }
     CU(cudaEventRecord(w.ev_k1, st));
     CU(cudaMemcpyAsync(w.h_stats, w.d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, st));
@@ -392,6 +439,7 @@ size_t default_out_bytes(int op, unsigned flags, size_t chunk) {
     case VCFX_OP_MISSING_DETECT: return chunk + chunk / 4 + 4096;
     case VCFX_OP_NONREF_FILTER: return chunk + 4096;          // never longer than the input plus one '\n'
     case VCFX_OP_PHASE_CHECK: return chunk + 4096;
+    case VCFX_OP_INBREEDING: return 1u << 20;                 // create() sizes it from the names
     case VCFX_OP_ALLELE_COUNT:
         if (flags & VCFX_F_AC_AGGREGATE) return chunk / 4 + (1u << 20);
         if (flags & VCFX_F_AC_BINARY) return chunk + 4096;
@@ -447,7 +495,7 @@ const char *vcfx_cuda_last_error(const vcfx_ctx *ctx) { return ctx ? ctx->last_e
 int vcfx_cuda_create(const vcfx_cfg *cfg, vcfx_ctx **out) {
     if (!cfg || !out) return VCFX_E_INVALID;
     *out = nullptr;
-    if (cfg->op < VCFX_OP_VARIANT_COUNT || cfg->op > VCFX_OP_PHASE_CHECK) return VCFX_E_INVALID;
+    if (cfg->op < VCFX_OP_VARIANT_COUNT || cfg->op > VCFX_OP_INBREEDING) return VCFX_E_INVALID;
     if (cfg->mode != VCFX_MODE_FILE && cfg->mode != VCFX_MODE_STDIN) return VCFX_E_INVALID;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return VCFX_E_NO_DEVICE;
@@ -510,6 +558,25 @@ int vcfx_cuda_create(const vcfx_cfg *cfg, vcfx_ctx **out) {
             ctx->ac_bulk = !(be && *be == '0');
         }
     }
+    if (cfg->op == VCFX_OP_INBREEDING) {
+        // the samples of the "#CHROM" line, in column order: names as for allele_counter (each followed by a tab)
+        if (cfg->n_sel == 0 || !cfg->sel_names || !cfg->sel_name_off) return fail(VCFX_E_INVALID);
+        ctx->n_sel = cfg->n_sel;
+        const size_t nb = cfg->sel_name_off[cfg->n_sel];
+        CUC(cudaMalloc(&ctx->d_name_off, sizeof(uint32_t) * (cfg->n_sel + 1)));
+        CUC(cudaMalloc(&ctx->d_names, nb + 16));
+        CUC(cudaMemcpy(ctx->d_name_off, cfg->sel_name_off, sizeof(uint32_t) * (cfg->n_sel + 1), cudaMemcpyHostToDevice));
+        CUC(cudaMemcpy(ctx->d_names, cfg->sel_names, nb, cudaMemcpyHostToDevice));
+        CUC(cudaMalloc(&ctx->d_ib_sum, sizeof(double) * cfg->n_sel));
+        CUC(cudaMalloc(&ctx->d_ib_het, sizeof(unsigned long long) * cfg->n_sel));
+        CUC(cudaMalloc(&ctx->d_ib_used, sizeof(unsigned int) * cfg->n_sel));
+        CUC(cudaMalloc(&ctx->d_ib_last, cfg->n_sel));
+        CUC(cudaMalloc(&ctx->d_ib, sizeof(IbState)));
+        IbState st0; st0.seq = 0; st0.variants = 0; st0.sum = ctx->d_ib_sum; st0.het = ctx->d_ib_het; st0.used = ctx->d_ib_used; st0.last = ctx->d_ib_last;
+        CUC(cudaMemcpy(ctx->d_ib, &st0, sizeof st0, cudaMemcpyHostToDevice));
+        CUC(cudaEventCreateWithFlags(&ctx->ib_event, cudaEventDisableTiming));
+        if (!cfg->out_bytes) ctx->out_bytes = nb + (size_t)cfg->n_sel * 48 + 4096;      // "name \t F \n" per sample
+    }
     if (cfg->stream) { ctx->dev_stream = (cudaStream_t)cfg->stream; ctx->dev_stream_owned = false; }
     else { CUC(cudaStreamCreateWithFlags(&ctx->dev_stream, cudaStreamNonBlocking)); ctx->dev_stream_owned = true; }
 #undef CUC
@@ -535,6 +602,8 @@ void vcfx_cuda_destroy(vcfx_ctx *ctx) {
     free_work(ctx->dev_work);
     if (ctx->dev_stream_owned && ctx->dev_stream) cudaStreamDestroy(ctx->dev_stream);
     cudaFree(ctx->d_sel_col); cudaFree(ctx->d_name_off); cudaFree(ctx->d_names); cudaFree(ctx->d_names16);
+    cudaFree(ctx->d_ib); cudaFree(ctx->d_ib_sum); cudaFree(ctx->d_ib_het); cudaFree(ctx->d_ib_used); cudaFree(ctx->d_ib_last);
+    if (ctx->ib_event) cudaEventDestroy(ctx->ib_event);
     delete ctx;
 }
 
@@ -630,6 +699,7 @@ int vcfx_cuda_submit(vcfx_ctx *ctx, size_t nbytes, const vcfx_chunk_info *info) 
     CU(cudaEventRecord(s.ev_h2d, s.stream));
     s.d_in_used = s.d_in;
     if (info) s.info = *info; else s.info = vcfx_chunk_info{0, 1, 0, 0, 0};
+    ib_begin(ctx, s.w, &s.info);
     int rc = launch_chunk(ctx, s.w, s.stream, s.d_in, nbytes, &s.info, s.d_out, s.out_cap, false);
     if (rc != VCFX_OK) return rc;
     s.nbytes = nbytes; s.in_flight = true; s.d2h_issued = false;
@@ -654,6 +724,7 @@ int vcfx_cuda_submit_host(vcfx_ctx *ctx, const void *host, size_t nbytes, const 
     CU(cudaEventRecord(s.ev_h2d, s.stream));
     s.d_in_used = s.d_in;
     if (info) s.info = *info; else s.info = vcfx_chunk_info{0, 1, 0, 0, 0};
+    ib_begin(ctx, s.w, &s.info);
     rc = launch_chunk(ctx, s.w, s.stream, s.d_in, nbytes, &s.info, s.d_out, s.out_cap, false);
     if (rc != VCFX_OK) return rc;
     s.nbytes = nbytes; s.in_flight = true; s.d2h_issued = false;
@@ -692,6 +763,7 @@ int vcfx_cuda_submit_shared(vcfx_ctx *ctx, vcfx_ctx *primary, const vcfx_chunk_i
         ps.shared_pending = true;
     }
     s.d_in_used = own_copy ? s.d_in : ps.d_in;
+    ib_begin(ctx, s.w, &s.info);
     rc = launch_chunk(ctx, s.w, s.stream, s.d_in_used, ps.nbytes, &s.info, s.d_out, s.out_cap, false);
     if (rc != VCFX_OK) return rc;
     if (!own_copy) {
@@ -772,6 +844,7 @@ int vcfx_cuda_run_device(vcfx_ctx *ctx, void *d_in, size_t nbytes, const vcfx_ch
     if (rc != VCFX_OK) return rc;
     ctx->dev_info = info ? *info : vcfx_chunk_info{0, 1, 0, 0, 0};
     ctx->dev_in = (uint8_t *)d_in; ctx->dev_out = (uint8_t *)d_out; ctx->dev_out_cap = out_cap;
+    ib_begin(ctx, ctx->dev_work, &ctx->dev_info);
     rc = launch_chunk(ctx, ctx->dev_work, ctx->dev_stream, ctx->dev_in, nbytes, &ctx->dev_info, ctx->dev_out, out_cap);
     if (rc != VCFX_OK) return rc;
     ctx->dev_pending = true; ctx->dev_nbytes = nbytes;
@@ -786,7 +859,7 @@ int vcfx_cuda_sync(vcfx_ctx *ctx, vcfx_chunk_stats *stats) {
     ctx->dev_pending = false;
     const int grew = grow_events(ctx, ctx->dev_work);
     if (grew < 0) return grew;
-    if ((ctx->dev_work.h_stats->overflow & 5) || grew) {      // more rows than sized for / speculative row sizes off / more events: run again
+    if ((ctx->dev_work.h_stats->overflow & 13) || grew) {      // more rows than sized for / speculative row sizes off / more events: run again
         if (ctx->dev_work.h_stats->overflow & 4) ctx->ac_exact = true;
         int rc2 = ensure_work(ctx, ctx->dev_work, ctx->dev_nbytes, ctx->dev_work.h_stats->n_recs + rec_slack(ctx));
         if (rc2 != VCFX_OK) return rc2;

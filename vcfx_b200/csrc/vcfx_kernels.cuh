@@ -36,7 +36,7 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int WARPS_PER_CTA = 8;
 constexpr uint32_t WINDOW = 512;
 
-enum : int { OP_VC = 0, OP_AF = 1, OP_HWE = 2, OP_MD = 3, OP_AC = 4, OP_NR = 5, OP_IX = 6, OP_PC = 7 };
+enum : int { OP_VC = 0, OP_AF = 1, OP_HWE = 2, OP_MD = 3, OP_AC = 4, OP_NR = 5, OP_IX = 6, OP_PC = 7, OP_IB = 8 };
 constexpr uint32_t NR_PLAIN = 0xFFFFFFFFu;     // Rec::b of a nonref_filter record: the line is written as its content + '\n' (or not at all)
 enum : int { MODE_FILE = 0, MODE_STDIN = 1 };
 enum : int { AC_TEXT_MT = 0, AC_TEXT_FWD = 1, AC_AGG = 2, AC_BIN = 3 };
@@ -49,6 +49,24 @@ struct Rec {                 // one output row (32 B)
     uint32_t off_in_tile;    // output offset of this row inside its tile's output
     uint32_t a, b, c, d;     // op-specific integers (AF: alt,total; HWE: homRef,het,homAlt)
 };
+
+// inbreeding_calculator: one row per line whose genotypes were looked at, in file order
+struct IbRow {
+    unsigned long long code_off;  // ib_codes index of the line's first sample column
+    uint32_t ncols;               // sample columns the line has (at most the number of samples)
+    uint32_t flags;               // bits 2c, 2c+1: what a sample with code c does here (0 nothing, 1 counted only, 2 counted and summed); bit 8: a used site
+    double e[3];                  // expected heterozygosity 2 f (1 - f) of a sample with code 0, 1, 2
+};
+struct IbState {
+    unsigned long long seq;       // chunks accumulated so far
+    unsigned long long variants;  // used sites of the stream so far
+    double *sum;                  // [S] expected heterozygotes, summed in file order
+    unsigned long long *het;      // [S] observed heterozygotes
+    unsigned int *used;           // [S] sites counted
+    uint8_t *last;                // [S] code of the last line that had the column (the reference reuses its code buffer)
+};
+constexpr uint32_t IB_NONE = 3, IB_ABSENT = 4;
+constexpr uint32_t IB_F_GLOBAL = 1, IB_F_SKIP_BOUNDARY = 2, IB_F_COUNT_BOUNDARY = 4;      // = VCFX_F_IB_* of the header
 
 constexpr unsigned int REC_BLOCK = 32;          // row-record slots a warp reserves at a time
 constexpr uint32_t RESUME_DONE = 0xFFFFFFFFu;
@@ -116,6 +134,13 @@ struct KParams {
     unsigned long long *events;      // short-line events (tile << 32 | index in tile)
     uint32_t ev_cap;
     unsigned long long fmt0_until;   // phase_checker, file mode: an empty FORMAT column of a line starting below this offset means GT index 0
+    // INBREEDING (sample-axis reduction): the scan leaves one code per sample column, a second pass walks the rows in file order
+    uint8_t *ib_codes;               // [n + pad] code of sample column j of the line starting at byte L: ib_codes[L + j] (0, 1, 2, IB_NONE, IB_ABSENT)
+    IbRow *ib_rows;                  // [rec_cap] the chunk's rows in file order (ib_rows_kernel)
+    IbState *ib;                     // what lives from chunk to chunk: per-sample sums, the last code of every column, the order guard
+    unsigned long long ib_seq;       // number of this chunk in its context (chunks are accumulated strictly in this order)
+    int32_t ib_first;                // first chunk of a stream: the per-sample state starts from zero
+    uint64_t text_cap;               // bytes the final text may take in out (out_cap is not compared with the row count)
     int32_t ev_raw;                  // 1: events are final values (phase_checker: line offset << 2 | kind), not (tile, index) keys
 };
 
@@ -317,6 +342,25 @@ __device__ __noinline__ bool pc_sample_phased(const uint8_t *p, bool file_mode, 
     const uint32_t al = (uint32_t)(ge - as);
     if (al == 0 || (al == 1 && ldb(as) == '.')) return false;
     return pipe;
+}
+
+// VCFX_inbreeding_calculator.cpp:296-339 parseGenotypeCode on the sample column starting at p: blanks and '\r' in front are
+// skipped, then digits, '/' or '|', digits — nothing behind them is looked at (a ':' only ends the genotype, and everything
+// that ends it is neither a digit nor a separator) — both alleles 0 or 1: 0, 1, 2; anything else IB_NONE.  A column that
+// starts at the line end (after a '\r' in front of the '\n' was cut) does not exist: IB_ABSENT.
+__device__ __noinline__ uint32_t ib_sample_code(const uint8_t *p) {
+    uint32_t c = ldb(p);
+    if (c == '\n' || (c == '\r' && ldb(p + 1) == '\n')) return IB_ABSENT;
+    while (c == ' ' || c == '\r') { ++p; c = ldb(p); }
+    if (c - '0' > 9u) return IB_NONE;
+    uint32_t a1 = 0, a2 = 0;
+    while (c - '0' <= 9u) { a1 = a1 * 10u + (c - '0'); ++p; c = ldb(p); }
+    if (c != '/' && c != '|') return IB_NONE;
+    ++p; c = ldb(p);
+    if (c - '0' > 9u) return IB_NONE;
+    while (c - '0' <= 9u) { a2 = a2 * 10u + (c - '0'); ++p; c = ldb(p); }
+    if (a1 > 1u || a2 > 1u) return IB_NONE;
+    return a1 + a2;
 }
 
 // VCFX_indexer on one data line [s, e) (a '\r' before the '\n' already cut off): where CHROM is and what POS reads as.
@@ -1420,6 +1464,80 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                 }
                 __syncwarp();
             }
+            // ================= INBREEDING: the genotype code of every sample column, one byte each, next to the line's own offset
+            uint32_t ib_alt = 0, ib_good = 0; bool ib_line = false;
+            if (OP == OP_IB && !hash && tabs >= 9 && (a0 + ls >= P.valid_from)) {
+                // ALT without a comma (:549-553 / :724); the file mode wants it non-empty too
+                int ok = 0;
+                if (lane == 0) {
+                    const uint32_t as = tp[3] + 1, ae = tp[4];
+                    ok = (P.mode == MODE_FILE) ? (ae > as) : 1;
+                    for (uint32_t q = as; q < ae && ok; ++q) if (ldb(tin + q) == ',') ok = 0;
+                }
+                ib_line = __shfl_sync(FULL, ok, 0) != 0;
+            }
+            if (OP == OP_IB && ib_line) {
+                uint8_t *codes = P.ib_codes + (a0 + ls);
+                bool firstw = true;
+                for (;;) {
+                    const uint32_t pb = wb + 16 * lane;
+                    uint32_t m0, m1, m2, m3;
+                    int r0;                                  // rank in the line of this lane's first tab
+                    if (firstw) { m0 = t0; m1 = t1; m2 = t2; m3 = t3; r0 = rank0; }
+                    else {
+                        m0 = eq_bytes(cur.x, C_TAB); m1 = eq_bytes(cur.y, C_TAB);
+                        m2 = eq_bytes(cur.z, C_TAB); m3 = eq_bytes(cur.w, C_TAB);
+                        const uint32_t n0 = eq_bytes(cur.x, C_NL), n1 = eq_bytes(cur.y, C_NL);
+                        const uint32_t n2 = eq_bytes(cur.z, C_NL), n3 = eq_bytes(cur.w, C_NL);
+                        const unsigned ebal = __ballot_sync(FULL, (n0 | n1 | n2 | n3) != 0);
+                        if (ebal) {
+                            const int src = __ffs(ebal) - 1;
+                            int k = first_byte(n0, n1, n2, n3);
+                            k = __shfl_sync(FULL, k, src);
+                            e = wb + 16 * src + k; found = true;
+                            clip4(m0, m1, m2, m3, pb, 0, e);
+                        }
+                        const int cnt = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+                        const int incl = warp_incl_scan(cnt, lane);
+                        r0 = tabs + incl - cnt;
+                        tabs += __shfl_sync(FULL, incl, 31);
+                    }
+                    uint32_t la = __shfl_down_sync(FULL, cur.x, 1);
+                    const uint32_t nx0 = __shfl_sync(FULL, nxt.x, 0);
+                    if (lane == 31) la = nx0;
+                    {
+                        const uint32_t wsd[5] = {cur.x, cur.y, cur.z, cur.w, la};
+                        const uint32_t ms[4] = {m0, m1, m2, m3};
+                        int r = r0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t m = ms[j];
+                            while (m) {
+                                const int k = (__ffs(m) - 1) >> 3;
+                                m &= m - 1;
+                                if (r >= 8 && (uint32_t)(r - 8) < P.n_sel) {
+                                    // the four bytes behind the tab: [01] [/|] [01] and no further digit is the whole story
+                                    const uint32_t q = __funnelshift_rc(wsd[j], wsd[j + 1], 8u * (uint32_t)(k + 1));
+                                    const uint32_t b1 = (q >> 8) & 0xFFu, b3 = q >> 24;
+                                    uint32_t code;
+                                    if ((q & 0x00FE00FEu) == 0x00300030u && (b1 == '/' || b1 == '|') && (b3 - '0') > 9u) code = (q & 1u) + ((q >> 16) & 1u);
+                                    else code = ib_sample_code(tin + pb + 4 * j + k + 1);
+                                    codes[r - 8] = (uint8_t)code;
+                                    if (code < IB_NONE) { ib_alt += code; ++ib_good; }
+                                }
+                                ++r;
+                            }
+                        }
+                    }
+                    if (found) break;
+                    firstw = false;
+                    wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
+                    if (((wb >> 9) & 7u) == 0) {          // every 8th window: L2 prefetch of the 4 KB that follow
+                        const uint32_t pf = wb + 8 * WINDOW + 128 * lane;
+                        if (pf < nrel) prefetch_l2(tin + pf);
+                    }
+                }
+            }
             // ================= MISSING_DETECT: look for a missing genotype in the sample columns
             bool md_flag = false, md_any = false;
             if (OP == OP_MD && !hash && tabs >= 9) {
@@ -1808,6 +1926,27 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                     }
                 }
             }
+            else if (OP == OP_IB) {
+                // VCFX_inbreeding_calculator.cpp:531-600 / :718-757: a row (alt alleles, genotyped samples, columns) for every line
+                // whose genotypes were looked at; the file mode also wants a byte behind the ninth tab
+                if (ib_line) {
+                    const uint32_t alt = __reduce_add_sync(FULL, ib_alt), good = __reduce_add_sync(FULL, ib_good);
+                    if (P.mode != MODE_FILE || tp[8] + 1 < ee) {
+                        VCFX_COUNT(C_DATA, 1);
+                        if (good >= 2) VCFX_COUNT(C_ROWS, 1);
+                        if (lane == 0) {
+                            const unsigned long long slot = alloc_slot(ws.rec_base, ws.rec_used, P.stats);
+                            if (slot < P.rec_cap) {
+                                Rec r; r.tile = tile; r.ls_rel = (uint32_t)(a0 + ls - a); r.prefix_len = 0;
+                                r.off_in_tile = (uint32_t)out_bytes; r.a = alt; r.b = good;
+                                r.c = min((uint32_t)(tabs - 8), P.n_sel); r.d = 0;
+                                P.recs[slot] = r;
+                            }
+                        }
+                        out_bytes += 1;                                  // (rows, not bytes: the scan turns them into the row's rank)
+                    }
+                }
+            }
             else if (OP == OP_PC) {
                 // VCFX_phase_checker.cpp:493-558 / 576-650: '#' lines and empty lines pass; a data line passes when it lies behind
                 // the "#CHROM" line, has its ten columns and a GT key, and every sample is fully phased; each dropped line leaves
@@ -1953,7 +2092,7 @@ vcfx_scan_kernel(const VCFX_GRID_CONSTANT KParams P) {
     const int lane = lane_id();
     const int wid = threadIdx.x >> 5;
     const uint64_t n = P.n;
-    const bool strip_cr = (OP == OP_HWE) || (P.mode == MODE_FILE && (OP == OP_AF || OP == OP_VC || OP == OP_MD || OP == OP_NR || OP == OP_PC)) || OP == OP_IX;
+    const bool strip_cr = (OP == OP_HWE) || (P.mode == MODE_FILE && (OP == OP_AF || OP == OP_VC || OP == OP_MD || OP == OP_NR || OP == OP_PC)) || OP == OP_IX || OP == OP_IB;
     if (OP == OP_AC && P.ac_pass && P.stats->overflow) return;
     if (VAR == 1 && P.stats->n_unfinished == 0) return;
 
@@ -2369,6 +2508,153 @@ md_copy_kernel(const KParams P) {
             warp_copy(o, P.in + (uint64_t)t * P.tile_bytes + P.tail_start[t], len, lane);
             if ((P.tail_len[t] >> 31) && lane == 0) o[len] = '\n';
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// inbreeding_calculator, second half: the sample-axis reduction
+// ---------------------------------------------------------------------------------------
+// K3a: row records -> rows in file order, with what a sample of each code contributes at this site
+// (VCFX_inbreeding_calculator.cpp:596-625: global p, or p without the sample itself; boundary frequencies)
+__global__ void __launch_bounds__(256)
+ib_rows_kernel(const KParams P) {
+    if (P.stats->overflow) return;
+    const unsigned long long nrec = P.stats->n_recs;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nrec; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const Rec r = P.recs[i];
+        if (r.tile == REC_INVALID) continue;
+        IbRow row;
+        row.code_off = (unsigned long long)r.tile * P.tile_bytes + r.ls_rel;
+        row.ncols = r.c; row.flags = 0; row.e[0] = row.e[1] = row.e[2] = 0.0;
+        const int alt_sum = (int)r.a, n_good = (int)r.b;
+        if (n_good >= 2) {
+            row.flags = 0x100u;
+            const double global_p = ddiv((double)alt_sum, dmul(2.0, (double)n_good));
+            for (int c = 0; c < 3; ++c) {
+                const double freq = (P.flags & IB_F_GLOBAL) ? global_p : ddiv((double)(alt_sum - c), dmul(2.0, (double)(n_good - 1)));
+                if ((P.flags & IB_F_SKIP_BOUNDARY) && (freq <= 0.0 || freq >= 1.0)) { if (P.flags & IB_F_COUNT_BOUNDARY) row.flags |= 1u << (2 * c); }
+                else { row.flags |= 2u << (2 * c); row.e[c] = dmul(dmul(2.0, freq), dsub(1.0, freq)); }
+            }
+        }
+        P.ib_rows[P.tile_base[r.tile] + r.off_in_tile] = row;
+    }
+}
+
+// K3b: one thread per sample walks the chunk's rows in file order (the reference adds the expectations of a sample in that
+// order, in double; any other order rounds differently).  A column the line does not have takes the code of the last line
+// that had it (file mode, :574-588 reuses the buffer) or none (stdin mode, :735-737).  Chunks are applied strictly in
+// order: a chunk whose predecessor has not been applied yet (it is being run again) is left alone and reported.
+__global__ void __launch_bounds__(64)
+ib_accumulate_kernel(const KParams P) {
+    if (P.stats->overflow) return;
+    IbState &S = *P.ib;
+    if (S.seq != P.ib_seq) return;                                   // applied already (a re-run), or not this chunk's turn yet
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.n_sel) return;
+    const unsigned long long R = P.stats->bytes_out;                 // rows of the chunk (tile_scan_kernel's total)
+    double sum = P.ib_first ? 0.0 : S.sum[s];
+    unsigned long long het = P.ib_first ? 0ULL : S.het[s];
+    unsigned int used = P.ib_first ? 0u : S.used[s];
+    uint32_t last = P.ib_first ? 0u : S.last[s];
+    unsigned long long variants = 0;
+    const bool file_mode = P.mode == MODE_FILE;
+    const uint32_t none = IB_ABSENT;                                 // (a column the line lacks and an empty last column are the same thing)
+    const IbRow *__restrict__ rows = P.ib_rows;
+    unsigned long long r = 0;
+    for (; r + 4 <= R; r += 4) {                                     // the loads of four rows are under way before the first add
+        uint32_t c[4], fl[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const IbRow &w = rows[r + k];
+            c[k] = s < w.ncols ? (uint32_t)P.ib_codes[w.code_off + s] : none;
+            fl[k] = w.flags;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (c[k] == IB_ABSENT) c[k] = file_mode ? last : IB_NONE; else last = c[k];
+            variants += fl[k] >> 8;
+            if (c[k] < IB_NONE) {
+                const uint32_t st = (fl[k] >> (2 * c[k])) & 3u;
+                if (st) ++used;
+                if (st == 2) { sum = dadd(sum, rows[r + k].e[c[k]]); het += (c[k] == 1u); }
+            }
+        }
+    }
+    for (; r < R; ++r) {
+        const IbRow &w = rows[r];
+        uint32_t c = s < w.ncols ? (uint32_t)P.ib_codes[w.code_off + s] : none;
+        if (c == IB_ABSENT) c = file_mode ? last : IB_NONE; else last = c;
+        variants += w.flags >> 8;
+        if (c < IB_NONE) {
+            const uint32_t st = (w.flags >> (2 * c)) & 3u;
+            if (st) ++used;
+            if (st == 2) { sum = dadd(sum, w.e[c]); het += (c == 1u); }
+        }
+    }
+    S.sum[s] = sum; S.het[s] = het; S.used[s] = used; S.last[s] = (uint8_t)last;
+    if (s == 0) S.variants = (P.ib_first ? 0ULL : S.variants) + variants;
+}
+
+// K3c: closes the chunk (order guard) and, behind the last chunk, writes the rows "name \t F \n" (:641-667): NA without a
+// used site, 1.000000 when nothing was expected, else 1 - observed / expected with six truncated decimals (:205-240).
+__global__ void __launch_bounds__(1024)
+ib_finish_kernel(const KParams P) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    __shared__ int s_state;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    IbState &S = *P.ib;
+    if (tid == 0) {
+        int st = 0;                                                  // 0 = go on, 1 = leave
+        if (P.stats->overflow) st = 1;
+        else if (S.seq == P.ib_seq) S.seq = P.ib_seq + 1;            // this launch applied the chunk
+        else if (S.seq != P.ib_seq + 1) { P.stats->overflow = 8; st = 1; }   // an earlier chunk is being run again: so will this one
+        if (st || !P.is_final) P.stats->bytes_out = 0;
+        s_state = st; s_carry = 0;
+    }
+    __syncthreads();
+    if (s_state || !P.is_final) return;
+    const bool none_used = S.variants == 0;
+    for (uint32_t base = 0; base < P.n_sel; base += 1024) {
+        const uint32_t s = base + tid;
+        char num[40]; uint32_t nl = 0, name_n = 0;
+        if (s < P.n_sel) {
+            name_n = P.name_off[s + 1] - P.name_off[s];              // the name and its tab
+            if (none_used || S.used[s] == 0) { num[0] = 'N'; num[1] = 'A'; nl = 2; }
+            else {
+                const double e = S.sum[s];
+                if (e <= 0.0) { const char one[] = "1.000000"; for (int k = 0; k < 8; ++k) num[k] = one[k]; nl = 8; }
+                else nl = (uint32_t)fmt_p_file(dsub(1.0, ddiv((double)S.het[s], e)), num);
+            }
+        }
+        const unsigned long long len = s < P.n_sel ? (unsigned long long)name_n + nl + 1u : 0ULL;
+        unsigned long long incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(FULL, incl, o); if ((int)lane >= o) incl += t; }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned long long v = s_warp[lane], iv = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(FULL, iv, o); if ((int)lane >= o) iv += t; }
+            s_warp[lane] = iv - v;
+        }
+        __syncthreads();
+        const unsigned long long off = s_carry + s_warp[wid] + incl - len;
+        if (s < P.n_sel && off + len <= P.text_cap) {
+            uint8_t *o = P.out + off;
+            const uint8_t *nm = P.names + P.name_off[s];
+            for (uint32_t k = 0; k < name_n; ++k) o[k] = nm[k];
+            for (uint32_t k = 0; k < nl; ++k) o[name_n + k] = (uint8_t)num[k];
+            o[name_n + nl] = '\n';
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = off + len;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        P.stats->bytes_out = s_carry;
+        if (s_carry > P.text_cap) P.stats->overflow = 2;
     }
 }
 

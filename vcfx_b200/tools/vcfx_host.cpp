@@ -339,6 +339,7 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_start = now(), t_read = 0, t_submit = 0, t_drain = 0, t_acquire = 0;
     std::vector<int> devices = env_devices();
+    if (opt.single_device && devices.size() > 1) devices.resize(1);
     // One GPU: hide the others from the CUDA runtime before it initialises (it would set up every visible GPU — on an
     // 8-GPU box that is most of a tool's wall time).  VCFX_CUDA_DEVICE counts within CUDA_VISIBLE_DEVICES when that is set.
     if (devices.size() == 1 && !getenv("VCFX_KEEP_VISIBLE")) {
@@ -383,7 +384,7 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
     Drain drain{ctxs, opt, tot, writer};
     const long n_slots = (long)cfg.n_slots * (long)G;     // pinned output buffers in rotation over all the contexts
     std::string carry = opt.preface;
-    bool eof = false, chrom_seen = false, in_hash_block = true, index_saw_hash = false, format_seen = false;
+    bool eof = false, chrom_seen = false, in_hash_block = true, index_saw_hash = false, format_seen = false, final_submitted = false;
     uint64_t file_pos = 0;                         // offset of the next chunk in the whole input
     long submitted = 0;
     while (!eof) {
@@ -428,7 +429,8 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
             const char *s = nl ? nl + 1 : buf;
             opt.last_unterminated_line->assign(s, (size_t)(buf + nbytes - s));
         }
-        if (nbytes == 0) break;
+        if (nbytes == 0 && !(opt.always_submit_final && !final_submitted)) break;
+        if (eof) final_submitted = true;
         vcfx_chunk_info info; memset(&info, 0, sizeof info);
         info.is_final = eof ? 1 : 0;
         info.file_offset = file_pos;

@@ -76,6 +76,10 @@ struct RunOptions {
     // when set, called once per chunk that has events, in stream order, with the chunk's input bytes and its sorted event
     // list (VCFX_OP_PHASE_CHECK: offset of a dropped line in the chunk << 2 | reason)
     std::function<void(const char *chunk, size_t nbytes, const uint64_t *events, size_t n)> on_events;
+    // a chunk marked final is always submitted, an empty one if need be (an op whose text only comes with the final chunk)
+    bool always_submit_final = false;
+    // chunks go to one GPU only, in order (an op that carries state from chunk to chunk)
+    bool single_device = false;
     // when set, only the text of the FINAL chunk is held back here (everything before is written)
     std::string *capture_final = nullptr;
     // keeps a copy of the last line of the input when it has no '\n' (missing_detector's quirk)
