@@ -49,6 +49,7 @@ def lib():
         for name in ("oracle_allele_freq", "oracle_hwe", "oracle_missing", "oracle_nonref_filter", "oracle_indexer", "oracle_phase_checker"):
             getattr(l, name).argtypes = [C.c_char_p, C.c_size_t, C.c_int, P]
         l.oracle_variant_count.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, P]
+        l.oracle_inbreeding.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, P]
         l.oracle_allele_counter.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_char_p, P]
         l.oracle_free.argtypes = [P]
         for name in ("oracle_fmt_af_file", "oracle_fmt_af_stdin", "oracle_fmt_p_file", "oracle_fmt_p_stdin"):
@@ -68,6 +69,8 @@ def lib():
 
 def _call(fn, *args) -> Result:
     r = _Result()
+    # (data, length, ...): the length as size_t — a bare Python int is passed as a C int and loses the bits above 2^31
+    args = tuple(C.c_size_t(a) if i == 1 else a for i, a in enumerate(args))
     fn(*args, C.byref(r))
     res = Result(r)
     lib().oracle_free(C.byref(r))

@@ -435,6 +435,29 @@ def test_inbreeding_calculator_cases(cuda_api, oracle):
         run_all(cuda_api, oracle, data, f"ib shape{shape}", tools=("ib",))
         run_all(cuda_api, oracle, data, f"ib shape{shape} chunks", chunk_bytes=1 << 20 if S > 1000 else 64 << 10, tools=("ib",))
     run_all(cuda_api, oracle, synth.make_vcf(3, 400, 100, seed=77), "ib tile512", tile_bytes=512, tools=("ib",))
+    # lines on the four-byte lattice (d|d + tab) of every length and phase against the 512-byte windows, a sample that leaves
+    # the lattice here and there (the rest of such a line goes tab by tab), three-byte samples that are not genotypes
+    hdr9 = b"##f\n#CHROM\tP\tI\tR\tA\tQ\tF\tI\tFORMAT\t"
+    for S in (100, 126, 127, 128, 129, 255, 256, 257, 700):
+        lines = []
+        for k in range(48):
+            gts = [[b"0|1", b"1|1", b"0/0", b"1|0"][(i * 7 + k) % 4] for i in range(S)]
+            if k % 4 == 1:
+                gts[(k * 37) % S] = [b"0", b".", b"./.", b"0|1:3", b"10|1", b"2|1", b" 0|1"][k % 7]
+            lines.append(b"%d\t%d\t%s\tA\tG\t.\tPASS\t.\tGT\t" % (k % 22 + 1, 10 ** (k % 7), b"r" * (k % 5)) + b"\t".join(gts))
+        data = hdr9 + b"\t".join(b"S%d" % i for i in range(S)) + b"\n" + b"\n".join(lines) + (b"\n" if S % 2 else b"")
+        run_all(cuda_api, oracle, data, f"ib lattice S{S}", tools=("ib",))
+        run_all(cuda_api, oracle, data, f"ib lattice S{S} tile512", tile_bytes=512, tools=("ib",))
+    # thousands of samples in the header, two columns on most lines: more rows x samples than the panels were sized for — the
+    # chunk is run again with larger ones, and the chunks behind it (already launched) wait their turn and are run again too
+    S = 4000
+    hdr = b"##f\n#CHROM\tP\tI\tR\tA\tQ\tF\tI\tFORMAT\t" + b"\t".join(b"N%d" % i for i in range(S)) + b"\n"
+    g = [b"0/1", b"1/1", b"0/0", b"0|1", b"./."]
+    lines = [b"1\t%d\t.\tA\tG\t.\t.\t.\tGT\t%s\t%s" % (k + 1, g[k % 5], g[(k * 3 + 1) % 5]) for k in range(2500)]
+    lines[7] += b"\t" + b"\t".join(g[(j * 7) % 5] for j in range(S - 2))
+    data = hdr + b"\n".join(lines) + b"\n"
+    for kw in ({"chunk_bytes": 16 << 10}, {}):
+        run_all(cuda_api, oracle, data, f"ib few columns {kw}", tools=("ib",), **kw)
     # a context is good for one stream after the other: the sums start again behind a final chunk
     a = synth.make_vcf(3, 200, 20, seed=5); b = synth.make_vcf(2, 150, 20, seed=6)
     names = [b"S%d" % i for i in range(20)]

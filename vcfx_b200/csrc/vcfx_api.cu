@@ -44,7 +44,8 @@ struct Work {                      // device-side bookkeeping for one launch
     uint32_t ev_cap = 0;                 // entries in events (phase_checker grows it when a chunk drops more lines)
     // inbreeding_calculator: a code per sample column (as many bytes as the chunk), the rows in file order, the chunk's place in the order
     uint8_t *ib_codes = nullptr; size_t ib_codes_cap = 0;
-    IbRow *ib_rows = nullptr; uint64_t ib_rows_cap = 0;
+    IbMeta *ib_rows = nullptr; uint64_t ib_rows_cap = 0;
+    uint8_t *ib_panels = nullptr; uint64_t ib_panel_cap = 0;
     unsigned long long ib_seq = 0; bool ib_first = false;
     DevStats *h_stats = nullptr;   // pinned: results of the last launch
     DevStats *h_init = nullptr;    // pinned: constant initial value uploaded before every launch
@@ -243,7 +244,7 @@ void free_work(Work &w) {
     cudaFree(w.tile_lines); cudaFree(w.tile_out); cudaFree(w.tile_base); cudaFree(w.line_base);
     cudaFree(w.rec_prefix); cudaFree(w.ticket); cudaFree(w.recs); cudaFree(w.d_stats); cudaFree(w.events);
     cudaFree(w.tail_start); cudaFree(w.tail_len); cudaFree(w.tail_off); cudaFree(w.col_scratch); cudaFree(w.tile_resume);
-    cudaFree(w.ib_codes); cudaFree(w.ib_rows);
+    cudaFree(w.ib_codes); cudaFree(w.ib_rows); cudaFree(w.ib_panels);
     if (w.h_stats) cudaFreeHost(w.h_stats);
     if (w.h_init) cudaFreeHost(w.h_init);
     if (w.ev_k0) cudaEventDestroy(w.ev_k0);
@@ -252,7 +253,7 @@ void free_work(Work &w) {
     w = Work();
 }
 
-int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes, uint64_t min_recs = 0) {
+int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes, uint64_t min_recs = 0, uint64_t min_panel_bytes = 0) {
     // sized for the smallest tile any launch of up to max_bytes can pick
     uint32_t tiles = tiles_for(ctx, max_bytes, ctx->tile_bytes ? ctx->tile_bytes : MIN_TILE);
     if (!w.d_stats) {
@@ -295,6 +296,14 @@ int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes, uint64_t min_recs = 0)
         CU(cudaMalloc(&w.col_scratch, n * sizeof(uint2)));
     }
     if (ctx->cfg.op == VCFX_OP_INBREEDING) {
+        // the codes once more in file order, 32 samples to a panel: lines that have all their columns need less than the
+        // input has bytes; min_panel_bytes is what a chunk that did not fit asked for
+        const uint64_t want_pan = std::max<uint64_t>(max_bytes + (1u << 20), min_panel_bytes);
+        if (want_pan > w.ib_panel_cap) {
+            cudaFree(w.ib_panels); w.ib_panels = nullptr; w.ib_panel_cap = 0;
+            CU(cudaMalloc(&w.ib_panels, want_pan));
+            w.ib_panel_cap = want_pan;
+        }
         if (max_bytes + VCFX_DEVICE_PAD > w.ib_codes_cap) {
             cudaFree(w.ib_codes); w.ib_codes = nullptr; w.ib_codes_cap = 0;
             CU(cudaMalloc(&w.ib_codes, max_bytes + VCFX_DEVICE_PAD));
@@ -303,7 +312,7 @@ int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes, uint64_t min_recs = 0)
         if (std::max<uint64_t>(recs, w.rec_cap) > w.ib_rows_cap) {
             const uint64_t want = std::max<uint64_t>(recs, w.rec_cap);
             cudaFree(w.ib_rows); w.ib_rows = nullptr; w.ib_rows_cap = 0;
-            CU(cudaMalloc(&w.ib_rows, want * sizeof(IbRow)));
+            CU(cudaMalloc(&w.ib_rows, want * sizeof(IbMeta)));
             w.ib_rows_cap = want;
         }
     }
@@ -315,6 +324,11 @@ int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes, uint64_t min_recs = 0)
         w.rec_cap = recs;
     }
     return VCFX_OK;
+}
+
+// bytes of panels that hold every row the last launch reserved a record for
+uint64_t ib_panel_need(const vcfx_ctx *ctx, const Work &w) {
+    return (uint64_t)w.h_stats->n_recs * 32u * ((ctx->n_sel + 31u) / 32u) + (1u << 20);
 }
 
 // inbreeding_calculator: a NEW chunk takes the next place in the order its context applies chunks in (a chunk that is run
@@ -353,7 +367,7 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
     P.ac_fmt = ctx->ac_fmt; P.ac_ident = ctx->ac_ident ? 1 : 0; P.ac_pass = 0; P.ac_spec = (ctx->cfg.op == VCFX_OP_ALLELE_COUNT && ctx->ac_fmt == AC_TEXT_MT && !ctx->ac_exact) ? 1 : 0; P.n_sel = ctx->n_sel; P.sel_col = ctx->d_sel_col; P.name_off = ctx->d_name_off;
     P.names = ctx->d_names; P.names16 = ctx->d_names16; P.name_len = ctx->name_len; P.ac_bulk = ctx->ac_bulk ? 1 : 0; P.max_col = ctx->max_col; P.col_scratch = w.col_scratch;
     P.ticket = w.ticket; P.ticket2 = w.ticket + 1; P.tile_resume = w.tile_resume; P.recs = w.recs; P.rec_prefix = w.rec_prefix; P.rec_cap = w.rec_cap;
-    P.ib_codes = w.ib_codes; P.ib_rows = w.ib_rows; P.ib = ctx->d_ib; P.ib_seq = w.ib_seq; P.ib_first = w.ib_first ? 1 : 0; P.text_cap = out_cap;
+    P.ib_codes = w.ib_codes; P.ib_rows = w.ib_rows; P.ib_panels = w.ib_panels; P.ib_panel_cap = w.ib_panel_cap; P.ib = ctx->d_ib; P.ib_seq = w.ib_seq; P.ib_first = w.ib_first ? 1 : 0; P.text_cap = out_cap;
     if (ctx->cfg.op == VCFX_OP_INBREEDING) P.out_cap = ~0ULL;       // the scan counts rows there, not bytes of text
     P.stats = w.d_stats; P.events = w.events; P.ev_cap = w.ev_cap; P.ev_raw = (ctx->cfg.op == VCFX_OP_PHASE_CHECK) ? 1 : 0;
 
@@ -383,7 +397,7 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
     if (ctx->cfg.op == VCFX_OP_INBREEDING) {
         // the sample-axis pass: chunks are applied one after the other, whatever stream they were scanned on
         if (ctx->ib_event_set) CU(cudaStreamWaitEvent(st, ctx->ib_event, 0));
-        VCFX_LAUNCH(ib_accumulate_kernel, (int)((ctx->n_sel + 63) / 64), 64, 0, st, P);   // (an empty chunk still opens or closes a stream)
+        VCFX_LAUNCH(ib_accumulate_kernel, (int)((ctx->n_sel + 31) / 32), 32, 0, st, P);   // (an empty chunk still opens or closes a stream)
         CU(cudaGetLastError());
         VCFX_LAUNCH(ib_finish_kernel, 1, 1024, 0, st, P);
         CU(cudaGetLastError());
@@ -799,6 +813,10 @@ int vcfx_cuda_next_output(vcfx_ctx *ctx, const char **text, size_t *n, vcfx_chun
             int rc = ensure_work(ctx, s.w, ctx->chunk_bytes, s.w.h_stats->n_recs + rec_slack(ctx));
             if (rc != VCFX_OK) return rc;
         }
+        if (ov & 16) {                  // inbreeding_calculator: more rows x samples than the panels hold (few columns per line)
+            int rc = ensure_work(ctx, s.w, ctx->chunk_bytes, 0, ib_panel_need(ctx, s.w));
+            if (rc != VCFX_OK) return rc;
+        }
         if (ov & 2) {
             const size_t want = std::max((size_t)s.w.h_stats->bytes_out + (1u << 20), s.out_cap + s.out_cap / 4);
             cudaFree(s.d_out); cudaFreeHost(s.h_out); s.d_out = nullptr; s.h_out = nullptr; s.out_cap = 0;
@@ -859,9 +877,10 @@ int vcfx_cuda_sync(vcfx_ctx *ctx, vcfx_chunk_stats *stats) {
     ctx->dev_pending = false;
     const int grew = grow_events(ctx, ctx->dev_work);
     if (grew < 0) return grew;
-    if ((ctx->dev_work.h_stats->overflow & 13) || grew) {      // more rows than sized for / speculative row sizes off / more events: run again
+    if ((ctx->dev_work.h_stats->overflow & 29) || grew) {      // more rows than sized for / speculative row sizes off / more events: run again
         if (ctx->dev_work.h_stats->overflow & 4) ctx->ac_exact = true;
-        int rc2 = ensure_work(ctx, ctx->dev_work, ctx->dev_nbytes, ctx->dev_work.h_stats->n_recs + rec_slack(ctx));
+        int rc2 = ensure_work(ctx, ctx->dev_work, ctx->dev_nbytes, ctx->dev_work.h_stats->n_recs + rec_slack(ctx),
+                              (ctx->dev_work.h_stats->overflow & 16) ? ib_panel_need(ctx, ctx->dev_work) : 0);
         if (rc2 != VCFX_OK) return rc2;
         rc2 = launch_chunk(ctx, ctx->dev_work, ctx->dev_stream, ctx->dev_in, ctx->dev_nbytes, &ctx->dev_info,
                            ctx->dev_out, ctx->dev_out_cap);

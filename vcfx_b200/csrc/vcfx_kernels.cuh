@@ -50,12 +50,10 @@ struct Rec {                 // one output row (32 B)
     uint32_t a, b, c, d;     // op-specific integers (AF: alt,total; HWE: homRef,het,homAlt)
 };
 
-// inbreeding_calculator: one row per line whose genotypes were looked at, in file order
-struct IbRow {
-    unsigned long long code_off;  // ib_codes index of the line's first sample column
-    uint32_t ncols;               // sample columns the line has (at most the number of samples)
-    uint32_t flags;               // bits 2c, 2c+1: what a sample with code c does here (0 nothing, 1 counted only, 2 counted and summed); bit 8: a used site
-    double e[3];                  // expected heterozygosity 2 f (1 - f) of a sample with code 0, 1, 2
+// inbreeding_calculator: what a sample contributes at a site, by its genotype code (0, 1, 2, IB_NONE); rows in file order
+struct IbMeta {
+    double x[4];                  // expected heterozygosity 2 f (1 - f) to add (+0.0 when the sample adds nothing here)
+    uint32_t inc[4];              // bit 0: the site counts as used for the sample; bit 16: an observed heterozygote
 };
 struct IbState {
     unsigned long long seq;       // chunks accumulated so far
@@ -136,7 +134,9 @@ struct KParams {
     unsigned long long fmt0_until;   // phase_checker, file mode: an empty FORMAT column of a line starting below this offset means GT index 0
     // INBREEDING (sample-axis reduction): the scan leaves one code per sample column, a second pass walks the rows in file order
     uint8_t *ib_codes;               // [n + pad] code of sample column j of the line starting at byte L: ib_codes[L + j] (0, 1, 2, IB_NONE, IB_ABSENT)
-    IbRow *ib_rows;                  // [rec_cap] the chunk's rows in file order (ib_rows_kernel)
+    IbMeta *ib_rows;                 // [rec_cap] the chunk's rows in file order (ib_rows_kernel)
+    uint8_t *ib_panels;              // codes again, in file order and in panels of 32 samples: [panel][row][32] (what a warp of the second pass streams)
+    uint64_t ib_panel_cap;           // bytes
     IbState *ib;                     // what lives from chunk to chunk: per-sample sums, the last code of every column, the order guard
     unsigned long long ib_seq;       // number of this chunk in its context (chunks are accumulated strictly in this order)
     int32_t ib_first;                // first chunk of a stream: the per-sample state starts from zero
@@ -1477,10 +1477,54 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                 ib_line = __shfl_sync(FULL, ok, 0) != 0;
             }
             if (OP == OP_IB && ib_line) {
-                uint8_t *codes = P.ib_codes + (a0 + ls);
-                bool firstw = true;
+                // (the codes of a line start within three bytes of the line's own offset, such that a lane's four codes of a
+                // lattice window — see below — land on a 32-bit boundary; the record says where)
+                const uint32_t first = tp[8] + 1u, tq = tp[8] & 3u;          // tq: where in a 32-bit word the tabs of a lattice line sit
+                uint8_t *codes = P.ib_codes + (((a0 + ls) & ~3ULL) + ((((first + 3u) >> 2) - 1u) & 3u));
+                bool firstw = true, lat = true;
                 for (;;) {
                     const uint32_t pb = wb + 16 * lane;
+                    uint32_t la = __shfl_down_sync(FULL, cur.x, 1);
+                    const uint32_t nx0 = __shfl_sync(FULL, nxt.x, 0);
+                    if (lane == 31) la = nx0;
+                    // ---- lattice window: no line end in sight and every sample so far (and here) is three bytes and a tab, at the
+                    // line's phase: a 32-bit word per sample, four codes per lane in one store, no ranking of tabs
+                    if (!firstw && lat) {
+                        const uint32_t nl_any = eq_bytes(cur.x, C_NL) | eq_bytes(cur.y, C_NL) | eq_bytes(cur.z, C_NL) | eq_bytes(cur.w, C_NL);
+                        if (!__any_sync(FULL, nl_any != 0)) {
+                            // like the tab-by-tab path, a window owns the samples whose leading tab lies in it: bytes tq of every word
+                            const uint32_t sh8 = 8u * (tq + 1u);
+                            const uint32_t u0 = __funnelshift_rc(cur.x, cur.y, sh8), u1 = __funnelshift_rc(cur.y, cur.z, sh8);
+                            const uint32_t u2 = __funnelshift_rc(cur.z, cur.w, sh8), u3 = __funnelshift_rc(cur.w, la, sh8);
+                            const uint32_t uu[4] = {u0, u1, u2, u3};
+                            uint32_t bad = 0, pk = 0;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint32_t u = uu[j];
+                                bad |= (eq_bytes(u, C_TAB) ^ 0x80000000u) | eq_bytes(u, C_NL);
+                                const uint32_t b1 = (u >> 8) & 0xFFu;
+                                const bool quick = ((u & 0x00FE00FEu) == 0x00300030u) && (b1 == '/' || b1 == '|');
+                                pk |= (quick ? ((u & 1u) + ((u >> 16) & 1u)) : IB_NONE) << (8 * j);
+                            }
+                            // the sample behind the window's first tab is number j0 of the line: by the tabs counted so far and by position
+                            const int j0 = tabs - 8;
+                            bool okl = bad == 0 && j0 == (int)((wb + tq + 1u - first) >> 2) && (uint32_t)(j0 + 4 * lane + 4) <= P.n_sel;
+                            if (lane == 0) okl = okl && ((eq_bytes(cur.x, C_TAB) & (0xFFFFFFFFu >> (24u - 8u * tq))) == (0x80u << (8u * tq)));
+                            if (__all_sync(FULL, okl)) {
+                                *reinterpret_cast<uint32_t *>(codes + j0 + 4 * lane) = pk;
+                                const uint32_t nn = (uint32_t)__popc(eq_bytes(pk, IB_NONE * 0x01010101u));
+                                ib_good += 4u - nn; ib_alt += dp4a_u(pk, 0x01010101u, 0u) - 3u * nn;
+                                tabs += 128;
+                                wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
+                                if (((wb >> 9) & 7u) == 0) {
+                                    const uint32_t pf = wb + 8 * WINDOW + 128 * lane;
+                                    if (pf < nrel) prefetch_l2(tin + pf);
+                                }
+                                continue;
+                            }
+                            lat = false;
+                        }
+                    }
                     uint32_t m0, m1, m2, m3;
                     int r0;                                  // rank in the line of this lane's first tab
                     if (firstw) { m0 = t0; m1 = t1; m2 = t2; m3 = t3; r0 = rank0; }
@@ -1502,9 +1546,6 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                         r0 = tabs + incl - cnt;
                         tabs += __shfl_sync(FULL, incl, 31);
                     }
-                    uint32_t la = __shfl_down_sync(FULL, cur.x, 1);
-                    const uint32_t nx0 = __shfl_sync(FULL, nxt.x, 0);
-                    if (lane == 31) la = nx0;
                     {
                         const uint32_t wsd[5] = {cur.x, cur.y, cur.z, cur.w, la};
                         const uint32_t ms[4] = {m0, m1, m2, m3};
@@ -1939,7 +1980,7 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                             if (slot < P.rec_cap) {
                                 Rec r; r.tile = tile; r.ls_rel = (uint32_t)(a0 + ls - a); r.prefix_len = 0;
                                 r.off_in_tile = (uint32_t)out_bytes; r.a = alt; r.b = good;
-                                r.c = min((uint32_t)(tabs - 8), P.n_sel); r.d = 0;
+                                r.c = min((uint32_t)(tabs - 8), P.n_sel); r.d = (((tp[8] + 4u) >> 2) - 1u) & 3u;
                                 P.recs[slot] = r;
                             }
                         }
@@ -2514,85 +2555,176 @@ md_copy_kernel(const KParams P) {
 // ---------------------------------------------------------------------------------------
 // inbreeding_calculator, second half: the sample-axis reduction
 // ---------------------------------------------------------------------------------------
-// K3a: row records -> rows in file order, with what a sample of each code contributes at this site
-// (VCFX_inbreeding_calculator.cpp:596-625: global p, or p without the sample itself; boundary frequencies)
+// K3a: row records -> rows in file order.  A warp per row: what a sample of each code contributes at this site
+// (VCFX_inbreeding_calculator.cpp:596-625: global p, or p without the sample itself; boundary frequencies), and the row's
+// codes copied next to those of the rows before and behind it, 32 samples to a panel.  A column the line does not have
+// (and an empty last one) is IB_ABSENT in file mode — the sample then keeps the code of the last line that had it, the
+// reference reuses its buffer (:574-588) — and has no genotype in stdin mode (:735-737).
 __global__ void __launch_bounds__(256)
 ib_rows_kernel(const KParams P) {
     if (P.stats->overflow) return;
+    const unsigned long long R = P.stats->bytes_out;                 // rows of the chunk (tile_scan_kernel's total)
+    const uint32_t npan = (P.n_sel + 31u) >> 5;
+    if (R * 32ULL * npan > P.ib_panel_cap) {                         // (every thread sees the same: nobody writes)
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&P.stats->overflow, 16ULL);
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    const bool file_mode = P.mode == MODE_FILE;
     const unsigned long long nrec = P.stats->n_recs;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nrec; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < nrec; i += nwarps) {
         const Rec r = P.recs[i];
         if (r.tile == REC_INVALID) continue;
-        IbRow row;
-        row.code_off = (unsigned long long)r.tile * P.tile_bytes + r.ls_rel;
-        row.ncols = r.c; row.flags = 0; row.e[0] = row.e[1] = row.e[2] = 0.0;
-        const int alt_sum = (int)r.a, n_good = (int)r.b;
-        if (n_good >= 2) {
-            row.flags = 0x100u;
-            const double global_p = ddiv((double)alt_sum, dmul(2.0, (double)n_good));
-            for (int c = 0; c < 3; ++c) {
-                const double freq = (P.flags & IB_F_GLOBAL) ? global_p : ddiv((double)(alt_sum - c), dmul(2.0, (double)(n_good - 1)));
-                if ((P.flags & IB_F_SKIP_BOUNDARY) && (freq <= 0.0 || freq >= 1.0)) { if (P.flags & IB_F_COUNT_BOUNDARY) row.flags |= 1u << (2 * c); }
-                else { row.flags |= 2u << (2 * c); row.e[c] = dmul(dmul(2.0, freq), dsub(1.0, freq)); }
+        const unsigned long long rank = P.tile_base[r.tile] + r.off_in_tile;
+        if (lane == 0) {
+            IbMeta m;
+            for (int c = 0; c < 4; ++c) { m.x[c] = 0.0; m.inc[c] = 0; }
+            const int alt_sum = (int)r.a, n_good = (int)r.b;
+            if (n_good >= 2) {
+                const double global_p = ddiv((double)alt_sum, dmul(2.0, (double)n_good));
+                for (int c = 0; c < 3; ++c) {
+                    const double freq = (P.flags & IB_F_GLOBAL) ? global_p : ddiv((double)(alt_sum - c), dmul(2.0, (double)(n_good - 1)));
+                    if ((P.flags & IB_F_SKIP_BOUNDARY) && (freq <= 0.0 || freq >= 1.0)) { if (P.flags & IB_F_COUNT_BOUNDARY) m.inc[c] = 1u; }
+                    else { m.inc[c] = (c == 1) ? 0x10001u : 1u; m.x[c] = dmul(dmul(2.0, freq), dsub(1.0, freq)); }
+                }
             }
+            P.ib_rows[rank] = m;
         }
-        P.ib_rows[P.tile_base[r.tile] + r.off_in_tile] = row;
+        // 16 codes per lane and step: aligned 32-bit loads around the (unaligned) source, one 16-byte store into the panel
+        const uint8_t *src = P.ib_codes + ((((unsigned long long)r.tile * P.tile_bytes + r.ls_rel) & ~3ULL) + r.d);
+        const uint32_t mis = (uint32_t)((uintptr_t)src & 3u), sh = 8u * mis;
+        const uint32_t *s4 = reinterpret_cast<const uint32_t *>(src - mis);
+        const uint32_t fill = (file_mode ? IB_ABSENT : IB_NONE) * 0x01010101u;
+        for (uint32_t s0 = 16u * (uint32_t)lane; s0 < (npan << 5); s0 += 512u) {
+            uint32_t w[4];
+            if (s0 + 16u <= r.c) {
+                const uint32_t *q = s4 + (s0 >> 2);
+                const uint32_t a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3], a4 = mis ? q[4] : 0u;      // (q[4] may lie behind the codes, never behind the arena's pad)
+                w[0] = __funnelshift_r(a0, a1, sh); w[1] = __funnelshift_r(a1, a2, sh); w[2] = __funnelshift_r(a2, a3, sh); w[3] = __funnelshift_r(a3, a4, sh);
+                if (!file_mode) {                                    // an empty last column has no genotype in stdin mode
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) w[j] -= (eq_bytes(w[j], IB_ABSENT * 0x01010101u) >> 7);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t v = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const uint32_t sidx = s0 + 4u * j + b;
+                        uint32_t c = sidx < r.c ? (uint32_t)src[sidx] : (sidx < P.n_sel ? (fill & 0xFFu) : IB_NONE);
+                        if (!file_mode && c == IB_ABSENT) c = IB_NONE;
+                        v |= c << (8 * b);
+                    }
+                    w[j] = v;
+                }
+            }
+            *reinterpret_cast<uint4 *>(P.ib_panels + ((unsigned long long)(s0 >> 5) * R + rank) * 32ULL + (s0 & 31u)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
     }
 }
 
-// K3b: one thread per sample walks the chunk's rows in file order (the reference adds the expectations of a sample in that
-// order, in double; any other order rounds differently).  A column the line does not have takes the code of the last line
-// that had it (file mode, :574-588 reuses the buffer) or none (stdin mode, :735-737).  Chunks are applied strictly in
-// order: a chunk whose predecessor has not been applied yet (it is being run again) is left alone and reported.
-__global__ void __launch_bounds__(64)
+// 16 bytes global -> shared without a register in between (LDGSTS); groups complete in order
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+#ifdef VCFX_EMU
+    *reinterpret_cast<uint4 *>(smem) = *reinterpret_cast<const uint4 *>(gmem);
+#else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef VCFX_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+#ifndef VCFX_EMU
+    asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
+#endif
+}
+
+// K3b: the sample-axis pass.  One thread per sample, one warp per panel of 32 samples: the warp streams its panel's codes and
+// the rows' contribution tables through shared memory (IB_STAGES tiles of IB_TILE rows under way, cp.async) and every thread
+// walks the chunk's sites IN FILE ORDER — the reference adds a sample's expectations in that order, in double, and any other
+// order rounds differently.  Per site and sample: one table look-up and one add (a sample that adds nothing adds +0.0).
+// Chunks are applied strictly in order: a chunk whose predecessor has not been applied yet (it is being run again) is left
+// alone and reported by ib_finish_kernel.
+constexpr int IB_TILE = 128, IB_STAGES = 4;
+__global__ void __launch_bounds__(32)
 ib_accumulate_kernel(const KParams P) {
+    __shared__ __align__(16) uint8_t sm_codes[IB_STAGES][IB_TILE * 32];
+    __shared__ __align__(16) IbMeta sm_meta[IB_STAGES][IB_TILE];
     if (P.stats->overflow) return;
     IbState &S = *P.ib;
     if (S.seq != P.ib_seq) return;                                   // applied already (a re-run), or not this chunk's turn yet
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= P.n_sel) return;
-    const unsigned long long R = P.stats->bytes_out;                 // rows of the chunk (tile_scan_kernel's total)
-    double sum = P.ib_first ? 0.0 : S.sum[s];
-    unsigned long long het = P.ib_first ? 0ULL : S.het[s];
-    unsigned int used = P.ib_first ? 0u : S.used[s];
-    uint32_t last = P.ib_first ? 0u : S.last[s];
-    unsigned long long variants = 0;
-    const bool file_mode = P.mode == MODE_FILE;
-    const uint32_t none = IB_ABSENT;                                 // (a column the line lacks and an empty last column are the same thing)
-    const IbRow *__restrict__ rows = P.ib_rows;
-    unsigned long long r = 0;
-    for (; r + 4 <= R; r += 4) {                                     // the loads of four rows are under way before the first add
-        uint32_t c[4], fl[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const IbRow &w = rows[r + k];
-            c[k] = s < w.ncols ? (uint32_t)P.ib_codes[w.code_off + s] : none;
-            fl[k] = w.flags;
+    const uint32_t lane = threadIdx.x, s = blockIdx.x * 32u + lane;
+    const bool live = s < P.n_sel;
+    const unsigned long long R = P.stats->bytes_out;
+    const bool fresh = P.ib_first != 0;
+    double sum = (fresh || !live) ? 0.0 : S.sum[s];
+    unsigned long long het = (fresh || !live) ? 0ULL : S.het[s];
+    unsigned int used = (fresh || !live) ? 0u : S.used[s];
+    uint32_t last = (fresh || !live) ? 0u : (uint32_t)S.last[s];
+    const uint8_t *pan = P.ib_panels + (unsigned long long)blockIdx.x * R * 32ULL;
+    const unsigned long long ntiles = (R + IB_TILE - 1) / IB_TILE;
+    auto issue = [&](unsigned long long t) {
+        if (t < ntiles) {
+            const int st = (int)(t % IB_STAGES);
+            const uint32_t nrows = (uint32_t)min((unsigned long long)IB_TILE, R - t * IB_TILE);
+            const uint8_t *gc = pan + t * (IB_TILE * 32ULL);
+            const uint8_t *gm = reinterpret_cast<const uint8_t *>(P.ib_rows) + t * (IB_TILE * (unsigned long long)sizeof(IbMeta));
+            for (uint32_t q = lane; q < nrows * 2u; q += 32) cp_async16(&sm_codes[st][q * 16u], gc + q * 16u);
+            for (uint32_t q = lane; q < nrows * 3u; q += 32) cp_async16(reinterpret_cast<uint8_t *>(&sm_meta[st][0]) + q * 16u, gm + q * 16u);
         }
+        cp_async_commit();                                           // (an empty group keeps the count of groups in step)
+    };
+    for (int j = 0; j < IB_STAGES - 1; ++j) issue((unsigned long long)j);
+    for (unsigned long long t = 0; t < ntiles; ++t) {
+        issue(t + IB_STAGES - 1);
+        cp_async_wait<IB_STAGES - 1>();
+        __syncwarp();
+        const int st = (int)(t % IB_STAGES);
+        const uint32_t nrows = (uint32_t)min((unsigned long long)IB_TILE, R - t * IB_TILE);
+        const uint8_t *cs = &sm_codes[st][lane];
+        const IbMeta *ms = &sm_meta[st][0];
+        uint32_t cnt = 0;
+        // The adds of one sample form a chain (each waits for the one before it); the look-ups of the NEXT eight rows are
+        // written between them so that the in-order issue has something to do while an add is under way.
+        uint32_t k = 0;
+        if (nrows >= 8) {
+            double xa[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (c[k] == IB_ABSENT) c[k] = file_mode ? last : IB_NONE; else last = c[k];
-            variants += fl[k] >> 8;
-            if (c[k] < IB_NONE) {
-                const uint32_t st = (fl[k] >> (2 * c[k])) & 3u;
-                if (st) ++used;
-                if (st == 2) { sum = dadd(sum, rows[r + k].e[c[k]]); het += (c[k] == 1u); }
+            for (int j = 0; j < 8; ++j) {
+                uint32_t c = cs[(uint32_t)j * 32u];
+                c = (c == IB_ABSENT) ? last : c; last = c;
+                xa[j] = ms[j].x[c]; cnt += ms[j].inc[c];
             }
+            for (k = 8; k + 8 <= nrows; k += 8) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint32_t c = cs[(k + j) * 32u];
+                    c = (c == IB_ABSENT) ? last : c; last = c;
+                    const double xn = ms[k + j].x[c];
+                    cnt += ms[k + j].inc[c];
+                    sum = dadd(sum, xa[j]);
+                    xa[j] = xn;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sum = dadd(sum, xa[j]);
         }
-    }
-    for (; r < R; ++r) {
-        const IbRow &w = rows[r];
-        uint32_t c = s < w.ncols ? (uint32_t)P.ib_codes[w.code_off + s] : none;
-        if (c == IB_ABSENT) c = file_mode ? last : IB_NONE; else last = c;
-        variants += w.flags >> 8;
-        if (c < IB_NONE) {
-            const uint32_t st = (w.flags >> (2 * c)) & 3u;
-            if (st) ++used;
-            if (st == 2) { sum = dadd(sum, w.e[c]); het += (c == 1u); }
+        for (; k < nrows; ++k) {
+            uint32_t c = cs[k * 32u];
+            c = (c == IB_ABSENT) ? last : c; last = c;
+            sum = dadd(sum, ms[k].x[c]);
+            cnt += ms[k].inc[c];
         }
+        used += cnt & 0xFFFFu; het += cnt >> 16;
+        __syncwarp();
     }
-    S.sum[s] = sum; S.het[s] = het; S.used[s] = used; S.last[s] = (uint8_t)last;
-    if (s == 0) S.variants = (P.ib_first ? 0ULL : S.variants) + variants;
+    if (live) { S.sum[s] = sum; S.het[s] = het; S.used[s] = used; S.last[s] = (uint8_t)last; }
+    if (s == 0) S.variants = (fresh ? 0ULL : S.variants) + P.stats->rows;
 }
 
 // K3c: closes the chunk (order guard) and, behind the last chunk, writes the rows "name \t F \n" (:641-667): NA without a
