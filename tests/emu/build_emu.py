@@ -21,10 +21,13 @@ def build(force: bool = False) -> Path:
     cmd = ["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas", "-Wno-unused-variable", "-x", "c++", "-DVCFX_EMU",
            "-I", str(HERE), "-I", str(ROOT / "include"), "-I", str(ROOT / "vcfx_b200" / "csrc"),
            "-fPIC", "-shared", "-o", str(OUT), *map(str, srcs)]
+    tmp = OUT.with_name(f".{OUT.name}.{os.getpid()}")               # (several test processes may build at once: link aside, rename)
+    cmd[cmd.index("-o") + 1] = str(tmp)
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
         raise RuntimeError("emulator build failed")
+    os.replace(tmp, OUT)
     return OUT
 
 
