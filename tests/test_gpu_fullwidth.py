@@ -42,12 +42,15 @@ def test_full_width(cuda_api, oracle, shape, V):
             "ac": _ref("allele_counter", ["-q", "-i"], f.name) or O.allele_counter(data).out,
             "nr": _ref("nonref_filter", ["-i"], f.name) or O.nonref_filter(data, 0).out,
             "ix": _ref("indexer", [], f.name) or O.indexer(data, 0).out,
+            "pc": _ref("phase_checker", ["-q", "-i"], f.name) or O.phase_checker(data, 0).out,
+            "ib": _ref("inbreeding_calculator", ["-q", "-i"], f.name) or O.inbreeding(data, 0, O.IB_QUIET).out,
         }
     # 1. the streaming path, default chunk (64 MiB) and default tiles
     kw = dict(chunk_bytes=64 << 20)
     got = {"af": api.allele_freq_calc(data, 0, **kw).out, "hwe": api.hwe_tester(data, 0, **kw).out, "md": api.missing_detector(data, 0, **kw).out,
            "vc": api.variant_counter(data, 0, **kw).out, "ac": api.allele_counter(data, chunk_bytes=16 << 20).out,
-           "nr": api.nonref_filter(data, 0, **kw).out, "ix": api.indexer(data, 0, **kw).out}
+           "nr": api.nonref_filter(data, 0, **kw).out, "ix": api.indexer(data, 0, **kw).out,
+           "pc": api.phase_checker(data, 0, quiet=True, **kw).out, "ib": api.inbreeding_calculator(data, 0, **kw).out}
     if want["md"] is None:
         del want["md"]
     for k in want:
@@ -63,12 +66,15 @@ def test_full_width(cuda_api, oracle, shape, V):
     line_len = data.index(b"\n", api.first_data_offset(data)) - api.first_data_offset(data) + 1
     for k, op, head, vf in (("af", api.OP_ALLELE_FREQ, api.AF_HEADER, api.find_chrom_header(data)), ("hwe", api.OP_HWE, api.HWE_HEADER, 0),
                             ("md", api.OP_MISSING_DETECT, b"", api.first_data_offset(data)), ("nr", api.OP_NONREF_FILTER, b"", api.find_chrom_header(data)),
-                            ("ix", api.OP_INDEX, api.INDEX_HEADER, api.find_chrom_header(data))):
+                            ("ix", api.OP_INDEX, api.INDEX_HEADER, api.find_chrom_header(data)),
+                            ("pc", api.OP_PHASE_CHECK, b"", api.find_chrom_header(data)), ("ib", api.OP_INBREEDING, api.IB_HEADER, 0)):
         if k not in want:
             continue
-        ctx = api.Context(op, api.FILE)
+        names = api._ib_header(data, api.FILE)[0]
+        ctx = api.Context(op, api.FILE, **(dict(sel_cols=list(range(len(names))), sel_names=names) if k == "ib" else {}))
         ctx.set_line_hint(line_len)
-        ctx.run_device(d_in.data_ptr(), len(data), d_out.data_ptr(), d_out.numel(), valid_from=vf)
+        ctx.run_device(d_in.data_ptr(), len(data), d_out.data_ptr(), d_out.numel(), valid_from=vf,
+                       format_cache_from=api.first_format_line(data[:1 << 20], vf) if k == "pc" else 0)
         st = ctx.sync()
         text = head + d_out[:int(st.bytes_out)].cpu().numpy().tobytes()
         ctx.close()
