@@ -1644,7 +1644,32 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                                 e = wb + 16 * src + k; found = true;
                             }
                         }
-                        if (nr_all) {                             // the reference stops at the first sample that is not hom-ref too
+                        // ---- lattice window: no line end in it, GT the first key, and behind every tab three bytes and the next tab, at
+                        // the phase of the line's first sample — a 32-bit word per sample decides the whole window without a look at
+                        // single tabs (nonref_filter: 0/0 or 0|0; phase_checker: x|y, neither a '.' nor the ':' that would end GT early)
+                        bool lat_pass = false;
+                        if (nr_all && !firstw && !found && gi == 0) {
+                            const uint32_t tq = lo & 3u, sh8 = 8u * (tq + 1u);
+                            uint32_t la = __shfl_down_sync(FULL, cur.x, 1);
+                            const uint32_t nx0 = __shfl_sync(FULL, nxt.x, 0);
+                            if (lane == 31) la = nx0;
+                            const uint32_t uu[4] = {__funnelshift_rc(cur.x, cur.y, sh8), __funnelshift_rc(cur.y, cur.z, sh8),
+                                                    __funnelshift_rc(cur.z, cur.w, sh8), __funnelshift_rc(cur.w, la, sh8)};
+                            uint32_t badw = 0;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint32_t u = uu[j];
+                                if (OP == OP_NR) badw |= (u != 0x09302F30u && u != 0x09307C30u) ? 1u : 0u;
+                                else {
+                                    badw |= (eq_bytes(u, C_TAB) ^ 0x80000000u) | eq_bytes(u, C_NL);
+                                    badw |= ((eq_bytes(u, C_DOT) | eq_bytes(u, 0x3A3A3A3Au)) & 0x00800080u) | ((u ^ 0x00007C00u) & 0x0000FF00u);
+                                }
+                            }
+                            // (the bytes in front of the window's first tab belong to a sample the window before has answered for)
+                            if (lane == 0) badw |= (eq_bytes(cur.x, C_TAB) & (0xFFFFFFFFu >> (24u - 8u * tq))) ^ (0x80u << (8u * tq));
+                            lat_pass = __all_sync(FULL, badw == 0);
+                        }
+                        if (nr_all && !lat_pass) {                // the reference stops at the first sample that is not hom-ref too
                             uint32_t m0 = eq_bytes(cur.x, C_TAB), m1 = eq_bytes(cur.y, C_TAB);
                             uint32_t m2 = eq_bytes(cur.z, C_TAB), m3 = eq_bytes(cur.w, C_TAB);
                             if (firstw || found) clip4(m0, m1, m2, m3, pb, firstw ? lo : 0u, found ? e : ~0u);
