@@ -51,10 +51,12 @@ struct Rec {                 // one output row (32 B)
 };
 
 // inbreeding_calculator: what a sample contributes at a site, by its genotype code (0, 1, 2, IB_NONE); rows in file order
-struct IbMeta {
-    double x[4];                  // expected heterozygosity 2 f (1 - f) to add (+0.0 when the sample adds nothing here)
-    uint32_t inc[4];              // bit 0: the site counts as used for the sample; bit 16: an observed heterozygote
+struct IbEntry {
+    double x;                     // expected heterozygosity 2 f (1 - f) to add (+0.0 when the sample adds nothing here)
+    uint32_t inc;                 // bit 0: the site counts as used for the sample; bit 16: an observed heterozygote
+    uint32_t flag;                // (entry IB_NONE only) 1: some sample column of the row is IB_ABSENT
 };
+struct IbMeta { IbEntry e[4]; };  // 64 B per row; the panels hold 16 * code, the byte offset of a sample's entry
 struct IbState {
     unsigned long long seq;       // chunks accumulated so far
     unsigned long long variants;  // used sites of the stream so far
@@ -2602,35 +2604,19 @@ ib_rows_kernel(const KParams P) {
         const Rec r = P.recs[i];
         if (r.tile == REC_INVALID) continue;
         const unsigned long long rank = P.tile_base[r.tile] + r.off_in_tile;
-        if (lane == 0) {
-            IbMeta m;
-            for (int c = 0; c < 4; ++c) { m.x[c] = 0.0; m.inc[c] = 0; }
-            const int alt_sum = (int)r.a, n_good = (int)r.b;
-            if (n_good >= 2) {
-                const double global_p = ddiv((double)alt_sum, dmul(2.0, (double)n_good));
-                for (int c = 0; c < 3; ++c) {
-                    const double freq = (P.flags & IB_F_GLOBAL) ? global_p : ddiv((double)(alt_sum - c), dmul(2.0, (double)(n_good - 1)));
-                    if ((P.flags & IB_F_SKIP_BOUNDARY) && (freq <= 0.0 || freq >= 1.0)) { if (P.flags & IB_F_COUNT_BOUNDARY) m.inc[c] = 1u; }
-                    else { m.inc[c] = (c == 1) ? 0x10001u : 1u; m.x[c] = dmul(dmul(2.0, freq), dsub(1.0, freq)); }
-                }
-            }
-            P.ib_rows[rank] = m;
-        }
-        // 16 codes per lane and step: aligned 32-bit loads around the (unaligned) source, one 16-byte store into the panel
+        // 16 codes per lane and step: aligned 32-bit loads around the (unaligned) source, one 16-byte store into the panel;
+        // what is stored is 16 * code, the offset of the sample's entry in the row's table
         const uint8_t *src = P.ib_codes + ((((unsigned long long)r.tile * P.tile_bytes + r.ls_rel) & ~3ULL) + r.d);
         const uint32_t mis = (uint32_t)((uintptr_t)src & 3u), sh = 8u * mis;
         const uint32_t *s4 = reinterpret_cast<const uint32_t *>(src - mis);
-        const uint32_t fill = (file_mode ? IB_ABSENT : IB_NONE) * 0x01010101u;
+        const uint32_t fill = file_mode ? IB_ABSENT : IB_NONE;
+        uint32_t absent = (file_mode && r.c < P.n_sel) ? 1u : 0u;
         for (uint32_t s0 = 16u * (uint32_t)lane; s0 < (npan << 5); s0 += 512u) {
             uint32_t w[4];
             if (s0 + 16u <= r.c) {
                 const uint32_t *q = s4 + (s0 >> 2);
                 const uint32_t a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3], a4 = mis ? q[4] : 0u;      // (q[4] may lie behind the codes, never behind the arena's pad)
                 w[0] = __funnelshift_r(a0, a1, sh); w[1] = __funnelshift_r(a1, a2, sh); w[2] = __funnelshift_r(a2, a3, sh); w[3] = __funnelshift_r(a3, a4, sh);
-                if (!file_mode) {                                    // an empty last column has no genotype in stdin mode
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) w[j] -= (eq_bytes(w[j], IB_ABSENT * 0x01010101u) >> 7);
-                }
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -2638,14 +2624,35 @@ ib_rows_kernel(const KParams P) {
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
                         const uint32_t sidx = s0 + 4u * j + b;
-                        uint32_t c = sidx < r.c ? (uint32_t)src[sidx] : (sidx < P.n_sel ? (fill & 0xFFu) : IB_NONE);
-                        if (!file_mode && c == IB_ABSENT) c = IB_NONE;
+                        const uint32_t c = sidx < r.c ? (uint32_t)src[sidx] : (sidx < P.n_sel ? fill : IB_NONE);
                         v |= c << (8 * b);
                     }
                     w[j] = v;
                 }
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t ab = eq_bytes(w[j], IB_ABSENT * 0x01010101u) >> 7;    // 0x01 in the bytes that are IB_ABSENT (an empty last column)
+                if (file_mode) absent |= ab; else w[j] -= ab;        // ... which has no genotype in stdin mode
+                w[j] <<= 4;
+            }
             *reinterpret_cast<uint4 *>(P.ib_panels + ((unsigned long long)(s0 >> 5) * R + rank) * 32ULL + (s0 & 31u)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        const bool any_absent = __any_sync(FULL, absent != 0);
+        if (lane == 0) {
+            IbMeta m;
+            for (int c = 0; c < 4; ++c) { m.e[c].x = 0.0; m.e[c].inc = 0; m.e[c].flag = 0; }
+            m.e[IB_NONE].flag = any_absent ? 1u : 0u;
+            const int alt_sum = (int)r.a, n_good = (int)r.b;
+            if (n_good >= 2) {
+                const double global_p = ddiv((double)alt_sum, dmul(2.0, (double)n_good));
+                for (int c = 0; c < 3; ++c) {
+                    const double freq = (P.flags & IB_F_GLOBAL) ? global_p : ddiv((double)(alt_sum - c), dmul(2.0, (double)(n_good - 1)));
+                    if ((P.flags & IB_F_SKIP_BOUNDARY) && (freq <= 0.0 || freq >= 1.0)) { if (P.flags & IB_F_COUNT_BOUNDARY) m.e[c].inc = 1u; }
+                    else { m.e[c].inc = (c == 1) ? 0x10001u : 1u; m.e[c].x = dmul(dmul(2.0, freq), dsub(1.0, freq)); }
+                }
+            }
+            P.ib_rows[rank] = m;
         }
     }
 }
@@ -2675,7 +2682,8 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 // order rounds differently.  Per site and sample: one table look-up and one add (a sample that adds nothing adds +0.0).
 // Chunks are applied strictly in order: a chunk whose predecessor has not been applied yet (it is being run again) is left
 // alone and reported by ib_finish_kernel.
-constexpr int IB_TILE = 128, IB_STAGES = 4;
+constexpr int IB_TILE = 128, IB_STAGES = 3;
+static_assert((IB_TILE - 16) % 16 == 0, "the row loop of ib_accumulate_kernel takes 8 + 16 n + 8 rows");
 __global__ void __launch_bounds__(32)
 ib_accumulate_kernel(const KParams P) {
     __shared__ __align__(16) uint8_t sm_codes[IB_STAGES][IB_TILE * 32];
@@ -2690,7 +2698,7 @@ ib_accumulate_kernel(const KParams P) {
     double sum = (fresh || !live) ? 0.0 : S.sum[s];
     unsigned long long het = (fresh || !live) ? 0ULL : S.het[s];
     unsigned int used = (fresh || !live) ? 0u : S.used[s];
-    uint32_t last = (fresh || !live) ? 0u : (uint32_t)S.last[s];
+    uint32_t last = (fresh || !live) ? 0u : 16u * (uint32_t)S.last[s];            // (as an entry offset, like the panel bytes)
     const uint8_t *pan = P.ib_panels + (unsigned long long)blockIdx.x * R * 32ULL;
     const unsigned long long ntiles = (R + IB_TILE - 1) / IB_TILE;
     auto issue = [&](unsigned long long t) {
@@ -2700,9 +2708,16 @@ ib_accumulate_kernel(const KParams P) {
             const uint8_t *gc = pan + t * (IB_TILE * 32ULL);
             const uint8_t *gm = reinterpret_cast<const uint8_t *>(P.ib_rows) + t * (IB_TILE * (unsigned long long)sizeof(IbMeta));
             for (uint32_t q = lane; q < nrows * 2u; q += 32) cp_async16(&sm_codes[st][q * 16u], gc + q * 16u);
-            for (uint32_t q = lane; q < nrows * 3u; q += 32) cp_async16(reinterpret_cast<uint8_t *>(&sm_meta[st][0]) + q * 16u, gm + q * 16u);
+            for (uint32_t q = lane; q < nrows * 4u; q += 32) cp_async16(reinterpret_cast<uint8_t *>(&sm_meta[st][0]) + q * 16u, gm + q * 16u);
         }
         cp_async_commit();                                           // (an empty group keeps the count of groups in step)
+    };
+    // one row: the sample's entry offset, its entry (one 16-byte load), one add to the chain, one to the counters
+    struct Ent { double x; uint32_t inc; };
+    auto entry = [](const uint8_t *row, uint32_t off) {
+        union { uint4 v; IbEntry e; } u;
+        u.v = *reinterpret_cast<const uint4 *>(row + off);
+        Ent e; e.x = u.e.x; e.inc = u.e.inc; return e;
     };
     for (int j = 0; j < IB_STAGES - 1; ++j) issue((unsigned long long)j);
     for (unsigned long long t = 0; t < ntiles; ++t) {
@@ -2712,43 +2727,52 @@ ib_accumulate_kernel(const KParams P) {
         const int st = (int)(t % IB_STAGES);
         const uint32_t nrows = (uint32_t)min((unsigned long long)IB_TILE, R - t * IB_TILE);
         const uint8_t *cs = &sm_codes[st][lane];
-        const IbMeta *ms = &sm_meta[st][0];
+        const uint8_t *ms = reinterpret_cast<const uint8_t *>(&sm_meta[st][0]);
+        // does any row of the tile lack a column?  (file mode only; the sample then keeps its last code)
+        uint32_t fl = 0;
+        for (uint32_t k = lane; k < nrows; k += 32) fl |= sm_meta[st][k].e[IB_NONE].flag;
+        const bool absent = __any_sync(FULL, fl != 0);
         uint32_t cnt = 0;
-        // The adds of one sample form a chain (each waits for the one before it); the look-ups of the NEXT eight rows are
-        // written between them so that the in-order issue has something to do while an add is under way.
+        // The adds of one sample form a chain; the look-ups of the NEXT eight rows are written between them so that the
+        // in-order issue has something to do while an add is under way.
         uint32_t k = 0;
-        if (nrows >= 8) {
-            double xa[8];
+        if (!absent && nrows == IB_TILE) {
+            Ent xa[8], xb[8];                                          // (two sets taking turns: no register is copied)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                uint32_t c = cs[(uint32_t)j * 32u];
-                c = (c == IB_ABSENT) ? last : c; last = c;
-                xa[j] = ms[j].x[c]; cnt += ms[j].inc[c];
-            }
-            for (k = 8; k + 8 <= nrows; k += 8) {
+            for (int j = 0; j < 8; ++j) xa[j] = entry(ms + j * 64, cs[j * 32]);
+#pragma unroll 1
+            for (k = 8; k + 16 <= IB_TILE; k += 16) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    uint32_t c = cs[(k + j) * 32u];
-                    c = (c == IB_ABSENT) ? last : c; last = c;
-                    const double xn = ms[k + j].x[c];
-                    cnt += ms[k + j].inc[c];
-                    sum = dadd(sum, xa[j]);
-                    xa[j] = xn;
+                    xb[j] = entry(ms + (k + j) * 64, cs[(k + j) * 32]);
+                    sum = dadd(sum, xa[j].x); cnt += xa[j].inc;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    xa[j] = entry(ms + (k + 8 + j) * 64, cs[(k + 8 + j) * 32]);
+                    sum = dadd(sum, xb[j].x); cnt += xb[j].inc;
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) sum = dadd(sum, xa[j]);
+            for (int j = 0; j < 8; ++j) {                            // rows IB_TILE-8 .. IB_TILE-1 come in while the set before them is added
+                xb[j] = entry(ms + (IB_TILE - 8 + j) * 64, cs[(IB_TILE - 8 + j) * 32]);
+                sum = dadd(sum, xa[j].x); cnt += xa[j].inc;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { sum = dadd(sum, xb[j].x); cnt += xb[j].inc; }
+            last = cs[(IB_TILE - 1) * 32];
+            k = IB_TILE;
         }
         for (; k < nrows; ++k) {
-            uint32_t c = cs[k * 32u];
-            c = (c == IB_ABSENT) ? last : c; last = c;
-            sum = dadd(sum, ms[k].x[c]);
-            cnt += ms[k].inc[c];
+            uint32_t off = cs[k * 32u];
+            off = (off == 16u * IB_ABSENT) ? last : off; last = off;
+            const Ent e = entry(ms + k * 64, off);
+            sum = dadd(sum, e.x); cnt += e.inc;
         }
         used += cnt & 0xFFFFu; het += cnt >> 16;
         __syncwarp();
     }
-    if (live) { S.sum[s] = sum; S.het[s] = het; S.used[s] = used; S.last[s] = (uint8_t)last; }
+    if (live) { S.sum[s] = sum; S.het[s] = het; S.used[s] = used; S.last[s] = (uint8_t)(last >> 4); }
     if (s == 0) S.variants = (fresh ? 0ULL : S.variants) + P.stats->rows;
 }
 
