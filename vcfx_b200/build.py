@@ -46,10 +46,22 @@ def _newer(target: Path, sources) -> bool:
 
 
 def _run(cmd, **kw):
-    r = subprocess.run([str(c) for c in cmd], capture_output=True, text=True, **kw)
+    """Runs a compiler.  The file behind "-o" is written under a private name and renamed when it is complete: several
+    processes (parallel test workers) may build the same target at once, and none of them may load a half-written one."""
+    cmd = [str(c) for c in cmd]
+    final = tmp = None
+    if "-o" in cmd:
+        i = cmd.index("-o") + 1
+        final = Path(cmd[i]); tmp = final.with_name(f".{final.name}.{os.getpid()}")
+        cmd[i] = str(tmp)
+    r = subprocess.run(cmd, capture_output=True, text=True, **kw)
     if r.returncode != 0:
-        sys.stderr.write(" ".join(str(c) for c in cmd) + "\n" + r.stdout + r.stderr)
+        if tmp is not None and tmp.exists():
+            tmp.unlink()
+        sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
         raise RuntimeError(f"build step failed: {cmd[0]}")
+    if tmp is not None:
+        os.replace(tmp, final)
     return r
 
 
