@@ -104,6 +104,18 @@ def phase_checker_stderr(data: bytes, mode: int = FILE) -> bytes:
     return out
 
 
+def genotype_query(data: bytes, query: str, mode: int = FILE, strict: bool = False):
+    """VCFX_genotype_query -g query [--strict]: (Result with stdout, stderr text of a run without -q)."""
+    l = lib()
+    l.oracle_genotype_query.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_char_p, C.c_int, C.POINTER(_Result), C.POINTER(_Result)]
+    r, e = _Result(), _Result()
+    l.oracle_genotype_query(data, len(data), mode, query.encode(), int(strict), C.byref(r), C.byref(e))
+    res = Result(r)
+    err = C.string_at(e.out, e.out_len) if e.out_len else b""
+    l.oracle_free(C.byref(r)); l.oracle_free(C.byref(e))
+    return res, err
+
+
 IB_GLOBAL, IB_SKIP_BOUNDARY, IB_COUNT_BOUNDARY, IB_QUIET = 1, 2, 4, 8
 IB_MESSAGES = {0: b"", 1: b"Error: Empty file.\n", 2: b"Error: No #CHROM line or no samples found.\n", 3: b"No biallelic variants found.\n",
                4: b"Error: No #CHROM line found.\n", 5: b"Error: No sample columns found.\n"}

@@ -1072,6 +1072,102 @@ int oracle_inbreeding(const char *in, size_t n, int mode, int flags, oracle_resu
     return 0;
 }
 
+/* ------------------------------------------------------------------ genotype_query (§8 f2): only lines in which at least one sample has the
+ * queried genotype pass; '#' lines pass (stdin mode holds them back until the next data line comes), empty lines vanish;
+ * no '\r' is cut anywhere. */
+
+/* VCFX_genotype_query.cpp:246-272 parseDiploidAlleles; *a1 / *a2 keep whatever was assigned before a failure (the query is
+ * parsed with them preset to -1 and used even when the parse fails, :640-644) */
+static int gq_parse(const char *g, size_t n, int *a1, int *a2) {
+    size_t sp = 0;
+    while (sp < n && g[sp] != '|' && g[sp] != '/') ++sp;
+    if (sp == n || sp == 0 || sp == n - 1) return 0;
+    if (sp == 1 && g[0] == '.') return 0;
+    *a1 = 0;
+    for (size_t i = 0; i < sp; ++i) { if (g[i] < '0' || g[i] > '9') return 0; *a1 = (int)((unsigned)*a1 * 10u + (unsigned)(g[i] - '0')); }
+    if (n - sp - 1 == 1 && g[sp + 1] == '.') return 0;
+    *a2 = 0;
+    for (size_t i = sp + 1; i < n; ++i) { if (g[i] < '0' || g[i] > '9') return 0; *a2 = (int)((unsigned)*a2 * 10u + (unsigned)(g[i] - '0')); }
+    return 1;
+}
+
+/* :275-317 genotypeMatchesFast (qa <= qb: the caller sorted them) */
+static int gq_match(const char *g, size_t n, const char *q, size_t qn, int qa, int qb, int strict) {
+    if (strict) return n == qn && memcmp(g, q, n) == 0;
+    if (n == 3 && qn == 3) {
+        if (g[1] != '|' && g[1] != '/') return 0;
+        if (g[0] < '0' || g[0] > '9' || g[2] < '0' || g[2] > '9') return 0;
+        int ga = g[0] - '0', gb = g[2] - '0';
+        if (ga > gb) { int t = ga; ga = gb; gb = t; }
+        return ga == qa && gb == qb;
+    }
+    int a1, a2;
+    if (!gq_parse(g, n, &a1, &a2)) return 0;
+    if (a1 > a2) { int t = a1; a1 = a2; a2 = t; }
+    return a1 == qa && a2 == qb;
+}
+
+/* :322-344 checkAnySampleMatches */
+static int gq_any(const char *s, const char *e, int gi, const char *q, size_t qn, int qa, int qb, int strict) {
+    const char *p = s;
+    for (int i = 0; i < 9 && p < e; ++i) { const char *t = memchr(p, '\t', (size_t)(e - p)); if (!t) return 0; p = t + 1; }
+    while (p < e) {
+        const char *se = memchr(p, '\t', (size_t)(e - p)); if (!se) se = e;
+        const char *gs, *ge;
+        nr_nth_piece(p, se, gi, &gs, &ge);
+        if (ge > gs && gq_match(gs, (size_t)(ge - gs), q, qn, qa, qb, strict)) return 1;
+        p = se + 1;
+    }
+    return 0;
+}
+
+/* r: stdout; err: what goes to stderr without -q */
+int oracle_genotype_query(const char *in, size_t n, int mode, const char *query, int strict, oracle_result *r, oracle_result *err) {
+    res_init(r); res_init(err);
+    obuf o = {0}, eb = {0};
+    const size_t qn = strlen(query);
+    int qa = -1, qb = -1;
+    if (!strict) { gq_parse(query, qn, &qa, &qb); if (qa > qb) { int t = qa; qa = qb; qb = t; } }
+    size_t pos = 0; line_t ln; int found = 0;
+    /* stdin mode: '#' lines wait for the next data line (:559-571) */
+    const char **hs = NULL; size_t *hl = NULL; size_t nh = 0, caph = 0;
+    while (next_line(in, n, &pos, &ln)) {
+        const char *s = ln.s, *e = ln.e;
+        if (s == e) continue;
+        if (*s == '#') {
+            if (e - s >= 6 && memcmp(s, "#CHROM", 6) == 0) found = 1;
+            if (mode == ORACLE_FILE) { ob_put(&o, s, (size_t)(e - s)); ob_ch(&o, '\n'); }
+            else {
+                if (nh == caph) { caph = caph ? caph * 2 : 64; hs = realloc(hs, caph * sizeof *hs); hl = realloc(hl, caph * sizeof *hl); }
+                hs[nh] = s; hl[nh] = (size_t)(e - s); ++nh;
+            }
+            continue;
+        }
+        if (!found) { ob_str(&eb, "Error: No #CHROM header found before data lines.\n"); goto done; }     /* the run ends here */
+        for (size_t i = 0; i < nh; ++i) { ob_put(&o, hs[i], hl[i]); ob_ch(&o, '\n'); }
+        nh = 0;
+        r->data_lines++;
+        const char *f = s; int short_line = 0;
+        for (int i = 0; i < 8 && f < e; ++i) { const char *t = memchr(f, '\t', (size_t)(e - f)); if (!t) { short_line = 1; break; } f = t + 1; }
+        if (short_line) {
+            r->warnings++;
+            ob_str(&eb, "Warning: skipping line with <9 fields");
+            if (mode != ORACLE_FILE) { ob_str(&eb, ": "); ob_put(&eb, s, (size_t)(e - s)); }
+            ob_ch(&eb, '\n');
+            continue;
+        }
+        const char *fe = memchr(f, '\t', (size_t)(e - f)); if (!fe) fe = e;
+        int gi = oracle_gt_index(f, (size_t)(fe - f));
+        if (gi < 0) continue;
+        if (gq_any(s, e, gi, query, qn, qa, qb, strict)) { ob_put(&o, s, (size_t)(e - s)); ob_ch(&o, '\n'); r->rows++; }
+    }
+    if (mode != ORACLE_FILE && !found) ob_str(&eb, "Error: No #CHROM line found in VCF.\n");
+done:
+    free(hs); free(hl);
+    res_take(r, &o); res_take(err, &eb);
+    return 0;
+}
+
 /* ------------------------------------------------------------------ variant_counter */
 
 /* variant_counter.cpp:31-44 — at least 7 tabs. */

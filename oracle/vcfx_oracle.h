@@ -51,6 +51,8 @@ int oracle_missing(const char *in, size_t n, int mode, oracle_result *r);
 int oracle_phase_checker(const char *in, size_t n, int mode, oracle_result *r);    /* VCFX_phase_checker (§8 f2) */
 int oracle_phase_checker_err(const char *in, size_t n, int mode, oracle_result *r, oracle_result *err);   /* + stderr text without -q */
 int oracle_indexer(const char *in, size_t n, int mode, oracle_result *r);          /* VCFX_indexer (§8 f4) */
+/* VCFX_genotype_query (§8 f2): r = stdout, err = the stderr text of a run without -q */
+int oracle_genotype_query(const char *in, size_t n, int mode, const char *query, int strict, oracle_result *r, oracle_result *err);
 /* VCFX_inbreeding_calculator (§8 f3); flags: 1 --freq-mode global, 2 --skip-boundary, 4 --count-boundary-as-used, 8 -q */
 int oracle_inbreeding(const char *in, size_t n, int mode, int flags, oracle_result *r);
 int oracle_nonref_filter(const char *in, size_t n, int mode, oracle_result *r);   /* VCFX_nonref_filter (§8 f2) */
