@@ -57,6 +57,11 @@ typedef enum {
                                      (a sample-axis reduction): cfg.n_sel / sel_names / sel_name_off = the samples of the
                                      "#CHROM" line in column order (sel_col is not used); the per-sample sums live in the context from
                                      chunk to chunk and the text ("name \t F \n" per sample) comes with the chunk submitted as final */
+    VCFX_OP_GENOTYPE_QUERY = 9,   /* VCFX_genotype_query.cpp:433-517 genotypeQueryMmap, :527-614 genotypeQueryStream: cfg.sel_names =
+                                     the -g argument, cfg.n_sel = its length in bytes (< 64); VCFX_F_GQ_STRICT = --strict.  The caller
+                                     ends the input in front of a data line that comes before the "#CHROM" line and, in stdin mode,
+                                     holds back '#' lines until a data line follows; vcfx_cuda_short_lines returns (offset << 2 | 2)
+                                     for every line that earns "skipping line with <9 fields" */
     VCFX_OP_INDEX          = 6,   /* VCFX_indexer.cpp:205-322 createVCFIndexMmap, :329-443 createVCFIndex */
     VCFX_OP_NONREF_FILTER  = 5    /* VCFX_nonref_filter.cpp:458-548 filterNonRefMmap, :553-631 filterNonRef */
 } vcfx_op;
@@ -79,6 +84,7 @@ typedef enum {
 } vcfx_err;
 
 /* allele_counter variants (cfg.flags) */
+#define VCFX_F_GQ_STRICT         0x01u  /* genotype_query --strict: byte-for-byte comparison (:277-279)               */
 #define VCFX_F_IB_GLOBAL         0x01u  /* inbreeding_calculator --freq-mode global (:596-604)                 */
 #define VCFX_F_IB_SKIP_BOUNDARY  0x02u  /* --skip-boundary (:614-620)                                          */
 #define VCFX_F_IB_COUNT_BOUNDARY 0x04u  /* --count-boundary-as-used                                            */

@@ -9,7 +9,7 @@ import pytest
 ROOT = Path(__file__).resolve().parent.parent
 BIN = ROOT / "vcfx_b200" / "bin"
 REF = ROOT / "oracle" / "_ref"
-TOOLS = ["allele_freq_calc", "hwe_tester", "missing_detector", "variant_counter", "allele_counter", "nonref_filter", "indexer", "phase_checker", "inbreeding_calculator"]
+TOOLS = ["allele_freq_calc", "hwe_tester", "missing_detector", "variant_counter", "allele_counter", "nonref_filter", "indexer", "phase_checker", "inbreeding_calculator", "genotype_query"]
 
 
 def run(exe, args):
@@ -29,8 +29,15 @@ def built():
 
 @pytest.mark.parametrize("tool", TOOLS)
 @pytest.mark.parametrize("args", [["--help"], ["-h"], ["--version"], ["-v"], ["-i", "/nonexistent/x.vcf"], ["/nonexistent/x.vcf"],
-                                  ["--no-such-option"], ["-q", "-i", "/nonexistent/x.vcf"], ["--help", "--version"]])
+                                  ["--no-such-option"], ["-q", "-i", "/nonexistent/x.vcf"], ["--help", "--version"], ["-g", "0/1", "-i", "/nonexistent/x.vcf"]])
 def test_same_as_reference_without_a_device(tool, args):
     mine = run(BIN / f"VCFX_{tool}", args)
     ref = run(REF / f"VCFX_{tool}", args)
     assert mine == ref, (tool, args, mine, ref)
+
+
+def test_genotype_query_without_a_query_prints_its_usage_line():
+    for args in ([], ["-q"], ["-i", "/nonexistent/x.vcf"], ["-g", ""]):
+        mine = run(BIN / "VCFX_genotype_query", args)
+        ref = run(REF / "VCFX_genotype_query", args)
+        assert mine == ref, (args, mine, ref)

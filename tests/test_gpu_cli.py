@@ -127,6 +127,34 @@ def test_phase_checker(files, tmp_path):
     assert a[2] == b[2]
 
 
+def test_genotype_query(files, tmp_path):
+    """VCFX_genotype_query: stdout and stderr, file and stdin, flexible and strict, several chunks (stdin mode's
+    '#' lines wait for a data line across chunk borders), the run that ends at a data line in front of the header."""
+    import golden_util
+    q = tmp_path / "q.vcf"; q.write_bytes(golden_util.load()["gq_quirks"][0])
+    tails = tmp_path / "t.vcf"
+    body = synth.make_vcf(3, 300, 60, seed=31)
+    tails.write_bytes(body + b"#t1\n\n#t2\n" + b"#pad\n" * 2000)                      # '#' lines behind the last data line, several chunks of them
+    nohdr = tmp_path / "n.vcf"; nohdr.write_bytes(b"##f\n#x\n1\t1\t.\tA\tG\t.\t.\t.\tGT\t0/1\n" + body)
+    for p in (files["late"], files["crlf"], q, tails, nohdr):
+        for args in (["-g", "0/1"], ["-g", "1|1", "--strict"]):
+            a, b = both("genotype_query", [*args, "-i", str(p)])
+            assert a[2] == b[2]
+            a, b = both("genotype_query", args, stdin=p.read_bytes())
+            assert a[2] == b[2]
+    a, b = both("genotype_query", ["-g", "0/1", "-q", str(q)])
+    assert a[2] == b[2] == b""
+    a, b = both("genotype_query", ["--genotype-query", "1/0", "--quiet"], stdin=q.read_bytes())
+    assert a[2] == b[2] == b""
+    for f, env in ((tails, {"VCFX_CHUNK_BYTES": "4096"}), (files["c3"], SMALL_CHUNK), (q, {"VCFX_CHUNK_BYTES": "256"})):
+        a, b = both("genotype_query", ["-g", "0/1", "-i", str(f)], env=env)
+        assert a[2] == b[2]
+        a, b = both("genotype_query", ["-g", "0/1"], stdin=f.read_bytes(), env=env)
+        assert a[2] == b[2]
+    a, b = both("genotype_query", ["-g", "2/2", "-i", str(files["c3"])], env=SMALL_CHUNK)     # nothing matches: the header alone
+    assert a[2] == b[2]
+
+
 def test_inbreeding_calculator(files, tmp_path):
     """VCFX_inbreeding_calculator: file (-i and positional) and stdin, every option, several chunks (the
     per-sample sums are carried from chunk to chunk in file order), the quirks fixture, the fixed messages."""
@@ -178,10 +206,14 @@ def test_indexer(files, tmp_path):
     both("indexer", [], stdin=files["nonl"].read_bytes(), env={"VCFX_CHUNK_BYTES": "4096"})
 
 
-@pytest.mark.parametrize("tool", ["allele_freq_calc", "hwe_tester", "missing_detector", "variant_counter", "allele_counter", "nonref_filter", "indexer", "phase_checker", "inbreeding_calculator"])
+@pytest.mark.parametrize("tool", ["allele_freq_calc", "hwe_tester", "missing_detector", "variant_counter", "allele_counter", "nonref_filter", "indexer", "phase_checker", "inbreeding_calculator", "genotype_query"])
 def test_flags(tool, files):
     for args in (["--help"], ["-v"]):
         both(tool, args)
+    if tool == "genotype_query":
+        a, b = both(tool, ["-g", "0/1", "-i", "/nonexistent/file.vcf"]); assert a[2] == b[2]
+        a, b = both(tool, ["-g", "0/1"], stdin=b""); assert a[2] == b[2]
+        return
     a, b = both(tool, ["/nonexistent/file.vcf"] if tool == "variant_counter" else (["-i", "/nonexistent/file.vcf"] if tool in ("nonref_filter", "phase_checker") else ["/nonexistent/file.vcf"] if tool == "indexer" else ["-q", "-i", "/nonexistent/file.vcf"]))
     assert a[2] == b[2]
     # empty stdin: per-tool behaviour (help+rc1 / header only / nothing / Total 0); phase_checker without arguments prints its

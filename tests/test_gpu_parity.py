@@ -20,7 +20,7 @@ def _cmp(name, got, exp):
                              f"  got {got[max(0, i - 60): i + 60]!r}\n  exp {exp[max(0, i - 60): i + 60]!r}")
 
 
-def run_all(api, O, data, tag, chunk_bytes=0, tile_bytes=0, tools=("af", "hwe", "vc", "md", "nr", "ix", "pc", "ib")):
+def run_all(api, O, data, tag, chunk_bytes=0, tile_bytes=0, tools=("af", "hwe", "vc", "md", "nr", "ix", "pc", "ib", "gq")):
     kw = dict(chunk_bytes=chunk_bytes, tile_bytes=tile_bytes)
     for mode in MODES:
         if "af" in tools:
@@ -51,6 +51,11 @@ def run_all(api, O, data, tag, chunk_bytes=0, tile_bytes=0, tools=("af", "hwe", 
             _cmp(f"{tag} pc mode{mode}", r.out, o.out)
             _cmp(f"{tag} pc mode{mode} stderr", r.err, O.phase_checker_stderr(data, mode))
             assert (r.totals.rows, r.totals.pre_header, r.totals.flagged) == (o.rows, o.warnings, o.flagged + o.warnings)
+        if "gq" in tools:
+            for q, strict in ((("0/1", False), ("1|1", True)) if mode == 0 else (("1/1", False), ("0|1", True))):
+                r = api.genotype_query(data, q, mode, strict, **kw); o, e = O.genotype_query(data, q, mode, strict)
+                _cmp(f"{tag} gq {q} strict{strict} mode{mode}", r.out, o.out)
+                _cmp(f"{tag} gq {q} strict{strict} mode{mode} stderr", r.err, e)
         if "ib" in tools:
             for fl in ((0, 6) if mode == 0 else (0, 1)):
                 r = api.inbreeding_calculator(data, mode, bool(fl & 1), bool(fl & 2), bool(fl & 4), quiet=False, **kw); o = O.inbreeding(data, mode, fl)
@@ -414,6 +419,37 @@ def test_phase_checker_more_dropped_lines_than_the_event_list(cuda_api, oracle):
     o = oracle.phase_checker(data, 0)
     assert r.out == o.out and r.totals.flagged == n
     assert r.err == b"Warning: Invalid VCF line with fewer than 10 columns; skipping line.\n" * n
+
+
+def test_genotype_query_cases(cuda_api, oracle):
+    """VCFX_genotype_query: flexible and strict queries (also ones the reference's parser gives up on half way), the quirks
+    fixture, lines on the four-byte lattice of every length where only the LAST sample — or none — has the genotype."""
+    import golden_util
+    data, _ = golden_util.load()["gq_quirks"]
+    for kw in ({}, {"tile_bytes": 512}, {"chunk_bytes": 4096}):
+        for mode in MODES:
+            for q, strict in (("0/1", False), ("1/0", False), ("0|1", True), ("1/1", False), ("0/x", False), ("x/0", False), ("./.", True), ("./.", False),
+                              ("10/1", False), ("0/01", False), ("0", True), ("1/0:4", True), ("0/1\r", True)):
+                r = cuda_api.genotype_query(data, q, mode, strict, **kw); o, e = oracle.genotype_query(data, q, mode, strict)
+                _cmp(f"gq quirks {kw} mode{mode} {q!r} strict{strict}", r.out, o.out)
+                _cmp(f"gq quirks {kw} mode{mode} {q!r} strict{strict} stderr", r.err, e)
+    hdr = b"##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t"
+    for S in (1, 2, 100, 127, 128, 129, 256, 257, 700):
+        lines = []
+        for k in range(40):
+            gts = [b"0|0" if (i + k) % 3 else b"0/0" for i in range(S)]
+            if k % 3 == 1:
+                gts[-1] = [b"0|1", b"1/0", b"1|1", b"0/1:5", b"01/0"][k % 5]
+            if k % 7 == 3:
+                gts[(k * 11) % S] = b"1|0"
+            lines.append(b"%d\t%d\t%s\tA\tG\t.\tPASS\t.\tGT\t" % (k % 22 + 1, 10 ** (k % 6), b"r" * (k % 4)) + b"\t".join(gts))
+        data = hdr + b"\t".join(b"S%d" % i for i in range(S)) + b"\n" + b"\n".join(lines) + (b"\n" if S % 2 else b"")
+        run_all(cuda_api, oracle, data, f"gq S{S}", tools=("gq",))
+        run_all(cuda_api, oracle, data, f"gq S{S} tile512", tile_bytes=512, tools=("gq",))
+    # the run ends at a data line in front of the header; '#' lines behind the last data line (stdin mode drops them)
+    for data in (b"##f\n1\t1\t.\tA\tG\t.\t.\t.\tGT\t0/1\n" + hdr + b"S1\n1\t1\t.\tA\tG\t.\t.\t.\tGT\t0/1\n",
+                 hdr + b"S1\n1\t1\t.\tA\tG\t.\t.\t.\tGT\t0/1\n#a\n\n#b\n", hdr + b"S1\n#only\n", b"##f\n#x\n", b"", b"\n\n"):
+        run_all(cuda_api, oracle, data, "gq stream edges", tools=("gq",))
 
 
 def test_inbreeding_calculator_cases(cuda_api, oracle):

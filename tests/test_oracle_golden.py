@@ -38,6 +38,12 @@ def check_case(O, data, exp, name):
             assert (r.rc, r.out) == exp[key][:2], (name, key)
             if not strict:
                 assert r.warnings == exp[key][2], (name, key)
+    for key, mode, q, strict in (("file.het", O.FILE, "0/1", False), ("stdin.het", O.STDIN, "1/0", False),
+                                 ("file.strict", O.FILE, "0|1", True), ("stdin.strict", O.STDIN, "1/1", True)):
+        k = f"genotype_query.{key}"
+        if k in exp:
+            r, err = O.genotype_query(data, q, mode, strict)
+            assert (r.rc, r.out, err) == tuple(exp[k][:3]), (name, k)
     for key, mode, flags in (("file", O.FILE, 0), ("stdin", O.STDIN, 0), ("file.global", O.FILE, O.IB_GLOBAL),
                              ("file.skipcount", O.FILE, O.IB_SKIP_BOUNDARY | O.IB_COUNT_BOUNDARY), ("stdin.skip", O.STDIN, O.IB_SKIP_BOUNDARY)):
         k = f"inbreeding_calculator.{key}"
@@ -98,6 +104,12 @@ def test_oracle_matches_reference_binaries_fuzz(oracle, seed):
         assert (r.rc, r.out, O.phase_checker_stderr(data, O.STDIN)) == (rc, out, err), "phase_checker stdin"
         rc, out, err = O.run_ref("phase_checker", ["-q"], stdin=data)
         assert (rc, out, err) == (r.rc, r.out, b""), "phase_checker -q"
+        for q, strict in (("0/1", False), ("1|1", True), ("2/0", False)):
+            a = ["-g", q] + (["--strict"] if strict else [])
+            rc, out, err = O.run_ref("genotype_query", [*a, "-i", f.name]); r, e = O.genotype_query(data, q, O.FILE, strict)
+            assert (r.rc, r.out, e) == (rc, out, err), ("genotype_query file", a)
+            rc, out, err = O.run_ref("genotype_query", a, stdin=data); r, e = O.genotype_query(data, q, O.STDIN, strict)
+            assert (r.rc, r.out, e) == (rc, out, err), ("genotype_query stdin", a)
         for flags, args in ((0, []), (O.IB_GLOBAL, ["--freq-mode", "global"]), (O.IB_SKIP_BOUNDARY, ["--skip-boundary"]),
                             (O.IB_SKIP_BOUNDARY | O.IB_COUNT_BOUNDARY, ["--skip-boundary", "--count-boundary-as-used"])):
             rc, out, err = O.run_ref("inbreeding_calculator", ["-q", *args, "-i", f.name]); r = O.inbreeding(data, O.FILE, flags | O.IB_QUIET)

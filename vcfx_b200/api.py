@@ -17,7 +17,7 @@ from pathlib import Path
 
 from . import build as _build
 
-OP_VARIANT_COUNT, OP_ALLELE_FREQ, OP_HWE, OP_MISSING_DETECT, OP_ALLELE_COUNT, OP_NONREF_FILTER, OP_INDEX, OP_PHASE_CHECK, OP_INBREEDING = range(9)
+OP_VARIANT_COUNT, OP_ALLELE_FREQ, OP_HWE, OP_MISSING_DETECT, OP_ALLELE_COUNT, OP_NONREF_FILTER, OP_INDEX, OP_PHASE_CHECK, OP_INBREEDING, OP_GENOTYPE_QUERY = range(10)
 FILE, STDIN = 0, 1
 F_AC_AGGREGATE, F_AC_BINARY, F_AC_FORWARD = 1, 2, 4
 DEVICE_PAD = 8192
@@ -152,7 +152,7 @@ class Context:
 
     def __init__(self, op: int, mode: int = FILE, device: int = 0, flags: int = 0, chunk_bytes: int = 0,
                  out_bytes: int = 0, n_slots: int = 0, tile_bytes: int = 0, stream: int | None = None,
-                 sel_cols=None, sel_names=None):
+                 sel_cols=None, sel_names=None, query: bytes | None = None):
         self._l = load()
         self._h = C.c_void_p()
         cfg = Cfg(device=device, op=op, mode=mode, flags=flags, chunk_bytes=chunk_bytes, out_bytes=out_bytes,
@@ -168,6 +168,9 @@ class Context:
             off_arr = (C.c_uint32 * (n + 1))(*offs)
             cfg.n_sel = n; cfg.sel_col = cols; cfg.sel_names = blob; cfg.sel_name_off = off_arr
             self._keep = [cols, blob, off_arr]
+        if query is not None:                      # genotype_query: the -g argument travels in sel_names, its length in n_sel
+            cfg.n_sel = len(query); cfg.sel_names = query
+            self._keep = [query]
         self._check(self._l.vcfx_cuda_create(C.byref(cfg), C.byref(self._h)))
         self.op, self.mode = op, mode
 
@@ -549,6 +552,63 @@ def inbreeding_calculator(data: bytes, mode: int = FILE, freq_global: bool = Fal
         ctx.close()
     err = IB_MESSAGES[3] if (tot.rows == 0 and not quiet) else b""
     return ToolResult(IB_HEADER + b"".join(outs), 0, tot, err)
+
+
+F_GQ_STRICT = 1
+
+
+def genotype_query(data: bytes, query: str, mode: int = FILE, strict: bool = False, quiet: bool = False, chunk_bytes: int = 0, **kw) -> ToolResult:
+    """VCFX_genotype_query -g query [--strict]: '#' lines pass, empty lines vanish, a data line passes when one of its
+    samples has the queried genotype (VCFX_genotype_query.cpp:433-517 file mode, :527-614 stdin mode).  What depends on
+    the lines before or behind is settled here: the run ends at a data line that comes before the "#CHROM" line (file
+    mode has written the '#' lines in front of it by then, stdin mode nothing), and stdin mode holds '#' lines back until
+    the next data line, so those behind the last data line never appear.  ``err`` = the text on stderr without -q."""
+    q = query.encode()
+    assert q, "the tool prints its usage line for an empty query"
+    n, pos, found, first_data, last_data_end = len(data), 0, False, None, 0
+    while pos < n:
+        nl = data.find(b"\n", pos)
+        le = n if nl < 0 else nl
+        if le > pos:
+            if data[pos:pos + 1] == b"#":
+                if first_data is None and data[pos:pos + 6] == b"#CHROM":
+                    found = True
+            else:
+                if first_data is None:
+                    first_data = pos
+                    if not found:
+                        break
+                last_data_end = min(le + 1, n)
+        pos = le + 1
+    msgs = []
+    if first_data is not None and not found:
+        body = data[:first_data] if mode == FILE else b""
+        msgs.append(b"Error: No #CHROM header found before data lines.\n")
+    elif first_data is None:
+        body = data if mode == FILE else b""
+        if mode == STDIN and not found:
+            msgs.append(b"Error: No #CHROM line found in VCF.\n")
+    else:
+        body = data if mode == FILE else data[:last_data_end]
+    warn = []
+
+    def on_events(start, events):
+        for ev in events:
+            off = start + (ev >> 2)
+            nl = body.find(b"\n", off)
+            line = bytes(body[off:len(body) if nl < 0 else nl])
+            warn.append(b"Warning: skipping line with <9 fields" + (b"" if mode == FILE else b": " + line) + b"\n")
+
+    tot = Totals(); out = b""
+    if body:
+        chunk_bytes = chunk_bytes or min(64 << 20, max(1 << 20, (len(body) + (1 << 20) - 1) & ~((1 << 20) - 1)))
+        ctx = Context(OP_GENOTYPE_QUERY, mode, flags=F_GQ_STRICT if strict else 0, chunk_bytes=chunk_bytes, query=q, **kw)
+        try:
+            outs, tot = stream_bytes(ctx, body, chunk_bytes, 0, on_events)
+        finally:
+            ctx.close()
+        out = b"".join(outs)
+    return ToolResult(out, 0, tot, b"" if quiet else b"".join(warn + msgs))
 
 
 PC_UNPHASED, PC_PRE_HEADER, PC_SHORT, PC_NO_GT = range(4)      # why VCFX_OP_PHASE_CHECK dropped a line (event & 3)

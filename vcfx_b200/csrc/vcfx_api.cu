@@ -109,6 +109,8 @@ struct vcfx_ctx {
     int ac_fmt = 0;
     bool ac_ident = false;               // allele_counter selection = columns 0 .. n_sel-1 in order
     bool ac_exact = false;               // a chunk had a count of two digits: rows are sized by parsing from now on
+    // genotype_query: the query and what parseDiploidAlleles leaves of it
+    uint8_t gq_query[64] = {0}; uint32_t gq_len = 0; int gq_a = -1, gq_b = -1;
     // inbreeding_calculator: the per-sample state that lives from chunk to chunk, and the order the chunks are applied in
     IbState *d_ib = nullptr; double *d_ib_sum = nullptr; unsigned long long *d_ib_het = nullptr; unsigned int *d_ib_used = nullptr; uint8_t *d_ib_last = nullptr;
     cudaEvent_t ib_event = nullptr;      // the last chunk launched has been applied
@@ -142,6 +144,11 @@ void hwe_pvalue_launch(int grid, const int32_t *c, size_t n, double *p) { HweArg
 void hwe_pvalue_launch(int grid, const int32_t *c, size_t n, double *p) { hwe_pvalue_kernel<<<grid, 256>>>(c, n, p); }
 #endif
 
+// ops whose output is the input with lines dropped or rewritten (md_copy_kernel writes it)
+bool is_copy_op(int op) {
+    return op == VCFX_OP_MISSING_DETECT || op == VCFX_OP_NONREF_FILTER || op == VCFX_OP_PHASE_CHECK || op == VCFX_OP_GENOTYPE_QUERY;
+}
+
 kernel_fn kernel_for(int op) {
     switch (op) {
     case VCFX_OP_VARIANT_COUNT: return vcfx_scan_kernel<OP_VC, 0>;
@@ -152,6 +159,7 @@ kernel_fn kernel_for(int op) {
     case VCFX_OP_INDEX: return vcfx_scan_kernel<OP_IX, 0>;
     case VCFX_OP_PHASE_CHECK: return vcfx_scan_kernel<OP_PC, 0>;
     case VCFX_OP_INBREEDING: return vcfx_scan_kernel<OP_IB, 0>;
+    case VCFX_OP_GENOTYPE_QUERY: return vcfx_scan_kernel<OP_GQ, 0>;
     case VCFX_OP_ALLELE_COUNT:  return vcfx_scan_kernel<OP_AC, 0>;
     default: return nullptr;
     }
@@ -172,6 +180,7 @@ kernel_fn format_kernel_for(int op, int ac_fmt = 0) {
     case VCFX_OP_MISSING_DETECT: return md_copy_kernel;
     case VCFX_OP_NONREF_FILTER: return md_copy_kernel;
     case VCFX_OP_PHASE_CHECK: return md_copy_kernel;
+    case VCFX_OP_GENOTYPE_QUERY: return md_copy_kernel;
     case VCFX_OP_INDEX: return format_rows_kernel<OP_IX>;
     case VCFX_OP_INBREEDING: return ib_rows_kernel;
     default: return nullptr;
@@ -280,7 +289,7 @@ int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes, uint64_t min_recs = 0,
             cudaFree(w.tile_resume); w.tile_resume = nullptr;
             CU(cudaMalloc(&w.tile_resume, sizeof(uint32_t) * tiles));
         }
-        if (ctx->cfg.op == VCFX_OP_MISSING_DETECT || ctx->cfg.op == VCFX_OP_NONREF_FILTER || ctx->cfg.op == VCFX_OP_PHASE_CHECK) {
+        if (is_copy_op(ctx->cfg.op)) {
             cudaFree(w.tail_start); cudaFree(w.tail_len); cudaFree(w.tail_off);
             w.tail_start = w.tail_len = w.tail_off = nullptr;
             CU(cudaMalloc(&w.tail_start, sizeof(uint32_t) * tiles));
@@ -367,9 +376,10 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
     P.ac_fmt = ctx->ac_fmt; P.ac_ident = ctx->ac_ident ? 1 : 0; P.ac_pass = 0; P.ac_spec = (ctx->cfg.op == VCFX_OP_ALLELE_COUNT && ctx->ac_fmt == AC_TEXT_MT && !ctx->ac_exact) ? 1 : 0; P.n_sel = ctx->n_sel; P.sel_col = ctx->d_sel_col; P.name_off = ctx->d_name_off;
     P.names = ctx->d_names; P.names16 = ctx->d_names16; P.name_len = ctx->name_len; P.ac_bulk = ctx->ac_bulk ? 1 : 0; P.max_col = ctx->max_col; P.col_scratch = w.col_scratch;
     P.ticket = w.ticket; P.ticket2 = w.ticket + 1; P.tile_resume = w.tile_resume; P.recs = w.recs; P.rec_prefix = w.rec_prefix; P.rec_cap = w.rec_cap;
+    memcpy(P.gq_query, ctx->gq_query, sizeof P.gq_query); P.gq_len = ctx->gq_len; P.gq_a = ctx->gq_a; P.gq_b = ctx->gq_b; P.gq_strict = (ctx->cfg.flags & VCFX_F_GQ_STRICT) ? 1 : 0;
     P.ib_codes = w.ib_codes; P.ib_rows = w.ib_rows; P.ib_panels = w.ib_panels; P.ib_panel_cap = w.ib_panel_cap; P.ib = ctx->d_ib; P.ib_seq = w.ib_seq; P.ib_first = w.ib_first ? 1 : 0; P.text_cap = out_cap;
     if (ctx->cfg.op == VCFX_OP_INBREEDING) P.out_cap = ~0ULL;       // the scan counts rows there, not bytes of text
-    P.stats = w.d_stats; P.events = w.events; P.ev_cap = w.ev_cap; P.ev_raw = (ctx->cfg.op == VCFX_OP_PHASE_CHECK) ? 1 : 0;
+    P.stats = w.d_stats; P.events = w.events; P.ev_cap = w.ev_cap; P.ev_raw = (ctx->cfg.op == VCFX_OP_PHASE_CHECK || ctx->cfg.op == VCFX_OP_GENOTYPE_QUERY) ? 1 : 0;
 
     CU(cudaEventRecord(w.ev_k0, st));
     if (nbytes > 0) {
@@ -384,7 +394,7 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
         VCFX_LAUNCH(tile_scan_kernel, 1, 1024, SCAN_SMEM_BYTES, st, P);
         CU(cudaGetLastError());
         if (kernel_fn ff = format_kernel_for(ctx->cfg.op, ctx->ac_fmt)) {
-            VCFX_LAUNCH(ff, ctx->sm_count * ((ctx->cfg.op == VCFX_OP_MISSING_DETECT || ctx->cfg.op == VCFX_OP_NONREF_FILTER || ctx->cfg.op == VCFX_OP_PHASE_CHECK) ? 8 : 16), 256, 0, st, P);
+            VCFX_LAUNCH(ff, ctx->sm_count * ((is_copy_op(ctx->cfg.op)) ? 8 : 16), 256, 0, st, P);
             CU(cudaGetLastError());
         } else if (ctx->cfg.op == VCFX_OP_ALLELE_COUNT) {
             // rows are sized in the first pass and written in a second one at their scanned offsets
@@ -438,7 +448,7 @@ int fetch_events(vcfx_ctx *ctx, const Work &w, cudaStream_t st) {
 // phase_checker reports every dropped line: a chunk that dropped more lines than the list holds gets a longer list (and
 // is run again by the caller).  Returns 1 when it grew, 0 when nothing was lost, a negative vcfx_err on failure.
 int grow_events(vcfx_ctx *ctx, Work &w) {
-    if (ctx->cfg.op != VCFX_OP_PHASE_CHECK || w.h_stats->n_events <= w.ev_cap) return 0;
+    if ((ctx->cfg.op != VCFX_OP_PHASE_CHECK && ctx->cfg.op != VCFX_OP_GENOTYPE_QUERY) || w.h_stats->n_events <= w.ev_cap) return 0;
     const uint64_t want = w.h_stats->n_events + (w.h_stats->n_events >> 3) + 1024;
     if (want > 0xFFFFFFFFull) return VCFX_E_OUTPUT_TOO_BIG;
     cudaFree(w.events); w.events = nullptr; w.ev_cap = 0;
@@ -453,6 +463,7 @@ size_t default_out_bytes(int op, unsigned flags, size_t chunk) {
     case VCFX_OP_MISSING_DETECT: return chunk + chunk / 4 + 4096;
     case VCFX_OP_NONREF_FILTER: return chunk + 4096;          // never longer than the input plus one '\n'
     case VCFX_OP_PHASE_CHECK: return chunk + 4096;
+    case VCFX_OP_GENOTYPE_QUERY: return chunk + 4096;
     case VCFX_OP_INBREEDING: return 1u << 20;                 // create() sizes it from the names
     case VCFX_OP_ALLELE_COUNT:
         if (flags & VCFX_F_AC_AGGREGATE) return chunk / 4 + (1u << 20);
@@ -509,7 +520,7 @@ const char *vcfx_cuda_last_error(const vcfx_ctx *ctx) { return ctx ? ctx->last_e
 int vcfx_cuda_create(const vcfx_cfg *cfg, vcfx_ctx **out) {
     if (!cfg || !out) return VCFX_E_INVALID;
     *out = nullptr;
-    if (cfg->op < VCFX_OP_VARIANT_COUNT || cfg->op > VCFX_OP_INBREEDING) return VCFX_E_INVALID;
+    if (cfg->op < VCFX_OP_VARIANT_COUNT || cfg->op > VCFX_OP_GENOTYPE_QUERY) return VCFX_E_INVALID;
     if (cfg->mode != VCFX_MODE_FILE && cfg->mode != VCFX_MODE_STDIN) return VCFX_E_INVALID;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return VCFX_E_NO_DEVICE;
@@ -570,6 +581,30 @@ int vcfx_cuda_create(const vcfx_cfg *cfg, vcfx_ctx **out) {
             ctx->name_len = nl;
             const char *be = getenv("VCFX_AC_BULK");          // staged rows leave shared memory through cp.async.bulk (default; 0 = 128-bit stores)
             ctx->ac_bulk = !(be && *be == '0');
+        }
+    }
+    if (cfg->op == VCFX_OP_GENOTYPE_QUERY) {
+        // cfg.sel_names = the -g argument, cfg.n_sel = its length.  VCFX_genotype_query.cpp:246-272 parseDiploidAlleles on it,
+        // keeping whatever the parse assigned before it gave up (:640-644 uses the two numbers whether it succeeded or not)
+        if (!cfg->sel_names || cfg->n_sel == 0 || cfg->n_sel >= sizeof ctx->gq_query) return fail(VCFX_E_INVALID);
+        ctx->gq_len = cfg->n_sel;
+        memcpy(ctx->gq_query, cfg->sel_names, cfg->n_sel);
+        if (!(cfg->flags & VCFX_F_GQ_STRICT)) {
+            const char *g = cfg->sel_names; const size_t n = cfg->n_sel;
+            int a1 = -1, a2 = -1;
+            size_t sp = 0;
+            while (sp < n && g[sp] != '|' && g[sp] != '/') ++sp;
+            bool ok = !(sp == n || sp == 0 || sp == n - 1) && !(sp == 1 && g[0] == '.');
+            if (ok) {
+                a1 = 0;
+                for (size_t i = 0; i < sp && ok; ++i) { if (g[i] < '0' || g[i] > '9') ok = false; else a1 = (int)((unsigned)a1 * 10u + (unsigned)(g[i] - '0')); }
+            }
+            if (ok && !(n - sp - 1 == 1 && g[sp + 1] == '.')) {
+                a2 = 0;
+                for (size_t i = sp + 1; i < n; ++i) { if (g[i] < '0' || g[i] > '9') break; a2 = (int)((unsigned)a2 * 10u + (unsigned)(g[i] - '0')); }
+            }
+            if (a1 > a2) std::swap(a1, a2);
+            ctx->gq_a = a1; ctx->gq_b = a2;
         }
     }
     if (cfg->op == VCFX_OP_INBREEDING) {

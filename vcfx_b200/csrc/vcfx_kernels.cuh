@@ -36,7 +36,7 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int WARPS_PER_CTA = 8;
 constexpr uint32_t WINDOW = 512;
 
-enum : int { OP_VC = 0, OP_AF = 1, OP_HWE = 2, OP_MD = 3, OP_AC = 4, OP_NR = 5, OP_IX = 6, OP_PC = 7, OP_IB = 8 };
+enum : int { OP_VC = 0, OP_AF = 1, OP_HWE = 2, OP_MD = 3, OP_AC = 4, OP_NR = 5, OP_IX = 6, OP_PC = 7, OP_IB = 8, OP_GQ = 9 };
 constexpr uint32_t NR_PLAIN = 0xFFFFFFFFu;     // Rec::b of a nonref_filter record: the line is written as its content + '\n' (or not at all)
 enum : int { MODE_FILE = 0, MODE_STDIN = 1 };
 enum : int { AC_TEXT_MT = 0, AC_TEXT_FWD = 1, AC_AGG = 2, AC_BIN = 3 };
@@ -134,6 +134,11 @@ struct KParams {
     unsigned long long *events;      // short-line events (tile << 32 | index in tile)
     uint32_t ev_cap;
     unsigned long long fmt0_until;   // phase_checker, file mode: an empty FORMAT column of a line starting below this offset means GT index 0
+    // GENOTYPE_QUERY
+    uint8_t gq_query[64];            // the -g argument (gq_len bytes)
+    uint32_t gq_len;
+    int32_t gq_a, gq_b;              // its two alleles, sorted (whatever parseDiploidAlleles left in them; -1 = nothing)
+    int32_t gq_strict;               // --strict: the GT must equal the query byte for byte
     // INBREEDING (sample-axis reduction): the scan leaves one code per sample column, a second pass walks the rows in file order
     uint8_t *ib_codes;               // [n + pad] code of sample column j of the line starting at byte L: ib_codes[L + j] (0, 1, 2, IB_NONE, IB_ABSENT)
     IbMeta *ib_rows;                 // [rec_cap] the chunk's rows in file order (ib_rows_kernel)
@@ -344,6 +349,50 @@ __device__ __noinline__ bool pc_sample_phased(const uint8_t *p, bool file_mode, 
     const uint32_t al = (uint32_t)(ge - as);
     if (al == 0 || (al == 1 && ldb(as) == '.')) return false;
     return pipe;
+}
+
+// VCFX_genotype_query.cpp:322-344 / 275-317: does the GT of the sample column starting at p equal the query?  The column ends at
+// a tab or the line end (a '\r' is content); GT = the gt_index-th ':' piece, an empty one never matches.  --strict: byte for
+// byte.  Otherwise both sides are digits, '/' or '|', digits, and the allele pairs are compared without their order.
+struct GqQuery { const uint8_t *q; uint32_t len; int a, b; bool strict; };
+// the same for a GT of exactly three bytes (the low three bytes of u)
+__device__ __forceinline__ bool gq_match3(uint32_t u, const GqQuery &Q) {
+    if (Q.strict) return Q.len == 3u && ((u ^ ((uint32_t)Q.q[0] | ((uint32_t)Q.q[1] << 8) | ((uint32_t)Q.q[2] << 16))) & 0x00FFFFFFu) == 0u;
+    const uint32_t b1 = (u >> 8) & 0xFFu, d0 = (u & 0xFFu) - '0', d2 = ((u >> 16) & 0xFFu) - '0';
+    if ((b1 != '/' && b1 != '|') || d0 > 9u || d2 > 9u) return false;
+    return (int)min(d0, d2) == Q.a && (int)max(d0, d2) == Q.b;
+}
+__device__ __noinline__ bool gq_sample_match(const uint8_t *p, int gt_index, const GqQuery Q) {
+    const uint8_t *se = p;
+    uint32_t c = ldb(se);
+    while (c != '\t' && c != '\n') { ++se; c = ldb(se); }
+    const uint8_t *gs = p, *ge = se;
+    {
+        int idx = 0; const uint8_t *fs = p; bool got = false;
+        for (const uint8_t *q = p; q <= se; ++q) {
+            if (q == se || ldb(q) == ':') {
+                if (idx == gt_index) { gs = fs; ge = q; got = true; break; }
+                ++idx; fs = q + 1;
+            }
+        }
+        if (!got) return false;
+    }
+    const uint32_t n = (uint32_t)(ge - gs);
+    if (n == 0) return false;
+    if (Q.strict) {
+        if (n != Q.len) return false;
+        for (uint32_t i = 0; i < n; ++i) if (ldb(gs + i) != Q.q[i]) return false;
+        return true;
+    }
+    uint32_t sp = 0;
+    while (sp < n && ldb(gs + sp) != '|' && ldb(gs + sp) != '/') ++sp;
+    if (sp == n || sp == 0 || sp == n - 1) return false;
+    uint32_t a1 = 0, a2 = 0;
+    for (uint32_t i = 0; i < sp; ++i) { const uint32_t d = ldb(gs + i) - '0'; if (d > 9u) return false; a1 = a1 * 10u + d; }
+    for (uint32_t i = sp + 1; i < n; ++i) { const uint32_t d = ldb(gs + i) - '0'; if (d > 9u) return false; a2 = a2 * 10u + d; }
+    int x = (int)a1, y = (int)a2;
+    if (x > y) { const int t = x; x = y; y = t; }
+    return x == Q.a && y == Q.b;
 }
 
 // VCFX_inbreeding_calculator.cpp:296-339 parseGenotypeCode on the sample column starting at p: blanks and '\r' in front are
@@ -1624,10 +1673,11 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
             }
             // ================= NONREF_FILTER: is every sample homozygous reference?
             bool nr_all = false;               // the line can be dropped and no sample so far speaks against it
-            if ((OP == OP_NR || OP == OP_PC) && !hash && tabs >= 9 && (a0 + ls >= P.valid_from)) {
+            if ((OP == OP_NR || OP == OP_PC || OP == OP_GQ) && !hash && tabs >= 9 && (a0 + ls >= P.valid_from)) {
                 const int gi_ = gt_index_of(tin + tp[7] + 1, tin + tp[8]);        // findGTIndex on FORMAT (nonref_filter :317-335, phase_checker :171-189)
                 // phase_checker's file mode starts with the FORMAT cache ("", 0): an empty FORMAT column is "GT first" until a non-empty one was seen
                 const int gi = (OP == OP_PC && gi_ < 0 && P.mode == MODE_FILE && tp[8] == tp[7] + 1 && (a0 + ls) < P.fmt0_until) ? 0 : gi_;
+                GqQuery gq; gq.q = P.gq_query; gq.len = P.gq_len; gq.a = P.gq_a; gq.b = P.gq_b; gq.strict = P.gq_strict != 0;
                 if (gi >= 0) {
                     nr_all = true;
                     const uint32_t lo = tp[8];                                    // the tab in front of the first sample
@@ -1662,6 +1712,11 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                             for (int j = 0; j < 4; ++j) {
                                 const uint32_t u = uu[j];
                                 if (OP == OP_NR) badw |= (u != 0x09302F30u && u != 0x09307C30u) ? 1u : 0u;
+                                else if (OP == OP_GQ) {
+                                    // a three-byte GT that is not the query (nr_all: "no sample has matched so far")
+                                    badw |= (eq_bytes(u, C_TAB) ^ 0x80000000u) | eq_bytes(u, C_NL) | (eq_bytes(u, 0x3A3A3A3Au) & 0x00808080u);
+                                    badw |= gq_match3(u, gq) ? 1u : 0u;
+                                }
                                 else {
                                     badw |= (eq_bytes(u, C_TAB) ^ 0x80000000u) | eq_bytes(u, C_NL);
                                     badw |= ((eq_bytes(u, C_DOT) | eq_bytes(u, 0x3A3A3A3Au)) & 0x00800080u) | ((u ^ 0x00007C00u) & 0x0000FF00u);
@@ -1688,6 +1743,11 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                                 if (OP == OP_NR) {
                                     const bool quick = (g3 == 0x00302F30u || g3 == 0x00307C30u) && (b3 == '\t' || (gi == 0 && b3 == ':'));
                                     if (!quick && !nr_sample_homref(sp, file_mode, gi)) bad = true;
+                                } else if (OP == OP_GQ) {
+                                    // GT = exactly the three bytes behind the tab: decided from the word; anything else by the scalar matcher
+                                    const uint32_t ends = eq_bytes(q, C_TAB) | eq_bytes(q, C_NL) | eq_bytes(q, 0x3A3A3A3Au);
+                                    if (gi == 0 && (ends & 0x00808080u) == 0 && (ends & 0x80000000u)) { if (gq_match3(q, gq)) bad = true; }
+                                    else if (gq_sample_match(sp, gi, gq)) bad = true;
                                 } else {
                                     // phase_checker: "x|y" of exactly three bytes, x and y anything but '.' (and not an end of the GT)
                                     const uint32_t b0 = q & 0xFFu, b2 = (q >> 16) & 0xFFu;
@@ -2063,6 +2123,48 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                 md_add_nl = false;
                 md_last_end = raw_end;
             }
+            else if (OP == OP_GQ) {
+                // VCFX_genotype_query.cpp:446-516 / 546-606: '#' lines pass, empty lines vanish, a data line passes when it has a
+                // FORMAT column with a GT key and a sample whose GT is the query; no '\r' is cut.  (The caller feeds nothing
+                // behind a data line that comes before the "#CHROM" line, and holds back stdin mode's trailing '#' lines.)
+                const bool term = (a0 + e) < n;
+                const uint32_t raw_end = term ? e + 1 : e;
+                const bool data = (e != ls) && !hash;
+                bool drop = (e == ls);
+                if (data) {
+                    VCFX_COUNT(C_DATA, 1);
+                    if (tabs < 8) {
+                        // skipToField(.., 8): NULL when a tab is missing and the line goes on; a line that ends with its last tab
+                        // gets an empty FORMAT instead, and no message
+                        drop = true;
+                        if (ldb(tin + e - 1) != '\t') {
+                            VCFX_COUNT(C_SHORT, 1);
+                            if (lane == 0) {
+                                const unsigned long long slot = atomicAdd(&P.stats->n_events, 1ULL);
+                                if (slot < P.ev_cap) P.events[slot] = ((unsigned long long)(a0 + ls) << 2) | 2ULL;
+                            }
+                        }
+                    }
+                    else if (gt_index_of(tin + tp[7] + 1, tin + (tabs >= 9 ? tp[8] : e)) < 0) drop = true;
+                    else drop = (tabs < 9) || nr_all;                    // nr_all: no sample matched
+                }
+                if (data && !drop) VCFX_COUNT(C_ROWS, 1);
+                if (drop || !term) {
+                    const uint32_t content_len = drop ? 0u : e - ls, mod_len = drop ? 0u : content_len + 1u;
+                    if (lane == 0) {
+                        unsigned long long slot = alloc_slot(ws.rec_base, ws.rec_used, P.stats);
+                        if (slot < P.rec_cap) {
+                            Rec r; r.tile = tile; r.ls_rel = (uint32_t)(a0 + ls - a); r.prefix_len = (uint32_t)(a0 + md_prev_end - a);
+                            r.off_in_tile = (uint32_t)out_bytes; r.a = 0; r.b = NR_PLAIN; r.c = content_len; r.d = mod_len;
+                            P.recs[slot] = r;
+                        }
+                    }
+                    out_bytes += (ls - md_prev_end) + mod_len;
+                    md_prev_end = raw_end;
+                }
+                md_add_nl = false;
+                md_last_end = raw_end;
+            }
             else if (OP == OP_NR) {
                 // VCFX_nonref_filter.cpp:478-544 / 553-631: every line is written as its content + '\n' (file mode: without a
                 // '\r' before the '\n'), except data lines behind the "#CHROM" line whose samples are all hom-ref.  Lines that
@@ -2244,7 +2346,7 @@ vcfx_scan_kernel(const VCFX_GRID_CONSTANT KParams P) {
         const bool md_add_nl = st.md_add_nl;
 
         if (!(OP == OP_AC && P.ac_pass)) VCFX_COUNT(C_LINES, VAR == 1 ? nlines - lines_before : nlines);
-        if (OP == OP_MD || OP == OP_NR || OP == OP_PC) {
+        if (OP == OP_MD || OP == OP_NR || OP == OP_PC || OP == OP_GQ) {
             const uint32_t tail = md_last_end - md_prev_end;
             if (lane == 0) {
                 P.tail_start[tile] = (uint32_t)(a0 + md_prev_end - a);

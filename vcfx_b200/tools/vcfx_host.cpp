@@ -282,13 +282,24 @@ class Writer {
 struct Drain {
     std::vector<vcfx_ctx *> ctxs; const RunOptions &opt; Totals &tot; Writer *writer = nullptr; uint64_t line_base = 0;
     long drained = 0, final_index = -1;
-    std::deque<std::pair<const char *, size_t>> inputs;      // the pinned input of every chunk in flight (intact until its slot is acquired again)
+    struct Input { const char *buf; size_t nbytes; size_t tail_out; bool has_data; };
+    std::deque<Input> inputs;               // the pinned input of every chunk in flight (intact until its slot is acquired again)
+    std::string held;                       // hold_trailing_hash: '#' lines waiting for a data line
     int one(std::string &err) {
         const char *text = nullptr; size_t n = 0; vcfx_chunk_stats st;
         vcfx_ctx *ctx = ctxs[(size_t)drained % ctxs.size()];        // chunks were dealt round-robin: the oldest one is this context's
         int rc = vcfx_cuda_next_output(ctx, &text, &n, &st);
         if (rc != VCFX_OK) { err = std::string(vcfx_cuda_strerror(rc)) + ": " + vcfx_cuda_last_error(ctx); return rc; }
-        if (opt.capture) { if (n) opt.capture->append(text, n); }
+        if (opt.hold_trailing_hash && !inputs.empty()) {
+            const Input &in = inputs.front();
+            const size_t tail = std::min(in.tail_out, n);
+            if (in.has_data) {
+                if (!held.empty()) { write_all(opt.out_fd, held.data(), held.size()); held.clear(); }
+                write_all(opt.out_fd, text, n - tail);
+                held.assign(text + (n - tail), tail);
+            } else held.append(text, n);
+        }
+        else if (opt.capture) { if (n) opt.capture->append(text, n); }
         else if (opt.capture_final && drained == final_index) { if (n) opt.capture_final->append(text, n); }
         else if (opt.sink) { if (n && !opt.sink(text, n)) { err = "output sink failed"; return VCFX_E_INVALID; } }
         else if (writer) writer->push(text, n);        // (empty pieces too: the writer's count follows the chunks)
@@ -308,7 +319,7 @@ struct Drain {
             std::vector<uint64_t> ev((size_t)st.n_events);
             size_t got = 0;
             vcfx_cuda_short_lines(ctx, ev.data(), ev.size(), &got);
-            opt.on_events(inputs.front().first, inputs.front().second, ev.data(), got);
+            opt.on_events(inputs.front().buf, inputs.front().nbytes, ev.data(), got);
         }
         if (!inputs.empty()) inputs.pop_front();
         tot.lines += st.lines;
@@ -329,7 +340,8 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
     if (!chunk) { const char *e = getenv("VCFX_CHUNK_BYTES"); chunk = e ? (size_t)strtoull(e, nullptr, 10) : (size_t)64 << 20; }
     cfg.chunk_bytes = chunk; cfg.n_slots = 3;
     std::string names_blob; std::vector<uint32_t> name_off;
-    if (!opt.sel_col.empty()) {
+    if (!opt.query.empty()) { cfg.n_sel = (uint32_t)opt.query.size(); cfg.sel_names = opt.query.data(); }
+    else if (!opt.sel_col.empty()) {
         name_off.push_back(0);
         for (const auto &s : opt.sel_names) { names_blob += s; names_blob.push_back('\t'); name_off.push_back((uint32_t)names_blob.size()); }
         cfg.n_sel = (uint32_t)opt.sel_col.size(); cfg.sel_col = opt.sel_col.data();
@@ -378,7 +390,7 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
     double t_create = now() - t_start;
     auto in_flight_total = [&ctxs] { long k = 0; for (vcfx_ctx *c : ctxs) k += vcfx_cuda_in_flight(c); return k; };
 
-    const bool direct = !opt.capture && !opt.sink;
+    const bool direct = !opt.capture && !opt.sink && !opt.hold_trailing_hash;
     Writer *writer = direct ? new Writer(opt.out_fd) : nullptr;
     struct WriterGuard { Writer *w; ~WriterGuard() { delete w; } } writer_guard{writer};     // joins after the last piece is out
     Drain drain{ctxs, opt, tot, writer};
@@ -411,7 +423,8 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
         size_t have = std::min(carry.size(), cap);
         memcpy(buf, carry.data(), have);
         carry.erase(0, have);
-        while (have < cap && carry.empty()) {
+        if (opt.preface_only && carry.empty()) eof = true;
+        while (have < cap && carry.empty() && !opt.preface_only) {
             long r = src.read(buf + have, cap - have);
             if (r < 0) { err = "read error"; destroy_all(); return VCFX_E_INVALID; }
             if (r == 0) { eof = true; break; }
@@ -514,7 +527,26 @@ int run_stream(Source &src, const RunOptions &opt, Totals &tot, std::string &err
         t0 = now();
         rc = vcfx_cuda_submit(ctx, nbytes, &info);
         t_submit += now() - t0;
-        drain.inputs.push_back({buf, nbytes});
+        {
+            Drain::Input in{buf, nbytes, 0, true};
+            if (opt.hold_trailing_hash) {
+                // the run of '#' and empty lines at the end of the chunk: what it puts out ('#' line + '\n' each), and whether
+                // any data line stands in front of it
+                size_t end = nbytes;
+                in.has_data = false;
+                while (end > 0) {
+                    const size_t le = (buf[end - 1] == '\n') ? end - 1 : end;          // line end (the last line may lack its '\n')
+                    const void *pnl = le ? memrchr(buf, '\n', le) : nullptr;
+                    const size_t ls = pnl ? (size_t)(static_cast<const char *>(pnl) - buf) + 1 : 0;
+                    if (le > ls) {
+                        if (buf[ls] != '#') { in.has_data = true; break; }
+                        in.tail_out += le - ls + 1;
+                    }
+                    end = ls;
+                }
+            }
+            drain.inputs.push_back(in);
+        }
         ++submitted;
         if (rc != VCFX_OK) { err = std::string(vcfx_cuda_strerror(rc)) + ": " + vcfx_cuda_last_error(ctx); destroy_all(); return rc; }
         if (opt.stop_at_first_short && in_flight_total() >= 2) {

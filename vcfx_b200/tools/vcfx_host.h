@@ -76,6 +76,13 @@ struct RunOptions {
     // when set, called once per chunk that has events, in stream order, with the chunk's input bytes and its sorted event
     // list (VCFX_OP_PHASE_CHECK: offset of a dropped line in the chunk << 2 | reason)
     std::function<void(const char *chunk, size_t nbytes, const uint64_t *events, size_t n)> on_events;
+    // genotype_query: the -g argument (cfg.sel_names = its bytes, cfg.n_sel = its length)
+    std::string query;
+    // nothing is read from the source: the input is `preface` alone
+    bool preface_only = false;
+    // VCFX_genotype_query's stdin mode prints '#' lines only once a data line follows them: the text of the '#' lines at the
+    // end of a chunk is held back until a later chunk has a data line, and dropped at the end of the input
+    bool hold_trailing_hash = false;
     // a chunk marked final is always submitted, an empty one if need be (an op whose text only comes with the final chunk)
     bool always_submit_final = false;
     // chunks go to one GPU only, in order (an op that carries state from chunk to chunk)
