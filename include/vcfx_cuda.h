@@ -62,6 +62,10 @@ typedef enum {
                                      ends the input in front of a data line that comes before the "#CHROM" line and, in stdin mode,
                                      holds back '#' lines until a data line follows; vcfx_cuda_short_lines returns (offset << 2 | 2)
                                      for every line that earns "skipping line with <9 fields" */
+    VCFX_OP_DOSAGE         = 10,  /* VCFX_dosage_calculator.cpp:375-591 processFileMmap, :209-366 calculateDosage: a row
+                                     "CHROM..ALT \t d,d,NA,.." per data line with ten columns; stats.short_lines = lines with fewer
+                                     (one warning each).  The caller prints the header row and ends the run at a data line that
+                                     comes before the "#CHROM" line */
     VCFX_OP_INDEX          = 6,   /* VCFX_indexer.cpp:205-322 createVCFIndexMmap, :329-443 createVCFIndex */
     VCFX_OP_NONREF_FILTER  = 5    /* VCFX_nonref_filter.cpp:458-548 filterNonRefMmap, :553-631 filterNonRef */
 } vcfx_op;

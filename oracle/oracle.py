@@ -46,7 +46,7 @@ def lib():
             subprocess.run(["make", "-C", str(HERE), "all"], check=True, capture_output=True)
         l = C.CDLL(str(LIB_PATH))
         P = C.POINTER(_Result)
-        for name in ("oracle_allele_freq", "oracle_hwe", "oracle_missing", "oracle_nonref_filter", "oracle_indexer", "oracle_phase_checker"):
+        for name in ("oracle_allele_freq", "oracle_hwe", "oracle_missing", "oracle_nonref_filter", "oracle_indexer", "oracle_phase_checker", "oracle_dosage"):
             getattr(l, name).argtypes = [C.c_char_p, C.c_size_t, C.c_int, P]
         l.oracle_variant_count.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, P]
         l.oracle_inbreeding.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, P]
@@ -102,6 +102,16 @@ def phase_checker_stderr(data: bytes, mode: int = FILE) -> bytes:
     out = C.string_at(e.out, e.out_len) if e.out_len else b""
     l.oracle_free(C.byref(r)); l.oracle_free(C.byref(e))
     return out
+
+
+DS_WARNING = b"Warning: Skipping VCF line with fewer than 10 fields.\n"
+DS_ERROR = b"Error: VCF header (#CHROM) not found before variant records.\n"
+
+
+def dosage(data: bytes, mode: int = FILE) -> Result:
+    """VCFX_dosage_calculator; .warnings = number of DS_WARNING lines on stderr (file mode: not with -q), .first_bad_line = 1:
+    DS_ERROR and nothing on stdout."""
+    return _call(lib().oracle_dosage, data, len(data), mode)
 
 
 def genotype_query(data: bytes, query: str, mode: int = FILE, strict: bool = False):

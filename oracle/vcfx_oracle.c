@@ -1168,6 +1168,68 @@ done:
     return 0;
 }
 
+/* ------------------------------------------------------------------ dosage_calculator (§8 f2): per data line "CHROM..ALT \t d,d,NA,.." with d =
+ * the number of alleles > 0 of a two-allele GT */
+
+/* VCFX_dosage_calculator.cpp:111-154 parseDosageInline */
+static int ds_dosage(const char *g, size_t n) {
+    if (n == 0) return -1;
+    int dosage = 0, count = 0; size_t pos = 0;
+    while (pos < n) {
+        while (pos < n && (g[pos] == '/' || g[pos] == '|')) ++pos;
+        if (pos >= n) break;
+        if (g[pos] == '.') return -1;
+        unsigned allele = 0; int digit = 0;
+        while (pos < n && g[pos] >= '0' && g[pos] <= '9') { allele = allele * 10u + (unsigned)(g[pos] - '0'); digit = 1; ++pos; }
+        if (!digit) return -1;
+        if ((int)allele > 0) ++dosage;
+        if (++count > 2) return -1;
+    }
+    return count == 2 ? dosage : -1;
+}
+
+/* r->rc = exit code; r->warnings = lines with fewer than ten fields (one message each; file mode: not with -q);
+ * r->first_bad_line = 1 when the run ended at a data line in front of the "#CHROM" line (message, nothing on stdout) */
+int oracle_dosage(const char *in, size_t n, int mode, oracle_result *r) {
+    res_init(r);
+    obuf o = {0};
+    if (mode == ORACLE_FILE && n == 0) { res_take(r, &o); return 0; }      /* :388-391 */
+    ob_str(&o, "CHROM\tPOS\tID\tREF\tALT\tDosages\n");
+    size_t pos = 0; line_t ln; int header = 0;
+    while (next_line(in, n, &pos, &ln)) {
+        const char *s = ln.s, *e = ln.e;
+        if (mode == ORACLE_FILE && e > s && e[-1] == '\r') --e;            /* :433-435 (stdin: getline keeps it) */
+        if (s == e) continue;
+        if (*s == '#') { if (e - s >= 6 && memcmp(s, "#CHROM", 6) == 0) header = 1; continue; }
+        if (!header) {                                                     /* :452-458 / :236-240: the buffered output is thrown away */
+            o.n = 0; r->first_bad_line = 1; r->rc = (mode == ORACLE_FILE) ? 1 : 0;
+            res_take(r, &o); return 0;
+        }
+        r->data_lines++;
+        const char *f[10]; size_t fl[10]; int nf = 0; size_t fs = 0, len = (size_t)(e - s);
+        for (size_t i = 0; i <= len && nf < 10; ++i)
+            if (i == len || s[i] == '\t') { f[nf] = s + fs; fl[nf] = i - fs; ++nf; fs = i + 1; }
+        if (nf < 10) { r->warnings++; continue; }
+        for (int k = 0; k < 5; ++k) { ob_put(&o, f[k], fl[k]); ob_ch(&o, '\t'); }
+        int gi = oracle_gt_index(f[8], fl[8]);
+        r->rows++;
+        if (gi < 0) { ob_str(&o, "NA\n"); continue; }
+        const char *sp = f[9]; int first = 1;
+        while (sp < e) {
+            const char *se = sp; while (se < e && *se != '\t') ++se;
+            if (!first) ob_ch(&o, ',');
+            first = 0;
+            const char *gs, *ge; nr_nth_piece(sp, se, gi, &gs, &ge);
+            int d = (ge > gs) ? ds_dosage(gs, (size_t)(ge - gs)) : -1;
+            if (d < 0) ob_str(&o, "NA"); else ob_ch(&o, (char)('0' + d));
+            sp = (se < e) ? se + 1 : e;
+        }
+        ob_ch(&o, '\n');
+    }
+    res_take(r, &o);
+    return 0;
+}
+
 /* ------------------------------------------------------------------ variant_counter */
 
 /* variant_counter.cpp:31-44 — at least 7 tabs. */

@@ -51,6 +51,8 @@ int oracle_missing(const char *in, size_t n, int mode, oracle_result *r);
 int oracle_phase_checker(const char *in, size_t n, int mode, oracle_result *r);    /* VCFX_phase_checker (§8 f2) */
 int oracle_phase_checker_err(const char *in, size_t n, int mode, oracle_result *r, oracle_result *err);   /* + stderr text without -q */
 int oracle_indexer(const char *in, size_t n, int mode, oracle_result *r);          /* VCFX_indexer (§8 f4) */
+/* VCFX_dosage_calculator (§8 f2); r->warnings = lines with fewer than ten fields, r->first_bad_line = 1: ended at a data line before the header */
+int oracle_dosage(const char *in, size_t n, int mode, oracle_result *r);
 /* VCFX_genotype_query (§8 f2): r = stdout, err = the stderr text of a run without -q */
 int oracle_genotype_query(const char *in, size_t n, int mode, const char *query, int strict, oracle_result *r, oracle_result *err);
 /* VCFX_inbreeding_calculator (§8 f3); flags: 1 --freq-mode global, 2 --skip-boundary, 4 --count-boundary-as-used, 8 -q */

@@ -17,7 +17,7 @@ from pathlib import Path
 
 from . import build as _build
 
-OP_VARIANT_COUNT, OP_ALLELE_FREQ, OP_HWE, OP_MISSING_DETECT, OP_ALLELE_COUNT, OP_NONREF_FILTER, OP_INDEX, OP_PHASE_CHECK, OP_INBREEDING, OP_GENOTYPE_QUERY = range(10)
+OP_VARIANT_COUNT, OP_ALLELE_FREQ, OP_HWE, OP_MISSING_DETECT, OP_ALLELE_COUNT, OP_NONREF_FILTER, OP_INDEX, OP_PHASE_CHECK, OP_INBREEDING, OP_GENOTYPE_QUERY, OP_DOSAGE = range(11)
 FILE, STDIN = 0, 1
 F_AC_AGGREGATE, F_AC_BINARY, F_AC_FORWARD = 1, 2, 4
 DEVICE_PAD = 8192
@@ -552,6 +552,37 @@ def inbreeding_calculator(data: bytes, mode: int = FILE, freq_global: bool = Fal
         ctx.close()
     err = IB_MESSAGES[3] if (tot.rows == 0 and not quiet) else b""
     return ToolResult(IB_HEADER + b"".join(outs), 0, tot, err)
+
+
+DS_HEADER = b"CHROM\tPOS\tID\tREF\tALT\tDosages\n"           # VCFX_dosage_calculator.cpp:414
+DS_WARNING = b"Warning: Skipping VCF line with fewer than 10 fields.\n"
+DS_ERROR = b"Error: VCF header (#CHROM) not found before variant records.\n"
+
+
+def dosage_calculator(data: bytes, mode: int = FILE, quiet: bool = False, chunk_bytes: int = 0, **kw) -> ToolResult:
+    """VCFX_dosage_calculator: per data line "CHROM..ALT \\t d,d,NA,.." (processFileMmap :375-591, calculateDosage :209-366).
+    A data line in front of the "#CHROM" line ends the run with nothing on stdout (exit code 1 in file mode); an empty FILE
+    gives nothing at all; stdin mode prints its warnings even with -q."""
+    if mode == FILE and len(data) == 0:
+        return ToolResult(b"", 0, Totals())
+    pos, n, found = 0, len(data), False
+    while pos < n:                                       # up to the first data line
+        nl = data.find(b"\n", pos)
+        le = n if nl < 0 else nl
+        line = data[pos:le]
+        if mode == FILE and line.endswith(b"\r"):
+            line = line[:-1]
+        if line:
+            if not line.startswith(b"#"):
+                if not found:
+                    return ToolResult(b"", 1 if mode == FILE else 0, Totals(), DS_ERROR)
+                break
+            if line.startswith(b"#CHROM"):
+                found = True
+        pos = le + 1
+    body, tot = _run(OP_DOSAGE, data, mode, chunk_bytes, **kw)
+    warn = b"" if (quiet and mode == FILE) else DS_WARNING * tot.short_lines
+    return ToolResult(DS_HEADER + body, 0, tot, warn)
 
 
 F_GQ_STRICT = 1

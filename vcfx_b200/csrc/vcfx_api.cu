@@ -160,6 +160,7 @@ kernel_fn kernel_for(int op) {
     case VCFX_OP_PHASE_CHECK: return vcfx_scan_kernel<OP_PC, 0>;
     case VCFX_OP_INBREEDING: return vcfx_scan_kernel<OP_IB, 0>;
     case VCFX_OP_GENOTYPE_QUERY: return vcfx_scan_kernel<OP_GQ, 0>;
+    case VCFX_OP_DOSAGE: return vcfx_scan_kernel<OP_DS, 0>;
     case VCFX_OP_ALLELE_COUNT:  return vcfx_scan_kernel<OP_AC, 0>;
     default: return nullptr;
     }
@@ -183,6 +184,7 @@ kernel_fn format_kernel_for(int op, int ac_fmt = 0) {
     case VCFX_OP_GENOTYPE_QUERY: return md_copy_kernel;
     case VCFX_OP_INDEX: return format_rows_kernel<OP_IX>;
     case VCFX_OP_INBREEDING: return ib_rows_kernel;
+    case VCFX_OP_DOSAGE: return ds_rows_kernel;
     default: return nullptr;
     }
 }
@@ -303,6 +305,11 @@ int ensure_work(vcfx_ctx *ctx, Work &w, size_t max_bytes, uint64_t min_recs = 0,
     if (ctx->cfg.op == VCFX_OP_ALLELE_COUNT && !w.col_scratch) {
         size_t n = (size_t)ctx->sm_count * ctx->blocks_per_sm * WARPS_PER_CTA * std::max<uint32_t>(ctx->max_col, 1);
         CU(cudaMalloc(&w.col_scratch, n * sizeof(uint2)));
+    }
+    if (ctx->cfg.op == VCFX_OP_DOSAGE && max_bytes + VCFX_DEVICE_PAD > w.ib_codes_cap) {      // a code per sample column, as for inbreeding_calculator
+        cudaFree(w.ib_codes); w.ib_codes = nullptr; w.ib_codes_cap = 0;
+        CU(cudaMalloc(&w.ib_codes, max_bytes + VCFX_DEVICE_PAD));
+        w.ib_codes_cap = max_bytes + VCFX_DEVICE_PAD;
     }
     if (ctx->cfg.op == VCFX_OP_INBREEDING) {
         // the codes once more in file order, 32 samples to a panel: lines that have all their columns need less than the
@@ -464,6 +471,7 @@ size_t default_out_bytes(int op, unsigned flags, size_t chunk) {
     case VCFX_OP_NONREF_FILTER: return chunk + 4096;          // never longer than the input plus one '\n'
     case VCFX_OP_PHASE_CHECK: return chunk + 4096;
     case VCFX_OP_GENOTYPE_QUERY: return chunk + 4096;
+    case VCFX_OP_DOSAGE: return chunk + 4096;                 // a sample column of two bytes or more gives at most two
     case VCFX_OP_INBREEDING: return 1u << 20;                 // create() sizes it from the names
     case VCFX_OP_ALLELE_COUNT:
         if (flags & VCFX_F_AC_AGGREGATE) return chunk / 4 + (1u << 20);
@@ -520,7 +528,7 @@ const char *vcfx_cuda_last_error(const vcfx_ctx *ctx) { return ctx ? ctx->last_e
 int vcfx_cuda_create(const vcfx_cfg *cfg, vcfx_ctx **out) {
     if (!cfg || !out) return VCFX_E_INVALID;
     *out = nullptr;
-    if (cfg->op < VCFX_OP_VARIANT_COUNT || cfg->op > VCFX_OP_GENOTYPE_QUERY) return VCFX_E_INVALID;
+    if (cfg->op < VCFX_OP_VARIANT_COUNT || cfg->op > VCFX_OP_DOSAGE) return VCFX_E_INVALID;
     if (cfg->mode != VCFX_MODE_FILE && cfg->mode != VCFX_MODE_STDIN) return VCFX_E_INVALID;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return VCFX_E_NO_DEVICE;

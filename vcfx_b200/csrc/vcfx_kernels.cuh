@@ -36,7 +36,7 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int WARPS_PER_CTA = 8;
 constexpr uint32_t WINDOW = 512;
 
-enum : int { OP_VC = 0, OP_AF = 1, OP_HWE = 2, OP_MD = 3, OP_AC = 4, OP_NR = 5, OP_IX = 6, OP_PC = 7, OP_IB = 8, OP_GQ = 9 };
+enum : int { OP_VC = 0, OP_AF = 1, OP_HWE = 2, OP_MD = 3, OP_AC = 4, OP_NR = 5, OP_IX = 6, OP_PC = 7, OP_IB = 8, OP_GQ = 9, OP_DS = 10 };
 constexpr uint32_t NR_PLAIN = 0xFFFFFFFFu;     // Rec::b of a nonref_filter record: the line is written as its content + '\n' (or not at all)
 enum : int { MODE_FILE = 0, MODE_STDIN = 1 };
 enum : int { AC_TEXT_MT = 0, AC_TEXT_FWD = 1, AC_AGG = 2, AC_BIN = 3 };
@@ -412,6 +412,41 @@ __device__ __noinline__ uint32_t ib_sample_code(const uint8_t *p) {
     while (c - '0' <= 9u) { a2 = a2 * 10u + (c - '0'); ++p; c = ldb(p); }
     if (a1 > 1u || a2 > 1u) return IB_NONE;
     return a1 + a2;
+}
+
+// VCFX_dosage_calculator.cpp:111-154 parseDosageInline on the GT (:182-204 extractGTFromSample: the gt_index-th ':' piece, none when it
+// is empty or missing) of the sample column starting at p: separators are skipped, every allele is a run of digits, a '.' or
+// any other byte spoils it, exactly two alleles: the number of alleles > 0; else IB_NONE ("NA").  The column ends at a tab or the
+// line end (file mode: a '\r' in front of the '\n' is cut first); a column that starts at the line end does not exist: IB_ABSENT.
+__device__ __noinline__ uint32_t ds_sample_code(const uint8_t *p, bool file_mode, int gt_index) {
+    const uint8_t *se = p;
+    uint32_t c = ldb(se);
+    while (c != '\t' && c != '\n') { ++se; c = ldb(se); }
+    if (file_mode && c == '\n' && se > p && ldb(se - 1) == '\r') --se;
+    if (se == p && c == '\n') return IB_ABSENT;
+    const uint8_t *gs = p, *ge = se;
+    {
+        int idx = 0; const uint8_t *fs = p; bool got = false;
+        for (const uint8_t *q = p; q <= se; ++q) {
+            if (q == se || ldb(q) == ':') {
+                if (idx == gt_index) { gs = fs; ge = q; got = true; break; }
+                ++idx; fs = q + 1;
+            }
+        }
+        if (!got || ge == gs) return IB_NONE;
+    }
+    uint32_t dosage = 0, alleles = 0;
+    const uint8_t *q = gs;
+    while (q < ge) {
+        while (q < ge && is_sep(ldb(q))) ++q;
+        if (q >= ge) break;
+        uint32_t allele = 0; bool digit = false;
+        while (q < ge && ldb(q) - '0' <= 9u) { allele = allele * 10u + (ldb(q) - '0'); digit = true; ++q; }
+        if (!digit) return IB_NONE;                                  // a '.' or any other byte
+        if ((int)allele > 0) ++dosage;
+        if (++alleles > 2) return IB_NONE;
+    }
+    return alleles == 2 ? dosage : IB_NONE;
 }
 
 // VCFX_indexer on one data line [s, e) (a '\r' before the '\n' already cut off): where CHROM is and what POS reads as.
@@ -1527,7 +1562,12 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                 }
                 ib_line = __shfl_sync(FULL, ok, 0) != 0;
             }
-            if (OP == OP_IB && ib_line) {
+            int ds_gi = -1;                    // dosage_calculator: index of the GT key, found once per line
+            if (OP == OP_DS && !hash && tabs >= 9) {
+                ds_gi = gt_index_of(tin + tp[7] + 1, tin + tp[8]);       // :316 / :526 findGTIndexRaw on FORMAT
+                ib_line = ds_gi >= 0;
+            }
+            if ((OP == OP_IB || OP == OP_DS) && ib_line) {
                 // (the codes of a line start within three bytes of the line's own offset, such that a lane's four codes of a
                 // lattice window — see below — land on a 32-bit boundary; the record says where)
                 const uint32_t first = tp[8] + 1u, tq = tp[8] & 3u;          // tq: where in a 32-bit word the tabs of a lattice line sit
@@ -1540,7 +1580,7 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                     if (lane == 31) la = nx0;
                     // ---- lattice window: no line end in sight and every sample so far (and here) is three bytes and a tab, at the
                     // line's phase: a 32-bit word per sample, four codes per lane in one store, no ranking of tabs
-                    if (!firstw && lat) {
+                    if (!firstw && lat && (OP == OP_IB || ds_gi == 0)) {
                         const uint32_t nl_any = eq_bytes(cur.x, C_NL) | eq_bytes(cur.y, C_NL) | eq_bytes(cur.z, C_NL) | eq_bytes(cur.w, C_NL);
                         if (!__any_sync(FULL, nl_any != 0)) {
                             // like the tab-by-tab path, a window owns the samples whose leading tab lies in it: bytes tq of every word
@@ -1554,17 +1594,25 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                                 const uint32_t u = uu[j];
                                 bad |= (eq_bytes(u, C_TAB) ^ 0x80000000u) | eq_bytes(u, C_NL);
                                 const uint32_t b1 = (u >> 8) & 0xFFu;
-                                const bool quick = ((u & 0x00FE00FEu) == 0x00300030u) && (b1 == '/' || b1 == '|');
-                                pk |= (quick ? ((u & 1u) + ((u >> 16) & 1u)) : IB_NONE) << (8 * j);
+                                if (OP == OP_IB) {
+                                    const bool quick = ((u & 0x00FE00FEu) == 0x00300030u) && (b1 == '/' || b1 == '|');
+                                    pk |= (quick ? ((u & 1u) + ((u >> 16) & 1u)) : IB_NONE) << (8 * j);
+                                } else {
+                                    // dosage: digit, separator, digit is the only three-byte GT with two alleles (a ':' in it cuts GT short)
+                                    const uint32_t d0 = (u & 0xFFu) - '0', d2 = ((u >> 16) & 0xFFu) - '0';
+                                    const bool quick = d0 <= 9u && d2 <= 9u && (b1 == '/' || b1 == '|');
+                                    pk |= (quick ? ((d0 ? 1u : 0u) + (d2 ? 1u : 0u)) : IB_NONE) << (8 * j);
+                                }
                             }
                             // the sample behind the window's first tab is number j0 of the line: by the tabs counted so far and by position
                             const int j0 = tabs - 8;
-                            bool okl = bad == 0 && j0 == (int)((wb + tq + 1u - first) >> 2) && (uint32_t)(j0 + 4 * lane + 4) <= P.n_sel;
+                            bool okl = bad == 0 && j0 == (int)((wb + tq + 1u - first) >> 2) && (OP == OP_DS || (uint32_t)(j0 + 4 * lane + 4) <= P.n_sel);
                             if (lane == 0) okl = okl && ((eq_bytes(cur.x, C_TAB) & (0xFFFFFFFFu >> (24u - 8u * tq))) == (0x80u << (8u * tq)));
                             if (__all_sync(FULL, okl)) {
                                 *reinterpret_cast<uint32_t *>(codes + j0 + 4 * lane) = pk;
                                 const uint32_t nn = (uint32_t)__popc(eq_bytes(pk, IB_NONE * 0x01010101u));
-                                ib_good += 4u - nn; ib_alt += dp4a_u(pk, 0x01010101u, 0u) - 3u * nn;
+                                if (OP == OP_IB) { ib_good += 4u - nn; ib_alt += dp4a_u(pk, 0x01010101u, 0u) - 3u * nn; }
+                                else ib_alt += nn;                   // dosage_calculator: the number of "NA"s
                                 tabs += 128;
                                 wb += WINDOW; cur = nxt; nxt = nx2; nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
                                 if (((wb >> 9) & 7u) == 0) {
@@ -1607,15 +1655,24 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                             while (m) {
                                 const int k = (__ffs(m) - 1) >> 3;
                                 m &= m - 1;
-                                if (r >= 8 && (uint32_t)(r - 8) < P.n_sel) {
-                                    // the four bytes behind the tab: [01] [/|] [01] and no further digit is the whole story
+                                if (r >= 8 && (OP == OP_DS || (uint32_t)(r - 8) < P.n_sel)) {
                                     const uint32_t q = __funnelshift_rc(wsd[j], wsd[j + 1], 8u * (uint32_t)(k + 1));
                                     const uint32_t b1 = (q >> 8) & 0xFFu, b3 = q >> 24;
                                     uint32_t code;
-                                    if ((q & 0x00FE00FEu) == 0x00300030u && (b1 == '/' || b1 == '|') && (b3 - '0') > 9u) code = (q & 1u) + ((q >> 16) & 1u);
-                                    else code = ib_sample_code(tin + pb + 4 * j + k + 1);
+                                    if (OP == OP_IB) {
+                                        // the four bytes behind the tab: [01] [/|] [01] and no further digit is the whole story
+                                        if ((q & 0x00FE00FEu) == 0x00300030u && (b1 == '/' || b1 == '|') && (b3 - '0') > 9u) code = (q & 1u) + ((q >> 16) & 1u);
+                                        else code = ib_sample_code(tin + pb + 4 * j + k + 1);
+                                        if (code < IB_NONE) { ib_alt += code; ++ib_good; }
+                                    } else {
+                                        // digit, separator, digit and the end of the GT (GT the first key)
+                                        const uint32_t d0 = (q & 0xFFu) - '0', d2 = ((q >> 16) & 0xFFu) - '0';
+                                        if (ds_gi == 0 && d0 <= 9u && d2 <= 9u && (b1 == '/' || b1 == '|') && (b3 == '\t' || b3 == ':' || b3 == '\n'))
+                                            code = (d0 ? 1u : 0u) + (d2 ? 1u : 0u);
+                                        else code = ds_sample_code(tin + pb + 4 * j + k + 1, P.mode == MODE_FILE, ds_gi);
+                                        if (code == IB_NONE) ++ib_alt;
+                                    }
                                     codes[r - 8] = (uint8_t)code;
-                                    if (code < IB_NONE) { ib_alt += code; ++ib_good; }
                                 }
                                 ++r;
                             }
@@ -2123,6 +2180,32 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                 md_add_nl = false;
                 md_last_end = raw_end;
             }
+            else if (OP == OP_DS) {
+                // VCFX_dosage_calculator.cpp:421-591 / :228-356: a row (CHROM .. ALT, then the dosages) for every data line with ten
+                // columns; "NA" alone without a GT key; a column that would start at the line end is not there
+                if (ee != ls && !hash) {
+                    VCFX_COUNT(C_DATA, 1);
+                    if (tabs < 9) {
+                        VCFX_COUNT(C_SHORT, 1);                          // "Skipping VCF line with fewer than 10 fields."
+                    } else {
+                        const uint32_t nna = __reduce_add_sync(FULL, ib_alt);
+                        const uint32_t prefix_len = tp[4] + 1 - ls;
+                        uint32_t ncols = (uint32_t)(tabs - 8);
+                        if (ldb(tin + ee - 1) == '\t') --ncols;
+                        const uint32_t dlen = ds_gi < 0 ? 2u : (ncols ? 2u * ncols - 1u + nna : 0u);
+                        if (lane == 0) {
+                            const unsigned long long slot = alloc_slot(ws.rec_base, ws.rec_used, P.stats);
+                            if (slot < P.rec_cap) {
+                                Rec r; r.tile = tile; r.ls_rel = (uint32_t)(a0 + ls - a); r.prefix_len = prefix_len;
+                                r.off_in_tile = (uint32_t)out_bytes; r.a = ncols; r.b = dlen; r.c = ds_gi < 0 ? 1u : 0u;
+                                r.d = (((tp[8] + 4u) >> 2) - 1u) & 3u;
+                                P.recs[slot] = r;
+                            }
+                        }
+                        out_bytes += prefix_len + dlen + 1u; VCFX_COUNT(C_ROWS, 1);
+                    }
+                }
+            }
             else if (OP == OP_GQ) {
                 // VCFX_genotype_query.cpp:446-516 / 546-606: '#' lines pass, empty lines vanish, a data line passes when it has a
                 // FORMAT column with a GT key and a sample whose GT is the query; no '\r' is cut.  (The caller feeds nothing
@@ -2262,7 +2345,7 @@ vcfx_scan_kernel(const VCFX_GRID_CONSTANT KParams P) {
     const int lane = lane_id();
     const int wid = threadIdx.x >> 5;
     const uint64_t n = P.n;
-    const bool strip_cr = (OP == OP_HWE) || (P.mode == MODE_FILE && (OP == OP_AF || OP == OP_VC || OP == OP_MD || OP == OP_NR || OP == OP_PC)) || OP == OP_IX || OP == OP_IB;
+    const bool strip_cr = (OP == OP_HWE) || (P.mode == MODE_FILE && (OP == OP_AF || OP == OP_VC || OP == OP_MD || OP == OP_NR || OP == OP_PC)) || OP == OP_IX || OP == OP_IB || (OP == OP_DS && P.mode == MODE_FILE);
     if (OP == OP_AC && P.ac_pass && P.stats->overflow) return;
     if (VAR == 1 && P.stats->n_unfinished == 0) return;
 
@@ -2756,6 +2839,42 @@ ib_rows_kernel(const KParams P) {
             }
             P.ib_rows[rank] = m;
         }
+    }
+}
+
+// dosage_calculator, K2b: a warp per row record writes "CHROM \t POS \t ID \t REF \t ALT \t" and the dosages d,d,NA,.. of the line's
+// sample columns from the codes the scan left (sample s: a ',' at 2s - 1 + (NAs before it) when it is not the first, its text behind)
+__global__ void __launch_bounds__(256)
+ds_rows_kernel(const KParams P) {
+    if (P.stats->overflow) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long nrec = P.stats->n_recs;
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < nrec; i += nwarps) {
+        const Rec r = P.recs[i];
+        if (r.tile == REC_INVALID) continue;
+        const unsigned long long line = (unsigned long long)r.tile * P.tile_bytes + r.ls_rel;
+        uint8_t *o = P.out + P.tile_base[r.tile] + r.off_in_tile;
+        if (P.tile_base[r.tile] + r.off_in_tile + r.prefix_len + r.b + 1u > P.out_cap) continue;        // (the scan has reported it)
+        warp_copy(o, P.in + line, r.prefix_len, lane);
+        o += r.prefix_len;
+        if (r.c) { if (lane == 0) { o[0] = 'N'; o[1] = 'A'; o[2] = '\n'; } continue; }
+        const uint8_t *codes = P.ib_codes + ((line & ~3ULL) + r.d);
+        uint32_t na_before = 0;
+        for (uint32_t s0 = 0; s0 < r.a; s0 += 32) {
+            const uint32_t s = s0 + (uint32_t)lane;
+            const bool in = s < r.a;
+            const uint32_t c = in ? (uint32_t)codes[s] : 0u;
+            const bool na = in && c >= IB_NONE;
+            const unsigned nb = __ballot_sync(FULL, na);
+            if (in) {
+                const uint32_t at = 2u * s + na_before + (uint32_t)__popc(nb & ((1u << lane) - 1u));
+                if (s) o[at - 1] = ',';
+                if (na) { o[at] = 'N'; o[at + 1] = 'A'; } else o[at] = (uint8_t)('0' + c);
+            }
+            na_before += (uint32_t)__popc(nb);
+        }
+        if (lane == 0) o[r.b] = '\n';
     }
 }
 
