@@ -392,7 +392,8 @@ def config_entries(torch, np, api, synth, O, dev, peak, threads, only=None):
         ("C2", 2, C2_VARIANTS, [("hwe_tester", api.OP_HWE, 0, {}, 20000), ("nonref_filter", api.OP_NONREF_FILTER, 0, {}, 20000),
                                 ("indexer", api.OP_INDEX, 0, {}, 60000), ("phase_checker", api.OP_PHASE_CHECK, 0, {}, 20000),
                                 ("inbreeding_calculator", api.OP_INBREEDING, 0, sel, 20000),
-                                ("genotype_query -g 1/1", api.OP_GENOTYPE_QUERY, 0, dict(query=b"1/1"), 20000)]),
+                                ("genotype_query -g 1/1", api.OP_GENOTYPE_QUERY, 0, dict(query=b"1/1"), 20000),
+                                ("dosage_calculator", api.OP_DOSAGE, 0, {}, 20000)]),
         ("C3", 3, C2_VARIANTS, [("missing_detector", api.OP_MISSING_DETECT, 0, {}, 20000),
                                 ("allele_counter", api.OP_ALLELE_COUNT, 0, sel, 4000),
                                 ("allele_counter -a", api.OP_ALLELE_COUNT, api.F_AC_AGGREGATE, sel, 400),
@@ -409,7 +410,7 @@ def config_entries(torch, np, api, synth, O, dev, peak, threads, only=None):
         log(f"[bench] {cname}: {sh.nbytes / 1e9:.2f} GB, {V} variants generated in {sh.gen_s:.1f}s")
         for tname, op, flags, kw, ref_variants in tools:
             out_cap = 64 << 20
-            if op in (api.OP_MISSING_DETECT, api.OP_NONREF_FILTER, api.OP_PHASE_CHECK, api.OP_GENOTYPE_QUERY):
+            if op in (api.OP_MISSING_DETECT, api.OP_NONREF_FILTER, api.OP_PHASE_CHECK, api.OP_GENOTYPE_QUERY, api.OP_DOSAGE):
                 out_cap = sh.nbytes + sh.nbytes // 50 + (1 << 20)
             if op == api.OP_ALLELE_COUNT and flags == 0:
                 out_cap = int(sh.nbytes * 9.5) + (1 << 20)
@@ -431,12 +432,12 @@ def config_entries(torch, np, api, synth, O, dev, peak, threads, only=None):
                    "input_GBps": sh.nbytes / k / 1e6, "genotypes_per_s": V * SAMPLES / (k / 1e3), "rows": int(st.rows)}
             ctx.close()
             # full-size byte parity of the resident output against the CPU restatement (small outputs only)
-            if tname in ("hwe_tester", "allele_freq_calc", "allele_counter -a"):
+            if tname in ("hwe_tester", "allele_freq_calc", "allele_counter -a", "dosage_calculator"):
                 got = hashlib.sha256(d_out[:int(st.bytes_out)].cpu().numpy().tobytes()).hexdigest()
                 if tname == "allele_counter -a":
                     exp, n_exp = oracle_parallel(O, "allele_counter", sh, np, path=O.AC_UNIFIED, fmt=O.AC_AGGREGATE)
                 else:
-                    exp, n_exp = oracle_parallel(O, {"hwe_tester": "hwe", "allele_freq_calc": "allele_freq"}[tname], sh, np)
+                    exp, n_exp = oracle_parallel(O, {"hwe_tester": "hwe", "allele_freq_calc": "allele_freq", "dosage_calculator": "dosage"}[tname], sh, np)
                 ent["parity_full"] = {"against": "oracle port, all host cores, the whole input", "bytes": int(st.bytes_out),
                                       "equal": got == exp and n_exp == int(st.bytes_out), "sha256": got}
             if tname == "inbreeding_calculator":
@@ -482,7 +483,7 @@ def parity_vs_reference(api, O, np, shard, tname, n_variants):
     """GPU tool output (through the C ABI, FILE semantics) against the stdout of the unmodified reference tool
     on the first n_variants lines of the shard."""
     tool = {"hwe_tester": "hwe_tester", "allele_freq_calc": "allele_freq_calc", "missing_detector": "missing_detector",
-            "allele_counter": "allele_counter", "allele_counter -a": "allele_counter", "variant_counter": "variant_counter", "nonref_filter": "nonref_filter", "indexer": "indexer", "phase_checker": "phase_checker", "inbreeding_calculator": "inbreeding_calculator", "genotype_query -g 1/1": "genotype_query"}[tname]
+            "allele_counter": "allele_counter", "allele_counter -a": "allele_counter", "variant_counter": "variant_counter", "nonref_filter": "nonref_filter", "indexer": "indexer", "phase_checker": "phase_checker", "inbreeding_calculator": "inbreeding_calculator", "genotype_query -g 1/1": "genotype_query", "dosage_calculator": "dosage_calculator"}[tname]
     exe = ref_tool(tool)
     data = shard.prefix_bytes(np, n_variants)
     if tname == "hwe_tester":
@@ -501,6 +502,8 @@ def parity_vs_reference(api, O, np, shard, tname, n_variants):
         got = api.inbreeding_calculator(data, api.FILE).out; args = ["-q", "-i"]
     elif tname == "genotype_query -g 1/1":
         got = api.genotype_query(data, "1/1", api.FILE, quiet=True).out; args = ["-q", "-g", "1/1", "-i"]
+    elif tname == "dosage_calculator":
+        got = api.dosage_calculator(data, api.FILE, quiet=True).out; args = ["-q", "-i"]
     elif tname == "allele_counter":
         got = api.allele_counter(data, api.AC_MT_TEXT, api.AC_TEXT).out; args = ["-q", "-i"]
     elif tname == "allele_counter -a":
@@ -511,7 +514,7 @@ def parity_vs_reference(api, O, np, shard, tname, n_variants):
     if exe is None:
         # no reference binary on this box: the CPU restatement (pinned to the reference by tests/) stands in
         fn = {"hwe_tester": lambda: O.hwe(data, 0), "allele_freq_calc": lambda: O.allele_freq(data, 0), "missing_detector": lambda: O.missing(data, 0),
-              "nonref_filter": lambda: O.nonref_filter(data, 0), "indexer": lambda: O.indexer(data, 0), "phase_checker": lambda: O.phase_checker(data, 0), "inbreeding_calculator": lambda: O.inbreeding(data, 0, O.IB_QUIET), "genotype_query -g 1/1": lambda: O.genotype_query(data, "1/1", 0)[0], "allele_counter": lambda: O.allele_counter(data), "allele_counter -a": lambda: O.allele_counter(data, O.AC_UNIFIED, O.AC_AGGREGATE),
+              "nonref_filter": lambda: O.nonref_filter(data, 0), "indexer": lambda: O.indexer(data, 0), "phase_checker": lambda: O.phase_checker(data, 0), "inbreeding_calculator": lambda: O.inbreeding(data, 0, O.IB_QUIET), "genotype_query -g 1/1": lambda: O.genotype_query(data, "1/1", 0)[0], "dosage_calculator": lambda: O.dosage(data, 0), "allele_counter": lambda: O.allele_counter(data), "allele_counter -a": lambda: O.allele_counter(data, O.AC_UNIFIED, O.AC_AGGREGATE),
               "variant_counter": lambda: O.variant_count(data, 0)}[tname]
         exp = fn().out
         res.update({"against": "oracle port (reference binary not built on this box)", "equal": exp == got})

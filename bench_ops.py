@@ -44,7 +44,7 @@ def main():
     plans = {
         "C2": (2, int(427409 * args.scale), [("allele_freq_calc", api.OP_ALLELE_FREQ, 0), ("variant_counter", api.OP_VARIANT_COUNT, 0),
                                              ("hwe_tester", api.OP_HWE, 0), ("nonref_filter", api.OP_NONREF_FILTER, 0), ("phase_checker", api.OP_PHASE_CHECK, 0),
-                                             ("indexer", api.OP_INDEX, 0), ("inbreeding_calculator", api.OP_INBREEDING, 0), ("genotype_query", api.OP_GENOTYPE_QUERY, 0)]),
+                                             ("indexer", api.OP_INDEX, 0), ("inbreeding_calculator", api.OP_INBREEDING, 0), ("genotype_query", api.OP_GENOTYPE_QUERY, 0), ("dosage_calculator", api.OP_DOSAGE, 0)]),
         "C3": (3, int(427409 * args.scale), [("missing_detector", api.OP_MISSING_DETECT, 0), ("allele_counter -a", api.OP_ALLELE_COUNT, api.F_AC_AGGREGATE),
                                              ("allele_counter", api.OP_ALLELE_COUNT, 0), ("allele_freq_calc", api.OP_ALLELE_FREQ, 0),
                                              ("inbreeding_calculator", api.OP_INBREEDING, 0)]),
@@ -70,7 +70,7 @@ def main():
             if args.tools and not any(t == tname for t in args.tools.split(",")):
                 continue
             out_cap = 64 << 20
-            if op in (api.OP_MISSING_DETECT, api.OP_NONREF_FILTER, api.OP_PHASE_CHECK, api.OP_GENOTYPE_QUERY):
+            if op in (api.OP_MISSING_DETECT, api.OP_NONREF_FILTER, api.OP_PHASE_CHECK, api.OP_GENOTYPE_QUERY, api.OP_DOSAGE):
                 out_cap = nbytes + nbytes // 50 + (1 << 20)
             if op == api.OP_ALLELE_COUNT and flags == 0:
                 out_cap = int(nbytes * 9.5) + (1 << 20)

@@ -97,6 +97,13 @@ def hand_cases():
         L("GT", "10/1", "1/10"), L("GT:DP", "0/0:3", "1/0:4"), L("DP:GT", "3:0/0", "4:0|1"), L("DP:GT", "3", "4:"), L("DP", "0/1", "0/1"), L("", "0/1", "0/1"),
         "#between\tdata", "", L("GT", "0/0", "") + "\t", L("GT", "", "0/1"), L("GT"), "1\t1\t.\tA\tG\t.\t.\t.\tGT", "1\t5\tx", "1\t5\t", "a\tb\tc\td\te\tf\tg\th",
         L("GT", "0/0", "0/1\r"), L("GT", "0/1", "0/0") + "\r", "\r", L("GT", "0|1:7", "0/0"), L("GT", "1/1", "0/0"), "#tail1", "", "#tail2"]) + "\n")
+    # dosage_calculator: what a dosage is (separators anywhere, several digits, more or fewer than two alleles, a '.', stray bytes),
+    # GT not the first key / no GT key, empty columns, a final tab (that column is not there), short lines, CRLF
+    c["ds_quirks"] = (H + "S1\tS2\tS3\n" + "\n".join([
+        L("GT", "0/0", "0|1", "1/1"), L("GT", "1|2", "10/0", "00/01"), L("GT", "/0/1", "0//1", "0/1/"), L("GT", "0", "0/1/2", "0/1x"), L("GT", ".", "./.", "1/."),
+        L("GT", "", "0/1", ""), L("GT", "0/1", "1/1") + "\t", L("GT", "0/1") + "\t\t", L("GT"), "1\t1\t.\tA\tG\t.\t.\t.\tGT", "1\t5\tx", "",
+        L("GT:DP", "0/1:3", "1/1:", "0/0"), L("DP:GT", "3:0/1", "4", "5:"), L("DP:GT", ":1/1", "::", "3:1|0:9"), L("DP", "0/1", "1/1", "0/0"), L("", "0/1", "1/1", "0/0"),
+        "#late\tline", L("GT", " 0/1", "0/1 ", "0:1"), L("GT", "0/1", "1/1", "0/1\r"), L("GT", "1/1", "0/0", "0/1") + "\r", "\r", L("GT", "2|3", "0|0", "1|0")]) + "\n")
     # indexer: what counts as CHROM and POS in the two modes (blanks in front, signs, wrap-around, CRLF, "#CHROM" look-alikes)
     c["ix_quirks"] = ("##x\n #CHROMX\tY\n#CHROM\tPOS\tID\n1\t100\t.\n 2\t+7x\t.\n\t3\t5\n4\t0\n5\t-3\n6\t 12\n7\n8\t99999999999999999999\n"
                       "9\t12\r\n\n#late\t1\nchrX\t007\tid\n10\t9223372036854775807\n11\t9223372036854775808\n12\t-9223372036854775808\n13\t5")
@@ -128,6 +135,10 @@ def run_all(data: bytes, ac_ok: bool, md_file_ok: bool = True):
         out["phase_checker.file"] = [rc, base64.b64encode(so).decode(), base64.b64encode(se).decode()]
         rc, so, se = O.run_ref("phase_checker", ["-"], stdin=data)
         out["phase_checker.stdin"] = [rc, base64.b64encode(so).decode(), base64.b64encode(se).decode()]
+        # dosage_calculator: both modes, stdout and the whole stderr text
+        for key, args, stdin in (("file", ["-i", f.name], None), ("stdin", [], data)):
+            rc, so, se = O.run_ref("dosage_calculator", args, stdin=stdin)
+            out[f"dosage_calculator.{key}"] = [rc, base64.b64encode(so).decode(), base64.b64encode(se).decode()]
         # genotype_query: a flexible and a strict query in both modes, stdout and the whole stderr text
         for key, args, stdin in (("file.het", ["-g", "0/1", "-i", f.name], None), ("stdin.het", ["-g", "1/0"], data),
                                  ("file.strict", ["-g", "0|1", "--strict", "-i", f.name], None), ("stdin.strict", ["-g", "1/1", "--strict"], data)):
@@ -158,7 +169,7 @@ def main():
     fixtures = {}
     for name, data in hand_cases().items():
         # (the reference allele_counter does not come back from these two inputs: no allele_counter outputs for them)
-        fixtures[name] = dict(input=base64.b64encode(data).decode(), expect=run_all(data, ac_ok=(name not in ("ib_quirks", "gq_quirks"))))
+        fixtures[name] = dict(input=base64.b64encode(data).decode(), expect=run_all(data, ac_ok=(name not in ("ib_quirks", "gq_quirks", "ds_quirks"))))
     for shape, V, S in ((1, 40, 12), (2, 12, 300), (3, 30, 60), (4, 12, 9)):
         data = synth.make_vcf(shape, V, S, seed=70 + shape)
         fixtures[f"shape{shape}"] = dict(input=base64.b64encode(data).decode(), expect=run_all(data, ac_ok=True))

@@ -13,7 +13,7 @@ def load():
     for name, f in fx.items():
         exp = {}
         for k, v in f["expect"].items():
-            if k.startswith(("phase_checker", "inbreeding_calculator", "genotype_query")):          # [rc, stdout, stderr text]
+            if k.startswith(("phase_checker", "inbreeding_calculator", "genotype_query", "dosage_calculator")):          # [rc, stdout, stderr text]
                 exp[k] = (v[0], base64.b64decode(v[1]), base64.b64decode(v[2]))
                 continue
             exp[k] = (v[0], base64.b64decode(v[1])) + tuple(v[2:])

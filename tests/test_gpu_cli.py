@@ -127,6 +127,25 @@ def test_phase_checker(files, tmp_path):
     assert a[2] == b[2]
 
 
+def test_dosage_calculator(files, tmp_path):
+    """VCFX_dosage_calculator: stdout, stderr and exit code, file and stdin, -q (which the stdin path ignores),
+    several chunks, the quirks fixture, a data line in front of the header (nothing on stdout, exit code 1 in file mode)."""
+    import golden_util
+    q = tmp_path / "q.vcf"; q.write_bytes(golden_util.load()["ds_quirks"][0])
+    nohdr = tmp_path / "n.vcf"; nohdr.write_bytes(b"##f\n1\t1\t.\tA\tG\t.\t.\t.\tGT\t0/1\n#CHROM\tP\tI\tR\tA\tQ\tF\tI\tFORMAT\tS1\n")
+    for p in (files["late"], files["crlf"], q, nohdr):
+        for args in ([], ["-q"]):
+            a, b = both("dosage_calculator", [*args, "-i", str(p)])
+            assert a[2] == b[2]
+            a, b = both("dosage_calculator", args, stdin=p.read_bytes())
+            assert a[2] == b[2]
+    a, b = both("dosage_calculator", [str(q)])
+    assert a[2] == b[2]
+    both("dosage_calculator", ["-q", "-i", str(files["c3"])], env=SMALL_CHUNK)
+    both("dosage_calculator", ["-q"], stdin=files["c3"].read_bytes(), env=SMALL_CHUNK)
+    both("dosage_calculator", ["-q"], stdin=files["nonl"].read_bytes(), env={"VCFX_CHUNK_BYTES": "4096"})
+
+
 def test_genotype_query(files, tmp_path):
     """VCFX_genotype_query: stdout and stderr, file and stdin, flexible and strict, several chunks (stdin mode's
     '#' lines wait for a data line across chunk borders), the run that ends at a data line in front of the header."""
@@ -206,7 +225,7 @@ def test_indexer(files, tmp_path):
     both("indexer", [], stdin=files["nonl"].read_bytes(), env={"VCFX_CHUNK_BYTES": "4096"})
 
 
-@pytest.mark.parametrize("tool", ["allele_freq_calc", "hwe_tester", "missing_detector", "variant_counter", "allele_counter", "nonref_filter", "indexer", "phase_checker", "inbreeding_calculator", "genotype_query"])
+@pytest.mark.parametrize("tool", ["allele_freq_calc", "hwe_tester", "missing_detector", "variant_counter", "allele_counter", "nonref_filter", "indexer", "phase_checker", "inbreeding_calculator", "genotype_query", "dosage_calculator"])
 def test_flags(tool, files):
     for args in (["--help"], ["-v"]):
         both(tool, args)
@@ -214,7 +233,7 @@ def test_flags(tool, files):
         a, b = both(tool, ["-g", "0/1", "-i", "/nonexistent/file.vcf"]); assert a[2] == b[2]
         a, b = both(tool, ["-g", "0/1"], stdin=b""); assert a[2] == b[2]
         return
-    a, b = both(tool, ["/nonexistent/file.vcf"] if tool == "variant_counter" else (["-i", "/nonexistent/file.vcf"] if tool in ("nonref_filter", "phase_checker") else ["/nonexistent/file.vcf"] if tool == "indexer" else ["-q", "-i", "/nonexistent/file.vcf"]))
+    a, b = both(tool, ["/nonexistent/file.vcf"] if tool == "variant_counter" else (["-i", "/nonexistent/file.vcf"] if tool in ("nonref_filter", "phase_checker", "dosage_calculator") else ["/nonexistent/file.vcf"] if tool == "indexer" else ["-q", "-i", "/nonexistent/file.vcf"]))
     assert a[2] == b[2]
     # empty stdin: per-tool behaviour (help+rc1 / header only / nothing / Total 0); phase_checker without arguments prints its
     # help text unless stdin is readable at that very moment (a race with the parent closing the pipe): give it an argument

@@ -20,7 +20,7 @@ def _cmp(name, got, exp):
                              f"  got {got[max(0, i - 60): i + 60]!r}\n  exp {exp[max(0, i - 60): i + 60]!r}")
 
 
-def run_all(api, O, data, tag, chunk_bytes=0, tile_bytes=0, tools=("af", "hwe", "vc", "md", "nr", "ix", "pc", "ib", "gq")):
+def run_all(api, O, data, tag, chunk_bytes=0, tile_bytes=0, tools=("af", "hwe", "vc", "md", "nr", "ix", "pc", "ib", "gq", "ds")):
     kw = dict(chunk_bytes=chunk_bytes, tile_bytes=tile_bytes)
     for mode in MODES:
         if "af" in tools:
@@ -51,6 +51,10 @@ def run_all(api, O, data, tag, chunk_bytes=0, tile_bytes=0, tools=("af", "hwe", 
             _cmp(f"{tag} pc mode{mode}", r.out, o.out)
             _cmp(f"{tag} pc mode{mode} stderr", r.err, O.phase_checker_stderr(data, mode))
             assert (r.totals.rows, r.totals.pre_header, r.totals.flagged) == (o.rows, o.warnings, o.flagged + o.warnings)
+        if "ds" in tools:
+            r = api.dosage_calculator(data, mode, **kw); o = O.dosage(data, mode)
+            _cmp(f"{tag} ds mode{mode}", r.out, o.out)
+            assert (r.rc, r.err) == (o.rc, O.DS_ERROR if o.first_bad_line else O.DS_WARNING * o.warnings)
         if "gq" in tools:
             for q, strict in ((("0/1", False), ("1|1", True)) if mode == 0 else (("1/1", False), ("0|1", True))):
                 r = api.genotype_query(data, q, mode, strict, **kw); o, e = O.genotype_query(data, q, mode, strict)
@@ -419,6 +423,28 @@ def test_phase_checker_more_dropped_lines_than_the_event_list(cuda_api, oracle):
     o = oracle.phase_checker(data, 0)
     assert r.out == o.out and r.totals.flagged == n
     assert r.err == b"Warning: Invalid VCF line with fewer than 10 columns; skipping line.\n" * n
+
+
+def test_dosage_calculator_cases(cuda_api, oracle):
+    """VCFX_dosage_calculator: the quirks fixture; lines on the four-byte lattice of every length and phase with samples that
+    leave it; several chunks and tiny tiles; the run that ends at a data line in front of the header."""
+    import golden_util
+    data, _ = golden_util.load()["ds_quirks"]
+    for kw in ({}, {"tile_bytes": 512}, {"chunk_bytes": 4096}):
+        run_all(cuda_api, oracle, data, f"ds quirks {kw}", tools=("ds",), **kw)
+    hdr = b"##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t"
+    for S in (1, 2, 100, 126, 127, 128, 129, 255, 256, 257, 700):
+        lines = []
+        for k in range(48):
+            gts = [[b"0|1", b"1|1", b"0/0", b"2|0", b"./."][(i * 7 + k) % 5] for i in range(S)]
+            if k % 4 == 1:
+                gts[(k * 37) % S] = [b"0", b".", b"0/1/1", b"0|1:3", b"10|1", b"", b" 0|1"][k % 7]
+            lines.append(b"%d\t%d\t%s\tA\tG\t.\tPASS\t.\tGT\t" % (k % 22 + 1, 10 ** (k % 7), b"r" * (k % 5)) + b"\t".join(gts))
+        data = hdr + b"\t".join(b"S%d" % i for i in range(S)) + b"\n" + b"\n".join(lines) + (b"\n" if S % 2 else b"")
+        run_all(cuda_api, oracle, data, f"ds S{S}", tools=("ds",))
+        run_all(cuda_api, oracle, data, f"ds S{S} tile512", tile_bytes=512, tools=("ds",))
+    for data in (b"##f\n1\t1\t.\tA\tG\t.\t.\t.\tGT\t0/1\n" + hdr + b"S1\n", hdr + b"S1\n", b"", b"\n", b"##f\n"):
+        run_all(cuda_api, oracle, data, "ds stream edges", tools=("ds",))
 
 
 def test_genotype_query_cases(cuda_api, oracle):

@@ -38,6 +38,11 @@ def check_case(O, data, exp, name):
             assert (r.rc, r.out) == exp[key][:2], (name, key)
             if not strict:
                 assert r.warnings == exp[key][2], (name, key)
+    for key, mode in (("file", O.FILE), ("stdin", O.STDIN)):
+        k = f"dosage_calculator.{key}"
+        if k in exp:
+            r = O.dosage(data, mode)
+            assert (r.rc, r.out, O.DS_ERROR if r.first_bad_line else O.DS_WARNING * r.warnings) == tuple(exp[k][:3]), (name, k)
     for key, mode, q, strict in (("file.het", O.FILE, "0/1", False), ("stdin.het", O.STDIN, "1/0", False),
                                  ("file.strict", O.FILE, "0|1", True), ("stdin.strict", O.STDIN, "1/1", True)):
         k = f"genotype_query.{key}"
@@ -104,6 +109,10 @@ def test_oracle_matches_reference_binaries_fuzz(oracle, seed):
         assert (r.rc, r.out, O.phase_checker_stderr(data, O.STDIN)) == (rc, out, err), "phase_checker stdin"
         rc, out, err = O.run_ref("phase_checker", ["-q"], stdin=data)
         assert (rc, out, err) == (r.rc, r.out, b""), "phase_checker -q"
+        rc, out, err = O.run_ref("dosage_calculator", ["-i", f.name]); r = O.dosage(data, O.FILE)
+        assert (r.rc, r.out, O.DS_ERROR if r.first_bad_line else O.DS_WARNING * r.warnings) == (rc, out, err), "dosage_calculator file"
+        rc, out, err = O.run_ref("dosage_calculator", ["-q"], stdin=data); r = O.dosage(data, O.STDIN)
+        assert (r.rc, r.out, O.DS_ERROR if r.first_bad_line else O.DS_WARNING * r.warnings) == (rc, out, err), "dosage_calculator stdin"
         for q, strict in (("0/1", False), ("1|1", True), ("2/0", False)):
             a = ["-g", q] + (["--strict"] if strict else [])
             rc, out, err = O.run_ref("genotype_query", [*a, "-i", f.name]); r, e = O.genotype_query(data, q, O.FILE, strict)
