@@ -310,7 +310,8 @@ def test_multi_gpu_same_bytes(tmp_path):
     env_multi = {"VCFX_CUDA_DEVICES": "all", "VCFX_CHUNK_BYTES": str(128 << 10)}
     env_one = {"VCFX_CHUNK_BYTES": str(128 << 10)}
     cases = [("allele_freq_calc", ["-q", "-i"]), ("hwe_tester", ["-q", "-i"]), ("missing_detector", ["-q", "-t", "1", "-i"]),
-             ("variant_counter", []), ("allele_counter", ["-q", "-i"]), ("allele_counter", ["-q", "-a", "-i"]), ("nonref_filter", ["-i"]), ("indexer", []), ("phase_checker", ["-i"])]
+             ("variant_counter", []), ("allele_counter", ["-q", "-i"]), ("allele_counter", ["-q", "-a", "-i"]), ("nonref_filter", ["-i"]), ("indexer", []), ("phase_checker", ["-i"]),
+             ("genotype_query", ["-g", "0/1", "-i"]), ("dosage_calculator", ["-q", "-i"]), ("inbreeding_calculator", ["-q", "-i"])]
     for f in (src, late):
         for tool, args in cases:
             one = run(BIN / f"VCFX_{tool}", [*args, str(f)], env=env_one)

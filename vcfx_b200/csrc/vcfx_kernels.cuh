@@ -2846,8 +2846,10 @@ ib_rows_kernel(const KParams P) {
 // sample columns from the codes the scan left (sample s: a ',' at 2s - 1 + (NAs before it) when it is not the first, its text behind)
 __global__ void __launch_bounds__(256)
 ds_rows_kernel(const KParams P) {
+    __shared__ __align__(16) uint8_t s_stage[8][AC_STAGE + 32];      // the text is put together here and leaves in aligned 128-bit stores
     if (P.stats->overflow) return;
     const int lane = threadIdx.x & 31;
+    uint8_t *stage = s_stage[threadIdx.x >> 5];
     const unsigned long long nrec = P.stats->n_recs;
     const unsigned long long nwarps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
     for (unsigned long long i = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < nrec; i += nwarps) {
@@ -2860,21 +2862,41 @@ ds_rows_kernel(const KParams P) {
         o += r.prefix_len;
         if (r.c) { if (lane == 0) { o[0] = 'N'; o[1] = 'A'; o[2] = '\n'; } continue; }
         const uint8_t *codes = P.ib_codes + ((line & ~3ULL) + r.d);
-        uint32_t na_before = 0;
-        for (uint32_t s0 = 0; s0 < r.a; s0 += 32) {
+        uint32_t na_before = 0, flushed = 0;
+        uint32_t base = (uint32_t)((uintptr_t)o & 15u);              // the staged bytes sit at the destination's offset modulo 16
+        for (uint32_t sb = 0; sb < r.a; sb += 128) {
+          uint32_t c4[4];                                            // four steps' codes are under way before the first is used
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { const uint32_t sx = sb + 32u * u + (uint32_t)lane; c4[u] = sx < r.a ? (uint32_t)codes[sx] : 0u; }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t s0 = sb + 32u * u;
+            if (s0 >= r.a) break;
             const uint32_t s = s0 + (uint32_t)lane;
             const bool in = s < r.a;
-            const uint32_t c = in ? (uint32_t)codes[s] : 0u;
+            const uint32_t c = c4[u];
             const bool na = in && c >= IB_NONE;
             const unsigned nb = __ballot_sync(FULL, na);
             if (in) {
-                const uint32_t at = 2u * s + na_before + (uint32_t)__popc(nb & ((1u << lane) - 1u));
-                if (s) o[at - 1] = ',';
-                if (na) { o[at] = 'N'; o[at + 1] = 'A'; } else o[at] = (uint8_t)('0' + c);
+                uint8_t *w = stage + base + (2u * s + na_before + (uint32_t)__popc(nb & ((1u << lane) - 1u)) - flushed);
+                if (s) w[-1] = ',';
+                if (na) { w[0] = 'N'; w[1] = 'A'; } else w[0] = (uint8_t)('0' + c);
             }
             na_before += (uint32_t)__popc(nb);
+            const uint32_t s_end = min(s0 + 32u, r.a);
+            const uint32_t written = 2u * s_end - 1u + na_before;    // text bytes up to (not including) the next sample's comma
+            if (written - flushed + 96u + 16u > AC_STAGE) {
+                __syncwarp();
+                warp_flush_smem(o + flushed, stage + base, written - flushed, lane);
+                __syncwarp();
+                flushed = written; base = (uint32_t)((uintptr_t)(o + flushed) & 15u);
+            }
+          }
         }
-        if (lane == 0) o[r.b] = '\n';
+        if (lane == 0) stage[base + (r.b - flushed)] = '\n';
+        __syncwarp();
+        warp_flush_smem(o + flushed, stage + base, r.b + 1u - flushed, lane);
+        __syncwarp();
     }
 }
 
