@@ -360,6 +360,33 @@ def measure_h2d_ceiling(torch, shard, dev, dist, world, seconds=1.0):
     return world * shard.nbytes / float(t.item()) / 1e9
 
 
+def measure_bidir_ceiling(torch, shard, dev, seconds=1.0):
+    """The same bare host->device copies with an equally large device->host copy under way for every chunk (pinned
+    buffers, streams of their own): what the link gives the INPUT while an output as large as the input goes back —
+    the ceiling of `e2e` for missing_detector / nonref_filter / phase_checker / genotype_query style tools."""
+    K = 3
+    up = [torch.cuda.Stream(device=dev) for _ in range(K)]
+    down = [torch.cuda.Stream(device=dev) for _ in range(K)]
+    bufs = [torch.empty(CHUNK, dtype=torch.uint8, device=dev) for _ in range(K)]
+    back_d = [torch.empty(CHUNK, dtype=torch.uint8, device=dev) for _ in range(K)]
+    back_h = [torch.empty(CHUNK, dtype=torch.uint8, pin_memory=True) for _ in range(K)]
+
+    def one_pass():
+        for i, (s, e) in enumerate(shard.bounds):
+            with torch.cuda.stream(up[i % K]):
+                bufs[i % K][: e - s].copy_(shard.host[s:e], non_blocking=True)
+            with torch.cuda.stream(down[i % K]):
+                back_h[i % K][: e - s].copy_(back_d[i % K][: e - s], non_blocking=True)
+    one_pass(); torch.cuda.synchronize()
+    t0 = time.perf_counter(); n = 0
+    while True:
+        one_pass(); n += 1
+        torch.cuda.synchronize()
+        if time.perf_counter() - t0 > seconds:
+            break
+    return shard.nbytes / ((time.perf_counter() - t0) / n) / 1e9
+
+
 # ----------------------------------------------------------------------------------------
 def e2e_stream(api, ctx, shard, valid_abs, steps):
     """One tool through the streaming C ABI from the shard's pinned host memory: H2D, kernels and D2H per chunk."""
@@ -407,7 +434,8 @@ def config_entries(torch, np, api, synth, O, dev, peak, threads, only=None):
         if only and cname not in only:
             continue
         sh = Shard(torch, np, synth, api, dev, shape, 0, V, True, threads)
-        log(f"[bench] {cname}: {sh.nbytes / 1e9:.2f} GB, {V} variants generated in {sh.gen_s:.1f}s")
+        bidir = measure_bidir_ceiling(torch, sh, dev)
+        log(f"[bench] {cname}: {sh.nbytes / 1e9:.2f} GB, {V} variants generated in {sh.gen_s:.1f}s; input rate with an equal output going back: {bidir:.1f} GB/s")
         for tname, op, flags, kw, ref_variants in tools:
             out_cap = 64 << 20
             if op in (api.OP_MISSING_DETECT, api.OP_NONREF_FILTER, api.OP_PHASE_CHECK, api.OP_GENOTYPE_QUERY, api.OP_DOSAGE):
@@ -467,6 +495,9 @@ def config_entries(torch, np, api, synth, O, dev, peak, threads, only=None):
                     sh.bounds.append((pos, end)); pos = end
             ent["e2e"], rows = e2e_stream(api, sctx, sh, vf, 2)
             ent["e2e"]["chunk_bytes"] = e2e_chunk
+            if ent["e2e"]["d2h_bytes_per_step"] >= sh.nbytes // 2:      # an output about as large as the input: both directions of the link are busy
+                ent["e2e"]["bidir_ceiling_GBps"] = bidir
+                ent["e2e"]["frac_of_bidir_ceiling"] = ent["e2e"]["value"] / bidir
             if e2e_chunk != CHUNK:
                 sh.bounds = keep
             sctx.close()
