@@ -495,9 +495,11 @@ def config_entries(torch, np, api, synth, O, dev, peak, threads, only=None):
                     sh.bounds.append((pos, end)); pos = end
             ent["e2e"], rows = e2e_stream(api, sctx, sh, vf, 2)
             ent["e2e"]["chunk_bytes"] = e2e_chunk
-            if ent["e2e"]["d2h_bytes_per_step"] >= sh.nbytes // 2:      # an output about as large as the input: both directions of the link are busy
+            if sh.nbytes // 2 <= ent["e2e"]["d2h_bytes_per_step"] <= 2 * sh.nbytes:      # an output about as large as the input: both directions of the link are busy
                 ent["e2e"]["bidir_ceiling_GBps"] = bidir
                 ent["e2e"]["frac_of_bidir_ceiling"] = ent["e2e"]["value"] / bidir
+            elif ent["e2e"]["d2h_bytes_per_step"] > 2 * sh.nbytes:                        # the text going back is the bound: its own rate
+                ent["e2e"]["d2h_GBps"] = ent["e2e"]["d2h_bytes_per_step"] / (ent["e2e"]["ms_per_step"] * 1e6)
             if e2e_chunk != CHUNK:
                 sh.bounds = keep
             sctx.close()
