@@ -332,9 +332,9 @@ _ctx_cache: dict = {}
 def _cached_context(op, mode, device, flags, chunk_bytes, **kw):
     """Contexts are reusable once drained; creating one costs pinned and device allocations, so the
     helpers below keep a few around (allele_counter contexts carry a selection and are not cached)."""
-    if "sel_cols" in kw:
+    if "sel_cols" in kw and op != OP_INBREEDING:
         return Context(op, mode, device=device, flags=flags, chunk_bytes=chunk_bytes, **kw), False
-    key = (op, mode, device, flags, chunk_bytes, tuple(sorted(kw.items())))
+    key = (op, mode, device, flags, chunk_bytes, tuple(sorted((k, tuple(v) if isinstance(v, list) else v) for k, v in kw.items())))
     ctx = _ctx_cache.get(key)
     if ctx is None:
         if len(_ctx_cache) >= 24:
@@ -538,7 +538,8 @@ def inbreeding_calculator(data: bytes, mode: int = FILE, freq_global: bool = Fal
     flags = (F_IB_GLOBAL if freq_global else 0) | (F_IB_SKIP_BOUNDARY if skip_boundary else 0) | (F_IB_COUNT_BOUNDARY if count_boundary else 0)
     body = data[start:]
     chunk_bytes = chunk_bytes or min(64 << 20, max(1 << 20, (len(body) + (1 << 20) - 1) & ~((1 << 20) - 1)))
-    ctx = Context(OP_INBREEDING, mode, flags=flags, chunk_bytes=chunk_bytes, sel_cols=list(range(len(names))), sel_names=names, **kw)
+    # (a context is good for one stream after the other: the per-sample state starts again behind a final chunk)
+    ctx, cached = _cached_context(OP_INBREEDING, mode, 0, flags, chunk_bytes, sel_cols=list(range(len(names))), sel_names=names, **kw)
     try:
         if len(body) == 0:                                 # no data line at all: a final chunk of nothing still reports
             buf, cap = ctx.acquire()
@@ -548,7 +549,12 @@ def inbreeding_calculator(data: bytes, mode: int = FILE, freq_global: bool = Fal
             outs = [out]
         else:
             outs, tot = stream_bytes(ctx, body, chunk_bytes, 0)
-    finally:
+    except Exception:
+        if cached:
+            _ctx_cache.pop(next(k for k, v in _ctx_cache.items() if v is ctx), None)
+        ctx.close()
+        raise
+    if not cached:
         ctx.close()
     err = IB_MESSAGES[3] if (tot.rows == 0 and not quiet) else b""
     return ToolResult(IB_HEADER + b"".join(outs), 0, tot, err)
@@ -633,10 +639,15 @@ def genotype_query(data: bytes, query: str, mode: int = FILE, strict: bool = Fal
     tot = Totals(); out = b""
     if body:
         chunk_bytes = chunk_bytes or min(64 << 20, max(1 << 20, (len(body) + (1 << 20) - 1) & ~((1 << 20) - 1)))
-        ctx = Context(OP_GENOTYPE_QUERY, mode, flags=F_GQ_STRICT if strict else 0, chunk_bytes=chunk_bytes, query=q, **kw)
+        ctx, cached = _cached_context(OP_GENOTYPE_QUERY, mode, 0, F_GQ_STRICT if strict else 0, chunk_bytes, query=q, **kw)
         try:
             outs, tot = stream_bytes(ctx, body, chunk_bytes, 0, on_events)
-        finally:
+        except Exception:
+            if cached:
+                _ctx_cache.pop(next(k for k, v in _ctx_cache.items() if v is ctx), None)
+            ctx.close()
+            raise
+        if not cached:
             ctx.close()
         out = b"".join(outs)
     return ToolResult(out, 0, tot, b"" if quiet else b"".join(warn + msgs))
