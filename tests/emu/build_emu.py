@@ -18,7 +18,7 @@ def build(force: bool = False) -> Path:
     if not force and OUT.exists() and all(d.stat().st_mtime <= OUT.stat().st_mtime for d in deps):
         return OUT
     OUT.parent.mkdir(exist_ok=True)
-    cmd = ["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas", "-Wno-unused-variable", "-x", "c++", "-DVCFX_EMU",
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-Wall", "-Wno-unused-function", "-Wno-unknown-pragmas", "-Wno-unused-variable", "-x", "c++", "-DVCFX_EMU", "-DVCFX_C4_RING=1",
            "-I", str(HERE), "-I", str(ROOT / "include"), "-I", str(ROOT / "vcfx_b200" / "csrc"),
            "-fPIC", "-shared", "-o", str(OUT), *map(str, srcs)]
     tmp = OUT.with_name(f".{OUT.name}.{os.getpid()}")               # (several test processes may build at once: link aside, rename)

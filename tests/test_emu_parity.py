@@ -43,3 +43,19 @@ _SKIP = {"test_more_rows_than_the_default_record_capacity", "test_phase_checker_
 for _name, _fn in sorted(vars(G).items()):
     if _name.startswith("test_") and callable(_fn) and _name not in _SKIP:
         globals()[_name + "_emulated"] = _clone(_fn)
+
+
+def test_skip_ahead_loop_through_the_bulk_copy_ring(emu_api, oracle, monkeypatch):
+    """The emulator build compiles the bulk-copy ring of the skip-ahead loop in (the product build leaves it out: measured, did
+    not pay): with VCFX_C4_BULK=1 the multi-key shapes go through it."""
+    from vcfx_b200 import synth
+    monkeypatch.setenv("VCFX_C4_BULK", "1")
+    emu_api.close_cached_contexts()
+    try:
+        G.test_multikey_format_exceptions(cuda_api=emu_api, oracle=oracle)
+        for V, S in ((60, 300), (12, 2504)):
+            data = synth.make_vcf(4, V, S, seed=17)
+            G.run_all(emu_api, oracle, data, f"ring shape4 {V}x{S}", tools=("af", "hwe"))
+            G.run_all(emu_api, oracle, data, f"ring shape4 {V}x{S} tile512", tile_bytes=512, tools=("af", "hwe"))
+    finally:
+        emu_api.close_cached_contexts()

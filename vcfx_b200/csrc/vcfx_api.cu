@@ -109,6 +109,7 @@ struct vcfx_ctx {
     int ac_fmt = 0;
     bool ac_ident = false;               // allele_counter selection = columns 0 .. n_sel-1 in order
     bool ac_exact = false;               // a chunk had a count of two digits: rows are sized by parsing from now on
+    bool c4_bulk = false;                // VCFX_C4_BULK=1: the skip-ahead loop reads through the bulk-copy ring (see vcfx_kernels.cuh)
     // genotype_query: the query and what parseDiploidAlleles leaves of it
     uint8_t gq_query[64] = {0}; uint32_t gq_len = 0; int gq_a = -1, gq_b = -1;
     // inbreeding_calculator: the per-sample state that lives from chunk to chunk, and the order the chunks are applied in
@@ -383,6 +384,7 @@ int launch_chunk(vcfx_ctx *ctx, Work &w, cudaStream_t st, uint8_t *d_in, size_t 
     P.ac_fmt = ctx->ac_fmt; P.ac_ident = ctx->ac_ident ? 1 : 0; P.ac_pass = 0; P.ac_spec = (ctx->cfg.op == VCFX_OP_ALLELE_COUNT && ctx->ac_fmt == AC_TEXT_MT && !ctx->ac_exact) ? 1 : 0; P.n_sel = ctx->n_sel; P.sel_col = ctx->d_sel_col; P.name_off = ctx->d_name_off;
     P.names = ctx->d_names; P.names16 = ctx->d_names16; P.name_len = ctx->name_len; P.ac_bulk = ctx->ac_bulk ? 1 : 0; P.max_col = ctx->max_col; P.col_scratch = w.col_scratch;
     P.ticket = w.ticket; P.ticket2 = w.ticket + 1; P.tile_resume = w.tile_resume; P.recs = w.recs; P.rec_prefix = w.rec_prefix; P.rec_cap = w.rec_cap;
+    P.c4_bulk = ctx->c4_bulk ? 1 : 0;
     memcpy(P.gq_query, ctx->gq_query, sizeof P.gq_query); P.gq_len = ctx->gq_len; P.gq_a = ctx->gq_a; P.gq_b = ctx->gq_b; P.gq_strict = (ctx->cfg.flags & VCFX_F_GQ_STRICT) ? 1 : 0;
     P.ib_codes = w.ib_codes; P.ib_rows = w.ib_rows; P.ib_panels = w.ib_panels; P.ib_panel_cap = w.ib_panel_cap; P.ib = ctx->d_ib; P.ib_seq = w.ib_seq; P.ib_first = w.ib_first ? 1 : 0; P.text_cap = out_cap;
     if (ctx->cfg.op == VCFX_OP_INBREEDING) P.out_cap = ~0ULL;       // the scan counts rows there, not bytes of text
@@ -591,6 +593,7 @@ int vcfx_cuda_create(const vcfx_cfg *cfg, vcfx_ctx **out) {
             ctx->ac_bulk = !(be && *be == '0');
         }
     }
+    { const char *be = getenv("VCFX_C4_BULK"); ctx->c4_bulk = be && *be == '1'; }
     if (cfg->op == VCFX_OP_GENOTYPE_QUERY) {
         // cfg.sel_names = the -g argument, cfg.n_sel = its length.  VCFX_genotype_query.cpp:246-272 parseDiploidAlleles on it,
         // keeping whatever the parse assigned before it gave up (:640-644 uses the two numbers whether it succeeded or not)

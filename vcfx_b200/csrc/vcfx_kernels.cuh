@@ -134,6 +134,7 @@ struct KParams {
     unsigned long long *events;      // short-line events (tile << 32 | index in tile)
     uint32_t ev_cap;
     unsigned long long fmt0_until;   // phase_checker, file mode: an empty FORMAT column of a line starting below this offset means GT index 0
+    int32_t c4_bulk;                 // the skip-ahead loop (FORMAT with several keys) is fed by cp.async.bulk through a ring in shared memory
     // GENOTYPE_QUERY
     uint8_t gq_query[64];            // the -g argument (gq_len bytes)
     uint32_t gq_len;
@@ -940,6 +941,9 @@ struct WarpShared {
     unsigned int *cnt;                     // event counters (CNT_SLOTS)
     unsigned long long *rec_base; unsigned int *rec_used;
     volatile unsigned int *odd, *reg, *tag;   // [WARPS_PER_CTA] arrays (indexed by the warp)
+    uint8_t *ring;                         // general kernel: C4_RING bytes of input staged by the bulk-copy engine
+    unsigned long long *bars;              //   its C4_STAGES mbarriers
+    uint32_t *ring_par;                    //   and their parities (bit s: what stage s is waited on next)
 };
 // what a warp carries from line to line inside a tile
 template <int OP> struct TileState {
@@ -955,8 +959,51 @@ template <int OP> struct TileState {
 // anything this does not decide (then nothing may be added for the window).
 //   allele_freq_calc (allele_freq_calc.cpp:262-293): "d sep d" closed by ':' or a tab is two alleles, ". sep ." is none
 //   hwe_tester (hwe_tester.cpp:339-378): "d sep d" and no third digit is a call (both alleles <= 1 count), ". sep ." is none
-template <int OP>
-__device__ __forceinline__ bool multikey_window(const uint4 v, const uint8_t *__restrict__ p, uint32_t &da, uint32_t &db, uint32_t &dc) {
+// ---- the ring the bulk-copy engine fills for the skip-ahead loop (north_star stage 3: "TMA bulk loads where record spans are
+// long enough to pay off"): C4_STAGES pieces of C4_PIECE bytes per warp; piece k of a run that starts at global offset g0 sits
+// at ring offset (k * C4_PIECE) mod C4_RING, so a byte at g0 + x sits at x mod C4_RING; ONE cp.async.bulk (global -> shared,
+// UBLKCP) per piece, completion on the piece's mbarrier
+// MEASURED (profiles/README.md, round 2): the stand-alone scan gains 27-31 % from this feed, the product's loop nothing (C4 hwe_tester
+// 1.928 -> 1.938 ms, allele_freq_calc 1.916 -> 1.887 ms), and the 32 KiB of shared memory per CTA cost the loop's L1 hits 4-5 % even
+// with the ring unused — so the ring is compiled in only with -DVCFX_C4_RING=1 (the warp emulator's build does, to keep it tested).
+#ifndef VCFX_C4_RING
+#define VCFX_C4_RING 0
+#endif
+constexpr uint32_t C4_PIECE = 1024, C4_STAGES = 4, C4_RING = C4_PIECE * C4_STAGES;
+__device__ __forceinline__ void ring_init(unsigned long long *bars, int lane) {
+#ifndef VCFX_EMU
+    if (lane == 0) {
+        const uint32_t b = (uint32_t)__cvta_generic_to_shared(bars);
+        for (uint32_t i = 0; i < C4_STAGES; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(b + 8u * i));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+#endif
+}
+__device__ __forceinline__ void ring_issue(uint8_t *ring, unsigned long long *bars, const uint8_t *g0, uint32_t k) {   // lane 0 only
+    const uint32_t st = k % C4_STAGES;
+#ifdef VCFX_EMU
+    for (uint32_t i = 0; i < C4_PIECE; ++i) ring[st * C4_PIECE + i] = g0[(size_t)k * C4_PIECE + i];
+#else
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(bars + st), dst = (uint32_t)__cvta_generic_to_shared(ring + st * C4_PIECE);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(C4_PIECE) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(g0 + (size_t)k * C4_PIECE), "r"(C4_PIECE), "r"(bar) : "memory");
+#endif
+}
+__device__ __forceinline__ void ring_wait(unsigned long long *bars, uint32_t st, uint32_t parity) {
+#ifndef VCFX_EMU
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(bars + st);
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+#endif
+}
+
+// RING: the four bytes behind the tab come from the ring (x = offset of p from the start of the run) instead of global memory
+template <int OP, bool RING = false>
+__device__ __forceinline__ bool multikey_window(const uint4 v, const uint8_t *__restrict__ p, uint32_t &da, uint32_t &db, uint32_t &dc,
+                                                const uint8_t *ring = nullptr, uint32_t x = 0) {
     // tab and '\n' markers by range: 3 adds and 2 LOP3 per word
     const uint32_t a0 = VCFX_GE(v.x, 0x09), b0 = VCFX_GE(v.x, 0x0A), c0 = VCFX_GE(v.x, 0x0B);
     const uint32_t a1 = VCFX_GE(v.y, 0x09), b1 = VCFX_GE(v.y, 0x0A), c1 = VCFX_GE(v.y, 0x0B);
@@ -971,9 +1018,17 @@ __device__ __forceinline__ bool multikey_window(const uint4 v, const uint8_t *__
                              (((tm2 * 0x00204081u) >> 20) & 0xF00u) | (((tm3 * 0x00204081u) >> 16) & 0xF000u);
         if (m16 & (m16 - 1u)) odd = true;            // two sample starts in 16 bytes
         // the four bytes behind the tab: two aligned loads (L1: the bytes were streamed by this warp a moment ago)
-        const uint8_t *s = p + __ffs(m16);
-        const uint32_t *s4 = reinterpret_cast<const uint32_t *>((uintptr_t)s & ~(uintptr_t)3);
-        const uint32_t q = __funnelshift_r(__ldg(s4), __ldg(s4 + 1), 8u * (uint32_t)((uintptr_t)s & 3));
+        uint32_t q;
+        if (RING) {
+            const uint32_t xs = x + (uint32_t)__ffs(m16);
+            const uint32_t w0 = *reinterpret_cast<const uint32_t *>(ring + ((xs & ~3u) & (C4_RING - 1u)));
+            const uint32_t w1 = *reinterpret_cast<const uint32_t *>(ring + (((xs & ~3u) + 4u) & (C4_RING - 1u)));
+            q = __funnelshift_r(w0, w1, 8u * (xs & 3u));
+        } else {
+            const uint8_t *s = p + __ffs(m16);
+            const uint32_t *s4 = reinterpret_cast<const uint32_t *>((uintptr_t)s & ~(uintptr_t)3);
+            q = __funnelshift_r(__ldg(s4), __ldg(s4 + 1), 8u * (uint32_t)((uintptr_t)s & 3));
+        }
         const uint32_t q1 = (q >> 8) & 0xFFu, q3 = q >> 24;
         const bool sep = (q1 == '/') | (q1 == '|');
         const uint32_t dg = q & 0x00FF00FFu;         // bytes 0 and 2
@@ -1148,7 +1203,46 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                     // for one window is not a wait for the newest load.  The window with the '\n', a lane with two tabs, a
                     // byte >= 0x80 and every genotype that needs more than four bytes leave the loop with nothing added, for
                     // the exact path below.
-                    if (VAR == 1 && !first_win && !lat_possible && gt_index == 0) {
+                    if (VCFX_C4_RING && VAR == 1 && !first_win && !lat_possible && gt_index == 0 && P.c4_bulk) {
+                        // the same loop fed by the bulk-copy engine: pieces of two windows, four of them in the ring (the one being
+                        // looked at, the next — a sample's four bytes may reach into it — and two on their way)
+                        const uint8_t *g0 = tin + wb;
+                        uint8_t *ring = ws.ring; unsigned long long *bars = ws.bars;
+                        uint32_t par = *ws.ring_par;                  // bit s: the parity stage s completes with next
+                        if (lane == 0) for (uint32_t q = 0; q < C4_STAGES; ++q) ring_issue(ring, bars, g0, q);
+                        uint32_t k = 0;
+                        ring_wait(bars, 0, (par >> 0) & 1u); par ^= 1u;
+                        for (;;) {
+                            const uint32_t st = k % C4_STAGES, st1 = (k + 1) % C4_STAGES;
+                            ring_wait(bars, st1, (par >> st1) & 1u); par ^= 1u << st1;       // the piece behind this one is in as well
+                            const uint8_t *rp = ring + st * C4_PIECE + 16 * lane;
+                            const uint4 v0 = *reinterpret_cast<const uint4 *>(rp), v1 = *reinterpret_cast<const uint4 *>(rp + WINDOW);
+                            uint32_t da0, db0, dc0, da1, db1, dc1;
+                            const uint32_t x0 = k * C4_PIECE + 16u * (uint32_t)lane;
+                            const bool o0 = multikey_window<OP, true>(v0, nullptr, da0, db0, dc0, ring, x0);
+                            const bool o1 = multikey_window<OP, true>(v1, nullptr, da1, db1, dc1, ring, x0 + WINDOW);
+                            if (__any_sync(FULL, o0 | o1)) break;
+                            ta += da0 + da1; tb += db0 + db1; tc += dc0 + dc1;
+                            __syncwarp();                                             // every lane is done with piece k
+                            if (lane == 0) {
+#ifndef VCFX_EMU
+                                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+                                ring_issue(ring, bars, g0, k + C4_STAGES);
+                            }
+                            ++k;
+                        }
+                        // pieces k+2, k+3 are still on their way (k+1 has been waited for): they must have landed before the ring is used again
+                        { const uint32_t s2 = (k + 2) % C4_STAGES, s3 = (k + 3) % C4_STAGES;
+                          ring_wait(bars, s2, (par >> s2) & 1u); par ^= 1u << s2;
+                          ring_wait(bars, s3, (par >> s3) & 1u); par ^= 1u << s3; }
+                        // piece k itself was waited for at the top of round k-1 (or before the loop); its flip is already in par
+                        *ws.ring_par = par;
+                        // back to the three windows the rest of the line loop works with: cur = the first window not added
+                        wb += k * C4_PIECE;
+                        cur = ld16(tin + wb + 16 * lane); nxt = ld16(tin + wb + WINDOW + 16 * lane); nx2 = ld16(tin + wb + 2 * WINDOW + 16 * lane);
+                    }
+                    else if (VAR == 1 && !first_win && !lat_possible && gt_index == 0) {
                         uint4 nx3 = ld16(tin + wb + 3 * WINDOW + 16 * lane);
                         int state = 0;                           // which pair met something odd: 1 = (cur, nxt), 2 = (nx2, nx3)
                         const uint8_t *lp = tin + wb + 16 * lane;
@@ -2340,6 +2434,9 @@ template <int OP, int VAR>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (OP == OP_VC) ? 5 : (VAR == 1 ? VCFX_GENERAL_CTAS : (OP == OP_AC ? VCFX_AC_CTAS : VCFX_PARSE_CTAS)))
 vcfx_scan_kernel(const VCFX_GRID_CONSTANT KParams P) {
     __shared__ uint32_t s_tp[WARPS_PER_CTA][12];
+    __shared__ __align__(128) uint8_t s_ring[(VCFX_C4_RING && VAR == 1) ? WARPS_PER_CTA * C4_RING : 16];
+    __shared__ __align__(8) unsigned long long s_bars[(VCFX_C4_RING && VAR == 1) ? WARPS_PER_CTA * C4_STAGES : 1];
+    __shared__ uint32_t s_ring_par[WARPS_PER_CTA];
     __shared__ __align__(16) uint8_t s_stage[(OP == OP_AC) ? WARPS_PER_CTA * (AC_STAGE + 32) : 16];
     __shared__ uint32_t s_u[(OP == OP_AC) ? WARPS_PER_CTA : 1][20];
     const int lane = lane_id();
@@ -2363,6 +2460,8 @@ vcfx_scan_kernel(const VCFX_GRID_CONSTANT KParams P) {
     __syncwarp();
     WarpShared ws;
     ws.tp = s_tp[wid]; ws.stage0 = s_stage + ((OP == OP_AC) ? wid * (AC_STAGE + 32) : 0); ws.cnt = s_cnt[wid]; ws.u = s_u[(OP == OP_AC) ? wid : 0];
+    ws.ring = s_ring + ((VCFX_C4_RING && VAR == 1) ? wid * C4_RING : 0); ws.bars = s_bars + ((VCFX_C4_RING && VAR == 1) ? wid * C4_STAGES : 0); ws.ring_par = &s_ring_par[wid];
+    if (VCFX_C4_RING && VAR == 1) { if ((threadIdx.x & 31) == 0) s_ring_par[wid] = 0; ring_init(ws.bars, threadIdx.x & 31); }
     ws.rec_base = &s_rec_base[wid]; ws.rec_used = &s_rec_used[wid]; ws.odd = s_odd; ws.reg = s_reg; ws.tag = s_tag;
 
     for (;;) {
