@@ -109,7 +109,7 @@ def test_phase_checker(files, tmp_path):
     phased = tmp_path / "p.vcf"
     rows = [b"21\t%d\t.\tA\tG\t.\tPASS\t.\tGT\t" % (i + 1) + b"\t".join([b"0|1"] * 299 + [b"0/1" if i % 3 == 0 else b"1|0"]) for i in range(400)]
     phased.write_bytes(b"##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + b"\t".join(b"S%d" % i for i in range(300)) + b"\n" + b"\n".join(rows) + b"\n")
-    for p in (files["late"], files["crlf"], q, fc, phased):
+    for p in (files["crlf"], q, fc, phased):
         a, b = both("phase_checker", ["-i", str(p)])
         assert a[2] == b[2]
         a, b = both("phase_checker", ["-"], stdin=p.read_bytes())
@@ -133,8 +133,8 @@ def test_dosage_calculator(files, tmp_path):
     import golden_util
     q = tmp_path / "q.vcf"; q.write_bytes(golden_util.load()["ds_quirks"][0])
     nohdr = tmp_path / "n.vcf"; nohdr.write_bytes(b"##f\n1\t1\t.\tA\tG\t.\t.\t.\tGT\t0/1\n#CHROM\tP\tI\tR\tA\tQ\tF\tI\tFORMAT\tS1\n")
-    for p in (files["late"], files["crlf"], q, nohdr):
-        for args in ([], ["-q"]):
+    for p, arg_sets in ((files["crlf"], ([],)), (q, ([], ["-q"])), (nohdr, ([],))):
+        for args in arg_sets:
             a, b = both("dosage_calculator", [*args, "-i", str(p)])
             assert a[2] == b[2]
             a, b = both("dosage_calculator", args, stdin=p.read_bytes())
@@ -155,8 +155,8 @@ def test_genotype_query(files, tmp_path):
     body = synth.make_vcf(3, 300, 60, seed=31)
     tails.write_bytes(body + b"#t1\n\n#t2\n" + b"#pad\n" * 2000)                      # '#' lines behind the last data line, several chunks of them
     nohdr = tmp_path / "n.vcf"; nohdr.write_bytes(b"##f\n#x\n1\t1\t.\tA\tG\t.\t.\t.\tGT\t0/1\n" + body)
-    for p in (files["late"], files["crlf"], q, tails, nohdr):
-        for args in (["-g", "0/1"], ["-g", "1|1", "--strict"]):
+    for p, arg_sets in ((files["crlf"], (["-g", "0/1"],)), (q, (["-g", "0/1"], ["-g", "1|1", "--strict"])), (tails, (["-g", "1|1", "--strict"],)), (nohdr, (["-g", "0/1"],))):
+        for args in arg_sets:          # (every invocation is a process with its own CUDA context: about a second each)
             a, b = both("genotype_query", [*args, "-i", str(p)])
             assert a[2] == b[2]
             a, b = both("genotype_query", args, stdin=p.read_bytes())
@@ -180,7 +180,7 @@ def test_inbreeding_calculator(files, tmp_path):
     import golden_util
     q = tmp_path / "q.vcf"; q.write_bytes(golden_util.load()["ib_quirks"][0])
     wide = tmp_path / "w.vcf"; wide.write_bytes(synth.make_vcf(3, 1500, 300, seed=21))
-    for p in (files["late"], files["crlf"], q, wide):
+    for p in (files["crlf"], q, wide):
         a, b = both("inbreeding_calculator", ["-q", "-i", str(p)])
         assert a[2] == b[2]
         a, b = both("inbreeding_calculator", ["-q"], stdin=p.read_bytes())
@@ -190,7 +190,8 @@ def test_inbreeding_calculator(files, tmp_path):
     for args in (["--freq-mode", "global"], ["--skip-boundary"], ["--skip-boundary", "--count-boundary-as-used"], ["--freq-mode", "bogus"]):
         a, b = both("inbreeding_calculator", ["-q", *args, "-i", str(q)])
         assert a[2] == b[2]
-        both("inbreeding_calculator", ["-q", *args], stdin=wide.read_bytes(), env=SMALL_CHUNK)
+    both("inbreeding_calculator", ["-q", "--skip-boundary", "--count-boundary-as-used"], stdin=wide.read_bytes(), env=SMALL_CHUNK)
+    both("inbreeding_calculator", ["-q", "--freq-mode", "global"], stdin=wide.read_bytes(), env=SMALL_CHUNK)
     both("inbreeding_calculator", ["-q", "-i", str(wide)], env=SMALL_CHUNK)
     both("inbreeding_calculator", ["-q", "-i", str(files["c3"])], env={"VCFX_CHUNK_BYTES": str(wide.stat().st_size // 3)})
     both("inbreeding_calculator", ["-q"], stdin=files["nonl"].read_bytes(), env={"VCFX_CHUNK_BYTES": "4096"})
