@@ -145,8 +145,10 @@ int main(int argc, char *argv[]) {
                     head.erase(0, next);
                     break;
                 }
-                // nothing in front of the header line matters: give the bytes up as they go by
-                head.erase(0, next); scan = 0;
+                // nothing in front of the header line matters: give the bytes up as they go by (in bulk: a stream may have
+                // millions of lines in front of a late header)
+                scan = next;
+                if (scan >= (1u << 20)) { head.erase(0, scan); scan = 0; }
             }
         }
     }
