@@ -370,6 +370,12 @@ def test_nonref_filter_cases(cuda_api, oracle):
     for kw in ({}, {"tile_bytes": 512}, {"chunk_bytes": 4096}):
         run_all(cuda_api, oracle, data, f"nr quirks {kw}", tools=("nr",), **kw)
     hdr = b"##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t"
+    # GT not the first key: a column that is just "0|0" has no GT piece at all — not hom-ref, the line stays (found by fuzzing)
+    data = hdr + b"S1\tS2\n" + b"".join(b"1\t%d\t.\tT\tG\t.\tq10\tDP=3;\t%s\t%s\t%s\n" % (k + 1, f, a, b2) for k, (f, a, b2) in enumerate(
+        [(b"DP:GQ:GT", b"0|0", b"0/1:35:0/0"), (b"DP:GQ:GT", b"3:35:0/0", b"0/0"), (b"DP:GT", b"0/0", b"0|0"), (b"DP:GT", b"1:0/0", b"2:0|0"),
+         (b"GT:DP", b"0|0", b"0/0:3"), (b"DP:GT", b"0/0:0/0", b"0|0:0|0")]))
+    for kw in ({}, {"tile_bytes": 512}):
+        run_all(cuda_api, oracle, data, f"nr GT not first {kw}", tools=("nr", "pc", "gq", "ds"), **kw)
     for S in (1, 2, 100, 126, 127, 128, 129, 255, 256, 257, 700):
         names = b"\t".join(b"S%d" % i for i in range(S))
         lines = []

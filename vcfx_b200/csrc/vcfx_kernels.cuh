@@ -1892,7 +1892,8 @@ __device__ __forceinline__ bool tile_lines(const KParams &P, const WarpShared ws
                                 const uint32_t q = __funnelshift_r(__ldg(s4), __ldg(s4 + 1), 8u * (uint32_t)((uintptr_t)sp & 3));
                                 const uint32_t g3 = q & 0x00FFFFFFu, b3 = q >> 24;
                                 if (OP == OP_NR) {
-                                    const bool quick = (g3 == 0x00302F30u || g3 == 0x00307C30u) && (b3 == '\t' || (gi == 0 && b3 == ':'));
+                                    // (only when GT is the first key: with GT further back a three-byte column has no GT at all)
+                                    const bool quick = gi == 0 && (g3 == 0x00302F30u || g3 == 0x00307C30u) && (b3 == '\t' || b3 == ':');
                                     if (!quick && !nr_sample_homref(sp, file_mode, gi)) bad = true;
                                 } else if (OP == OP_GQ) {
                                     // GT = exactly the three bytes behind the tab: decided from the word; anything else by the scalar matcher
