@@ -746,11 +746,12 @@ def allele_counter(data: bytes, path: int = AC_MT_TEXT, fmt: int = AC_TEXT, limi
         # a full selection over all names so far (allele_counter.cpp:1139-1178); blank lines are skipped;
         # a data line before any "#CHROM" line is an error with nothing written; no header at all ends
         # with the header row and rc 1
-        names, cols, pos, n = [], [], 0, len(data)
+        names, cols, pos, n, saw_chrom = [], [], 0, len(data), False
         while pos < n and data[pos:pos + 1] in (b"#", b"\n"):
             nl = data.find(b"\n", pos)
             line = data[pos:(n if nl < 0 else nl)]
             if line.startswith(b"#CHROM"):
+                saw_chrom = True
                 f = line.split(b"\t")
                 add = f[9:] if len(f) > 9 else []
                 if add and add[-1] == b"":
@@ -764,7 +765,7 @@ def allele_counter(data: bytes, path: int = AC_MT_TEXT, fmt: int = AC_TEXT, limi
                 else:
                     cols += list(range(len(names)))
             pos = n if nl < 0 else nl + 1
-        if not cols and not names:
+        if not saw_chrom:
             has_data = any(l and not l.startswith(b"#") for l in data[pos:].split(b"\n"))
             return ToolResult(b"" if has_data else AC_TEXT_HEADER, 1, Totals())
     if path != AC_STREAM:
