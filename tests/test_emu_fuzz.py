@@ -14,12 +14,14 @@ sys.path.insert(0, str(Path(__file__).resolve().parent))
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 
 
-def one_case(api, O, rng):
+def one_case(api, O, rng, data=None):
     import vcfgen
     from vcfx_b200 import synth
     seed = rng.randrange(10 ** 9)
     kind = rng.random()
-    if kind < 0.6:
+    if data is not None:
+        d = data; kind = 0.7                  # (allele_counter runs as well)
+    elif kind < 0.6:
         d = vcfgen.make_vcf(seed, n_lines=rng.randrange(1, 120), n_samples=rng.randrange(1, 40), crlf=rng.random() < 0.2,
                             final_newline=rng.random() < 0.7, header=rng.choice(["normal", "normal", "late", "none", "double"]))
     elif kind < 0.8:
@@ -37,7 +39,8 @@ def one_case(api, O, rng):
     tag = f"seed {seed} mode {mode} {kw}"
     r = api.allele_freq_calc(d, mode, **kw); o = O.allele_freq(d, mode); assert (r.out, r.rc) == (o.out, o.rc), f"af {tag}"
     r = api.hwe_tester(d, mode, **kw); o = O.hwe(d, mode); assert r.out == o.out, f"hwe {tag}"
-    r = api.missing_detector(d, mode, **kw); o = O.missing(d, mode); assert r.out == o.out, f"md {tag}"
+    if not (mode == 0 and max(len(x) for x in d.split(b"\n")) > 60000):       # (the reference's file mode has a 64 KB line buffer)
+        r = api.missing_detector(d, mode, **kw); o = O.missing(d, mode); assert r.out == o.out, f"md {tag}"
     st = rng.random() < 0.5
     r = api.variant_counter(d, mode, st, **kw); o = O.variant_count(d, mode, st); assert (r.out, r.rc) == (o.out, o.rc), f"vc {tag}"
     if kind >= 0.6:
@@ -53,6 +56,43 @@ def one_case(api, O, rng):
     q = rng.choice(["0/1", "1/1", "0|1", "0/0", "1/2", "./.", "0/x", "2/1"]); strict = rng.random() < 0.3
     r = api.genotype_query(d, q, mode, strict, **kw); o, e = O.genotype_query(d, q, mode, strict); assert (r.out, r.err) == (o.out, e), f"gq {q} {strict} {tag}"
     r = api.dosage_calculator(d, mode, **kw); o = O.dosage(d, mode); assert (r.out, r.rc) == (o.out, o.rc), f"ds {tag}"
+
+
+def lattice_file(rng):
+    """Lines of three-byte genotypes (the four-byte lattice the fast paths work on) of random widths and phases, with samples that
+    leave the lattice at a random rate, GT first / with a second key / behind another key, CRLF, a final tab, odd lines between."""
+    base = [b"0|0", b"0|1", b"1|0", b"1|1", b"0/0", b"0/1", b"1/1"]
+    odd = [b"0", b".", b"./.", b".|.", b"0|1:3", b"10|1", b"2|1", b" 0|1", b"", b"0|1|1", b"1", b"0/", b"|1", b"1|2", b"00|1", b"0|.", b"./1", b"0|1:9:9", b"0\r"]
+    S = rng.choice([rng.randrange(1, 40), rng.randrange(100, 300), rng.randrange(120, 135), rng.randrange(250, 262), rng.randrange(500, 1500)])
+    fmt = rng.choice([b"GT", b"GT", b"GT", b"GT:DP", b"DP:GT"])
+    p_odd = rng.choice([0, 0, 0.002, 0.02, 0.2])
+    lines = []
+    for _ in range(rng.randrange(1, 12)):
+        if rng.random() < 0.05:
+            lines.append(rng.choice([b"", b"#c\tx", b"1\t2\tx"])); continue
+        gts = []
+        for _i in range(S):
+            g = rng.choice(base) if rng.random() >= p_odd else rng.choice(odd)
+            if fmt == b"GT:DP" and rng.random() < 0.9:
+                g += b":7"
+            if fmt == b"DP:GT":
+                g = b"7:" + g
+            gts.append(g)
+        ln = b"%d\t%d\t%s\tA\t%s\t.\tPASS\t%s\t%s\t" % (rng.randrange(1, 23), 10 ** rng.randrange(0, 9), b"r" * rng.randrange(0, 6),
+                                                     rng.choice([b"G", b"G", b"G,T", b""]), b"x" * rng.randrange(0, 40), fmt) + b"\t".join(gts)
+        lines.append(ln + (b"\t" if rng.random() < 0.05 else b""))
+    eol = b"\r\n" if rng.random() < 0.15 else b"\n"
+    hdr = b"##f" + eol + b"#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + b"\t".join(b"S%d" % i for i in range(S)) + eol
+    return hdr + eol.join(lines) + (eol if rng.random() < 0.7 else b"")
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_lattice_lines(oracle, seed):
+    import build_emu
+    api = build_emu.load_api()
+    rng = random.Random(2000 + seed)
+    for _ in range(12):
+        one_case(api, oracle, rng, lattice_file(rng))
 
 
 @pytest.mark.parametrize("seed", range(6))
