@@ -104,12 +104,16 @@ def test_random_inputs_and_geometries(oracle, seed):
         one_case(api, oracle, rng)
 
 
-if __name__ == "__main__":
-    import build_emu
+if __name__ == "__main__":            # python tests/test_emu_fuzz.py [--gpu] SEED SECONDS   (--gpu: the real library on cuda:0)
     from oracle import oracle as O
-    api = build_emu.load_api()
-    rng = random.Random(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
+    args = [a for a in sys.argv[1:] if a != "--gpu"]
+    if "--gpu" in sys.argv:
+        from vcfx_b200 import api
+    else:
+        import build_emu
+        api = build_emu.load_api()
+    rng = random.Random(int(args[0]) if args else 1)
     t0 = time.time(); n = 0
-    while time.time() - t0 < float(sys.argv[2] if len(sys.argv) > 2 else 60):
-        one_case(api, O, rng); n += 1
+    while time.time() - t0 < float(args[1] if len(args) > 1 else 60):
+        one_case(api, O, rng, lattice_file(rng) if n % 3 == 2 else None); n += 1
     print(f"{n} cases, no difference")
